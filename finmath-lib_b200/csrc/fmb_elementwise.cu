@@ -1,0 +1,243 @@
+// Element-wise RandomVariable arithmetic on device-resident vectors.
+// Semantics: J/montecarlo/RandomVariableFromDoubleArray.java:742-1504 (one streaming pass per op there; one kernel here).
+// HBM-bound: 8 B read per vector operand + 8 B written per element.  Grid-stride, two elements per thread per trip,
+// 16-byte vector accesses when every pointer is 16-byte aligned.  Compiled with -fmad=false: x + y*z is a rounded
+// multiply followed by a rounded add, as on the JVM.
+#include "fmb_common.cuh"
+
+namespace fmb {
+
+// Java Math.min / Math.max: NaN-propagating, -0.0 < +0.0 (CUDA fmin/fmax drop NaNs, so written out)
+__device__ __forceinline__ double jmin(double a, double b) {
+	if (a != a) return a;
+	if (a == 0.0 && b == 0.0 && signbit(b)) return b;
+	return (a <= b) ? a : b;
+}
+__device__ __forceinline__ double jmax(double a, double b) {
+	if (a != a) return a;
+	if (a == 0.0 && b == 0.0 && signbit(a)) return b;
+	return (a >= b) ? a : b;
+}
+
+template <int OP> __device__ __forceinline__ double unaryOp(double x, double a) {
+	switch (OP) {
+	case FMB_U_SQUARED: return x * x;
+	case FMB_U_SQRT: return sqrt(x);
+	case FMB_U_EXP: return exp(x);
+	case FMB_U_LOG: return log(x);
+	case FMB_U_SIN: return sin(x);
+	case FMB_U_COS: return cos(x);
+	case FMB_U_INVERT: return 1.0 / x;
+	case FMB_U_ABS: return fabs(x);
+	case FMB_U_ISNAN: return (x != x) ? 1.0 : 0.0;
+	case FMB_U_EXPM1: return expm1(x);
+	case FMB_U_ADD: return x + a;
+	case FMB_U_SUB: return x - a;
+	case FMB_U_BUS: return a - x;
+	case FMB_U_MULT: return x * a;
+	case FMB_U_DIV: return x / a;
+	case FMB_U_VID: return a / x;
+	case FMB_U_CAP: return jmin(x, a);
+	case FMB_U_FLOOR: return jmax(x, a);
+	case FMB_U_POW: return pow(x, a);
+	}
+	return x;
+}
+template <int OP> __device__ __forceinline__ double binaryOp(double x, double y) {
+	switch (OP) {
+	case FMB_B_ADD: return x + y;
+	case FMB_B_SUB: return x - y;
+	case FMB_B_MULT: return x * y;
+	case FMB_B_DIV: return x / y;
+	case FMB_B_CAP: return jmin(x, y);
+	case FMB_B_FLOOR: return jmax(x, y);
+	}
+	return x;
+}
+template <int OP> __device__ __forceinline__ double ternaryOp(double x, double y, double z, double a) {
+	switch (OP) {
+	case FMB_T_ADD_PRODUCT: return x + y * z;
+	case FMB_T_ADD_PRODUCT_D: return x + y * a;
+	case FMB_T_ADD_RATIO: return x + y / z;
+	case FMB_T_SUB_RATIO: return x - y / z;
+	case FMB_T_ACCRUE: return x * (1 + y * a);
+	case FMB_T_DISCOUNT: return x / (1.0 + y * a);
+	case FMB_T_CHOOSE: return x >= 0.0 ? y : z;
+	}
+	return x;
+}
+
+__device__ __forceinline__ double2 ld2(const double* p, uint64_t i, double s) {
+	if (p) return *reinterpret_cast<const double2*>(p + i);
+	return make_double2(s, s);
+}
+__device__ __forceinline__ double ld1(const double* p, uint64_t i, double s) { return p ? p[i] : s; }
+
+template <int OP> __global__ void __launch_bounds__(256) unaryKernel(const double* __restrict__ x, double a, double* __restrict__ out, uint64_t n, int vec) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (vec) {
+		const uint64_t n2 = n >> 1;
+		for (; i < n2; i += stride) {
+			const double2 v = *reinterpret_cast<const double2*>(x + 2 * i);
+			*reinterpret_cast<double2*>(out + 2 * i) = make_double2(unaryOp<OP>(v.x, a), unaryOp<OP>(v.y, a));
+		}
+		if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[n - 1] = unaryOp<OP>(x[n - 1], a);
+	} else {
+		for (; i < n; i += stride) out[i] = unaryOp<OP>(x[i], a);
+	}
+}
+template <int OP> __global__ void __launch_bounds__(256) binaryKernel(const double* __restrict__ x, double sx, const double* __restrict__ y, double sy,
+		double* __restrict__ out, uint64_t n, int vec) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (vec) {
+		const uint64_t n2 = n >> 1;
+		for (; i < n2; i += stride) {
+			const double2 a = ld2(x, 2 * i, sx), b = ld2(y, 2 * i, sy);
+			*reinterpret_cast<double2*>(out + 2 * i) = make_double2(binaryOp<OP>(a.x, b.x), binaryOp<OP>(a.y, b.y));
+		}
+		if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[n - 1] = binaryOp<OP>(ld1(x, n - 1, sx), ld1(y, n - 1, sy));
+	} else {
+		for (; i < n; i += stride) out[i] = binaryOp<OP>(ld1(x, i, sx), ld1(y, i, sy));
+	}
+}
+template <int OP> __global__ void __launch_bounds__(256) ternaryKernel(const double* __restrict__ x, double sx, const double* __restrict__ y, double sy,
+		const double* __restrict__ z, double sz, double a, double* __restrict__ out, uint64_t n, int vec) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+	if (vec) {
+		const uint64_t n2 = n >> 1;
+		for (; i < n2; i += stride) {
+			const double2 p = ld2(x, 2 * i, sx), q = ld2(y, 2 * i, sy), r = ld2(z, 2 * i, sz);
+			*reinterpret_cast<double2*>(out + 2 * i) = make_double2(ternaryOp<OP>(p.x, q.x, r.x, a), ternaryOp<OP>(p.y, q.y, r.y, a));
+		}
+		if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+			out[n - 1] = ternaryOp<OP>(ld1(x, n - 1, sx), ld1(y, n - 1, sy), ld1(z, n - 1, sz), a);
+	} else {
+		for (; i < n; i += stride) out[i] = ternaryOp<OP>(ld1(x, i, sx), ld1(y, i, sy), ld1(z, i, sz), a);
+	}
+}
+
+static inline int aligned16(const void* p) { return p == nullptr || (((uintptr_t)p) & 15) == 0; }
+
+// grid sized as a multiple of the SM count (8 resident CTAs of 256 threads per SM), capped by the work
+static inline int ewGrid(uint64_t n) {
+	uint64_t want = (n / 2 + 255) / 256;
+	uint64_t cap = (uint64_t)ctx().smCount * 8;
+	if (want > cap) want = cap;
+	if (want < 1) want = 1;
+	return (int)want;
+}
+
+#define LAUNCH_UNARY(OPC) case OPC: unaryKernel<OPC><<<grid, 256, 0, c.stream>>>(xp, a, dst, n, vec); break;
+#define LAUNCH_BINARY(OPC) case OPC: binaryKernel<OPC><<<grid, 256, 0, c.stream>>>(xp, sx, yp, sy, dst, n, vec); break;
+#define LAUNCH_TERNARY(OPC) case OPC: ternaryKernel<OPC><<<grid, 256, 0, c.stream>>>(xp, sx, yp, sy, zp, sz, a, dst, n, vec); break;
+
+static int finishLaunch(fmb_handle* out) {
+	countLaunch();
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) {
+		setError("element-wise kernel launch failed: %s", cudaGetErrorString(e));
+		fmb_rv_free(*out);
+		*out = 0;
+		return FMB_ECUDA;
+	}
+	return FMB_OK;
+}
+
+} // namespace fmb
+
+using namespace fmb;
+
+extern "C" {
+
+int fmb_rv_unary(int opcode, fmb_handle x, double a, fmb_handle* out) {
+	FMB_TRY(requireInit());
+	if (!out) return FMB_EINVAL;
+	if (opcode < 0 || opcode > FMB_U_POW) { setError("unknown unary op %d", opcode); return FMB_EINVAL; }
+	Context& c = ctx();
+	Vec* vx;
+	FMB_TRY(lookup(x, &vx));
+	const uint64_t n = vx->n;
+	const double* xp = vx->ptr;
+	// Math.pow(x, 0.5) / Math.pow(x, 2.0) must equal sqrt / x*x bit-for-bit (T/montecarlo/RandomVariableTest.java:101-127)
+	if (opcode == FMB_U_POW && a == 0.5) opcode = FMB_U_SQRT;
+	else if (opcode == FMB_U_POW && a == 2.0) opcode = FMB_U_SQUARED;
+	double* dst;
+	FMB_TRY(newVec(n, out, &dst));
+	if (n == 0) return FMB_OK;
+	const int vec = aligned16(xp) && aligned16(dst);
+	const int grid = ewGrid(n);
+	switch (opcode) {
+		LAUNCH_UNARY(FMB_U_SQUARED) LAUNCH_UNARY(FMB_U_SQRT) LAUNCH_UNARY(FMB_U_EXP) LAUNCH_UNARY(FMB_U_LOG) LAUNCH_UNARY(FMB_U_SIN)
+		LAUNCH_UNARY(FMB_U_COS) LAUNCH_UNARY(FMB_U_INVERT) LAUNCH_UNARY(FMB_U_ABS) LAUNCH_UNARY(FMB_U_ISNAN) LAUNCH_UNARY(FMB_U_EXPM1)
+		LAUNCH_UNARY(FMB_U_ADD) LAUNCH_UNARY(FMB_U_SUB) LAUNCH_UNARY(FMB_U_BUS) LAUNCH_UNARY(FMB_U_MULT) LAUNCH_UNARY(FMB_U_DIV)
+		LAUNCH_UNARY(FMB_U_VID) LAUNCH_UNARY(FMB_U_CAP) LAUNCH_UNARY(FMB_U_FLOOR) LAUNCH_UNARY(FMB_U_POW)
+	}
+	return finishLaunch(out);
+}
+
+// length of the result = length of the vector operands (all must agree); at least one operand must be a vector
+static int commonLength(const fmb_handle* hs, int cnt, uint64_t* n) {
+	*n = 0;
+	bool any = false;
+	for (int i = 0; i < cnt; i++) {
+		if (hs[i] == 0) continue;
+		Vec* v;
+		FMB_TRY(lookup(hs[i], &v));
+		if (any && v->n != *n) { setError("operand sizes differ (%llu vs %llu)", (unsigned long long)v->n, (unsigned long long)*n); return FMB_EINVAL; }
+		*n = v->n; any = true;
+	}
+	if (!any) { setError("all operands are scalars; deterministic arithmetic stays on the host"); return FMB_EINVAL; }
+	return FMB_OK;
+}
+
+int fmb_rv_binary(int opcode, fmb_handle x, double sx, fmb_handle y, double sy, fmb_handle* out) {
+	FMB_TRY(requireInit());
+	if (!out) return FMB_EINVAL;
+	if (opcode < 0 || opcode > FMB_B_FLOOR) { setError("unknown binary op %d", opcode); return FMB_EINVAL; }
+	Context& c = ctx();
+	uint64_t n;
+	const fmb_handle hs[2] = { x, y };
+	FMB_TRY(commonLength(hs, 2, &n));
+	const double *xp, *yp;
+	FMB_TRY(lookupPtr(x, 0, &xp));
+	FMB_TRY(lookupPtr(y, 0, &yp));
+	double* dst;
+	FMB_TRY(newVec(n, out, &dst));
+	if (n == 0) return FMB_OK;
+	const int vec = aligned16(xp) && aligned16(yp) && aligned16(dst);
+	const int grid = ewGrid(n);
+	switch (opcode) {
+		LAUNCH_BINARY(FMB_B_ADD) LAUNCH_BINARY(FMB_B_SUB) LAUNCH_BINARY(FMB_B_MULT) LAUNCH_BINARY(FMB_B_DIV) LAUNCH_BINARY(FMB_B_CAP)
+		LAUNCH_BINARY(FMB_B_FLOOR)
+	}
+	return finishLaunch(out);
+}
+
+int fmb_rv_ternary(int opcode, fmb_handle x, double sx, fmb_handle y, double sy, fmb_handle z, double sz, double a, fmb_handle* out) {
+	FMB_TRY(requireInit());
+	if (!out) return FMB_EINVAL;
+	if (opcode < 0 || opcode > FMB_T_CHOOSE) { setError("unknown ternary op %d", opcode); return FMB_EINVAL; }
+	Context& c = ctx();
+	uint64_t n;
+	const fmb_handle hs[3] = { x, y, z };
+	FMB_TRY(commonLength(hs, 3, &n));
+	const double *xp, *yp, *zp;
+	FMB_TRY(lookupPtr(x, 0, &xp));
+	FMB_TRY(lookupPtr(y, 0, &yp));
+	FMB_TRY(lookupPtr(z, 0, &zp));
+	double* dst;
+	FMB_TRY(newVec(n, out, &dst));
+	if (n == 0) return FMB_OK;
+	const int vec = aligned16(xp) && aligned16(yp) && aligned16(zp) && aligned16(dst);
+	const int grid = ewGrid(n);
+	switch (opcode) {
+		LAUNCH_TERNARY(FMB_T_ADD_PRODUCT) LAUNCH_TERNARY(FMB_T_ADD_PRODUCT_D) LAUNCH_TERNARY(FMB_T_ADD_RATIO) LAUNCH_TERNARY(FMB_T_SUB_RATIO)
+		LAUNCH_TERNARY(FMB_T_ACCRUE) LAUNCH_TERNARY(FMB_T_DISCOUNT) LAUNCH_TERNARY(FMB_T_CHOOSE)
+	}
+	return finishLaunch(out);
+}
+
+} // extern "C"

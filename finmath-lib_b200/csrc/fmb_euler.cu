@@ -1,0 +1,498 @@
+// Fused Euler / log-Euler path evolution: one kernel per simulation instead of dozens of array passes per time step.
+//
+// Replaces EulerSchemeFromProcessModel.doPrecalculateProcess (J/montecarlo/process/EulerSchemeFromProcessModel.java:170-326)
+// for the four models of the path.  One thread owns one path for the whole time loop (lanes = consecutive paths), so
+//   * every load of dW[t][f][path] and every store of X[t+1][component][path] is coalesced (getProcessValue(t, c) stays
+//     a contiguous device vector), and
+//   * the per-path arithmetic runs in exactly the reference's order (j ascending, k ascending, no FMA contraction in
+//     STRICT mode: this file is compiled with -fmad=false).
+// The kernels are FP64-pipe bound (double exp/log per component-step), not HBM bound; see DESIGN.md for the numbers.
+//
+// Algorithmic HBM bytes per path-step: 8*F read (increments) + 8*live(t) written (process values).
+#include "fmb_common.cuh"
+#include <cmath>
+#include <algorithm>
+
+namespace fmb {
+
+__device__ __forceinline__ double jminE(double a, double b) {
+	if (a != a) return a;
+	if (a == 0.0 && b == 0.0 && signbit(b)) return b;
+	return (a <= b) ? a : b;
+}
+__device__ __forceinline__ double jmaxE(double a, double b) {
+	if (a != a) return a;
+	if (a == 0.0 && b == 0.0 && signbit(a)) return b;
+	return (a >= b) ? a : b;
+}
+
+enum { SCHEME_EULER = 0, SCHEME_PC = 1, SCHEME_EULER_FUNCTIONAL = 2, SCHEME_PC_FUNCTIONAL = 3 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// Black-Scholes: BlackScholesModel.java:60-139.  Y += (r - sigma^2/2) dt + sigma dW ; X = exp(Y); functional schemes
+// re-apply log every step (:235-237 of the Euler scheme).  The drift does not depend on the state, so the corrector adds
+// ((mu - mu)/2)*dt = +0.0 and PREDICTOR_CORRECTOR reproduces EULER bit for bit.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) eulerBlackScholesKernel(int functional, int T, int F, uint64_t P, const double* __restrict__ dt,
+		const double* const* __restrict__ dW, double* const* __restrict__ X, double x0, double y0, double ylog0, double drift, double sigma) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < P; p += stride) {
+		double x = x0, y = y0;
+		for (int t = 0; t < T; t++) {
+			if (functional) y = (t == 0) ? ylog0 : log(x);
+			const double w = dW[(size_t)t * F][p];
+			y = y + drift * dt[t];
+			y = y + w * sigma;
+			x = exp(y);
+			X[t + 1][p] = x;
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Heston: HestonModel.java:336-420 (full truncation / reflection).  Components (asset, variance), two factors.
+// ---------------------------------------------------------------------------------------------------------------
+struct HestonParams { double x0, v0, ylog0, theta, kappa, xi, rho, rhoBar; int hestonScheme, scheme; };
+
+__device__ __forceinline__ void hestonDrift(const HestonParams& h, double v, double r, double& var, double& mu0, double& mu1) {
+	var = h.hestonScheme == 1 ? jmaxE(v, 0.0) : fabs(v);
+	mu0 = r - var / 2.0;
+	mu1 = (h.theta - var) * h.kappa;
+}
+
+__global__ void __launch_bounds__(256) eulerHestonKernel(HestonParams h, int T, uint64_t P, const double* __restrict__ dt,
+		const double* __restrict__ rate, const double* const* __restrict__ dW, double* const* __restrict__ X) {
+	const bool functional = (h.scheme == SCHEME_EULER_FUNCTIONAL || h.scheme == SCHEME_PC_FUNCTIONAL);
+	const bool pc = (h.scheme == SCHEME_PC || h.scheme == SCHEME_PC_FUNCTIONAL);
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < P; p += stride) {
+		double s = h.x0, v = h.v0, y0 = h.ylog0, y1 = h.v0;
+		for (int t = 0; t < T; t++) {
+			const double w0 = dW[2 * (size_t)t][p], w1 = dW[2 * (size_t)t + 1][p];
+			const double d = dt[t], r = rate[t];
+			double var, mu0, mu1;
+			hestonDrift(h, v, r, var, mu0, mu1);
+			const double vol = sqrt(var);
+			if (functional) { y0 = (t == 0) ? h.ylog0 : log(s); y1 = v; }
+			y0 = y0 + mu0 * d;
+			y0 = y0 + vol * w0;
+			y0 = y0 + w1 * 0.0;
+			const double volv = vol * h.xi;
+			y1 = y1 + mu1 * d;
+			y1 = y1 + (volv * h.rho) * w0;
+			y1 = y1 + (volv * h.rhoBar) * w1;
+			s = exp(y0);
+			v = y1;
+			if (pc) {
+				double varP, mu0P, mu1P;
+				hestonDrift(h, v, r, varP, mu0P, mu1P);
+				y0 = y0 + ((mu0P - mu0) / 2.0) * d;
+				y1 = y1 + ((mu1P - mu1) / 2.0) * d;
+				s = exp(y0);
+				v = y1;
+			}
+			X[2 * (size_t)(t + 1)][p] = s;
+			X[2 * (size_t)(t + 1) + 1][p] = v;
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Hull-White: HullWhiteModel.java:367-424.  Identity state-space transform; per-step deterministic coefficients.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) eulerHullWhiteKernel(int T, uint64_t P, const double* __restrict__ dt, const double* __restrict__ c0,
+		const double* __restrict__ c1, const double* __restrict__ fl, const double* const* __restrict__ dW, double* const* __restrict__ X) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < P; p += stride) {
+		double x0 = 0.0, x1 = 0.0;
+		for (int t = 0; t < T; t++) {
+			const double w0 = dW[2 * (size_t)t][p], w1 = dW[2 * (size_t)t + 1][p];
+			const double d = dt[t];
+			const double mu0 = x0 * c0[t], mu1 = x0 * c1[t];
+			double y0 = x0 + mu0 * d;
+			y0 = y0 + w0 * fl[4 * t + 0];
+			y0 = y0 + w1 * fl[4 * t + 1];
+			double y1 = x1 + mu1 * d;
+			y1 = y1 + w0 * fl[4 * t + 2];
+			y1 = y1 + w1 * fl[4 * t + 3];
+			x0 = y0; x1 = y1;
+			X[2 * (size_t)(t + 1)][p] = x0;
+			X[2 * (size_t)(t + 1) + 1][p] = x1;
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LIBOR market model: LIBORMarketModelFromCovarianceModel.java:1124-1223 inside the Euler scheme.
+//   drift (spot):   a_j = 1/(L_j*(d/d) + 1/d) [*L_j if lognormal];  S_k += a_j*fl_jk;  mu_j = sum_k S_k*fl_jk  (+ -0.5*var_j)
+//   drift (terminal): the mirrored suffix sum with a_j = 1/(L_j*(d/(-d)) + 1/(-d)), mu_j formed BEFORE S is updated.
+// State: the current forward rates of the thread's path live in shared memory as Lsh[j][thread] (conflict-free, j is a
+// run-time loop so the drift's prefix sum over the rate index runs sequentially per lane in the reference's order).
+// Y (non-functional schemes) and mu (predictor-corrector) live in a block-private, L2-resident global scratch.
+// ---------------------------------------------------------------------------------------------------------------
+struct LmmParams {
+	int scheme, measure, lognormal, hasCap;
+	double cap;
+	int T, N, F;
+	const double* dt;        // [T]
+	const double* fl;        // [T][N][F]
+	const double* hv;        // [T][N]  variance * (-0.5)
+	const int* firstLive;    // [T]
+	const double* ratio;     // [N]  periodLength / value   (value = +-periodLength)
+	const double* invv;      // [N]  1.0 / value
+	const double* x0;        // [N]  X_j(0) (host libm)
+	const double* y0;        // [N]  Y_j(0)
+	const double* ylog0;     // [N]  inverse transform of X_j(0) (host libm), used at the first step of functional schemes
+};
+
+template <int FT> __device__ __forceinline__ double lmmDriftTerm(const LmmParams& q, const double* __restrict__ flj, double* S, double a, bool spot) {
+	const int F = FT > 0 ? FT : q.F;
+	double mu;
+	if (spot) {
+#pragma unroll
+		for (int k = 0; k < (FT > 0 ? FT : 16); k++) if (k < F) S[k] = S[k] + a * flj[k];
+		mu = S[0] * flj[0] + 0.0;
+#pragma unroll
+		for (int k = 1; k < (FT > 0 ? FT : 16); k++) if (k < F) mu = mu + S[k] * flj[k];
+	} else {
+		mu = S[0] * flj[0] + 0.0;
+#pragma unroll
+		for (int k = 1; k < (FT > 0 ? FT : 16); k++) if (k < F) mu = mu + S[k] * flj[k];
+#pragma unroll
+		for (int k = 0; k < (FT > 0 ? FT : 16); k++) if (k < F) S[k] = S[k] + a * flj[k];
+	}
+	return mu;
+}
+
+template <int FT> __global__ void __launch_bounds__(128) eulerLmmKernel(LmmParams q, uint64_t P, const double* const* __restrict__ dW,
+		double* const* __restrict__ X, double* __restrict__ scratch) {
+	extern __shared__ double Lsh[];                       // [N][blockDim]
+	const int BD = blockDim.x, tid = threadIdx.x;
+	const int N = q.N, F = FT > 0 ? FT : q.F;
+	constexpr int FMAX = FT > 0 ? FT : 16;
+	const bool functional = (q.scheme == SCHEME_EULER_FUNCTIONAL || q.scheme == SCHEME_PC_FUNCTIONAL);
+	const bool pc = (q.scheme == SCHEME_PC || q.scheme == SCHEME_PC_FUNCTIONAL);
+	const bool spot = (q.measure == 0);
+	double* Ybuf = scratch + (size_t)blockIdx.x * 2 * N * BD;       // [N][BD]
+	double* Mbuf = Ybuf + (size_t)N * BD;                          // [N][BD]
+	const bool needY = pc || !functional;
+
+	const uint64_t tiles = (P + BD - 1) / BD;
+	for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+		const uint64_t p = tile * BD + tid;
+		if (p >= P) continue;                             // no block-wide barriers below: every thread only touches its own column
+		for (int j = 0; j < N; j++) {
+			Lsh[j * BD + tid] = q.x0[j];
+			if (needY) Ybuf[(size_t)j * BD + tid] = q.y0[j];
+		}
+		for (int t = 0; t < q.T; t++) {
+			const int first = q.firstLive[t];
+			if (first >= N) continue;
+			double w[FMAX], S[FMAX];
+#pragma unroll
+			for (int k = 0; k < FMAX; k++) { w[k] = (k < F) ? dW[(size_t)t * F + k][p] : 0.0; S[k] = 0.0; }
+			const double d = q.dt[t];
+			const double* flt = q.fl + (size_t)t * N * F;
+			const double* hvt = q.hv + (size_t)t * N;
+			double* const* Xn = X + (size_t)(t + 1) * N;
+			const int jBeg = spot ? first : N - 1, jEnd = spot ? N : first - 1, jStep = spot ? 1 : -1;
+			// predictor (or the whole step for the Euler schemes)
+			for (int j = jBeg; j != jEnd; j += jStep) {
+				const double Lj = Lsh[j * BD + tid];
+				double a = 1.0 / (Lj * q.ratio[j] + q.invv[j]);
+				if (q.lognormal) a = a * Lj;
+				const double* flj = flt + (size_t)j * F;
+				double mu = lmmDriftTerm<FT>(q, flj, S, a, spot);
+				if (q.lognormal) mu = mu + hvt[j];
+				double y;
+				if (functional) y = (t == 0) ? q.ylog0[j] : (q.lognormal ? log(Lj) : Lj);
+				else y = Ybuf[(size_t)j * BD + tid];
+				y = y + mu * d;
+#pragma unroll
+				for (int k = 0; k < FMAX; k++) if (k < F) y = y + w[k] * flj[k];
+				double Ln = q.lognormal ? exp(y) : y;
+				if (q.hasCap) Ln = jminE(Ln, q.cap);
+				Lsh[j * BD + tid] = Ln;
+				if (needY) Ybuf[(size_t)j * BD + tid] = y;
+				if (pc) Mbuf[(size_t)j * BD + tid] = mu; else Xn[j][p] = Ln;
+			}
+			if (pc) {
+				// corrector: drift re-evaluated on the predicted rates (:292-314)
+#pragma unroll
+				for (int k = 0; k < FMAX; k++) S[k] = 0.0;
+				for (int j = jBeg; j != jEnd; j += jStep) {
+					const double Lj = Lsh[j * BD + tid];
+					double a = 1.0 / (Lj * q.ratio[j] + q.invv[j]);
+					if (q.lognormal) a = a * Lj;
+					const double* flj = flt + (size_t)j * F;
+					double mu2 = lmmDriftTerm<FT>(q, flj, S, a, spot);
+					if (q.lognormal) mu2 = mu2 + hvt[j];
+					double y = Ybuf[(size_t)j * BD + tid];
+					y = y + ((mu2 - Mbuf[(size_t)j * BD + tid]) / 2.0) * d;
+					double Ln = q.lognormal ? exp(y) : y;
+					if (q.hasCap) Ln = jminE(Ln, q.cap);
+					Lsh[j * BD + tid] = Ln;
+					Ybuf[(size_t)j * BD + tid] = y;
+					Xn[j][p] = Ln;
+				}
+			}
+		}
+	}
+}
+
+// ---- host helpers -------------------------------------------------------------------------------------------------
+struct DeviceBlob {                // one pool allocation holding all parameter tables of a launch
+	void* base = nullptr;
+	size_t bytes = 0;
+	std::vector<unsigned char> host;
+	size_t add(const void* src, size_t n) {
+		size_t off = (host.size() + 15) & ~(size_t)15;
+		host.resize(off + n);
+		if (src) memcpy(host.data() + off, src, n);
+		return off;
+	}
+	int upload() {
+		bytes = std::max<size_t>(host.size(), 16);
+		FMB_TRY(poolAlloc(bytes, &base));
+		FMB_CUDA(cudaMemcpyAsync(base, host.data(), host.size(), cudaMemcpyHostToDevice, ctx().stream));
+		FMB_CUDA(cudaStreamSynchronize(ctx().stream));      // host vector may go away
+		return FMB_OK;
+	}
+	template <class Tp> const Tp* at(size_t off) const { return reinterpret_cast<const Tp*>((const unsigned char*)base + off); }
+	void release() { if (base) poolFree(base, bytes); base = nullptr; }
+};
+
+static int gatherIncrements(const fmb_handle* dW, int count, uint64_t paths, std::vector<const double*>& ptrs) {
+	ptrs.resize(count);
+	for (int i = 0; i < count; i++) {
+		if (dW[i] == 0) { setError("Brownian increment %d is not a device vector", i); return FMB_EINVAL; }
+		FMB_TRY(lookupPtr(dW[i], paths, &ptrs[i]));
+	}
+	return FMB_OK;
+}
+
+// process storage: one slab [(T+1)*N][paths]; rows that are never written (time 0 = deterministic, frozen components) get no view
+struct ProcessStore {
+	Slab* slab = nullptr;
+	std::vector<double*> rowPtr;    // device row pointers, nullptr when the entry is not materialised
+};
+
+static int launchCheck(const char* what) {
+	countLaunch();
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { setError("%s launch failed: %s", what, cudaGetErrorString(e)); return FMB_ECUDA; }
+	return FMB_OK;
+}
+
+} // namespace fmb
+
+using namespace fmb;
+
+extern "C" {
+
+int fmb_euler_black_scholes(int scheme, int T, int F, uint64_t paths, const double* dt, const fmb_handle* dW,
+                            double initial_value, double risk_free_rate, double volatility, fmb_handle* out) {
+	FMB_TRY(requireInit());
+	if (scheme < 0 || scheme > 3 || T <= 0 || F <= 0 || paths == 0 || !dt || !dW || !out) { setError("euler_black_scholes: bad argument"); return FMB_EINVAL; }
+	Context& c = ctx();
+	std::vector<const double*> inc;
+	FMB_TRY(gatherIncrements(dW, T * F, paths, inc));
+	Slab* slab;
+	FMB_TRY(newSlab((size_t)T * paths * sizeof(double), &slab));
+	std::vector<double*> rows(T + 1, nullptr);
+	for (int t = 1; t <= T; t++) rows[t] = (double*)slab->base + (size_t)(t - 1) * paths;
+	DeviceBlob blob;
+	const size_t oDt = blob.add(dt, T * sizeof(double));
+	const size_t oInc = blob.add(inc.data(), inc.size() * sizeof(double*));
+	const size_t oRows = blob.add(rows.data(), rows.size() * sizeof(double*));
+	int rc = blob.upload();
+	if (rc == FMB_OK) {
+		// BlackScholesModel.java:76-78: drift = r - sigma^2/2 (host scalars), initial state log(S0), X0 = exp(log S0)
+		const double drift = risk_free_rate - (volatility * volatility) / 2;
+		const double y0 = std::log(initial_value), x0 = std::exp(y0), ylog0 = std::log(x0);
+		const int functional = (scheme == SCHEME_EULER_FUNCTIONAL || scheme == SCHEME_PC_FUNCTIONAL) ? 1 : 0;
+		const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * 8, (paths + 255) / 256));
+		eulerBlackScholesKernel<<<grid, 256, 0, c.stream>>>(functional, T, F, paths, blob.at<double>(oDt), blob.at<const double*>(oInc),
+		                                                   (double* const*)blob.at<double*>(oRows), x0, y0, ylog0, drift, volatility);
+		rc = launchCheck("euler_black_scholes");
+	}
+	if (rc == FMB_OK) {
+		out[0] = 0;
+		for (int t = 1; t <= T; t++) out[t] = newView(slab, rows[t], paths);
+	} else { poolFree(slab->base, slab->bytes); delete slab; }
+	blob.release();
+	return rc;
+}
+
+int fmb_euler_heston(int scheme, int heston_scheme, int T, uint64_t paths, const double* dt, const fmb_handle* dW,
+                     double initial_value, const double* risk_free_rate, double volatility, double theta, double kappa, double xi, double rho,
+                     fmb_handle* out) {
+	FMB_TRY(requireInit());
+	if (scheme < 0 || scheme > 3 || heston_scheme < 0 || heston_scheme > 1 || T <= 0 || paths == 0 || !dt || !dW || !risk_free_rate || !out) {
+		setError("euler_heston: bad argument"); return FMB_EINVAL;
+	}
+	Context& c = ctx();
+	std::vector<const double*> inc;
+	FMB_TRY(gatherIncrements(dW, T * 2, paths, inc));
+	Slab* slab;
+	FMB_TRY(newSlab((size_t)T * 2 * paths * sizeof(double), &slab));
+	std::vector<double*> rows((size_t)(T + 1) * 2, nullptr);
+	for (int t = 1; t <= T; t++) for (int k = 0; k < 2; k++) rows[(size_t)t * 2 + k] = (double*)slab->base + ((size_t)(t - 1) * 2 + k) * paths;
+	DeviceBlob blob;
+	const size_t oDt = blob.add(dt, T * sizeof(double));
+	const size_t oRate = blob.add(risk_free_rate, T * sizeof(double));
+	const size_t oInc = blob.add(inc.data(), inc.size() * sizeof(double*));
+	const size_t oRows = blob.add(rows.data(), rows.size() * sizeof(double*));
+	int rc = blob.upload();
+	if (rc == FMB_OK) {
+		HestonParams h;
+		const double y0 = std::log(initial_value);
+		h.x0 = std::exp(y0); h.ylog0 = std::log(h.x0); h.v0 = volatility * volatility;
+		h.theta = theta; h.kappa = kappa; h.xi = xi; h.rho = rho;
+		h.rhoBar = std::sqrt(((rho * rho) - 1) * -1);      // HestonModel.java:182
+		h.hestonScheme = heston_scheme; h.scheme = scheme;
+		if (scheme == SCHEME_EULER || scheme == SCHEME_PC) h.ylog0 = y0;
+		const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * 8, (paths + 255) / 256));
+		eulerHestonKernel<<<grid, 256, 0, c.stream>>>(h, T, paths, blob.at<double>(oDt), blob.at<double>(oRate), blob.at<const double*>(oInc),
+		                                             (double* const*)blob.at<double*>(oRows));
+		rc = launchCheck("euler_heston");
+	}
+	if (rc == FMB_OK) {
+		out[0] = out[1] = 0;
+		for (size_t i = 2; i < rows.size(); i++) out[i] = newView(slab, rows[i], paths);
+	} else { poolFree(slab->base, slab->bytes); delete slab; }
+	blob.release();
+	return rc;
+}
+
+int fmb_euler_hull_white(int T, uint64_t paths, const double* dt, const fmb_handle* dW, const double* drift0, const double* drift1,
+                         const double* fl, fmb_handle* out) {
+	FMB_TRY(requireInit());
+	if (T <= 0 || paths == 0 || !dt || !dW || !drift0 || !drift1 || !fl || !out) { setError("euler_hull_white: bad argument"); return FMB_EINVAL; }
+	Context& c = ctx();
+	std::vector<const double*> inc;
+	FMB_TRY(gatherIncrements(dW, T * 2, paths, inc));
+	Slab* slab;
+	FMB_TRY(newSlab((size_t)T * 2 * paths * sizeof(double), &slab));
+	std::vector<double*> rows((size_t)(T + 1) * 2, nullptr);
+	for (int t = 1; t <= T; t++) for (int k = 0; k < 2; k++) rows[(size_t)t * 2 + k] = (double*)slab->base + ((size_t)(t - 1) * 2 + k) * paths;
+	DeviceBlob blob;
+	const size_t oDt = blob.add(dt, T * sizeof(double));
+	const size_t oC0 = blob.add(drift0, T * sizeof(double));
+	const size_t oC1 = blob.add(drift1, T * sizeof(double));
+	const size_t oFl = blob.add(fl, (size_t)T * 4 * sizeof(double));
+	const size_t oInc = blob.add(inc.data(), inc.size() * sizeof(double*));
+	const size_t oRows = blob.add(rows.data(), rows.size() * sizeof(double*));
+	int rc = blob.upload();
+	if (rc == FMB_OK) {
+		const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * 8, (paths + 255) / 256));
+		eulerHullWhiteKernel<<<grid, 256, 0, c.stream>>>(T, paths, blob.at<double>(oDt), blob.at<double>(oC0), blob.at<double>(oC1), blob.at<double>(oFl),
+		                                                blob.at<const double*>(oInc), (double* const*)blob.at<double*>(oRows));
+		rc = launchCheck("euler_hull_white");
+	}
+	if (rc == FMB_OK) {
+		out[0] = out[1] = 0;
+		for (size_t i = 2; i < rows.size(); i++) out[i] = newView(slab, rows[i], paths);
+	} else { poolFree(slab->base, slab->bytes); delete slab; }
+	blob.release();
+	return rc;
+}
+
+int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, int T, int N, int F, uint64_t paths,
+                  const double* dt, const fmb_handle* dW, const double* initial_state, const double* period_length,
+                  const double* factor_loading, const double* variance, const int32_t* first_live, fmb_handle* out) {
+	FMB_TRY(requireInit());
+	if (scheme < 0 || scheme > 3 || measure < 0 || measure > 1 || state_space < 0 || state_space > 1 || T <= 0 || N <= 0 || F <= 0 || F > 16 ||
+	    paths == 0 || !dt || !dW || !initial_state || !period_length || !factor_loading || !variance || !first_live || !out) {
+		setError("euler_lmm: bad argument"); return FMB_EINVAL;
+	}
+	Context& c = ctx();
+	std::vector<const double*> inc;
+	FMB_TRY(gatherIncrements(dW, T * F, paths, inc));
+
+	// which (t, j) are materialised: component j is written at time index t+1 iff j >= first_live[t]
+	size_t liveRows = 0;
+	for (int t = 0; t < T; t++) { if (first_live[t] < 0) { setError("euler_lmm: negative first_live"); return FMB_EINVAL; } liveRows += (size_t)std::max(0, N - first_live[t]); }
+	Slab* slab = nullptr;
+	if (liveRows) FMB_TRY(newSlab(liveRows * paths * sizeof(double), &slab));
+	std::vector<double*> rows((size_t)(T + 1) * N, nullptr);
+	{
+		size_t r = 0;
+		for (int t = 0; t < T; t++) for (int j = first_live[t]; j < N; j++) rows[(size_t)(t + 1) * N + j] = (double*)slab->base + (r++) * paths;
+	}
+	std::vector<double> hv((size_t)T * N), ratio(N), invv(N), x0(N), ylog0(N);
+	for (size_t i = 0; i < hv.size(); i++) hv[i] = variance[i] * -0.5;                      // :1187 addProduct(variance, -0.5)
+	for (int j = 0; j < N; j++) {
+		const double value = measure == 0 ? period_length[j] : -period_length[j];          // Scalar.of(+-periodLength).discount(...) :1149,:1167
+		ratio[j] = period_length[j] / value;
+		invv[j] = 1.0 / value;
+		double x = state_space == 1 ? std::exp(initial_state[j]) : initial_state[j];       // applyStateSpaceTransform :1199-1212 (host scalars at t=0)
+		if (!std::isinf(libor_cap)) x = (x != x) ? x : std::min(x, libor_cap);
+		x0[j] = x;
+		ylog0[j] = state_space == 1 ? std::log(x) : x;
+	}
+	DeviceBlob blob;
+	const size_t oDt = blob.add(dt, T * sizeof(double));
+	const size_t oFl = blob.add(factor_loading, (size_t)T * N * F * sizeof(double));
+	const size_t oHv = blob.add(hv.data(), hv.size() * sizeof(double));
+	const size_t oFirst = blob.add(first_live, T * sizeof(int32_t));
+	const size_t oRatio = blob.add(ratio.data(), N * sizeof(double));
+	const size_t oInvv = blob.add(invv.data(), N * sizeof(double));
+	const size_t oX0 = blob.add(x0.data(), N * sizeof(double));
+	const size_t oY0 = blob.add(initial_state, N * sizeof(double));
+	const size_t oYl = blob.add(ylog0.data(), N * sizeof(double));
+	const size_t oInc = blob.add(inc.data(), inc.size() * sizeof(double*));
+	const size_t oRows = blob.add(rows.data(), rows.size() * sizeof(double*));
+	int rc = blob.upload();
+	void* scratch = nullptr;
+	size_t scratchBytes = 0;
+	if (rc == FMB_OK && liveRows) {
+		LmmParams q;
+		q.scheme = scheme; q.measure = measure; q.lognormal = state_space; q.hasCap = std::isinf(libor_cap) ? 0 : 1; q.cap = libor_cap;
+		q.T = T; q.N = N; q.F = F;
+		q.dt = blob.at<double>(oDt); q.fl = blob.at<double>(oFl); q.hv = blob.at<double>(oHv); q.firstLive = blob.at<int>(oFirst);
+		q.ratio = blob.at<double>(oRatio); q.invv = blob.at<double>(oInvv); q.x0 = blob.at<double>(oX0); q.y0 = blob.at<double>(oY0);
+		q.ylog0 = blob.at<double>(oYl);
+		// block size: the shared-memory column store is 8*N bytes per thread
+		int BD = 128;
+		while (BD > 32 && (size_t)BD * N * sizeof(double) > 200 * 1024) BD >>= 1;
+		const size_t smem = (size_t)BD * N * sizeof(double);
+		if (smem > 220 * 1024) { setError("euler_lmm: %d components exceed the shared-memory state store", N); rc = FMB_EUNSUPPORTED; }
+		if (rc == FMB_OK) {
+			const int perSm = (int)std::max<size_t>(1, std::min<size_t>(16, (220 * 1024) / std::max<size_t>(smem, 1)));
+			const uint64_t tiles = (paths + BD - 1) / BD;
+			const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * perSm, tiles));
+			const bool needScratch = (scheme != SCHEME_EULER_FUNCTIONAL);
+			scratchBytes = needScratch ? (size_t)grid * 2 * N * BD * sizeof(double) : 16;
+			rc = poolAlloc(scratchBytes, &scratch);
+			if (rc == FMB_OK) {
+				auto launch = [&](auto kernel) {
+					cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+					kernel<<<grid, BD, smem, c.stream>>>(q, paths, blob.at<const double*>(oInc), (double* const*)blob.at<double*>(oRows), (double*)scratch);
+				};
+				switch (F) {
+				case 1: launch(eulerLmmKernel<1>); break;
+				case 2: launch(eulerLmmKernel<2>); break;
+				case 3: launch(eulerLmmKernel<3>); break;
+				case 4: launch(eulerLmmKernel<4>); break;
+				default: launch(eulerLmmKernel<0>); break;
+				}
+				rc = launchCheck("euler_lmm");
+			}
+		}
+	}
+	if (rc == FMB_OK) {
+		// handles: time 0 deterministic (0); a frozen component aliases the previous time index (one more reference)
+		for (int j = 0; j < N; j++) out[j] = 0;
+		for (int t = 1; t <= T; t++) for (int j = 0; j < N; j++) {
+			const size_t i = (size_t)t * N + j;
+			if (rows[i]) out[i] = newView(slab, rows[i], paths);
+			else { out[i] = out[i - N]; if (out[i]) fmb_rv_retain(out[i]); }
+		}
+	} else if (slab) { poolFree(slab->base, slab->bytes); delete slab; }
+	if (scratch) poolFree(scratch, scratchBytes);
+	blob.release();
+	return rc;
+}
+
+} // extern "C"

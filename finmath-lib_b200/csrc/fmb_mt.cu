@@ -1,0 +1,611 @@
+// Counter-addressable MT19937 (jump-ahead) + AS241 Brownian increment generation.
+//
+// Replaces BrownianMotionFromMersenneRandomNumbers.doGenerateBrownianMotion
+// (J/montecarlo/BrownianMotionFromMersenneRandomNumbers.java:141-191): ONE sequential MersenneTwister(seed) stream, draw
+// order path -> time -> factor, two 32-bit words per uniform.  Here the stream is cut into B contiguous sub-streams (one
+// per thread block); the 624-word state at the head of each sub-stream is obtained by jump-ahead:
+//
+//   x[k+J] = sum_i g_i x[k+i]   with  g(x) = x^J mod phi(x),  phi = characteristic polynomial (degree 19937),
+//
+// i.e. a jumped state is a GF(2) linear combination of shifted copies of the source sequence (no sequential Horner loop:
+// every output word is an independent XOR reduction, which is what the GPU wants).  phi is found once per process with
+// Berlekamp-Massey on the generator's own output (no tables to download), jump polynomials by square-and-multiply.
+// Sub-stream heads are filled by a doubling tree: level k applies g_{chunk*2^k} to heads [0,2^k) to get heads [2^k,2^(k+1)).
+//
+// HBM layout of the result: one slab double[T*F][paths] ("[t][f][path]"), each row a RandomVariable of the caller.
+#include "fmb_common.cuh"
+#include "fmb_icdf.cuh"
+#include <algorithm>
+#include <memory>
+
+namespace fmb {
+
+// ================================================================================================================
+// Host: MT19937 seeding (commons-math3 MersenneTwister(long) == init_by_array{hi, lo}) and raw sequence
+// ================================================================================================================
+static const int MT_N = 624, MT_M = 397;
+static const int DEG = 19937;
+
+static void mtSeedState(int64_t seed, uint32_t* st) {
+	const uint32_t key[2] = { (uint32_t)((uint64_t)seed >> 32), (uint32_t)((uint64_t)seed & 0xffffffffull) };
+	st[0] = 19650218u;
+	for (int i = 1; i < MT_N; i++) st[i] = 1812433253u * (st[i - 1] ^ (st[i - 1] >> 30)) + (uint32_t)i;
+	int i = 1, j = 0;
+	for (int k = MT_N; k > 0; k--) {
+		st[i] = (st[i] ^ ((st[i - 1] ^ (st[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+		if (++i >= MT_N) { st[0] = st[MT_N - 1]; i = 1; }
+		if (++j >= 2) j = 0;
+	}
+	for (int k = MT_N - 1; k > 0; k--) {
+		st[i] = (st[i] ^ ((st[i - 1] ^ (st[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+		if (++i >= MT_N) { st[0] = st[MT_N - 1]; i = 1; }
+	}
+	st[0] = 0x80000000u;
+}
+
+static inline uint32_t hostTwist(uint32_t a, uint32_t b) {
+	const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+	return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+// raw[k], k < n: raw[0..623] = state, raw[k] = raw[k-227] ^ twist(raw[k-624], raw[k-623])
+static void mtRawSequence(const uint32_t* st, size_t n, std::vector<uint32_t>& raw) {
+	raw.resize(n);
+	for (size_t k = 0; k < n && k < (size_t)MT_N; k++) raw[k] = st[k];
+	for (size_t k = MT_N; k < n; k++) raw[k] = raw[k - (MT_N - MT_M)] ^ hostTwist(raw[k - MT_N], raw[k - MT_N + 1]);
+}
+
+// ================================================================================================================
+// Host: GF(2)[x] arithmetic modulo the characteristic polynomial
+// ================================================================================================================
+static const int PW = (DEG + 64) / 64;            // words holding bits 0..DEG (312)
+struct CharPoly {
+	std::vector<int> exps;                        // exponents with coefficient 1, ascending, last == DEG
+	int gap = 0;                                  // DEG - second highest exponent
+	std::vector<uint64_t> bits;                   // dense form, PW words
+	bool ready = false;
+};
+static CharPoly g_phi;
+static std::mutex g_phiMu;
+
+// Berlekamp-Massey over GF(2) on one output bit-plane of the raw sequence.
+static bool computeCharPoly() {
+	uint32_t st[MT_N];
+	mtSeedState(4357, st);
+	const int NB = 2 * DEG + 64;
+	std::vector<uint32_t> raw;
+	mtRawSequence(st, (size_t)NB + 1, raw);
+	std::vector<uint8_t> s(NB);
+	for (int i = 0; i < NB; i++) s[i] = (uint8_t)(raw[i + 1] & 1u);   // skip raw[0] (its low 31 bits are not state)
+	// reversed sequence in words so that a window of it lines up with the connection polynomial
+	const int RW = (NB + 63) / 64 + 4;
+	std::vector<uint64_t> R(RW, 0);
+	for (int i = 0; i < NB; i++) if (s[i]) { const int j = NB - 1 - i; R[j >> 6] |= 1ull << (j & 63); }
+	const int CWORDS = (DEG + 2 + 63) / 64 + 1;
+	std::vector<uint64_t> Cc(CWORDS, 0), Bc(CWORDS, 0), Tc(CWORDS, 0);
+	Cc[0] = 1; Bc[0] = 1;
+	int L = 0, m = 1;
+	for (int n = 0; n < NB; n++) {
+		// d = sum_{i=0..L} C_i s[n-i];  s[n-i] = Rbit[NB-1-n+i]
+		const int off = NB - 1 - n;
+		const int w0 = off >> 6, sh = off & 63;
+		uint64_t acc = 0;
+		const int words = (L >> 6) + 1;
+		for (int w = 0; w < words; w++) {
+			uint64_t win = R[w0 + w] >> sh;
+			if (sh) win |= R[w0 + w + 1] << (64 - sh);
+			acc ^= win & Cc[w];
+		}
+		const int d = __builtin_parityll(acc);
+		if (!d) { m++; continue; }
+		const bool grow = (2 * L <= n);
+		if (grow) Tc = Cc;
+		// C ^= B << m
+		const int ws = m >> 6, bs = m & 63;
+		for (int w = CWORDS - 1; w >= ws; w--) {
+			uint64_t v = Bc[w - ws] << bs;
+			if (bs && w - ws - 1 >= 0) v |= Bc[w - ws - 1] >> (64 - bs);
+			Cc[w] ^= v;
+		}
+		if (grow) { L = n + 1 - L; Bc = Tc; m = 1; } else m++;
+	}
+	if (L != DEG) return false;
+	// characteristic polynomial: phi_{L-i} = C_i
+	g_phi.bits.assign(PW, 0);
+	g_phi.exps.clear();
+	for (int i = L; i >= 0; i--) if ((Cc[i >> 6] >> (i & 63)) & 1ull) {
+		const int e = L - i;
+		g_phi.exps.push_back(e);
+		g_phi.bits[e >> 6] |= 1ull << (e & 63);
+	}
+	if (g_phi.exps.back() != DEG || g_phi.exps.size() < 2) return false;
+	g_phi.gap = DEG - g_phi.exps[g_phi.exps.size() - 2];
+	// self-check: phi annihilates every bit-plane of the raw sequence (from index 1 on)
+	for (int n = 1; n < 40; n++) {
+		uint32_t acc = 0;
+		for (int e : g_phi.exps) acc ^= raw[n + e];
+		if (acc != 0) return false;
+	}
+	g_phi.ready = true;
+	return true;
+}
+
+static int ensureCharPoly() {
+	std::lock_guard<std::mutex> lk(g_phiMu);
+	if (g_phi.ready) return FMB_OK;
+	if (!computeCharPoly()) { setError("MT19937 characteristic polynomial derivation failed its self-check"); return FMB_ECUDA; }
+	return FMB_OK;
+}
+
+typedef std::vector<uint64_t> Poly;               // PW words, degree < DEG
+
+// v: 2*PW words holding a polynomial of degree < 2*DEG; reduce modulo phi in place; result in the low PW words
+static void reduceModPhi(std::vector<uint64_t>& v) {
+	const CharPoly& phi = g_phi;
+	const int top = (int)v.size() - 1;
+	if (phi.gap >= 64) {
+		const int wDeg = DEG >> 6, bDeg = DEG & 63;
+		for (int w = top; w >= wDeg; w--) {
+			uint64_t chunk = v[w];
+			if (w == wDeg) chunk &= ~((1ull << bDeg) - 1ull);
+			if (!chunk) continue;
+			v[w] ^= chunk;
+			const long base = (long)w * 64 - DEG;
+			for (size_t k = 0; k + 1 < phi.exps.size(); k++) {
+				const long Tpos = base + phi.exps[k];
+				if (Tpos >= 0) {
+					const long tw = Tpos >> 6; const int ts = (int)(Tpos & 63);
+					v[tw] ^= chunk << ts;
+					if (ts) v[tw + 1] ^= chunk >> (64 - ts);
+				} else {
+					v[0] ^= chunk >> (-Tpos);
+				}
+			}
+		}
+	} else {
+		for (int i = (int)v.size() * 64 - 1; i >= DEG; i--) {
+			if (!((v[i >> 6] >> (i & 63)) & 1ull)) continue;
+			for (int e : phi.exps) { const int t = i - DEG + e; v[t >> 6] ^= 1ull << (t & 63); }
+		}
+	}
+}
+
+static inline uint64_t spread32(uint32_t x) {     // interleave zeros: bit i -> bit 2i
+	uint64_t v = x;
+	v = (v | (v << 16)) & 0x0000ffff0000ffffull;
+	v = (v | (v << 8)) & 0x00ff00ff00ff00ffull;
+	v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0full;
+	v = (v | (v << 2)) & 0x3333333333333333ull;
+	v = (v | (v << 1)) & 0x5555555555555555ull;
+	return v;
+}
+
+static void polySquare(Poly& p) {
+	std::vector<uint64_t> v(2 * PW + 1, 0);
+	for (int w = 0; w < PW; w++) {
+		v[2 * w] = spread32((uint32_t)(p[w] & 0xffffffffull));
+		v[2 * w + 1] = spread32((uint32_t)(p[w] >> 32));
+	}
+	reduceModPhi(v);
+	for (int w = 0; w < PW; w++) p[w] = v[w];
+}
+
+static void polyMulX(Poly& p) {
+	uint64_t carry = 0;
+	for (int w = 0; w < PW; w++) { const uint64_t nc = p[w] >> 63; p[w] = (p[w] << 1) | carry; carry = nc; }
+	if ((p[DEG >> 6] >> (DEG & 63)) & 1ull) for (int w = 0; w < PW; w++) p[w] ^= g_phi.bits[w];
+}
+
+// x^J mod phi
+static Poly polyPowX(uint64_t J) {
+	Poly r(PW, 0);
+	r[0] = 1;
+	if (J == 0) return r;
+	int top = 63 - __builtin_clzll(J);
+	for (int b = top; b >= 0; b--) {
+		polySquare(r);
+		if ((J >> b) & 1ull) polyMulX(r);
+	}
+	return r;
+}
+
+static void polyToWords32(const Poly& p, uint32_t* out /* MT_N words */) {
+	for (int i = 0; i < MT_N; i++) {
+		const int w = i >> 1;
+		out[i] = (w < PW) ? (uint32_t)((i & 1) ? (p[w] >> 32) : (p[w] & 0xffffffffull)) : 0u;
+	}
+}
+
+// ================================================================================================================
+// Device kernels
+// ================================================================================================================
+static const int SEQ_LEN = DEG + MT_N;            // 20561 raw words cover every x[n+i], n < 624, i < 19937
+static const int JUMP_THREADS = 640;
+
+// grid (numOutputs, segments).  Block (o, s): expands source state src[o] to SEQ_LEN raw words in shared memory, then
+// thread n XORs seq[n+i] over the set coefficients i of poly within coefficient words [s*wordsPerSeg, (s+1)*wordsPerSeg).
+__global__ void __launch_bounds__(JUMP_THREADS) mtJumpApplyKernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+		const uint32_t* __restrict__ poly, int wordsPerSeg, int atomicCombine) {
+	extern __shared__ uint32_t seq[];
+	const int tid = threadIdx.x;
+	const uint32_t* s = src + (size_t)blockIdx.x * MT_N;
+	for (int i = tid; i < MT_N; i += JUMP_THREADS) seq[i] = s[i];
+	__syncthreads();
+	const int wBeg = blockIdx.y * wordsPerSeg;
+	const int wEnd = min(MT_N, wBeg + wordsPerSeg);
+	const int needEnd = min(SEQ_LEN, wEnd * 32 + MT_N);   // raw words needed by this segment
+	for (int j0 = MT_N; j0 < needEnd; j0 += (MT_N - MT_M)) {
+		const int j = j0 + tid;
+		if (tid < (MT_N - MT_M) && j < needEnd) seq[j] = seq[j - (MT_N - MT_M)] ^ mtTwist(seq[j - MT_N], seq[j - MT_N + 1]);
+		__syncthreads();
+	}
+	if (tid < MT_N) {
+		uint32_t acc = 0;
+		for (int w = wBeg; w < wEnd; w++) {
+			uint32_t bits = __ldg(poly + w);
+			const uint32_t* base = seq + tid + 32 * w;
+			while (bits) {
+				const int b = __ffs(bits) - 1;
+				bits &= bits - 1;
+				acc ^= base[b];
+			}
+		}
+		uint32_t* d = dst + (size_t)blockIdx.x * MT_N + tid;
+		if (atomicCombine) atomicXor(d, acc); else *d = acc;
+	}
+}
+
+// tempered outputs of one state (test hook fmb_mt_words): single block, sequential 227-wide refresh
+__global__ void __launch_bounds__(256) mtWordsKernel(const uint32_t* __restrict__ state, uint32_t* __restrict__ out, uint64_t n) {
+	__shared__ uint32_t ring[2048];
+	const int tid = threadIdx.x;
+	for (int i = tid; i < MT_N; i += 256) ring[i] = state[i];
+	__syncthreads();
+	uint64_t genEnd = MT_N;
+	for (uint64_t o0 = 0; o0 < n; o0 += 227) {
+		if (tid < 227) {
+			const uint64_t j = genEnd + tid;
+			ring[j & 2047] = ring[(j - 227) & 2047] ^ mtTwist(ring[(j - MT_N) & 2047], ring[(j - MT_N + 1) & 2047]);
+		}
+		__syncthreads();
+		if (tid < 227 && o0 + tid < n) out[o0 + tid] = mtTemper(ring[(genEnd + tid) & 2047]);
+		genEnd += 227;
+		__syncthreads();
+	}
+}
+
+__global__ void icdfKernel(const double* __restrict__ p, double* __restrict__ out, uint64_t n) {
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+		out[i] = inverseCumulativeNormal(p[i]);
+}
+
+__global__ void uniformsFromWordsKernel(const uint32_t* __restrict__ w, double* __restrict__ out, uint64_t n) {
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+		out[i] = mtUniform(w[2 * i], w[2 * i + 1]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Brownian increments.  Block b owns paths [b*ppb, min(P,(b+1)*ppb)) and the MT sub-stream that starts at its first word.
+// Per iteration the block (1) refreshes the raw ring 227 words at a time until 2*BM_THREADS words are available,
+// (2) each thread turns two tempered words into a uniform, applies AS241, scales by sqrt(dt) and drops the value
+// into a shared-memory tile laid out [c = t*F+f][path in tile], (3) full tiles are written to HBM as rows of
+// consecutive paths (coalesced, whole 32-byte sectors).
+// Algorithmic HBM bytes: 8 per increment (write only).
+// ---------------------------------------------------------------------------------------------------------------
+static const int BM_THREADS = 256;
+static const int RING = 2048;
+
+__global__ void __launch_bounds__(BM_THREADS) bmGenerateKernel(const uint32_t* __restrict__ states, double* __restrict__ out,
+		uint64_t P, uint32_t TF, uint32_t ppb, uint32_t tileN, uint32_t nPad, const double* __restrict__ sqrtDtPerColumn) {
+	extern __shared__ __align__(16) unsigned char smemRaw[];
+	uint32_t* ring = reinterpret_cast<uint32_t*>(smemRaw);
+	double* sq = reinterpret_cast<double*>(smemRaw + RING * sizeof(uint32_t));
+	double* tile = sq + ((TF + 1) & ~1u);
+	const int tid = threadIdx.x;
+	const int lane = tid & 31, warp = tid >> 5;
+
+	for (int i = tid; i < MT_N; i += BM_THREADS) ring[i] = states[(size_t)blockIdx.x * MT_N + i];
+	for (uint32_t i = tid; i < TF; i += BM_THREADS) sq[i] = sqrtDtPerColumn[i];
+	__syncthreads();
+
+	uint64_t genEnd = MT_N;         // raw words [.., genEnd) exist in the ring
+	uint64_t cpos = MT_N;           // raw index of the next unconsumed word
+	const uint64_t pBeg = (uint64_t)blockIdx.x * ppb;
+	const uint64_t pEnd = min(P, pBeg + (uint64_t)ppb);
+
+	for (uint64_t p0 = pBeg; p0 < pEnd; p0 += tileN) {
+		const uint32_t n = (uint32_t)min((uint64_t)tileN, pEnd - p0);
+		const uint32_t U = n * TF;
+		for (uint32_t u0 = 0; u0 < U; u0 += BM_THREADS) {
+			const uint32_t need = min((uint32_t)BM_THREADS, U - u0);
+			while (genEnd < cpos + 2ull * need) {
+				if (tid < 227) {
+					const uint64_t j = genEnd + tid;
+					ring[j & (RING - 1)] = ring[(j - 227) & (RING - 1)] ^ mtTwist(ring[(j - MT_N) & (RING - 1)], ring[(j - MT_N + 1) & (RING - 1)]);
+				}
+				genEnd += 227;
+				__syncthreads();
+			}
+			if ((uint32_t)tid < need) {
+				const uint64_t j = cpos + 2ull * tid;
+				const uint32_t w0 = mtTemper(ring[j & (RING - 1)]);
+				const uint32_t w1 = mtTemper(ring[(j + 1) & (RING - 1)]);
+				const double z = inverseCumulativeNormal(mtUniform(w0, w1));
+				const uint32_t ul = u0 + tid;
+				const uint32_t pl = ul / TF;
+				const uint32_t c = ul - pl * TF;
+				tile[c * nPad + pl] = z * sq[c];
+			}
+			cpos += 2ull * need;
+		}
+		__syncthreads();
+		if (n >= 32) {
+			for (uint32_t c = warp; c < TF; c += BM_THREADS / 32) {
+				double* dst = out + (size_t)c * P + p0;
+				const double* srcRow = tile + c * nPad;
+				for (uint32_t i = lane; i < n; i += 32) dst[i] = srcRow[i];
+			}
+		} else {
+			for (uint32_t idx = tid; idx < U; idx += BM_THREADS) {
+				const uint32_t c = idx / n, i = idx - c * n;
+				out[(size_t)c * P + p0 + i] = tile[c * nPad + i];
+			}
+		}
+		__syncthreads();
+	}
+}
+
+// ================================================================================================================
+// Host orchestration
+// ================================================================================================================
+struct DevicePolys {                               // g_{chunk * 2^k}, k = 0..levels-1, MT_N uint32 words each, on the device
+	uint32_t* dev = nullptr;
+	int levels = 0;
+	Poly last;                                     // host copy of the highest level (to extend by squaring)
+};
+static std::map<uint64_t, DevicePolys> g_polyCache;     // key: chunk (words)
+static std::mutex g_polyMu;
+static const int MAX_LEVELS = 24;
+
+static int getLevelPolys(uint64_t chunk, int levels, const uint32_t** dev) {
+	FMB_TRY(ensureCharPoly());
+	std::lock_guard<std::mutex> lk(g_polyMu);
+	if (levels > MAX_LEVELS) { setError("too many jump levels"); return FMB_EINVAL; }
+	DevicePolys& dp = g_polyCache[chunk];
+	if (!dp.dev) {
+		FMB_CUDA(cudaMalloc(&dp.dev, (size_t)MAX_LEVELS * MT_N * sizeof(uint32_t)));
+	}
+	while (dp.levels < levels) {
+		if (dp.levels == 0) dp.last = polyPowX(chunk); else polySquare(dp.last);
+		uint32_t w32[MT_N];
+		polyToWords32(dp.last, w32);
+		FMB_CUDA(cudaMemcpyAsync(dp.dev + (size_t)dp.levels * MT_N, w32, sizeof(w32), cudaMemcpyHostToDevice, ctx().stream));
+		FMB_CUDA(cudaStreamSynchronize(ctx().stream));
+		dp.levels++;
+	}
+	*dev = dp.dev;
+	return FMB_OK;
+}
+
+static int launchJump(const uint32_t* src, uint32_t* dst, const uint32_t* poly, int count) {
+	static bool attrSet = false;
+	const size_t smem = (size_t)SEQ_LEN * sizeof(uint32_t);
+	if (!attrSet) {
+		FMB_CUDA(cudaFuncSetAttribute(mtJumpApplyKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		attrSet = true;
+	}
+	// split the coefficient range over several blocks while the level has fewer outputs than the machine has SM slots
+	const int slots = 2 * ctx().smCount;
+	int segs = std::max(1, std::min(32, slots / count));
+	int wordsPerSeg = (MT_N + segs - 1) / segs;
+	segs = (MT_N + wordsPerSeg - 1) / wordsPerSeg;
+	if (segs > 1) FMB_CUDA(cudaMemsetAsync(dst, 0, (size_t)count * MT_N * sizeof(uint32_t), ctx().stream));
+	mtJumpApplyKernel<<<dim3(count, segs), JUMP_THREADS, smem, ctx().stream>>>(src, dst, poly, wordsPerSeg, segs > 1 ? 1 : 0);
+	countLaunch();
+	FMB_CUDA(cudaGetLastError());
+	return FMB_OK;
+}
+
+// heads[0] <- state of MersenneTwister(seed) jumped by firstWord; heads[b] <- heads[0] jumped by b*chunk, b < B
+static int buildStreamHeads(int64_t seed, uint64_t firstWord, uint64_t chunk, int B, uint32_t* heads /* device, B*MT_N */) {
+	Context& c = ctx();
+	uint32_t st[MT_N];
+	mtSeedState(seed, st);
+	if (firstWord == 0) {
+		FMB_CUDA(cudaMemcpyAsync(heads, st, sizeof(st), cudaMemcpyHostToDevice, c.stream));
+		FMB_CUDA(cudaStreamSynchronize(c.stream));
+	} else {
+		const uint32_t* poly;
+		FMB_TRY(getLevelPolys(firstWord, 1, &poly));
+		void* tmp;
+		FMB_TRY(poolAlloc(sizeof(st), &tmp));
+		FMB_CUDA(cudaMemcpyAsync(tmp, st, sizeof(st), cudaMemcpyHostToDevice, c.stream));
+		FMB_CUDA(cudaStreamSynchronize(c.stream));
+		int rc = launchJump((const uint32_t*)tmp, heads, poly, 1);
+		poolFree(tmp, sizeof(st));
+		FMB_TRY(rc);
+	}
+	if (B > 1) {
+		int levels = 0;
+		while ((1 << levels) < B) levels++;
+		const uint32_t* polys;
+		FMB_TRY(getLevelPolys(chunk, levels, &polys));
+		for (int k = 0; k < levels; k++) {
+			const int have = 1 << k;
+			const int cnt = std::min(have, B - have);
+			FMB_TRY(launchJump(heads, heads + (size_t)have * MT_N, polys + (size_t)k * MT_N, cnt));
+		}
+	}
+	return FMB_OK;
+}
+
+} // namespace fmb
+
+using namespace fmb;
+
+extern "C" {
+
+// Host-only self-test hook (no GPU needed): the jumped state computed with the same polynomial code the device path uses,
+// applied on the CPU.  tests/ check it against the sequentially skipped oracle stream.
+int fmb_test_host_jump(int64_t seed, uint64_t J, uint32_t* state_out /* 624 */, int* phi_weight, int* phi_gap) {
+	FMB_TRY(ensureCharPoly());
+	if (phi_weight) *phi_weight = (int)g_phi.exps.size();
+	if (phi_gap) *phi_gap = g_phi.gap;
+	uint32_t st[MT_N];
+	mtSeedState(seed, st);
+	std::vector<uint32_t> raw;
+	mtRawSequence(st, SEQ_LEN, raw);
+	Poly g = polyPowX(J);
+	uint32_t w32[MT_N];
+	polyToWords32(g, w32);
+	for (int n = 0; n < MT_N; n++) {
+		uint32_t acc = 0;
+		for (int w = 0; w < MT_N; w++) {
+			uint32_t bits = w32[w];
+			while (bits) { const int b = __builtin_ctz(bits); bits &= bits - 1; acc ^= raw[n + 32 * w + b]; }
+		}
+		state_out[n] = acc;
+	}
+	return FMB_OK;
+}
+
+int fmb_mt_words(int64_t seed, uint64_t word_offset, uint64_t n, uint32_t* host_out) {
+	FMB_TRY(requireInit());
+	if (n == 0) return FMB_OK;
+	if (!host_out) { setError("null output"); return FMB_EINVAL; }
+	void* head; void* dout;
+	FMB_TRY(poolAlloc(MT_N * sizeof(uint32_t), &head));
+	int rc = poolAlloc(n * sizeof(uint32_t), &dout);
+	if (rc) { poolFree(head, MT_N * sizeof(uint32_t)); return rc; }
+	rc = buildStreamHeads(seed, word_offset, 0, 1, (uint32_t*)head);
+	if (rc == FMB_OK) {
+		mtWordsKernel<<<1, 256, 0, ctx().stream>>>((const uint32_t*)head, (uint32_t*)dout, n);
+		countLaunch();
+		cudaError_t e = cudaMemcpyAsync(host_out, dout, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx().stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().stream);
+		if (e != cudaSuccess) { setError("mt_words: %s", cudaGetErrorString(e)); rc = FMB_ECUDA; }
+	}
+	poolFree(head, MT_N * sizeof(uint32_t));
+	poolFree(dout, n * sizeof(uint32_t));
+	return rc;
+}
+
+int fmb_mt_uniforms(int64_t seed, uint64_t uniform_offset, uint64_t n, double* host_out) {
+	FMB_TRY(requireInit());
+	if (n == 0) return FMB_OK;
+	if (!host_out) { setError("null output"); return FMB_EINVAL; }
+	void* head; void* dw; void* du;
+	FMB_TRY(poolAlloc(MT_N * sizeof(uint32_t), &head));
+	FMB_TRY(poolAlloc(2 * n * sizeof(uint32_t), &dw));
+	FMB_TRY(poolAlloc(n * sizeof(double), &du));
+	int rc = buildStreamHeads(seed, 2 * uniform_offset, 0, 1, (uint32_t*)head);
+	if (rc == FMB_OK) {
+		mtWordsKernel<<<1, 256, 0, ctx().stream>>>((const uint32_t*)head, (uint32_t*)dw, 2 * n);
+		uniformsFromWordsKernel<<<gridFor(n, 256), 256, 0, ctx().stream>>>((const uint32_t*)dw, (double*)du, n);
+		countLaunch(2);
+		cudaError_t e = cudaMemcpyAsync(host_out, du, n * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().stream);
+		if (e != cudaSuccess) { setError("mt_uniforms: %s", cudaGetErrorString(e)); rc = FMB_ECUDA; }
+	}
+	poolFree(head, MT_N * sizeof(uint32_t));
+	poolFree(dw, 2 * n * sizeof(uint32_t));
+	poolFree(du, n * sizeof(double));
+	return rc;
+}
+
+int fmb_icdf(const double* host_p, uint64_t n, double* host_out) {
+	FMB_TRY(requireInit());
+	if (n == 0) return FMB_OK;
+	void* dp; void* dq;
+	FMB_TRY(poolAlloc(n * sizeof(double), &dp));
+	FMB_TRY(poolAlloc(n * sizeof(double), &dq));
+	cudaError_t e = cudaMemcpyAsync(dp, host_p, n * sizeof(double), cudaMemcpyHostToDevice, ctx().stream);
+	icdfKernel<<<gridFor(n, 256), 256, 0, ctx().stream>>>((const double*)dp, (double*)dq, n);
+	countLaunch();
+	if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, dq, n * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().stream);
+	poolFree(dp, n * sizeof(double));
+	poolFree(dq, n * sizeof(double));
+	if (e != cudaSuccess) { setError("icdf: %s", cudaGetErrorString(e)); return FMB_ECUDA; }
+	return FMB_OK;
+}
+
+int fmb_bm_generate(int32_t seed, int T, int F, uint64_t paths, uint64_t path_offset, const double* sqrt_dt, fmb_handle* out) {
+	FMB_TRY(requireInit());
+	if (T <= 0 || F <= 0 || paths == 0 || !sqrt_dt || !out) { setError("bm_generate: bad argument"); return FMB_EINVAL; }
+	Context& c = ctx();
+	const uint64_t TF = (uint64_t)T * F;
+	if (TF > 24000) { setError("bm_generate: T*F = %llu exceeds the shared-memory tile limit (24000)", (unsigned long long)TF); return FMB_EUNSUPPORTED; }
+
+	// shared-memory tile: [TF][nPad] doubles + ring + per-column sqrt(dt)
+	const size_t fixed = RING * sizeof(uint32_t) + ((TF + 1) & ~1ull) * sizeof(double);
+	// two blocks per SM when a >= 4-path tile fits in half of the 227 KB, else one block with the whole of it
+	uint32_t tileN = 0;
+	const size_t budgets[2] = { 112 * 1024, 224 * 1024 };
+	for (int attempt = 0; attempt < 2; attempt++) {
+		const size_t avail = budgets[attempt] > fixed ? budgets[attempt] - fixed : 0;
+		const uint64_t maxPad = avail / (TF * sizeof(double));
+		if (maxPad >= 5) { tileN = (uint32_t)std::min<uint64_t>(((maxPad - 1) / 4) * 4, 256); break; }
+		if (attempt == 1) tileN = maxPad >= 2 ? (uint32_t)(maxPad - 1) : (uint32_t)maxPad;
+	}
+	if (tileN == 0) { setError("bm_generate: tile does not fit shared memory"); return FMB_EUNSUPPORTED; }
+	const uint32_t nPad = tileN >= 2 ? (tileN | 1u) : tileN;      // odd row stride: conflict-free 8-byte column writes
+	const size_t smem = fixed + (size_t)TF * nPad * sizeof(double);
+
+	// sub-streams: enough blocks to fill the machine, but at least ~32k uniforms each so that jump-ahead stays a small fraction
+	const int blocksPerSm = smem <= 113 * 1024 ? 2 : 1;
+	uint64_t Bmax = (uint64_t)c.smCount * blocksPerSm;            // one wave of equal sub-streams
+	const uint64_t totalUniforms = paths * TF;
+	Bmax = std::max<uint64_t>(1, std::min<uint64_t>(Bmax, totalUniforms / 32768 + 1));
+	uint64_t ppb = (paths + Bmax - 1) / Bmax;
+	ppb = ((ppb + tileN - 1) / tileN) * tileN;
+	const int B = (int)((paths + ppb - 1) / ppb);
+	if (ppb > 0xffffffffull) { setError("bm_generate: too many paths per block"); return FMB_EUNSUPPORTED; }
+	const uint64_t chunk = ppb * 2ull * TF;
+
+	void* heads = nullptr;
+	FMB_TRY(poolAlloc((size_t)B * MT_N * sizeof(uint32_t), &heads));
+	int rc = buildStreamHeads((int64_t)seed, path_offset * 2ull * TF, chunk, B, (uint32_t*)heads);
+
+	Slab* slab = nullptr;
+	void* dsq = nullptr;
+	if (rc == FMB_OK) rc = poolAlloc(TF * sizeof(double), &dsq);
+	if (rc == FMB_OK) {
+		std::lock_guard<std::mutex> lk(c.scratchMu);
+		rc = ensureScratch(TF * sizeof(double), 0);
+		if (rc == FMB_OK) {
+			double* h = (double*)c.pinned;
+			for (int t = 0; t < T; t++) for (int f = 0; f < F; f++) h[(size_t)t * F + f] = sqrt_dt[t];
+			cudaError_t e = cudaMemcpyAsync(dsq, h, TF * sizeof(double), cudaMemcpyHostToDevice, c.stream);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+			if (e != cudaSuccess) { setError("bm_generate: %s", cudaGetErrorString(e)); rc = FMB_ECUDA; }
+		}
+	}
+	if (rc == FMB_OK) rc = newSlab(TF * paths * sizeof(double), &slab);
+	if (rc == FMB_OK) {
+		static size_t attrSmem = 0;
+		if (smem > attrSmem) {
+			cudaError_t e = cudaFuncSetAttribute(bmGenerateKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if (e != cudaSuccess) { setError("bm_generate: %s", cudaGetErrorString(e)); rc = FMB_ECUDA; }
+			attrSmem = smem;
+		}
+	}
+	if (rc == FMB_OK) {
+		bmGenerateKernel<<<B, BM_THREADS, smem, c.stream>>>((const uint32_t*)heads, (double*)slab->base, paths, (uint32_t)TF, (uint32_t)ppb,
+		                                                    tileN, nPad, (const double*)dsq);
+		countLaunch();
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) { setError("bm_generate launch: %s", cudaGetErrorString(e)); rc = FMB_ECUDA; }
+	}
+	if (rc == FMB_OK) {
+		for (uint64_t i = 0; i < TF; i++) out[i] = newView(slab, (double*)slab->base + i * paths, paths);
+	} else if (slab) {
+		poolFree(slab->base, slab->bytes);
+		delete slab;
+	}
+	if (dsq) poolFree(dsq, TF * sizeof(double));
+	poolFree(heads, (size_t)B * MT_N * sizeof(uint32_t));
+	return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,326 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_core.h header).  Brownian driver, Euler scheme and the model
+// callbacks, restated op-by-op on the orc::RV semantics so that rounding order follows the reference's dispatch.
+// J/ = /root/reference/src/main/java/net/finmath/
+#pragma once
+#include "orc_core.h"
+#include <map>
+
+namespace orc {
+
+// J/montecarlo/BrownianMotionFromMersenneRandomNumbers.java:141-191 — draw order path, time, factor; value
+// [t][f][p] = ICDF(u) * sqrt(dt_t); wrapped as RandomVariableFromDoubleArray with filtration time t_{i+1}.
+struct BrownianMotion {
+	TimeDiscretization td;
+	int F, paths, seed;
+	std::vector<std::vector<P>> inc;   // [t][f]
+	// pathOffset/pathCount select a shard of the single sequential stream (paths [pathOffset, pathOffset+pathCount))
+	BrownianMotion(const TimeDiscretization& td_, int F_, int paths_, int seed_, long pathOffset = 0)
+		: td(td_), F(F_), paths(paths_), seed(seed_) {
+		const int T = td.getNumberOfTimeSteps();
+		MersenneTwister mt((int64_t)seed);
+		mt.skipWords((uint64_t)pathOffset * 2ull * (uint64_t)T * (uint64_t)F);
+		std::vector<std::vector<std::vector<double>>> a(T, std::vector<std::vector<double>>(F, std::vector<double>(paths)));
+		std::vector<double> sq(T);
+		for (int t = 0; t < T; t++) sq[t] = std::sqrt(td.getTimeStep(t));
+		for (int p = 0; p < paths; p++)
+			for (int t = 0; t < T; t++)
+				for (int f = 0; f < F; f++) {
+					const double u = mt.nextDouble();
+					a[t][f][p] = inverseCumulativeNormal(u) * sq[t];
+				}
+		inc.resize(T);
+		for (int t = 0; t < T; t++)
+			for (int f = 0; f < F; f++) inc[t].push_back(rvvec(td.getTime(t + 1), std::move(a[t][f])));
+	}
+	P getBrownianIncrement(int t, int f) const { return inc[t][f]; }
+	const std::vector<P>& getIncrement(int t) const { return inc[t]; }
+	P getRandomVariableForConstant(double v) const { return scalar(v); }   // default factory -> Scalar
+};
+
+struct Process;
+
+// J/montecarlo/model/ProcessModel.java:47-174
+struct ProcessModel {
+	virtual ~ProcessModel() {}
+	virtual int getNumberOfComponents() const = 0;
+	virtual std::vector<P> getInitialState(const Process&) = 0;
+	virtual std::vector<P> getDrift(const Process&, int timeIndex, const std::vector<P>& x) = 0;   // null entries = frozen
+	virtual std::vector<P> getFactorLoading(const Process&, int timeIndex, int component, const std::vector<P>& x) = 0;
+	virtual P applyStateSpaceTransform(int timeIndex, int component, const P& y) = 0;
+	virtual bool hasInverse() const = 0;
+	virtual P applyStateSpaceTransformInverse(int timeIndex, int component, const P& x) = 0;
+};
+
+enum Scheme { EULER = 0, PREDICTOR_CORRECTOR = 1, EULER_FUNCTIONAL = 2, PREDICTOR_CORRECTOR_FUNCTIONAL = 3 };
+
+// J/montecarlo/process/EulerSchemeFromProcessModel.java:170-326
+struct Process {
+	ProcessModel* model;
+	const BrownianMotion* bm;
+	int scheme;
+	std::vector<std::vector<P>> X;     // [timeIndex][component]
+	P weights;
+	Process(ProcessModel* m, const BrownianMotion* b, int scheme_ = -1) : model(m), bm(b) {
+		scheme = scheme_ >= 0 ? scheme_ : (m->hasInverse() ? EULER_FUNCTIONAL : EULER);   // :108-123
+	}
+	const TimeDiscretization& getTimeDiscretization() const { return bm->td; }
+	double getTime(int i) const { return bm->td.getTime(i); }
+	int getTimeIndex(double t) const { return bm->td.getTimeIndex(t); }
+	int getNumberOfPaths() const { return bm->paths; }
+	P getMonteCarloWeights() { precalc(); return weights; }
+	P getProcessValue(int timeIndex, int component) { precalc(); return X.at(timeIndex).at(component); }
+
+	void precalc() {
+		if (!X.empty()) return;
+		const int T = bm->td.getNumberOfTimeSteps();
+		const int N = model->getNumberOfComponents();
+		X.assign(T + 1, std::vector<P>(N));
+		weights = bm->getRandomVariableForConstant(1.0 / bm->paths);                       // :184
+		std::vector<P> cur = model->getInitialState(*this);
+		for (int c = 0; c < N; c++) X[0][c] = model->applyStateSpaceTransform(0, c, cur[c]);
+		for (int ti = 1; ti <= T; ti++) {
+			const double deltaT = getTime(ti) - getTime(ti - 1);
+			std::vector<P> drift = model->getDrift(*this, ti - 1, X[ti - 1]);
+			const std::vector<P>& dW = bm->getIncrement(ti - 1);
+			for (int c = 0; c < N; c++) {
+				if (!drift[c]) { X[ti][c] = X[ti - 1][c]; continue; }                         // :236-240, :285
+				if (scheme == EULER_FUNCTIONAL || scheme == PREDICTOR_CORRECTOR_FUNCTIONAL)
+					cur[c] = model->applyStateSpaceTransformInverse(ti - 1, c, X[ti - 1][c]);
+				std::vector<P> fl = model->getFactorLoading(*this, ti - 1, c, X[ti - 1]);
+				if (fl.empty()) { X[ti][c] = X[ti - 1][c]; continue; }
+				cur[c] = addProduct(cur[c], drift[c], deltaT);
+				cur[c] = addSumProduct(cur[c], fl, dW);
+				X[ti][c] = model->applyStateSpaceTransform(ti, c, cur[c]);
+			}
+			if (scheme == PREDICTOR_CORRECTOR || scheme == PREDICTOR_CORRECTOR_FUNCTIONAL) {   // :292-314
+				std::vector<P> driftP = model->getDrift(*this, ti - 1, X[ti]);
+				for (int c = 0; c < N; c++) {
+					if (!driftP[c] || !drift[c]) continue;
+					P adj = mult(div(sub(driftP[c], drift[c]), 2.0), deltaT);
+					cur[c] = add(cur[c], adj);
+					X[ti][c] = model->applyStateSpaceTransform(ti, c, cur[c]);
+				}
+			}
+		}
+	}
+};
+
+// J/montecarlo/assetderivativevaluation/models/BlackScholesModel.java:60-139
+struct BlackScholesModel : ProcessModel {
+	P initialValue, riskFreeRate, volatility;
+	std::vector<P> initialState, drift, fl;
+	BlackScholesModel(double s0, double r, double sigma) {
+		initialValue = scalar(s0); riskFreeRate = scalar(r); volatility = scalar(sigma);
+		initialState = { log(initialValue) };
+		drift = { sub(riskFreeRate, div(squared(volatility), 2)) };
+		fl = { volatility };
+	}
+	int getNumberOfComponents() const override { return 1; }
+	std::vector<P> getInitialState(const Process&) override { return initialState; }
+	std::vector<P> getDrift(const Process&, int, const std::vector<P>&) override { return drift; }
+	std::vector<P> getFactorLoading(const Process&, int, int, const std::vector<P>&) override { return fl; }
+	P applyStateSpaceTransform(int, int, const P& y) override { return exp(y); }
+	bool hasInverse() const override { return true; }
+	P applyStateSpaceTransformInverse(int, int, const P& x) override { return log(x); }
+	P getNumeraire(double time) const { return exp(mult(riskFreeRate, time)); }
+};
+
+// J/montecarlo/assetderivativevaluation/models/HestonModel.java:325-430 (constant-rate constructor path)
+struct HestonModel : ProcessModel {
+	enum HScheme { REFLECTION = 0, FULL_TRUNCATION = 1 };
+	P initialValue, riskFreeRate, volatility, discountRate, theta, kappa, xi, rho, rhoBar, ZERO;
+	int hscheme;
+	HestonModel(double s0, double r, double sigma, double discRate, double theta_, double kappa_, double xi_, double rho_, int hs) {
+		initialValue = scalar(s0); riskFreeRate = scalar(r); volatility = scalar(sigma); discountRate = scalar(discRate);
+		theta = scalar(theta_); kappa = scalar(kappa_); xi = scalar(xi_); rho = scalar(rho_);
+		rhoBar = sqrt(mult(sub(squared(rho), 1), -1));                                    // :182
+		ZERO = scalar(0.0);
+		hscheme = hs;
+	}
+	int getNumberOfComponents() const override { return 2; }
+	std::vector<P> getInitialState(const Process&) override { return { log(initialValue), squared(volatility) }; }
+	P truncated(const P& v) const { return hscheme == FULL_TRUNCATION ? floor(v, 0.0) : abs(v); }
+	std::vector<P> getDrift(const Process&, int, const std::vector<P>& x) override {
+		P var = truncated(x[1]);
+		return { sub(riskFreeRate, div(var, 2.0)), mult(sub(theta, var), kappa) };          // :361-362
+	}
+	std::vector<P> getFactorLoading(const Process&, int, int c, const std::vector<P>& x) override {
+		P vol = sqrt(truncated(x[1]));
+		if (c == 0) return { vol, ZERO };
+		P v = mult(vol, xi);
+		return { mult(v, rho), mult(v, rhoBar) };
+	}
+	P applyStateSpaceTransform(int, int c, const P& y) override { return c == 0 ? exp(y) : y; }
+	bool hasInverse() const override { return true; }
+	P applyStateSpaceTransformInverse(int, int c, const P& x) override { return c == 0 ? log(x) : x; }
+	P getNumeraire(double time) const { return exp(mult(discountRate, time)); }
+};
+
+// J/montecarlo/interestrate/models/LIBORMarketModelFromCovarianceModel.java.  The covariance model is the
+// deterministic table pair (sigma[t][j], F[j][k]) of LIBORCovarianceModelFromVolatilityAndCorrelation (:47-93):
+// factor loading = sigma.mult(F[j][k]); variance = sigma.mult(sigma).mult(corr_jj) with corr_jj == 1.0.
+struct LIBORMarketModel : ProcessModel {
+	enum Measure { SPOT = 0, TERMINAL = 1 };
+	enum StateSpace { NORMAL = 0, LOGNORMAL = 1 };
+	TimeDiscretization tenor;          // liborPeriodDiscretization
+	std::vector<double> L0;            // forward curve values L_j(0)
+	std::vector<double> discountFactors; // P^d(T_i) on the tenor grid (size N+1) or empty (no discount curve)
+	std::vector<double> sigma;         // [T][N] instantaneous volatilities on the simulation grid
+	std::vector<double> factorMatrix;  // [N][F]
+	int F;
+	int measure = SPOT, stateSpace = LOGNORMAL;
+	double liborCap = 1e5;
+	// caches (:202-204)
+	std::map<int, P> numeraires;
+	std::map<int, P> numeraireDiscountFactors;
+
+	int getNumberOfComponents() const override { return tenor.getNumberOfTimeSteps(); }
+	int getLiborPeriodIndex(double time) const { return tenor.getTimeIndex(time); }
+	double getLiborPeriod(int i) const { return tenor.getTime(i); }
+
+	std::vector<P> getInitialState(const Process&) override {                               // :1080-1093
+		std::vector<P> s;
+		for (int j = 0; j < getNumberOfComponents(); j++) {
+			const double rate = L0[j];
+			s.push_back(scalar(stateSpace == LOGNORMAL ? std::log(std::max(rate, 0.0)) : rate));
+		}
+		return s;
+	}
+	int simTimeIndexOf(const Process& p, double time) const {                              // AbstractLIBORCovarianceModel.java:58-63
+		int ti = p.getTimeIndex(time);
+		if (ti < 0) ti = -ti - 2;
+		return ti;
+	}
+	P volatility(int ti, int j) const { return scalar(sigma[(size_t)ti * getNumberOfComponents() + j]); }
+	std::vector<P> factorLoadingAt(int ti, int j) const {                                   // ...VolatilityAndCorrelation.java:47-57
+		std::vector<P> fl(F);
+		P vol = volatility(ti, j);
+		for (int k = 0; k < F; k++) fl[k] = mult(vol, factorMatrix[(size_t)j * F + k]);
+		return fl;
+	}
+	std::vector<P> getFactorLoading(const Process& p, int timeIndex, int c, const std::vector<P>&) override {   // :1193-1197
+		return factorLoadingAt(simTimeIndexOf(p, p.getTime(timeIndex)), c);
+	}
+	std::vector<P> getDrift(const Process& p, int timeIndex, const std::vector<P>& x) override {   // :1124-1191
+		const double time = p.getTime(timeIndex);
+		int first = getLiborPeriodIndex(time) + 1;
+		if (first < 0) first = -first - 1 + 1;
+		const int N = getNumberOfComponents();
+		P zero = scalar(0.0);
+		std::vector<P> drift(N);
+		for (int c = first; c < N; c++) drift[c] = zero;
+		std::vector<P> sums(F, zero);
+		const int ti = simTimeIndexOf(p, time);
+		if (measure == SPOT) {
+			for (int c = first; c < N; c++) {
+				const double pl = tenor.getTimeStep(c);
+				P fr = x[c];
+				P ost = discount(scalar(pl), fr, pl);
+				if (stateSpace == LOGNORMAL) ost = mult(ost, fr);
+				std::vector<P> fl = factorLoadingAt(ti, c);
+				for (int k = 0; k < F; k++) sums[k] = addProduct(sums[k], ost, fl[k]);
+				drift[c] = addSumProduct(drift[c], sums, fl);
+			}
+		} else {
+			for (int c = N - 1; c >= first; c--) {
+				const double pl = tenor.getTimeStep(c);
+				P fr = x[c];
+				P ost = discount(scalar(-pl), fr, pl);
+				if (stateSpace == LOGNORMAL) ost = mult(ost, fr);
+				std::vector<P> fl = factorLoadingAt(ti, c);
+				drift[c] = addSumProduct(drift[c], sums, fl);
+				for (int k = 0; k < F; k++) sums[k] = addProduct(sums[k], ost, fl[k]);
+			}
+		}
+		if (stateSpace == LOGNORMAL) {
+			for (int c = first; c < N; c++) {
+				P vol = volatility(ti, c);
+				P variance = mult(mult(vol, vol), 1.0);
+				drift[c] = addProduct(drift[c], variance, -0.5);
+			}
+		}
+		return drift;
+	}
+	P applyStateSpaceTransform(int, int, const P& y) override {                             // :1199-1212
+		P v = y;
+		if (stateSpace == LOGNORMAL) v = exp(v);
+		if (!std::isinf(liborCap)) v = cap(v, liborCap);
+		return v;
+	}
+	bool hasInverse() const override { return true; }
+	P applyStateSpaceTransformInverse(int, int, const P& x) override { return stateSpace == LOGNORMAL ? log(x) : x; }
+
+	P getLIBOR(Process& p, int timeIndex, int liborIndex) { return p.getProcessValue(timeIndex, liborIndex); }
+
+	// :1237-1305, tenor-grid periods only (the configs never leave the grid)
+	P getForwardRate(Process& p, double time, double periodStart, double periodEnd) {
+		const int ps = getLiborPeriodIndex(periodStart), pe = getLiborPeriodIndex(periodEnd);
+		time = std::min(time, periodStart);
+		int ti = p.getTimeIndex(time);
+		if (ti < 0) {
+			ti = -ti - 2;
+			if (time - p.getTime(ti) > p.getTime(ti + 1) - time) ti++;                        // ROUND_NEAREST
+		}
+		if (ps < 0 || pe < 0) throw std::runtime_error("oracle: tenor interpolation not restated");
+		if (ps + 1 == pe) return getLIBOR(p, ti, ps);
+		P acc;
+		for (int k = ps; k < pe; k++) {
+			const double sub = getLiborPeriod(k + 1) - getLiborPeriod(k);
+			P l = getLIBOR(p, ti, k);
+			acc = !acc ? add(mult(l, sub), 1.0) : accrue(acc, l, sub);
+		}
+		return div(orc::sub(acc, 1.0), periodEnd - periodStart);
+	}
+	// :1017-1074 (spot / terminal on the tenor grid)
+	P numeraireUnadjustedAtIndex(Process& p, int li) {
+		auto it = numeraires.find(li);
+		if (it != numeraires.end()) return it->second;
+		P n;
+		if (measure == TERMINAL) {
+			int ti = p.getTimeIndex(tenor.getTime(li));
+			if (ti < 0) ti = -ti - 1;
+			n = scalar(1.0);
+			for (int k = li; k <= tenor.getNumberOfTimeSteps() - 1; k++) n = discount(n, getLIBOR(p, ti, k), tenor.getTimeStep(k));
+		} else {
+			if (li != 0) {
+				int ti = p.getTimeIndex(tenor.getTime(li - 1));
+				if (ti < 0) ti = -ti - 1;
+				n = accrue(numeraireUnadjustedAtIndex(p, li - 1), getLIBOR(p, ti, li - 1), tenor.getTimeStep(li - 1));
+			} else n = scalar(1.0);
+		}
+		numeraires[li] = n;
+		return n;
+	}
+	P numeraireUnadjusted(Process& p, double time) {                                        // :962-1015
+		const int li = getLiborPeriodIndex(time);
+		if (li < 0) throw std::runtime_error("oracle: numeraire off the tenor grid not restated");
+		return numeraireUnadjustedAtIndex(p, li);
+	}
+	P defaultableZeroBondAsOfTimeZero(int timeIndex) {                                      // :915-944
+		if (numeraireDiscountFactors.empty()) {
+			P adj = scalar(discountFactors[0]);
+			numeraireDiscountFactors[0] = adj;
+			for (int i = 0; i < tenor.getNumberOfTimeSteps(); i++) {
+				const double dfPrev = discountFactors[i], dfNext = discountFactors[i + 1], ts = tenor.getTimeStep(i);
+				P fr = scalar((dfPrev / dfNext - 1.0) / ts);
+				adj = discount(adj, fr, ts);
+				numeraireDiscountFactors[i + 1] = adj;
+			}
+		}
+		return numeraireDiscountFactors.at(timeIndex);
+	}
+	P getNumeraire(Process& p, double time) {                                               // :859-876
+		if (time < 0) throw std::runtime_error("oracle: numeraire for negative time not restated");
+		P n = numeraireUnadjusted(p, time);
+		if (!discountFactors.empty()) {
+			const int ti = tenor.getTimeIndex(time);
+			if (ti < 0) throw std::runtime_error("oracle: numeraire adjustment off the tenor grid not restated");
+			P dz = defaultableZeroBondAsOfTimeZero(ti);
+			const double nonDefaultableZeroBond = getAverage(mult(invert(n), numeraireUnadjusted(p, 0.0)));
+			n = div(mult(n, nonDefaultableZeroBond), dz);
+		}
+		return n;
+	}
+};
+
+} // namespace orc
