@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py — LMM forward-rate path-steps/s (BASELINE.json metric) on N B200s, plus the Bermudan swaption wall time.
+
+Workload at N = 1: configs[3] "LIBOR Market Model 40 forward rates, 3-factor covariance, 0.5y steps, 4M paths" (C4), the
+configuration the headline metric is quoted on; under torchrun every rank simulates its own contiguous block of
+4M paths of ONE logical simulation of N*4M paths (weak scaling, MT19937 jump-ahead, no data-path collective).
+One step = {Brownian generation (MT19937 jump-ahead + AS241) + fused log-Euler evolution} of all paths, every realization
+X[t][j][path] stored in HBM (getProcessValue semantics).  The C5 Bermudan swaption (1M paths per GPU) is timed separately
+and reported under "bermudan".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import __graft_entry__ as graft  # noqa: E402
+
+N_LIBORS, N_FACTORS, PERIOD = 40, 3, 0.5
+SCHEME_NAMES = {0: "EULER", 1: "PREDICTOR_CORRECTOR", 2: "EULER_FUNCTIONAL", 3: "PREDICTOR_CORRECTOR_FUNCTIONAL"}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        busy = [c for c in sm if c > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def market(pkg):
+    from common import lmm_setup
+    return lmm_setup(pkg, n_libors=N_LIBORS, n_factors=N_FACTORS, period=PERIOD, dt=PERIOD)
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU path (oracle port, all host threads) on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pkg = graft.load_package()
+    orc = graft.load_oracle()
+    s = market(pkg)
+    cores = os.cpu_count() or 1
+    T = s["T"]
+    sample = args.cpu_paths
+    sec, _ = orc.time_lmm_fused(3141, s["sim"].times, s["tenor"].times, N_FACTORS, min(sample, 20000), s["L0"], s["sigma"], s["factor_matrix"], args.scheme, cores)
+    times = []
+    for _ in range(args.warmup + args.steps):
+        sec, _ = orc.time_lmm_fused(3141, s["sim"].times, s["tenor"].times, N_FACTORS, sample, s["L0"], s["sigma"], s["factor_matrix"], args.scheme, cores)
+        times.append(sec)
+    times = times[args.warmup:]
+    tot = sum(times)
+    value = sample * T * len(times) / tot
+    line = {
+        "impl": "reference", "metric": "LMM forward-rate path-steps/sec", "value": value, "unit": "path-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "C4 LMM 40 forward rates x 3 factors x 40 steps (0.5y), scheme %s; bounded sample of %d paths per step" % (SCHEME_NAMES[args.scheme], sample)},
+        "cpu_baseline": {"value": value, "unit": "path-steps/s", "cores": cores, "kind": "port",
+                         "sample": "%d paths x %d steps per timed step; oracle C++ restatement of the reference's arithmetic, fused per path, path-parallel over %d threads "
+                                   "(faster than the reference's own execution shape; the JVM reference cannot run here: no JVM)" % (sample, T, cores)},
+        "e2e": {"value": value, "unit": "path-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native")
+    ap.add_argument("--paths", type=int, default=4_000_000, help="paths per GPU (C4: 4M)")
+    ap.add_argument("--bermudan-paths", type=int, default=1_000_000, help="paths per GPU for the C5 Bermudan swaption")
+    ap.add_argument("--scheme", type=int, default=2, help="0 EULER, 1 PREDICTOR_CORRECTOR, 2 EULER_FUNCTIONAL (reference default), 3 PC_FUNCTIONAL")
+    ap.add_argument("--cpu-paths", type=int, default=0, help="sample size of the CPU baseline (0 = auto)")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-bermudan", action="store_true")
+    args = ap.parse_args()
+    if args.cpu_paths == 0:
+        args.cpu_paths = 20000 * max(1, (os.cpu_count() or 1))
+    if args.impl == "reference":
+        return run_reference(args)
+
+    pkg = graft.load_package()
+    nv = pkg.native
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    shard = pkg.from_environment()
+    nv.init(local_rank)                                      # raises without a GPU: there is no CPU fallback
+    import torch
+    dist = torch.distributed if world > 1 else None
+
+    def barrier():
+        nv.synchronize()
+        if dist is not None:
+            dist.barrier()
+        nv.synchronize()
+
+    s = market(pkg)
+    T, N, F = s["T"], s["N"], s["F"]
+    P_local = args.paths
+    P_global = P_local * world
+    factory = pkg.RandomVariableCudaFactory(shard)
+    model = pkg.LIBORMarketModelFromCovarianceModel.of(s["tenor"], None, s["L0"], s["df"], factory, s["cov"], None, {"measure": "SPOT", "stateSpace": "LOGNORMAL"})
+    fixing = [5.0 + 0.5 * i for i in range(10)]
+    payment = [5.5 + 0.5 * i for i in range(10)]
+    swaption = pkg.Swaption(5.0, fixing, payment, [0.05] * 10)
+
+    def step(seed, price=False):
+        bm = pkg.BrownianMotionCuda(s["sim"], F, P_global, seed, factory)
+        process = pkg.EulerSchemeFromProcessModel(model, bm, args.scheme)
+        process.getProcessValue(T, N - 1)                   # triggers generation + evolution (lazy like the reference)
+        if price:
+            return swaption.getValue(pkg.LIBORMonteCarloSimulationFromLIBORModel(process))
+        return None
+
+    # ---- kernel-level timing: device events on the library's stream, K steps back to back ------------------------------
+    for w in range(args.warmup):
+        step(1000 + w)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = nv.launch_count()
+    nv.timer_start()
+    for k in range(args.steps):
+        step(3141 + k)
+    ms = nv.timer_stop_ms()
+    launches = nv.launch_count() - launches0
+    barrier()
+    clocks = sampler.finish()
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=shard.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = P_global * T * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the host API: host tables in, price out, per step ---------------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    prices = [step(3141 + k, price=True) for k in range(args.steps)]
+    nv.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=shard.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = P_global * T * args.steps / e2e_s
+    h2d = 8 * (T * F + T + T * N * F + T * N + 4 * N) + 4 * T + 8 * (T * F + (T + 1) * N) + 624 * 4
+    d2h = 2 * 8 * 148 * 4 * 6                               # double-double partials of the reductions behind the price
+
+    # ---- per-kernel durations for the roofline (separate, instrumented steps) ----------------------------------------------
+    bm_ms, eu_ms = [], []
+    for k in range(min(3, args.steps)):
+        bm = pkg.BrownianMotionCuda(s["sim"], F, P_global, 7000 + k, factory)
+        nv.synchronize()
+        nv.timer_start()
+        bm.getBrownianIncrement(0, 0)
+        bm_ms.append(nv.timer_stop_ms())
+        process = pkg.EulerSchemeFromProcessModel(model, bm, args.scheme)
+        nv.timer_start()
+        process.getProcessValue(T, N - 1)
+        eu_ms.append(nv.timer_stop_ms())
+        del process, bm
+    live = sum(max(0, N - (t + 1)) for t in range(T))
+    euler_bytes = P_local * (8 * live + 8 * F * sum(1 for t in range(T) if N - (t + 1) > 0))
+    bm_bytes = P_local * T * F * 8
+    peak, peak_src = measured_peaks()
+    eu = float(np.mean(eu_ms))
+    achieved = euler_bytes / (eu * 1e-3) / 1e9
+    import ctypes as C
+    tf = C.c_double()
+    nv.check(nv.load().fmb_bench_dfma_tflops(C.byref(tf)))
+    roofline = {"bound": "hbm", "kernel": "eulerLmmKernel<3>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": euler_bytes, "avg_launch_ms": eu,
+                "note": "FP64-pipe bound (double exp/log per rate-step), see DESIGN.md; fp64 numbers under 'fp64'"}
+    fp64 = {"dfma_peak_tflops_measured": tf.value, "euler_ms": eu, "brownian_ms": float(np.mean(bm_ms)),
+            "brownian_achieved_gbs": bm_bytes / (float(np.mean(bm_ms)) * 1e-3) / 1e9}
+
+    # ---- C5: Bermudan swaption wall time (simulation + backward induction with regression, price on the host) ------------------
+    bermudan = None
+    if not args.skip_bermudan:
+        from common import bermudan_spec
+        b = bermudan_spec(s)
+        product = pkg.BermudanSwaption(b["is_exercise"], b["fixing"], b["lengths"], b["payment"], b["notionals"], b["swaprates"])
+        Pb = args.bermudan_paths * world
+        walls = []
+        price_b = None
+        for rep in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            bm = pkg.BrownianMotionCuda(s["sim"], F, Pb, 3141, factory)
+            sim = pkg.LIBORMonteCarloSimulationFromLIBORModel(pkg.EulerSchemeFromProcessModel(model, bm, args.scheme))
+            price_b = product.getValue(sim)
+            nv.synchronize()
+            walls.append(time.perf_counter() - t0)
+            del sim, bm
+        wall = min(walls[1:])
+        if dist is not None:
+            t = torch.tensor([wall], dtype=torch.float64, device=shard.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall = float(t.item())
+        bermudan = {"wall_ms": 1e3 * wall, "paths": Pb, "price": price_b, "exercise_dates": 20, "basis_functions": 6}
+
+    # ---- CPU baseline on the host cores (rank 0, N = 1 only; bounded sample) ----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        orc = graft.load_oracle()
+        cores = os.cpu_count() or 1
+        sec, _ = orc.time_lmm_fused(3141, s["sim"].times, s["tenor"].times, F, args.cpu_paths, s["L0"], s["sigma"], s["factor_matrix"], args.scheme, cores)
+        shaped_paths = 20000
+        sec_shaped, _ = orc.time_lmm_reference_shaped(3141, s["sim"].times, s["tenor"].times, F, shaped_paths, s["L0"], s["sigma"], s["factor_matrix"], args.scheme)
+        cpu = {"value": args.cpu_paths * T / sec, "unit": "path-steps/s", "cores": cores, "kind": "port",
+               "sample": "%d paths x %d steps, oracle port fused per path, %d threads, %.1f s" % (args.cpu_paths, T, cores, sec),
+               "reference_shaped": {"value": shaped_paths * T / sec_shaped, "cores": 1,
+                                    "sample": "%d paths, one array pass + allocation per RandomVariable op, single sequential MT stream, %.1f s" % (shaped_paths, sec_shaped)}}
+
+    if rank == 0:
+        line = {
+            "metric": "LMM forward-rate path-steps/sec", "value": value, "unit": "path-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4 LMM 40 forward rates x 3 factors x 40 steps (0.5y), %d paths per GPU, scheme %s, spot measure, log-normal, STRICT fp (no FMA contraction)"
+                                   % (P_local, SCHEME_NAMES[args.scheme]),
+                       "paths_total": P_global, "l2": "inputs/outputs far larger than L2: %.1f GB written per step per GPU" % ((euler_bytes + bm_bytes) / 1e9),
+                       "step": "Brownian generation (MT19937 jump-ahead + AS241) + fused Euler evolution, all X[t][j][path] stored"},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": "path-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "what": "BrownianMotionCuda + EulerSchemeFromProcessModel + Swaption.getValue through the host API, price on the host each step",
+                    "price": prices[-1]},
+            "roofline": roofline, "fp64": fp64, "bermudan": bermudan, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

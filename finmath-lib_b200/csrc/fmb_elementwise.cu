@@ -119,6 +119,11 @@ template <int OP> __global__ void __launch_bounds__(256) ternaryKernel(const dou
 	}
 }
 
+__global__ void __launch_bounds__(256) fillKernel(double* __restrict__ out, double v, uint64_t n) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) out[i] = v;
+}
+
 static inline int aligned16(const void* p) { return p == nullptr || (((uintptr_t)p) & 15) == 0; }
 
 // grid sized as a multiple of the SM count (8 resident CTAs of 256 threads per SM), capped by the work
@@ -151,6 +156,16 @@ static int finishLaunch(fmb_handle* out) {
 using namespace fmb;
 
 extern "C" {
+
+int fmb_rv_fill(double value, uint64_t n, fmb_handle* out) {
+	FMB_TRY(requireInit());
+	if (!out) return FMB_EINVAL;
+	double* dst;
+	FMB_TRY(newVec(n, out, &dst));
+	if (n == 0) return FMB_OK;
+	fillKernel<<<ewGrid(n), 256, 0, ctx().stream>>>(dst, value, n);
+	return finishLaunch(out);
+}
 
 int fmb_rv_unary(int opcode, fmb_handle x, double a, fmb_handle* out) {
 	FMB_TRY(requireInit());

@@ -1,0 +1,435 @@
+"""ProcessModel mirrors (SDE specifications) and the simulation façades.  Host-side logic only: every model keeps the
+reference's callback contract (J/montecarlo/model/ProcessModel.java:47-174) on RandomVariables — so the generic Euler
+loop can run it unchanged — and additionally describes itself to the fused kernels through getFusedSpecification().
+
+* BlackScholesModel                       J/montecarlo/assetderivativevaluation/models/BlackScholesModel.java:42-203
+* HestonModel                             J/montecarlo/assetderivativevaluation/models/HestonModel.java:75-523
+* LIBORMarketModelFromCovarianceModel     J/montecarlo/interestrate/models/LIBORMarketModelFromCovarianceModel.java:161-1757
+  with LIBORVolatilityModelFourParameterExponentialForm (…/covariance/…:168-190), LIBORCorrelationModelExponentialDecay
+  (…:87-134, PCA factor reduction J/functions/LinearAlgebra.java:392-482), LIBORCovarianceModelFromVolatilityAndCorrelation (…:47-93)
+* MonteCarloAssetModel / MonteCarloBlackScholesModel   J/montecarlo/assetderivativevaluation/MonteCarloAssetModel.java:31-209
+* LIBORMonteCarloSimulationFromLIBORModel  J/montecarlo/interestrate/LIBORMonteCarloSimulationFromLIBORModel.java:27-206
+"""
+import math
+
+import numpy as np
+
+from .montecarlo import BrownianMotionCuda, EulerSchemeFromProcessModel, Scheme
+from .stochastic import RandomVariableCudaFactory, Scalar
+
+
+class BlackScholesModel:
+    def __init__(self, initialValue, riskFreeRate, volatility, randomVariableFactory=None):
+        f = randomVariableFactory if randomVariableFactory is not None else RandomVariableCudaFactory()
+        self.randomVariableFactory = f
+        self.initialValue = f.createRandomVariable(initialValue)
+        self.riskFreeRate = f.createRandomVariable(riskFreeRate)
+        self.volatility = f.createRandomVariable(volatility)
+        self.initialState = [self.initialValue.log()]                                          # :76
+        self.drift = [self.riskFreeRate.sub(self.volatility.squared().div(2))]                 # :77
+        self.factorLoadings = [self.volatility]
+
+    def getNumberOfComponents(self): return 1
+    def getNumberOfFactors(self): return 1
+    def getInitialState(self, process): return self.initialState
+    def getDrift(self, process, timeIndex, realizationAtTimeIndex, realizationPredictor): return self.drift
+    def getFactorLoading(self, process, timeIndex, component, realizationAtTimeIndex): return self.factorLoadings
+    def applyStateSpaceTransform(self, process, timeIndex, componentIndex, rv): return rv.exp()
+    def applyStateSpaceTransformInverse(self, process, timeIndex, componentIndex, rv): return rv.log()
+    def getNumeraire(self, process, time): return self.riskFreeRate.mult(time).exp()
+    def getRandomVariableForConstant(self, value): return self.randomVariableFactory.createRandomVariable(value)
+
+    def getFusedSpecification(self, process):
+        s0 = self.initialValue.doubleValue()
+        return dict(kernel="black_scholes", initialValue=s0, riskFreeRate=self.riskFreeRate.doubleValue(),
+                    volatility=self.volatility.doubleValue(), initialValues=[math.exp(math.log(s0))])
+
+
+class HestonModel:
+    REFLECTION, FULL_TRUNCATION = 0, 1
+
+    def __init__(self, initialValue, riskFreeRate, volatility, discountRate, theta, kappa, xi, rho, scheme, randomVariableFactory=None):
+        f = randomVariableFactory if randomVariableFactory is not None else RandomVariableCudaFactory()
+        self.randomVariableFactory = f
+        c = f.createRandomVariable
+        self.initialValue, self.riskFreeRate, self.volatility, self.discountRate = c(initialValue), c(riskFreeRate), c(volatility), c(discountRate)
+        self.theta, self.kappa, self.xi, self.rho = c(theta), c(kappa), c(xi), c(rho)
+        self.rhoBar = self.rho.squared().sub(1).mult(-1).sqrt()                                # :182
+        self.scheme = scheme
+        self.ZERO = Scalar(0.0)                                                                 # :92
+
+    def getNumberOfComponents(self): return 2
+    def getNumberOfFactors(self): return 1                                                       # :437-440 (sic)
+    def getInitialState(self, process): return [self.initialValue.log(), self.volatility.squared()]
+
+    def _variance(self, rv):
+        return rv.floor(0.0) if self.scheme == HestonModel.FULL_TRUNCATION else rv.abs()
+
+    def getDrift(self, process, timeIndex, x, predictor):
+        var = self._variance(x[1])
+        return [self.riskFreeRate.sub(var.div(2.0)), self.theta.sub(var).mult(self.kappa)]     # :361-362
+
+    def getFactorLoading(self, process, timeIndex, component, x):
+        vol = self._variance(x[1]).sqrt()
+        if component == 0:
+            return [vol, self.ZERO]
+        v = vol.mult(self.xi)
+        return [v.mult(self.rho), v.mult(self.rhoBar)]
+
+    def applyStateSpaceTransform(self, process, timeIndex, componentIndex, rv): return rv.exp() if componentIndex == 0 else rv
+    def applyStateSpaceTransformInverse(self, process, timeIndex, componentIndex, rv): return rv.log() if componentIndex == 0 else rv
+    def getNumeraire(self, process, time): return self.discountRate.mult(time).exp()
+    def getRandomVariableForConstant(self, value): return self.randomVariableFactory.createRandomVariable(value)
+
+    def getFusedSpecification(self, process):
+        T = process.getTimeDiscretization().getNumberOfTimeSteps()
+        s0, sigma = self.initialValue.doubleValue(), self.volatility.doubleValue()
+        return dict(kernel="heston", hestonScheme=self.scheme, initialValue=s0, riskFreeRates=[self.riskFreeRate.doubleValue()] * T,
+                    volatility=sigma, theta=self.theta.doubleValue(), kappa=self.kappa.doubleValue(), xi=self.xi.doubleValue(),
+                    rho=self.rho.doubleValue(), initialValues=[math.exp(math.log(s0)), sigma * sigma])
+
+
+class MonteCarloAssetModel:
+    def __init__(self, model, process_or_driver, scheme=None):
+        self.model = model
+        if isinstance(process_or_driver, EulerSchemeFromProcessModel):
+            self.process = process_or_driver
+        else:
+            self.process = EulerSchemeFromProcessModel(model, process_or_driver, scheme)      # MonteCarloAssetModel.java:54-56
+
+    def getTimeDiscretization(self): return self.process.getTimeDiscretization()
+    def getTime(self, i): return self.process.getTime(i)
+    def getTimeIndex(self, t): return self.process.getTimeIndex(t)
+    def getNumberOfPaths(self): return self.process.getNumberOfPaths()
+    def getNumberOfAssets(self): return 1
+    def getModel(self): return self.model
+    def getProcess(self): return self.process
+    def getRandomVariableForConstant(self, v): return self.model.getRandomVariableForConstant(v)
+
+    def getAssetValue(self, time, assetIndex):
+        if isinstance(time, float):
+            timeIndex = self.getTimeIndex(time)
+            if timeIndex < 0:
+                raise ValueError("The model does not provide an interpolation of simulation time (time given was %r)." % time)
+        else:
+            timeIndex = time
+        return self.process.getProcessValue(timeIndex, assetIndex)
+
+    def getNumeraire(self, time):
+        if not isinstance(time, float):
+            time = self.getTime(time)
+        return self.model.getNumeraire(self.process, time)
+
+    def getMonteCarloWeights(self, time):
+        timeIndex = self.getTimeIndex(time) if isinstance(time, float) else time
+        return self.process.getMonteCarloWeights(timeIndex)
+
+
+class MonteCarloBlackScholesModel(MonteCarloAssetModel):
+    seed = 3141                                                                                 # MonteCarloBlackScholesModel.java:50
+
+    def __init__(self, *args, shard=None):
+        if len(args) == 5:                                   # (timeDiscretization, numberOfPaths, initialValue, riskFreeRate, volatility) :77-87
+            td, paths, s0, r, sigma = args
+            driver = BrownianMotionCuda(td, 1, paths, self.seed, shard=shard)
+        else:                                                # (initialValue, riskFreeRate, volatility, brownianMotion)
+            s0, r, sigma, driver = args
+        super().__init__(BlackScholesModel(s0, r, sigma, driver.randomVariableFactory), driver)
+
+
+# ---- LIBOR market model ------------------------------------------------------------------------------------------------
+class LIBORVolatilityModelFourParameterExponentialForm:
+    def __init__(self, timeDiscretization, liborPeriodDiscretization, a, b, c, d, isCalibrateable=False):
+        self.td, self.tenor, self.a, self.b, self.c, self.d = timeDiscretization, liborPeriodDiscretization, a, b, c, d
+
+    def getVolatility(self, timeIndex, liborIndex):          # :168-190
+        ttm = self.tenor.getTime(liborIndex) - self.td.getTime(timeIndex)
+        if ttm <= 0:
+            return 0.0
+        return (self.b * ttm + self.a) * math.exp(self.c * (-ttm)) + self.d
+
+
+def _factor_matrix(correlation, numberOfFactors):
+    """LinearAlgebra.getFactorMatrixUsingCommonsMath :392-443 (symmetric eigen-decomposition, largest eigenvalues first,
+    first entry of each eigenvector positive, column scaled by sqrt(eigenvalue / |v|^2))."""
+    ev, V = np.linalg.eigh(correlation)
+    order = np.argsort(-ev, kind="stable")
+    n = correlation.shape[0]
+    fm = np.zeros((n, numberOfFactors))
+    for f in range(numberOfFactors):
+        idx = order[f]
+        sign = 1.0 if V[0, idx] > 0.0 else -1.0
+        norm2 = float(np.sum(V[:, idx] * V[:, idx]))
+        e = max(float(ev[idx]), 0.0)
+        fm[:, f] = sign * math.sqrt(e / norm2) * V[:, idx]
+    return fm
+
+
+def factorReduction(correlation, numberOfFactors):           # LinearAlgebra.factorReductionUsingCommonsMath :452-482
+    fm = _factor_matrix(correlation, numberOfFactors)
+    for row in range(fm.shape[0]):
+        s = float(np.sum(fm[row] * fm[row]))
+        fm[row] = fm[row] / math.sqrt(s) if s != 0 else 1.0
+    return _factor_matrix(fm @ fm.T, numberOfFactors)
+
+
+class LIBORCorrelationModelExponentialDecay:
+    def __init__(self, timeDiscretization, liborPeriodDiscretization, numberOfFactors, a, isCalibrateable=False):
+        a = max(a, 0)
+        n = liborPeriodDiscretization.getNumberOfTimeSteps()
+        T = liborPeriodDiscretization.getAsDoubleArray()
+        corr = np.array([[math.exp(-a * abs(T[r] - T[c])) for c in range(n)] for r in range(n)])     # :102-112
+        self.factorMatrix = factorReduction(corr, numberOfFactors)
+        self.correlationMatrix = self.factorMatrix @ self.factorMatrix.T
+        np.fill_diagonal(self.correlationMatrix, 1.0)                                               # :129
+
+    def getNumberOfFactors(self): return self.factorMatrix.shape[1]
+    def getFactorLoading(self, timeIndex, factor, component): return float(self.factorMatrix[component, factor])
+    def getCorrelation(self, timeIndex, c1, c2): return float(self.correlationMatrix[c1, c2])
+
+
+class LIBORCovarianceModelFromVolatilityAndCorrelation:
+    def __init__(self, timeDiscretization, liborPeriodDiscretization, volatilityModel, correlationModel):
+        self.td, self.tenor, self.volatilityModel, self.correlationModel = timeDiscretization, liborPeriodDiscretization, volatilityModel, correlationModel
+
+    def getNumberOfFactors(self): return self.correlationModel.getNumberOfFactors()
+
+    def getFactorLoadingTable(self):
+        """[T][N][F] deterministic factor loadings sigma_j(t_i) * F[j][k] (:47-57) and [T][N] variances sigma*sigma*corr_jj (:82-93)."""
+        T, N, F = self.td.getNumberOfTimeSteps(), self.tenor.getNumberOfTimeSteps(), self.getNumberOfFactors()
+        fl = np.zeros((T, N, F))
+        var = np.zeros((T, N))
+        for t in range(T):
+            for j in range(N):
+                vol = self.volatilityModel.getVolatility(t, j)
+                for k in range(F):
+                    fl[t, j, k] = vol * self.correlationModel.getFactorLoading(t, k, j)
+                var[t, j] = (vol * vol) * self.correlationModel.getCorrelation(t, j, j)
+        return fl, var
+
+
+class LIBORMarketModelFromCovarianceModel:
+    SPOT, TERMINAL = 0, 1
+    NORMAL, LOGNORMAL = 0, 1
+
+    def __init__(self, liborPeriodDiscretization, forwardRates, discountFactors, randomVariableFactory, covarianceModel, properties=None,
+                 factorLoadingTable=None):
+        """forwardRates[j] = L_j(0) on the tenor grid (the forward curve evaluated there); discountFactors[i] = P^d(T_i) or None."""
+        properties = dict(properties or {})
+        self.tenor = liborPeriodDiscretization
+        self.L0 = np.asarray(forwardRates, dtype=np.float64)
+        self.discountFactors = None if discountFactors is None else np.asarray(discountFactors, dtype=np.float64)
+        self.randomVariableFactory = randomVariableFactory if randomVariableFactory is not None else RandomVariableCudaFactory()
+        self.covarianceModel = covarianceModel
+        self.measure = {"SPOT": 0, "TERMINAL": 1}[properties.get("measure", "SPOT")]                 # defaults :186-194
+        self.stateSpace = {"NORMAL": 0, "LOGNORMAL": 1}[properties.get("stateSpace", "LOGNORMAL")]
+        self.liborCap = float(properties.get("liborCap", 1e5))
+        self._tables = factorLoadingTable
+        self._numeraires, self._numeraireDiscountFactors, self._numerairesProcess = {}, {}, None
+
+    @classmethod
+    def of(cls, liborPeriodDiscretization, analyticModel, forwardRates, discountFactors, randomVariableFactory, covarianceModel, calibrationItems=None,
+           properties=None):
+        return cls(liborPeriodDiscretization, forwardRates, discountFactors, randomVariableFactory, covarianceModel, properties)
+
+    # ---- ProcessModel callbacks -----------------------------------------------------------------------------------------
+    def getNumberOfComponents(self): return self.tenor.getNumberOfTimeSteps()
+    def getNumberOfLibors(self): return self.getNumberOfComponents()
+    def getNumberOfFactors(self): return self.covarianceModel.getNumberOfFactors()
+    def getLiborPeriodDiscretization(self): return self.tenor
+    def getLiborPeriod(self, i): return self.tenor.getTime(i)
+    def getLiborPeriodIndex(self, time): return self.tenor.getTimeIndex(time)
+    def getRandomVariableForConstant(self, v): return self.randomVariableFactory.createRandomVariable(v)
+
+    def _tables_for(self, process):
+        if self._tables is None:
+            self._tables = self.covarianceModel.getFactorLoadingTable()
+        return self._tables
+
+    def getInitialState(self, process):                      # :1080-1093
+        c = self.getRandomVariableForConstant
+        if self.stateSpace == self.LOGNORMAL:
+            return [c(math.log(max(r, 0.0)) if max(r, 0.0) > 0 else float("-inf")) for r in self.L0]
+        return [c(float(r)) for r in self.L0]
+
+    def _first(self, time):
+        first = self.getLiborPeriodIndex(time) + 1          # :1127-1130
+        if first < 0:
+            first = -first - 1 + 1
+        return first
+
+    def _sim_index(self, process, time):
+        ti = process.getTimeIndex(time)
+        return ti if ti >= 0 else -ti - 2
+
+    def getFactorLoading(self, process, timeIndex, componentIndex, realizationAtTimeIndex):
+        fl, _ = self._tables_for(process)
+        ti = self._sim_index(process, process.getTime(timeIndex))
+        return [Scalar(fl[ti, componentIndex, k]) for k in range(fl.shape[2])]
+
+    def getDrift(self, process, timeIndex, x, predictor):    # :1124-1191 on RandomVariables (used by the generic Euler loop)
+        time = process.getTime(timeIndex)
+        first = self._first(time)
+        N, F = self.getNumberOfComponents(), self.getNumberOfFactors()
+        fl, var = self._tables_for(process)
+        ti = self._sim_index(process, time)
+        zero = Scalar(0.0)
+        drift = [None] * N
+        for c in range(first, N):
+            drift[c] = zero
+        sums = [zero] * F
+        order = range(first, N) if self.measure == self.SPOT else range(N - 1, first - 1, -1)
+        for c in order:
+            pl = self.tenor.getTimeStep(c)
+            fr = x[c]
+            ost = Scalar(pl if self.measure == self.SPOT else -pl).discount(fr, pl)
+            if self.stateSpace == self.LOGNORMAL:
+                ost = ost.mult(fr)
+            flc = [Scalar(fl[ti, c, k]) for k in range(F)]
+            if self.measure == self.SPOT:
+                sums = [sums[k].addProduct(ost, flc[k]) for k in range(F)]
+                drift[c] = drift[c].addSumProduct(sums, flc)
+            else:
+                drift[c] = drift[c].addSumProduct(sums, flc)
+                sums = [sums[k].addProduct(ost, flc[k]) for k in range(F)]
+        if self.stateSpace == self.LOGNORMAL:
+            for c in range(first, N):
+                drift[c] = drift[c].addProduct(Scalar(var[ti, c]), -0.5)
+        return drift
+
+    def applyStateSpaceTransform(self, process, timeIndex, componentIndex, rv):      # :1199-1212
+        v = rv
+        if self.stateSpace == self.LOGNORMAL:
+            v = v.exp()
+        if not math.isinf(self.liborCap):
+            v = v.cap(self.liborCap)
+        return v
+
+    def applyStateSpaceTransformInverse(self, process, timeIndex, componentIndex, rv):
+        return rv.log() if self.stateSpace == self.LOGNORMAL else rv
+
+    def getFusedSpecification(self, process):
+        td = process.getTimeDiscretization()
+        T, N = td.getNumberOfTimeSteps(), self.getNumberOfComponents()
+        fl, var = self._tables_for(process)
+        y0 = [s.doubleValue() for s in self.getInitialState(process)]
+        x0 = []
+        for y in y0:
+            x = math.exp(y) if self.stateSpace == self.LOGNORMAL else y
+            x0.append(x if math.isinf(self.liborCap) else min(x, self.liborCap))
+        return dict(kernel="lmm", measure=self.measure, stateSpace=self.stateSpace, liborCap=self.liborCap, initialState=y0,
+                    periodLength=[self.tenor.getTimeStep(j) for j in range(N)], factorLoading=fl, variance=var,
+                    firstLive=[self._first(td.getTime(t)) for t in range(T)], initialValues=x0)
+
+    # ---- term-structure functions on RandomVariables (unchanged host logic) -------------------------------------------------
+    def getLIBOR(self, process, timeIndex, liborIndex):
+        return process.getProcessValue(timeIndex, liborIndex)
+
+    def getForwardRate(self, process, time, periodStart, periodEnd):                 # :1237-1305 (tenor-grid periods)
+        ps, pe = self.getLiborPeriodIndex(periodStart), self.getLiborPeriodIndex(periodEnd)
+        time = min(time, periodStart)
+        ti = process.getTimeIndex(time)
+        if ti < 0:
+            ti = -ti - 2
+            if time - process.getTime(ti) > process.getTime(ti + 1) - time:           # ROUND_NEAREST
+                ti += 1
+        if ps < 0 or pe < 0:
+            raise NotImplementedError("forward rates off the tenor grid (tenor interpolation) are outside the hot path")
+        if ps + 1 == pe:
+            return self.getLIBOR(process, ti, ps)
+        acc = None
+        for k in range(ps, pe):
+            sub = self.getLiborPeriod(k + 1) - self.getLiborPeriod(k)
+            l = self.getLIBOR(process, ti, k)
+            acc = l.mult(sub).add(1.0) if acc is None else acc.accrue(l, sub)
+        return acc.sub(1.0).div(periodEnd - periodStart)
+
+    def _ensure_cache(self, process):
+        if process is not self._numerairesProcess:                                     # :951-961
+            self._numeraires.clear()
+            self._numeraireDiscountFactors.clear()
+            self._numerairesProcess = process
+
+    def _numeraire_unadjusted_at(self, process, li):                                   # :1017-1074
+        self._ensure_cache(process)
+        n = self._numeraires.get(li)
+        if n is None:
+            if self.measure == self.TERMINAL:
+                ti = process.getTimeIndex(self.tenor.getTime(li))
+                if ti < 0:
+                    ti = -ti - 1
+                n = self.getRandomVariableForConstant(1.0)
+                for k in range(li, self.tenor.getNumberOfTimeSteps()):
+                    n = n.discount(self.getLIBOR(process, ti, k), self.tenor.getTimeStep(k))
+            else:
+                if li != 0:
+                    ti = process.getTimeIndex(self.tenor.getTime(li - 1))
+                    if ti < 0:
+                        ti = -ti - 1
+                    n = self._numeraire_unadjusted_at(process, li - 1).accrue(self.getLIBOR(process, ti, li - 1), self.tenor.getTimeStep(li - 1))
+                else:
+                    n = self.getRandomVariableForConstant(1.0)
+            self._numeraires[li] = n
+        return n
+
+    def _numeraire_unadjusted(self, process, time):
+        li = self.getLiborPeriodIndex(time)
+        if li < 0:
+            raise NotImplementedError("numeraire off the tenor grid is outside the hot path")
+        return self._numeraire_unadjusted_at(process, li)
+
+    def _defaultable_zero_bond(self, process, timeIndex):                              # :915-944
+        self._ensure_cache(process)
+        if not self._numeraireDiscountFactors:
+            c = self.randomVariableFactory.createRandomVariable
+            adj = c(float(self.discountFactors[0]))
+            self._numeraireDiscountFactors[0] = adj
+            for i in range(self.tenor.getNumberOfTimeSteps()):
+                dfPrev, dfNext, ts = float(self.discountFactors[i]), float(self.discountFactors[i + 1]), self.tenor.getTimeStep(i)
+                adj = adj.discount(c((dfPrev / dfNext - 1.0) / ts), ts)
+                self._numeraireDiscountFactors[i + 1] = adj
+        return self._numeraireDiscountFactors[timeIndex]
+
+    def getNumeraire(self, process, time):                                             # :859-876
+        if time < 0:
+            raise NotImplementedError("numeraire for negative times is outside the hot path")
+        n = self._numeraire_unadjusted(process, time)
+        if self.discountFactors is not None:
+            ti = self.tenor.getTimeIndex(time)
+            if ti < 0:
+                raise NotImplementedError("numeraire adjustment off the tenor grid is outside the hot path")
+            dz = self._defaultable_zero_bond(process, ti)
+            nonDefaultableZeroBond = n.invert().mult(self._numeraire_unadjusted(process, 0.0)).getAverage()
+            n = n.mult(nonDefaultableZeroBond).div(dz)
+        return n
+
+
+class LIBORMonteCarloSimulationFromLIBORModel:
+    def __init__(self, process_or_model, process=None):
+        if process is None:
+            self.process, self.model = process_or_model, process_or_model.getModel()
+        else:
+            self.model, self.process = process_or_model, process
+
+    def getModel(self): return self.model
+    def getProcess(self): return self.process
+    def getBrownianMotion(self): return self.process.getStochasticDriver()
+    def getTimeDiscretization(self): return self.process.getTimeDiscretization()
+    def getTime(self, i): return self.process.getTime(i)
+    def getTimeIndex(self, t): return self.process.getTimeIndex(t)
+    def getNumberOfPaths(self): return self.process.getNumberOfPaths()
+    def getNumberOfLibors(self): return self.model.getNumberOfLibors()
+    def getLiborPeriodDiscretization(self): return self.model.getLiborPeriodDiscretization()
+    def getLiborPeriod(self, i): return self.model.getLiborPeriod(i)
+    def getLiborPeriodIndex(self, t): return self.model.getLiborPeriodIndex(t)
+    def getLIBOR(self, timeIndex, liborIndex): return self.model.getLIBOR(self.process, timeIndex, liborIndex)
+    def getForwardRate(self, time, periodStart, periodEnd): return self.model.getForwardRate(self.process, time, periodStart, periodEnd)
+    def getNumeraire(self, time): return self.model.getNumeraire(self.process, time)
+    def getRandomVariableForConstant(self, v): return self.model.getRandomVariableForConstant(v)
+
+    def getMonteCarloWeights(self, time):
+        ti = self.getTimeIndex(time) if isinstance(time, float) else time
+        return self.process.getMonteCarloWeights(ti)
+
+    def getCloneWithModifiedSeed(self, seed):
+        return LIBORMonteCarloSimulationFromLIBORModel(self.model, self.process.getCloneWithModifiedSeed(seed))

