@@ -12,8 +12,10 @@ def _vectors(n, seed=1):
     x = rng.standard_normal(n)
     y = rng.standard_normal(n) * 3.0 + 0.5
     z = rng.random(n) + 0.25
-    x[:8] = [0.0, -0.0, np.nan, np.inf, -np.inf, 1.0, -1.0, 2.0]
-    y[:8] = [-0.0, 0.0, 1.0, np.nan, 2.0, np.inf, -0.0, 0.5]
+    sx = [0.0, -0.0, np.nan, np.inf, -np.inf, 1.0, -1.0, 2.0]
+    sy = [-0.0, 0.0, 1.0, np.nan, 2.0, np.inf, -0.0, 0.5]
+    m = min(n, 8)
+    x[:m], y[:m] = sx[:m], sy[:m]
     return x, y, z
 
 
