@@ -4,6 +4,7 @@
 // 16-byte vector accesses when every pointer is 16-byte aligned.  Compiled with -fmad=false: x + y*z is a rounded
 // multiply followed by a rounded add, as on the JVM.
 #include "fmb_common.cuh"
+#include "fmb_math.cuh"
 
 namespace fmb {
 
@@ -23,8 +24,8 @@ template <int OP> __device__ __forceinline__ double unaryOp(double x, double a) 
 	switch (OP) {
 	case FMB_U_SQUARED: return x * x;
 	case FMB_U_SQRT: return sqrt(x);
-	case FMB_U_EXP: return exp(x);
-	case FMB_U_LOG: return log(x);
+	case FMB_U_EXP: return fexp(x);
+	case FMB_U_LOG: return flog(x);
 	case FMB_U_SIN: return sin(x);
 	case FMB_U_COS: return cos(x);
 	case FMB_U_INVERT: return 1.0 / x;

@@ -10,6 +10,7 @@
 //
 // Algorithmic HBM bytes per path-step: 8*F read (increments) + 8*live(t) written (process values).
 #include "fmb_common.cuh"
+#include "fmb_math.cuh"
 #include <cmath>
 #include <algorithm>
 
@@ -26,6 +27,10 @@ __device__ __forceinline__ double jmaxE(double a, double b) {
 	return (a >= b) ? a : b;
 }
 
+#ifndef FMB_LMM_U
+#define FMB_LMM_U 2          // live rates processed together per thread (ILP); 2 measured best on B200 (profiles/r01_notes.md)
+#endif
+
 enum { SCHEME_EULER = 0, SCHEME_PC = 1, SCHEME_EULER_FUNCTIONAL = 2, SCHEME_PC_FUNCTIONAL = 3 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -39,11 +44,11 @@ __global__ void __launch_bounds__(256) eulerBlackScholesKernel(int functional, i
 	for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < P; p += stride) {
 		double x = x0, y = y0;
 		for (int t = 0; t < T; t++) {
-			if (functional) y = (t == 0) ? ylog0 : log(x);
+			if (functional) y = (t == 0) ? ylog0 : flog(x);
 			const double w = dW[(size_t)t * F][p];
 			y = y + drift * dt[t];
 			y = y + w * sigma;
-			x = exp(y);
+			x = fexp(y);
 			X[t + 1][p] = x;
 		}
 	}
@@ -73,7 +78,7 @@ __global__ void __launch_bounds__(256) eulerHestonKernel(HestonParams h, int T, 
 			double var, mu0, mu1;
 			hestonDrift(h, v, r, var, mu0, mu1);
 			const double vol = sqrt(var);
-			if (functional) { y0 = (t == 0) ? h.ylog0 : log(s); y1 = v; }
+			if (functional) { y0 = (t == 0) ? h.ylog0 : flog(s); y1 = v; }
 			y0 = y0 + mu0 * d;
 			y0 = y0 + vol * w0;
 			y0 = y0 + w1 * 0.0;
@@ -81,14 +86,14 @@ __global__ void __launch_bounds__(256) eulerHestonKernel(HestonParams h, int T, 
 			y1 = y1 + mu1 * d;
 			y1 = y1 + (volv * h.rho) * w0;
 			y1 = y1 + (volv * h.rhoBar) * w1;
-			s = exp(y0);
+			s = fexp(y0);
 			v = y1;
 			if (pc) {
 				double varP, mu0P, mu1P;
 				hestonDrift(h, v, r, varP, mu0P, mu1P);
 				y0 = y0 + ((mu0P - mu0) / 2.0) * d;
 				y1 = y1 + ((mu1P - mu1) / 2.0) * d;
-				s = exp(y0);
+				s = fexp(y0);
 				v = y1;
 			}
 			X[2 * (size_t)(t + 1)][p] = s;
@@ -131,59 +136,140 @@ __global__ void __launch_bounds__(256) eulerHullWhiteKernel(int T, uint64_t P, c
 // Y (non-functional schemes) and mu (predictor-corrector) live in a block-private, L2-resident global scratch.
 // ---------------------------------------------------------------------------------------------------------------
 struct LmmParams {
-	int scheme, measure, lognormal, hasCap;
+	int scheme, measure, hasCap;
 	double cap;
-	int T, N, F;
+	int T, N, F, recStride;
 	const double* dt;        // [T]
-	const double* fl;        // [T][N][F]
-	const double* hv;        // [T][N]  variance * (-0.5)
 	const int* firstLive;    // [T]
-	const double* ratio;     // [N]  periodLength / value   (value = +-periodLength)
-	const double* invv;      // [N]  1.0 / value
+	const double* rec;       // [T][N][recStride]: ratio, invv, hv, (bits of) X[t+1][j] row pointer, fl[0..F), pad
 	const double* x0;        // [N]  X_j(0) (host libm)
 	const double* y0;        // [N]  Y_j(0)
 	const double* ylog0;     // [N]  inverse transform of X_j(0) (host libm), used at the first step of functional schemes
 };
 
-template <int FT> __device__ __forceinline__ double lmmDriftTerm(const LmmParams& q, const double* __restrict__ flj, double* S, double a, bool spot) {
-	const int F = FT > 0 ? FT : q.F;
-	double mu;
-	if (spot) {
+// One (t, j) record is read by every thread of every block in the same order: 16-byte uniform loads, L1-resident.
+template <int FT> struct LmmRec {
+	double ratio, invv, hv;
+	double* xrow;
+	double fl[FT > 0 ? FT : 16];
+	__device__ __forceinline__ void load(const double* __restrict__ r, int F) {
+		const double2 a = __ldg(reinterpret_cast<const double2*>(r));
+		const double2 b = __ldg(reinterpret_cast<const double2*>(r) + 1);
+		ratio = a.x; invv = a.y; hv = b.x;
+		xrow = reinterpret_cast<double*>(__double_as_longlong(b.y));
+		if (FT > 0) {
 #pragma unroll
-		for (int k = 0; k < (FT > 0 ? FT : 16); k++) if (k < F) S[k] = S[k] + a * flj[k];
-		mu = S[0] * flj[0] + 0.0;
-#pragma unroll
-		for (int k = 1; k < (FT > 0 ? FT : 16); k++) if (k < F) mu = mu + S[k] * flj[k];
-	} else {
-		mu = S[0] * flj[0] + 0.0;
-#pragma unroll
-		for (int k = 1; k < (FT > 0 ? FT : 16); k++) if (k < F) mu = mu + S[k] * flj[k];
-#pragma unroll
-		for (int k = 0; k < (FT > 0 ? FT : 16); k++) if (k < F) S[k] = S[k] + a * flj[k];
+			for (int k = 0; k < FT; k += 2) {
+				const double2 c = __ldg(reinterpret_cast<const double2*>(r) + 2 + k / 2);
+				fl[k] = c.x;
+				if (k + 1 < FT) fl[k + 1] = c.y;
+			}
+		} else {
+			for (int k = 0; k < F; k++) fl[k] = __ldg(r + 4 + k);
+		}
 	}
-	return mu;
+};
+
+// U consecutive live rates of one path at once (i = position in processing order; j = first+i for the spot measure,
+// N-1-i for the terminal measure).  Per rate the operations and their order are exactly those of the scalar recipe; the
+// only cross-rate dependency is the running factor sum S, so the U log / exp / reciprocal chains overlap (ILP U).
+template <int FT, bool LOGN, int MODE, int U, bool CORRECTOR>
+__device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __restrict__ rect, int j0, int jStep, int BD, int F, bool spot, bool functional,
+		bool firstStep, double d, const double* w, double* S, double* Lcol, double* Ybuf, double* Mbuf, uint64_t p) {
+	constexpr int FMAX = FT > 0 ? FT : 16;
+	LmmRec<FT> r[U];
+	double L[U], a[U], mu[U], y[U], Ln[U];
+#pragma unroll
+	for (int u = 0; u < U; u++) {
+		const int j = j0 + u * jStep;
+		r[u].load(rect + (size_t)j * q.recStride, F);
+		L[u] = Lcol[j * BD];
+	}
+#pragma unroll
+	for (int u = 0; u < U; u++) {
+		a[u] = 1.0 / (L[u] * r[u].ratio + r[u].invv);
+		if (LOGN) a[u] = a[u] * L[u];
+	}
+#pragma unroll
+	for (int u = 0; u < U; u++) {
+		if (spot) {
+#pragma unroll
+			for (int k = 0; k < FMAX; k++) if (k < F) S[k] = S[k] + a[u] * r[u].fl[k];
+		}
+		double m = S[0] * r[u].fl[0] + 0.0;
+#pragma unroll
+		for (int k = 1; k < FMAX; k++) if (k < F) m = m + S[k] * r[u].fl[k];
+		if (!spot) {
+#pragma unroll
+			for (int k = 0; k < FMAX; k++) if (k < F) S[k] = S[k] + a[u] * r[u].fl[k];
+		}
+		if (LOGN) m = m + r[u].hv;
+		mu[u] = m;
+	}
+	if (!CORRECTOR) {
+		if (MODE == 1 || (MODE == 2 && !functional)) {
+#pragma unroll
+			for (int u = 0; u < U; u++) y[u] = Ybuf[(size_t)(j0 + u * jStep) * BD];
+		} else if (firstStep) {
+#pragma unroll
+			for (int u = 0; u < U; u++) y[u] = q.ylog0[j0 + u * jStep];
+		} else if (LOGN) {
+			flogN<U>(L, y);
+		} else {
+#pragma unroll
+			for (int u = 0; u < U; u++) y[u] = L[u];
+		}
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			y[u] = y[u] + mu[u] * d;
+#pragma unroll
+			for (int k = 0; k < FMAX; k++) if (k < F) y[u] = y[u] + w[k] * r[u].fl[k];
+		}
+	} else {
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			const int j = j0 + u * jStep;
+			y[u] = Ybuf[(size_t)j * BD];
+			y[u] = y[u] + ((mu[u] - Mbuf[(size_t)j * BD]) / 2.0) * d;
+		}
+	}
+	if (LOGN) fexpN<U>(y, Ln);
+	else {
+#pragma unroll
+		for (int u = 0; u < U; u++) Ln[u] = y[u];
+	}
+#pragma unroll
+	for (int u = 0; u < U; u++) {
+		const int j = j0 + u * jStep;
+		if (q.hasCap) Ln[u] = jminE(Ln[u], q.cap);
+		Lcol[j * BD] = Ln[u];
+		if (MODE != 0) Ybuf[(size_t)j * BD] = y[u];
+		if (MODE == 2 && !CORRECTOR) Mbuf[(size_t)j * BD] = mu[u]; else r[u].xrow[p] = Ln[u];
+	}
 }
 
-template <int FT> __global__ void __launch_bounds__(128) eulerLmmKernel(LmmParams q, uint64_t P, const double* const* __restrict__ dW,
-		double* const* __restrict__ X, double* __restrict__ scratch) {
+// MODE 0: EULER_FUNCTIONAL (state = L in shared memory only).  MODE 1: EULER (Y carried in scratch).
+// MODE 2: PREDICTOR_CORRECTOR[_FUNCTIONAL] (Y and the predictor drift in scratch).
+template <int FT, bool LOGN, int MODE> __global__ void __launch_bounds__(128) eulerLmmKernel(LmmParams q, uint64_t P,
+		const double* const* __restrict__ dW, double* __restrict__ scratch) {
 	extern __shared__ double Lsh[];                       // [N][blockDim]
 	const int BD = blockDim.x, tid = threadIdx.x;
 	const int N = q.N, F = FT > 0 ? FT : q.F;
 	constexpr int FMAX = FT > 0 ? FT : 16;
-	const bool functional = (q.scheme == SCHEME_EULER_FUNCTIONAL || q.scheme == SCHEME_PC_FUNCTIONAL);
-	const bool pc = (q.scheme == SCHEME_PC || q.scheme == SCHEME_PC_FUNCTIONAL);
+	constexpr int U = FMB_LMM_U;
+	const bool functional = (MODE == 0) || (MODE == 2 && q.scheme == SCHEME_PC_FUNCTIONAL);
 	const bool spot = (q.measure == 0);
-	double* Ybuf = scratch + (size_t)blockIdx.x * 2 * N * BD;       // [N][BD]
-	double* Mbuf = Ybuf + (size_t)N * BD;                          // [N][BD]
-	const bool needY = pc || !functional;
+	double* Ybuf = scratch + (size_t)blockIdx.x * 2 * N * BD + tid;      // [N][BD], this thread's column
+	double* Mbuf = Ybuf + (size_t)N * BD;
+	double* Lcol = Lsh + tid;
 
 	const uint64_t tiles = (P + BD - 1) / BD;
 	for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
 		const uint64_t p = tile * BD + tid;
 		if (p >= P) continue;                             // no block-wide barriers below: every thread only touches its own column
 		for (int j = 0; j < N; j++) {
-			Lsh[j * BD + tid] = q.x0[j];
-			if (needY) Ybuf[(size_t)j * BD + tid] = q.y0[j];
+			Lcol[j * BD] = q.x0[j];
+			if (MODE != 0) Ybuf[(size_t)j * BD] = q.y0[j];
 		}
 		for (int t = 0; t < q.T; t++) {
 			const int first = q.firstLive[t];
@@ -192,49 +278,21 @@ template <int FT> __global__ void __launch_bounds__(128) eulerLmmKernel(LmmParam
 #pragma unroll
 			for (int k = 0; k < FMAX; k++) { w[k] = (k < F) ? dW[(size_t)t * F + k][p] : 0.0; S[k] = 0.0; }
 			const double d = q.dt[t];
-			const double* flt = q.fl + (size_t)t * N * F;
-			const double* hvt = q.hv + (size_t)t * N;
-			double* const* Xn = X + (size_t)(t + 1) * N;
-			const int jBeg = spot ? first : N - 1, jEnd = spot ? N : first - 1, jStep = spot ? 1 : -1;
-			// predictor (or the whole step for the Euler schemes)
-			for (int j = jBeg; j != jEnd; j += jStep) {
-				const double Lj = Lsh[j * BD + tid];
-				double a = 1.0 / (Lj * q.ratio[j] + q.invv[j]);
-				if (q.lognormal) a = a * Lj;
-				const double* flj = flt + (size_t)j * F;
-				double mu = lmmDriftTerm<FT>(q, flj, S, a, spot);
-				if (q.lognormal) mu = mu + hvt[j];
-				double y;
-				if (functional) y = (t == 0) ? q.ylog0[j] : (q.lognormal ? log(Lj) : Lj);
-				else y = Ybuf[(size_t)j * BD + tid];
-				y = y + mu * d;
-#pragma unroll
-				for (int k = 0; k < FMAX; k++) if (k < F) y = y + w[k] * flj[k];
-				double Ln = q.lognormal ? exp(y) : y;
-				if (q.hasCap) Ln = jminE(Ln, q.cap);
-				Lsh[j * BD + tid] = Ln;
-				if (needY) Ybuf[(size_t)j * BD + tid] = y;
-				if (pc) Mbuf[(size_t)j * BD + tid] = mu; else Xn[j][p] = Ln;
-			}
-			if (pc) {
-				// corrector: drift re-evaluated on the predicted rates (:292-314)
+			const double* rect = q.rec + (size_t)t * N * q.recStride;
+			const int live = N - first, jBeg = spot ? first : N - 1, jStep = spot ? 1 : -1;
+			int i = 0;
+			for (; i + U <= live; i += U)
+				lmmChunk<FT, LOGN, MODE, U, false>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p);
+			for (; i < live; i++)
+				lmmChunk<FT, LOGN, MODE, 1, false>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p);
+			if (MODE == 2) {
+				// corrector: drift re-evaluated on the predicted rates (EulerSchemeFromProcessModel.java:292-314)
 #pragma unroll
 				for (int k = 0; k < FMAX; k++) S[k] = 0.0;
-				for (int j = jBeg; j != jEnd; j += jStep) {
-					const double Lj = Lsh[j * BD + tid];
-					double a = 1.0 / (Lj * q.ratio[j] + q.invv[j]);
-					if (q.lognormal) a = a * Lj;
-					const double* flj = flt + (size_t)j * F;
-					double mu2 = lmmDriftTerm<FT>(q, flj, S, a, spot);
-					if (q.lognormal) mu2 = mu2 + hvt[j];
-					double y = Ybuf[(size_t)j * BD + tid];
-					y = y + ((mu2 - Mbuf[(size_t)j * BD + tid]) / 2.0) * d;
-					double Ln = q.lognormal ? exp(y) : y;
-					if (q.hasCap) Ln = jminE(Ln, q.cap);
-					Lsh[j * BD + tid] = Ln;
-					Ybuf[(size_t)j * BD + tid] = y;
-					Xn[j][p] = Ln;
-				}
+				for (i = 0; i + U <= live; i += U)
+					lmmChunk<FT, LOGN, MODE, U, true>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p);
+				for (; i < live; i++)
+					lmmChunk<FT, LOGN, MODE, 1, true>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p);
 			}
 		}
 	}
@@ -420,39 +478,42 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
 		size_t r = 0;
 		for (int t = 0; t < T; t++) for (int j = first_live[t]; j < N; j++) rows[(size_t)(t + 1) * N + j] = (double*)slab->base + (r++) * paths;
 	}
-	std::vector<double> hv((size_t)T * N), ratio(N), invv(N), x0(N), ylog0(N);
-	for (size_t i = 0; i < hv.size(); i++) hv[i] = variance[i] * -0.5;                      // :1187 addProduct(variance, -0.5)
+	std::vector<double> x0(N), ylog0(N);
+	const int FP = (F + 1) & ~1, RS = 4 + FP;
+	std::vector<double> rec((size_t)T * N * RS, 0.0);
 	for (int j = 0; j < N; j++) {
-		const double value = measure == 0 ? period_length[j] : -period_length[j];          // Scalar.of(+-periodLength).discount(...) :1149,:1167
-		ratio[j] = period_length[j] / value;
-		invv[j] = 1.0 / value;
 		double x = state_space == 1 ? std::exp(initial_state[j]) : initial_state[j];       // applyStateSpaceTransform :1199-1212 (host scalars at t=0)
 		if (!std::isinf(libor_cap)) x = (x != x) ? x : std::min(x, libor_cap);
 		x0[j] = x;
 		ylog0[j] = state_space == 1 ? std::log(x) : x;
 	}
+	for (int t = 0; t < T; t++) for (int j = 0; j < N; j++) {
+		double* r = &rec[((size_t)t * N + j) * RS];
+		const double value = measure == 0 ? period_length[j] : -period_length[j];          // Scalar.of(+-periodLength).discount(...) :1149,:1167
+		r[0] = period_length[j] / value;
+		r[1] = 1.0 / value;
+		r[2] = variance[(size_t)t * N + j] * -0.5;                                         // :1187 addProduct(variance, -0.5)
+		double* rowp = rows[(size_t)(t + 1) * N + j];
+		memcpy(&r[3], &rowp, sizeof(double*));
+		for (int k = 0; k < F; k++) r[4 + k] = factor_loading[((size_t)t * N + j) * F + k];
+	}
 	DeviceBlob blob;
 	const size_t oDt = blob.add(dt, T * sizeof(double));
-	const size_t oFl = blob.add(factor_loading, (size_t)T * N * F * sizeof(double));
-	const size_t oHv = blob.add(hv.data(), hv.size() * sizeof(double));
 	const size_t oFirst = blob.add(first_live, T * sizeof(int32_t));
-	const size_t oRatio = blob.add(ratio.data(), N * sizeof(double));
-	const size_t oInvv = blob.add(invv.data(), N * sizeof(double));
+	const size_t oRec = blob.add(rec.data(), rec.size() * sizeof(double));
 	const size_t oX0 = blob.add(x0.data(), N * sizeof(double));
 	const size_t oY0 = blob.add(initial_state, N * sizeof(double));
 	const size_t oYl = blob.add(ylog0.data(), N * sizeof(double));
 	const size_t oInc = blob.add(inc.data(), inc.size() * sizeof(double*));
-	const size_t oRows = blob.add(rows.data(), rows.size() * sizeof(double*));
 	int rc = blob.upload();
 	void* scratch = nullptr;
 	size_t scratchBytes = 0;
 	if (rc == FMB_OK && liveRows) {
 		LmmParams q;
-		q.scheme = scheme; q.measure = measure; q.lognormal = state_space; q.hasCap = std::isinf(libor_cap) ? 0 : 1; q.cap = libor_cap;
-		q.T = T; q.N = N; q.F = F;
-		q.dt = blob.at<double>(oDt); q.fl = blob.at<double>(oFl); q.hv = blob.at<double>(oHv); q.firstLive = blob.at<int>(oFirst);
-		q.ratio = blob.at<double>(oRatio); q.invv = blob.at<double>(oInvv); q.x0 = blob.at<double>(oX0); q.y0 = blob.at<double>(oY0);
-		q.ylog0 = blob.at<double>(oYl);
+		q.scheme = scheme; q.measure = measure; q.hasCap = std::isinf(libor_cap) ? 0 : 1; q.cap = libor_cap;
+		q.T = T; q.N = N; q.F = F; q.recStride = RS;
+		q.dt = blob.at<double>(oDt); q.firstLive = blob.at<int>(oFirst); q.rec = blob.at<double>(oRec);
+		q.x0 = blob.at<double>(oX0); q.y0 = blob.at<double>(oY0); q.ylog0 = blob.at<double>(oYl);
 		// block size: the shared-memory column store is 8*N bytes per thread
 		int BD = 128;
 		while (BD > 32 && (size_t)BD * N * sizeof(double) > 200 * 1024) BD >>= 1;
@@ -462,21 +523,25 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
 			const int perSm = (int)std::max<size_t>(1, std::min<size_t>(16, (220 * 1024) / std::max<size_t>(smem, 1)));
 			const uint64_t tiles = (paths + BD - 1) / BD;
 			const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * perSm, tiles));
-			const bool needScratch = (scheme != SCHEME_EULER_FUNCTIONAL);
-			scratchBytes = needScratch ? (size_t)grid * 2 * N * BD * sizeof(double) : 16;
+			const int mode = scheme == SCHEME_EULER_FUNCTIONAL ? 0 : (scheme == SCHEME_EULER ? 1 : 2);
+			scratchBytes = mode != 0 ? (size_t)grid * 2 * N * BD * sizeof(double) : 16;
 			rc = poolAlloc(scratchBytes, &scratch);
 			if (rc == FMB_OK) {
 				auto launch = [&](auto kernel) {
 					cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-					kernel<<<grid, BD, smem, c.stream>>>(q, paths, blob.at<const double*>(oInc), (double* const*)blob.at<double*>(oRows), (double*)scratch);
+					kernel<<<grid, BD, smem, c.stream>>>(q, paths, blob.at<const double*>(oInc), (double*)scratch);
 				};
+#define LMM_MODE(FTV, LOGNV) \
+				switch (mode) { case 0: launch(eulerLmmKernel<FTV, LOGNV, 0>); break; case 1: launch(eulerLmmKernel<FTV, LOGNV, 1>); break; default: launch(eulerLmmKernel<FTV, LOGNV, 2>); break; }
+#define LMM_LOGN(FTV) if (state_space == 1) { LMM_MODE(FTV, true) } else { LMM_MODE(FTV, false) }
 				switch (F) {
-				case 1: launch(eulerLmmKernel<1>); break;
-				case 2: launch(eulerLmmKernel<2>); break;
-				case 3: launch(eulerLmmKernel<3>); break;
-				case 4: launch(eulerLmmKernel<4>); break;
-				default: launch(eulerLmmKernel<0>); break;
+				case 1: LMM_LOGN(1) break;
+				case 2: LMM_LOGN(2) break;
+				case 3: LMM_LOGN(3) break;
+				default: LMM_LOGN(0) break;
 				}
+#undef LMM_LOGN
+#undef LMM_MODE
 				rc = launchCheck("euler_lmm");
 			}
 		}
