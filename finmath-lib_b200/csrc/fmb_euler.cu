@@ -31,6 +31,10 @@ __device__ __forceinline__ double jmaxE(double a, double b) {
 #define FMB_LMM_U 2          // live rates processed together per thread (ILP); 2 measured best on B200 (profiles/r01_notes.md)
 #endif
 
+#ifndef FMB_LMM_MINB
+#define FMB_LMM_MINB 5
+#endif
+
 enum { SCHEME_EULER = 0, SCHEME_PC = 1, SCHEME_EULER_FUNCTIONAL = 2, SCHEME_PC_FUNCTIONAL = 3 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -173,17 +177,36 @@ template <int FT> struct LmmRec {
 // U consecutive live rates of one path at once (i = position in processing order; j = first+i for the spot measure,
 // N-1-i for the terminal measure).  Per rate the operations and their order are exactly those of the scalar recipe; the
 // only cross-rate dependency is the running factor sum S, so the U log / exp / reciprocal chains overlap (ILP U).
-template <int FT, bool LOGN, int MODE, int U, bool CORRECTOR>
+template <int FT, bool LOGN, int MODE, int U, bool CORRECTOR, bool PARTIAL>
 __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __restrict__ rect, int j0, int jStep, int BD, int F, bool spot, bool functional,
-		bool firstStep, double d, const double* w, double* S, double* Lcol, double* Ybuf, double* Mbuf, uint64_t p) {
+		bool firstStep, double d, const double* w, double* S, double* Lcol, double* Ybuf, double* Mbuf, uint64_t p, int cnt) {
+	// PARTIAL: only the first cnt (< U) rates are real; the others recompute rate cnt-1 and are masked out of S and of every store,
+	// so a short remainder costs one chunk latency instead of cnt sequential ones.
 	constexpr int FMAX = FT > 0 ? FT : 16;
 	LmmRec<FT> r[U];
 	double L[U], a[U], mu[U], y[U], Ln[U];
 #pragma unroll
+	int jj[U];
+#pragma unroll
 	for (int u = 0; u < U; u++) {
-		const int j = j0 + u * jStep;
-		r[u].load(rect + (size_t)j * q.recStride, F);
-		L[u] = Lcol[j * BD];
+		jj[u] = j0 + ((PARTIAL && u >= cnt) ? cnt - 1 : u) * jStep;
+		r[u].load(rect + (size_t)jj[u] * q.recStride, F);
+		L[u] = Lcol[jj[u] * BD];
+	}
+	// the logarithms depend on the state only: start them before the drift needs the records
+	if (!CORRECTOR) {
+		if (MODE == 1 || (MODE == 2 && !functional)) {
+#pragma unroll
+			for (int u = 0; u < U; u++) y[u] = Ybuf[(size_t)jj[u] * BD];
+		} else if (firstStep) {
+#pragma unroll
+			for (int u = 0; u < U; u++) y[u] = q.ylog0[jj[u]];
+		} else if (LOGN) {
+			flogN<U>(L, y);
+		} else {
+#pragma unroll
+			for (int u = 0; u < U; u++) y[u] = L[u];
+		}
 	}
 #pragma unroll
 	for (int u = 0; u < U; u++) {
@@ -192,14 +215,15 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 	}
 #pragma unroll
 	for (int u = 0; u < U; u++) {
-		if (spot) {
+		const bool valid = !PARTIAL || u < cnt;
+		if (spot && valid) {
 #pragma unroll
 			for (int k = 0; k < FMAX; k++) if (k < F) S[k] = S[k] + a[u] * r[u].fl[k];
 		}
 		double m = S[0] * r[u].fl[0] + 0.0;
 #pragma unroll
 		for (int k = 1; k < FMAX; k++) if (k < F) m = m + S[k] * r[u].fl[k];
-		if (!spot) {
+		if (!spot && valid) {
 #pragma unroll
 			for (int k = 0; k < FMAX; k++) if (k < F) S[k] = S[k] + a[u] * r[u].fl[k];
 		}
@@ -207,18 +231,6 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 		mu[u] = m;
 	}
 	if (!CORRECTOR) {
-		if (MODE == 1 || (MODE == 2 && !functional)) {
-#pragma unroll
-			for (int u = 0; u < U; u++) y[u] = Ybuf[(size_t)(j0 + u * jStep) * BD];
-		} else if (firstStep) {
-#pragma unroll
-			for (int u = 0; u < U; u++) y[u] = q.ylog0[j0 + u * jStep];
-		} else if (LOGN) {
-			flogN<U>(L, y);
-		} else {
-#pragma unroll
-			for (int u = 0; u < U; u++) y[u] = L[u];
-		}
 #pragma unroll
 		for (int u = 0; u < U; u++) {
 			y[u] = y[u] + mu[u] * d;
@@ -228,9 +240,8 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 	} else {
 #pragma unroll
 		for (int u = 0; u < U; u++) {
-			const int j = j0 + u * jStep;
-			y[u] = Ybuf[(size_t)j * BD];
-			y[u] = y[u] + ((mu[u] - Mbuf[(size_t)j * BD]) / 2.0) * d;
+			y[u] = Ybuf[(size_t)jj[u] * BD];
+			y[u] = y[u] + ((mu[u] - Mbuf[(size_t)jj[u] * BD]) / 2.0) * d;
 		}
 	}
 	if (LOGN) fexpN<U>(y, Ln);
@@ -240,7 +251,8 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 	}
 #pragma unroll
 	for (int u = 0; u < U; u++) {
-		const int j = j0 + u * jStep;
+		if (PARTIAL && u >= cnt) continue;
+		const int j = jj[u];
 		if (q.hasCap) Ln[u] = jminE(Ln[u], q.cap);
 		Lcol[j * BD] = Ln[u];
 		if (MODE != 0) Ybuf[(size_t)j * BD] = y[u];
@@ -250,7 +262,7 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 
 // MODE 0: EULER_FUNCTIONAL (state = L in shared memory only).  MODE 1: EULER (Y carried in scratch).
 // MODE 2: PREDICTOR_CORRECTOR[_FUNCTIONAL] (Y and the predictor drift in scratch).
-template <int FT, bool LOGN, int MODE> __global__ void __launch_bounds__(128) eulerLmmKernel(LmmParams q, uint64_t P,
+template <int FT, bool LOGN, int MODE> __global__ void __launch_bounds__(128, FMB_LMM_MINB) eulerLmmKernel(LmmParams q, uint64_t P,
 		const double* const* __restrict__ dW, double* __restrict__ scratch) {
 	extern __shared__ double Lsh[];                       // [N][blockDim]
 	const int BD = blockDim.x, tid = threadIdx.x;
@@ -271,28 +283,36 @@ template <int FT, bool LOGN, int MODE> __global__ void __launch_bounds__(128) eu
 			Lcol[j * BD] = q.x0[j];
 			if (MODE != 0) Ybuf[(size_t)j * BD] = q.y0[j];
 		}
+		// Brownian increments come from HBM (~1 us away): fetch step t+1 while step t computes
+		double wNext[FMAX];
+#pragma unroll
+		for (int k = 0; k < FMAX; k++) wNext[k] = (k < F) ? dW[k][p] : 0.0;
 		for (int t = 0; t < q.T; t++) {
 			const int first = q.firstLive[t];
-			if (first >= N) continue;
 			double w[FMAX], S[FMAX];
 #pragma unroll
-			for (int k = 0; k < FMAX; k++) { w[k] = (k < F) ? dW[(size_t)t * F + k][p] : 0.0; S[k] = 0.0; }
+			for (int k = 0; k < FMAX; k++) { w[k] = wNext[k]; S[k] = 0.0; }
+			if (t + 1 < q.T) {
+#pragma unroll
+				for (int k = 0; k < FMAX; k++) if (k < F) wNext[k] = dW[(size_t)(t + 1) * F + k][p];
+			}
+			if (first >= N) continue;
 			const double d = q.dt[t];
 			const double* rect = q.rec + (size_t)t * N * q.recStride;
 			const int live = N - first, jBeg = spot ? first : N - 1, jStep = spot ? 1 : -1;
 			int i = 0;
 			for (; i + U <= live; i += U)
-				lmmChunk<FT, LOGN, MODE, U, false>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p);
-			for (; i < live; i++)
-				lmmChunk<FT, LOGN, MODE, 1, false>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p);
+				lmmChunk<FT, LOGN, MODE, U, false, false>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p, U);
+			if (i < live)
+				lmmChunk<FT, LOGN, MODE, U, false, true>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p, live - i);
 			if (MODE == 2) {
 				// corrector: drift re-evaluated on the predicted rates (EulerSchemeFromProcessModel.java:292-314)
 #pragma unroll
 				for (int k = 0; k < FMAX; k++) S[k] = 0.0;
 				for (i = 0; i + U <= live; i += U)
-					lmmChunk<FT, LOGN, MODE, U, true>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p);
-				for (; i < live; i++)
-					lmmChunk<FT, LOGN, MODE, 1, true>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p);
+					lmmChunk<FT, LOGN, MODE, U, true, false>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p, U);
+				if (i < live)
+					lmmChunk<FT, LOGN, MODE, U, true, true>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p, live - i);
 			}
 		}
 	}

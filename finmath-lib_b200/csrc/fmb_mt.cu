@@ -294,61 +294,105 @@ __global__ void uniformsFromWordsKernel(const uint32_t* __restrict__ w, double* 
 // ---------------------------------------------------------------------------------------------------------------
 static const int BM_THREADS = 256;
 static const int RING = 2048;
+static const int TAILQ = 2048;        // deferred tail draws per block (p and tile slot), drained densely
+
+// Tail draws (|u - 0.5| > 0.425, 15 % of all) cost ~3x a central draw (log, sqrt, a second rational) and would make
+// almost every warp execute both branches.  They are parked in a shared-memory queue and evaluated by full warps.
+__device__ __forceinline__ void bmDrainTails(const double* __restrict__ qP, const uint32_t* __restrict__ qSlot, uint32_t count,
+		double* __restrict__ tile, const double* __restrict__ sq, uint32_t nPad, int tid) {
+	for (uint32_t i = tid; i < count; i += BM_THREADS) {
+		const double p = qP[i];
+		const uint32_t slot = qSlot[i];
+		tile[slot] = as241Tail(p, p - 0.5) * sq[slot / nPad];
+	}
+}
 
 __global__ void __launch_bounds__(BM_THREADS) bmGenerateKernel(const uint32_t* __restrict__ states, double* __restrict__ out,
 		uint64_t P, uint32_t TF, uint32_t ppb, uint32_t tileN, uint32_t nPad, const double* __restrict__ sqrtDtPerColumn) {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
 	uint32_t* ring = reinterpret_cast<uint32_t*>(smemRaw);
-	double* sq = reinterpret_cast<double*>(smemRaw + RING * sizeof(uint32_t));
+	double* qP = reinterpret_cast<double*>(smemRaw + RING * sizeof(uint32_t));
+	uint32_t* qSlot = reinterpret_cast<uint32_t*>(qP + TAILQ);
+	double* sq = reinterpret_cast<double*>(qSlot + TAILQ);
 	double* tile = sq + ((TF + 1) & ~1u);
+	__shared__ uint32_t qCount;
 	const int tid = threadIdx.x;
 	const int lane = tid & 31, warp = tid >> 5;
 
 	for (int i = tid; i < MT_N; i += BM_THREADS) ring[i] = states[(size_t)blockIdx.x * MT_N + i];
 	for (uint32_t i = tid; i < TF; i += BM_THREADS) sq[i] = sqrtDtPerColumn[i];
+	if (tid == 0) qCount = 0;
 	__syncthreads();
 
-	uint64_t genEnd = MT_N;         // raw words [.., genEnd) exist in the ring
-	uint64_t cpos = MT_N;           // raw index of the next unconsumed word
+	// ring positions (mod RING) of the next raw word to generate and of the next unconsumed word (always even), and their distance
+	uint32_t gpos = MT_N, cpos = MT_N;
+	int avail = 0;
 	const uint64_t pBeg = (uint64_t)blockIdx.x * ppb;
 	const uint64_t pEnd = min(P, pBeg + (uint64_t)ppb);
+	// (path in tile, column) of this thread's draw, advanced by BM_THREADS draws per iteration without divisions
+	const uint32_t stepP = BM_THREADS / TF, stepC = BM_THREADS % TF;
 
 	for (uint64_t p0 = pBeg; p0 < pEnd; p0 += tileN) {
 		const uint32_t n = (uint32_t)min((uint64_t)tileN, pEnd - p0);
 		const uint32_t U = n * TF;
+		uint32_t pl = (uint32_t)tid / TF, c = (uint32_t)tid % TF, it = 0;
 		for (uint32_t u0 = 0; u0 < U; u0 += BM_THREADS) {
 			const uint32_t need = min((uint32_t)BM_THREADS, U - u0);
-			while (genEnd < cpos + 2ull * need) {
+			while (avail < (int)(2 * need)) {
 				if (tid < 227) {
-					const uint64_t j = genEnd + tid;
+					const uint32_t j = gpos + tid;
 					ring[j & (RING - 1)] = ring[(j - 227) & (RING - 1)] ^ mtTwist(ring[(j - MT_N) & (RING - 1)], ring[(j - MT_N + 1) & (RING - 1)]);
 				}
-				genEnd += 227;
+				gpos = (gpos + 227) & (RING - 1);
+				avail += 227;
 				__syncthreads();
 			}
 			if ((uint32_t)tid < need) {
-				const uint64_t j = cpos + 2ull * tid;
-				const uint32_t w0 = mtTemper(ring[j & (RING - 1)]);
-				const uint32_t w1 = mtTemper(ring[(j + 1) & (RING - 1)]);
-				const double z = inverseCumulativeNormal(mtUniform(w0, w1));
-				const uint32_t ul = u0 + tid;
-				const uint32_t pl = ul / TF;
-				const uint32_t c = ul - pl * TF;
-				tile[c * nPad + pl] = z * sq[c];
+				const uint32_t j = (cpos + 2 * tid) & (RING - 1);     // even, pair never wraps
+				const uint2 ww = *reinterpret_cast<const uint2*>(ring + j);
+				const double u = mtUniform(mtTemper(ww.x), mtTemper(ww.y));
+				const double q = u - 0.5;
+				const uint32_t slot = c * nPad + pl;
+				if (fabs(q) <= 0.425) {
+					tile[slot] = as241Central(q) * sq[c];
+				} else {
+					const uint32_t k = atomicAdd(&qCount, 1u);
+					qP[k] = u;
+					qSlot[k] = slot;
+				}
 			}
-			cpos += 2ull * need;
+			cpos = (cpos + 2 * need) & (RING - 1);
+			avail -= (int)(2 * need);
+			pl += stepP; c += stepC;
+			if (c >= TF) { c -= TF; pl++; }
+			// every 4th batch: make sure the queue keeps room for the next four (at most 4 * BM_THREADS new tails)
+			if ((++it & 3u) == 0) {
+				__syncthreads();
+				if (qCount > TAILQ - 5 * BM_THREADS) {
+					bmDrainTails(qP, qSlot, qCount, tile, sq, nPad, tid);
+					__syncthreads();
+					if (tid == 0) qCount = 0;
+					__syncthreads();
+				}
+			}
 		}
 		__syncthreads();
+		bmDrainTails(qP, qSlot, qCount, tile, sq, nPad, tid);
+		__syncthreads();
+		if (tid == 0) qCount = 0;
 		if (n >= 32) {
-			for (uint32_t c = warp; c < TF; c += BM_THREADS / 32) {
-				double* dst = out + (size_t)c * P + p0;
-				const double* srcRow = tile + c * nPad;
-				for (uint32_t i = lane; i < n; i += 32) dst[i] = srcRow[i];
+			double* dst = out + (size_t)warp * P + p0 + lane;
+			const double* srcRow = tile + warp * nPad + lane;
+			for (uint32_t cc = warp; cc < TF; cc += BM_THREADS / 32) {
+#pragma unroll 4
+				for (uint32_t i = 0; i + lane < n; i += 32) dst[i] = srcRow[i];
+				dst += (size_t)(BM_THREADS / 32) * P;
+				srcRow += (BM_THREADS / 32) * nPad;
 			}
 		} else {
 			for (uint32_t idx = tid; idx < U; idx += BM_THREADS) {
-				const uint32_t c = idx / n, i = idx - c * n;
-				out[(size_t)c * P + p0 + i] = tile[c * nPad + i];
+				const uint32_t cc = idx / n, i = idx - cc * n;
+				out[(size_t)cc * P + p0 + i] = tile[cc * nPad + i];
 			}
 		}
 		__syncthreads();
@@ -538,7 +582,7 @@ int fmb_bm_generate(int32_t seed, int T, int F, uint64_t paths, uint64_t path_of
 	if (TF > 24000) { setError("bm_generate: T*F = %llu exceeds the shared-memory tile limit (24000)", (unsigned long long)TF); return FMB_EUNSUPPORTED; }
 
 	// shared-memory tile: [TF][nPad] doubles + ring + per-column sqrt(dt)
-	const size_t fixed = RING * sizeof(uint32_t) + ((TF + 1) & ~1ull) * sizeof(double);
+	const size_t fixed = RING * sizeof(uint32_t) + TAILQ * (sizeof(double) + sizeof(uint32_t)) + ((TF + 1) & ~1ull) * sizeof(double);
 	// two blocks per SM when a >= 4-path tile fits in half of the 227 KB, else one block with the whole of it
 	uint32_t tileN = 0;
 	const size_t budgets[2] = { 112 * 1024, 224 * 1024 };
