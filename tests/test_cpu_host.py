@@ -1,0 +1,210 @@
+"""-m "not gpu": the C-ABI library loads and exports every symbol of include/finmath_b200.h, fails loudly without a GPU
+(no CPU fallback), and the host-side logic (time grid, Scalar, dispatch of deterministic values, jump-ahead polynomial
+arithmetic, sharding arithmetic, device exp/log compiled for the host) is correct."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    header = open(os.path.join(ROOT, "include", "finmath_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(fmb_\w+)\s*\(", header, flags=re.M))
+    assert len(declared) >= 40
+    lib = C.CDLL(pkg.native.LIB_PATH)
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert declared == set(pkg.native.PROTOTYPES.keys())          # the Python binding covers the whole header, nothing else
+
+
+def test_no_cpu_fallback_without_a_gpu(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    nv = pkg.native
+    with pytest.raises(nv.NoDeviceError):
+        nv.init(0)
+    with pytest.raises(nv.NoDeviceError):
+        pkg.RandomVariableCuda(0.0, [1.0, 2.0, 3.0])
+    td = pkg.TimeDiscretizationFromArray(0.0, 4, 0.25)
+    with pytest.raises(nv.NoDeviceError):
+        pkg.BrownianMotionCuda(td, 1, 100, 3141).getBrownianIncrement(0, 0)
+    # deterministic values never touch the device (host scalars, like the reference's Scalar branch)
+    assert pkg.RandomVariableCuda(0.0, 2.0).mult(3.0).add(pkg.Scalar(1.0)).doubleValue() == 7.0
+
+
+def test_product_path_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under finmath-lib_b200/ may reference it."""
+    pkg_dir = os.path.join(ROOT, "finmath-lib_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".java", ".c")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "liboracle" not in text and "import oracle" not in text and "orc_" not in text, os.path.join(dirpath, f)
+
+
+def test_jump_ahead_polynomial_arithmetic_on_host(pkg, orc):
+    """x^J mod phi applied as a GF(2) combination of shifted raw words == the sequentially advanced state."""
+    lib = pkg.native.load()
+    st = np.empty(624, dtype=np.uint32)
+    w, g = C.c_int(), C.c_int()
+    lib.fmb_test_host_jump.argtypes = [C.c_int64, C.c_uint64, pkg.native.c_u32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    assert lib.fmb_test_host_jump(3141, 0, st.ctypes.data_as(pkg.native.c_u32p), C.byref(w), C.byref(g)) == 0
+    assert w.value == 135 and g.value >= 64                      # weight of the MT19937 characteristic polynomial
+    for seed, J in [(3141, 1), (3141, 624), (-1, 12345), (53252, 240 * 13514), (3141, 2 * 40 * 3 * 500_000)]:
+        assert lib.fmb_test_host_jump(seed, J, st.ctypes.data_as(pkg.native.c_u32p), None, None) == 0
+        raw = list(int(v) for v in st)
+        for k in range(624, 634):                               # ten outputs generated from the jumped state
+            y = (raw[k - 624] & 0x80000000) | (raw[k - 623] & 0x7fffffff)
+            raw.append(raw[k - 227] ^ (y >> 1) ^ (0x9908b0df if y & 1 else 0))
+        out = []
+        for y in raw[624:]:
+            y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680; y ^= (y << 15) & 0xefc60000; y ^= y >> 18
+            out.append(y & 0xffffffff)
+        assert out == [int(v) for v in orc.mt_words(seed, J, 10)], (seed, J)
+
+
+def test_time_discretization_mirror_equals_oracle(pkg, orc):
+    for args in [(0.0, 100, 0.05), (0.0, 1000, 0.005), (0.0, 40, 0.5), (0.0, 200, 0.1)]:
+        td = pkg.TimeDiscretizationFromArray(*args)
+        assert np.array_equal(td.times, orc.time_discretization(*args))
+        for t in (0.0, 0.3, 0.35, 5.0, 100.0, -1.0):
+            assert td.getTimeIndex(t) == orc.time_index(td.times, t)
+    td = pkg.TimeDiscretizationFromArray([0.5, 0.0, 0.5, 0.25])
+    assert td.times.tolist() == [0.0, 0.25, 0.5] and td.getNumberOfTimeSteps() == 2 and td.getTimeStep(1) == 0.25
+
+
+def test_scalar_and_deterministic_dispatch(pkg):
+    S, G, CPU = pkg.Scalar, pkg.RandomVariableCuda, pkg.RandomVariableFromDoubleArray
+    a = S(2.0)
+    assert a.add(S(3.0)).doubleValue() == 5.0 and a.sub(S(3.0)).doubleValue() == -1.0 and a.div(S(4.0)).doubleValue() == 0.5
+    assert a.discount(S(0.05), 0.5).doubleValue() == 1.0 / (0.05 * (0.5 / 2.0) + 1.0 / 2.0)       # Scalar.java:320-328
+    assert a.accrue(S(0.05), 0.5).doubleValue() == 0.05 * (0.5 * 2.0) + 2.0
+    assert S(0.0).discount(S(0.05), 0.5).doubleValue() == 0.0
+    assert a.addProduct(S(3.0), 4.0).doubleValue() == 14.0 and a.choose(S(1.0), S(-1.0)).doubleValue() == 1.0
+    assert a.getFiltrationTime() == float("-inf") and a.getTypePriority() == 0
+    d = G(1.5, 2.0)
+    r = d.add(S(1.0))                                                            # deterministic GPU value: host arithmetic, keeps its time
+    assert isinstance(r, G) and r.isDeterministic() and r.doubleValue() == 3.0 and r.getFiltrationTime() == 1.5
+    assert d.addProduct(G(2.5, 3.0), G(0.5, 4.0)).getFiltrationTime() == 2.5 and d.addProduct(S(3.0), 4.0).doubleValue() == 14.0
+    assert d.accrue(S(0.1), 0.5).doubleValue() == 2.0 * (1.0 + 0.1 * 0.5) and d.discount(S(0.1), 0.5).doubleValue() == 2.0 / (1.0 + 0.1 * 0.5)
+    assert CPU(1.0).mult(d).doubleValue() == 2.0 and isinstance(CPU(1.0).mult(d), G)         # priority 2 wins over the CPU type
+    assert d.getAverage() == 2.0 and d.getVariance() == 0.0 and d.getStandardError() == 0.0 and d.getQuantile(0.3) == 2.0
+    assert d.pow(0.5).doubleValue() == 2.0 ** 0.5 and d.cap(1.0).doubleValue() == 1.0 and d.floor(3.0).doubleValue() == 3.0
+    assert np.isnan(G(0.0, float("nan")).cap(1.0).doubleValue())
+    assert d.getHistogram([1.0, 3.0]).tolist() == [1.0, 0.0, 1.0]                        # deterministic branch :505-517
+    assert d.invert().doubleValue() == 0.5 and G(0.0, 0.0).invert().doubleValue() == float("inf")
+
+
+def test_models_host_tables(pkg):
+    from common import lmm_setup
+    s = lmm_setup(pkg)
+    fm = s["factor_matrix"]
+    assert fm.shape == (40, 3)
+    assert np.allclose(np.sum(fm * fm, axis=1), 1.0, atol=1e-12)             # rows re-normalised by the factor reduction
+    assert np.all(fm[0] * np.array([1, 1, 1]) != 0) and fm[0, 0] > 0          # sign convention: first entry positive
+    fl, var = s["cov"].getFactorLoadingTable()
+    assert fl.shape == (40, 40, 3) and np.all(fl[5, :6] == 0.0) and np.all(fl[5, 6:] != 0.0)   # fixed rates have no volatility
+    assert var[3, 10] == s["sigma"][3, 10] * s["sigma"][3, 10] * 1.0
+    model = pkg.LIBORMarketModelFromCovarianceModel.of(s["tenor"], None, s["L0"], s["df"], None, s["cov"], None, {"measure": "SPOT"})
+    assert [model._first(t) for t in (0.0, 0.5, 0.75, 19.5)] == [1, 2, 2, 40]
+
+
+def test_dd_merge_and_local_shard(pkg):
+    from finmath_lib_b200.sharding import dd_merge, ShardContext
+    h, l = dd_merge(1.0, 1e-20, 1e-16, 3e-33)
+    assert h == 1.0000000000000002 or h == 1.0
+    assert abs((h + l) - (1.0 + 1e-16)) < 1e-30
+    sc = ShardContext(1, 4)
+    assert sc.local_range(10) == (2, 5) and [ShardContext(r, 4).local_range(10) for r in range(4)] == [(0, 2), (2, 5), (5, 7), (7, 10)]
+    assert pkg.LOCAL.sum_dd(1.0, 2.0) == (1.0, 2.0) and pkg.LOCAL.global_count(7) == 7
+
+
+def test_device_exp_log_accuracy_on_host(tmp_path):
+    """fmb_math.cuh (the exp / log of every kernel) compiled for the host and measured against mpmath: < 1 ulp."""
+    import mpmath as mp
+    so = tmp_path / "libshim.so"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-mfma", "-o", str(so),
+                           os.path.join(ROOT, "tests", "host_math_shim.cpp")])
+    L = C.CDLL(str(so))
+    dp = C.POINTER(C.c_double)
+
+    def run(fn, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        getattr(L, fn)(x.ctypes.data_as(dp), y.ctypes.data_as(dp), C.c_long(x.size))
+        return y
+
+    mp.mp.dps = 40
+    rng = np.random.default_rng(1)
+
+    def max_ulp(y, x, f):
+        worst = 0.0
+        for yi, xi in zip(y, x):
+            t = f(mp.mpf(float(xi)))
+            worst = max(worst, float(abs(mp.mpf(float(yi)) - t) / mp.mpf(float(np.spacing(abs(float(t)))))))
+        return worst
+
+    xe = np.concatenate([rng.uniform(-12, 12, 4000), rng.uniform(-700, 700, 1000), rng.uniform(-1e-3, 1e-3, 500)])
+    assert max_ulp(run("shim_exp", xe), xe, mp.exp) < 1.0
+    assert np.array_equal(run("shim_exp", xe), run("shim_exp2", xe))
+    xl = np.concatenate([np.exp(rng.uniform(-12, 12, 4000)), rng.uniform(0.5, 2.0, 2000), np.exp(rng.uniform(-700, 700, 1000))])
+    assert max_ulp(run("shim_log", xl), xl, mp.log) < 0.8
+    assert np.array_equal(run("shim_log", xl), run("shim_log2", xl))
+    sp = np.array([0.0, -1.0, np.inf, np.nan, 5e-324, 1.0])
+    got = run("shim_log", sp)
+    assert got[0] == -np.inf and np.isnan(got[1]) and got[2] == np.inf and np.isnan(got[3]) and abs(got[4] + 744.4400719213812) < 1e-12 and got[5] == 0.0
+    se = np.array([0.0, 709.79, -745.2, -746.0, -720.0, np.inf, -np.inf, np.nan])
+    ge = run("shim_exp", se)
+    assert ge[0] == 1.0 and ge[1] == np.inf and ge[3] == 0.0 and abs(ge[4] / 2.03223080e-313 - 1) < 1e-6 and ge[5] == np.inf and ge[6] == 0.0 and np.isnan(ge[7])
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["FMB_ROOT"])
+import numpy as np
+import torch.distributed as dist
+import __graft_entry__ as graft
+pkg = graft.load_package()
+shard = pkg.from_environment(backend="gloo")
+assert shard.world == 2
+n = 1001
+lo, hi = shard.local_range(n)
+x = np.linspace(-1.0, 3.0, n) ** 3
+# what RandomVariableCuda.getAverage does across shards: per-rank double-double partial -> all_gather -> merge in rank order
+local_hi = float(np.sum(x[lo:hi])); local_lo = 0.0
+H, L = shard.sum_dd(local_hi, local_lo)
+tot = shard._all_gather([local_hi])[:, 0]
+assert H + L == tot[0] + tot[1]
+assert shard.global_count(hi - lo) == n
+Hm, Lm = shard.sum_dd_many(np.array([1.0 + shard.rank, 2.0]), np.array([0.0, 1e-20]))
+assert Hm.tolist() == [3.0, 4.0]
+assert shard.min(float(shard.rank)) == 0.0 and shard.max(float(shard.rank)) == 1.0
+g = shard.gather(x[lo:hi])
+assert np.array_equal(g, x)
+# every rank holds identical bits
+allH = shard._all_gather([H, L])
+assert allH[0].tolist() == allH[1].tolist()
+bm = pkg.BrownianMotionCuda(pkg.TimeDiscretizationFromArray(0.0, 4, 0.5), 3, 1001, 3141, shard=shard)
+assert bm.getPathRange() == (lo, hi) and bm.getNumberOfLocalPaths() == hi - lo
+dist.barrier()
+dist.destroy_process_group()
+print("rank", shard.rank, "ok")
+'''
+
+
+def test_sharding_collectives_world_size_2_gloo(tmp_path):
+    """N > 1 host logic on CPU: two processes, gloo backend, 127.0.0.1 rendezvous."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, FMB_ROOT=ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout

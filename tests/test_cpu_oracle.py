@@ -1,0 +1,156 @@
+"""-m "not gpu": pins the oracle (the checker of the GPU tests) against the committed golden fixtures and against the
+reference tests' own exact identities / closed-form tolerances.  Fixtures: tests/golden/mt_as241.json (make_golden.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from common import rel_err
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mt_as241.json")))
+
+
+def test_mt19937_public_known_answer(orc):
+    assert [int(v) for v in orc.mt_words_key(GOLDEN["mt_kat_key"], 8)] == GOLDEN["mt_kat_words"]
+
+
+@pytest.mark.parametrize("seed", sorted(GOLDEN["seeds"].keys(), key=int))
+def test_mt19937_seeding_and_doubles(orc, seed):
+    g = GOLDEN["seeds"][seed]
+    s = int(seed)
+    assert [int(v) for v in orc.mt_words(s, 0, 8)] == g["words_0_8"]
+    assert [int(v) for v in orc.mt_words(s, 1990, 10)] == g["words_1990_2000"]          # across three state refreshes
+    assert list(orc.mt_uniforms(s, 0, 4)) == g["uniforms_0_4"]                            # 26+26 bit doubles, bit-exact
+
+
+def test_mt_skip_equals_sequential(orc):
+    full = orc.mt_words(3141, 0, 5000)
+    for off in (1, 623, 624, 625, 1247, 4000):
+        assert np.array_equal(orc.mt_words(3141, off, 100), full[off:off + 100])
+    raw = orc.mt_raw_sequence(3141, 2000)
+    # tempering of the raw recurrence reproduces the output stream (output i = temper(raw[624 + i]))
+    y = raw[624:1624].astype(np.uint64)
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680; y ^= (y << 15) & 0xefc60000; y ^= y >> 18
+    assert np.array_equal((y & 0xffffffff).astype(np.uint32), full[:1000])
+
+
+def test_as241_against_independent_values(orc):
+    p = np.array([e["p"] for e in GOLDEN["icdf"]])
+    z = orc.icdf(p)
+    for e, v in zip(GOLDEN["icdf"], z):
+        assert abs(v - e["z"]) <= 2e-15 * max(1.0, abs(e["z"])), e
+    assert orc.icdf([0.0])[0] == 0.0 and orc.icdf([1.0])[0] == 0.0       # quirk NormalDistribution.java:141-143
+    assert orc.icdf([0.5])[0] == 0.0
+    # symmetry and monotonicity on a grid
+    g = np.linspace(1e-6, 1 - 1e-6, 20001)
+    zg = orc.icdf(g)
+    assert np.all(np.diff(zg) > 0) and rel_err(zg, -zg[::-1], scale=1e-3) < 1e-9
+
+
+def test_time_discretization_tick_rounding(orc):
+    for e in GOLDEN["tick_rounding"]:
+        t = orc.time_discretization_from_array([0.0, e["t"]])
+        assert t[-1] == e["rounded"], e
+    td = orc.time_discretization(0.0, 10, 0.1)
+    assert td.size == 11 and td[1] == 0.09999999999999999
+    assert orc.time_index(td, 0.3) == 3 and orc.time_index(td, 0.35) == -5 and orc.time_index(td, 5.0) == -12
+    fine = orc.time_discretization(0.0, 1000, 0.005)
+    steps = np.unique(np.round(np.diff(fine) * 8760))
+    assert set(steps) <= {43.0, 44.0}                                      # 0.005y = 43.8 ticks -> a 44/44/.../43 pattern
+    assert orc.time_discretization_from_array([0.5, 0.0, 0.5, 0.25]).tolist() == [0.0, 0.25, 0.5]   # sorted, de-duplicated
+
+
+def test_randomvariable_reference_identities(orc):
+    """T/montecarlo/RandomVariableTest.java:53-142 on the oracle's element-wise semantics."""
+    x = np.array([3.0, 1.0, 0.0, 2.0, 4.0, 1.0 / 3.0])
+    assert np.array_equal(orc.rv_unary(1, x), orc.rv_unary(18, x, 0.5))     # sqrt == pow(0.5), tolerance 0.0
+    assert np.array_equal(orc.rv_unary(0, x), orc.rv_unary(18, x, 2.0))     # squared == pow(2.0)
+    s = np.array([-4.0, -2.0, 0.0, 2.0, 4.0])
+    s = orc.rv_unary(14, orc.rv_unary(10, s, 4.0), 2.0)
+    assert orc.rv_reduce(0, s) == 2.0 and orc.rv_reduce(2, s) == 2.0
+    assert orc.rv_reduce(7, x) == np.sqrt(orc.rv_reduce(2, x))
+    # Math.min / Math.max semantics and choose
+    m = orc.rv_unary(16, np.array([np.nan, -0.0, 0.0, 1.0]), 0.0)
+    assert np.isnan(m[0]) and np.signbit(m[1]) and not np.signbit(m[2]) and m[3] == 0.0
+    c = orc.rv_ternary(6, np.array([np.nan, -0.0, 0.0, -1.0]), np.ones(4), np.full(4, 2.0))
+    assert c.tolist() == [2.0, 1.0, 1.0, 2.0]
+    # Kahan mean is the correctly rounded mean here where the naive sum is not
+    v = np.array([1.0] + [1e-16] * 1000000)
+    assert orc.rv_reduce(0, v) == (1.0 + 1e-10) / 1000001
+    # quantile index round((n+1)q - 1) clamped (:454-459)
+    q = np.arange(10.0)
+    assert [orc.rv_reduce(9, q, a=a) for a in (0.0, 0.1, 0.5, 0.95, 1.0)] == [0.0, 0.0, 5.0, 9.0, 9.0]
+    assert np.allclose(orc.rv_histogram(q, np.array([2.0, 5.5])), [0.3, 0.3, 0.4])
+
+
+def test_black_scholes_price_like_reference_test(orc):
+    """T/montecarlo/assetderivativevaluation/MonteCarloBlackScholesModelTest.java:80 — MC value within 0.005 of the analytic value."""
+    g = GOLDEN["black_scholes_call"]
+    td = orc.time_discretization(0.0, 100, 0.05)
+    price, proc, vals = orc.bs_european(3141, td, 100000, g["S0"], g["r"], g["sigma"], 2, g["T"], g["K"])
+    assert abs(price - g["value"]) < 0.005
+    assert proc.shape == (101, 1, 100000) and np.all(proc[0] == 1.0)
+    # Euler vs functional Euler differ only by rounding (log(exp(y)) vs y)
+    price_e, proc_e, _ = orc.bs_european(3141, td, 2000, g["S0"], g["r"], g["sigma"], 0, g["T"], g["K"])
+    price_f, proc_f, _ = orc.bs_european(3141, td, 2000, g["S0"], g["r"], g["sigma"], 2, g["T"], g["K"])
+    assert rel_err(proc_e, proc_f) < 1e-13 and not np.array_equal(proc_e, proc_f)
+
+
+def test_heston_xi_zero_equals_black_scholes(orc):
+    """T/montecarlo/assetderivativevaluation/HestonModelTest.java:143-145 (1e-10 on the same Brownian driver)."""
+    td = orc.time_discretization(0.0, 50, 0.1)
+    ph, _, _ = orc.heston_european(3141, td, 20000, 1.0, 0.05, 0.3, 0.05, 0.09, 0.1, 0.0, 0.1, 1, 2, 5.0, 1.25)
+    # same driver: BS with 2 factors is not exposed, but factor 0 of a 2-factor driver differs from a 1-factor driver's draws;
+    # compare through the closed form of the variance path instead: xi = 0 keeps V = sigma^2 exactly
+    _, proc, _ = orc.heston_european(3141, td, 2000, 1.0, 0.05, 0.3, 0.05, 0.09, 0.1, 0.0, 0.1, 1, 2, 5.0, 1.25)
+    assert rel_err(proc[:, 1], np.full_like(proc[:, 1], 0.09)) < 1e-15
+    assert 0.25 < ph < 0.40
+
+
+def test_lmm_oracle_against_reference_test_tolerances(orc, pkg):
+    """LIBORMarketModelValuationTest.java: bond (:199, 5e-4 ... 1e-2 range of tolerances) and swaption vs analytic approximation."""
+    from common import lmm_setup, lmm_oracle
+    s = lmm_setup(pkg)
+    ref = lmm_oracle(orc, s, 20000, scheme=1)
+    # zero bond P(5y;0) = E[1/N(5)] against the curve value (testBond)
+    n = ref.numeraire(5.0)
+    assert abs(np.mean(1.0 / n) - s["df"][10]) < 5e-4
+    # par swaption 5y into 5y: positive, and at-the-money value consistent with the Black approximation to 1e-2 (testSwaption tolerance)
+    fixing = [5.0 + 0.5 * i for i in range(10)]
+    payment = [5.5 + 0.5 * i for i in range(10)]
+    price, vals, se = ref.swaption(5.0, fixing, payment, [0.05] * 10)
+    annuity = sum(0.5 * s["df"][11 + i] for i in range(10))
+    swaprate = (s["df"][10] - s["df"][20]) / annuity
+    from scipy.stats import norm
+    # the implied Black volatility of the MC price must be a sensible swap-rate volatility for sigma_j in [0.3, 0.5], rho < 1
+    def black(vol):
+        d1 = (np.log(swaprate / 0.05) + 0.5 * vol * vol * 5) / (vol * np.sqrt(5))
+        return annuity * (swaprate * norm.cdf(d1) - 0.05 * norm.cdf(d1 - vol * np.sqrt(5)))
+    assert black(0.25) < price < black(0.50)
+    assert se < 2e-3
+    # spot-measure frozen rates: L_j stops moving at its fixing
+    proc = ref.process()
+    assert np.array_equal(proc[7, 3], proc[3, 3]) and not np.array_equal(proc[3, 3], proc[2, 3])
+    assert rel_err(proc[0], np.full_like(proc[0], 0.05)) < 3e-16            # exp(log(0.05)): the reference also goes through log/exp at t = 0
+
+
+def test_fused_cpu_port_equals_reference_shaped_oracle(orc, pkg):
+    """The best-effort CPU baseline (fused, path-parallel) is the same arithmetic as the reference-shaped RV-op oracle: bit-identical."""
+    from common import lmm_setup, lmm_oracle
+    s = lmm_setup(pkg, n_libors=12, n_factors=3)
+    for scheme in (0, 1, 2, 3):
+        ref = lmm_oracle(orc, s, 500, scheme=scheme, with_discount_curve=False).process()
+        _, fused = orc.time_lmm_fused(3141, s["sim"].times, s["tenor"].times, 3, 500, s["L0"], s["sigma"], s["factor_matrix"], scheme, 3, want_process=True)
+        assert np.array_equal(ref, fused), scheme
+
+
+def test_regression_solver_against_numpy(orc):
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((1000, 5))
+    A, b = X.T @ X / 1000, X.T @ rng.standard_normal(1000) / 1000
+    x, cond = orc.solve_pinv(A, b)
+    assert np.allclose(x, np.linalg.solve(A, b), rtol=1e-11) and abs(cond - np.linalg.cond(A)) < 1e-8 * cond
+    A2 = np.array([[1.0, 1.0], [1.0, 1.0]])
+    x2, _ = orc.solve_pinv(A2, np.array([2.0, 2.0]))
+    assert np.allclose(x2, [1.0, 1.0])                                      # minimum-norm solution of a singular system
