@@ -536,6 +536,7 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
 		q.x0 = blob.at<double>(oX0); q.y0 = blob.at<double>(oY0); q.ylog0 = blob.at<double>(oYl);
 		// block size: the shared-memory column store is 8*N bytes per thread
 		int BD = 128;
+		if (const char* e = getenv("FMB_LMM_BD")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 128) BD = v; }   // tuning hook (profiles/r01_notes.md)
 		while (BD > 32 && (size_t)BD * N * sizeof(double) > 200 * 1024) BD >>= 1;
 		const size_t smem = (size_t)BD * N * sizeof(double);
 		if (smem > 220 * 1024) { setError("euler_lmm: %d components exceed the shared-memory state store", N); rc = FMB_EUNSUPPORTED; }
