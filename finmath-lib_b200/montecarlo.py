@@ -106,7 +106,7 @@ class BrownianMotionCuda:
         incs = []
         for t in range(T):
             time = self.timeDiscretization.getTime(t + 1)    # filtration time t_{i+1} :184-190
-            incs.append([self.randomVariableFactory.fromDevice(time, nv.DeviceVector(out[t * F + f], hi - lo)) for f in range(F)])
+            incs.append([self.randomVariableFactory.fromDevice(time, nv.DeviceVector(out[t * F + f], hi - lo), self.numberOfPaths) for f in range(F)])
         self._increments = incs
 
     def _ensure(self):
@@ -279,7 +279,7 @@ class EulerSchemeFromProcessModel:
                     nv.load().fmb_rv_free(h)                  # aliased entry: drop the extra reference, share the object (:285)
                     row.append(proc[t - 1][c])
                 else:
-                    row.append(factory.fromDevice(td.getTime(t), nv.DeviceVector(h, P)))
+                    row.append(factory.fromDevice(td.getTime(t), nv.DeviceVector(h, P), bm.getNumberOfPaths()))
             proc.append(row)
         self._discreteProcess = proc
 
@@ -396,7 +396,7 @@ class MonteCarloConditionalExpectationRegression:
             nv.check(nv.load().fmb_regression_predict(K, nv.hptr(hs), nv.dptr(sc), nv.dptr(xs), C.byref(out)))
             n = next(b.dv.n for b in basis if b.dv is not None)
             time = max(b.getFiltrationTime() for b in basis)
-            return RandomVariableCuda(time, None, shard, _dv=nv.DeviceVector(out.value, n))
+            return RandomVariableCuda(time, None, shard, _dv=nv.DeviceVector(out.value, n), _n=randomVariable.size())
         ce = basis[0].mult(float(x[0]))
         for i in range(1, K):
             ce = ce.addProduct(basis[i], float(x[i]))

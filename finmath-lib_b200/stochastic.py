@@ -295,17 +295,21 @@ class RandomVariableFromDoubleArray(RandomVariable):
 class RandomVariableCuda(RandomVariable):
     """Device-resident RandomVariable, type priority 2."""
 
-    def __init__(self, time, value, shard=None, _dv=None):
+    def __init__(self, time, value, shard=None, _dv=None, _n=None):
         self.time = float(time)
         self.shard = shard if shard is not None else LOCAL
+        self.nGlobal = _n                                  # logical (all-shard) number of paths; known without a collective
         if _dv is not None:
             self.dv, self.valueIfNonStochastic = _dv, float("nan")
+            if _n is None:
+                self.nGlobal = self.shard.global_count(_dv.n)
         elif _is_number(value):
             self.dv, self.valueIfNonStochastic = None, float(value)
         else:
             a = np.ascontiguousarray(value, dtype=np.float64)
             lo, hi = self.shard.local_range(a.size)
             self.dv, self.valueIfNonStochastic = nv.DeviceVector.upload(a[lo:hi]), float("nan")
+            self.nGlobal = a.size
 
     # ---- accessors -------------------------------------------------------------------------------------------
     def getTypePriority(self):
@@ -318,7 +322,7 @@ class RandomVariableCuda(RandomVariable):
         return self.dv is None
 
     def size(self):                                        # :246-252
-        return 1 if self.dv is None else self.shard.global_count(self.dv.n)
+        return 1 if self.dv is None else self.nGlobal
 
     def get(self, i):
         if self.dv is None:
@@ -362,19 +366,31 @@ class RandomVariableCuda(RandomVariable):
         raise NotImplementedError("getRealizationsStream() is not available for device-resident values")
 
     # ---- helpers ----------------------------------------------------------------------------------------------
-    def _new(self, time, dv):
-        return RandomVariableCuda(time, None, self.shard, _dv=dv)
+    def _new(self, time, dv, n=None):
+        return RandomVariableCuda(time, None, self.shard, _dv=dv, _n=n if n is not None else self._n_of(dv))
+
+    def _n_of(self, dv):
+        """Logical length of a result: all stochastic operands of one operation are shards of equally long logical vectors."""
+        if self.nGlobal is not None and self.dv is not None and self.dv.n == dv.n:
+            return self.nGlobal
+        return self._pending_n
 
     def _det(self, time, v):
         return RandomVariableCuda(time, v, self.shard)
 
+    _pending_n = None
+
     def _operand(self, rv):
         """(device vector or None, scalar value) of any RandomVariable."""
         if isinstance(rv, RandomVariableCuda):
+            if rv.dv is not None:
+                self._pending_n = rv.nGlobal
             return rv.dv, rv.valueIfNonStochastic
         if rv.isDeterministic():
             return None, rv.doubleValue()
-        return RandomVariableCuda(rv.getFiltrationTime(), rv.getRealizations(), self.shard).dv, float("nan")
+        up = RandomVariableCuda(rv.getFiltrationTime(), rv.getRealizations(), self.shard)
+        self._pending_n = up.nGlobal
+        return up.dv, float("nan")
 
     def _map1(self, op, a=0.0):
         if self.dv is None:
@@ -728,5 +744,5 @@ class RandomVariableCudaFactory:
     def createRandomVariableMatrix(self, values):
         return [[self.createRandomVariable(NEG_INF, float(v)) for v in row] for row in values]
 
-    def fromDevice(self, time, dv):
-        return RandomVariableCuda(time, None, self.shard, _dv=dv)
+    def fromDevice(self, time, dv, n=None):
+        return RandomVariableCuda(time, None, self.shard, _dv=dv, _n=n)
