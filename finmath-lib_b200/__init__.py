@@ -13,5 +13,5 @@ from .montecarlo import (TimeDiscretizationFromArray, BrownianMotionCuda, EulerS
 from .models import (BlackScholesModel, HestonModel, MonteCarloAssetModel, MonteCarloBlackScholesModel,
                      LIBORVolatilityModelFourParameterExponentialForm, LIBORCorrelationModelExponentialDecay,
                      LIBORCovarianceModelFromVolatilityAndCorrelation, LIBORMarketModelFromCovarianceModel,
-                     LIBORMonteCarloSimulationFromLIBORModel, factorReduction)
+                     LIBORMonteCarloSimulationFromLIBORModel, factorReduction, HullWhiteModel, ShortRateVolatilityModelAsGiven)
 from .products import EuropeanOption, Caplet, Swaption, BermudanSwaption

@@ -433,3 +433,135 @@ class LIBORMonteCarloSimulationFromLIBORModel:
 
     def getCloneWithModifiedSeed(self, seed):
         return LIBORMonteCarloSimulationFromLIBORModel(self.model, self.process.getCloneWithModifiedSeed(seed))
+
+
+# ---- Hull-White ------------------------------------------------------------------------------------------------------------
+class ShortRateVolatilityModelAsGiven:
+    """J/montecarlo/interestrate/models/covariance/ShortRateVolatilityModelAsGiven.java:20-60 (piecewise constant sigma(t), a(t))."""
+
+    def __init__(self, timeDiscretization, volatility, meanReversion):
+        self.timeDiscretization, self.volatility, self.meanReversion = timeDiscretization, list(volatility), list(meanReversion)
+
+    def getTimeDiscretization(self): return self.timeDiscretization
+    def getVolatility(self, timeIndex): return Scalar(self.volatility[timeIndex])
+    def getMeanReversion(self, timeIndex): return Scalar(self.meanReversion[timeIndex])
+
+
+class HullWhiteModel:
+    """J/montecarlo/interestrate/models/HullWhiteModel.java — the process part (:277-424) with the closed forms for piecewise
+    constant coefficients (:584-795).  All coefficients are deterministic Scalars evaluated on the host in the reference's
+    operation order; the fused kernel receives them as per-step tables (drift multipliers of x0, four factor loadings)."""
+
+    def __init__(self, randomVariableFactory, liborPeriodDiscretization, volatilityModel, properties=None):
+        self.randomVariableFactory = randomVariableFactory if randomVariableFactory is not None else RandomVariableCudaFactory()
+        self.liborPeriodDiscretization = liborPeriodDiscretization
+        self.volatilityModel = volatilityModel
+
+    def getNumberOfComponents(self): return 2
+    def getNumberOfFactors(self): return 1                                                        # :287-290 (sic; the driver's count is used)
+    def getLiborPeriodDiscretization(self): return self.liborPeriodDiscretization
+    def getRandomVariableForConstant(self, v): return self.randomVariableFactory.createRandomVariable(v)
+    def applyStateSpaceTransform(self, process, timeIndex, componentIndex, rv): return rv
+    def applyStateSpaceTransformInverse(self, process, timeIndex, componentIndex, rv): return rv
+
+    def getInitialState(self, process):
+        zero = self.getRandomVariableForConstant(0.0)
+        return [zero, zero]
+
+    def _vol_index(self, t):
+        i = self.volatilityModel.getTimeDiscretization().getTimeIndex(t)
+        return i if i >= 0 else -i - 2
+
+    def getMRTime(self, time, maturity):                                                          # :584-607
+        vm, td = self.volatilityModel, self.volatilityModel.getTimeDiscretization()
+        i0, i1 = self._vol_index(time), self._vol_index(maturity)
+        integral, timePrev = Scalar(0.0), time
+        for ti in range(i0 + 1, i1 + 1):
+            timeNext = td.getTime(ti)
+            integral = integral.add(vm.getMeanReversion(ti - 1).mult(timeNext - timePrev))
+            timePrev = timeNext
+        return integral.add(vm.getMeanReversion(i1).mult(maturity - timePrev))
+
+    def getB(self, time, maturity):                                                               # :609-640
+        vm, td = self.volatilityModel, self.volatilityModel.getTimeDiscretization()
+        i0, i1 = self._vol_index(time), self._vol_index(maturity)
+        integral, timePrev = Scalar(0.0), time
+        for ti in range(i0 + 1, i1 + 1):
+            timeNext = td.getTime(ti)
+            integral = integral.add(self.getMRTime(timeNext, maturity).mult(-1.0).exp().sub(
+                self.getMRTime(timePrev, maturity).mult(-1.0).exp()).div(vm.getMeanReversion(ti - 1)))
+            timePrev = timeNext
+        return integral.add(self.getMRTime(maturity, maturity).mult(-1.0).exp().sub(
+            self.getMRTime(timePrev, maturity).mult(-1.0).exp()).div(vm.getMeanReversion(i1)))
+
+    def _segments(self, time, maturity):
+        vm, td = self.volatilityModel, self.volatilityModel.getTimeDiscretization()
+        i0, i1 = self._vol_index(time), self._vol_index(maturity)
+        timePrev = time
+        for ti in range(i0 + 1, i1 + 1):
+            timeNext = td.getTime(ti)
+            yield timePrev, timeNext, vm.getMeanReversion(ti - 1), vm.getVolatility(ti - 1)
+            timePrev = timeNext
+        yield timePrev, maturity, vm.getMeanReversion(i1), vm.getVolatility(i1)
+
+    def getV(self, time, maturity):                                                               # :642-690
+        if time == maturity:
+            return Scalar(0.0)
+        integral = Scalar(0.0)
+        ePrev = self.getMRTime(time, maturity).mult(-1).exp()
+        for timePrev, timeNext, m, v in self._segments(time, maturity):
+            v2 = v.squared().div(m.squared())
+            eNext = self.getMRTime(timeNext, maturity).mult(-1).exp()
+            integral = integral.add(v2.mult(eNext.sub(ePrev).mult(-2).div(m).add(eNext.squared().sub(ePrev.squared()).div(m).div(2.0)).add(timeNext - timePrev)))
+            ePrev = eNext
+        return integral
+
+    def getDV(self, time, maturity):                                                              # :692-738
+        if time == maturity:
+            return Scalar(0.0)
+        integral = Scalar(0.0)
+        ePrev = self.getMRTime(time, maturity).mult(-1).exp()
+        for timePrev, timeNext, m, v in self._segments(time, maturity):
+            v2 = v.squared().div(m.squared())
+            eNext = self.getMRTime(timeNext, maturity).mult(-1).exp()
+            integral = integral.add(v2.mult(eNext.sub(ePrev).add(eNext.squared().sub(ePrev.squared()).div(-2.0))))
+            ePrev = eNext
+        return integral
+
+    def _drift_coefficients(self, process, timeIndex):                                            # :367-387
+        time, timeNext = process.getTime(timeIndex), process.getTime(timeIndex + 1)
+        m = self.volatilityModel.getMeanReversion(self._vol_index(time))
+        B = self.getB(time, timeNext)
+        return m.mult(B.div(-1 * (timeNext - time))), B.div(timeNext - time)
+
+    def getDrift(self, process, timeIndex, x, predictor):
+        if process.getTime(timeIndex + 1) == process.getTime(timeIndex):
+            return [None, None]
+        c0, c1 = self._drift_coefficients(process, timeIndex)
+        return [x[0].mult(c0), x[0].mult(c1)]
+
+    def getFactorLoading(self, process, timeIndex, componentIndex, x):                            # :389-424
+        time, timeNext = process.getTime(timeIndex), process.getTime(timeIndex + 1)
+        vi = self._vol_index(time)
+        m = self.volatilityModel.getMeanReversion(vi)
+        mrt = m.mult(-2.0 * (timeNext - time))
+        scaling = mrt.exp().sub(1.0).div(mrt).sqrt()
+        volEff = scaling.mult(self.volatilityModel.getVolatility(vi))
+        if componentIndex == 0:
+            return [volEff, Scalar(0.0)]
+        volLogNum = self.getV(time, timeNext).div(timeNext - time).sqrt()
+        rho = self.getDV(time, timeNext).div(timeNext - time).div(volEff.mult(volLogNum))
+        return [volLogNum.mult(rho), volLogNum.mult(rho.squared().sub(1).mult(-1).sqrt())]
+
+    def getFusedSpecification(self, process):
+        if process.getScheme() in (Scheme.PREDICTOR_CORRECTOR, Scheme.PREDICTOR_CORRECTOR_FUNCTIONAL):
+            return None                                       # the corrector is not fused for this model: generic device loop
+        T = process.getTimeDiscretization().getNumberOfTimeSteps()
+        d0, d1, fl = [], [], []
+        for t in range(T):
+            c0, c1 = self._drift_coefficients(process, t)
+            f0, f1 = self.getFactorLoading(process, t, 0, None), self.getFactorLoading(process, t, 1, None)
+            d0.append(c0.doubleValue())
+            d1.append(c1.doubleValue())
+            fl.append([f0[0].doubleValue(), f0[1].doubleValue(), f1[0].doubleValue(), f1[1].doubleValue()])
+        return dict(kernel="hull_white", drift0=d0, drift1=d1, factorLoadings=np.array(fl), initialValues=[0.0, 0.0])

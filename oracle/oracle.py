@@ -283,3 +283,15 @@ def time_lmm_fused(seed, sim_times, tenor_times, F, paths, L0, sigma, factor_mat
     sec = lib().orc_time_lmm_fused(C.c_int(seed), sp, C.c_int(st.size), tp, C.c_int(tt.size), C.c_int(F), C.c_int(paths), lp, sgp, fp,
                                    C.c_int(scheme), C.c_int(threads), proc.ctypes.data_as(c_dp) if want_process else None)
     return sec, proc
+
+
+def hull_white_process(seed, times, paths, vol_times, vol, mr, scheme=0, path_offset=0):
+    t, tp = _d(times)
+    vt, vtp = _d(vol_times)
+    v, vp = _d(vol)
+    m, mp_ = _d(mr)
+    proc = np.empty((t.size, 2, paths))
+    coef = np.empty((t.size - 1, 6))
+    lib().orc_hull_white_process(C.c_int(seed), tp, C.c_int(t.size), C.c_int(paths), C.c_int64(path_offset), vtp, C.c_int(vt.size), vp, mp_,
+                                 C.c_int(scheme), proc.ctypes.data_as(c_dp), coef.ctypes.data_as(c_dp))
+    return proc, coef

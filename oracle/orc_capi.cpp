@@ -233,6 +233,26 @@ double orc_lmm_bermudan(void* hv, const int* isExercise, const double* fixingDat
 	return getAverage(r.value);
 }
 
+// ---- Hull-White (process values only; [T+1][2][P]) -----------------------------------------------------------------
+void orc_hull_white_process(int seed, const double* times, int nTimes, int paths, int64_t pathOffset, const double* volTimes, int nVolTimes,
+		const double* vol, const double* mr, int scheme, double* processOut, double* coefOut /* [T][6]: c0, c1, l00, l01, l10, l11 or NULL */) {
+	BrownianMotion bm(tdFrom(times, nTimes), 2, paths, seed, pathOffset);
+	HullWhiteModel m;
+	m.volTimes = tdFrom(volTimes, nVolTimes);
+	m.vol = vecOf(vol, nVolTimes); m.mr = vecOf(mr, nVolTimes);
+	Process pr(&m, &bm, scheme);
+	dumpProcess(pr, nTimes - 1, 2, paths, processOut);
+	if (coefOut) {
+		std::vector<P> one = { scalar(1.0), scalar(0.0) };
+		for (int t = 0; t < nTimes - 1; t++) {
+			std::vector<P> d = m.getDrift(pr, t, one);
+			std::vector<P> f0 = m.getFactorLoading(pr, t, 0, one), f1 = m.getFactorLoading(pr, t, 1, one);
+			double* c = coefOut + 6 * t;
+			c[0] = d[0]->v; c[1] = d[1]->v; c[2] = f0[0]->v; c[3] = f0[1]->v; c[4] = f1[0]->v; c[5] = f1[1]->v;
+		}
+	}
+}
+
 // ---- CPU baselines for bench.py (bounded samples) --------------------------------------------------------
 // (1) reference-shaped: the RV-op path above (one array pass + one allocation per op, single sequential MT stream).
 //     Returns seconds for {Brownian generation + Euler evolution} of `paths` LMM paths.

@@ -323,4 +323,110 @@ struct LIBORMarketModel : ProcessModel {
 	}
 };
 
+// J/montecarlo/interestrate/models/HullWhiteModel.java:277-424 (process callbacks) with the piecewise-constant closed forms
+// :584-795 (getMRTime, getB, getV, getDV).  Volatility model = ShortRateVolatilityModelAsGiven (Scalars).
+struct HullWhiteModel : ProcessModel {
+	TimeDiscretization volTimes;       // time discretization of the volatility model
+	std::vector<double> vol, mr;       // per volatility-time index
+
+	int volIndex(double t) const { int i = volTimes.getTimeIndex(t); if (i < 0) i = -i - 2; return i; }
+	P meanReversion(int i) const { return scalar(mr.at(i)); }
+	P volatility(int i) const { return scalar(vol.at(i)); }
+
+	P getMRTime(double time, double maturity) const {                                       // :584-607
+		const int i0 = volIndex(time), i1 = volIndex(maturity);
+		P integral = scalar(0.0);
+		double timePrev = time, timeNext;
+		for (int ti = i0 + 1; ti <= i1; ti++) {
+			timeNext = volTimes.getTime(ti);
+			integral = add(integral, mult(meanReversion(ti - 1), timeNext - timePrev));
+			timePrev = timeNext;
+		}
+		timeNext = maturity;
+		integral = add(integral, mult(meanReversion(i1), timeNext - timePrev));
+		return integral;
+	}
+	P getB(double time, double maturity) const {                                            // :609-640
+		const int i0 = volIndex(time), i1 = volIndex(maturity);
+		P integral = scalar(0.0);
+		double timePrev = time, timeNext;
+		for (int ti = i0 + 1; ti <= i1; ti++) {
+			timeNext = volTimes.getTime(ti);
+			integral = add(integral, div(sub(exp(mult(getMRTime(timeNext, maturity), -1.0)), exp(mult(getMRTime(timePrev, maturity), -1.0))), meanReversion(ti - 1)));
+			timePrev = timeNext;
+		}
+		timeNext = maturity;
+		integral = add(integral, div(sub(exp(mult(getMRTime(timeNext, maturity), -1.0)), exp(mult(getMRTime(timePrev, maturity), -1.0))), meanReversion(i1)));
+		return integral;
+	}
+	P vTerm(const P& v2mr2, const P& eNext, const P& ePrev, const P& mrv, double dt) const {
+		return mult(v2mr2, add(add(div(mult(sub(eNext, ePrev), -2), mrv), div(div(sub(squared(eNext), squared(ePrev)), mrv), 2.0)), dt));
+	}
+	P getV(double time, double maturity) const {                                            // :642-690
+		if (time == maturity) return scalar(0.0);
+		const int i0 = volIndex(time), i1 = volIndex(maturity);
+		P integral = scalar(0.0);
+		double timePrev = time, timeNext;
+		P ePrev = exp(mult(getMRTime(timePrev, maturity), -1));
+		for (int ti = i0 + 1; ti <= i1; ti++) {
+			timeNext = volTimes.getTime(ti);
+			P m = meanReversion(ti - 1), v = volatility(ti - 1);
+			P eNext = exp(mult(getMRTime(timeNext, maturity), -1));
+			integral = add(integral, vTerm(div(squared(v), squared(m)), eNext, ePrev, m, timeNext - timePrev));
+			timePrev = timeNext; ePrev = eNext;
+		}
+		timeNext = maturity;
+		P m = meanReversion(i1), v = volatility(i1);
+		P eNext = exp(mult(getMRTime(timeNext, maturity), -1));
+		return add(integral, vTerm(div(squared(v), squared(m)), eNext, ePrev, m, timeNext - timePrev));
+	}
+	P getDV(double time, double maturity) const {                                           // :692-738
+		if (time == maturity) return scalar(0.0);
+		const int i0 = volIndex(time), i1 = volIndex(maturity);
+		P integral = scalar(0.0);
+		double timePrev = time, timeNext;
+		P ePrev = exp(mult(getMRTime(timePrev, maturity), -1));
+		auto term = [](const P& v2mr2, const P& eNext, const P& ePrev) {
+			return mult(v2mr2, add(sub(eNext, ePrev), div(sub(squared(eNext), squared(ePrev)), -2.0)));
+		};
+		for (int ti = i0 + 1; ti <= i1; ti++) {
+			timeNext = volTimes.getTime(ti);
+			P m = meanReversion(ti - 1), v = volatility(ti - 1);
+			P eNext = exp(mult(getMRTime(timeNext, maturity), -1));
+			integral = add(integral, term(div(squared(v), squared(m)), eNext, ePrev));
+			timePrev = timeNext; ePrev = eNext;
+		}
+		timeNext = maturity;
+		P m = meanReversion(i1), v = volatility(i1);
+		P eNext = exp(mult(getMRTime(timeNext, maturity), -1));
+		return add(integral, term(div(squared(v), squared(m)), eNext, ePrev));
+	}
+
+	int getNumberOfComponents() const override { return 2; }
+	std::vector<P> getInitialState(const Process&) override { P z = scalar(0.0); return { z, z }; }   // :298-303
+	std::vector<P> getDrift(const Process& p, int timeIndex, const std::vector<P>& x) override {       // :367-387
+		const double time = p.getTime(timeIndex), timeNext = p.getTime(timeIndex + 1);
+		if (timeNext == time) return { P(), P() };
+		P m = meanReversion(volIndex(time));
+		P d0 = mult(x[0], mult(m, div(getB(time, timeNext), -1 * (timeNext - time))));
+		P d1 = mult(x[0], div(getB(time, timeNext), timeNext - time));
+		return { d0, d1 };
+	}
+	std::vector<P> getFactorLoading(const Process& p, int timeIndex, int c, const std::vector<P>&) override {   // :389-424
+		const double time = p.getTime(timeIndex), timeNext = p.getTime(timeIndex + 1);
+		const int vi = volIndex(time);
+		P m = meanReversion(vi);
+		P mrt = mult(m, -2.0 * (timeNext - time));
+		P scaling = sqrt(div(sub(exp(mrt), 1.0), mrt));
+		P volEff = mult(scaling, volatility(vi));
+		if (c == 0) return { volEff, scalar(0.0) };
+		P volLogNum = sqrt(div(getV(time, timeNext), timeNext - time));
+		P rho = div(div(getDV(time, timeNext), timeNext - time), mult(volEff, volLogNum));
+		return { mult(volLogNum, rho), mult(volLogNum, sqrt(mult(sub(squared(rho), 1), -1))) };
+	}
+	P applyStateSpaceTransform(int, int, const P& y) override { return y; }
+	bool hasInverse() const override { return true; }
+	P applyStateSpaceTransformInverse(int, int, const P& x) override { return x; }
+};
+
 } // namespace orc

@@ -208,3 +208,22 @@ def test_sharding_collectives_world_size_2_gloo(tmp_path):
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
     assert out.stdout.count("ok") == 2, out.stdout               # both ranks finished every assertion (their prints may interleave)
+
+
+def test_hull_white_coefficient_tables_equal_oracle(pkg, orc):
+    """Host-side Hull-White closed forms (Scalar arithmetic in the reference's order) == oracle, bit for bit."""
+    class P:                                                       # minimal process stand-in: only the time grid is consulted
+        def __init__(self, td): self.td = td
+        def getTime(self, i): return self.td.getTime(i)
+        def getTimeDiscretization(self): return self.td
+        def getScheme(self): return 0
+    for (nsteps, dt, vt, vol, mr) in [(40, 0.5, [0.0], [0.005], [0.1]),
+                                      (200, 0.1, list(np.arange(0, 21.0)), list(0.005 + 0.0005 * np.floor(np.arange(0, 21.0)) / 20), [0.1] * 21),
+                                      (30, 0.25, [0.0, 1.0, 2.5, 4.0], [0.01, 0.012, 0.008, 0.02], [0.05, 0.1, 0.2, 0.15])]:
+        td = pkg.TimeDiscretizationFromArray(0.0, nsteps, dt)
+        vm = pkg.ShortRateVolatilityModelAsGiven(pkg.TimeDiscretizationFromArray(vt), vol, mr)
+        model = pkg.HullWhiteModel(None, td, vm)
+        spec = model.getFusedSpecification(P(td))
+        _, coef = orc.hull_white_process(3141, td.times, 4, vm.getTimeDiscretization().times, vol, mr, 0)
+        mine = np.column_stack([spec["drift0"], spec["drift1"], spec["factorLoadings"]])
+        assert np.array_equal(mine, coef)

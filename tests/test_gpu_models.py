@@ -195,3 +195,25 @@ def test_regression_moments_and_solver(gpu, orc):
     est2 = gpu.MonteCarloConditionalExpectationRegression([RV(0.0, b1), RV(0.0, b1)])
     x2 = est2.getLinearRegressionParameters(RV(0.0, 4.0 * b1))
     assert np.allclose(x2, [2.0, 2.0], atol=1e-9)
+
+
+# ---- Hull-White (C2 shape, small) -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scheme", [0, 2, 1])
+def test_hull_white_process_matches_oracle(gpu, orc, scheme):
+    paths = 20_000
+    td = gpu.TimeDiscretizationFromArray(0.0, 200, 0.1)
+    vt = np.arange(0, 21.0)
+    vol, mr = 0.005 + 0.0005 * np.floor(vt) / 20, np.full(vt.size, 0.1)
+    vm = gpu.ShortRateVolatilityModelAsGiven(gpu.TimeDiscretizationFromArray(vt), vol, mr)
+    bm = gpu.BrownianMotionCuda(td, 2, paths, 3141)
+    model = gpu.HullWhiteModel(bm.randomVariableFactory, gpu.TimeDiscretizationFromArray(0.0, 40, 0.5), vm)
+    process = gpu.EulerSchemeFromProcessModel(model, bm, scheme)
+    ref, _ = orc.hull_white_process(3141, td.times, paths, vt, vol, mr, scheme)
+    got = np.empty_like(ref)
+    for t in range(201):
+        for c in range(2):
+            rv = process.getProcessValue(t, c)
+            got[t, c] = rv.doubleValue() if rv.isDeterministic() else rv.getRealizations()
+    assert process.usedFusedKernel == ("hull_white" if scheme != 1 else None)
+    # short-rate state ~ 1e-2, log-numeraire ~ 1e-1: absolute scales for the relative test
+    assert rel_err(got[:, 0], ref[:, 0], scale=1e-2) < PATH_TOL and rel_err(got[:, 1], ref[:, 1], scale=1e-1) < PATH_TOL
