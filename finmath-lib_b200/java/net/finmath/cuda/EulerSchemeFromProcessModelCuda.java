@@ -65,8 +65,7 @@ public class EulerSchemeFromProcessModelCuda extends MonteCarloProcessFromProces
 					var[t * N + j] = lmm.getCovarianceModel().getCovariance(td.getTime(t), j, j, null).doubleValue();
 				}
 			}
-			final Map<String, ?> p = lmm.getModelParameters() == null ? null : null;   // measure / state space / cap are read from the model's getters
-			out = FinmathB200.eulerLmm(scheme.ordinal() == 1 ? 1 : scheme.ordinal() == 0 ? 0 : scheme.ordinal() == 2 ? 2 : 3,
+			out = FinmathB200.eulerLmm(scheme.ordinal() /* enum order == C-ABI codes (:68-73) */,
 					lmm.getMeasure().ordinal(), lmm.getStateSpace().ordinal(), lmm.getLiborCap(), T, N, F, driver.getNumberOfPaths(), dt, driver.getIncrementHandles(),
 					y0, pl, fl, var, first);
 			initialValues = new double[N];
