@@ -210,7 +210,7 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 	}
 #pragma unroll
 	for (int u = 0; u < U; u++) {
-		a[u] = 1.0 / (L[u] * r[u].ratio + r[u].invv);
+		a[u] = 1.0 / ((r[u].ratio < 0.0 ? -L[u] : L[u]) + r[u].invv);      // L * (d / +-d) == +-L exactly: a sign flip, bit-identical
 		if (LOGN) a[u] = a[u] * L[u];
 	}
 #pragma unroll
