@@ -229,10 +229,24 @@ def main():
     import ctypes as C
     tf = C.c_double()
     nv.check(nv.load().fmb_bench_dfma_tflops(C.byref(tf)))
-    roofline = {"bound": "hbm", "kernel": "eulerLmmKernel<3>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": euler_bytes, "avg_launch_ms": eu,
-                "note": "FP64-pipe bound (double exp/log per rate-step), see DESIGN.md; fp64 numbers under 'fp64'"}
-    fp64 = {"dfma_peak_tflops_measured": tf.value, "euler_ms": eu, "brownian_ms": float(np.mean(bm_ms)),
+    # DRAM traffic per launch from the committed ncu --set full capture (profiles/r01_top_kernels_ncu.json), valid for the 4 M-path launch
+    traffic = None
+    try:
+        if P_local == 4_000_000 and args.scheme == 2:
+            for k in json.load(open(os.path.join(ROOT, "profiles", "r01_top_kernels_ncu.json"))):
+                if "eulerLmmKernel" in k["Kernel Name"]:
+                    traffic = (float(k["dram__bytes_read.sum"].split()[0]) + float(k["dram__bytes_write.sum"].split()[0])) * 1e9
+    except Exception:
+        traffic = None
+    # FP64 work of the kernel: 75 FP64 instructions per live rate-step (ncu --page source, profiles/r01_notes.md), DFMA-equivalent flops = 2 each
+    fp64_instr = 75.0 * live * P_local
+    fp64_achieved_tflops = 2.0 * fp64_instr / (eu * 1e-3) / 1e12
+    roofline = {"bound": "hbm", "kernel": "eulerLmmKernel<3,1,0>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": euler_bytes, "avg_launch_ms": eu,
+                "note": "this kernel is FP64-pipe bound (double log + exp + division per rate-step), not HBM bound: see 'fp64' and DESIGN.md 4.3"}
+    fp64 = {"bound": "fp64", "achieved": fp64_achieved_tflops, "peak": tf.value, "unit": "TFLOP/s (DFMA-equivalent)", "frac": fp64_achieved_tflops / tf.value,
+            "peak_source": "fmb_bench_dfma_tflops, measured in this run (8 independent DFMA chains per thread)",
+            "fp64_instructions_per_rate_step": 75, "euler_ms": eu, "brownian_ms": float(np.mean(bm_ms)),
             "brownian_achieved_gbs": bm_bytes / (float(np.mean(bm_ms)) * 1e-3) / 1e9}
 
     # ---- C5: Bermudan swaption wall time (simulation + backward induction with regression, price on the host) ------------------
