@@ -194,6 +194,8 @@ def main():
     value = P_global * T * args.steps / (ms * 1e-3)
 
     # ---- end to end through the host API: host tables in, price out, per step ---------------------------------------------
+    for w in range(min(2, args.warmup)):
+        step(2000 + w, price=True)                           # warm-up of the priced path (pool blocks of the product's temporaries)
     barrier()
     t0 = time.perf_counter()
     prices = [step(3141 + k, price=True) for k in range(args.steps)]
