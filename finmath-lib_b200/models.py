@@ -11,6 +11,7 @@ loop can run it unchanged — and additionally describes itself to the fused ker
 * LIBORMonteCarloSimulationFromLIBORModel  J/montecarlo/interestrate/LIBORMonteCarloSimulationFromLIBORModel.java:27-206
 """
 import math
+import weakref
 
 import numpy as np
 
@@ -345,10 +346,11 @@ class LIBORMarketModelFromCovarianceModel:
         return acc.sub(1.0).div(periodEnd - periodStart)
 
     def _ensure_cache(self, process):
-        if process is not self._numerairesProcess:                                     # :951-961
+        # :951-961; a weak reference: the process owns device memory and already references this model (no cycle for the GC to find)
+        if self._numerairesProcess is None or self._numerairesProcess() is not process:
             self._numeraires.clear()
             self._numeraireDiscountFactors.clear()
-            self._numerairesProcess = process
+            self._numerairesProcess = weakref.ref(process)
 
     def _numeraire_unadjusted_at(self, process, li):                                   # :1017-1074
         self._ensure_cache(process)

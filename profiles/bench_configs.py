@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""Side benchmark: path-steps/s of the other BASELINE.json configurations (C1 Black-Scholes, C2 Hull-White, C3 Heston, C5 Bermudan)
+on one B200, through the host API.  Output: one JSON object per configuration (kept in profiles/r01_configs.jsonl).
+Not the driver's bench (that is /bench.py, C4); timing with device events on the library's stream, 1 warm-up + 3 timed repetitions."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import __graft_entry__ as graft  # noqa: E402
+
+pkg = graft.load_package()
+nv = pkg.native
+nv.init(0)
+
+
+def timed(fn, reps=3):
+    fn(0)
+    nv.synchronize()
+    ms = []
+    for r in range(reps):
+        nv.timer_start()
+        fn(r + 1)
+        ms.append(nv.timer_stop_ms())
+    return float(np.mean(ms))
+
+
+def report(name, paths, steps, bytes_per_path_step, ms, extra=None):
+    d = {"config": name, "paths": paths, "steps": steps, "ms": ms, "path_steps_per_s": paths * steps / (ms * 1e-3),
+         "algorithmic_GBps": paths * steps * bytes_per_path_step / (ms * 1e-3) / 1e9}
+    d.update(extra or {})
+    print(json.dumps(d), flush=True)
+
+
+def c1(seed):
+    td = pkg.TimeDiscretizationFromArray(0.0, 100, 0.05)
+    m = pkg.MonteCarloBlackScholesModel(1.0, 0.05, 0.30, pkg.BrownianMotionCuda(td, 1, 100_000, 3141 + seed))
+    return pkg.EuropeanOption(5.0, 1.05).getValue(m)
+
+
+def c2(seed):
+    td = pkg.TimeDiscretizationFromArray(0.0, 200, 0.1)
+    vt = np.arange(0, 21.0)
+    vm = pkg.ShortRateVolatilityModelAsGiven(pkg.TimeDiscretizationFromArray(vt), 0.005 + 0.0005 * np.floor(vt) / 20, np.full(vt.size, 0.1))
+    bm = pkg.BrownianMotionCuda(td, 2, 1_000_000, 3141 + seed)
+    p = pkg.EulerSchemeFromProcessModel(pkg.HullWhiteModel(bm.randomVariableFactory, pkg.TimeDiscretizationFromArray(0.0, 40, 0.5), vm), bm, 0)
+    return p.getProcessValue(200, 1).getAverage()
+
+
+def c3(paths):
+    def run(seed):
+        td = pkg.TimeDiscretizationFromArray(0.0, 1000, 0.005)
+        bm = pkg.BrownianMotionCuda(td, 2, paths, 31415 + seed)
+        model = pkg.HestonModel(1.0, 0.05, 0.3, 0.05, 0.09, 0.1, 0.5, 0.1, 1, bm.randomVariableFactory)
+        mc = pkg.MonteCarloAssetModel(model, bm)
+        return [pkg.EuropeanOption(5.0, 1.10 * k).getValue(mc) for k in (0.8, 0.9, 1.0, 1.1, 1.2, 1.3, 1.4, 1.5)]
+    return run
+
+
+def c5(paths):
+    from common import lmm_setup, lmm_device, bermudan_spec
+    s = lmm_setup(pkg)
+    b = bermudan_spec(s)
+    product = pkg.BermudanSwaption(b["is_exercise"], b["fixing"], b["lengths"], b["payment"], b["notionals"], b["swaprates"])
+
+    def run(seed):
+        return product.getValue(lmm_device(pkg, s, paths, seed=3141 + seed))
+    return run
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c1", "c2", "c3", "c5"]
+    if "c1" in which:
+        report("C1 Black-Scholes 100k x 100, EULER_FUNCTIONAL, incl. call price", 100_000, 100, 16, timed(c1))
+    if "c2" in which:
+        report("C2 Hull-White 1M x 200 (dt 0.1y), piecewise-constant sigma(t), EULER", 1_000_000, 200, 32, timed(c2))
+    if "c3" in which:
+        for paths in (1_000_000, 4_000_000):
+            t0 = time.time()
+            report("C3 Heston full truncation %dM x 1000, 8-strike smile" % (paths // 1_000_000), paths, 1000, 32, timed(c3(paths), reps=2), {"wall_s_total": None})
+            nv.load().fmb_pool_trim()
+    if "c5" in which:
+        for paths in (1_000_000, 8_000_000):
+            report("C5 LMM Bermudan swaption %dM paths (simulate + 20 exercise dates x 6 basis functions)" % (paths // 1_000_000), paths, 40, 180, timed(c5(paths), reps=2))
+            nv.load().fmb_pool_trim()
