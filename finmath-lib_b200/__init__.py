@@ -8,7 +8,7 @@ it as the module ``finmath_lib_b200``.  Layout: ``csrc/`` hand-written CUDA for 
 from . import native
 from .sharding import ShardContext, LOCAL, from_environment
 from .stochastic import (RandomVariable, Scalar, RandomVariableFromDoubleArray, RandomVariableCuda, RandomVariableCudaFactory)
-from .montecarlo import (TimeDiscretizationFromArray, BrownianMotionCuda, EulerSchemeFromProcessModel, Scheme,
+from .montecarlo import (TimeDiscretizationFromArray, BrownianMotionCuda, BrownianMotionView, CorrelatedBrownianMotion, EulerSchemeFromProcessModel, Scheme,
                          MonteCarloConditionalExpectationRegression)
 from .models import (BlackScholesModel, HestonModel, MonteCarloAssetModel, MonteCarloBlackScholesModel,
                      LIBORVolatilityModelFourParameterExponentialForm, LIBORCorrelationModelExponentialDecay,

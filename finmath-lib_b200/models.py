@@ -454,10 +454,16 @@ class HullWhiteModel:
     constant coefficients (:584-795).  All coefficients are deterministic Scalars evaluated on the host in the reference's
     operation order; the fused kernel receives them as per-step tables (drift multipliers of x0, four factor loadings)."""
 
-    def __init__(self, randomVariableFactory, liborPeriodDiscretization, volatilityModel, properties=None):
+    def __init__(self, randomVariableFactory, liborPeriodDiscretization, volatilityModel, properties=None, discountFactors=None,
+                 discountFactorsFromForwardCurve=None):
+        """discountFactors[i] = discountCurve.getDiscountFactor(T_i) (or None: no discount curve), discountFactorsFromForwardCurve[i] =
+        DiscountCurveFromForwardCurve(forwardRateCurve).getDiscountFactor(T_i), both on the tenor grid (curves are host-side inputs)."""
         self.randomVariableFactory = randomVariableFactory if randomVariableFactory is not None else RandomVariableCudaFactory()
         self.liborPeriodDiscretization = liborPeriodDiscretization
         self.volatilityModel = volatilityModel
+        self.dfDiscount = None if discountFactors is None else np.asarray(discountFactors, dtype=np.float64)
+        self.dfForward = None if discountFactorsFromForwardCurve is None else np.asarray(discountFactorsFromForwardCurve, dtype=np.float64)
+        self._numeraireDiscountFactors, self._dfFromForwardCache, self._forwardRateCache = [], [], []
 
     def getNumberOfComponents(self): return 2
     def getNumberOfFactors(self): return 1                                                        # :287-290 (sic; the driver's count is used)
@@ -567,3 +573,107 @@ class HullWhiteModel:
             d1.append(c1.doubleValue())
             fl.append([f0[0].doubleValue(), f0[1].doubleValue(), f1[0].doubleValue(), f1[1].doubleValue()])
         return dict(kernel="hull_white", drift0=d0, drift1=d1, factorLoadings=np.array(fl), initialValues=[0.0, 0.0])
+
+    # ---- term structure functions of the Hull-White model (:305-357, :431-582, :797-950); deterministic parts are Scalars -------------
+    def getLiborPeriod(self, i): return self.liborPeriodDiscretization.getTime(i)
+    def getLiborPeriodIndex(self, t): return self.liborPeriodDiscretization.getTimeIndex(t)
+    def getNumberOfLibors(self): return self.liborPeriodDiscretization.getNumberOfTimeSteps()
+    def getModel(self): return self
+
+    def getShortRateConditionalVariance(self, time, maturity):                                     # :740-775
+        integral = Scalar(0.0)
+        ePrev = self.getMRTime(time, maturity).mult(-2).exp()
+        for timePrev, timeNext, m, v in self._segments(time, maturity):
+            eNext = self.getMRTime(timeNext, maturity).mult(-2).exp()
+            integral = integral.add(v.squared().div(m).mult(eNext.sub(ePrev).div(2)))
+            ePrev = eNext
+        return integral
+
+    def _forward_rate_initial_value(self, i):                                                      # :935-950
+        td = self.liborPeriodDiscretization
+        while len(self._forwardRateCache) <= i:
+            k = len(self._forwardRateCache)
+            self._forwardRateCache.append(self.getRandomVariableForConstant((self.dfForward[k] / self.dfForward[k + 1] - 1.0) / td.getTimeStep(k)))
+        return self._forwardRateCache[i]
+
+    def _df_from_forward_curve_at(self, timeIndex):                                                # :912-933
+        td = self.liborPeriodDiscretization
+        while len(self._dfFromForwardCache) <= timeIndex:
+            i = len(self._dfFromForwardCache)
+            if i == 0:
+                self._dfFromForwardCache.append(self.getRandomVariableForConstant(float(self.dfForward[0])))
+            else:
+                self._dfFromForwardCache.append(self._dfFromForwardCache[i - 1].div(self._forward_rate_initial_value(i - 1).mult(td.getTimeStep(i - 1)).add(1.0)))
+        return self._dfFromForwardCache[timeIndex]
+
+    def _curve_interpolated(self, time, at):                                                       # :845-860, :896-910
+        td = self.liborPeriodDiscretization
+        ti = td.getTimeIndex(time)
+        if ti >= 0:
+            return at(ti)
+        prev = min(-ti - 2, td.getNumberOfTimes() - 2)
+        tp, tn = td.getTime(prev), td.getTime(prev + 1)
+        a, b = at(prev), at(prev + 1)
+        return a.mult(b.div(a).pow((time - tp) / (tn - tp)))
+
+    def _df_from_forward_curve(self, time): return self._curve_interpolated(time, self._df_from_forward_curve_at)
+
+    def _discount_factor_at(self, timeIndex):                                                      # :862-889
+        td = self.liborPeriodDiscretization
+        if not self._numeraireDiscountFactors:
+            adj = self.getRandomVariableForConstant(float(self.dfDiscount[0]))
+            self._numeraireDiscountFactors.append(adj)
+            for i in range(td.getNumberOfTimeSteps()):
+                ts = td.getTimeStep(i)
+                adj = adj.discount(self.getRandomVariableForConstant((self.dfDiscount[i] / self.dfDiscount[i + 1] - 1.0) / ts), ts)
+                self._numeraireDiscountFactors.append(adj)
+        return self._numeraireDiscountFactors[timeIndex]
+
+    def _zero_rate_from_forward_curve(self, time):                                                 # :891-902 (same index twice: sic)
+        td = self.liborPeriodDiscretization
+        ti = td.getTimeIndex(time)
+        if ti < 0:
+            ti = min(-ti - 2, td.getNumberOfTimes() - 2)
+        d = self._df_from_forward_curve_at(ti)
+        return d.div(d).log().div(td.getTimeStep(ti))
+
+    def _short_rate(self, process, timeIndex):                                                     # :493-510
+        time = process.getTime(timeIndex)
+        value = process.getProcessValue(timeIndex, 0).add(self.getDV(0, time))
+        return value.add(self._zero_rate_from_forward_curve(time))
+
+    def _A(self, process, time, maturity):                                                         # :543-557
+        zeroRate = self._zero_rate_from_forward_curve(time)
+        forwardBond = self._df_from_forward_curve(maturity).div(self._df_from_forward_curve(time)).log()
+        B = self.getB(time, maturity)
+        return B.mult(zeroRate).sub(B.squared().mult(self.getShortRateConditionalVariance(0, time).div(2))).add(forwardBond).exp()
+
+    def getZeroCouponBond(self, process, time, maturity):                                          # :512-523
+        ti = process.getTimeIndex(time)
+        if ti < 0:
+            timeLo = process.getTime(-ti - 1 - 1)
+            return self.getZeroCouponBond(process, timeLo, maturity).div(self.getZeroCouponBond(process, timeLo, time))
+        return self._short_rate(process, ti).mult(self.getB(time, maturity).mult(-1)).exp().mult(self._A(process, time, maturity))
+
+    def getForwardRate(self, process, time, periodStart, periodEnd):                               # :431-435
+        return self.getZeroCouponBond(process, time, periodStart).div(self.getZeroCouponBond(process, time, periodEnd)).sub(1.0).div(periodEnd - periodStart)
+
+    def getLIBOR(self, process, timeIndex, liborIndex):                                            # :437-440
+        t = process.getTime(timeIndex)
+        return self.getZeroCouponBond(process, t, self.getLiborPeriod(liborIndex)).div(self.getZeroCouponBond(process, t, self.getLiborPeriod(liborIndex + 1))) \
+            .sub(1.0).div(self.liborPeriodDiscretization.getTimeStep(liborIndex))
+
+    def getNumeraire(self, process, time):                                                         # :305-357
+        if time == process.getTime(0):
+            return self.getRandomVariableForConstant(1.0)
+        ti = process.getTimeIndex(time)
+        if ti < 0:
+            raise NotImplementedError("Hull-White numeraire off the simulation grid (log-linear interpolation) is outside the hot path")
+        numeraireNormalized = process.getProcessValue(ti, 1).add(self.getV(0, time).mult(0.5)).exp()
+        numeraireNormalized = numeraireNormalized.mult(numeraireNormalized.invert().getAverage())   # control variate on the zero bond
+        fromForward = self._df_from_forward_curve(time)
+        if self.dfDiscount is not None:
+            discountFactor = self._curve_interpolated(time, self._discount_factor_at).div(fromForward.getAverage()).mult(fromForward)
+        else:
+            discountFactor = fromForward
+        return numeraireNormalized.div(discountFactor)

@@ -157,6 +157,56 @@ class BrownianMotionCuda:
         return hash((self.timeDiscretization, self.numberOfFactors, self.numberOfPaths, self.seed))
 
 
+
+class _BrownianMotionDecorator:
+    """Shared plumbing of the two wrappers below: they are not BrownianMotionCuda instances, so an Euler scheme on top of them
+    runs the generic device loop (one kernel per RandomVariable operation) — the fused kernels need the raw increment slab."""
+
+    def getIncrement(self, timeIndex, factor=None):
+        if factor is None:
+            return [self.getBrownianIncrement(timeIndex, f) for f in range(self.getNumberOfFactors())]
+        return self.getBrownianIncrement(timeIndex, factor)
+
+    def getTimeDiscretization(self): return self.brownianMotion.getTimeDiscretization()
+    def getNumberOfPaths(self): return self.brownianMotion.getNumberOfPaths()
+    def getRandomVariableForConstant(self, value): return self.brownianMotion.getRandomVariableForConstant(value)
+
+
+class BrownianMotionView(_BrownianMotionDecorator):
+    """J/montecarlo/BrownianMotionView.java:27-87 — a selection of factors of another Brownian motion (same device vectors)."""
+
+    def __init__(self, brownianMotion, factors):
+        self.brownianMotion, self.factors = brownianMotion, list(factors)
+
+    def getBrownianIncrement(self, timeIndex, factor): return self.brownianMotion.getBrownianIncrement(timeIndex, self.factors[factor])
+    def getNumberOfFactors(self): return len(self.factors)
+    def getCloneWithModifiedSeed(self, seed): return BrownianMotionView(self.brownianMotion.getCloneWithModifiedSeed(seed), self.factors)
+
+    def getCloneWithModifiedTimeDiscretization(self, td):
+        return BrownianMotionView(self.brownianMotion.getCloneWithModifiedTimeDiscretization(td), self.factors)
+
+
+class CorrelatedBrownianMotion(_BrownianMotionDecorator):
+    """J/montecarlo/CorrelatedBrownianMotion.java:45-110 — dW_factor = sum_k factorLoadings[factor][k] * dU_k, accumulated with
+    addProduct from a RandomVariableFromDoubleArray(0.0) in factor order, zero loadings skipped (:63-72)."""
+
+    def __init__(self, uncollelatedFactors, factorLoadings):
+        self.brownianMotion, self.factorLoadings = uncollelatedFactors, [list(map(float, row)) for row in factorLoadings]
+
+    def getBrownianIncrement(self, timeIndex, factor):
+        from .stochastic import RandomVariableFromDoubleArray
+        increment = RandomVariableFromDoubleArray(0.0)
+        for k, loading in enumerate(self.factorLoadings[factor]):
+            if loading != 0:
+                increment = increment.addProduct(self.brownianMotion.getBrownianIncrement(timeIndex, k), loading)
+        return increment
+
+    def getNumberOfFactors(self): return len(self.factorLoadings)
+    def getCloneWithModifiedSeed(self, seed): return CorrelatedBrownianMotion(self.brownianMotion.getCloneWithModifiedSeed(seed), self.factorLoadings)
+
+    def getCloneWithModifiedTimeDiscretization(self, td):
+        return CorrelatedBrownianMotion(self.brownianMotion.getCloneWithModifiedTimeDiscretization(td), self.factorLoadings)
+
 class Scheme:
     EULER, PREDICTOR_CORRECTOR, EULER_FUNCTIONAL, PREDICTOR_CORRECTOR_FUNCTIONAL = range(4)
 

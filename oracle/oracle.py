@@ -39,6 +39,7 @@ def lib():
         L.orc_lmm_bermudan.restype = C.c_double
         L.orc_time_lmm_reference_shaped.restype = C.c_double
         L.orc_time_lmm_fused.restype = C.c_double
+        L.orc_hull_white_caplet.restype = C.c_double
     return _LIB
 
 
@@ -295,3 +296,18 @@ def hull_white_process(seed, times, paths, vol_times, vol, mr, scheme=0, path_of
     lib().orc_hull_white_process(C.c_int(seed), tp, C.c_int(t.size), C.c_int(paths), C.c_int64(path_offset), vtp, C.c_int(vt.size), vp, mp_,
                                  C.c_int(scheme), proc.ctypes.data_as(c_dp), coef.ctypes.data_as(c_dp))
     return proc, coef
+
+
+def hull_white_caplet(seed, times, paths, vol_times, vol, mr, curve_times, df_discount, df_forward, scheme, maturity, period_length, strike):
+    t, tp = _d(times)
+    vt, vtp = _d(vol_times)
+    v, vp = _d(vol)
+    m, mp_ = _d(mr)
+    ct, ctp = _d(curve_times)
+    dd, ddp = _dn(df_discount)
+    dfw, dfwp = _d(df_forward)
+    vals, num, fr = np.empty(paths), np.empty(paths), np.empty(paths)
+    price = lib().orc_hull_white_caplet(C.c_int(seed), tp, C.c_int(t.size), C.c_int(paths), vtp, C.c_int(vt.size), vp, mp_, ctp, C.c_int(ct.size), ddp, dfwp,
+                                        C.c_int(scheme), C.c_double(maturity), C.c_double(period_length), C.c_double(strike),
+                                        vals.ctypes.data_as(c_dp), num.ctypes.data_as(c_dp), fr.ctypes.data_as(c_dp))
+    return price, vals, num, fr

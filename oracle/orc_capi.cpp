@@ -253,6 +253,31 @@ void orc_hull_white_process(int seed, const double* times, int nTimes, int paths
 	}
 }
 
+// Hull-White caplet (Caplet.java:114-160 on the Hull-White model's getForwardRate / getNumeraire); returns the price, fills values
+double orc_hull_white_caplet(int seed, const double* times, int nTimes, int paths, const double* volTimes, int nVolTimes, const double* vol, const double* mr,
+		const double* curveTimes, int nCurveTimes, const double* dfDiscount /* or NULL */, const double* dfForward, int scheme,
+		double maturity, double periodLength, double strike, double* valuesOut, double* numeraireOut /* at maturity+periodLength */, double* forwardRateOut) {
+	BrownianMotion bm(tdFrom(times, nTimes), 2, paths, seed, 0);
+	HullWhiteModel m;
+	m.volTimes = tdFrom(volTimes, nVolTimes);
+	m.vol = vecOf(vol, nVolTimes); m.mr = vecOf(mr, nVolTimes);
+	m.curveTimes = tdFrom(curveTimes, nCurveTimes);
+	if (dfDiscount) m.dfDiscount = vecOf(dfDiscount, nCurveTimes);
+	m.dfForward = vecOf(dfForward, nCurveTimes);
+	Process pr(&m, &bm, scheme);
+	const double paymentDate = maturity + periodLength;
+	P fr = m.getForwardRate(pr, maturity, maturity, paymentDate);
+	P numeraire = m.getNumeraire(pr, paymentDate);
+	P w = pr.getMonteCarloWeights();
+	P values = mult(floor(sub(fr, strike), 0.0), periodLength);
+	values = mult(div(values, numeraire), w);
+	values = div(mult(values, m.getNumeraire(pr, 0.0)), w);
+	if (valuesOut) store(values, valuesOut, paths);
+	if (numeraireOut) store(numeraire, numeraireOut, paths);
+	if (forwardRateOut) store(fr, forwardRateOut, paths);
+	return getAverage(values);
+}
+
 // ---- CPU baselines for bench.py (bounded samples) --------------------------------------------------------
 // (1) reference-shaped: the RV-op path above (one array pass + one allocation per op, single sequential MT stream).
 //     Returns seconds for {Brownian generation + Euler evolution} of `paths` LMM paths.

@@ -427,6 +427,106 @@ struct HullWhiteModel : ProcessModel {
 	P applyStateSpaceTransform(int, int, const P& y) override { return y; }
 	bool hasInverse() const override { return true; }
 	P applyStateSpaceTransformInverse(int, int, const P& x) override { return x; }
+
+	// ---- term structure functions (:305-357, :431-582, :797-950).  Curves are host inputs given on the curve time grid:
+	// dfDiscount[i] = discountCurve.getDiscountFactor(T_i), dfForward[i] = discountCurveFromForwardCurve.getDiscountFactor(T_i).
+	TimeDiscretization curveTimes;     // liborPeriodDiscretization (isInterpolateDiscountFactorsOnLiborPeriodDiscretization = true)
+	std::vector<double> dfDiscount, dfForward;
+	std::vector<P> numeraireDiscountFactors, dfFromForwardCache, forwardRateCache;
+
+	P getShortRateConditionalVariance(double time, double maturity) const {                    // :740-775
+		const int i0 = volIndex(time), i1 = volIndex(maturity);
+		P integral = scalar(0.0);
+		double timePrev = time, timeNext;
+		P ePrev = exp(mult(getMRTime(timePrev, maturity), -2));
+		for (int ti = i0 + 1; ti <= i1; ti++) {
+			timeNext = volTimes.getTime(ti);
+			P m = meanReversion(ti - 1), v = volatility(ti - 1);
+			P eNext = exp(mult(getMRTime(timeNext, maturity), -2));
+			integral = add(integral, mult(div(squared(v), m), div(sub(eNext, ePrev), 2)));
+			timePrev = timeNext; ePrev = eNext;
+		}
+		timeNext = maturity;
+		P m = meanReversion(i1), v = volatility(i1);
+		P eNext = exp(mult(getMRTime(timeNext, maturity), -2));
+		return add(integral, mult(div(squared(v), m), div(sub(eNext, ePrev), 2)));
+	}
+	P forwardRateInitialValue(int i) {                                                         // :935-950
+		while ((int)forwardRateCache.size() <= i) {
+			const int k = (int)forwardRateCache.size();
+			forwardRateCache.push_back(scalar((dfForward[k] / dfForward[k + 1] - 1.0) / curveTimes.getTimeStep(k)));
+		}
+		return forwardRateCache[i];
+	}
+	P dfFromForwardCurveAt(int timeIndex) {                                                    // :912-933
+		while ((int)dfFromForwardCache.size() <= timeIndex) {
+			const int i = (int)dfFromForwardCache.size();
+			if (i == 0) dfFromForwardCache.push_back(scalar(dfForward[0]));
+			else dfFromForwardCache.push_back(div(dfFromForwardCache[i - 1], add(mult(forwardRateInitialValue(i - 1), curveTimes.getTimeStep(i - 1)), 1.0)));
+		}
+		return dfFromForwardCache[timeIndex];
+	}
+	P curveInterp(double time, const std::function<P(int)>& at) {                              // :845-860, :896-910
+		const int ti = curveTimes.getTimeIndex(time);
+		if (ti >= 0) return at(ti);
+		const int prev = std::min(-ti - 2, curveTimes.getNumberOfTimes() - 2), next = prev + 1;
+		const double tp = curveTimes.getTime(prev), tn = curveTimes.getTime(next);
+		P a = at(prev), b = at(next);
+		return mult(a, pow(div(b, a), (time - tp) / (tn - tp)));
+	}
+	P dfFromForwardCurve(double time) { return curveInterp(time, [this](int i) { return dfFromForwardCurveAt(i); }); }
+	P discountFactorAt(int timeIndex) {                                                        // :862-889
+		if (numeraireDiscountFactors.empty()) {
+			P adj = scalar(dfDiscount[0]);
+			numeraireDiscountFactors.push_back(adj);
+			for (int i = 0; i < curveTimes.getNumberOfTimeSteps(); i++) {
+				const double ts = curveTimes.getTimeStep(i);
+				adj = discount(adj, scalar((dfDiscount[i] / dfDiscount[i + 1] - 1.0) / ts), ts);
+				numeraireDiscountFactors.push_back(adj);
+			}
+		}
+		return numeraireDiscountFactors.at(timeIndex);
+	}
+	P discountFactor(double time) { return curveInterp(time, [this](int i) { return discountFactorAt(i); }); }
+	P zeroRateFromForwardCurve(double time) {                                                  // :891-902 (same index twice: sic)
+		int ti = curveTimes.getTimeIndex(time);
+		if (ti < 0) ti = std::min(-ti - 2, curveTimes.getNumberOfTimes() - 2);
+		return div(log(div(dfFromForwardCurveAt(ti), dfFromForwardCurveAt(ti))), curveTimes.getTimeStep(ti));
+	}
+	P getShortRate(Process& p, int timeIndex) {                                                // :493-510
+		const double time = p.getTime(timeIndex);
+		P value = add(p.getProcessValue(timeIndex, 0), getDV(0, time));
+		return add(value, zeroRateFromForwardCurve(time));
+	}
+	P getA(Process& p, double time, double maturity) {                                         // :543-557
+		P zeroRate = zeroRateFromForwardCurve(time);
+		P forwardBond = log(div(dfFromForwardCurve(maturity), dfFromForwardCurve(time)));
+		P B = getB(time, maturity);
+		P lnA = add(sub(mult(B, zeroRate), mult(squared(B), div(getShortRateConditionalVariance(0, time), 2))), forwardBond);
+		return exp(lnA);
+	}
+	P getZeroCouponBond(Process& p, double time, double maturity) {                            // :512-523
+		const int ti = p.getTimeIndex(time);
+		if (ti < 0) {
+			const double timeLo = p.getTime(-ti - 1 - 1);
+			return div(getZeroCouponBond(p, timeLo, maturity), getZeroCouponBond(p, timeLo, time));
+		}
+		return mult(exp(mult(getShortRate(p, ti), mult(getB(time, maturity), -1))), getA(p, time, maturity));
+	}
+	P getForwardRate(Process& p, double time, double periodStart, double periodEnd) {          // :431-435
+		return div(sub(div(getZeroCouponBond(p, time, periodStart), getZeroCouponBond(p, time, periodEnd)), 1.0), periodEnd - periodStart);
+	}
+	P getNumeraire(Process& p, double time) {                                                  // :305-357
+		if (time == p.getTime(0)) return scalar(1.0);
+		const int ti = p.getTimeIndex(time);
+		if (ti < 0) throw std::runtime_error("oracle: Hull-White numeraire off the simulation grid not restated");
+		P logNum = add(p.getProcessValue(ti, 1), mult(getV(0, time), 0.5));
+		P n = exp(logNum);
+		n = mult(n, getAverage(invert(n)));
+		P df = dfDiscount.empty() ? dfFromForwardCurve(time)
+			: mult(div(discountFactor(time), getAverage(dfFromForwardCurve(time))), dfFromForwardCurve(time));
+		return div(n, df);
+	}
 };
 
 } // namespace orc

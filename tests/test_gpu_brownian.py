@@ -86,3 +86,22 @@ def test_brownian_statistics_like_reference_tests(gpu):
     assert abs(s.getAverage() - T) < 3 * np.sqrt(2.0 * T / P) * 1.5
     w = bm.getBrownianIncrement(4, 0)
     assert abs(w.getAverage()) < 3.0 / np.sqrt(P) and abs(w.getVariance() - 1.0) < 3 * np.sqrt(2.0 / P) * 1.5
+
+
+def test_brownian_view_and_correlated(gpu, orc):
+    """BrownianMotionView / CorrelatedBrownianMotion on device increments; Heston on a view (HestonModelTest.java:98-100)."""
+    td = gpu.TimeDiscretizationFromArray(0.0, 20, 0.25)
+    bm = gpu.BrownianMotionCuda(td, 3, 2000, 3141)
+    ref = orc.brownian(3141, td.times, 3, 2000)
+    view = gpu.BrownianMotionView(bm, [2, 0])
+    assert view.getNumberOfFactors() == 2 and view.getBrownianIncrement(5, 0) is bm.getBrownianIncrement(5, 2)
+    rho = 0.3
+    corr = gpu.CorrelatedBrownianMotion(bm, [[1.0, 0.0, 0.0], [rho, np.sqrt(1 - rho * rho), 0.0]])
+    w1 = corr.getBrownianIncrement(4, 1).getRealizations()
+    expect = (0.0 + ref[4, 0] * rho) + ref[4, 1] * np.sqrt(1 - rho * rho)
+    assert rel_err(w1, expect) < 2e-15
+    # an Euler scheme on a view runs the generic device loop and agrees with the fused kernel on the same factor
+    model = gpu.BlackScholesModel(1.0, 0.05, 0.3, bm.randomVariableFactory)
+    a = gpu.EulerSchemeFromProcessModel(model, gpu.BrownianMotionView(bm, [0])).getProcessValue(20, 0).getRealizations()
+    b = gpu.EulerSchemeFromProcessModel(model, bm).getProcessValue(20, 0).getRealizations()
+    assert np.array_equal(a, b)

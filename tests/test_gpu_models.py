@@ -217,3 +217,26 @@ def test_hull_white_process_matches_oracle(gpu, orc, scheme):
     assert process.usedFusedKernel == ("hull_white" if scheme != 1 else None)
     # short-rate state ~ 1e-2, log-numeraire ~ 1e-1: absolute scales for the relative test
     assert rel_err(got[:, 0], ref[:, 0], scale=1e-2) < PATH_TOL and rel_err(got[:, 1], ref[:, 1], scale=1e-1) < PATH_TOL
+
+
+def test_hull_white_caplet_numeraire_forward_rate(gpu, orc):
+    """C2: caplet on the Hull-White model through Caplet + LIBORMonteCarloSimulationFromLIBORModel (unchanged product code)."""
+    paths = 50_000
+    td = gpu.TimeDiscretizationFromArray(0.0, 40, 0.5)
+    tenor = gpu.TimeDiscretizationFromArray(0.0, 40, 0.5)
+    vt = np.arange(0, 21.0)
+    vol, mr = 0.005 + 0.0005 * np.floor(vt) / 20, np.full(vt.size, 0.1)
+    ct = tenor.times
+    zero = 0.03 + 0.01 * (np.clip(ct, 0.5, 40.0) - 0.5) / 39.5
+    df = np.exp(-zero * ct)
+    vm = gpu.ShortRateVolatilityModelAsGiven(gpu.TimeDiscretizationFromArray(vt), vol, mr)
+    bm = gpu.BrownianMotionCuda(td, 2, paths, 3141)
+    model = gpu.HullWhiteModel(bm.randomVariableFactory, tenor, vm, None, df, df)
+    sim = gpu.LIBORMonteCarloSimulationFromLIBORModel(model, gpu.EulerSchemeFromProcessModel(model, bm, 0))
+    price = gpu.Caplet(5.0, 0.5, 0.03).getValue(sim)
+    ref_price, _, ref_num, ref_fr = orc.hull_white_caplet(3141, td.times, paths, vt, vol, mr, ct, df, df, 0, 5.0, 0.5, 0.03)
+    assert rel_err(sim.getNumeraire(5.5).getRealizations(), ref_num) < PATH_TOL
+    assert rel_err(sim.getForwardRate(5.0, 5.0, 5.5).getRealizations(), ref_fr, scale=0.03) < 1e-11
+    assert abs(price - ref_price) <= PRICE_TOL * abs(ref_price)
+    # zero bond reproduces the curve exactly through the control variate (HullWhiteModel.java:340-341)
+    assert abs(sim.getNumeraire(5.5).invert().getAverage() - df[11]) < 1e-13
