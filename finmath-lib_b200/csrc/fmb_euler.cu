@@ -37,21 +37,24 @@ __device__ __forceinline__ double jmaxE(double a, double b) {
 
 enum { SCHEME_EULER = 0, SCHEME_PC = 1, SCHEME_EULER_FUNCTIONAL = 2, SCHEME_PC_FUNCTIONAL = 3 };
 
+// a*b + c: STRICT = rounded product then rounded sum (the JVM never contracts); FAST (fmb_set_fp_mode(1)) = one fused multiply-add.
+template <bool FAST> __device__ __forceinline__ double mad(double a, double b, double c) { return FAST ? fma(a, b, c) : a * b + c; }
+
 // ---------------------------------------------------------------------------------------------------------------
 // Black-Scholes: BlackScholesModel.java:60-139.  Y += (r - sigma^2/2) dt + sigma dW ; X = exp(Y); functional schemes
 // re-apply log every step (:235-237 of the Euler scheme).  The drift does not depend on the state, so the corrector adds
 // ((mu - mu)/2)*dt = +0.0 and PREDICTOR_CORRECTOR reproduces EULER bit for bit.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) eulerBlackScholesKernel(int functional, int T, int F, uint64_t P, const double* __restrict__ dt,
+template <bool FAST> __global__ void __launch_bounds__(256) eulerBlackScholesKernel(int functional, int T, int F, uint64_t P, const double* __restrict__ dt,
 		const double* const* __restrict__ dW, double* const* __restrict__ X, double x0, double y0, double ylog0, double drift, double sigma) {
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 	for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < P; p += stride) {
-		double x = x0, y = y0;
+		double x = x0, y = functional ? ylog0 : y0;
 		for (int t = 0; t < T; t++) {
-			if (functional) y = (t == 0) ? ylog0 : flog(x);
+			if (functional && !FAST && t > 0) y = flog(x);          // FAST: log(exp(y)) == y up to one rounding, the state is carried
 			const double w = dW[(size_t)t * F][p];
-			y = y + drift * dt[t];
-			y = y + w * sigma;
+			y = mad<FAST>(drift, dt[t], y);
+			y = mad<FAST>(w, sigma, y);
 			x = fexp(y);
 			X[t + 1][p] = x;
 		}
@@ -140,8 +143,8 @@ __global__ void __launch_bounds__(256) eulerHullWhiteKernel(int T, uint64_t P, c
 // Y (non-functional schemes) and mu (predictor-corrector) live in a block-private, L2-resident global scratch.
 // ---------------------------------------------------------------------------------------------------------------
 struct LmmParams {
-	int scheme, measure, hasCap;
-	double cap;
+	int scheme, measure, hasCap, capFix;
+	double cap, logCap;
 	int T, N, F, recStride;
 	const double* dt;        // [T]
 	const int* firstLive;    // [T]
@@ -177,7 +180,7 @@ template <int FT> struct LmmRec {
 // U consecutive live rates of one path at once (i = position in processing order; j = first+i for the spot measure,
 // N-1-i for the terminal measure).  Per rate the operations and their order are exactly those of the scalar recipe; the
 // only cross-rate dependency is the running factor sum S, so the U log / exp / reciprocal chains overlap (ILP U).
-template <int FT, bool LOGN, int MODE, int U, bool CORRECTOR, bool PARTIAL>
+template <int FT, bool LOGN, int MODE, int U, bool CORRECTOR, bool PARTIAL, bool FAST>
 __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __restrict__ rect, int j0, int jStep, int BD, int F, bool spot, bool functional,
 		bool firstStep, double d, const double* w, double* S, double* Lcol, double* Ybuf, double* Mbuf, uint64_t p, int cnt) {
 	// PARTIAL: only the first cnt (< U) rates are real; the others recompute rate cnt-1 and are masked out of S and of every store,
@@ -185,7 +188,6 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 	constexpr int FMAX = FT > 0 ? FT : 16;
 	LmmRec<FT> r[U];
 	double L[U], a[U], mu[U], y[U], Ln[U];
-#pragma unroll
 	int jj[U];
 #pragma unroll
 	for (int u = 0; u < U; u++) {
@@ -218,14 +220,14 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 		const bool valid = !PARTIAL || u < cnt;
 		if (spot && valid) {
 #pragma unroll
-			for (int k = 0; k < FMAX; k++) if (k < F) S[k] = S[k] + a[u] * r[u].fl[k];
+			for (int k = 0; k < FMAX; k++) if (k < F) S[k] = mad<FAST>(a[u], r[u].fl[k], S[k]);
 		}
-		double m = S[0] * r[u].fl[0] + 0.0;
+		double m = FAST ? S[0] * r[u].fl[0] : S[0] * r[u].fl[0] + 0.0;
 #pragma unroll
-		for (int k = 1; k < FMAX; k++) if (k < F) m = m + S[k] * r[u].fl[k];
+		for (int k = 1; k < FMAX; k++) if (k < F) m = mad<FAST>(S[k], r[u].fl[k], m);
 		if (!spot && valid) {
 #pragma unroll
-			for (int k = 0; k < FMAX; k++) if (k < F) S[k] = S[k] + a[u] * r[u].fl[k];
+			for (int k = 0; k < FMAX; k++) if (k < F) S[k] = mad<FAST>(a[u], r[u].fl[k], S[k]);
 		}
 		if (LOGN) m = m + r[u].hv;
 		mu[u] = m;
@@ -233,15 +235,15 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 	if (!CORRECTOR) {
 #pragma unroll
 		for (int u = 0; u < U; u++) {
-			y[u] = y[u] + mu[u] * d;
+			y[u] = mad<FAST>(mu[u], d, y[u]);
 #pragma unroll
-			for (int k = 0; k < FMAX; k++) if (k < F) y[u] = y[u] + w[k] * r[u].fl[k];
+			for (int k = 0; k < FMAX; k++) if (k < F) y[u] = mad<FAST>(w[k], r[u].fl[k], y[u]);
 		}
 	} else {
 #pragma unroll
 		for (int u = 0; u < U; u++) {
 			y[u] = Ybuf[(size_t)jj[u] * BD];
-			y[u] = y[u] + ((mu[u] - Mbuf[(size_t)jj[u] * BD]) / 2.0) * d;
+			y[u] = mad<FAST>((mu[u] - Mbuf[(size_t)jj[u] * BD]) / 2.0, d, y[u]);
 		}
 	}
 	if (LOGN) fexpN<U>(y, Ln);
@@ -254,6 +256,8 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 		if (PARTIAL && u >= cnt) continue;
 		const int j = jj[u];
 		if (q.hasCap) Ln[u] = jminE(Ln[u], q.cap);
+		// carried state of a capped rate at the END of a step: log(cap), what the functional scheme would re-derive from X
+		if (FAST && (MODE != 2 || CORRECTOR) && q.capFix && Ln[u] == q.cap) y[u] = q.logCap;
 		Lcol[j * BD] = Ln[u];
 		if (MODE != 0) Ybuf[(size_t)j * BD] = y[u];
 		if (MODE == 2 && !CORRECTOR) Mbuf[(size_t)j * BD] = mu[u]; else r[u].xrow[p] = Ln[u];
@@ -262,7 +266,7 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 
 // MODE 0: EULER_FUNCTIONAL (state = L in shared memory only).  MODE 1: EULER (Y carried in scratch).
 // MODE 2: PREDICTOR_CORRECTOR[_FUNCTIONAL] (Y and the predictor drift in scratch).
-template <int FT, bool LOGN, int MODE> __global__ void __launch_bounds__(128, FMB_LMM_MINB) eulerLmmKernel(LmmParams q, uint64_t P,
+template <int FT, bool LOGN, int MODE, bool FAST> __global__ void __launch_bounds__(128, FMB_LMM_MINB) eulerLmmKernel(LmmParams q, uint64_t P,
 		const double* const* __restrict__ dW, double* __restrict__ scratch) {
 	extern __shared__ double Lsh[];                       // [N][blockDim]
 	const int BD = blockDim.x, tid = threadIdx.x;
@@ -302,17 +306,17 @@ template <int FT, bool LOGN, int MODE> __global__ void __launch_bounds__(128, FM
 			const int live = N - first, jBeg = spot ? first : N - 1, jStep = spot ? 1 : -1;
 			int i = 0;
 			for (; i + U <= live; i += U)
-				lmmChunk<FT, LOGN, MODE, U, false, false>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p, U);
+				lmmChunk<FT, LOGN, MODE, U, false, false, FAST>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p, U);
 			if (i < live)
-				lmmChunk<FT, LOGN, MODE, U, false, true>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p, live - i);
+				lmmChunk<FT, LOGN, MODE, U, false, true, FAST>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p, live - i);
 			if (MODE == 2) {
 				// corrector: drift re-evaluated on the predicted rates (EulerSchemeFromProcessModel.java:292-314)
 #pragma unroll
 				for (int k = 0; k < FMAX; k++) S[k] = 0.0;
 				for (i = 0; i + U <= live; i += U)
-					lmmChunk<FT, LOGN, MODE, U, true, false>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p, U);
+					lmmChunk<FT, LOGN, MODE, U, true, false, FAST>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p, U);
 				if (i < live)
-					lmmChunk<FT, LOGN, MODE, U, true, true>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p, live - i);
+					lmmChunk<FT, LOGN, MODE, U, true, true, FAST>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p, live - i);
 			}
 		}
 	}
@@ -390,8 +394,12 @@ int fmb_euler_black_scholes(int scheme, int T, int F, uint64_t paths, const doub
 		const double y0 = std::log(initial_value), x0 = std::exp(y0), ylog0 = std::log(x0);
 		const int functional = (scheme == SCHEME_EULER_FUNCTIONAL || scheme == SCHEME_PC_FUNCTIONAL) ? 1 : 0;
 		const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * 8, (paths + 255) / 256));
-		eulerBlackScholesKernel<<<grid, 256, 0, c.stream>>>(functional, T, F, paths, blob.at<double>(oDt), blob.at<const double*>(oInc),
-		                                                   (double* const*)blob.at<double*>(oRows), x0, y0, ylog0, drift, volatility);
+		if (c.fpMode.load() == 1)
+			eulerBlackScholesKernel<true><<<grid, 256, 0, c.stream>>>(functional, T, F, paths, blob.at<double>(oDt), blob.at<const double*>(oInc),
+			                                                         (double* const*)blob.at<double*>(oRows), x0, y0, ylog0, drift, volatility);
+		else
+			eulerBlackScholesKernel<false><<<grid, 256, 0, c.stream>>>(functional, T, F, paths, blob.at<double>(oDt), blob.at<const double*>(oInc),
+			                                                          (double* const*)blob.at<double*>(oRows), x0, y0, ylog0, drift, volatility);
 		rc = launchCheck("euler_black_scholes");
 	}
 	if (rc == FMB_OK) {
@@ -530,7 +538,14 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
 	size_t scratchBytes = 0;
 	if (rc == FMB_OK && liveRows) {
 		LmmParams q;
-		q.scheme = scheme; q.measure = measure; q.hasCap = std::isinf(libor_cap) ? 0 : 1; q.cap = libor_cap;
+		// FAST (fmb_set_fp_mode(1)): FMA contraction, and the functional schemes carry Y instead of re-deriving it as log(exp(Y)) every
+		// step (equal up to one rounding of Y per step; a capped rate carries log(cap)).  Only for the log-normal model.
+		const bool fast = (c.fpMode.load() == 1) && state_space == 1;
+		const bool functionalScheme = (scheme == SCHEME_EULER_FUNCTIONAL || scheme == SCHEME_PC_FUNCTIONAL);
+		int kernelScheme = scheme;
+		if (fast && functionalScheme) kernelScheme = (scheme == SCHEME_EULER_FUNCTIONAL) ? SCHEME_EULER : SCHEME_PC;
+		q.scheme = kernelScheme; q.measure = measure; q.hasCap = std::isinf(libor_cap) ? 0 : 1; q.cap = libor_cap;
+		q.capFix = (fast && functionalScheme && q.hasCap) ? 1 : 0; q.logCap = q.hasCap ? std::log(libor_cap) : 0.0;
 		q.T = T; q.N = N; q.F = F; q.recStride = RS;
 		q.dt = blob.at<double>(oDt); q.firstLive = blob.at<int>(oFirst); q.rec = blob.at<double>(oRec);
 		q.x0 = blob.at<double>(oX0); q.y0 = blob.at<double>(oY0); q.ylog0 = blob.at<double>(oYl);
@@ -544,7 +559,7 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
 			const int perSm = (int)std::max<size_t>(1, std::min<size_t>(16, (220 * 1024) / std::max<size_t>(smem, 1)));
 			const uint64_t tiles = (paths + BD - 1) / BD;
 			const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * perSm, tiles));
-			const int mode = scheme == SCHEME_EULER_FUNCTIONAL ? 0 : (scheme == SCHEME_EULER ? 1 : 2);
+			const int mode = kernelScheme == SCHEME_EULER_FUNCTIONAL ? 0 : (kernelScheme == SCHEME_EULER ? 1 : 2);
 			scratchBytes = mode != 0 ? (size_t)grid * 2 * N * BD * sizeof(double) : 16;
 			rc = poolAlloc(scratchBytes, &scratch);
 			if (rc == FMB_OK) {
@@ -553,8 +568,9 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
 					kernel<<<grid, BD, smem, c.stream>>>(q, paths, blob.at<const double*>(oInc), (double*)scratch);
 				};
 #define LMM_MODE(FTV, LOGNV) \
-				switch (mode) { case 0: launch(eulerLmmKernel<FTV, LOGNV, 0>); break; case 1: launch(eulerLmmKernel<FTV, LOGNV, 1>); break; default: launch(eulerLmmKernel<FTV, LOGNV, 2>); break; }
-#define LMM_LOGN(FTV) if (state_space == 1) { LMM_MODE(FTV, true) } else { LMM_MODE(FTV, false) }
+				switch (mode) { case 0: launch(eulerLmmKernel<FTV, LOGNV, 0, false>); break; case 1: launch(eulerLmmKernel<FTV, LOGNV, 1, false>); break; default: launch(eulerLmmKernel<FTV, LOGNV, 2, false>); break; }
+#define LMM_FAST(FTV) if (mode == 1) launch(eulerLmmKernel<FTV, true, 1, true>); else launch(eulerLmmKernel<FTV, true, 2, true>);
+#define LMM_LOGN(FTV) if (fast) { LMM_FAST(FTV) } else if (state_space == 1) { LMM_MODE(FTV, true) } else { LMM_MODE(FTV, false) }
 				switch (F) {
 				case 1: LMM_LOGN(1) break;
 				case 2: LMM_LOGN(2) break;
@@ -562,6 +578,7 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
 				default: LMM_LOGN(0) break;
 				}
 #undef LMM_LOGN
+#undef LMM_FAST
 #undef LMM_MODE
 				rc = launchCheck("euler_lmm");
 			}

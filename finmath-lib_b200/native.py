@@ -218,3 +218,9 @@ def timer_stop_ms():
     ms = C.c_float()
     check(load().fmb_timer_stop_ms(C.byref(ms)))
     return ms.value
+
+
+def set_fp_mode(mode):
+    """0 = STRICT (default: reference operation order, no FMA contraction), 1 = FAST (FMA contraction; functional schemes carry the
+    log-state instead of re-deriving it as log(exp(y)) each step) — both within 1e-12 of the reference's paths."""
+    check(load().fmb_set_fp_mode(int(mode)))

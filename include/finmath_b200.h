@@ -44,7 +44,8 @@ int fmb_device_count(int* count);
 int fmb_device_name(char* buf, int len);
 int fmb_synchronize(void);
 /* 0 = STRICT (default): reference operation order, no FMA contraction -> as close to the JVM's arithmetic as the
- * device's exp/log allow.  1 = FAST: FMA contraction allowed in the fused kernels (still within 1e-12 of the reference). */
+ * device's exp/log allow.  1 = FAST (fused LMM / Black-Scholes kernels): FMA contraction, functional schemes carry the
+ * log-state instead of log(exp(y)) per step (a capped rate carries log(cap)); still within 1e-12 of the reference. */
 int fmb_set_fp_mode(int mode);
 int fmb_get_fp_mode(int* mode);
 /* device event timing on the library's compute stream (used by bench.py; torch.cuda.Event cannot see this stream) */

@@ -240,3 +240,35 @@ def test_hull_white_caplet_numeraire_forward_rate(gpu, orc):
     assert abs(price - ref_price) <= PRICE_TOL * abs(ref_price)
     # zero bond reproduces the curve exactly through the control variate (HullWhiteModel.java:340-341)
     assert abs(sim.getNumeraire(5.5).invert().getAverage() - df[11]) < 1e-13
+
+
+# ---- FAST floating-point mode -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scheme,cap", [(2, 1e5), (3, 1e5), (0, 1e5), (1, 1e5), (2, 0.08), (3, 0.08)])
+def test_fast_mode_lmm_within_path_tolerance(gpu, orc, scheme, cap):
+    """fmb_set_fp_mode(1): FMA contraction + carried log-state.  Still within the 1e-12 path tolerance of the north star."""
+    paths = 3000
+    s = lmm_setup(gpu)
+    ref = lmm_oracle(orc, s, paths, scheme=scheme, libor_cap=cap).process()
+    gpu.native.set_fp_mode(1)
+    try:
+        dev = lmm_device(gpu, s, paths, scheme=scheme, libor_cap=cap)
+        got = device_process_array(dev, s["T"], s["N"])
+    finally:
+        gpu.native.set_fp_mode(0)
+    strict = device_process_array(lmm_device(gpu, s, paths, scheme=scheme, libor_cap=cap), s["T"], s["N"])
+    assert rel_err(got, ref, scale=0.05) < PATH_TOL
+    assert not np.array_equal(got, strict)                      # it really is a different arithmetic
+    assert rel_err(strict, ref, scale=0.05) < PATH_TOL
+
+
+def test_fast_mode_black_scholes(gpu, orc):
+    td = gpu.TimeDiscretizationFromArray(0.0, 100, 0.05)
+    ref_price, ref_proc, _ = orc.bs_european(3141, td.times, 20000, 1.0, 0.05, 0.30, 2, 5.0, 1.05)
+    gpu.native.set_fp_mode(1)
+    try:
+        mc = gpu.MonteCarloBlackScholesModel(td, 20000, 1.0, 0.05, 0.30)
+        price = gpu.EuropeanOption(5.0, 1.05).getValue(mc)
+        got = mc.getAssetValue(5.0, 0).getRealizations()
+    finally:
+        gpu.native.set_fp_mode(0)
+    assert rel_err(got, ref_proc[100, 0]) < PATH_TOL and abs(price - ref_price) <= PRICE_TOL * abs(ref_price)
