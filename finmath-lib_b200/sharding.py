@@ -54,15 +54,19 @@ class ShardContext:
         n = len(values)
         bufs = self._buffers.get(n)
         if bufs is None:
-            dev = self.device if self.device is not None else "cpu"
-            src_host = torch.empty(n, dtype=torch.float64, pin_memory=self.device is not None)
-            bufs = (src_host, torch.empty(n, dtype=torch.float64, device=dev), torch.empty(self.world * n, dtype=torch.float64, device=dev))
+            on_gpu = self.device is not None
+            dev = self.device if on_gpu else "cpu"
+            src_host = torch.empty(n, dtype=torch.float64, pin_memory=on_gpu)
+            out_host = torch.empty(self.world * n, dtype=torch.float64, pin_memory=on_gpu)
+            bufs = (src_host, src_host.numpy(), torch.empty(n, dtype=torch.float64, device=dev),
+                    torch.empty(self.world * n, dtype=torch.float64, device=dev), out_host, out_host.numpy())
             self._buffers[n] = bufs
-        src_host, src, out = bufs
-        src_host.copy_(torch.as_tensor(values, dtype=torch.float64))
+        src_host, src_np, src, out, out_host, out_np = bufs
+        src_np[:] = values
         src.copy_(src_host, non_blocking=True)
         dist.all_gather_into_tensor(out, src, group=self.group)
-        return out.cpu().numpy().reshape(self.world, n).copy()
+        out_host.copy_(out)                                  # synchronising device-to-host copy into the cached pinned buffer
+        return out_np.reshape(self.world, n).copy()
 
     def sum_dd(self, hi, lo):
         if self.world == 1:
