@@ -292,7 +292,11 @@ __global__ void uniformsFromWordsKernel(const uint32_t* __restrict__ w, double* 
 // consecutive paths (coalesced, whole 32-byte sectors).
 // Algorithmic HBM bytes: 8 per increment (write only).
 // ---------------------------------------------------------------------------------------------------------------
-static const int BM_THREADS = 256;
+#ifndef FMB_BM_THREADS
+#define FMB_BM_THREADS 512
+#endif
+static const int BM_THREADS = FMB_BM_THREADS;
+static const int BM_CHECK_EVERY = (BM_THREADS >= 512) ? 2 : 4;      // batches between two looks at the tail queue
 static const int RING = 2048;
 static const int TAILQ = 2048;        // deferred tail draws per block (p and tile slot), drained densely
 
@@ -324,9 +328,11 @@ __global__ void __launch_bounds__(BM_THREADS) bmGenerateKernel(const uint32_t* _
 	if (tid == 0) qCount = 0;
 	__syncthreads();
 
-	// ring positions (mod RING) of the next raw word to generate and of the next unconsumed word (always even), and their distance
-	uint32_t gpos = MT_N, cpos = MT_N;
+	// ring positions (mod RING) of the next raw word to generate and of the next unconsumed word (always even), and their distance.
+	// Each refreshing thread keeps its four ring indices and advances them by 227 per refresh step.
+	uint32_t cpos = MT_N;
 	int avail = 0;
+	uint32_t iNew = (MT_N + tid) & (RING - 1), iM = (MT_N + tid - 227) & (RING - 1), i0 = tid & (RING - 1), i1 = (tid + 1) & (RING - 1);
 	const uint64_t pBeg = (uint64_t)blockIdx.x * ppb;
 	const uint64_t pEnd = min(P, pBeg + (uint64_t)ppb);
 	// (path in tile, column) of this thread's draw, advanced by BM_THREADS draws per iteration without divisions
@@ -339,11 +345,9 @@ __global__ void __launch_bounds__(BM_THREADS) bmGenerateKernel(const uint32_t* _
 		for (uint32_t u0 = 0; u0 < U; u0 += BM_THREADS) {
 			const uint32_t need = min((uint32_t)BM_THREADS, U - u0);
 			while (avail < (int)(2 * need)) {
-				if (tid < 227) {
-					const uint32_t j = gpos + tid;
-					ring[j & (RING - 1)] = ring[(j - 227) & (RING - 1)] ^ mtTwist(ring[(j - MT_N) & (RING - 1)], ring[(j - MT_N + 1) & (RING - 1)]);
-				}
-				gpos = (gpos + 227) & (RING - 1);
+				if (tid < 227) ring[iNew] = ring[iM] ^ mtTwist(ring[i0], ring[i1]);
+				iNew = (iNew + 227) & (RING - 1); iM = (iM + 227) & (RING - 1);
+				i0 = (i0 + 227) & (RING - 1); i1 = (i1 + 227) & (RING - 1);
 				avail += 227;
 				__syncthreads();
 			}
@@ -365,10 +369,10 @@ __global__ void __launch_bounds__(BM_THREADS) bmGenerateKernel(const uint32_t* _
 			avail -= (int)(2 * need);
 			pl += stepP; c += stepC;
 			if (c >= TF) { c -= TF; pl++; }
-			// every 4th batch: make sure the queue keeps room for the next four (at most 4 * BM_THREADS new tails)
-			if ((++it & 3u) == 0) {
+			// every BM_CHECK_EVERY-th batch: make sure the queue keeps room for the next ones (at most BM_THREADS new tails per batch)
+			if ((++it & (BM_CHECK_EVERY - 1)) == 0) {
 				__syncthreads();
-				if (qCount > TAILQ - 5 * BM_THREADS) {
+				if (qCount > TAILQ - (BM_CHECK_EVERY + 1) * BM_THREADS) {
 					bmDrainTails(qP, qSlot, qCount, tile, sq, nPad, tid);
 					__syncthreads();
 					if (tid == 0) qCount = 0;

@@ -149,3 +149,36 @@ def test_pool_reuse_and_handle_errors(gpu):
     assert lib.fmb_rv_download(h, nv.dptr(out), 1000) == nv.FMB_EHANDLE                         # freed handle is rejected, not dereferenced
     with pytest.raises(ValueError):
         nv.binary(0, nv.DeviceVector.upload(np.zeros(3)), 0.0, nv.DeviceVector.upload(np.zeros(4)), 0.0)
+
+
+def test_concurrent_callers_like_the_reference_thread_pool(gpu):
+    """EulerSchemeFromProcessModel.java:199,:232-269 submits one task per component to a thread pool, and the JVM frees from GC
+    threads: the C ABI must be re-entrant.  8 host threads hammer ops, reductions and frees concurrently (ctypes drops the GIL)."""
+    import threading
+    RV = gpu.RandomVariableCuda
+    n = 200_003
+    base = np.linspace(0.5, 2.5, n)
+    errors = []
+
+    def worker(k):
+        try:
+            x = RV(float(k), base * (k + 1))
+            for it in range(30):
+                y = x.mult(2.0).add(x).sub(x.mult(3.0)).add(1.0)          # == 1.0 everywhere (exact: 2x + x - 3x for these magnitudes up to rounding)
+                z = x.log().exp().div(x)
+                s = x.squared().getAverage()
+                if abs(y.getAverage() - 1.0) > 1e-12 or abs(z.getAverage() - 1.0) > 1e-12:
+                    errors.append(("value", k, it))
+                ref = float(np.mean((base * (k + 1)) ** 2))
+                if abs(s - ref) > 1e-12 * ref:
+                    errors.append(("reduce", k, it, s, ref))
+                del y, z
+        except Exception as e:                                              # noqa: BLE001
+            errors.append(("exception", k, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
