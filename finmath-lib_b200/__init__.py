@@ -9,9 +9,10 @@ from . import native
 from .sharding import ShardContext, LOCAL, from_environment
 from .stochastic import (RandomVariable, Scalar, RandomVariableFromDoubleArray, RandomVariableCuda, RandomVariableCudaFactory)
 from .montecarlo import (TimeDiscretizationFromArray, BrownianMotionCuda, BrownianMotionView, CorrelatedBrownianMotion, EulerSchemeFromProcessModel, Scheme,
-                         MonteCarloConditionalExpectationRegression)
+                         MonteCarloConditionalExpectationRegression, MonteCarloConditionalExpectationRegressionLocalizedOnDependents,
+                         LinearRegression)
 from .models import (BlackScholesModel, HestonModel, MonteCarloAssetModel, MonteCarloBlackScholesModel,
                      LIBORVolatilityModelFourParameterExponentialForm, LIBORCorrelationModelExponentialDecay,
                      LIBORCovarianceModelFromVolatilityAndCorrelation, LIBORMarketModelFromCovarianceModel,
                      LIBORMonteCarloSimulationFromLIBORModel, factorReduction, HullWhiteModel, ShortRateVolatilityModelAsGiven)
-from .products import EuropeanOption, Caplet, Swaption, BermudanSwaption
+from .products import EuropeanOption, Caplet, Swaption, BermudanSwaption, BermudanOption

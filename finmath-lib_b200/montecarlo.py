@@ -446,8 +446,62 @@ class MonteCarloConditionalExpectationRegression:
             nv.check(nv.load().fmb_regression_predict(K, nv.hptr(hs), nv.dptr(sc), nv.dptr(xs), C.byref(out)))
             n = next(b.dv.n for b in basis if b.dv is not None)
             time = max(b.getFiltrationTime() for b in basis)
-            return RandomVariableCuda(time, None, shard, _dv=nv.DeviceVector(out.value, n), _n=randomVariable.size())
+            n_logical = next(b.nGlobal for b in basis if b.dv is not None)      # the dependents may be deterministic (size 1)
+            return RandomVariableCuda(time, None, shard, _dv=nv.DeviceVector(out.value, n), _n=n_logical)
         ce = basis[0].mult(float(x[0]))
         for i in range(1, K):
             ce = ce.addProduct(basis[i], float(x[i]))
         return ce
+
+
+class MonteCarloConditionalExpectationRegressionLocalizedOnDependents(MonteCarloConditionalExpectationRegression):
+    """J/montecarlo/conditionalexpectation/MonteCarloConditionalExpectationRegressionLocalizedOnDependents.java:85-128: the regression
+    is restricted to the paths where |dependents| < standardDeviations * stddev(dependents) (a 0/1 weight multiplies basis functions
+    and dependents), no caching of XtX.  The moment accumulation is the same fused kernel."""
+
+    def __init__(self, basisFunctionsEstimator, basisFunctionsPredictor=None, standardDeviations=4.0):
+        super().__init__(basisFunctionsEstimator, basisFunctionsPredictor)
+        self.standardDeviations = standardDeviations
+
+    def getLinearRegressionParameters(self, dependents):
+        localizerWeights = dependents.squared().sub(math.pow(dependents.getStandardDeviation() * self.standardDeviations, 2.0)).choose(Scalar(0.0), Scalar(1.0))
+        saved = self.basisFunctionsEstimator
+        try:
+            self.basisFunctionsEstimator = [b.mult(localizerWeights) for b in saved]
+            self._XTX = None
+            return super().getLinearRegressionParameters(dependents.mult(localizerWeights))
+        finally:
+            self.basisFunctionsEstimator = saved
+            self._XTX = None
+
+
+class LinearRegression:
+    """J/montecarlo/conditionalexpectation/LinearRegression.java:30-88 (closed forms for one and two basis functions, least squares else)."""
+
+    def __init__(self, basisFunctions):
+        self.basisFunctions = list(basisFunctions)
+
+    def getRegressionCoefficients(self, value):
+        b = self.basisFunctions
+        if len(b) == 0:
+            return np.array([])
+        if len(b) == 1:
+            return np.array([value.mult(b[0]).getAverage() / b[0].squared().getAverage()])
+        if len(b) == 2:
+            a = b[0].squared().getAverage()
+            bb = b[0].mult(b[1]).average().squared().doubleValue()           # :45 (sic: the squared average)
+            c, d = bb, b[1].squared().getAverage()
+            determinant = a * d - bb * c
+            if determinant != 0:
+                x, y = value.mult(b[0]).getAverage(), value.mult(b[1]).getAverage()
+                return np.array([(d * x - bb * y) / determinant, (a * y - c * x) / determinant])
+        K = len(b)
+        BTB = np.zeros((K, K))
+        for i in range(K):
+            for j in range(i + 1):
+                BTB[i, j] = BTB[j, i] = b[i].mult(b[j]).getAverage()
+        BTX = np.array([b[i].mult(value).getAverage() for i in range(K)])
+        x = np.zeros(K)
+        A, rhs = nv.as_f64(BTB), nv.as_f64(BTX)
+        nv.check(nv.load().fmb_regression_solve_svd(K, nv.dptr(A), nv.dptr(rhs), nv.dptr(x), None))
+        return x

@@ -144,3 +144,58 @@ class BermudanSwaption(AbstractMonteCarloProduct):
         numeraire = model.getNumeraire(float(fixingDate)).invert()
         basisFunctions.append(numeraire)
         return basisFunctions
+
+
+class BermudanOption(AbstractMonteCarloProduct):
+    """Asset Bermudan option, J/montecarlo/assetderivativevaluation/products/BermudanOption.java:150-330, exercise method
+    ESTIMATE_COND_EXPECTATION (lower bound).  Like the reference it pulls the underlying to the host for its basis functions
+    (:298, :314 `new RandomVariableFromDoubleArray(0.0, underlying.getRealizations())`); the CPU-typed basis functions are handed
+    back to the device by type priority, so powers, regression and exercise decisions still run as kernels."""
+
+    ESTIMATE_COND_EXPECTATION, UPPER_BOUND_METHOD = 0, 1
+
+    def __init__(self, exerciseDates, notionals, strikes, exerciseMethod=0, numberOfBasisFunctions=5, intrinsicValueAsBasisFunction=False, useBinning=False):
+        if numberOfBasisFunctions <= 0:
+            raise ValueError("The vaue of numberOfBasisFunctions must be larger or equal 1. %s" % numberOfBasisFunctions)
+        if exerciseMethod != self.ESTIMATE_COND_EXPECTATION:
+            raise NotImplementedError("UPPER_BOUND_METHOD (golden-section search over a martingale) is outside the hot path")
+        self.exerciseDates, self.notionals, self.strikes = list(exerciseDates), list(notionals), list(strikes)
+        self.numberOfBasisFunctions, self.intrinsicValueAsBasisFunction, self.useBinning = numberOfBasisFunctions, intrinsicValueAsBasisFunction, useBinning
+        self.lastValuationExerciseTime = None
+        self.lastRegressions = []
+
+    def getValueRV(self, evaluationTime, model):
+        self.lastRegressions = []
+        value = model.getRandomVariableForConstant(0.0)
+        exerciseTime = model.getRandomVariableForConstant(self.exerciseDates[-1] + 1)
+        for e in range(len(self.exerciseDates) - 1, -1, -1):
+            exerciseDate, notional, strike = float(self.exerciseDates[e]), self.notionals[e], self.strikes[e]
+            underlyingAtExercise = model.getAssetValue(exerciseDate, 0)
+            numeraireAtPayment = model.getNumeraire(exerciseDate)
+            monteCarloWeights = model.getMonteCarloWeights(exerciseDate)
+            valueOfPaymentsIfExercised = underlyingAtExercise.sub(strike).mult(notional).div(numeraireAtPayment).mult(monteCarloWeights)
+            basisUnderlying = underlyingAtExercise.sub(strike).floor(0.0) if self.intrinsicValueAsBasisFunction else underlyingAtExercise
+            basis = self._binning(basisUnderlying) if self.useBinning else self._polynomials(basisUnderlying)
+            estimator = MonteCarloConditionalExpectationRegression(basis)
+            valueIfNotExcercisedEstimated = value.getConditionalExpectation(estimator)
+            self.lastRegressions.append(estimator)
+            exerciseCriteria = valueIfNotExcercisedEstimated.sub(valueOfPaymentsIfExercised)
+            value = exerciseCriteria.choose(value, valueOfPaymentsIfExercised)
+            exerciseTime = exerciseCriteria.choose(exerciseTime, Scalar(exerciseDate))
+        self.lastValuationExerciseTime = exerciseTime
+        return value.mult(model.getNumeraire(float(evaluationTime))).div(model.getMonteCarloWeights(float(evaluationTime)))
+
+    def _polynomials(self, underlying):                       # :292-306
+        u = RandomVariableFromDoubleArray(0.0, underlying.getRealizations())
+        return [u.pow(float(k)) for k in range(self.numberOfBasisFunctions)]
+
+    def _binning(self, underlying):                           # :308-326
+        import numpy as np
+        u = RandomVariableFromDoubleArray(0.0, underlying.getRealizations())
+        values = np.sort(u.getRealizations())
+        n = self.numberOfBasisFunctions
+        out = []
+        for i in range(n):
+            binLeft = float(values[int(float(i) / float(n) * values.size)])
+            out.append(u.sub(binLeft).choose(RandomVariableFromDoubleArray(1.0), RandomVariableFromDoubleArray(0.0)))
+        return out

@@ -280,9 +280,11 @@ class RandomVariableFromDoubleArray(RandomVariable):
         return self._gpu().getAverage(probabilities)
 
     def _gpu(self):
-        if self.realizations is None:
-            return RandomVariableCuda(self.time, self.valueIfNonStochastic)
-        return RandomVariableCuda(self.time, self.realizations)
+        g = self.__dict__.get("_gpu_twin")
+        if g is None:                                       # uploaded once, then reused (the array is immutable by contract)
+            g = RandomVariableCuda(self.time, self.valueIfNonStochastic if self.realizations is None else self.realizations)
+            self.__dict__["_gpu_twin"] = g
+        return g
 
     def __getattr__(self, name):
         # any arithmetic on the CPU type is routed to the GPU type (priority 2 wins; there is no CPU arithmetic here)

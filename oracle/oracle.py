@@ -40,6 +40,7 @@ def lib():
         L.orc_time_lmm_reference_shaped.restype = C.c_double
         L.orc_time_lmm_fused.restype = C.c_double
         L.orc_hull_white_caplet.restype = C.c_double
+        L.orc_bs_bermudan_option.restype = C.c_double
     return _LIB
 
 
@@ -311,3 +312,24 @@ def hull_white_caplet(seed, times, paths, vol_times, vol, mr, curve_times, df_di
                                         C.c_int(scheme), C.c_double(maturity), C.c_double(period_length), C.c_double(strike),
                                         vals.ctypes.data_as(c_dp), num.ctypes.data_as(c_dp), fr.ctypes.data_as(c_dp))
     return price, vals, num, fr
+
+
+def bs_bermudan_option(seed, times, paths, s0, r, sigma, scheme, exercise_dates, notionals, strikes, n_basis=5, intrinsic=False, binning=False):
+    t, tp = _d(times)
+    e, ep = _d(exercise_dates)
+    nt, ntp = _d(notionals)
+    k, kp = _d(strikes)
+    vals, ext, reg = np.empty(paths), np.empty(paths), np.zeros((e.size, n_basis))
+    price = lib().orc_bs_bermudan_option(C.c_int(seed), tp, C.c_int(t.size), C.c_int(paths), C.c_double(s0), C.c_double(r), C.c_double(sigma),
+                                         C.c_int(scheme), ep, ntp, kp, C.c_int(e.size), C.c_int(n_basis), C.c_int(1 if intrinsic else 0),
+                                         C.c_int(1 if binning else 0), vals.ctypes.data_as(c_dp), ext.ctypes.data_as(c_dp), reg.ctypes.data_as(c_dp))
+    return dict(price=price, values=vals, exercise_time=ext, regression=reg)
+
+
+def regression_localized(basis, y, standard_deviations):
+    b, bp = _d(basis)
+    y, yp = _d(y)
+    K = b.shape[0]
+    x, ce = np.empty(K), np.empty(y.size)
+    lib().orc_regression_localized(bp, C.c_int(K), yp, C.c_uint64(y.size), C.c_double(standard_deviations), x.ctypes.data_as(c_dp), ce.ctypes.data_as(c_dp))
+    return x, ce

@@ -278,6 +278,31 @@ double orc_hull_white_caplet(int seed, const double* times, int nTimes, int path
 	return getAverage(values);
 }
 
+// Asset Bermudan option on the Black-Scholes model (BermudanOption.java, ESTIMATE_COND_EXPECTATION); returns the price
+double orc_bs_bermudan_option(int seed, const double* times, int nTimes, int paths, double s0, double r, double sigma, int scheme,
+		const double* exerciseDates, const double* notionals, const double* strikes, int nExercise, int numberOfBasisFunctions,
+		int intrinsicValueAsBasisFunction, int useBinning, double* valuesOut, double* exerciseTimeOut, double* regressionOut) {
+	BrownianMotion bm(tdFrom(times, nTimes), 1, paths, seed, 0);
+	BlackScholesModel m(s0, r, sigma);
+	Process pr(&m, &bm, scheme);
+	BermudanOptionResult res = bermudanOptionValue(m, pr, 0.0, vecOf(exerciseDates, nExercise), vecOf(notionals, nExercise), vecOf(strikes, nExercise),
+		numberOfBasisFunctions, intrinsicValueAsBasisFunction != 0, useBinning != 0);
+	if (valuesOut) store(res.value, valuesOut, paths);
+	if (exerciseTimeOut) store(res.exerciseTime, exerciseTimeOut, paths);
+	if (regressionOut) for (size_t e = 0; e < res.regressionParameters.size(); e++)
+		for (size_t k = 0; k < res.regressionParameters[e].size(); k++) regressionOut[e * numberOfBasisFunctions + k] = res.regressionParameters[e][k];
+	return getAverage(res.value);
+}
+// localized regression: parameters for dependents y on basis b[K][n]
+void orc_regression_localized(const double* basis, int K, const double* y, uint64_t n, double standardDeviations, double* xOut, double* ceOut) {
+	std::vector<P> b;
+	for (int k = 0; k < K; k++) b.push_back(wrap(basis + (size_t)k * n, n));
+	RegressionLocalized reg(b, standardDeviations);
+	P ce = reg.getConditionalExpectationLocalized(wrap(y, n));
+	for (int k = 0; k < K; k++) xOut[k] = reg.lastParameters[k];
+	if (ceOut) store(ce, ceOut, n);
+}
+
 // ---- CPU baselines for bench.py (bounded samples) --------------------------------------------------------
 // (1) reference-shaped: the RV-op path above (one array pass + one allocation per op, single sequential MT stream).
 //     Returns seconds for {Brownian generation + Euler evolution} of `paths` LMM paths.

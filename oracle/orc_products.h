@@ -199,4 +199,71 @@ template <class Model> inline P europeanOptionValue(Model& model, Process& proce
 	return values;
 }
 
+// J/montecarlo/conditionalexpectation/MonteCarloConditionalExpectationRegressionLocalizedOnDependents.java:85-128
+struct RegressionLocalized : Regression {
+	double standardDeviations;
+	RegressionLocalized(const std::vector<P>& b, double sd) : Regression(b), standardDeviations(sd) {}
+	std::vector<double> getLinearRegressionParametersLocalized(P dependents) {
+		P w = choose(sub(squared(dependents), std::pow(getStandardDeviation(dependents) * standardDeviations, 2.0)), scalar(0.0), scalar(1.0));
+		const int K = (int)basis.size();
+		std::vector<P> bl(K);
+		for (int i = 0; i < K; i++) bl[i] = mult(basis[i], w);
+		dependents = mult(dependents, w);
+		std::vector<double> A((size_t)K * K), b(K);
+		for (int i = 0; i < K; i++) for (int j = i; j < K; j++) A[(size_t)i * K + j] = A[(size_t)j * K + i] = getAverage(mult(bl[i], bl[j]));
+		for (int i = 0; i < K; i++) b[i] = getAverage(mult(dependents, bl[i]));
+		lastParameters = solveSymmetricPseudoInverse(A, b, K, &lastCond);
+		return lastParameters;
+	}
+	P getConditionalExpectationLocalized(const P& y) {
+		std::vector<double> x = getLinearRegressionParametersLocalized(y);
+		P ce = mult(basis[0], x[0]);
+		for (size_t i = 1; i < basis.size(); i++) ce = addProduct(ce, basis[i], x[i]);
+		return ce;
+	}
+};
+
+// J/montecarlo/assetderivativevaluation/products/BermudanOption.java:150-330, ExerciseMethod.ESTIMATE_COND_EXPECTATION
+struct BermudanOptionResult { P value, exerciseTime; std::vector<std::vector<double>> regressionParameters; };
+template <class Model> inline BermudanOptionResult bermudanOptionValue(Model& model, Process& process, double evaluationTime,
+		const std::vector<double>& exerciseDates, const std::vector<double>& notionals, const std::vector<double>& strikes,
+		int numberOfBasisFunctions, bool intrinsicValueAsBasisFunction, bool useBinning) {
+	BermudanOptionResult res;
+	P value = scalar(0.0);
+	P exerciseTime = scalar(exerciseDates.back() + 1);
+	P w = process.getMonteCarloWeights();
+	for (int e = (int)exerciseDates.size() - 1; e >= 0; e--) {
+		const double exerciseDate = exerciseDates[e];
+		const int ti = process.getTimeIndex(exerciseDate);
+		if (ti < 0) throw std::runtime_error("The model does not provide an interpolation of simulation time");
+		P underlying = process.getProcessValue(ti, 0);
+		P numeraire = model.getNumeraire(exerciseDate);
+		P valueIfExercised = mult(div(mult(sub(underlying, strikes[e]), notionals[e]), numeraire), w);
+		P bu = intrinsicValueAsBasisFunction ? floor(sub(underlying, strikes[e]), 0.0) : underlying;
+		// new RandomVariableFromDoubleArray(0.0, underlying.getRealizations()) :298, :314
+		std::vector<double> vals(process.getNumberOfPaths());
+		for (size_t i = 0; i < vals.size(); i++) vals[i] = bu->get(i);
+		P u0 = rvvec(0.0, std::vector<double>(vals));
+		std::vector<P> basis;
+		if (!useBinning) {
+			for (int k = 0; k <= numberOfBasisFunctions - 1; k++) basis.push_back(pow(u0, (double)k));
+		} else {
+			std::sort(vals.begin(), vals.end());
+			for (int i = 0; i < numberOfBasisFunctions; i++) {
+				const double binLeft = vals[(size_t)((double)i / (double)numberOfBasisFunctions * vals.size())];
+				basis.push_back(choose(sub(u0, binLeft), rvconst(NEG_INF, 1.0), rvconst(NEG_INF, 0.0)));
+			}
+		}
+		Regression reg(basis);
+		P estimated = reg.getConditionalExpectation(value);
+		res.regressionParameters.push_back(reg.lastParameters);
+		P exerciseCriteria = sub(estimated, valueIfExercised);
+		value = choose(exerciseCriteria, value, valueIfExercised);
+		exerciseTime = choose(exerciseCriteria, exerciseTime, scalar(exerciseDate));
+	}
+	value = div(mult(value, model.getNumeraire(evaluationTime)), w);
+	res.value = value; res.exerciseTime = exerciseTime;
+	return res;
+}
+
 } // namespace orc

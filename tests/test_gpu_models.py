@@ -272,3 +272,43 @@ def test_fast_mode_black_scholes(gpu, orc):
     finally:
         gpu.native.set_fp_mode(0)
     assert rel_err(got, ref_proc[100, 0]) < PATH_TOL and abs(price - ref_price) <= PRICE_TOL * abs(ref_price)
+
+
+# ---- localized regression, LinearRegression, asset BermudanOption ------------------------------------------
+@pytest.mark.parametrize("binning,nbasis", [(False, 5), (True, 20)])
+def test_asset_bermudan_option_matches_oracle(gpu, orc, binning, nbasis):
+    paths = 20_000
+    td = gpu.TimeDiscretizationFromArray(0.0, 20, 0.25)
+    mc = gpu.MonteCarloBlackScholesModel(td, paths, 1.0, 0.05, 0.30)
+    dates, notionals, strikes = [1.0, 2.0, 3.0, 4.0, 5.0], [1.0] * 5, [1.05] * 5
+    product = gpu.BermudanOption(dates, notionals, strikes, numberOfBasisFunctions=nbasis, useBinning=binning)
+    price = product.getValue(mc)
+    r = orc.bs_bermudan_option(3141, td.times, paths, 1.0, 0.05, 0.30, 2, dates, notionals, strikes, n_basis=nbasis, binning=binning)
+    # the monomial basis 1, S, ..., S^4 is ill-conditioned (cond ~ 1e8) and pow() differs by an ulp between libm and the device:
+    # a handful of paths with |continuation - exercise| ~ 1e-9 may flip; each flip moves the average by < 1e-9 / paths
+    ex = product.lastValuationExerciseTime.getRealizations()
+    flips = int(np.sum(ex != r["exercise_time"]))
+    assert flips <= 3, flips
+    assert abs(price - r["price"]) <= (PRICE_TOL if flips == 0 else 1e-8) * abs(r["price"])
+
+
+def test_localized_regression_and_linear_regression(gpu, orc):
+    RV = gpu.RandomVariableCuda
+    rng = np.random.default_rng(11)
+    n = 100_000
+    b1 = rng.standard_normal(n)
+    y = 1.0 + 2.0 * b1 + 0.3 * rng.standard_normal(n)
+    y[:50] += 40.0                                                              # outliers the localization must cut away
+    basis_np = np.stack([np.ones(n), b1])
+    est = gpu.MonteCarloConditionalExpectationRegressionLocalizedOnDependents([RV(0.0, basis_np[0]), RV(0.0, b1)], standardDeviations=3.0)
+    x = est.getLinearRegressionParameters(RV(0.0, y))
+    xr, cer = orc.regression_localized(basis_np, y, 3.0)
+    assert np.max(np.abs(x - xr)) <= 1e-10 * np.max(np.abs(xr))
+    assert rel_err(est.getConditionalExpectation(RV(0.0, y)).getRealizations(), cer) < 1e-10
+    plain = gpu.MonteCarloConditionalExpectationRegression([RV(0.0, basis_np[0]), RV(0.0, b1)]).getLinearRegressionParameters(RV(0.0, y))
+    assert abs(x[0] - 1.0) < abs(plain[0] - 1.0)                                # the outliers bias the plain regression, not the localized one
+    lr = gpu.LinearRegression([RV(0.0, b1)]).getRegressionCoefficients(RV(0.0, y))
+    assert abs(lr[0] - np.mean(y * b1) / np.mean(b1 * b1)) < 1e-12
+    lr3 = gpu.LinearRegression([RV(0.0, np.ones(n)), RV(0.0, b1), RV(0.0, b1 * b1)]).getRegressionCoefficients(RV(0.0, y))
+    X = np.stack([np.ones(n), b1, b1 * b1], axis=1)
+    assert np.allclose(lr3, np.linalg.lstsq(X, y, rcond=None)[0], rtol=1e-9, atol=1e-10)
