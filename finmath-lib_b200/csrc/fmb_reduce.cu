@@ -165,19 +165,6 @@ template <int K> __global__ void __launch_bounds__(RED_THREADS) momentsKernel(Ba
 }
 
 // conditional expectation: b_0*x_0, then + b_i*x_i in order (…Regression.java:103-107); 8 B per stochastic basis read, 8 B written
-template <int K> __global__ void __launch_bounds__(256) predictKernel(BasisArgs b, const double* __restrict__ xIn, double* __restrict__ out, uint64_t n) {
-	double coef[K];
-#pragma unroll
-	for (int k = 0; k < K; k++) coef[k] = xIn[k];
-	const uint64_t stride = (uint64_t)gridDim.x * 256;
-	for (uint64_t i = blockIdx.x * (uint64_t)256 + threadIdx.x; i < n; i += stride) {
-		double ce = (b.ptr[0] ? b.ptr[0][i] : b.scalar[0]) * coef[0];
-#pragma unroll
-		for (int k = 1; k < K; k++) ce = ce + (b.ptr[k] ? b.ptr[k][i] : b.scalar[k]) * coef[k];
-		out[i] = ce;
-	}
-}
-
 struct PredictCoef { double x[8]; };
 template <int K> __global__ void __launch_bounds__(256) predictKernelV(BasisArgs b, PredictCoef c, double* __restrict__ out, uint64_t n) {
 	const uint64_t stride = (uint64_t)gridDim.x * 256;
