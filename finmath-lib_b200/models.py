@@ -227,6 +227,7 @@ class LIBORMarketModelFromCovarianceModel:
         self.liborCap = float(properties.get("liborCap", 1e5))
         self._tables = factorLoadingTable
         self._numeraires, self._numeraireDiscountFactors, self._numerairesProcess = {}, {}, None
+        self._numerairesAdjusted = {}
 
     @classmethod
     def of(cls, liborPeriodDiscretization, analyticModel, forwardRates, discountFactors, randomVariableFactory, covarianceModel, calibrationItems=None,
@@ -350,6 +351,7 @@ class LIBORMarketModelFromCovarianceModel:
         if self._numerairesProcess is None or self._numerairesProcess() is not process:
             self._numeraires.clear()
             self._numeraireDiscountFactors.clear()
+            self._numerairesAdjusted.clear()
             self._numerairesProcess = weakref.ref(process)
 
     def _numeraire_unadjusted_at(self, process, li):                                   # :1017-1074
@@ -397,12 +399,19 @@ class LIBORMarketModelFromCovarianceModel:
             raise NotImplementedError("numeraire for negative times is outside the hot path")
         n = self._numeraire_unadjusted(process, time)
         if self.discountFactors is not None:
+            # The reference re-evaluates the adjustment (three array passes and a getAverage) on every call; the value is a pure function
+            # of (process, time), so the immutable result is kept per time: identical numbers, one reduction (and, sharded, one collective)
+            # per distinct date instead of one per call.
+            cached = self._numerairesAdjusted.get(time)
+            if cached is not None:
+                return cached
             ti = self.tenor.getTimeIndex(time)
             if ti < 0:
                 raise NotImplementedError("numeraire adjustment off the tenor grid is outside the hot path")
             dz = self._defaultable_zero_bond(process, ti)
             nonDefaultableZeroBond = n.invert().mult(self._numeraire_unadjusted(process, 0.0)).getAverage()
             n = n.mult(nonDefaultableZeroBond).div(dz)
+            self._numerairesAdjusted[time] = n
         return n
 
 

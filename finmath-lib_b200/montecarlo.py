@@ -211,6 +211,60 @@ class Scheme:
     EULER, PREDICTOR_CORRECTOR, EULER_FUNCTIONAL, PREDICTOR_CORRECTOR_FUNCTIONAL = range(4)
 
 
+class _LazyRow:
+    __slots__ = ("store", "t")
+
+    def __init__(self, store, t):
+        self.store, self.t = store, t
+
+    def __getitem__(self, c):
+        return self.store.get(self.t, c)
+
+
+class _LazyProcessValues:
+    """discreteProcess[t][c] of a fused simulation: native handles wrapped into RandomVariableCuda objects on first use.
+    A frozen component returns the very object of the earlier time index (aliasing of EulerSchemeFromProcessModel.java:285)."""
+
+    def __init__(self, handles, T, N, P, bm, td, initialValues):
+        self.handles, self.T, self.N, self.P = handles, T, N, P
+        self.factory, self.nPaths, self.td, self.initialValues = bm.randomVariableFactory, bm.getNumberOfPaths(), td, initialValues
+        self.cache = {}
+        self.owned = set()                                   # indices whose handle reference has been handed to a DeviceVector
+
+    def __getitem__(self, t):
+        return _LazyRow(self, t)
+
+    def get(self, t, c):
+        i = t * self.N + c
+        h = int(self.handles[i])
+        if h == 0:
+            key = ("det", c)
+            if key not in self.cache:
+                self.cache[key] = self.factory.createRandomVariable(self.initialValues[c])
+            return self.cache[key]
+        # first time index carrying this handle (later ones are aliases holding an extra native reference)
+        t0 = t
+        while t0 > 0 and int(self.handles[(t0 - 1) * self.N + c]) == h:
+            t0 -= 1
+        i0 = t0 * self.N + c
+        rv = self.cache.get(i0)
+        if rv is None:
+            rv = self.factory.fromDevice(self.td.getTime(t0), nv.DeviceVector(h, self.P), self.nPaths)
+            self.cache[i0] = rv
+            self.owned.add(i0)
+        return rv
+
+    def __del__(self):
+        try:
+            lib = nv.load()
+            for i, h in enumerate(self.handles):
+                h = int(h)
+                if h != 0 and i not in self.owned:
+                    lib.fmb_rv_free(h)                       # one native reference per returned entry (aliases included)
+        except Exception:
+            pass
+
+
 class EulerSchemeFromProcessModel:
     """Euler scheme on the device.
 
@@ -258,7 +312,7 @@ class EulerSchemeFromProcessModel:
             if self._discreteProcess is None:
                 self._precalculate()
         if componentIndex is None:
-            return list(self._discreteProcess[timeIndex])
+            return [self._discreteProcess[timeIndex][c] for c in range(self.getNumberOfComponents())]
         return self._discreteProcess[timeIndex][componentIndex]
 
     def getMonteCarloWeights(self, timeIndex):
@@ -315,23 +369,9 @@ class EulerSchemeFromProcessModel:
                                        nv.dptr(y0), nv.dptr(pl), nv.dptr(fl), nv.dptr(var), first.ctypes.data_as(nv.c_ip), nv.hptr(out)))
         else:
             raise ValueError("unknown fused kernel " + str(k))
-        factory = bm.randomVariableFactory
-        initial = spec["initialValues"]                       # X(0): deterministic host scalars
-        proc = []
-        owned = {}
-        for t in range(T + 1):
-            row = []
-            for c in range(N):
-                h = int(out[t * N + c])
-                if h == 0:
-                    row.append(factory.createRandomVariable(initial[c]))
-                elif t > 0 and h == int(out[(t - 1) * N + c]):
-                    nv.load().fmb_rv_free(h)                  # aliased entry: drop the extra reference, share the object (:285)
-                    row.append(proc[t - 1][c])
-                else:
-                    row.append(factory.fromDevice(td.getTime(t), nv.DeviceVector(h, P), bm.getNumberOfPaths()))
-            proc.append(row)
-        self._discreteProcess = proc
+        # RandomVariable wrappers are created on demand (a simulation has (T+1)*N = 1640 process values for C4, a product touches a
+        # few dozen); handles never wrapped are released when the process is collected.
+        self._discreteProcess = _LazyProcessValues(out, T, N, P, bm, td, spec["initialValues"])
 
     def _precalculate_generic(self):
         model, driver, td = self.model, self.stochasticDriver, self.timeDiscretization
