@@ -181,28 +181,31 @@ template <int FT> struct LmmRec {
 // N-1-i for the terminal measure).  Per rate the operations and their order are exactly those of the scalar recipe; the
 // only cross-rate dependency is the running factor sum S, so the U log / exp / reciprocal chains overlap (ILP U).
 template <int FT, bool LOGN, int MODE, int U, bool CORRECTOR, bool PARTIAL, bool FAST>
-__device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __restrict__ rect, int j0, int jStep, int BD, int F, bool spot, bool functional,
-		bool firstStep, double d, const double* w, double* S, double* Lcol, double* Ybuf, double* Mbuf, uint64_t p, int cnt) {
+__device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __restrict__ rec0, int recStep, int j0, int jStep, int colStep, int F, bool spot,
+		bool functional, bool firstStep, double d, const double* w, double* S, double* L0, double* Y0, double* M0, uint64_t p, int cnt) {
+	// rec0 / L0 / Y0 / M0 point at rate j0 (record, shared-memory state, scratch columns); recStep / colStep move them to the next rate in
+	// processing order (the callers advance them chunk by chunk, so no index multiplications are left in the loop).
 	// PARTIAL: only the first cnt (< U) rates are real; the others recompute rate cnt-1 and are masked out of S and of every store,
 	// so a short remainder costs one chunk latency instead of cnt sequential ones.
 	constexpr int FMAX = FT > 0 ? FT : 16;
 	LmmRec<FT> r[U];
 	double L[U], a[U], mu[U], y[U], Ln[U];
-	int jj[U];
+	int co[U];                                                        // column offset of rate u relative to rate j0
 #pragma unroll
 	for (int u = 0; u < U; u++) {
-		jj[u] = j0 + ((PARTIAL && u >= cnt) ? cnt - 1 : u) * jStep;
-		r[u].load(rect + (size_t)jj[u] * q.recStride, F);
-		L[u] = Lcol[jj[u] * BD];
+		const int uu = (PARTIAL && u >= cnt) ? cnt - 1 : u;
+		co[u] = uu * colStep;
+		r[u].load(rec0 + uu * recStep, F);
+		L[u] = L0[co[u]];
 	}
 	// the logarithms depend on the state only: start them before the drift needs the records
 	if (!CORRECTOR) {
 		if (MODE == 1 || (MODE == 2 && !functional)) {
 #pragma unroll
-			for (int u = 0; u < U; u++) y[u] = Ybuf[(size_t)jj[u] * BD];
+			for (int u = 0; u < U; u++) y[u] = Y0[co[u]];
 		} else if (firstStep) {
 #pragma unroll
-			for (int u = 0; u < U; u++) y[u] = q.ylog0[jj[u]];
+			for (int u = 0; u < U; u++) y[u] = q.ylog0[j0 + ((PARTIAL && u >= cnt) ? cnt - 1 : u) * jStep];
 		} else if (LOGN) {
 			flogN<U>(L, y);
 		} else {
@@ -242,8 +245,8 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 	} else {
 #pragma unroll
 		for (int u = 0; u < U; u++) {
-			y[u] = Ybuf[(size_t)jj[u] * BD];
-			y[u] = mad<FAST>((mu[u] - Mbuf[(size_t)jj[u] * BD]) / 2.0, d, y[u]);
+			y[u] = Y0[co[u]];
+			y[u] = mad<FAST>((mu[u] - M0[co[u]]) / 2.0, d, y[u]);
 		}
 	}
 	if (LOGN) fexpN<U>(y, Ln);
@@ -254,13 +257,13 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 #pragma unroll
 	for (int u = 0; u < U; u++) {
 		if (PARTIAL && u >= cnt) continue;
-		const int j = jj[u];
-		if (q.hasCap) Ln[u] = jminE(Ln[u], q.cap);
+		// Math.min(L, cap): for a positive cap it is (L > cap ? cap : L) bit for bit (NaN stays NaN, no signed-zero case)
+		if (q.hasCap == 2) Ln[u] = (Ln[u] > q.cap) ? q.cap : Ln[u]; else if (q.hasCap) Ln[u] = jminE(Ln[u], q.cap);
 		// carried state of a capped rate at the END of a step: log(cap), what the functional scheme would re-derive from X
 		if (FAST && (MODE != 2 || CORRECTOR) && q.capFix && Ln[u] == q.cap) y[u] = q.logCap;
-		Lcol[j * BD] = Ln[u];
-		if (MODE != 0) Ybuf[(size_t)j * BD] = y[u];
-		if (MODE == 2 && !CORRECTOR) Mbuf[(size_t)j * BD] = mu[u]; else r[u].xrow[p] = Ln[u];
+		L0[co[u]] = Ln[u];
+		if (MODE != 0) Y0[co[u]] = y[u];
+		if (MODE == 2 && !CORRECTOR) M0[co[u]] = mu[u]; else r[u].xrow[p] = Ln[u];
 	}
 }
 
@@ -302,21 +305,24 @@ template <int FT, bool LOGN, int MODE, bool FAST> __global__ void __launch_bound
 			}
 			if (first >= N) continue;
 			const double d = q.dt[t];
-			const double* rect = q.rec + (size_t)t * N * q.recStride;
 			const int live = N - first, jBeg = spot ? first : N - 1, jStep = spot ? 1 : -1;
-			int i = 0;
-			for (; i + U <= live; i += U)
-				lmmChunk<FT, LOGN, MODE, U, false, false, FAST>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p, U);
+			const int recStep = jStep * q.recStride, colStep = jStep * BD;
+			const double* recBeg = q.rec + ((size_t)t * N + jBeg) * q.recStride;
+			const double* rp = recBeg;
+			int co = jBeg * BD, j = jBeg, i = 0;
+			for (; i + U <= live; i += U, rp += U * recStep, co += U * colStep, j += U * jStep)
+				lmmChunk<FT, LOGN, MODE, U, false, false, FAST>(q, rp, recStep, j, jStep, colStep, F, spot, functional, t == 0, d, w, S, Lcol + co, Ybuf + co, Mbuf + co, p, U);
 			if (i < live)
-				lmmChunk<FT, LOGN, MODE, U, false, true, FAST>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p, live - i);
+				lmmChunk<FT, LOGN, MODE, U, false, true, FAST>(q, rp, recStep, j, jStep, colStep, F, spot, functional, t == 0, d, w, S, Lcol + co, Ybuf + co, Mbuf + co, p, live - i);
 			if (MODE == 2) {
 				// corrector: drift re-evaluated on the predicted rates (EulerSchemeFromProcessModel.java:292-314)
 #pragma unroll
 				for (int k = 0; k < FMAX; k++) S[k] = 0.0;
-				for (i = 0; i + U <= live; i += U)
-					lmmChunk<FT, LOGN, MODE, U, true, false, FAST>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p, U);
+				rp = recBeg; co = jBeg * BD; j = jBeg;
+				for (i = 0; i + U <= live; i += U, rp += U * recStep, co += U * colStep, j += U * jStep)
+					lmmChunk<FT, LOGN, MODE, U, true, false, FAST>(q, rp, recStep, j, jStep, colStep, F, spot, functional, t == 0, d, w, S, Lcol + co, Ybuf + co, Mbuf + co, p, U);
 				if (i < live)
-					lmmChunk<FT, LOGN, MODE, U, true, true, FAST>(q, rect, jBeg + i * jStep, jStep, BD, F, spot, functional, t == 0, d, w, S, Lcol, Ybuf, Mbuf, p, live - i);
+					lmmChunk<FT, LOGN, MODE, U, true, true, FAST>(q, rp, recStep, j, jStep, colStep, F, spot, functional, t == 0, d, w, S, Lcol + co, Ybuf + co, Mbuf + co, p, live - i);
 			}
 		}
 	}
@@ -544,7 +550,7 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
 		const bool functionalScheme = (scheme == SCHEME_EULER_FUNCTIONAL || scheme == SCHEME_PC_FUNCTIONAL);
 		int kernelScheme = scheme;
 		if (fast && functionalScheme) kernelScheme = (scheme == SCHEME_EULER_FUNCTIONAL) ? SCHEME_EULER : SCHEME_PC;
-		q.scheme = kernelScheme; q.measure = measure; q.hasCap = std::isinf(libor_cap) ? 0 : 1; q.cap = libor_cap;
+		q.scheme = kernelScheme; q.measure = measure; q.hasCap = std::isinf(libor_cap) ? 0 : (libor_cap > 0.0 ? 2 : 1); q.cap = libor_cap;
 		q.capFix = (fast && functionalScheme && q.hasCap) ? 1 : 0; q.logCap = q.hasCap ? std::log(libor_cap) : 0.0;
 		q.T = T; q.N = N; q.F = F; q.recStride = RS;
 		q.dt = blob.at<double>(oDt); q.firstLive = blob.at<int>(oFirst); q.rec = blob.at<double>(oRec);
