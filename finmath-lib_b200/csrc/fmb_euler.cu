@@ -180,8 +180,8 @@ template <int FT> struct LmmRec {
 // U consecutive live rates of one path at once (i = position in processing order; j = first+i for the spot measure,
 // N-1-i for the terminal measure).  Per rate the operations and their order are exactly those of the scalar recipe; the
 // only cross-rate dependency is the running factor sum S, so the U log / exp / reciprocal chains overlap (ILP U).
-template <int FT, bool LOGN, int MODE, int U, bool CORRECTOR, bool PARTIAL, bool FAST>
-__device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __restrict__ rec0, int recStep, int j0, int jStep, int colStep, int F, bool spot,
+template <int FT, bool LOGN, int MODE, bool SPOT, int U, bool CORRECTOR, bool PARTIAL, bool FAST>
+__device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __restrict__ rec0, int recStep, int j0, int jStep, int colStep, int F,
 		bool functional, bool firstStep, double d, const double* w, double* S, double* L0, double* Y0, double* M0, uint64_t p, int cnt) {
 	// rec0 / L0 / Y0 / M0 point at rate j0 (record, shared-memory state, scratch columns); recStep / colStep move them to the next rate in
 	// processing order (the callers advance them chunk by chunk, so no index multiplications are left in the loop).
@@ -213,22 +213,25 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 			for (int u = 0; u < U; u++) y[u] = L[u];
 		}
 	}
+	{
+		double den[U];
 #pragma unroll
-	for (int u = 0; u < U; u++) {
-		a[u] = 1.0 / ((r[u].ratio < 0.0 ? -L[u] : L[u]) + r[u].invv);      // L * (d / +-d) == +-L exactly: a sign flip, bit-identical
-		if (LOGN) a[u] = a[u] * L[u];
+		for (int u = 0; u < U; u++) den[u] = (SPOT ? L[u] : -L[u]) + r[u].invv;   // L * (d / +-d) == +-L exactly (ratio is +1 under the spot measure, -1 under the terminal measure)
+		frcpN<U>(den, a);                                                                         // == 1.0 / den, bit for bit
+#pragma unroll
+		for (int u = 0; u < U; u++) if (LOGN) a[u] = a[u] * L[u];
 	}
 #pragma unroll
 	for (int u = 0; u < U; u++) {
 		const bool valid = !PARTIAL || u < cnt;
-		if (spot && valid) {
+		if (SPOT && valid) {
 #pragma unroll
 			for (int k = 0; k < FMAX; k++) if (k < F) S[k] = mad<FAST>(a[u], r[u].fl[k], S[k]);
 		}
 		double m = FAST ? S[0] * r[u].fl[0] : S[0] * r[u].fl[0] + 0.0;
 #pragma unroll
 		for (int k = 1; k < FMAX; k++) if (k < F) m = mad<FAST>(S[k], r[u].fl[k], m);
-		if (!spot && valid) {
+		if (!SPOT && valid) {
 #pragma unroll
 			for (int k = 0; k < FMAX; k++) if (k < F) S[k] = mad<FAST>(a[u], r[u].fl[k], S[k]);
 		}
@@ -258,7 +261,8 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 	for (int u = 0; u < U; u++) {
 		if (PARTIAL && u >= cnt) continue;
 		// Math.min(L, cap): for a positive cap it is (L > cap ? cap : L) bit for bit (NaN stays NaN, no signed-zero case)
-		if (q.hasCap == 2) Ln[u] = (Ln[u] > q.cap) ? q.cap : Ln[u]; else if (q.hasCap) Ln[u] = jminE(Ln[u], q.cap);
+		// (q.cap is +infinity when there is no cap: the select keeps L)
+		if (q.hasCap == 1) Ln[u] = jminE(Ln[u], q.cap); else Ln[u] = (Ln[u] > q.cap) ? q.cap : Ln[u];
 		// carried state of a capped rate at the END of a step: log(cap), what the functional scheme would re-derive from X
 		if (FAST && (MODE != 2 || CORRECTOR) && q.capFix && Ln[u] == q.cap) y[u] = q.logCap;
 		L0[co[u]] = Ln[u];
@@ -269,7 +273,7 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 
 // MODE 0: EULER_FUNCTIONAL (state = L in shared memory only).  MODE 1: EULER (Y carried in scratch).
 // MODE 2: PREDICTOR_CORRECTOR[_FUNCTIONAL] (Y and the predictor drift in scratch).
-template <int FT, bool LOGN, int MODE, bool FAST> __global__ void __launch_bounds__(128, FMB_LMM_MINB) eulerLmmKernel(LmmParams q, uint64_t P,
+template <int FT, bool LOGN, int MODE, bool SPOT, bool FAST> __global__ void __launch_bounds__(128, FMB_LMM_MINB) eulerLmmKernel(LmmParams q, uint64_t P,
 		const double* const* __restrict__ dW, double* __restrict__ scratch) {
 	extern __shared__ double Lsh[];                       // [N][blockDim]
 	const int BD = blockDim.x, tid = threadIdx.x;
@@ -277,7 +281,6 @@ template <int FT, bool LOGN, int MODE, bool FAST> __global__ void __launch_bound
 	constexpr int FMAX = FT > 0 ? FT : 16;
 	constexpr int U = FMB_LMM_U;
 	const bool functional = (MODE == 0) || (MODE == 2 && q.scheme == SCHEME_PC_FUNCTIONAL);
-	const bool spot = (q.measure == 0);
 	double* Ybuf = scratch + (size_t)blockIdx.x * 2 * N * BD + tid;      // [N][BD], this thread's column
 	double* Mbuf = Ybuf + (size_t)N * BD;
 	double* Lcol = Lsh + tid;
@@ -305,24 +308,24 @@ template <int FT, bool LOGN, int MODE, bool FAST> __global__ void __launch_bound
 			}
 			if (first >= N) continue;
 			const double d = q.dt[t];
-			const int live = N - first, jBeg = spot ? first : N - 1, jStep = spot ? 1 : -1;
+			const int live = N - first, jBeg = SPOT ? first : N - 1, jStep = SPOT ? 1 : -1;
 			const int recStep = jStep * q.recStride, colStep = jStep * BD;
 			const double* recBeg = q.rec + ((size_t)t * N + jBeg) * q.recStride;
 			const double* rp = recBeg;
 			int co = jBeg * BD, j = jBeg, i = 0;
 			for (; i + U <= live; i += U, rp += U * recStep, co += U * colStep, j += U * jStep)
-				lmmChunk<FT, LOGN, MODE, U, false, false, FAST>(q, rp, recStep, j, jStep, colStep, F, spot, functional, t == 0, d, w, S, Lcol + co, Ybuf + co, Mbuf + co, p, U);
+				lmmChunk<FT, LOGN, MODE, SPOT, U, false, false, FAST>(q, rp, recStep, j, jStep, colStep, F, functional, t == 0, d, w, S, Lcol + co, Ybuf + co, Mbuf + co, p, U);
 			if (i < live)
-				lmmChunk<FT, LOGN, MODE, U, false, true, FAST>(q, rp, recStep, j, jStep, colStep, F, spot, functional, t == 0, d, w, S, Lcol + co, Ybuf + co, Mbuf + co, p, live - i);
+				lmmChunk<FT, LOGN, MODE, SPOT, U, false, true, FAST>(q, rp, recStep, j, jStep, colStep, F, functional, t == 0, d, w, S, Lcol + co, Ybuf + co, Mbuf + co, p, live - i);
 			if (MODE == 2) {
 				// corrector: drift re-evaluated on the predicted rates (EulerSchemeFromProcessModel.java:292-314)
 #pragma unroll
 				for (int k = 0; k < FMAX; k++) S[k] = 0.0;
 				rp = recBeg; co = jBeg * BD; j = jBeg;
 				for (i = 0; i + U <= live; i += U, rp += U * recStep, co += U * colStep, j += U * jStep)
-					lmmChunk<FT, LOGN, MODE, U, true, false, FAST>(q, rp, recStep, j, jStep, colStep, F, spot, functional, t == 0, d, w, S, Lcol + co, Ybuf + co, Mbuf + co, p, U);
+					lmmChunk<FT, LOGN, MODE, SPOT, U, true, false, FAST>(q, rp, recStep, j, jStep, colStep, F, functional, t == 0, d, w, S, Lcol + co, Ybuf + co, Mbuf + co, p, U);
 				if (i < live)
-					lmmChunk<FT, LOGN, MODE, U, true, true, FAST>(q, rp, recStep, j, jStep, colStep, F, spot, functional, t == 0, d, w, S, Lcol + co, Ybuf + co, Mbuf + co, p, live - i);
+					lmmChunk<FT, LOGN, MODE, SPOT, U, true, true, FAST>(q, rp, recStep, j, jStep, colStep, F, functional, t == 0, d, w, S, Lcol + co, Ybuf + co, Mbuf + co, p, live - i);
 			}
 		}
 	}
@@ -550,7 +553,7 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
 		const bool functionalScheme = (scheme == SCHEME_EULER_FUNCTIONAL || scheme == SCHEME_PC_FUNCTIONAL);
 		int kernelScheme = scheme;
 		if (fast && functionalScheme) kernelScheme = (scheme == SCHEME_EULER_FUNCTIONAL) ? SCHEME_EULER : SCHEME_PC;
-		q.scheme = kernelScheme; q.measure = measure; q.hasCap = std::isinf(libor_cap) ? 0 : (libor_cap > 0.0 ? 2 : 1); q.cap = libor_cap;
+		q.scheme = kernelScheme; q.measure = measure; q.hasCap = (std::isinf(libor_cap) && libor_cap > 0) ? 0 : (libor_cap > 0.0 ? 2 : 1); q.cap = libor_cap;
 		q.capFix = (fast && functionalScheme && q.hasCap) ? 1 : 0; q.logCap = q.hasCap ? std::log(libor_cap) : 0.0;
 		q.T = T; q.N = N; q.F = F; q.recStride = RS;
 		q.dt = blob.at<double>(oDt); q.firstLive = blob.at<int>(oFirst); q.rec = blob.at<double>(oRec);
@@ -573,9 +576,11 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
 					cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 					kernel<<<grid, BD, smem, c.stream>>>(q, paths, blob.at<const double*>(oInc), (double*)scratch);
 				};
+#define LMM_SPOT(FTV, LOGNV, MODEV, FASTV) \
+				if (measure == 0) launch(eulerLmmKernel<FTV, LOGNV, MODEV, true, FASTV>); else launch(eulerLmmKernel<FTV, LOGNV, MODEV, false, FASTV>);
 #define LMM_MODE(FTV, LOGNV) \
-				switch (mode) { case 0: launch(eulerLmmKernel<FTV, LOGNV, 0, false>); break; case 1: launch(eulerLmmKernel<FTV, LOGNV, 1, false>); break; default: launch(eulerLmmKernel<FTV, LOGNV, 2, false>); break; }
-#define LMM_FAST(FTV) if (mode == 1) launch(eulerLmmKernel<FTV, true, 1, true>); else launch(eulerLmmKernel<FTV, true, 2, true>);
+				switch (mode) { case 0: LMM_SPOT(FTV, LOGNV, 0, false) break; case 1: LMM_SPOT(FTV, LOGNV, 1, false) break; default: LMM_SPOT(FTV, LOGNV, 2, false) break; }
+#define LMM_FAST(FTV) if (mode == 1) { LMM_SPOT(FTV, true, 1, true) } else { LMM_SPOT(FTV, true, 2, true) }
 #define LMM_LOGN(FTV) if (fast) { LMM_FAST(FTV) } else if (state_space == 1) { LMM_MODE(FTV, true) } else { LMM_MODE(FTV, false) }
 				switch (F) {
 				case 1: LMM_LOGN(1) break;
@@ -585,6 +590,7 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
 				}
 #undef LMM_LOGN
 #undef LMM_FAST
+#undef LMM_SPOT
 #undef LMM_MODE
 				rc = launchCheck("euler_lmm");
 			}
