@@ -181,10 +181,11 @@ template <int FT> struct LmmRec {
 // N-1-i for the terminal measure).  Per rate the operations and their order are exactly those of the scalar recipe; the
 // only cross-rate dependency is the running factor sum S, so the U log / exp / reciprocal chains overlap (ILP U).
 template <int FT, bool LOGN, int MODE, bool SPOT, int U, bool CORRECTOR, bool PARTIAL, bool FAST>
-__device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __restrict__ rec0, int recStep, int j0, int jStep, int colStep, int F,
-		bool functional, bool firstStep, double d, const double* w, double* S, double* L0, double* Y0, double* M0, uint64_t p, int cnt) {
-	// rec0 / L0 / Y0 / M0 point at rate j0 (record, shared-memory state, scratch columns); recStep / colStep move them to the next rate in
-	// processing order (the callers advance them chunk by chunk, so no index multiplications are left in the loop).
+__device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __restrict__ rec0, int recStep, int i0, int jBeg, int colStep, int F,
+		bool functional, bool firstStep, double d, const double* w, double* S, double* L0, double* Y0, size_t mOff, uint64_t p, int cnt) {
+	// rec0 / L0 / Y0 point at the chunk's first rate (record, shared-memory state, scratch column; the predictor drift column is Y0 + mOff);
+	// recStep / colStep move them to the next rate in processing order (the caller advances them chunk by chunk, so no index
+	// multiplications are left in the loop).  i0 = position of the first rate in processing order (j = jBeg +- i).
 	// PARTIAL: only the first cnt (< U) rates are real; the others recompute rate cnt-1 and are masked out of S and of every store,
 	// so a short remainder costs one chunk latency instead of cnt sequential ones.
 	constexpr int FMAX = FT > 0 ? FT : 16;
@@ -198,19 +199,23 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 		r[u].load(rec0 + uu * recStep, F);
 		L[u] = L0[co[u]];
 	}
-	// the logarithms depend on the state only: start them before the drift needs the records
+	// the logarithms depend on the state only: start them before the drift needs the records.  At the first step of a functional scheme the
+	// state is the host's log of X(0); the device logarithm is evaluated anyway and replaced (a branch around it would split the chunk
+	// into basic blocks and keep the log chains from overlapping the reciprocals).
 	if (!CORRECTOR) {
 		if (MODE == 1 || (MODE == 2 && !functional)) {
 #pragma unroll
 			for (int u = 0; u < U; u++) y[u] = Y0[co[u]];
-		} else if (firstStep) {
-#pragma unroll
-			for (int u = 0; u < U; u++) y[u] = q.ylog0[j0 + ((PARTIAL && u >= cnt) ? cnt - 1 : u) * jStep];
-		} else if (LOGN) {
-			flogN<U>(L, y);
 		} else {
+			if (LOGN) flogN<U>(L, y);
+			else {
 #pragma unroll
-			for (int u = 0; u < U; u++) y[u] = L[u];
+				for (int u = 0; u < U; u++) y[u] = L[u];
+			}
+			if (firstStep) {
+#pragma unroll
+				for (int u = 0; u < U; u++) { const int i = i0 + ((PARTIAL && u >= cnt) ? cnt - 1 : u); y[u] = q.ylog0[SPOT ? jBeg + i : jBeg - i]; }
+			}
 		}
 	}
 	{
@@ -249,7 +254,7 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 #pragma unroll
 		for (int u = 0; u < U; u++) {
 			y[u] = Y0[co[u]];
-			y[u] = mad<FAST>((mu[u] - M0[co[u]]) / 2.0, d, y[u]);
+			y[u] = mad<FAST>((mu[u] - Y0[mOff + co[u]]) / 2.0, d, y[u]);
 		}
 	}
 	if (LOGN) fexpN<U>(y, Ln);
@@ -267,7 +272,7 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 		if (FAST && (MODE != 2 || CORRECTOR) && q.capFix && Ln[u] == q.cap) y[u] = q.logCap;
 		L0[co[u]] = Ln[u];
 		if (MODE != 0) Y0[co[u]] = y[u];
-		if (MODE == 2 && !CORRECTOR) M0[co[u]] = mu[u]; else r[u].xrow[p] = Ln[u];
+		if (MODE == 2 && !CORRECTOR) Y0[mOff + co[u]] = mu[u]; else r[u].xrow[p] = Ln[u];
 	}
 }
 
@@ -282,7 +287,7 @@ template <int FT, bool LOGN, int MODE, bool SPOT, bool FAST> __global__ void __l
 	constexpr int U = FMB_LMM_U;
 	const bool functional = (MODE == 0) || (MODE == 2 && q.scheme == SCHEME_PC_FUNCTIONAL);
 	double* Ybuf = scratch + (size_t)blockIdx.x * 2 * N * BD + tid;      // [N][BD], this thread's column
-	double* Mbuf = Ybuf + (size_t)N * BD;
+	const size_t mOff = (size_t)N * BD;                                   // the predictor drift columns follow the Y columns
 	double* Lcol = Lsh + tid;
 
 	const uint64_t tiles = (P + BD - 1) / BD;
@@ -308,24 +313,27 @@ template <int FT, bool LOGN, int MODE, bool SPOT, bool FAST> __global__ void __l
 			}
 			if (first >= N) continue;
 			const double d = q.dt[t];
-			const int live = N - first, jBeg = SPOT ? first : N - 1, jStep = SPOT ? 1 : -1;
-			const int recStep = jStep * q.recStride, colStep = jStep * BD;
-			const double* recBeg = q.rec + ((size_t)t * N + jBeg) * q.recStride;
+			const int live = N - first, jBeg = SPOT ? first : N - 1;
+			const int RS = FT > 0 ? 4 + ((FT + 1) & ~1) : q.recStride;                 // doubles per (t,j) record
+			const int recStep = SPOT ? RS : -RS, colStep = SPOT ? BD : -BD;
+			const double* recBeg = q.rec + ((size_t)t * N + jBeg) * RS;
 			const double* rp = recBeg;
-			int co = jBeg * BD, j = jBeg, i = 0;
-			for (; i + U <= live; i += U, rp += U * recStep, co += U * colStep, j += U * jStep)
-				lmmChunk<FT, LOGN, MODE, SPOT, U, false, false, FAST>(q, rp, recStep, j, jStep, colStep, F, functional, t == 0, d, w, S, Lcol + co, Ybuf + co, Mbuf + co, p, U);
+			double* Lp = Lcol + jBeg * BD;
+			double* Yp = Ybuf + jBeg * BD;
+			int i = 0;
+			for (; i + U <= live; i += U, rp += U * recStep, Lp += U * colStep, Yp += U * colStep)
+				lmmChunk<FT, LOGN, MODE, SPOT, U, false, false, FAST>(q, rp, recStep, i, jBeg, colStep, F, functional, t == 0, d, w, S, Lp, Yp, mOff, p, U);
 			if (i < live)
-				lmmChunk<FT, LOGN, MODE, SPOT, U, false, true, FAST>(q, rp, recStep, j, jStep, colStep, F, functional, t == 0, d, w, S, Lcol + co, Ybuf + co, Mbuf + co, p, live - i);
+				lmmChunk<FT, LOGN, MODE, SPOT, U, false, true, FAST>(q, rp, recStep, i, jBeg, colStep, F, functional, t == 0, d, w, S, Lp, Yp, mOff, p, live - i);
 			if (MODE == 2) {
 				// corrector: drift re-evaluated on the predicted rates (EulerSchemeFromProcessModel.java:292-314)
 #pragma unroll
 				for (int k = 0; k < FMAX; k++) S[k] = 0.0;
-				rp = recBeg; co = jBeg * BD; j = jBeg;
-				for (i = 0; i + U <= live; i += U, rp += U * recStep, co += U * colStep, j += U * jStep)
-					lmmChunk<FT, LOGN, MODE, SPOT, U, true, false, FAST>(q, rp, recStep, j, jStep, colStep, F, functional, t == 0, d, w, S, Lcol + co, Ybuf + co, Mbuf + co, p, U);
+				rp = recBeg; Lp = Lcol + jBeg * BD; Yp = Ybuf + jBeg * BD;
+				for (i = 0; i + U <= live; i += U, rp += U * recStep, Lp += U * colStep, Yp += U * colStep)
+					lmmChunk<FT, LOGN, MODE, SPOT, U, true, false, FAST>(q, rp, recStep, i, jBeg, colStep, F, functional, t == 0, d, w, S, Lp, Yp, mOff, p, U);
 				if (i < live)
-					lmmChunk<FT, LOGN, MODE, SPOT, U, true, true, FAST>(q, rp, recStep, j, jStep, colStep, F, functional, t == 0, d, w, S, Lcol + co, Ybuf + co, Mbuf + co, p, live - i);
+					lmmChunk<FT, LOGN, MODE, SPOT, U, true, true, FAST>(q, rp, recStep, i, jBeg, colStep, F, functional, t == 0, d, w, S, Lp, Yp, mOff, p, live - i);
 			}
 		}
 	}
