@@ -180,9 +180,9 @@ template <int FT> struct LmmRec {
 // U consecutive live rates of one path at once (i = position in processing order; j = first+i for the spot measure,
 // N-1-i for the terminal measure).  Per rate the operations and their order are exactly those of the scalar recipe; the
 // only cross-rate dependency is the running factor sum S, so the U log / exp / reciprocal chains overlap (ILP U).
-template <int FT, bool LOGN, int MODE, bool SPOT, int U, bool CORRECTOR, bool PARTIAL, bool FAST>
+template <int FT, bool LOGN, int MODE, bool SPOT, int U, bool CORRECTOR, bool PARTIAL, bool FAST, bool FIRST>
 __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __restrict__ rec0, int recStep, int i0, int jBeg, int colStep, int F,
-		bool functional, bool firstStep, double d, const double* w, double* S, double* L0, double* Y0, size_t mOff, uint64_t p, int cnt) {
+		bool functional, double d, const double* w, double* S, double* L0, double* Y0, size_t mOff, uint64_t pOff, int cnt) {
 	// rec0 / L0 / Y0 point at the chunk's first rate (record, shared-memory state, scratch column; the predictor drift column is Y0 + mOff);
 	// recStep / colStep move them to the next rate in processing order (the caller advances them chunk by chunk, so no index
 	// multiplications are left in the loop).  i0 = position of the first rate in processing order (j = jBeg +- i).
@@ -212,7 +212,7 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 #pragma unroll
 				for (int u = 0; u < U; u++) y[u] = L[u];
 			}
-			if (firstStep) {
+			if (FIRST) {
 #pragma unroll
 				for (int u = 0; u < U; u++) { const int i = i0 + ((PARTIAL && u >= cnt) ? cnt - 1 : u); y[u] = q.ylog0[SPOT ? jBeg + i : jBeg - i]; }
 			}
@@ -262,17 +262,64 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 #pragma unroll
 		for (int u = 0; u < U; u++) Ln[u] = y[u];
 	}
+	// Math.min(L, cap): unless the cap is a zero or NaN it is (L > cap ? cap : L) bit for bit (NaN stays NaN, no signed-zero case);
+	// q.cap is +infinity when there is no cap, so the select keeps L
+	if (q.hasCap == 1) {
+#pragma unroll
+		for (int u = 0; u < U; u++) Ln[u] = jminE(Ln[u], q.cap);
+	} else {
+#pragma unroll
+		for (int u = 0; u < U; u++) Ln[u] = (Ln[u] > q.cap) ? q.cap : Ln[u];
+	}
 #pragma unroll
 	for (int u = 0; u < U; u++) {
 		if (PARTIAL && u >= cnt) continue;
-		// Math.min(L, cap): for a positive cap it is (L > cap ? cap : L) bit for bit (NaN stays NaN, no signed-zero case)
-		// (q.cap is +infinity when there is no cap: the select keeps L)
-		if (q.hasCap == 1) Ln[u] = jminE(Ln[u], q.cap); else Ln[u] = (Ln[u] > q.cap) ? q.cap : Ln[u];
 		// carried state of a capped rate at the END of a step: log(cap), what the functional scheme would re-derive from X
 		if (FAST && (MODE != 2 || CORRECTOR) && q.capFix && Ln[u] == q.cap) y[u] = q.logCap;
 		L0[co[u]] = Ln[u];
 		if (MODE != 0) Y0[co[u]] = y[u];
-		if (MODE == 2 && !CORRECTOR) Y0[mOff + co[u]] = mu[u]; else r[u].xrow[p] = Ln[u];
+		if (MODE == 2 && !CORRECTOR) Y0[mOff + co[u]] = mu[u];
+		else *reinterpret_cast<double*>(reinterpret_cast<char*>(r[u].xrow) + pOff) = Ln[u];
+	}
+}
+
+// One time step of one path: all live rates in chunks of U, then (predictor-corrector) the corrector pass.
+template <int FT, bool LOGN, int MODE, bool SPOT, bool FAST, bool FIRST>
+__device__ __forceinline__ void lmmTimeStep(const LmmParams& q, int t, int N, int F, int BD, bool functional, const double* const* __restrict__ dW,
+		uint64_t p, uint64_t pOff, double* wNext, double* Lcol, double* Ybuf, size_t mOff) {
+	constexpr int FMAX = FT > 0 ? FT : 16;
+	constexpr int U = FMB_LMM_U;
+	const int first = q.firstLive[t];
+	double w[FMAX], S[FMAX];
+#pragma unroll
+	for (int k = 0; k < FMAX; k++) { w[k] = wNext[k]; S[k] = 0.0; }
+	if (t + 1 < q.T) {
+#pragma unroll
+		for (int k = 0; k < FMAX; k++) if (k < F) wNext[k] = dW[(size_t)(t + 1) * F + k][p];
+	}
+	if (first >= N) return;
+	const double d = q.dt[t];
+	const int live = N - first, jBeg = SPOT ? first : N - 1;
+	const int RS = FT > 0 ? 4 + ((FT + 1) & ~1) : q.recStride;                 // doubles per (t,j) record
+	const int recStep = SPOT ? RS : -RS, colStep = SPOT ? BD : -BD;
+	const double* recBeg = q.rec + ((size_t)t * N + jBeg) * RS;
+	const double* rp = recBeg;
+	double* Lp = Lcol + jBeg * BD;
+	double* Yp = Ybuf + jBeg * BD;
+	int i = 0;
+	for (; i + U <= live; i += U, rp += U * recStep, Lp += U * colStep, Yp += U * colStep)
+		lmmChunk<FT, LOGN, MODE, SPOT, U, false, false, FAST, FIRST>(q, rp, recStep, i, jBeg, colStep, F, functional, d, w, S, Lp, Yp, mOff, pOff, U);
+	if (i < live)
+		lmmChunk<FT, LOGN, MODE, SPOT, U, false, true, FAST, FIRST>(q, rp, recStep, i, jBeg, colStep, F, functional, d, w, S, Lp, Yp, mOff, pOff, live - i);
+	if (MODE == 2) {
+		// corrector: drift re-evaluated on the predicted rates (EulerSchemeFromProcessModel.java:292-314)
+#pragma unroll
+		for (int k = 0; k < FMAX; k++) S[k] = 0.0;
+		rp = recBeg; Lp = Lcol + jBeg * BD; Yp = Ybuf + jBeg * BD;
+		for (i = 0; i + U <= live; i += U, rp += U * recStep, Lp += U * colStep, Yp += U * colStep)
+			lmmChunk<FT, LOGN, MODE, SPOT, U, true, false, FAST, false>(q, rp, recStep, i, jBeg, colStep, F, functional, d, w, S, Lp, Yp, mOff, pOff, U);
+		if (i < live)
+			lmmChunk<FT, LOGN, MODE, SPOT, U, true, true, FAST, false>(q, rp, recStep, i, jBeg, colStep, F, functional, d, w, S, Lp, Yp, mOff, pOff, live - i);
 	}
 }
 
@@ -298,44 +345,16 @@ template <int FT, bool LOGN, int MODE, bool SPOT, bool FAST> __global__ void __l
 			Lcol[j * BD] = q.x0[j];
 			if (MODE != 0) Ybuf[(size_t)j * BD] = q.y0[j];
 		}
+		uint64_t pOff = p * sizeof(double);
+		asm volatile("" : "+l"(pOff));                    // keep the byte offset in registers (otherwise it is re-derived from tile and tid in every chunk)
 		// Brownian increments come from HBM (~1 us away): fetch step t+1 while step t computes
 		double wNext[FMAX];
 #pragma unroll
 		for (int k = 0; k < FMAX; k++) wNext[k] = (k < F) ? dW[k][p] : 0.0;
-		for (int t = 0; t < q.T; t++) {
-			const int first = q.firstLive[t];
-			double w[FMAX], S[FMAX];
-#pragma unroll
-			for (int k = 0; k < FMAX; k++) { w[k] = wNext[k]; S[k] = 0.0; }
-			if (t + 1 < q.T) {
-#pragma unroll
-				for (int k = 0; k < FMAX; k++) if (k < F) wNext[k] = dW[(size_t)(t + 1) * F + k][p];
-			}
-			if (first >= N) continue;
-			const double d = q.dt[t];
-			const int live = N - first, jBeg = SPOT ? first : N - 1;
-			const int RS = FT > 0 ? 4 + ((FT + 1) & ~1) : q.recStride;                 // doubles per (t,j) record
-			const int recStep = SPOT ? RS : -RS, colStep = SPOT ? BD : -BD;
-			const double* recBeg = q.rec + ((size_t)t * N + jBeg) * RS;
-			const double* rp = recBeg;
-			double* Lp = Lcol + jBeg * BD;
-			double* Yp = Ybuf + jBeg * BD;
-			int i = 0;
-			for (; i + U <= live; i += U, rp += U * recStep, Lp += U * colStep, Yp += U * colStep)
-				lmmChunk<FT, LOGN, MODE, SPOT, U, false, false, FAST>(q, rp, recStep, i, jBeg, colStep, F, functional, t == 0, d, w, S, Lp, Yp, mOff, p, U);
-			if (i < live)
-				lmmChunk<FT, LOGN, MODE, SPOT, U, false, true, FAST>(q, rp, recStep, i, jBeg, colStep, F, functional, t == 0, d, w, S, Lp, Yp, mOff, p, live - i);
-			if (MODE == 2) {
-				// corrector: drift re-evaluated on the predicted rates (EulerSchemeFromProcessModel.java:292-314)
-#pragma unroll
-				for (int k = 0; k < FMAX; k++) S[k] = 0.0;
-				rp = recBeg; Lp = Lcol + jBeg * BD; Yp = Ybuf + jBeg * BD;
-				for (i = 0; i + U <= live; i += U, rp += U * recStep, Lp += U * colStep, Yp += U * colStep)
-					lmmChunk<FT, LOGN, MODE, SPOT, U, true, false, FAST>(q, rp, recStep, i, jBeg, colStep, F, functional, t == 0, d, w, S, Lp, Yp, mOff, p, U);
-				if (i < live)
-					lmmChunk<FT, LOGN, MODE, SPOT, U, true, true, FAST>(q, rp, recStep, i, jBeg, colStep, F, functional, t == 0, d, w, S, Lp, Yp, mOff, p, live - i);
-			}
-		}
+		// the first step of a functional scheme starts from the host's log X(0): its own instantiation, no per-chunk test
+		lmmTimeStep<FT, LOGN, MODE, SPOT, FAST, true>(q, 0, N, F, BD, functional, dW, p, pOff, wNext, Lcol, Ybuf, mOff);
+		for (int t = 1; t < q.T; t++)
+			lmmTimeStep<FT, LOGN, MODE, SPOT, FAST, false>(q, t, N, F, BD, functional, dW, p, pOff, wNext, Lcol, Ybuf, mOff);
 	}
 }
 
@@ -561,7 +580,7 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
 		const bool functionalScheme = (scheme == SCHEME_EULER_FUNCTIONAL || scheme == SCHEME_PC_FUNCTIONAL);
 		int kernelScheme = scheme;
 		if (fast && functionalScheme) kernelScheme = (scheme == SCHEME_EULER_FUNCTIONAL) ? SCHEME_EULER : SCHEME_PC;
-		q.scheme = kernelScheme; q.measure = measure; q.hasCap = (std::isinf(libor_cap) && libor_cap > 0) ? 0 : (libor_cap > 0.0 ? 2 : 1); q.cap = libor_cap;
+		q.scheme = kernelScheme; q.measure = measure; q.hasCap = (std::isinf(libor_cap) && libor_cap > 0) ? 0 : ((libor_cap == 0.0 || std::isnan(libor_cap)) ? 1 : 2); q.cap = libor_cap;
 		q.capFix = (fast && functionalScheme && q.hasCap) ? 1 : 0; q.logCap = q.hasCap ? std::log(libor_cap) : 0.0;
 		q.T = T; q.N = N; q.F = F; q.recStride = RS;
 		q.dt = blob.at<double>(oDt); q.firstLive = blob.at<int>(oFirst); q.rec = blob.at<double>(oRec);
