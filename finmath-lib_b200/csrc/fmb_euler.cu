@@ -27,6 +27,9 @@ __device__ __forceinline__ double jmaxE(double a, double b) {
 	return (a >= b) ? a : b;
 }
 
+#ifndef FMB_LMM_PREFETCH
+#define FMB_LMM_PREFETCH 0   // 1: fetch the Brownian increments of step t+1 while step t computes (measured 1 % slower: six more live registers)
+#endif
 #ifndef FMB_LMM_U
 #define FMB_LMM_U 2          // live rates processed together per thread (ILP); 2 measured best on B200 (profiles/r01_notes.md)
 #endif
@@ -148,7 +151,7 @@ struct LmmParams {
 	int T, N, F, recStride;
 	const double* dt;        // [T]
 	const int* firstLive;    // [T]
-	const double* rec;       // [T][N][recStride]: ratio, invv, hv, (bits of) X[t+1][j] row pointer, fl[0..F), pad
+	const double* rec;       // [T][N][recStride]: invv, hv, (bits of) X[t+1][j] row pointer, fl[0..F), pad
 	const double* x0;        // [N]  X_j(0) (host libm)
 	const double* y0;        // [N]  Y_j(0)
 	const double* ylog0;     // [N]  inverse transform of X_j(0) (host libm), used at the first step of functional schemes
@@ -156,23 +159,26 @@ struct LmmParams {
 
 // One (t, j) record is read by every thread of every block in the same order: 16-byte uniform loads, L1-resident.
 template <int FT> struct LmmRec {
-	double ratio, invv, hv;
+	double invv, hv;
 	double* xrow;
 	double fl[FT > 0 ? FT : 16];
+	// layout: invv, hv, row pointer, fl[0..F), padded to an even number of doubles (F = 3: 48 bytes, three 16-byte loads)
 	__device__ __forceinline__ void load(const double* __restrict__ r, int F) {
 		const double2 a = __ldg(reinterpret_cast<const double2*>(r));
-		const double2 b = __ldg(reinterpret_cast<const double2*>(r) + 1);
-		ratio = a.x; invv = a.y; hv = b.x;
-		xrow = reinterpret_cast<double*>(__double_as_longlong(b.y));
+		invv = a.x; hv = a.y;
 		if (FT > 0) {
+			double v[(FT + 2) & ~1];
 #pragma unroll
-			for (int k = 0; k < FT; k += 2) {
-				const double2 c = __ldg(reinterpret_cast<const double2*>(r) + 2 + k / 2);
-				fl[k] = c.x;
-				if (k + 1 < FT) fl[k + 1] = c.y;
+			for (int k = 0; k < ((FT + 2) & ~1); k += 2) {
+				const double2 c = __ldg(reinterpret_cast<const double2*>(r) + 1 + k / 2);
+				v[k] = c.x; v[k + 1] = c.y;
 			}
+			xrow = reinterpret_cast<double*>(__double_as_longlong(v[0]));
+#pragma unroll
+			for (int k = 0; k < FT; k++) fl[k] = v[1 + k];
 		} else {
-			for (int k = 0; k < F; k++) fl[k] = __ldg(r + 4 + k);
+			xrow = reinterpret_cast<double*>(__double_as_longlong(__ldg(r + 2)));
+			for (int k = 0; k < F; k++) fl[k] = __ldg(r + 3 + k);
 		}
 	}
 };
@@ -292,15 +298,21 @@ __device__ __forceinline__ void lmmTimeStep(const LmmParams& q, int t, int N, in
 	const int first = q.firstLive[t];
 	double w[FMAX], S[FMAX];
 #pragma unroll
+#if FMB_LMM_PREFETCH
 	for (int k = 0; k < FMAX; k++) { w[k] = wNext[k]; S[k] = 0.0; }
+#else
+	for (int k = 0; k < FMAX; k++) { w[k] = (k < F) ? dW[(size_t)t * F + k][p] : 0.0; S[k] = 0.0; }
+#endif
+#if FMB_LMM_PREFETCH
 	if (t + 1 < q.T) {
 #pragma unroll
 		for (int k = 0; k < FMAX; k++) if (k < F) wNext[k] = dW[(size_t)(t + 1) * F + k][p];
 	}
+#endif
 	if (first >= N) return;
 	const double d = q.dt[t];
 	const int live = N - first, jBeg = SPOT ? first : N - 1;
-	const int RS = FT > 0 ? 4 + ((FT + 1) & ~1) : q.recStride;                 // doubles per (t,j) record
+	const int RS = FT > 0 ? ((FT + 4) & ~1) : q.recStride;                     // doubles per (t,j) record
 	const int recStep = SPOT ? RS : -RS, colStep = SPOT ? BD : -BD;
 	const double* recBeg = q.rec + ((size_t)t * N + jBeg) * RS;
 	const double* rp = recBeg;
@@ -543,7 +555,7 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
 		for (int t = 0; t < T; t++) for (int j = first_live[t]; j < N; j++) rows[(size_t)(t + 1) * N + j] = (double*)slab->base + (r++) * paths;
 	}
 	std::vector<double> x0(N), ylog0(N);
-	const int FP = (F + 1) & ~1, RS = 4 + FP;
+	const int RS = (F + 4) & ~1;                    // invv, hv, row pointer, F factor loadings, padded to 16 bytes
 	std::vector<double> rec((size_t)T * N * RS, 0.0);
 	for (int j = 0; j < N; j++) {
 		double x = state_space == 1 ? std::exp(initial_state[j]) : initial_state[j];       // applyStateSpaceTransform :1199-1212 (host scalars at t=0)
@@ -554,12 +566,12 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
 	for (int t = 0; t < T; t++) for (int j = 0; j < N; j++) {
 		double* r = &rec[((size_t)t * N + j) * RS];
 		const double value = measure == 0 ? period_length[j] : -period_length[j];          // Scalar.of(+-periodLength).discount(...) :1149,:1167
-		r[0] = period_length[j] / value;
-		r[1] = 1.0 / value;
-		r[2] = variance[(size_t)t * N + j] * -0.5;                                         // :1187 addProduct(variance, -0.5)
+		// (the discount's other factor, periodLength / value = +-1, is the sign applied to L in the kernel)
+		r[0] = 1.0 / value;
+		r[1] = variance[(size_t)t * N + j] * -0.5;                                         // :1187 addProduct(variance, -0.5)
 		double* rowp = rows[(size_t)(t + 1) * N + j];
-		memcpy(&r[3], &rowp, sizeof(double*));
-		for (int k = 0; k < F; k++) r[4 + k] = factor_loading[((size_t)t * N + j) * F + k];
+		memcpy(&r[2], &rowp, sizeof(double*));
+		for (int k = 0; k < F; k++) r[3 + k] = factor_loading[((size_t)t * N + j) * F + k];
 	}
 	DeviceBlob blob;
 	const size_t oDt = blob.add(dt, T * sizeof(double));
