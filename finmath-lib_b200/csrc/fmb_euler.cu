@@ -205,33 +205,35 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 		r[u].load(rec0 + uu * recStep, F);
 		L[u] = L0[co[u]];
 	}
-	// the logarithms depend on the state only: start them before the drift needs the records.  At the first step of a functional scheme the
-	// state is the host's log of X(0); the device logarithm is evaluated anyway and replaced (a branch around it would split the chunk
-	// into basic blocks and keep the log chains from overlapping the reciprocals).
+	// The logarithms depend on the state only: start them before the drift needs the records.  Logarithm and reciprocal run their fast
+	// paths unconditionally and share ONE cold fix-up branch (special arguments), so that all chains of the chunk stay in one basic block.
+	// At the first step of a functional scheme the state is the host's log of X(0) (FIRST: its own instantiation).
+	const bool fromLog = !CORRECTOR && !(MODE == 1 || (MODE == 2 && !functional));
+	bool regular = true;
 	if (!CORRECTOR) {
-		if (MODE == 1 || (MODE == 2 && !functional)) {
+		if (!fromLog) {
 #pragma unroll
 			for (int u = 0; u < U; u++) y[u] = Y0[co[u]];
+		} else if (FIRST) {
+#pragma unroll
+			for (int u = 0; u < U; u++) { const int i = i0 + ((PARTIAL && u >= cnt) ? cnt - 1 : u); y[u] = q.ylog0[SPOT ? jBeg + i : jBeg - i]; }
+		} else if (LOGN) {
+			regular = flogNFast<U>(L, y);
 		} else {
-			if (LOGN) flogN<U>(L, y);
-			else {
 #pragma unroll
-				for (int u = 0; u < U; u++) y[u] = L[u];
-			}
-			if (FIRST) {
-#pragma unroll
-				for (int u = 0; u < U; u++) { const int i = i0 + ((PARTIAL && u >= cnt) ? cnt - 1 : u); y[u] = q.ylog0[SPOT ? jBeg + i : jBeg - i]; }
-			}
+			for (int u = 0; u < U; u++) y[u] = L[u];
 		}
 	}
-	{
-		double den[U];
+	double den[U];
 #pragma unroll
-		for (int u = 0; u < U; u++) den[u] = (SPOT ? L[u] : -L[u]) + r[u].invv;   // L * (d / +-d) == +-L exactly (ratio is +1 under the spot measure, -1 under the terminal measure)
-		frcpN<U>(den, a);                                                                         // == 1.0 / den, bit for bit
-#pragma unroll
-		for (int u = 0; u < U; u++) if (LOGN) a[u] = a[u] * L[u];
+	for (int u = 0; u < U; u++) den[u] = (SPOT ? L[u] : -L[u]) + r[u].invv;   // L * (d / +-d) == +-L exactly (ratio is +1 under the spot measure, -1 under the terminal measure)
+	regular = frcpNFast<U>(den, a) & regular;                                 // == 1.0 / den, bit for bit
+	if (!regular) {
+		if (fromLog && !FIRST && LOGN) flogNSlow<U>(L, y);
+		frcpNSlow<U>(den, a);
 	}
+#pragma unroll
+	for (int u = 0; u < U; u++) if (LOGN) a[u] = a[u] * L[u];
 #pragma unroll
 	for (int u = 0; u < U; u++) {
 		const bool valid = !PARTIAL || u < cnt;
@@ -263,19 +265,21 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 			y[u] = mad<FAST>((mu[u] - Y0[mOff + co[u]]) / 2.0, d, y[u]);
 		}
 	}
-	if (LOGN) fexpN<U>(y, Ln);
-	else {
+	// X = exp(Y) and Math.min(X, cap), with one cold branch for both: unless the cap is a zero or NaN (hasCap == 1), min is
+	// (X > cap ? cap : X) bit for bit (NaN stays NaN, no signed-zero case); q.cap is +infinity when there is no cap
+	double pe[U];
+	int ke[U];
+	bool plain = (q.hasCap != 1);
+	if (LOGN) plain = fexpNParts<U>(y, pe, ke) & plain;
+	if (plain) {
 #pragma unroll
-		for (int u = 0; u < U; u++) Ln[u] = y[u];
-	}
-	// Math.min(L, cap): unless the cap is a zero or NaN it is (L > cap ? cap : L) bit for bit (NaN stays NaN, no signed-zero case);
-	// q.cap is +infinity when there is no cap, so the select keeps L
-	if (q.hasCap == 1) {
-#pragma unroll
-		for (int u = 0; u < U; u++) Ln[u] = jminE(Ln[u], q.cap);
+		for (int u = 0; u < U; u++) { Ln[u] = LOGN ? fexpScaleFast(pe[u], ke[u]) : y[u]; Ln[u] = (Ln[u] > q.cap) ? q.cap : Ln[u]; }
 	} else {
 #pragma unroll
-		for (int u = 0; u < U; u++) Ln[u] = (Ln[u] > q.cap) ? q.cap : Ln[u];
+		for (int u = 0; u < U; u++) {
+			Ln[u] = LOGN ? expFinish(pe[u], ke[u], y[u]) : y[u];
+			Ln[u] = (q.hasCap == 1) ? jminE(Ln[u], q.cap) : ((Ln[u] > q.cap) ? q.cap : Ln[u]);
+		}
 	}
 #pragma unroll
 	for (int u = 0; u < U; u++) {
