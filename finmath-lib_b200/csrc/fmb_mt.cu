@@ -209,6 +209,17 @@ static Poly polyPowX(uint64_t J) {
 	return r;
 }
 
+// ascending exponents of the set coefficients, as 16-bit indices (degree < 19937), padded with JUMP_PAD to a multiple of 8.
+// JUMP_PAD points at a zero word behind the expanded sequence, so padded entries XOR in nothing.
+static const int JUMP_LIST_MAX = 19944;           // 19937 rounded up to a multiple of 8
+static int polyToBitList(const Poly& p, uint16_t* out /* JUMP_LIST_MAX */, uint16_t pad) {
+	int n = 0;
+	for (int i = 0; i < DEG; i++) if ((p[i >> 6] >> (i & 63)) & 1ull) out[n++] = (uint16_t)i;
+	const int padded = (n + 7) & ~7;
+	for (int i = n; i < padded; i++) out[i] = pad;
+	return padded;
+}
+
 static void polyToWords32(const Poly& p, uint32_t* out /* MT_N words */) {
 	for (int i = 0; i < MT_N; i++) {
 		const int w = i >> 1;
@@ -221,37 +232,45 @@ static void polyToWords32(const Poly& p, uint32_t* out /* MT_N words */) {
 // ================================================================================================================
 static const int SEQ_LEN = DEG + MT_N;            // 20561 raw words cover every x[n+i], n < 624, i < 19937
 static const int JUMP_THREADS = 640;
+static const int JUMP_PAD = SEQ_LEN;              // list padding entry: seq[n + JUMP_PAD] is a zero word for every n < 624
+static const int JUMP_SMEM_WORDS = SEQ_LEN + MT_N;
 
-// grid (numOutputs, segments).  Block (o, s): expands source state src[o] to SEQ_LEN raw words in shared memory, then
-// thread n XORs seq[n+i] over the set coefficients i of poly within coefficient words [s*wordsPerSeg, (s+1)*wordsPerSeg).
+// grid (numOutputs, segments).  Block (o, s): expands source state src[o] to the raw words its share of the coefficient list needs
+// (shared memory), then thread n XORs seq[n + i] over the set coefficients i in list[s*perSeg, (s+1)*perSeg).  The list (ascending
+// exponents, one per set coefficient, built once per polynomial on the host) replaces a bit-scan loop: eight independent
+// shared-memory loads per iteration, addresses known up front.
 __global__ void __launch_bounds__(JUMP_THREADS) mtJumpApplyKernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
-		const uint32_t* __restrict__ poly, int wordsPerSeg, int atomicCombine) {
+		const uint16_t* __restrict__ list, int listLen, int perSeg, int atomicCombine) {
 	extern __shared__ uint32_t seq[];
 	const int tid = threadIdx.x;
 	const uint32_t* s = src + (size_t)blockIdx.x * MT_N;
-	for (int i = tid; i < MT_N; i += JUMP_THREADS) seq[i] = s[i];
+	const int kBeg = blockIdx.y * perSeg;
+	const int kEnd = min(listLen, kBeg + perSeg);
+	if (kBeg >= kEnd) return;
+	for (int i = tid; i < MT_N; i += JUMP_THREADS) { seq[i] = s[i]; seq[SEQ_LEN + i] = 0u; }
 	__syncthreads();
-	const int wBeg = blockIdx.y * wordsPerSeg;
-	const int wEnd = min(MT_N, wBeg + wordsPerSeg);
-	const int needEnd = min(SEQ_LEN, wEnd * 32 + MT_N);   // raw words needed by this segment
+	// the list is ascending: the last real entry of the segment bounds the raw words needed
+	int last = kEnd - 1;
+	while (last > kBeg && __ldg(list + last) == JUMP_PAD) last--;
+	const int needEnd = min(SEQ_LEN, (int)__ldg(list + last) + MT_N);
 	for (int j0 = MT_N; j0 < needEnd; j0 += (MT_N - MT_M)) {
 		const int j = j0 + tid;
 		if (tid < (MT_N - MT_M) && j < needEnd) seq[j] = seq[j - (MT_N - MT_M)] ^ mtTwist(seq[j - MT_N], seq[j - MT_N + 1]);
 		__syncthreads();
 	}
 	if (tid < MT_N) {
-		uint32_t acc = 0;
-		for (int w = wBeg; w < wEnd; w++) {
-			uint32_t bits = __ldg(poly + w);
-			const uint32_t* base = seq + tid + 32 * w;
-			while (bits) {
-				const int b = __ffs(bits) - 1;
-				bits &= bits - 1;
-				acc ^= base[b];
-			}
+		uint32_t acc0 = 0, acc1 = 0;
+		const uint32_t* base = seq + tid;
+#pragma unroll 4
+		for (int k = kBeg; k < kEnd; k += 8) {                 // perSeg and listLen are multiples of 8, the list is 16-byte aligned
+			const uint4 q = __ldg(reinterpret_cast<const uint4*>(list + k));
+			acc0 ^= base[q.x & 0xffffu]; acc1 ^= base[q.x >> 16];
+			acc0 ^= base[q.y & 0xffffu]; acc1 ^= base[q.y >> 16];
+			acc0 ^= base[q.z & 0xffffu]; acc1 ^= base[q.z >> 16];
+			acc0 ^= base[q.w & 0xffffu]; acc1 ^= base[q.w >> 16];
 		}
 		uint32_t* d = dst + (size_t)blockIdx.x * MT_N + tid;
-		if (atomicCombine) atomicXor(d, acc); else *d = acc;
+		if (atomicCombine) atomicXor(d, acc0 ^ acc1); else *d = acc0 ^ acc1;
 	}
 }
 
@@ -286,19 +305,24 @@ __global__ void uniformsFromWordsKernel(const uint32_t* __restrict__ w, double* 
 
 // ---------------------------------------------------------------------------------------------------------------
 // Brownian increments.  Block b owns paths [b*ppb, min(P,(b+1)*ppb)) and the MT sub-stream that starts at its first word.
-// Per iteration the block (1) refreshes the raw ring 227 words at a time until 2*BM_THREADS words are available,
-// (2) each thread turns two tempered words into a uniform, applies AS241, scales by sqrt(dt) and drops the value
-// into a shared-memory tile laid out [c = t*F+f][path in tile], (3) full tiles are written to HBM as rows of
-// consecutive paths (coalesced, whole 32-byte sectors).
+// The raw MT19937 words live in a shared-memory ring of four 624-word blocks.  Whenever fewer than 2*need raw words are
+// left, the block generates the next 624 (three barrier-separated steps of 227 + 227 + 170 words, the recurrence's natural
+// parallelism, every index a compile-time offset from the block base).  Then (2) each thread turns two tempered words
+// into a uniform, applies AS241, scales by sqrt(dt) and drops the value into a shared-memory tile laid out
+// [c = t*F+f][path in tile], (3) full tiles are written to HBM as rows of consecutive paths (coalesced, whole 32-byte sectors).
+// Four blocks: at most 1262 raw words are unconsumed when a block is regenerated, so the 624 words being overwritten are never
+// ones a slower warp of the previous batch may still be reading (no barrier between consumption and the next refresh).
 // Algorithmic HBM bytes: 8 per increment (write only).
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef FMB_BM_THREADS
-#define FMB_BM_THREADS 512
+#define FMB_BM_THREADS 320          // 10 warps: 312 uniforms per 624-word block keep 97.5 % of the lanes busy
 #endif
 static const int BM_THREADS = FMB_BM_THREADS;
-static const int BM_CHECK_EVERY = (BM_THREADS >= 512) ? 2 : 4;      // batches between two looks at the tail queue
-static const int RING = 2048;
-static const int TAILQ = 2048;        // deferred tail draws per block (p and tile slot), drained densely
+static const int BM_CHECK_EVERY = 2;             // batches between two looks at the tail queue
+static const int RING = 4 * MT_N;                // raw words (four refresh blocks)
+static const int RING_ALLOC = RING + 2;          // + guard word ring[RING] == ring[0] (the recurrence reads one word past a block)
+static const int TAILQ = 2048;                   // deferred tail draws per block (p and tile slot), drained densely
+static const int BM_HEADER = 16;                 // bytes in front of the ring (tail-queue counter)
 
 // Tail draws (|u - 0.5| > 0.425, 15 % of all) cost ~3x a central draw (log, sqrt, a second rational) and would make
 // almost every warp execute both branches.  They are parked in a shared-memory queue and evaluated by full warps.
@@ -311,28 +335,45 @@ __device__ __forceinline__ void bmDrainTails(const double* __restrict__ qP, cons
 	}
 }
 
-__global__ void __launch_bounds__(BM_THREADS) bmGenerateKernel(const uint32_t* __restrict__ states, double* __restrict__ out,
+// next 624 raw words: block nb from block nb-1 (mod 4).  x[k+624] = x[k+397] ^ twist(x[k], x[k+1]).
+__device__ __forceinline__ void bmRefreshBlock(uint32_t* __restrict__ ring, uint32_t nb, int tid) {
+	uint32_t* nw = ring + nb * MT_N;
+	const uint32_t* od = ring + ((nb + 3) & 3) * MT_N;
+	if (tid < MT_N - MT_M) {
+		const uint32_t v = od[tid + MT_M] ^ mtTwist(od[tid], od[tid + 1]);
+		nw[tid] = v;
+		if (tid == 0 && nb == 0) ring[RING] = v;              // guard: block 3's "word 624"
+	}
+	__syncthreads();
+	if (tid < MT_N - MT_M) nw[tid + (MT_N - MT_M)] = nw[tid] ^ mtTwist(od[tid + (MT_N - MT_M)], od[tid + (MT_N - MT_M) + 1]);
+	__syncthreads();
+	if (tid < MT_N - 2 * (MT_N - MT_M))                       // 170 words; the last one reads od[624] == nw[0] (contiguous, or the guard)
+		nw[tid + 2 * (MT_N - MT_M)] = nw[tid + (MT_N - MT_M)] ^ mtTwist(od[tid + 2 * (MT_N - MT_M)], od[tid + 2 * (MT_N - MT_M) + 1]);
+	__syncthreads();
+}
+
+__global__ void __launch_bounds__(BM_THREADS, 2) bmGenerateKernel(const uint32_t* __restrict__ states, double* __restrict__ out,
 		uint64_t P, uint32_t TF, uint32_t ppb, uint32_t tileN, uint32_t nPad, const double* __restrict__ sqrtDtPerColumn) {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
-	uint32_t* ring = reinterpret_cast<uint32_t*>(smemRaw);
-	double* qP = reinterpret_cast<double*>(smemRaw + RING * sizeof(uint32_t));
+	uint32_t* qCountP = reinterpret_cast<uint32_t*>(smemRaw);
+	uint32_t* ring = reinterpret_cast<uint32_t*>(smemRaw + BM_HEADER);
+	double* qP = reinterpret_cast<double*>(smemRaw + BM_HEADER + RING_ALLOC * sizeof(uint32_t));
 	uint32_t* qSlot = reinterpret_cast<uint32_t*>(qP + TAILQ);
 	double* sq = reinterpret_cast<double*>(qSlot + TAILQ);
 	double* tile = sq + ((TF + 1) & ~1u);
-	__shared__ uint32_t qCount;
 	const int tid = threadIdx.x;
 	const int lane = tid & 31, warp = tid >> 5;
+	static_assert(BM_THREADS >= MT_N - MT_M && 2 * BM_THREADS <= 2 * MT_N, "block size against the refresh width / ring depth");
+	static_assert((BM_HEADER + RING_ALLOC * sizeof(uint32_t)) % 8 == 0, "queue alignment");
 
 	for (int i = tid; i < MT_N; i += BM_THREADS) ring[i] = states[(size_t)blockIdx.x * MT_N + i];
 	for (uint32_t i = tid; i < TF; i += BM_THREADS) sq[i] = sqrtDtPerColumn[i];
-	if (tid == 0) qCount = 0;
+	if (tid == 0) *qCountP = 0;
 	__syncthreads();
 
-	// ring positions (mod RING) of the next raw word to generate and of the next unconsumed word (always even), and their distance.
-	// Each refreshing thread keeps its four ring indices and advances them by 227 per refresh step.
-	uint32_t cpos = MT_N;
+	// ring position of the next unconsumed raw word (always even), number of generated but unconsumed words, next block to generate
+	uint32_t cpos = MT_N, nb = 1;
 	int avail = 0;
-	uint32_t iNew = (MT_N + tid) & (RING - 1), iM = (MT_N + tid - 227) & (RING - 1), i0 = tid & (RING - 1), i1 = (tid + 1) & (RING - 1);
 	const uint64_t pBeg = (uint64_t)blockIdx.x * ppb;
 	const uint64_t pEnd = min(P, pBeg + (uint64_t)ppb);
 	// (path in tile, column) of this thread's draw, advanced by BM_THREADS draws per iteration without divisions
@@ -345,14 +386,13 @@ __global__ void __launch_bounds__(BM_THREADS) bmGenerateKernel(const uint32_t* _
 		for (uint32_t u0 = 0; u0 < U; u0 += BM_THREADS) {
 			const uint32_t need = min((uint32_t)BM_THREADS, U - u0);
 			while (avail < (int)(2 * need)) {
-				if (tid < 227) ring[iNew] = ring[iM] ^ mtTwist(ring[i0], ring[i1]);
-				iNew = (iNew + 227) & (RING - 1); iM = (iM + 227) & (RING - 1);
-				i0 = (i0 + 227) & (RING - 1); i1 = (i1 + 227) & (RING - 1);
-				avail += 227;
-				__syncthreads();
+				bmRefreshBlock(ring, nb, tid);
+				nb = (nb + 1) & 3;
+				avail += MT_N;
 			}
 			if ((uint32_t)tid < need) {
-				const uint32_t j = (cpos + 2 * tid) & (RING - 1);     // even, pair never wraps
+				uint32_t j = cpos + 2 * tid;                           // even, pair never wraps (RING is even)
+				if (j >= RING) j -= RING;
 				const uint2 ww = *reinterpret_cast<const uint2*>(ring + j);
 				const double u = mtUniform(mtTemper(ww.x), mtTemper(ww.y));
 				const double q = u - 0.5;
@@ -360,30 +400,31 @@ __global__ void __launch_bounds__(BM_THREADS) bmGenerateKernel(const uint32_t* _
 				if (fabs(q) <= 0.425) {
 					tile[slot] = as241Central(q) * sq[c];
 				} else {
-					const uint32_t k = atomicAdd(&qCount, 1u);
+					const uint32_t k = atomicAdd(qCountP, 1u);
 					qP[k] = u;
 					qSlot[k] = slot;
 				}
 			}
-			cpos = (cpos + 2 * need) & (RING - 1);
+			cpos += 2 * need;
+			if (cpos >= RING) cpos -= RING;
 			avail -= (int)(2 * need);
 			pl += stepP; c += stepC;
 			if (c >= TF) { c -= TF; pl++; }
 			// every BM_CHECK_EVERY-th batch: make sure the queue keeps room for the next ones (at most BM_THREADS new tails per batch)
 			if ((++it & (BM_CHECK_EVERY - 1)) == 0) {
 				__syncthreads();
-				if (qCount > TAILQ - (BM_CHECK_EVERY + 1) * BM_THREADS) {
-					bmDrainTails(qP, qSlot, qCount, tile, sq, nPad, tid);
+				if (*qCountP > TAILQ - (BM_CHECK_EVERY + 1) * BM_THREADS) {
+					bmDrainTails(qP, qSlot, *qCountP, tile, sq, nPad, tid);
 					__syncthreads();
-					if (tid == 0) qCount = 0;
+					if (tid == 0) *qCountP = 0;
 					__syncthreads();
 				}
 			}
 		}
 		__syncthreads();
-		bmDrainTails(qP, qSlot, qCount, tile, sq, nPad, tid);
+		bmDrainTails(qP, qSlot, *qCountP, tile, sq, nPad, tid);
 		__syncthreads();
-		if (tid == 0) qCount = 0;
+		if (tid == 0) *qCountP = 0;
 		if (n >= 32) {
 			double* dst = out + (size_t)warp * P + p0 + lane;
 			const double* srcRow = tile + warp * nPad + lane;
@@ -406,49 +447,58 @@ __global__ void __launch_bounds__(BM_THREADS) bmGenerateKernel(const uint32_t* _
 // ================================================================================================================
 // Host orchestration
 // ================================================================================================================
-struct DevicePolys {                               // g_{chunk * 2^k}, k = 0..levels-1, MT_N uint32 words each, on the device
-	uint32_t* dev = nullptr;
+struct DevicePolys {                               // g_{chunk * 2^k}, k = 0..levels-1, as coefficient lists (JUMP_LIST_MAX uint16 each) on the device
+	uint16_t* dev = nullptr;
 	int levels = 0;
+	int listLen[24] = {0};                         // padded list length per level
 	Poly last;                                     // host copy of the highest level (to extend by squaring)
 };
 static std::map<uint64_t, DevicePolys> g_polyCache;     // key: chunk (words)
 static std::mutex g_polyMu;
 static const int MAX_LEVELS = 24;
 
-static int getLevelPolys(uint64_t chunk, int levels, const uint32_t** dev) {
+struct LevelLists { const uint16_t* dev; const int* listLen; };
+
+static int getLevelPolys(uint64_t chunk, int levels, LevelLists* out) {
 	FMB_TRY(ensureCharPoly());
 	std::lock_guard<std::mutex> lk(g_polyMu);
 	if (levels > MAX_LEVELS) { setError("too many jump levels"); return FMB_EINVAL; }
 	DevicePolys& dp = g_polyCache[chunk];
 	if (!dp.dev) {
-		FMB_CUDA(cudaMalloc(&dp.dev, (size_t)MAX_LEVELS * MT_N * sizeof(uint32_t)));
+		FMB_CUDA(cudaMalloc(&dp.dev, (size_t)MAX_LEVELS * JUMP_LIST_MAX * sizeof(uint16_t)));
 	}
 	while (dp.levels < levels) {
 		if (dp.levels == 0) dp.last = polyPowX(chunk); else polySquare(dp.last);
-		uint32_t w32[MT_N];
-		polyToWords32(dp.last, w32);
-		FMB_CUDA(cudaMemcpyAsync(dp.dev + (size_t)dp.levels * MT_N, w32, sizeof(w32), cudaMemcpyHostToDevice, ctx().stream));
+		std::vector<uint16_t> list(JUMP_LIST_MAX);
+		dp.listLen[dp.levels] = polyToBitList(dp.last, list.data(), (uint16_t)JUMP_PAD);
+		FMB_CUDA(cudaMemcpyAsync(dp.dev + (size_t)dp.levels * JUMP_LIST_MAX, list.data(), JUMP_LIST_MAX * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx().stream));
 		FMB_CUDA(cudaStreamSynchronize(ctx().stream));
 		dp.levels++;
 	}
-	*dev = dp.dev;
+	out->dev = dp.dev;
+	out->listLen = dp.listLen;
 	return FMB_OK;
 }
 
-static int launchJump(const uint32_t* src, uint32_t* dst, const uint32_t* poly, int count) {
+static int launchJump(const uint32_t* src, uint32_t* dst, const uint16_t* list, int listLen, int count) {
 	static bool attrSet = false;
-	const size_t smem = (size_t)SEQ_LEN * sizeof(uint32_t);
+	const size_t smem = (size_t)JUMP_SMEM_WORDS * sizeof(uint32_t);
 	if (!attrSet) {
 		FMB_CUDA(cudaFuncSetAttribute(mtJumpApplyKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attrSet = true;
 	}
-	// split the coefficient range over several blocks while the level has fewer outputs than the machine has SM slots
+	if (listLen == 0) {                                        // zero polynomial cannot occur (x^J mod phi != 0); keep the output defined
+		FMB_CUDA(cudaMemsetAsync(dst, 0, (size_t)count * MT_N * sizeof(uint32_t), ctx().stream));
+		return FMB_OK;
+	}
+	// split the coefficient list over several blocks while the level has fewer outputs than the machine has SM slots
 	const int slots = 2 * ctx().smCount;
-	int segs = std::max(1, std::min(32, slots / count));
-	int wordsPerSeg = (MT_N + segs - 1) / segs;
-	segs = (MT_N + wordsPerSeg - 1) / wordsPerSeg;
+	// (about two waves of blocks: a level whose output count is not a multiple of the SM count would otherwise wait for a ragged last wave)
+	int segs = std::max(1, std::min(32, (2 * slots + count - 1) / count));
+	int perSeg = (((listLen + segs - 1) / segs) + 7) & ~7;
+	segs = (listLen + perSeg - 1) / perSeg;
 	if (segs > 1) FMB_CUDA(cudaMemsetAsync(dst, 0, (size_t)count * MT_N * sizeof(uint32_t), ctx().stream));
-	mtJumpApplyKernel<<<dim3(count, segs), JUMP_THREADS, smem, ctx().stream>>>(src, dst, poly, wordsPerSeg, segs > 1 ? 1 : 0);
+	mtJumpApplyKernel<<<dim3(count, segs), JUMP_THREADS, smem, ctx().stream>>>(src, dst, list, listLen, perSeg, segs > 1 ? 1 : 0);
 	countLaunch();
 	FMB_CUDA(cudaGetLastError());
 	return FMB_OK;
@@ -463,25 +513,25 @@ static int buildStreamHeads(int64_t seed, uint64_t firstWord, uint64_t chunk, in
 		FMB_CUDA(cudaMemcpyAsync(heads, st, sizeof(st), cudaMemcpyHostToDevice, c.stream));
 		FMB_CUDA(cudaStreamSynchronize(c.stream));
 	} else {
-		const uint32_t* poly;
-		FMB_TRY(getLevelPolys(firstWord, 1, &poly));
+		LevelLists ll;
+		FMB_TRY(getLevelPolys(firstWord, 1, &ll));
 		void* tmp;
 		FMB_TRY(poolAlloc(sizeof(st), &tmp));
 		FMB_CUDA(cudaMemcpyAsync(tmp, st, sizeof(st), cudaMemcpyHostToDevice, c.stream));
 		FMB_CUDA(cudaStreamSynchronize(c.stream));
-		int rc = launchJump((const uint32_t*)tmp, heads, poly, 1);
+		int rc = launchJump((const uint32_t*)tmp, heads, ll.dev, ll.listLen[0], 1);
 		poolFree(tmp, sizeof(st));
 		FMB_TRY(rc);
 	}
 	if (B > 1) {
 		int levels = 0;
 		while ((1 << levels) < B) levels++;
-		const uint32_t* polys;
-		FMB_TRY(getLevelPolys(chunk, levels, &polys));
+		LevelLists ll;
+		FMB_TRY(getLevelPolys(chunk, levels, &ll));
 		for (int k = 0; k < levels; k++) {
 			const int have = 1 << k;
 			const int cnt = std::min(have, B - have);
-			FMB_TRY(launchJump(heads, heads + (size_t)have * MT_N, polys + (size_t)k * MT_N, cnt));
+			FMB_TRY(launchJump(heads, heads + (size_t)have * MT_N, ll.dev + (size_t)k * JUMP_LIST_MAX, ll.listLen[k], cnt));
 		}
 	}
 	return FMB_OK;
@@ -586,8 +636,9 @@ int fmb_bm_generate(int32_t seed, int T, int F, uint64_t paths, uint64_t path_of
 	if (TF > 24000) { setError("bm_generate: T*F = %llu exceeds the shared-memory tile limit (24000)", (unsigned long long)TF); return FMB_EUNSUPPORTED; }
 
 	// shared-memory tile: [TF][nPad] doubles + ring + per-column sqrt(dt)
-	const size_t fixed = RING * sizeof(uint32_t) + TAILQ * (sizeof(double) + sizeof(uint32_t)) + ((TF + 1) & ~1ull) * sizeof(double);
-	// two blocks per SM when a >= 4-path tile fits in half of the 227 KB, else one block with the whole of it
+	const size_t fixed = BM_HEADER + RING_ALLOC * sizeof(uint32_t) + TAILQ * (sizeof(double) + sizeof(uint32_t)) + ((TF + 1) & ~1ull) * sizeof(double);
+	// two blocks per SM when a >= 4-path tile fits in half of the 227 KB, else one block with the whole of it.  (Three blocks per SM with
+	// smaller tiles measured slower: one more level of jump-ahead heads costs more than the extra warps give, profiles/r01_notes.md.)
 	uint32_t tileN = 0;
 	const size_t budgets[2] = { 112 * 1024, 224 * 1024 };
 	for (int attempt = 0; attempt < 2; attempt++) {
