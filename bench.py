@@ -237,18 +237,20 @@ def main():
         if P_local == 4_000_000 and args.scheme == 2:
             for k in json.load(open(os.path.join(ROOT, "profiles", "r01_top_kernels_ncu.json"))):
                 if "eulerLmmKernel" in k["Kernel Name"]:
-                    traffic = (float(k["dram__bytes_read.sum"].split()[0]) + float(k["dram__bytes_write.sum"].split()[0])) * 1e9
+                    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+                    traffic = sum(float(k[m].split()[0]) * scale[k[m].split()[1]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
     except Exception:
         traffic = None
-    # FP64 work of the kernel: 75 FP64 instructions per live rate-step (ncu --page source, profiles/r01_notes.md), DFMA-equivalent flops = 2 each
-    fp64_instr = 75.0 * live * P_local
+    # FP64 work of the kernel: 64 FP64 instructions (DFMA/DADD/DMUL/DSETP) per live rate-step on the kernel's hot path, counted from the
+    # executed-instruction column of the ncu source page (profiles/r01_notes.md, profiles/tools/hot_path.py); DFMA-equivalent flops = 2 each
+    fp64_instr = 64.0 * live * P_local
     fp64_achieved_tflops = 2.0 * fp64_instr / (eu * 1e-3) / 1e12
-    roofline = {"bound": "hbm", "kernel": "eulerLmmKernel<3,1,0>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roofline = {"bound": "hbm", "kernel": "eulerLmmKernel<3,1,0,1,0>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": euler_bytes, "avg_launch_ms": eu,
                 "note": "this kernel is FP64-pipe bound (double log + exp + division per rate-step), not HBM bound: see 'fp64' and DESIGN.md 4.3"}
     fp64 = {"bound": "fp64", "achieved": fp64_achieved_tflops, "peak": tf.value, "unit": "TFLOP/s (DFMA-equivalent)", "frac": fp64_achieved_tflops / tf.value,
             "peak_source": "fmb_bench_dfma_tflops, measured in this run (8 independent DFMA chains per thread)",
-            "fp64_instructions_per_rate_step": 75, "euler_ms": eu, "brownian_ms": float(np.mean(bm_ms)),
+            "fp64_instructions_per_rate_step": 64, "euler_ms": eu, "brownian_ms": float(np.mean(bm_ms)),
             "brownian_achieved_gbs": bm_bytes / (float(np.mean(bm_ms)) * 1e-3) / 1e9}
 
     # ---- optional FAST floating-point mode (not the headline: the headline is STRICT), same step, same sizes ---------------------------

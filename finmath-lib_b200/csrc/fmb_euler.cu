@@ -155,6 +155,7 @@ struct LmmParams {
 	const double* x0;        // [N]  X_j(0) (host libm)
 	const double* y0;        // [N]  Y_j(0)
 	const double* ylog0;     // [N]  inverse transform of X_j(0) (host libm), used at the first step of functional schemes
+	unsigned long long* tileCounter;   // zero at launch: next 32-path tile to hand to a warp
 };
 
 // One (t, j) record is read by every thread of every block in the same order: 16-byte uniform loads, L1-resident.
@@ -353,10 +354,17 @@ template <int FT, bool LOGN, int MODE, bool SPOT, bool FAST> __global__ void __l
 	const size_t mOff = (size_t)N * BD;                                   // the predictor drift columns follow the Y columns
 	double* Lcol = Lsh + tid;
 
-	const uint64_t tiles = (P + BD - 1) / BD;
-	for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-		const uint64_t p = tile * BD + tid;
-		if (p >= P) continue;                             // no block-wide barriers below: every thread only touches its own column
+	// Warps take 32-path tiles from a global counter (no block-wide barriers anywhere: every thread only touches its own column), so the
+	// resident warps stay busy until the paths run out instead of each block owning a fixed share.
+	const uint64_t tiles = (P + 31) / 32;
+	const int lane = tid & 31;
+	for (;;) {
+		unsigned long long tile = 0;
+		if (lane == 0) tile = atomicAdd(q.tileCounter, 1ull);
+		tile = __shfl_sync(0xffffffffu, tile, 0);
+		if (tile >= tiles) break;
+		const uint64_t p = tile * 32 + lane;
+		if (p >= P) continue;                             // the tail lanes of the last tile: the next counter value ends the loop for the whole warp
 		for (int j = 0; j < N; j++) {
 			Lcol[j * BD] = q.x0[j];
 			if (MODE != 0) Ybuf[(size_t)j * BD] = q.y0[j];
@@ -585,6 +593,8 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
 	const size_t oY0 = blob.add(initial_state, N * sizeof(double));
 	const size_t oYl = blob.add(ylog0.data(), N * sizeof(double));
 	const size_t oInc = blob.add(inc.data(), inc.size() * sizeof(double*));
+	const unsigned long long zeroCounter = 0;
+	const size_t oCounter = blob.add(&zeroCounter, sizeof(zeroCounter));
 	int rc = blob.upload();
 	void* scratch = nullptr;
 	size_t scratchBytes = 0;
@@ -601,6 +611,7 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
 		q.T = T; q.N = N; q.F = F; q.recStride = RS;
 		q.dt = blob.at<double>(oDt); q.firstLive = blob.at<int>(oFirst); q.rec = blob.at<double>(oRec);
 		q.x0 = blob.at<double>(oX0); q.y0 = blob.at<double>(oY0); q.ylog0 = blob.at<double>(oYl);
+		q.tileCounter = const_cast<unsigned long long*>(blob.at<unsigned long long>(oCounter));
 		// block size: the shared-memory column store is 8*N bytes per thread
 		int BD = 128;
 		if (const char* e = getenv("FMB_LMM_BD")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 128) BD = v; }   // tuning hook (profiles/r01_notes.md)
