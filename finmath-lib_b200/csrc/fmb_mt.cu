@@ -305,54 +305,61 @@ __global__ void uniformsFromWordsKernel(const uint32_t* __restrict__ w, double* 
 
 // ---------------------------------------------------------------------------------------------------------------
 // Brownian increments.  Block b owns paths [b*ppb, min(P,(b+1)*ppb)) and the MT sub-stream that starts at its first word.
-// The raw MT19937 words live in a shared-memory ring of four 624-word blocks.  Whenever fewer than 2*need raw words are
-// left, the block generates the next 624 (three barrier-separated steps of 227 + 227 + 170 words, the recurrence's natural
-// parallelism, every index a compile-time offset from the block base).  Then (2) each thread turns two tempered words
-// into a uniform, applies AS241, scales by sqrt(dt) and drops the value into a shared-memory tile laid out
-// [c = t*F+f][path in tile], (3) full tiles are written to HBM as rows of consecutive paths (coalesced, whole 32-byte sectors).
-// Four blocks: at most 1262 raw words are unconsumed when a block is regenerated, so the 624 words being overwritten are never
-// ones a slower warp of the previous batch may still be reading (no barrier between consumption and the next refresh).
+// The raw MT19937 words live in a shared-memory ring of five 624-word blocks.  (1) Whenever fewer than 2*need raw words are
+// left, the block generates the next 624 (227 threads, three words each, one barrier; every index a compile-time offset from the
+// block base).  Then (2) each thread turns two tempered words into a uniform, applies AS241, scales by sqrt(dt) and drops the
+// value into a shared-memory tile laid out [c = t*F+f][path in tile], (3) full tiles are written to HBM as rows of consecutive
+// paths (coalesced, whole 32-byte sectors).
+// Ring depth: at most 2*NT - 2 + 624 raw words are unconsumed when a block is regenerated (1262 for 320 threads, 1902 for 640), so
+// with five blocks the 624 words being overwritten are never ones a slower warp of the previous batch may still be reading (no
+// barrier between consumption and the next refresh).
 // Algorithmic HBM bytes: 8 per increment (write only).
 // ---------------------------------------------------------------------------------------------------------------
-#ifndef FMB_BM_THREADS
-#define FMB_BM_THREADS 320          // 10 warps: 312 uniforms per 624-word block keep 97.5 % of the lanes busy
-#endif
-static const int BM_THREADS = FMB_BM_THREADS;
-static const int BM_CHECK_EVERY = 2;             // batches between two looks at the tail queue
-static const int RING = 4 * MT_N;                // raw words (four refresh blocks)
-static const int RING_ALLOC = RING + 2;          // + guard word ring[RING] == ring[0] (the recurrence reads one word past a block)
+static const int BM_THREADS = 320;               // 10 warps: 312 uniforms per 624-word block keep 97.5 % of the lanes busy; two CTAs per SM
+static const int BM_THREADS_WIDE = 640;          // used when the tile is so wide (large T*F) that only one CTA per SM fits
+static const int RING_BLOCKS = 5;                // enough for both block sizes (see above: 2*NT - 2 + 624 unconsumed words at most)
+static const int RING = RING_BLOCKS * MT_N;      // raw words
+static const int RING_ALLOC = RING + 2;          // (+ padding: thread 169 reads one word past the last block before replacing the value)
 static const int TAILQ = 2048;                   // deferred tail draws per block (p and tile slot), drained densely
 static const int BM_HEADER = 16;                 // bytes in front of the ring (tail-queue counter)
 
 // Tail draws (|u - 0.5| > 0.425, 15 % of all) cost ~3x a central draw (log, sqrt, a second rational) and would make
 // almost every warp execute both branches.  They are parked in a shared-memory queue and evaluated by full warps.
-__device__ __forceinline__ void bmDrainTails(const double* __restrict__ qP, const uint32_t* __restrict__ qSlot, uint32_t count,
+template <int NT> __device__ __forceinline__ void bmDrainTails(const double* __restrict__ qP, const uint32_t* __restrict__ qSlot, uint32_t count,
 		double* __restrict__ tile, const double* __restrict__ sq, uint32_t nPad, int tid) {
-	for (uint32_t i = tid; i < count; i += BM_THREADS) {
+	for (uint32_t i = tid; i < count; i += NT) {
 		const double p = qP[i];
 		const uint32_t slot = qSlot[i];
 		tile[slot] = as241Tail(p, p - 0.5) * sq[slot / nPad];
 	}
 }
 
-// next 624 raw words: block nb from block nb-1 (mod 4).  x[k+624] = x[k+397] ^ twist(x[k], x[k+1]).
+// next 624 raw words: block nb from block nb-1 (mod RING_BLOCKS).  x[k+624] = x[k+397] ^ twist(x[k], x[k+1]).
+// Thread i < 227 produces words i, i+227 and i+454 one after the other: word i+227 needs word i and word i+454 needs word i+227
+// (its own results, kept in registers), everything else comes from the previous block - so the whole block needs ONE barrier.
+// The only cross-thread input, x[624] = new word 0 for the very last word, is recomputed by that thread.
 __device__ __forceinline__ void bmRefreshBlock(uint32_t* __restrict__ ring, uint32_t nb, int tid) {
-	uint32_t* nw = ring + nb * MT_N;
-	const uint32_t* od = ring + ((nb + 3) & 3) * MT_N;
-	if (tid < MT_N - MT_M) {
-		const uint32_t v = od[tid + MT_M] ^ mtTwist(od[tid], od[tid + 1]);
-		nw[tid] = v;
-		if (tid == 0 && nb == 0) ring[RING] = v;              // guard: block 3's "word 624"
+	constexpr int W = MT_N - MT_M;                                 // 227
+	if (tid < W) {
+		uint32_t* nw = ring + nb * MT_N + tid;
+		const uint32_t* od = ring + (nb == 0 ? RING_BLOCKS - 1 : nb - 1) * MT_N + tid;
+		const uint32_t v0 = od[MT_M] ^ mtTwist(od[0], od[1]);
+		nw[0] = v0;
+		const uint32_t v1 = v0 ^ mtTwist(od[W], od[W + 1]);
+		nw[W] = v1;
+		if (tid < MT_N - 2 * W) {                                  // 170 words
+			uint32_t next = od[2 * W + 1];
+			if (tid == MT_N - 2 * W - 1) {                             // word 623 reads x[624]: the new word 0
+				const uint32_t* o0 = od - tid;
+				next = o0[MT_M] ^ mtTwist(o0[0], o0[1]);
+			}
+			nw[2 * W] = v1 ^ mtTwist(od[2 * W], next);
+		}
 	}
-	__syncthreads();
-	if (tid < MT_N - MT_M) nw[tid + (MT_N - MT_M)] = nw[tid] ^ mtTwist(od[tid + (MT_N - MT_M)], od[tid + (MT_N - MT_M) + 1]);
-	__syncthreads();
-	if (tid < MT_N - 2 * (MT_N - MT_M))                       // 170 words; the last one reads od[624] == nw[0] (contiguous, or the guard)
-		nw[tid + 2 * (MT_N - MT_M)] = nw[tid + (MT_N - MT_M)] ^ mtTwist(od[tid + 2 * (MT_N - MT_M)], od[tid + 2 * (MT_N - MT_M) + 1]);
 	__syncthreads();
 }
 
-__global__ void __launch_bounds__(BM_THREADS, 2) bmGenerateKernel(const uint32_t* __restrict__ states, double* __restrict__ out,
+template <int NT> __global__ void __launch_bounds__(NT, NT == BM_THREADS ? 2 : 1) bmGenerateKernel(const uint32_t* __restrict__ states, double* __restrict__ out,
 		uint64_t P, uint32_t TF, uint32_t ppb, uint32_t tileN, uint32_t nPad, const double* __restrict__ sqrtDtPerColumn) {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
 	uint32_t* qCountP = reinterpret_cast<uint32_t*>(smemRaw);
@@ -363,11 +370,12 @@ __global__ void __launch_bounds__(BM_THREADS, 2) bmGenerateKernel(const uint32_t
 	double* tile = sq + ((TF + 1) & ~1u);
 	const int tid = threadIdx.x;
 	const int lane = tid & 31, warp = tid >> 5;
-	static_assert(BM_THREADS >= MT_N - MT_M && 2 * BM_THREADS <= 2 * MT_N, "block size against the refresh width / ring depth");
+	static_assert(NT >= MT_N - MT_M && 2 * NT - 2 + 2 * MT_N <= RING, "block size against the refresh width / ring depth");
+	constexpr int BM_CHECK_EVERY = (NT >= 512) ? 1 : 2;              // batches between two looks at the tail queue
 	static_assert((BM_HEADER + RING_ALLOC * sizeof(uint32_t)) % 8 == 0, "queue alignment");
 
-	for (int i = tid; i < MT_N; i += BM_THREADS) ring[i] = states[(size_t)blockIdx.x * MT_N + i];
-	for (uint32_t i = tid; i < TF; i += BM_THREADS) sq[i] = sqrtDtPerColumn[i];
+	for (int i = tid; i < MT_N; i += NT) ring[i] = states[(size_t)blockIdx.x * MT_N + i];
+	for (uint32_t i = tid; i < TF; i += NT) sq[i] = sqrtDtPerColumn[i];
 	if (tid == 0) *qCountP = 0;
 	__syncthreads();
 
@@ -376,18 +384,18 @@ __global__ void __launch_bounds__(BM_THREADS, 2) bmGenerateKernel(const uint32_t
 	int avail = 0;
 	const uint64_t pBeg = (uint64_t)blockIdx.x * ppb;
 	const uint64_t pEnd = min(P, pBeg + (uint64_t)ppb);
-	// (path in tile, column) of this thread's draw, advanced by BM_THREADS draws per iteration without divisions
-	const uint32_t stepP = BM_THREADS / TF, stepC = BM_THREADS % TF;
+	// (path in tile, column) of this thread's draw, advanced by NT draws per iteration without divisions
+	const uint32_t stepP = NT / TF, stepC = NT % TF;
 
 	for (uint64_t p0 = pBeg; p0 < pEnd; p0 += tileN) {
 		const uint32_t n = (uint32_t)min((uint64_t)tileN, pEnd - p0);
 		const uint32_t U = n * TF;
 		uint32_t pl = (uint32_t)tid / TF, c = (uint32_t)tid % TF, it = 0;
-		for (uint32_t u0 = 0; u0 < U; u0 += BM_THREADS) {
-			const uint32_t need = min((uint32_t)BM_THREADS, U - u0);
+		for (uint32_t u0 = 0; u0 < U; u0 += NT) {
+			const uint32_t need = min((uint32_t)NT, U - u0);
 			while (avail < (int)(2 * need)) {
 				bmRefreshBlock(ring, nb, tid);
-				nb = (nb + 1) & 3;
+				nb = (nb == RING_BLOCKS - 1) ? 0 : nb + 1;
 				avail += MT_N;
 			}
 			if ((uint32_t)tid < need) {
@@ -410,11 +418,11 @@ __global__ void __launch_bounds__(BM_THREADS, 2) bmGenerateKernel(const uint32_t
 			avail -= (int)(2 * need);
 			pl += stepP; c += stepC;
 			if (c >= TF) { c -= TF; pl++; }
-			// every BM_CHECK_EVERY-th batch: make sure the queue keeps room for the next ones (at most BM_THREADS new tails per batch)
+			// every BM_CHECK_EVERY-th batch: make sure the queue keeps room for the next ones (at most NT new tails per batch)
 			if ((++it & (BM_CHECK_EVERY - 1)) == 0) {
 				__syncthreads();
-				if (*qCountP > TAILQ - (BM_CHECK_EVERY + 1) * BM_THREADS) {
-					bmDrainTails(qP, qSlot, *qCountP, tile, sq, nPad, tid);
+				if (*qCountP > TAILQ - (BM_CHECK_EVERY + 1) * NT) {
+					bmDrainTails<NT>(qP, qSlot, *qCountP, tile, sq, nPad, tid);
 					__syncthreads();
 					if (tid == 0) *qCountP = 0;
 					__syncthreads();
@@ -422,22 +430,26 @@ __global__ void __launch_bounds__(BM_THREADS, 2) bmGenerateKernel(const uint32_t
 			}
 		}
 		__syncthreads();
-		bmDrainTails(qP, qSlot, *qCountP, tile, sq, nPad, tid);
+		bmDrainTails<NT>(qP, qSlot, *qCountP, tile, sq, nPad, tid);
 		__syncthreads();
 		if (tid == 0) *qCountP = 0;
 		if (n >= 32) {
 			double* dst = out + (size_t)warp * P + p0 + lane;
 			const double* srcRow = tile + warp * nPad + lane;
-			for (uint32_t cc = warp; cc < TF; cc += BM_THREADS / 32) {
+			for (uint32_t cc = warp; cc < TF; cc += NT / 32) {
 #pragma unroll 4
 				for (uint32_t i = 0; i + lane < n; i += 32) dst[i] = srcRow[i];
-				dst += (size_t)(BM_THREADS / 32) * P;
-				srcRow += (BM_THREADS / 32) * nPad;
+				dst += (size_t)(NT / 32) * P;
+				srcRow += (NT / 32) * nPad;
 			}
 		} else {
-			for (uint32_t idx = tid; idx < U; idx += BM_THREADS) {
-				const uint32_t cc = idx / n, i = idx - cc * n;
+			// narrow tile (wide T*F): n consecutive paths per column, (column, path) advanced without a division per element
+			uint32_t cc = (uint32_t)tid / n, i = (uint32_t)tid - cc * n;
+			const uint32_t sC = NT / n, sI = NT - sC * n;
+			for (uint32_t idx = tid; idx < U; idx += NT) {
 				out[(size_t)cc * P + p0 + i] = tile[cc * nPad + i];
+				cc += sC; i += sI;
+				if (i >= n) { i -= n; cc++; }
 			}
 		}
 		__syncthreads();
@@ -681,17 +693,24 @@ int fmb_bm_generate(int32_t seed, int T, int F, uint64_t paths, uint64_t path_of
 		}
 	}
 	if (rc == FMB_OK) rc = newSlab(TF * paths * sizeof(double), &slab);
+	// one CTA per SM only (wide tile): 640 threads, so that the SM still has 20 resident warps
+	const bool wide = blocksPerSm == 1;
 	if (rc == FMB_OK) {
-		static size_t attrSmem = 0;
-		if (smem > attrSmem) {
-			cudaError_t e = cudaFuncSetAttribute(bmGenerateKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		static size_t attrSmem[2] = {0, 0};
+		if (smem > attrSmem[wide ? 1 : 0]) {
+			cudaError_t e = wide ? cudaFuncSetAttribute(bmGenerateKernel<BM_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+			                     : cudaFuncSetAttribute(bmGenerateKernel<BM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if (e != cudaSuccess) { setError("bm_generate: %s", cudaGetErrorString(e)); rc = FMB_ECUDA; }
-			attrSmem = smem;
+			attrSmem[wide ? 1 : 0] = smem;
 		}
 	}
 	if (rc == FMB_OK) {
-		bmGenerateKernel<<<B, BM_THREADS, smem, c.stream>>>((const uint32_t*)heads, (double*)slab->base, paths, (uint32_t)TF, (uint32_t)ppb,
-		                                                    tileN, nPad, (const double*)dsq);
+		if (wide)
+			bmGenerateKernel<BM_THREADS_WIDE><<<B, BM_THREADS_WIDE, smem, c.stream>>>((const uint32_t*)heads, (double*)slab->base, paths, (uint32_t)TF,
+			                                                                      (uint32_t)ppb, tileN, nPad, (const double*)dsq);
+		else
+			bmGenerateKernel<BM_THREADS><<<B, BM_THREADS, smem, c.stream>>>((const uint32_t*)heads, (double*)slab->base, paths, (uint32_t)TF,
+			                                                          (uint32_t)ppb, tileN, nPad, (const double*)dsq);
 		countLaunch();
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess) { setError("bm_generate launch: %s", cudaGetErrorString(e)); rc = FMB_ECUDA; }
