@@ -128,6 +128,34 @@ def test_lmm_ragged_and_capped(gpu, orc):
         assert rel_err(device_process_array(dev, s["T"], s["N"]), ref.process(), scale=0.05) < PATH_TOL
 
 
+@pytest.mark.parametrize("case", ["zero_forward", "huge_vol", "huge_vol_terminal", "cap_zero", "cap_negative"])
+@pytest.mark.parametrize("scheme", [2, 3])
+def test_lmm_special_values_take_the_cold_paths(gpu, orc, case, scheme):
+    """Arguments outside the fast paths of the fused kernel's log / reciprocal / exp / min (zero and subnormal rates, exp underflow, a zero or
+    negative cap with its NaN propagation): the cold fix-up branches must reproduce the reference's special-value semantics
+    (Math.log(0) = -inf, Math.exp(-inf) = 0, Math.min NaN-propagating; LIBORMarketModelFromCovarianceModel.java:1085, :1146-1160)."""
+    big = case.startswith("huge_vol")
+    s = lmm_setup(gpu, n_libors=8, n_factors=2, a=60.0 if big else 0.2, d=60.0 if big else 0.3)
+    if case == "zero_forward":
+        s["L0"][2] = 0.0
+        s["L0"][5] = 0.0
+        for i in range(s["N"]):
+            s["df"][i + 1] = s["df"][i] / (1.0 + s["L0"][i] * s["tenor"].getTimeStep(i))
+    cap = {"cap_zero": 0.0, "cap_negative": -1.0}.get(case, 1e5)
+    measure = "TERMINAL" if case == "huge_vol_terminal" else "SPOT"
+    for paths in (1, 257):
+        dev = lmm_device(gpu, s, paths, scheme=scheme, measure=measure, libor_cap=cap)
+        ref = lmm_oracle(orc, s, paths, scheme=scheme, measure=0 if measure == "SPOT" else 1, libor_cap=cap)
+        got, want = device_process_array(dev, s["T"], s["N"]), ref.process()
+        assert dev.getProcess().usedFusedKernel == "lmm"
+        assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.isinf(got), np.isinf(want))
+        assert rel_err(got, want, scale=0.05) < PATH_TOL
+        if case == "zero_forward":
+            assert np.all(got[1:3, 2] == 0.0)
+        if case == "cap_negative":
+            assert np.isnan(got).any()
+
+
 def test_lmm_numeraire_forward_rate_swaption_caplet(gpu, orc):
     paths = 20_000
     s = lmm_setup(gpu)
