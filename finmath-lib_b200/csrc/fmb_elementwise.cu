@@ -125,6 +125,89 @@ __global__ void __launch_bounds__(256) fillKernel(double* __restrict__ out, doub
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) out[i] = v;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Chains of element-wise operations in ONE pass (fmb_rv_eval_chain).  The host binding defers RandomVariable arithmetic: a result
+// that is only consumed by the next operation never becomes a vector in HBM.  acc = leaf[start][i]; every instruction replaces acc by
+// op(.., acc, ..) with acc at operand position `pos` and the other operands taken from leaf vectors or broadcast scalars.  The
+// operations are the same device functions as the one-op kernels, applied in the same order with the same roundings (no
+// contraction), so a chain is bit-identical to the sequence of single operations.
+// ---------------------------------------------------------------------------------------------------------------
+struct ChainInstr { unsigned char kind, op, pos, refA, refB, refC, pad0, pad1; };    // ref: bit 7 set = scalars[ref & 127], else leaf[ref]
+struct ChainProg {
+	int n, start;
+	ChainInstr code[FMB_CHAIN_MAX_INSTR];
+	const double* leaf[FMB_CHAIN_MAX_LEAVES];
+	double scalar[FMB_CHAIN_MAX_SCALARS];
+};
+
+__device__ __forceinline__ double unaryDyn(int op, double x, double a) {
+	switch (op) {
+	case FMB_U_SQUARED: return unaryOp<FMB_U_SQUARED>(x, a);
+	case FMB_U_SQRT: return unaryOp<FMB_U_SQRT>(x, a);
+	case FMB_U_EXP: return unaryOp<FMB_U_EXP>(x, a);
+	case FMB_U_LOG: return unaryOp<FMB_U_LOG>(x, a);
+	case FMB_U_SIN: return unaryOp<FMB_U_SIN>(x, a);
+	case FMB_U_COS: return unaryOp<FMB_U_COS>(x, a);
+	case FMB_U_INVERT: return unaryOp<FMB_U_INVERT>(x, a);
+	case FMB_U_ABS: return unaryOp<FMB_U_ABS>(x, a);
+	case FMB_U_ISNAN: return unaryOp<FMB_U_ISNAN>(x, a);
+	case FMB_U_EXPM1: return unaryOp<FMB_U_EXPM1>(x, a);
+	case FMB_U_ADD: return unaryOp<FMB_U_ADD>(x, a);
+	case FMB_U_SUB: return unaryOp<FMB_U_SUB>(x, a);
+	case FMB_U_BUS: return unaryOp<FMB_U_BUS>(x, a);
+	case FMB_U_MULT: return unaryOp<FMB_U_MULT>(x, a);
+	case FMB_U_DIV: return unaryOp<FMB_U_DIV>(x, a);
+	case FMB_U_VID: return unaryOp<FMB_U_VID>(x, a);
+	case FMB_U_CAP: return unaryOp<FMB_U_CAP>(x, a);
+	case FMB_U_FLOOR: return unaryOp<FMB_U_FLOOR>(x, a);
+	default: return unaryOp<FMB_U_POW>(x, a);
+	}
+}
+__device__ __forceinline__ double binaryDyn(int op, double x, double y) {
+	switch (op) {
+	case FMB_B_ADD: return binaryOp<FMB_B_ADD>(x, y);
+	case FMB_B_SUB: return binaryOp<FMB_B_SUB>(x, y);
+	case FMB_B_MULT: return binaryOp<FMB_B_MULT>(x, y);
+	case FMB_B_DIV: return binaryOp<FMB_B_DIV>(x, y);
+	case FMB_B_CAP: return binaryOp<FMB_B_CAP>(x, y);
+	default: return binaryOp<FMB_B_FLOOR>(x, y);
+	}
+}
+__device__ __forceinline__ double ternaryDyn(int op, double x, double y, double z, double a) {
+	switch (op) {
+	case FMB_T_ADD_PRODUCT: return ternaryOp<FMB_T_ADD_PRODUCT>(x, y, z, a);
+	case FMB_T_ADD_PRODUCT_D: return ternaryOp<FMB_T_ADD_PRODUCT_D>(x, y, z, a);
+	case FMB_T_ADD_RATIO: return ternaryOp<FMB_T_ADD_RATIO>(x, y, z, a);
+	case FMB_T_SUB_RATIO: return ternaryOp<FMB_T_SUB_RATIO>(x, y, z, a);
+	case FMB_T_ACCRUE: return ternaryOp<FMB_T_ACCRUE>(x, y, z, a);
+	case FMB_T_DISCOUNT: return ternaryOp<FMB_T_DISCOUNT>(x, y, z, a);
+	default: return ternaryOp<FMB_T_CHOOSE>(x, y, z, a);
+	}
+}
+
+__global__ void __launch_bounds__(256) chainKernel(const __grid_constant__ ChainProg p, double* __restrict__ out, uint64_t n) {
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+		double acc = p.leaf[p.start][i];
+		for (int k = 0; k < p.n; k++) {
+			const ChainInstr c = p.code[k];
+			if (c.kind == 0) {
+				acc = unaryDyn(c.op, acc, p.scalar[c.refA & 127]);
+			} else {
+				const double u = (c.refA & 128) ? p.scalar[c.refA & 127] : p.leaf[c.refA][i];
+				if (c.kind == 1) {
+					acc = (c.pos == 0) ? binaryDyn(c.op, acc, u) : binaryDyn(c.op, u, acc);
+				} else {
+					const double v = (c.refB & 128) ? p.scalar[c.refB & 127] : p.leaf[c.refB][i];
+					const double a = p.scalar[c.refC & 127];
+					acc = (c.pos == 0) ? ternaryDyn(c.op, acc, u, v, a) : (c.pos == 1) ? ternaryDyn(c.op, u, acc, v, a) : ternaryDyn(c.op, u, v, acc, a);
+				}
+			}
+		}
+		out[i] = acc;
+	}
+}
+
 static inline int aligned16(const void* p) { return p == nullptr || (((uintptr_t)p) & 15) == 0; }
 
 // grid sized as a multiple of the SM count (8 resident CTAs of 256 threads per SM), capped by the work
@@ -253,6 +336,49 @@ int fmb_rv_ternary(int opcode, fmb_handle x, double sx, fmb_handle y, double sy,
 		LAUNCH_TERNARY(FMB_T_ADD_PRODUCT) LAUNCH_TERNARY(FMB_T_ADD_PRODUCT_D) LAUNCH_TERNARY(FMB_T_ADD_RATIO) LAUNCH_TERNARY(FMB_T_SUB_RATIO)
 		LAUNCH_TERNARY(FMB_T_ACCRUE) LAUNCH_TERNARY(FMB_T_DISCOUNT) LAUNCH_TERNARY(FMB_T_CHOOSE)
 	}
+	return finishLaunch(out);
+}
+
+int fmb_rv_eval_chain(int n_instr, const unsigned char* code, int start_leaf, const fmb_handle* leaves, int n_leaves,
+                      const double* scalars, int n_scalars, fmb_handle* out) {
+	FMB_TRY(requireInit());
+	if (!out || !code || !leaves || n_instr < 1 || n_instr > FMB_CHAIN_MAX_INSTR || n_leaves < 1 || n_leaves > FMB_CHAIN_MAX_LEAVES ||
+	    n_scalars < 0 || n_scalars > FMB_CHAIN_MAX_SCALARS || (n_scalars > 0 && !scalars) || start_leaf < 0 || start_leaf >= n_leaves) {
+		setError("eval_chain: bad argument");
+		return FMB_EINVAL;
+	}
+	ChainProg p;
+	memset(&p, 0, sizeof(p));
+	p.n = n_instr; p.start = start_leaf;
+	uint64_t n;
+	FMB_TRY(commonLength(leaves, n_leaves, &n));
+	for (int i = 0; i < n_leaves; i++) {
+		if (leaves[i] == 0) { setError("eval_chain: leaf %d is not a device vector", i); return FMB_EINVAL; }
+		FMB_TRY(lookupPtr(leaves[i], n, &p.leaf[i]));
+	}
+	for (int i = 0; i < n_scalars; i++) p.scalar[i] = scalars[i];
+	auto refOk = [&](unsigned char r) { return (r & 128) ? (int)(r & 127) < n_scalars : (int)r < n_leaves; };
+	for (int k = 0; k < n_instr; k++) {
+		ChainInstr c;
+		memcpy(&c, code + 8 * k, sizeof(c));
+		bool ok = c.kind <= 2;
+		if (ok && c.kind == 0) {
+			ok = c.op <= FMB_U_POW && (c.refA & 128) && refOk(c.refA);
+			// Math.pow(x, 0.5) / Math.pow(x, 2.0) must equal sqrt / x*x bit-for-bit, as in fmb_rv_unary
+			if (ok && c.op == FMB_U_POW && p.scalar[c.refA & 127] == 0.5) c.op = FMB_U_SQRT;
+			else if (ok && c.op == FMB_U_POW && p.scalar[c.refA & 127] == 2.0) c.op = FMB_U_SQUARED;
+		} else if (ok && c.kind == 1) {
+			ok = c.op <= FMB_B_FLOOR && c.pos <= 1 && refOk(c.refA);
+		} else if (ok) {
+			ok = c.op <= FMB_T_CHOOSE && c.pos <= 2 && refOk(c.refA) && refOk(c.refB) && (c.refC & 128) && refOk(c.refC);
+		}
+		if (!ok) { setError("eval_chain: malformed instruction %d", k); return FMB_EINVAL; }
+		p.code[k] = c;
+	}
+	double* dst;
+	FMB_TRY(newVec(n, out, &dst));
+	if (n == 0) return FMB_OK;
+	chainKernel<<<ewGrid(2 * n), 256, 0, ctx().stream>>>(p, dst, n);
 	return finishLaunch(out);
 }
 

@@ -66,6 +66,7 @@ PROTOTYPES = {
     "fmb_rv_unary": [C.c_int, C.c_uint64, C.c_double, c_hp],
     "fmb_rv_binary": [C.c_int, C.c_uint64, C.c_double, C.c_uint64, C.c_double, c_hp],
     "fmb_rv_ternary": [C.c_int, C.c_uint64, C.c_double, C.c_uint64, C.c_double, C.c_uint64, C.c_double, C.c_double, c_hp],
+    "fmb_rv_eval_chain": [C.c_int, C.c_char_p, C.c_int, c_hp, C.c_int, c_dp, C.c_int, c_hp],
     "fmb_rv_reduce": [C.c_int, C.c_uint64, C.c_uint64, C.c_double, c_dp],
     "fmb_rv_sorted": [C.c_uint64, c_hp],
     "fmb_rv_count_le": [C.c_uint64, c_dp, C.c_int, c_hp],
@@ -173,13 +174,169 @@ class DeviceVector:
         return v.value
 
 
+# ---- deferred element-wise arithmetic --------------------------------------------------------------------------------------
+# unary / binary / ternary return a LazyVector: the operation is recorded, not launched.  When the result is consumed by the next
+# element-wise operation the chain grows; when anything else needs it (a reduction, a kernel argument, a download: every access to
+# `.h`), the whole chain is evaluated in ONE pass by fmb_rv_eval_chain.  Same device functions, order and roundings as the one-op
+# kernels: results are bit-identical to eager evaluation (tests/test_gpu_rv.py compares both modes).  FMB_LAZY=0 or
+# set_lazy(False) switches the deferral off.
+CHAIN_MAX_INSTR, CHAIN_MAX_LEAVES, CHAIN_MAX_SCALARS = 16, 8, 24
+_lazy = os.environ.get("FMB_LAZY", "1") != "0"
+
+
+def set_lazy(on):
+    global _lazy
+    _lazy = bool(on)
+
+
+def lazy_enabled():
+    return _lazy
+
+
+class LazyVector:
+    """Result of element-wise operations that has not been evaluated yet.  Duck-types DeviceVector (h, n, download, get).
+    start: the leaf the accumulator starts from; prog: [(kind, op, pos, others, a)] with others = vectors (DeviceVector) or floats."""
+    __slots__ = ("_h", "n", "start", "prog", "uses", "__weakref__")
+
+    def __init__(self, n, start, prog):
+        self._h = 0
+        self.n = n
+        self.start = start
+        self.prog = prog
+        self.uses = 0
+
+    @property
+    def h(self):
+        if self._h == 0:
+            self._materialize()
+        return self._h
+
+    def pending(self):
+        return self._h == 0
+
+    def __del__(self):
+        h, self._h = self._h, 0
+        if h and _lib is not None:
+            try:
+                _lib.fmb_rv_free(h)
+            except Exception:
+                pass
+
+    def download(self):
+        out = np.empty(self.n, dtype=np.float64)
+        check(load().fmb_rv_download(self.h, dptr(out), self.n))
+        return out
+
+    def get(self, i):
+        v = C.c_double()
+        check(load().fmb_rv_get(self.h, int(i), C.byref(v)))
+        return v.value
+
+    def _materialize(self):
+        out = C.c_uint64()
+        prog, lib = self.prog, load()
+        if len(prog) == 1:                                   # one operation: the specialised kernel
+            kind, op, pos, others, a = prog[0]
+            ops = list(others)
+            ops.insert(pos, self.start)
+            hs = [o.h if not isinstance(o, float) else 0 for o in ops]
+            sc = [o if isinstance(o, float) else 0.0 for o in ops]
+            if kind == 0:
+                check(lib.fmb_rv_unary(op, hs[0], a, C.byref(out)))
+            elif kind == 1:
+                check(lib.fmb_rv_binary(op, hs[0], sc[0], hs[1], sc[1], C.byref(out)))
+            else:
+                check(lib.fmb_rv_ternary(op, hs[0], sc[0], hs[1], sc[1], hs[2], sc[2], a, C.byref(out)))
+        else:
+            leaves, leaf_index, scalars, scalar_index = [], {}, [], {}
+
+            def ref(o):
+                if isinstance(o, float):
+                    key = o.hex() if o == o else "nan"
+                    i = scalar_index.get(key)
+                    if i is None:
+                        i = scalar_index[key] = len(scalars)
+                        scalars.append(o)
+                    return 128 | i
+                i = leaf_index.get(id(o))
+                if i is None:
+                    i = leaf_index[id(o)] = len(leaves)
+                    leaves.append(o)
+                return i
+
+            start = ref(self.start)
+            code = bytearray()
+            for kind, op, pos, others, a in prog:
+                if kind == 0:
+                    code += bytes((0, op, 0, ref(float(a)), 0, 0, 0, 0))
+                elif kind == 1:
+                    code += bytes((1, op, pos, ref(others[0]), 0, 0, 0, 0))
+                else:
+                    code += bytes((2, op, pos, ref(others[0]), ref(others[1]), ref(float(a)), 0, 0))
+            hs = np.array([o.h for o in leaves], dtype=np.uint64)
+            sc = np.array(scalars if scalars else [0.0], dtype=np.float64)
+            check(lib.fmb_rv_eval_chain(len(prog), bytes(code), start, hptr(hs), len(leaves), dptr(sc), len(scalars), C.byref(out)))
+        self._h = out.value
+        self.start = None
+        self.prog = None
+
+
+def _chain_cost(prog, extra_vectors, extra_scalars):
+    """(instructions, distinct leaf vectors, scalars) upper bounds of a chain after one more instruction."""
+    vec, sca = {0}, 0                                        # 0 stands for the start leaf
+    for kind, op, pos, others, a in prog:
+        for o in others:
+            if isinstance(o, float):
+                sca += 1
+            else:
+                vec.add(id(o))
+        sca += 1 if kind != 1 else 0
+    for o in extra_vectors:
+        vec.add(id(o))
+    return len(prog) + 1, len(vec), sca + extra_scalars
+
+
+def _lazy_op(kind, op, operands, a):
+    """operands: positional list of DeviceVector / LazyVector / float (scalar broadcast).  Returns a LazyVector."""
+    n = next(o.n for o in operands if not isinstance(o, float))
+    for o in operands:
+        if not isinstance(o, float) and o.n != n:
+            raise ValueError("finmath_b200: operand sizes differ (%d vs %d)" % (o.n, n))      # IllegalArgumentException, as the eager call
+    # the operand whose pending chain this operation extends: the first unevaluated, not yet consumed LazyVector
+    host = -1
+    for i, o in enumerate(operands):
+        if isinstance(o, LazyVector) and o._h == 0:
+            if host < 0 and o.uses == 0:
+                others = [x for j, x in enumerate(operands) if j != i]
+                instr, vec, sca = _chain_cost(o.prog, [x for x in others if not isinstance(x, float)],
+                                              sum(1 for x in others if isinstance(x, float)) + (1 if kind != 1 else 0))
+                if instr <= CHAIN_MAX_INSTR and vec <= CHAIN_MAX_LEAVES and sca <= CHAIN_MAX_SCALARS:
+                    host = i
+                    continue
+            o.h                                              # second consumer, or the chain is full: evaluate it, use it as a leaf
+    if host >= 0 and operands[host]._h != 0:                 # the same object in two operand positions: it has just been evaluated
+        host = -1
+    if host >= 0:
+        base = operands[host]
+        base.uses += 1
+        others = tuple(x for j, x in enumerate(operands) if j != host)
+        return LazyVector(n, base.start, base.prog + [(kind, op, host, others, float(a))])
+    start = next(i for i, o in enumerate(operands) if not isinstance(o, float))
+    others = tuple(x for j, x in enumerate(operands) if j != start)
+    return LazyVector(n, operands[start], [(kind, op, start, others, float(a))])
+
+
 def unary(op, x, a=0.0):
+    if _lazy:
+        return _lazy_op(0, op, [x], a)
     out = C.c_uint64()
     check(load().fmb_rv_unary(op, x.h, float(a), C.byref(out)))
     return DeviceVector(out.value, x.n)
 
 
 def binary(op, x, sx, y, sy):
+    if _lazy:
+        return _lazy_op(1, op, [x if x is not None else float(sx), y if y is not None else float(sy)], 0.0)
     out = C.c_uint64()
     check(load().fmb_rv_binary(op, x.h if x is not None else 0, float(sx), y.h if y is not None else 0, float(sy), C.byref(out)))
     n = x.n if x is not None else y.n
@@ -187,6 +344,8 @@ def binary(op, x, sx, y, sy):
 
 
 def ternary(op, x, sx, y, sy, z, sz, a=0.0):
+    if _lazy:
+        return _lazy_op(2, op, [x if x is not None else float(sx), y if y is not None else float(sy), z if z is not None else float(sz)], a)
     out = C.c_uint64()
     check(load().fmb_rv_ternary(op, x.h if x is not None else 0, float(sx), y.h if y is not None else 0, float(sy),
                                 z.h if z is not None else 0, float(sz), float(a), C.byref(out)))

@@ -99,6 +99,20 @@ int fmb_rv_unary(int op, fmb_handle x, double a, fmb_handle* out);
 int fmb_rv_binary(int op, fmb_handle x, double sx, fmb_handle y, double sy, fmb_handle* out);
 int fmb_rv_ternary(int op, fmb_handle x, double sx, fmb_handle y, double sy, fmb_handle z, double sz, double a, fmb_handle* out);
 
+/* A chain of element-wise operations evaluated in ONE pass over the vectors (deferred evaluation in the host binding: a result that
+ * is only consumed by the next operation never becomes a vector in HBM).  acc = leaves[start_leaf][i]; instruction k replaces acc by
+ * its operation with acc at operand position `pos`; the other operands are leaf vectors or broadcast scalars.  Same device functions,
+ * order and roundings as fmb_rv_unary/binary/ternary, so the result is bit-identical to issuing the operations one by one
+ * (RandomVariableFromDoubleArray.java:742-1504 applied repeatedly).
+ * code: 8 bytes per instruction {kind (0 unary, 1 binary, 2 ternary), opcode, pos, refA, refB, refC, 0, 0}; a ref with bit 7 set is
+ * scalars[ref & 127], otherwise leaves[ref].  unary: refA = the op's double argument (scalar).  binary: refA = the other operand.
+ * ternary: refA, refB = the other two operands in x, y, z order, refC = the op's double argument (scalar). */
+#define FMB_CHAIN_MAX_INSTR 16
+#define FMB_CHAIN_MAX_LEAVES 8
+#define FMB_CHAIN_MAX_SCALARS 24
+int fmb_rv_eval_chain(int n_instr, const unsigned char* code, int start_leaf, const fmb_handle* leaves, int n_leaves,
+                      const double* scalars, int n_scalars, fmb_handle* out);
+
 /* ---- reductions (getAverage/getVariance/getMin/getMax ... :262-428).  Sums are accumulated in double-double
  *      (block + warp tree), returned as out2[0] = hi, out2[1] = lo so that shards can be combined exactly; the caller
  *      divides by n.  MIN/MAX return the value in out2[0]. -------------------------------------------------------------- */

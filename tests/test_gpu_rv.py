@@ -182,3 +182,72 @@ def test_concurrent_callers_like_the_reference_thread_pool(gpu):
     for t in threads:
         t.join()
     assert not errors, errors[:3]
+
+
+def _random_algebra(gpu, lazy, trials=50, n=1537):
+    """The same pseudo-random sequence of RandomVariable operations, evaluated with or without deferral."""
+    nvm = gpu.native
+    rng = np.random.default_rng(7)
+    base = [rng.normal(size=n) for _ in range(4)]
+    base[1][:6] = [np.nan, np.inf, -np.inf, 0.0, -0.0, 1e-310]
+    base[2] = np.abs(base[2]) + 0.1
+    nvm.set_lazy(lazy)
+    try:
+        vs = [gpu.RandomVariableCuda(float(i), b) for i, b in enumerate(base)]
+        rs = np.random.default_rng(11)
+        outs, times = [], []
+        l0 = nvm.launch_count()
+        for _ in range(trials):
+            x = vs[rs.integers(4)]
+            for _ in range(int(rs.integers(1, 24))):
+                c = int(rs.integers(0, 20))
+                y, z = vs[rs.integers(4)], vs[rs.integers(4)]
+                if c == 0: x = x.add(0.3)
+                elif c == 1: x = x.sub(y)
+                elif c == 2: x = x.bus(y)
+                elif c == 3: x = x.mult(y)
+                elif c == 4: x = x.div(y)
+                elif c == 5: x = x.vid(1.5)
+                elif c == 6: x = x.cap(0.7)
+                elif c == 7: x = x.floor(y)
+                elif c == 8: x = x.squared()
+                elif c == 9: x = x.abs().sqrt()
+                elif c == 10: x = x.addProduct(y, z)
+                elif c == 11: x = x.addProduct(y, 0.25)
+                elif c == 12: x = x.addRatio(y, z)
+                elif c == 13: x = x.subRatio(z, y)
+                elif c == 14: x = x.accrue(y, 0.5)
+                elif c == 15: x = x.discount(y, 0.5)
+                elif c == 16: x = y.choose(x, z)
+                elif c == 17: x = x.pow(2.0).add(x.pow(0.5))          # x consumed twice; pow special cases
+                elif c == 18: x = x.mult(x)                             # the same pending value in two operand positions
+                else: x = y.sub(0.03).mult(0.5).div(x).mult(z)          # x extends somebody else's chain from the second operand position
+            outs.append(x.getRealizations())
+            times.append(x.getFiltrationTime())
+        launches = nvm.launch_count() - l0
+    finally:
+        nvm.set_lazy(True)
+    return outs, times, launches
+
+
+@pytest.mark.gpu
+def test_deferred_chains_are_bit_identical_to_eager_evaluation(gpu):
+    """Deferred evaluation (one fmb_rv_eval_chain pass per chain) against one kernel per operation: same bits, fewer launches."""
+    lazy, tl, nl = _random_algebra(gpu, True)
+    eager, te, ne = _random_algebra(gpu, False)
+    assert tl == te
+    for a, b in zip(lazy, eager):
+        assert same_bits(a, b)
+    assert nl < 0.5 * ne, (nl, ne)
+
+
+@pytest.mark.gpu
+def test_deferred_operations_report_size_mismatch_at_once(gpu):
+    a, b = gpu.RandomVariableCuda(0.0, np.ones(10)), gpu.RandomVariableCuda(0.0, np.ones(11))
+    for lazy in (True, False):
+        gpu.native.set_lazy(lazy)
+        try:
+            with pytest.raises(ValueError):
+                a.add(1.0).mult(b)
+        finally:
+            gpu.native.set_lazy(True)
