@@ -185,26 +185,53 @@ __device__ __forceinline__ double ternaryDyn(int op, double x, double y, double 
 	}
 }
 
-__global__ void __launch_bounds__(256) chainKernel(const __grid_constant__ ChainProg p, double* __restrict__ out, uint64_t n) {
+// Two elements per thread.  Phase 1 issues the loads of ALL leaf vectors back to back (a fetch inside the interpreter loop would wait
+// ~1 us for HBM once per instruction) and parks the values in the thread's own shared-memory column, where the interpreter can index
+// them dynamically; phase 2 walks the instructions.  No barrier: a column is private to its thread.  (Four elements per thread measured
+// slower: 124 registers, and the dispatch is not the dominant cost - profiles/r01_notes.md.)
+__global__ void __launch_bounds__(256) chainKernel(const __grid_constant__ ChainProg p, double* __restrict__ out, uint64_t n, int nLeaves, int vec) {
+	__shared__ double2 col[FMB_CHAIN_MAX_LEAVES][256];
+	const int tid = threadIdx.x;
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-		double acc = p.leaf[p.start][i];
+	const uint64_t pairs = (n + 1) >> 1;
+	for (uint64_t i2 = blockIdx.x * (uint64_t)blockDim.x + tid; i2 < pairs; i2 += stride) {
+		const uint64_t i = 2 * i2;
+		const bool two = i + 1 < n;
+		double2 v[FMB_CHAIN_MAX_LEAVES];
+#pragma unroll
+		for (int l = 0; l < FMB_CHAIN_MAX_LEAVES; l++) {
+			if (l < nLeaves) {
+				if (two && vec) v[l] = *reinterpret_cast<const double2*>(p.leaf[l] + i);
+				else v[l] = make_double2(p.leaf[l][i], two ? p.leaf[l][i + 1] : 0.0);
+			}
+		}
+#pragma unroll
+		for (int l = 0; l < FMB_CHAIN_MAX_LEAVES; l++) if (l < nLeaves) col[l][tid] = v[l];
+		double2 acc = col[p.start][tid];
 		for (int k = 0; k < p.n; k++) {
 			const ChainInstr c = p.code[k];
 			if (c.kind == 0) {
-				acc = unaryDyn(c.op, acc, p.scalar[c.refA & 127]);
+				const double a = p.scalar[c.refA & 127];
+				acc.x = unaryDyn(c.op, acc.x, a);
+				acc.y = unaryDyn(c.op, acc.y, a);
 			} else {
-				const double u = (c.refA & 128) ? p.scalar[c.refA & 127] : p.leaf[c.refA][i];
+				double2 u;
+				if (c.refA & 128) { const double sv = p.scalar[c.refA & 127]; u = make_double2(sv, sv); } else u = col[c.refA][tid];
 				if (c.kind == 1) {
-					acc = (c.pos == 0) ? binaryDyn(c.op, acc, u) : binaryDyn(c.op, u, acc);
+					if (c.pos == 0) { acc.x = binaryDyn(c.op, acc.x, u.x); acc.y = binaryDyn(c.op, acc.y, u.y); }
+					else { acc.x = binaryDyn(c.op, u.x, acc.x); acc.y = binaryDyn(c.op, u.y, acc.y); }
 				} else {
-					const double v = (c.refB & 128) ? p.scalar[c.refB & 127] : p.leaf[c.refB][i];
+					double2 w;
+					if (c.refB & 128) { const double sv = p.scalar[c.refB & 127]; w = make_double2(sv, sv); } else w = col[c.refB][tid];
 					const double a = p.scalar[c.refC & 127];
-					acc = (c.pos == 0) ? ternaryDyn(c.op, acc, u, v, a) : (c.pos == 1) ? ternaryDyn(c.op, u, acc, v, a) : ternaryDyn(c.op, u, v, acc, a);
+					if (c.pos == 0) { acc.x = ternaryDyn(c.op, acc.x, u.x, w.x, a); acc.y = ternaryDyn(c.op, acc.y, u.y, w.y, a); }
+					else if (c.pos == 1) { acc.x = ternaryDyn(c.op, u.x, acc.x, w.x, a); acc.y = ternaryDyn(c.op, u.y, acc.y, w.y, a); }
+					else { acc.x = ternaryDyn(c.op, u.x, w.x, acc.x, a); acc.y = ternaryDyn(c.op, u.y, w.y, acc.y, a); }
 				}
 			}
 		}
-		out[i] = acc;
+		if (two && vec) *reinterpret_cast<double2*>(out + i) = acc;
+		else { out[i] = acc.x; if (two) out[i + 1] = acc.y; }
 	}
 }
 
@@ -378,7 +405,9 @@ int fmb_rv_eval_chain(int n_instr, const unsigned char* code, int start_leaf, co
 	double* dst;
 	FMB_TRY(newVec(n, out, &dst));
 	if (n == 0) return FMB_OK;
-	chainKernel<<<ewGrid(2 * n), 256, 0, ctx().stream>>>(p, dst, n);
+	int vec = aligned16(dst);
+	for (int i = 0; i < n_leaves; i++) vec = vec && aligned16(p.leaf[i]);
+	chainKernel<<<ewGrid(n), 256, 0, ctx().stream>>>(p, dst, n, n_leaves, vec);
 	return finishLaunch(out);
 }
 

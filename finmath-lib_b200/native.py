@@ -182,28 +182,42 @@ class DeviceVector:
 # set_lazy(False) switches the deferral off.
 CHAIN_MAX_INSTR, CHAIN_MAX_LEAVES, CHAIN_MAX_SCALARS = 16, 8, 24
 _lazy = os.environ.get("FMB_LAZY", "1") != "0"
+# Deferral pays where the device time dominates (it removes kernel launches and HBM round trips of intermediate results); on short
+# vectors a valuation is bound by the host, and eager launches overlap the device with the host better (measured on C5, profiles/
+# r01_notes.md).  Vectors shorter than this are evaluated eagerly.
+_lazy_min_n = int(os.environ.get("FMB_LAZY_MIN_N", "2000000"))
 
 
-def set_lazy(on):
-    global _lazy
+def set_lazy(on, min_n=None):
+    """Switch deferred evaluation on / off; min_n = shortest vector that is deferred (None keeps the current threshold)."""
+    global _lazy, _lazy_min_n
     _lazy = bool(on)
+    if min_n is not None:
+        _lazy_min_n = int(min_n)
 
 
 def lazy_enabled():
     return _lazy
 
 
+def lazy_min_n():
+    return _lazy_min_n
+
+
 class LazyVector:
     """Result of element-wise operations that has not been evaluated yet.  Duck-types DeviceVector (h, n, download, get).
-    start: the leaf the accumulator starts from; prog: [(kind, op, pos, others, a)] with others = vectors (DeviceVector) or floats."""
-    __slots__ = ("_h", "n", "start", "prog", "uses", "__weakref__")
+    start: the leaf the accumulator starts from; prog: tuple of (kind, op, pos, others, a) with others = vectors or floats;
+    nvec / nsca: upper bounds of the distinct leaf vectors / scalars the chain needs."""
+    __slots__ = ("_h", "n", "start", "prog", "uses", "nvec", "nsca", "__weakref__")
 
-    def __init__(self, n, start, prog):
+    def __init__(self, n, start, prog, nvec, nsca):
         self._h = 0
         self.n = n
         self.start = start
         self.prog = prog
         self.uses = 0
+        self.nvec = nvec
+        self.nsca = nsca
 
     @property
     def h(self):
@@ -215,8 +229,9 @@ class LazyVector:
         return self._h == 0
 
     def __del__(self):
-        h, self._h = self._h, 0
+        h = self._h
         if h and _lib is not None:
+            self._h = 0
             try:
                 _lib.fmb_rv_free(h)
             except Exception:
@@ -234,109 +249,112 @@ class LazyVector:
 
     def _materialize(self):
         out = C.c_uint64()
-        prog, lib = self.prog, load()
+        prog, lib = self.prog, _lib
         if len(prog) == 1:                                   # one operation: the specialised kernel
             kind, op, pos, others, a = prog[0]
-            ops = list(others)
-            ops.insert(pos, self.start)
-            hs = [o.h if not isinstance(o, float) else 0 for o in ops]
-            sc = [o if isinstance(o, float) else 0.0 for o in ops]
             if kind == 0:
-                check(lib.fmb_rv_unary(op, hs[0], a, C.byref(out)))
-            elif kind == 1:
-                check(lib.fmb_rv_binary(op, hs[0], sc[0], hs[1], sc[1], C.byref(out)))
+                rc = lib.fmb_rv_unary(op, self.start.h, a, _byref(out))
             else:
-                check(lib.fmb_rv_ternary(op, hs[0], sc[0], hs[1], sc[1], hs[2], sc[2], a, C.byref(out)))
+                ops = list(others)
+                ops.insert(pos, self.start)
+                hs = [0 if type(o) is float else o.h for o in ops]
+                sc = [o if type(o) is float else 0.0 for o in ops]
+                if kind == 1:
+                    rc = lib.fmb_rv_binary(op, hs[0], sc[0], hs[1], sc[1], _byref(out))
+                else:
+                    rc = lib.fmb_rv_ternary(op, hs[0], sc[0], hs[1], sc[1], hs[2], sc[2], a, _byref(out))
         else:
-            leaves, leaf_index, scalars, scalar_index = [], {}, [], {}
-
-            def ref(o):
-                if isinstance(o, float):
-                    key = o.hex() if o == o else "nan"
-                    i = scalar_index.get(key)
-                    if i is None:
-                        i = scalar_index[key] = len(scalars)
-                        scalars.append(o)
-                    return 128 | i
-                i = leaf_index.get(id(o))
-                if i is None:
-                    i = leaf_index[id(o)] = len(leaves)
-                    leaves.append(o)
-                return i
-
-            start = ref(self.start)
+            leaves, leaf_index, scalars, scalar_index = [self.start], {id(self.start): 0}, [], {}
             code = bytearray()
             for kind, op, pos, others, a in prog:
-                if kind == 0:
-                    code += bytes((0, op, 0, ref(float(a)), 0, 0, 0, 0))
-                elif kind == 1:
-                    code += bytes((1, op, pos, ref(others[0]), 0, 0, 0, 0))
-                else:
-                    code += bytes((2, op, pos, ref(others[0]), ref(others[1]), ref(float(a)), 0, 0))
-            hs = np.array([o.h for o in leaves], dtype=np.uint64)
-            sc = np.array(scalars if scalars else [0.0], dtype=np.float64)
-            check(lib.fmb_rv_eval_chain(len(prog), bytes(code), start, hptr(hs), len(leaves), dptr(sc), len(scalars), C.byref(out)))
+                refs = [0, 0, 0]
+                k = 0
+                for o in others:
+                    if type(o) is float:
+                        mergeable = o == o and o != 0.0                   # NaN and signed zeros are never merged (0.0 == -0.0)
+                        i = scalar_index.get(o) if mergeable else None
+                        if i is None:
+                            i = len(scalars)
+                            scalars.append(o)
+                            if mergeable:
+                                scalar_index[o] = i
+                        refs[k] = 128 | i
+                    else:
+                        i = leaf_index.get(id(o))
+                        if i is None:
+                            i = leaf_index[id(o)] = len(leaves)
+                            leaves.append(o)
+                        refs[k] = i
+                    k += 1
+                if kind != 1:                                # the operation's own double argument
+                    mergeable = a == a and a != 0.0
+                    i = scalar_index.get(a) if mergeable else None
+                    if i is None:
+                        i = len(scalars)
+                        scalars.append(a)
+                        if mergeable:
+                            scalar_index[a] = i
+                    refs[2 if kind == 2 else 0] = 128 | i
+                code += bytes((kind, op, pos, refs[0], refs[1], refs[2], 0, 0))
+            hs = (C.c_uint64 * len(leaves))(*[o.h for o in leaves])
+            sc = (C.c_double * max(1, len(scalars)))(*scalars)
+            rc = lib.fmb_rv_eval_chain(len(prog), bytes(code), 0, hs, len(leaves), sc, len(scalars), _byref(out))
+        if rc != FMB_OK:
+            check(rc)
         self._h = out.value
         self.start = None
         self.prog = None
 
 
-def _chain_cost(prog, extra_vectors, extra_scalars):
-    """(instructions, distinct leaf vectors, scalars) upper bounds of a chain after one more instruction."""
-    vec, sca = {0}, 0                                        # 0 stands for the start leaf
-    for kind, op, pos, others, a in prog:
-        for o in others:
-            if isinstance(o, float):
-                sca += 1
-            else:
-                vec.add(id(o))
-        sca += 1 if kind != 1 else 0
-    for o in extra_vectors:
-        vec.add(id(o))
-    return len(prog) + 1, len(vec), sca + extra_scalars
+_byref = C.byref
 
 
 def _lazy_op(kind, op, operands, a):
     """operands: positional list of DeviceVector / LazyVector / float (scalar broadcast).  Returns a LazyVector."""
-    n = next(o.n for o in operands if not isinstance(o, float))
-    for o in operands:
-        if not isinstance(o, float) and o.n != n:
-            raise ValueError("finmath_b200: operand sizes differ (%d vs %d)" % (o.n, n))      # IllegalArgumentException, as the eager call
-    # the operand whose pending chain this operation extends: the first unevaluated, not yet consumed LazyVector
+    n = -1
     host = -1
+    nvec = nsca = 0
     for i, o in enumerate(operands):
-        if isinstance(o, LazyVector) and o._h == 0:
-            if host < 0 and o.uses == 0:
-                others = [x for j, x in enumerate(operands) if j != i]
-                instr, vec, sca = _chain_cost(o.prog, [x for x in others if not isinstance(x, float)],
-                                              sum(1 for x in others if isinstance(x, float)) + (1 if kind != 1 else 0))
-                if instr <= CHAIN_MAX_INSTR and vec <= CHAIN_MAX_LEAVES and sca <= CHAIN_MAX_SCALARS:
-                    host = i
-                    continue
-            o.h                                              # second consumer, or the chain is full: evaluate it, use it as a leaf
-    if host >= 0 and operands[host]._h != 0:                 # the same object in two operand positions: it has just been evaluated
-        host = -1
+        if type(o) is float:
+            nsca += 1
+            continue
+        if n < 0:
+            n = o.n
+        elif o.n != n:
+            raise ValueError("finmath_b200: operand sizes differ (%d vs %d)" % (o.n, n))      # IllegalArgumentException, as the eager call
+        nvec += 1
+        # the operand whose pending chain this operation extends: the first unevaluated, not yet consumed LazyVector with room left
+        if type(o) is LazyVector and o._h == 0:
+            if host < 0 and o.uses == 0 and len(o.prog) < CHAIN_MAX_INSTR and o.nvec + 2 <= CHAIN_MAX_LEAVES and o.nsca + 3 <= CHAIN_MAX_SCALARS:
+                host = i
+            else:
+                o._materialize()                             # second consumer, or the chain is full: evaluate it, use it as a leaf
+    if kind != 1:
+        nsca += 1
     if host >= 0:
         base = operands[host]
-        base.uses += 1
-        others = tuple(x for j, x in enumerate(operands) if j != host)
-        return LazyVector(n, base.start, base.prog + [(kind, op, host, others, float(a))])
-    start = next(i for i, o in enumerate(operands) if not isinstance(o, float))
+        if base._h == 0:                                     # (not the case when the same object sits in two operand positions)
+            base.uses = 1
+            others = tuple(x for j, x in enumerate(operands) if j != host)
+            return LazyVector(n, base.start, base.prog + ((kind, op, host, others, a),), base.nvec + nvec - 1, base.nsca + nsca)
+    start = 0
+    while type(operands[start]) is float:
+        start += 1
     others = tuple(x for j, x in enumerate(operands) if j != start)
-    return LazyVector(n, operands[start], [(kind, op, start, others, float(a))])
+    return LazyVector(n, operands[start], ((kind, op, start, others, a),), nvec, nsca)
 
 
 def unary(op, x, a=0.0):
-    if _lazy:
-        return _lazy_op(0, op, [x], a)
+    if _lazy and x.n >= _lazy_min_n:
+        return _lazy_op(0, op, (x,), float(a))
     out = C.c_uint64()
     check(load().fmb_rv_unary(op, x.h, float(a), C.byref(out)))
     return DeviceVector(out.value, x.n)
 
 
 def binary(op, x, sx, y, sy):
-    if _lazy:
-        return _lazy_op(1, op, [x if x is not None else float(sx), y if y is not None else float(sy)], 0.0)
+    if _lazy and (x if x is not None else y).n >= _lazy_min_n:
+        return _lazy_op(1, op, (x if x is not None else float(sx), y if y is not None else float(sy)), 0.0)
     out = C.c_uint64()
     check(load().fmb_rv_binary(op, x.h if x is not None else 0, float(sx), y.h if y is not None else 0, float(sy), C.byref(out)))
     n = x.n if x is not None else y.n
@@ -344,8 +362,8 @@ def binary(op, x, sx, y, sy):
 
 
 def ternary(op, x, sx, y, sy, z, sz, a=0.0):
-    if _lazy:
-        return _lazy_op(2, op, [x if x is not None else float(sx), y if y is not None else float(sy), z if z is not None else float(sz)], a)
+    if _lazy and next(v for v in (x, y, z) if v is not None).n >= _lazy_min_n:
+        return _lazy_op(2, op, (x if x is not None else float(sx), y if y is not None else float(sy), z if z is not None else float(sz)), float(a))
     out = C.c_uint64()
     check(load().fmb_rv_ternary(op, x.h if x is not None else 0, float(sx), y.h if y is not None else 0, float(sy),
                                 z.h if z is not None else 0, float(sz), float(a), C.byref(out)))

@@ -40,3 +40,4 @@ run(4000)
 pr.disable()
 print("launches in one valuation:", nv.launch_count() - l0)
 pstats.Stats(pr).sort_stats("tottime").print_stats(14)
+pstats.Stats(pr).sort_stats("cumtime").print_stats(28)

@@ -340,3 +340,28 @@ def test_localized_regression_and_linear_regression(gpu, orc):
     lr3 = gpu.LinearRegression([RV(0.0, np.ones(n)), RV(0.0, b1), RV(0.0, b1 * b1)]).getRegressionCoefficients(RV(0.0, y))
     X = np.stack([np.ones(n), b1, b1 * b1], axis=1)
     assert np.allclose(lr3, np.linalg.lstsq(X, y, rcond=None)[0], rtol=1e-9, atol=1e-10)
+
+
+def test_products_price_identically_with_deferred_arithmetic(gpu):
+    """Bermudan swaption, swaption and caplet through the unchanged product algebra, once with every element-wise operation deferred
+    into fused chains (fmb_rv_eval_chain) and once with one kernel per operation: identical bits, fewer launches."""
+    nvm = gpu.native
+    s = lmm_setup(gpu)
+    b = bermudan_spec(s)
+    keep = nvm.lazy_min_n()
+    prices, launches = [], []
+    for lazy in (True, False):
+        nvm.set_lazy(lazy, min_n=0)
+        try:
+            sim = lmm_device(gpu, s, 2500)
+            sim.getProcess().getProcessValue(s["T"], s["N"] - 1)
+            l0 = nvm.launch_count()
+            berm = gpu.BermudanSwaption(b["is_exercise"], b["fixing"], b["lengths"], b["payment"], b["notionals"], b["swaprates"]).getValue(sim)
+            swpt = gpu.Swaption(1.0, [1.0, 1.5, 2.0, 2.5], [1.5, 2.0, 2.5, 3.0], [0.05] * 4).getValue(sim)
+            capl = gpu.Caplet(2.0, 0.5, 0.05).getValue(sim)
+            launches.append(nvm.launch_count() - l0)
+            prices.append((berm, swpt, capl))
+        finally:
+            nvm.set_lazy(True, min_n=keep)
+    assert prices[0] == prices[1]
+    assert launches[0] < 0.6 * launches[1], launches

@@ -191,7 +191,8 @@ def _random_algebra(gpu, lazy, trials=50, n=1537):
     base = [rng.normal(size=n) for _ in range(4)]
     base[1][:6] = [np.nan, np.inf, -np.inf, 0.0, -0.0, 1e-310]
     base[2] = np.abs(base[2]) + 0.1
-    nvm.set_lazy(lazy)
+    keep = nvm.lazy_min_n()
+    nvm.set_lazy(lazy, min_n=0)
     try:
         vs = [gpu.RandomVariableCuda(float(i), b) for i, b in enumerate(base)]
         rs = np.random.default_rng(11)
@@ -226,7 +227,7 @@ def _random_algebra(gpu, lazy, trials=50, n=1537):
             times.append(x.getFiltrationTime())
         launches = nvm.launch_count() - l0
     finally:
-        nvm.set_lazy(True)
+        nvm.set_lazy(True, min_n=keep)
     return outs, times, launches
 
 
@@ -244,10 +245,11 @@ def test_deferred_chains_are_bit_identical_to_eager_evaluation(gpu):
 @pytest.mark.gpu
 def test_deferred_operations_report_size_mismatch_at_once(gpu):
     a, b = gpu.RandomVariableCuda(0.0, np.ones(10)), gpu.RandomVariableCuda(0.0, np.ones(11))
+    keep = gpu.native.lazy_min_n()
     for lazy in (True, False):
-        gpu.native.set_lazy(lazy)
+        gpu.native.set_lazy(lazy, min_n=0)
         try:
             with pytest.raises(ValueError):
                 a.add(1.0).mult(b)
         finally:
-            gpu.native.set_lazy(True)
+            gpu.native.set_lazy(True, min_n=keep)
