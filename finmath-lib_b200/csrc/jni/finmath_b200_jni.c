@@ -56,6 +56,22 @@ JNIEXPORT jlong JNICALL Java_net_finmath_cuda_FinmathB200_ternary(JNIEnv* env, j
 		jlong z, jdouble sz, jdouble a) {
 	fmb_handle out = 0; CHECK(fmb_rv_ternary(op, (fmb_handle)x, sx, (fmb_handle)y, sy, (fmb_handle)z, sz, a, &out)); return (jlong)out;
 }
+/* a chain of element-wise operations in one pass (a RandomVariableCuda that defers evaluation builds code / leaves / scalars) */
+JNIEXPORT jlong JNICALL Java_net_finmath_cuda_FinmathB200_evalChain(JNIEnv* env, jclass c, jbyteArray code, jint startLeaf, jlongArray leaves,
+		jdoubleArray scalars) {
+	const jsize nCode = (*env)->GetArrayLength(env, code), nLeaves = (*env)->GetArrayLength(env, leaves);
+	const jsize nScalars = (*env)->GetArrayLength(env, scalars);
+	jbyte* pc = (*env)->GetByteArrayElements(env, code, NULL);
+	jlong* pl = (*env)->GetLongArrayElements(env, leaves, NULL);
+	jdouble* ps = (*env)->GetDoubleArrayElements(env, scalars, NULL);
+	fmb_handle out = 0;
+	const int rc = fmb_rv_eval_chain(nCode / 8, (const unsigned char*)pc, startLeaf, (const fmb_handle*)pl, nLeaves, ps, nScalars, &out);
+	(*env)->ReleaseByteArrayElements(env, code, pc, JNI_ABORT);
+	(*env)->ReleaseLongArrayElements(env, leaves, pl, JNI_ABORT);
+	(*env)->ReleaseDoubleArrayElements(env, scalars, ps, JNI_ABORT);
+	CHECK(rc);
+	return (jlong)out;
+}
 /* returns hi + lo of the double-double sum (single-GPU JVM); min / max in [0] */
 JNIEXPORT jdouble JNICALL Java_net_finmath_cuda_FinmathB200_reduce(JNIEnv* env, jclass c, jint op, jlong x, jlong w, jdouble a) {
 	double out[2] = {0, 0}; CHECK(fmb_rv_reduce(op, (fmb_handle)x, (fmb_handle)w, a, out)); return out[0] + out[1];

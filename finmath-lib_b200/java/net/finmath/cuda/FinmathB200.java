@@ -29,6 +29,8 @@ public final class FinmathB200 {
 	public static native long unary(int op, long x, double a);
 	public static native long binary(int op, long x, double sx, long y, double sy);
 	public static native long ternary(int op, long x, double sx, long y, double sy, long z, double sz, double a);
+	/** A chain of element-wise operations in one pass: code = 8 bytes per instruction (include/finmath_b200.h, fmb_rv_eval_chain). */
+	public static native long evalChain(byte[] code, int startLeaf, long[] leaves, double[] scalars);
 	public static native double reduce(int op, long x, long w, double a);
 	public static native long[] brownianGenerate(int seed, int numberOfTimeSteps, int numberOfFactors, long paths, long pathOffset, double[] sqrtDt);
 	public static native long[] eulerLmm(int scheme, int measure, int stateSpace, double liborCap, int T, int N, int F, long paths, double[] dt, long[] dW,
