@@ -189,7 +189,8 @@ template <int FT> struct LmmRec {
 // only cross-rate dependency is the running factor sum S, so the U log / exp / reciprocal chains overlap (ILP U).
 template <int FT, bool LOGN, int MODE, bool SPOT, int U, bool CORRECTOR, bool PARTIAL, bool FAST, bool FIRST>
 __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __restrict__ rec0, int recStep, int i0, int jBeg, int colStep, int F,
-		bool functional, double d, const double* w, double* S, double* L0, double* Y0, size_t mOff, uint64_t pOff, int cnt) {
+		bool functional, double d, const double* w, double* S, double* L0, double* Y0, size_t mOff, uint64_t pOff, int cnt,
+		const double* __restrict__ logTab) {
 	// rec0 / L0 / Y0 point at the chunk's first rate (record, shared-memory state, scratch column; the predictor drift column is Y0 + mOff);
 	// recStep / colStep move them to the next rate in processing order (the caller advances them chunk by chunk, so no index
 	// multiplications are left in the loop).  i0 = position of the first rate in processing order (j = jBeg +- i).
@@ -219,7 +220,7 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 #pragma unroll
 			for (int u = 0; u < U; u++) { const int i = i0 + ((PARTIAL && u >= cnt) ? cnt - 1 : u); y[u] = q.ylog0[SPOT ? jBeg + i : jBeg - i]; }
 		} else if (LOGN) {
-			regular = flogNFast<U>(L, y);
+			regular = flogNFast<U>(logTab, L, y);
 		} else {
 #pragma unroll
 			for (int u = 0; u < U; u++) y[u] = L[u];
@@ -297,7 +298,7 @@ __device__ __forceinline__ void lmmChunk(const LmmParams& q, const double* __res
 // One time step of one path: all live rates in chunks of U, then (predictor-corrector) the corrector pass.
 template <int FT, bool LOGN, int MODE, bool SPOT, bool FAST, bool FIRST>
 __device__ __forceinline__ void lmmTimeStep(const LmmParams& q, int t, int N, int F, int BD, bool functional, const double* const* __restrict__ dW,
-		uint64_t p, uint64_t pOff, double* wNext, double* Lcol, double* Ybuf, size_t mOff) {
+		uint64_t p, uint64_t pOff, double* wNext, double* Lcol, double* Ybuf, size_t mOff, const double* __restrict__ logTab) {
 	constexpr int FMAX = FT > 0 ? FT : 16;
 	constexpr int U = FMB_LMM_U;
 	const int first = q.firstLive[t];
@@ -325,18 +326,18 @@ __device__ __forceinline__ void lmmTimeStep(const LmmParams& q, int t, int N, in
 	double* Yp = Ybuf + jBeg * BD;
 	int i = 0;
 	for (; i + U <= live; i += U, rp += U * recStep, Lp += U * colStep, Yp += U * colStep)
-		lmmChunk<FT, LOGN, MODE, SPOT, U, false, false, FAST, FIRST>(q, rp, recStep, i, jBeg, colStep, F, functional, d, w, S, Lp, Yp, mOff, pOff, U);
+		lmmChunk<FT, LOGN, MODE, SPOT, U, false, false, FAST, FIRST>(q, rp, recStep, i, jBeg, colStep, F, functional, d, w, S, Lp, Yp, mOff, pOff, U, logTab);
 	if (i < live)
-		lmmChunk<FT, LOGN, MODE, SPOT, U, false, true, FAST, FIRST>(q, rp, recStep, i, jBeg, colStep, F, functional, d, w, S, Lp, Yp, mOff, pOff, live - i);
+		lmmChunk<FT, LOGN, MODE, SPOT, U, false, true, FAST, FIRST>(q, rp, recStep, i, jBeg, colStep, F, functional, d, w, S, Lp, Yp, mOff, pOff, live - i, logTab);
 	if (MODE == 2) {
 		// corrector: drift re-evaluated on the predicted rates (EulerSchemeFromProcessModel.java:292-314)
 #pragma unroll
 		for (int k = 0; k < FMAX; k++) S[k] = 0.0;
 		rp = recBeg; Lp = Lcol + jBeg * BD; Yp = Ybuf + jBeg * BD;
 		for (i = 0; i + U <= live; i += U, rp += U * recStep, Lp += U * colStep, Yp += U * colStep)
-			lmmChunk<FT, LOGN, MODE, SPOT, U, true, false, FAST, false>(q, rp, recStep, i, jBeg, colStep, F, functional, d, w, S, Lp, Yp, mOff, pOff, U);
+			lmmChunk<FT, LOGN, MODE, SPOT, U, true, false, FAST, false>(q, rp, recStep, i, jBeg, colStep, F, functional, d, w, S, Lp, Yp, mOff, pOff, U, logTab);
 		if (i < live)
-			lmmChunk<FT, LOGN, MODE, SPOT, U, true, true, FAST, false>(q, rp, recStep, i, jBeg, colStep, F, functional, d, w, S, Lp, Yp, mOff, pOff, live - i);
+			lmmChunk<FT, LOGN, MODE, SPOT, U, true, true, FAST, false>(q, rp, recStep, i, jBeg, colStep, F, functional, d, w, S, Lp, Yp, mOff, pOff, live - i, logTab);
 	}
 }
 
@@ -353,6 +354,10 @@ template <int FT, bool LOGN, int MODE, bool SPOT, bool FAST> __global__ void __l
 	double* Ybuf = scratch + (size_t)blockIdx.x * 2 * N * BD + tid;      // [N][BD], this thread's column
 	const size_t mOff = (size_t)N * BD;                                   // the predictor drift columns follow the Y columns
 	double* Lcol = Lsh + tid;
+	// the log table (3 KB) behind the state store: dynamic per-lane indices are cheap in shared memory
+	double* logTab = Lsh + (size_t)N * BD;
+	for (int i = tid; i < 384; i += BD) logTab[i] = kLogTab[i];
+	__syncthreads();
 
 	// Warps take 32-path tiles from a global counter (no block-wide barriers anywhere: every thread only touches its own column), so the
 	// resident warps stay busy until the paths run out instead of each block owning a fixed share.
@@ -376,9 +381,9 @@ template <int FT, bool LOGN, int MODE, bool SPOT, bool FAST> __global__ void __l
 #pragma unroll
 		for (int k = 0; k < FMAX; k++) wNext[k] = (k < F) ? dW[k][p] : 0.0;
 		// the first step of a functional scheme starts from the host's log X(0): its own instantiation, no per-chunk test
-		lmmTimeStep<FT, LOGN, MODE, SPOT, FAST, true>(q, 0, N, F, BD, functional, dW, p, pOff, wNext, Lcol, Ybuf, mOff);
+		lmmTimeStep<FT, LOGN, MODE, SPOT, FAST, true>(q, 0, N, F, BD, functional, dW, p, pOff, wNext, Lcol, Ybuf, mOff, logTab);
 		for (int t = 1; t < q.T; t++)
-			lmmTimeStep<FT, LOGN, MODE, SPOT, FAST, false>(q, t, N, F, BD, functional, dW, p, pOff, wNext, Lcol, Ybuf, mOff);
+			lmmTimeStep<FT, LOGN, MODE, SPOT, FAST, false>(q, t, N, F, BD, functional, dW, p, pOff, wNext, Lcol, Ybuf, mOff, logTab);
 	}
 }
 
@@ -615,8 +620,8 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
 		// block size: the shared-memory column store is 8*N bytes per thread
 		int BD = 128;
 		if (const char* e = getenv("FMB_LMM_BD")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 128) BD = v; }   // tuning hook (profiles/r01_notes.md)
-		while (BD > 32 && (size_t)BD * N * sizeof(double) > 200 * 1024) BD >>= 1;
-		const size_t smem = (size_t)BD * N * sizeof(double);
+		while (BD > 32 && (size_t)BD * N * sizeof(double) > 196 * 1024) BD >>= 1;
+		const size_t smem = (size_t)BD * N * sizeof(double) + 384 * sizeof(double);      // state store + log table
 		if (smem > 220 * 1024) { setError("euler_lmm: %d components exceed the shared-memory state store", N); rc = FMB_EUNSUPPORTED; }
 		if (rc == FMB_OK) {
 			const int perSm = (int)std::max<size_t>(1, std::min<size_t>(16, (220 * 1024) / std::max<size_t>(smem, 1)));

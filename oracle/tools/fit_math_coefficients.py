@@ -38,15 +38,47 @@ err = max(abs((1 + x + x * x * horner(Q, x)) / mp.exp(x) - 1) for x in [(-R + 2 
 print("// exp: Q degree 9, max rel err of the rounded polynomial = %s" % mp.nstr(err, 3))
 print("EXP_Q = {" + ", ".join("%.17e" % v for v in Q) + "}")
 
-# log(1+f) = 2s + s*z*P(z),  s = f/(2+f), z = s^2, z in [0, (3-2*sqrt2)^2... ] : s in [-0.1716, 0.1716]
-smax = (mp.sqrt(2) - 1) / (mp.sqrt(2) + 1) * mp.mpf("1.0005")
-zmax = smax ** 2
-P = fit(lambda z: (2 * mp.atanh(mp.sqrt(z)) / mp.sqrt(z) - 2) / z if z != 0 else mp.mpf(2) / 3, mp.mpf(0), zmax, 7)
+# log: table-driven.  x = 2^k z, z in [0.6875, 1.375) cut into 128 intervals of equal bit-pattern length; log z = log c_i + log1p(r),
+# r = z * invc_i - 1.  logc is split into a multiple of 2^-43 (k*ln2_hi + logc_hi is then exact) and the rest.  The two intervals next
+# to 1 use invc = 1 (r = z - 1 exact, relative accuracy kept as x -> 1), which sets the polynomial's range to |r| <= 2^-7.
+import struct
+
+OFF_HI = 0x3fe60000
+
+
+def from_hi(hi):
+    return struct.unpack("<d", struct.pack("<Q", hi << 32))[0]
+
+
+tab, rmax = [], mp.mpf(0)
+for i in range(128):
+    lo_bits = OFF_HI + (i << 13)
+    a, b = mp.mpf(from_hi(lo_bits)), mp.mpf(from_hi(lo_bits + (1 << 13)))
+    invc = 1.0 if i in (79, 80) else float(1 / ((a + b) / 2))
+    logc = -mp.log(mp.mpf(invc))
+    hi = float(mp.nint(logc * mp.mpf(2) ** 43) / mp.mpf(2) ** 43)
+    tab.append((invc, hi, float(logc - mp.mpf(hi))))
+    rmax = max(rmax, abs(a * mp.mpf(invc) - 1), abs(b * mp.mpf(invc) - 1))
+
+
+def g(r):
+    if abs(r) < mp.mpf(10) ** -15:
+        return -mp.mpf(1) / 2 + r / 3 - r * r / 4
+    return (mp.log1p(r) - r) / r ** 2
+
+
+R = rmax * mp.mpf("1.001")
+A = fit(g, -R, R, 5)
 err = 0
 for k in range(1, 4001):
-    s = smax * k / 4000
-    z = s * s
-    approx = 2 * s + s * z * horner(P, z)
-    err = max(err, abs(approx / (2 * mp.atanh(s)) - 1))
-print("// log: P degree 7 in z = s^2, max rel err of the rounded polynomial = %s" % mp.nstr(err, 3))
-print("LOG_P = {" + ", ".join("%.17e" % v for v in P) + "}")
+    for sgn in (-1, 1):
+        r = sgn * R * k / 4000
+        err = max(err, abs((r + r * r * horner(A, r)) / mp.log1p(r) - 1))
+print("// log: |r| <= %s, A degree 5, max rel err of the rounded polynomial against log1p(r) = %s" % (mp.nstr(rmax, 6), mp.nstr(err, 3)))
+print("LOG_A (Horner order A5..A0) = {" + ", ".join("%.17e" % v for v in reversed(A)) + "}")
+print("LOG_TAB = {   // [0,128) invc, [128,256) logc_hi, [256,384) logc_lo")
+for col in range(3):
+    vals = [t[col] for t in tab]
+    for r0 in range(0, 128, 4):
+        print("\t" + ", ".join("%.17e" % v for v in vals[r0:r0 + 4]) + ",")
+print("};")
