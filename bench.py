@@ -39,7 +39,9 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md recipe).  The sampler is started before the
+    warm-up (a first nvidia-smi query on a fresh box can take a second), samples every 20 ms with a timestamp, and finish() keeps the
+    samples that fall inside the timed windows."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -49,16 +51,21 @@ class ClockSampler(threading.Thread):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
                     break
-                self.samples.append([x.strip() for x in line.split(",")])
+                self.samples.append((time.time(), [x.strip() for x in line.split(",")]))
         except Exception:
             pass
 
-    def finish(self):
+    def wait_first_sample(self, timeout=5.0):
+        t0 = time.time()
+        while not self.samples and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def finish(self, windows):
         self.stop_flag = True
         if self.proc is not None:
             try:
@@ -66,7 +73,9 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
         sm, mx, reasons = [], 0.0, set()
-        for s in self.samples:
+        for ts, s in self.samples:
+            if not any(a <= ts <= b for a, b in windows):
+                continue
             try:
                 sm.append(float(s[0]))
                 mx = max(mx, float(s[1]))
@@ -76,7 +85,8 @@ class ClockSampler(threading.Thread):
             except Exception:
                 continue
         busy = [c for c in sm if c > 0]
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm),
+                "window": "device-timed steps + end-to-end steps (20 ms period)"}
 
 
 def market(pkg):
@@ -173,20 +183,21 @@ def main():
         return None
 
     # ---- kernel-level timing: device events on the library's stream, K steps back to back ------------------------------
-    for w in range(args.warmup):
-        step(1000 + w)
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.3)
+    for w in range(args.warmup):
+        step(1000 + w)
+    sampler.wait_first_sample()
+    barrier()
     launches0 = nv.launch_count()
+    win_a = time.time()
     nv.timer_start()
     for k in range(args.steps):
         step(3141 + k)
     ms = nv.timer_stop_ms()
+    win_b = time.time()
     launches = nv.launch_count() - launches0
     barrier()
-    clocks = sampler.finish()
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device=shard.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -197,10 +208,12 @@ def main():
     for w in range(min(2, args.warmup)):
         step(2000 + w, price=True)                           # warm-up of the priced path (pool blocks of the product's temporaries)
     barrier()
+    win_c = time.time()
     t0 = time.perf_counter()
     prices = [step(3141 + k, price=True) for k in range(args.steps)]
     nv.synchronize()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.finish([(win_a, win_b), (win_c, time.time())])
     if dist is not None:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=shard.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -241,16 +254,16 @@ def main():
                     traffic = sum(float(k[m].split()[0]) * scale[k[m].split()[1]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
     except Exception:
         traffic = None
-    # FP64 work of the kernel: 64 FP64 instructions (DFMA/DADD/DMUL/DSETP) per live rate-step on the kernel's hot path, counted from the
+    # FP64 work of the kernel: 56 FP64 instructions (DFMA/DADD/DMUL/DSETP) per live rate-step on the kernel's hot path, counted from the
     # executed-instruction column of the ncu source page (profiles/r01_notes.md, profiles/tools/hot_path.py); DFMA-equivalent flops = 2 each
-    fp64_instr = 64.0 * live * P_local
+    fp64_instr = 56.0 * live * P_local
     fp64_achieved_tflops = 2.0 * fp64_instr / (eu * 1e-3) / 1e12
     roofline = {"bound": "hbm", "kernel": "eulerLmmKernel<3,1,0,1,0>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": euler_bytes, "avg_launch_ms": eu,
                 "note": "this kernel is FP64-pipe bound (double log + exp + division per rate-step), not HBM bound: see 'fp64' and DESIGN.md 4.3"}
     fp64 = {"bound": "fp64", "achieved": fp64_achieved_tflops, "peak": tf.value, "unit": "TFLOP/s (DFMA-equivalent)", "frac": fp64_achieved_tflops / tf.value,
             "peak_source": "fmb_bench_dfma_tflops, measured in this run (8 independent DFMA chains per thread)",
-            "fp64_instructions_per_rate_step": 64, "euler_ms": eu, "brownian_ms": float(np.mean(bm_ms)),
+            "fp64_instructions_per_rate_step": 56, "euler_ms": eu, "brownian_ms": float(np.mean(bm_ms)),
             "brownian_achieved_gbs": bm_bytes / (float(np.mean(bm_ms)) * 1e-3) / 1e9}
 
     # ---- optional FAST floating-point mode (not the headline: the headline is STRICT), same step, same sizes ---------------------------
