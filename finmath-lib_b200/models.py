@@ -473,6 +473,7 @@ class HullWhiteModel:
         self.dfDiscount = None if discountFactors is None else np.asarray(discountFactors, dtype=np.float64)
         self.dfForward = None if discountFactorsFromForwardCurve is None else np.asarray(discountFactorsFromForwardCurve, dtype=np.float64)
         self._numeraireDiscountFactors, self._dfFromForwardCache, self._forwardRateCache = [], [], []
+        self._mrTimeCache = {}
 
     def getNumberOfComponents(self): return 2
     def getNumberOfFactors(self): return 1                                                        # :287-290 (sic; the driver's count is used)
@@ -490,6 +491,14 @@ class HullWhiteModel:
         return i if i >= 0 else -i - 2
 
     def getMRTime(self, time, maturity):                                                          # :584-607
+        # (memoised: the integrals below ask for the same (time, maturity) pairs again and again; the values are immutable Scalars)
+        key = (time, maturity)
+        hit = self._mrTimeCache.get(key)
+        if hit is None:
+            hit = self._mrTimeCache[key] = self._getMRTime(time, maturity)
+        return hit
+
+    def _getMRTime(self, time, maturity):
         vm, td = self.volatilityModel, self.volatilityModel.getTimeDiscretization()
         i0, i1 = self._vol_index(time), self._vol_index(maturity)
         integral, timePrev = Scalar(0.0), time

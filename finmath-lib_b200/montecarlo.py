@@ -11,6 +11,8 @@ import ctypes as C
 import math
 import threading
 
+import bisect
+
 import numpy as np
 
 from . import native as nv
@@ -30,9 +32,14 @@ class TimeDiscretizationFromArray:
             times = list(args[0])
         rounded = sorted(set(self._round(t) for t in times))      # :57-64 round, distinct, sorted
         self.times = np.array(rounded, dtype=np.float64)
+        self._list = rounded                                # the same values as Python floats (scalar lookups without numpy overhead)
+        self._index = {t: i for i, t in enumerate(rounded)}
 
     def _round(self, t):
-        return float(np.rint(t / self.tick) * self.tick)           # Math.rint (half-even) :387-389
+        try:
+            return float(round(t / self.tick)) * self.tick         # Math.rint (half-even) :387-389; Python's round() is half-even too
+        except (OverflowError, ValueError):
+            return float(np.rint(t / self.tick) * self.tick)
 
     def getNumberOfTimes(self):
         return self.times.size
@@ -41,17 +48,17 @@ class TimeDiscretizationFromArray:
         return self.times.size - 1
 
     def getTime(self, i):
-        return float(self.times[i])
+        return self._list[i]
 
     def getTimeStep(self, i):
-        return float(self.times[i + 1] - self.times[i])
+        return self._list[i + 1] - self._list[i]
 
     def getTimeIndex(self, time):                           # Arrays.binarySearch :272-274
         key = self._round(time)
-        i = int(np.searchsorted(self.times, key, side="left"))
-        if i < self.times.size and self.times[i] == key:
+        i = self._index.get(key)
+        if i is not None:
             return i
-        return -(i + 1)
+        return -(bisect.bisect_left(self._list, key) + 1)
 
     def getTimeIndexNearestLessOrEqual(self, time):
         i = self.getTimeIndex(time)

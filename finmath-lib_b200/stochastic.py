@@ -108,11 +108,13 @@ class RandomVariable:
 
 
 def _is_number(x):
-    return isinstance(x, (int, float, np.floating, np.integer))
+    t = type(x)
+    return t is float or t is int or isinstance(x, (int, float, np.floating, np.integer))
 
 
 class Scalar(RandomVariable):
     """J/stochastic/Scalar.java — deterministic, priority 0, filtration time -inf."""
+    __slots__ = ("value",)
 
     def __init__(self, value):
         self.value = float(value)
@@ -190,16 +192,23 @@ class Scalar(RandomVariable):
     def pow(self, e): return self._u(nv.U_POW, e)
 
     # binary: Scalar.java:276-312 — delegate to the argument with the re-ordered arithmetic
+    # (the Scalar-with-Scalar shortcuts below evaluate exactly the expression the delegation would: same operations, same order)
     def add(self, x):
+        if type(x) is Scalar:
+            return Scalar(x.value + self.value)
         return Scalar(self.value + x) if _is_number(x) else x.add(self.value)
 
     def sub(self, x):
+        if type(x) is Scalar:
+            return Scalar((x.value - self.value) * -1.0)
         return Scalar(self.value - x) if _is_number(x) else x.sub(self.value).mult(-1.0)
 
     def bus(self, x):
         return Scalar(x - self.value) if _is_number(x) else x.sub(self.value)
 
     def mult(self, x):
+        if type(x) is Scalar:
+            return Scalar(x.value * self.value)
         return Scalar(self.value * x) if _is_number(x) else x.mult(self.value)
 
     def div(self, x):
