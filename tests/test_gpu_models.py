@@ -156,6 +156,19 @@ def test_lmm_special_values_take_the_cold_paths(gpu, orc, case, scheme):
             assert np.isnan(got).any()
 
 
+@pytest.mark.parametrize("n_libors,period", [(130, 0.25), (260, 0.125)])
+def test_lmm_many_rates_shrinks_the_block(gpu, orc, n_libors, period):
+    """More forward rates than a 128-thread block can keep in shared memory (8*N bytes per thread): the fused kernel runs with 128-thread
+    blocks at one block per SM (N = 130) and with 64-thread blocks (N = 260); the warps still pull 32-path tiles."""
+    s = lmm_setup(gpu, n_libors=n_libors, n_factors=3, period=period, dt=1.0, horizon=8.0)
+    for paths in (97, 700):
+        dev = lmm_device(gpu, s, paths, scheme=2)
+        ref = lmm_oracle(orc, s, paths, scheme=2)
+        got = device_process_array(dev, s["T"], s["N"])
+        assert dev.getProcess().usedFusedKernel == "lmm"
+        assert rel_err(got, ref.process(), scale=0.05) < PATH_TOL
+
+
 def test_lmm_numeraire_forward_rate_swaption_caplet(gpu, orc):
     paths = 20_000
     s = lmm_setup(gpu)
