@@ -227,3 +227,86 @@ def test_hull_white_coefficient_tables_equal_oracle(pkg, orc):
         _, coef = orc.hull_white_process(3141, td.times, 4, vm.getTimeDiscretization().times, vol, mr, 0)
         mine = np.column_stack([spec["drift0"], spec["drift1"], spec["factorLoadings"]])
         assert np.array_equal(mine, coef)
+
+
+class _FakeLib:
+    """Stands in for libfinmath_b200.so under native.LazyVector: records the C-ABI calls a chain turns into (no device needed)."""
+
+    def __init__(self):
+        self.calls, self.next_handle = [], 100
+
+    def _out(self, ref):
+        self.next_handle += 1
+        ref._obj.value = self.next_handle
+        return 0
+
+    def fmb_rv_unary(self, op, x, a, out):
+        self.calls.append(("unary", op, x, a))
+        return self._out(out)
+
+    def fmb_rv_binary(self, op, x, sx, y, sy, out):
+        self.calls.append(("binary", op, x, sx, y, sy))
+        return self._out(out)
+
+    def fmb_rv_ternary(self, op, x, sx, y, sy, z, sz, a, out):
+        self.calls.append(("ternary", op, x, sx, y, sy, z, sz, a))
+        return self._out(out)
+
+    def fmb_rv_eval_chain(self, n, code, start, leaves, nl, scalars, ns, out):
+        self.calls.append(("chain", n, bytes(code), start, [int(leaves[i]) for i in range(nl)], [float(scalars[i]) for i in range(ns)]))
+        return self._out(out)
+
+    def fmb_rv_free(self, h):
+        return 0
+
+
+def test_deferred_arithmetic_builds_the_documented_chain_encoding(pkg, monkeypatch):
+    """native.LazyVector (host logic of fmb_rv_eval_chain): chains grow while a result has one consumer, a second consumer or a non
+    element-wise consumer evaluates them, one-operation chains use the specialised kernel, scalars that must not be merged are not."""
+    nv = pkg.native
+    fake = _FakeLib()
+    monkeypatch.setattr(nv, "_lib", fake)
+    monkeypatch.setattr(nv, "_lazy", True)
+    monkeypatch.setattr(nv, "_lazy_min_n", 0)
+    x, y, z = nv.DeviceVector(11, 8), nv.DeviceVector(12, 8), nv.DeviceVector(13, 8)
+    try:
+        # (x - 0.03) * 0.5 / y, then  z + that * y  (the pending chain sits in the second operand position of the ternary)
+        a = nv.binary(nv.B_DIV, nv.unary(nv.U_MULT, nv.unary(nv.U_SUB, x, 0.03), 0.5), 0.0, y, 0.0)
+        b = nv.ternary(nv.T_ADD_PRODUCT, z, 0.0, a, 0.0, y, 0.0)
+        assert fake.calls == [] and b.pending() and b.n == 8
+        h = b.h
+        assert h == 101 and not b.pending() and len(fake.calls) == 1
+        kind, n, code, start, leaves, scalars = fake.calls[0]
+        assert (kind, n, start, leaves, scalars) == ("chain", 4, 0, [11, 12, 13], [0.03, 0.5, 0.0])
+        assert code == bytes((0, nv.U_SUB, 0, 128, 0, 0, 0, 0)) + bytes((0, nv.U_MULT, 0, 129, 0, 0, 0, 0)) \
+            + bytes((1, nv.B_DIV, 0, 1, 0, 0, 0, 0)) + bytes((2, nv.T_ADD_PRODUCT, 1, 2, 1, 130, 0, 0))
+        # one operation: the specialised kernel, with the scalar broadcast in its operand position
+        fake.calls.clear()
+        assert nv.binary(nv.B_SUB, None, 2.0, x, 0.0).h == 102
+        assert fake.calls == [("binary", nv.B_SUB, 0, 2.0, 11, 0.0)]
+        # a second consumer evaluates the shared prefix once and uses it as a leaf
+        fake.calls.clear()
+        p = nv.unary(nv.U_EXP, nv.unary(nv.U_SQUARED, x))
+        q1, q2 = nv.unary(nv.U_ADD, p, 1.0), nv.unary(nv.U_ADD, p, 2.0)
+        assert [c[0] for c in fake.calls] == ["chain"] and fake.calls[0][1] == 2          # p itself (squared, exp), when q2 was built
+        q1.h, q2.h
+        assert [c[0] for c in fake.calls] == ["chain", "chain", "unary"]                  # q1 = x..+1 in one pass, q2 = p + 2
+        assert fake.calls[1][1] == 3 and fake.calls[2][2] == p.h
+        # +0.0 / -0.0 and NaN scalars keep their own slots
+        fake.calls.clear()
+        nv.unary(nv.U_MULT, nv.unary(nv.U_ADD, nv.unary(nv.U_ADD, x, 0.0), -0.0), float("nan")).h
+        sc = fake.calls[0][5]
+        assert len(sc) == 3 and np.signbit(sc[1]) and not np.signbit(sc[0]) and np.isnan(sc[2])
+        # operands of different lengths are rejected when the operation is issued
+        with pytest.raises(ValueError):
+            nv.binary(nv.B_ADD, x, 0.0, nv.DeviceVector(14, 9), 0.0)
+        # a full chain is evaluated and continued from its result
+        fake.calls.clear()
+        c = x
+        for _ in range(nv.CHAIN_MAX_INSTR + 3):
+            c = nv.unary(nv.U_ADD, c, 1.0)
+        c.h
+        assert [cc[1] for cc in fake.calls if cc[0] == "chain"] == [nv.CHAIN_MAX_INSTR, 3]
+    finally:
+        for v in (x, y, z):
+            v.h = 0                                            # fake handles: nothing to free
