@@ -326,11 +326,10 @@ static const int BM_HEADER = 16;                 // bytes in front of the ring (
 // Tail draws (|u - 0.5| > 0.425, 15 % of all) cost ~3x a central draw (log, sqrt, a second rational) and would make
 // almost every warp execute both branches.  They are parked in a shared-memory queue and evaluated by full warps.
 template <int NT> __device__ __forceinline__ void bmDrainTails(const double* __restrict__ qP, const uint32_t* __restrict__ qSlot, uint32_t count,
-		double* __restrict__ tile, const double* __restrict__ sq, uint32_t nPad, int tid) {
+		double* __restrict__ tile, int tid) {
 	for (uint32_t i = tid; i < count; i += NT) {
 		const double p = qP[i];
-		const uint32_t slot = qSlot[i];
-		tile[slot] = as241Tail(p, p - 0.5) * sq[slot / nPad];
+		tile[qSlot[i]] = as241Tail(p, p - 0.5);
 	}
 }
 
@@ -360,22 +359,24 @@ __device__ __forceinline__ void bmRefreshBlock(uint32_t* __restrict__ ring, uint
 }
 
 template <int NT> __global__ void __launch_bounds__(NT, NT == BM_THREADS ? 2 : 1) bmGenerateKernel(const uint32_t* __restrict__ states, double* __restrict__ out,
-		uint64_t P, uint32_t TF, uint32_t ppb, uint32_t tileN, uint32_t nPad, const double* __restrict__ sqrtDtPerColumn) {
+		uint64_t P, uint32_t TF, uint32_t ppb, uint32_t tileN, uint32_t nPad, uint32_t qCap, const double* __restrict__ sqrtDtPerColumn) {
 	extern __shared__ __align__(16) unsigned char smemRaw[];
 	uint32_t* qCountP = reinterpret_cast<uint32_t*>(smemRaw);
 	uint32_t* ring = reinterpret_cast<uint32_t*>(smemRaw + BM_HEADER);
 	double* qP = reinterpret_cast<double*>(smemRaw + BM_HEADER + RING_ALLOC * sizeof(uint32_t));
-	uint32_t* qSlot = reinterpret_cast<uint32_t*>(qP + TAILQ);
-	double* sq = reinterpret_cast<double*>(qSlot + TAILQ);
-	double* tile = sq + ((TF + 1) & ~1u);
+	uint32_t* qSlot = reinterpret_cast<uint32_t*>(qP + qCap);          // qCap entries (even): tail draws parked until a dense drain
+	double* tile = reinterpret_cast<double*>(qSlot + qCap);      // standard normals; sqrt(dt) of the column is applied when the tile is written out
 	const int tid = threadIdx.x;
 	const int lane = tid & 31, warp = tid >> 5;
 	static_assert(NT >= MT_N - MT_M && 2 * NT - 2 + 2 * MT_N <= RING, "block size against the refresh width / ring depth");
-	constexpr int BM_CHECK_EVERY = (NT >= 512) ? 1 : 2;              // batches between two looks at the tail queue
+	static_assert(TAILQ / 2 >= 2 * BM_THREADS + 64 && TAILQ >= 2 * BM_THREADS_WIDE + 64, "tail queue against the batch size");
+	// batches between two looks at the tail queue: two when that still leaves a full pass of work for a drain (queue >= 4 batches of
+	// worst-case tails), else one
+	const uint32_t checkEvery = (qCap >= 4u * NT) ? 2u : 1u;
+	const uint32_t drainAbove = qCap - (checkEvery + 1u) * NT;
 	static_assert((BM_HEADER + RING_ALLOC * sizeof(uint32_t)) % 8 == 0, "queue alignment");
 
 	for (int i = tid; i < MT_N; i += NT) ring[i] = states[(size_t)blockIdx.x * MT_N + i];
-	for (uint32_t i = tid; i < TF; i += NT) sq[i] = sqrtDtPerColumn[i];
 	if (tid == 0) *qCountP = 0;
 	__syncthreads();
 
@@ -406,7 +407,7 @@ template <int NT> __global__ void __launch_bounds__(NT, NT == BM_THREADS ? 2 : 1
 				const double q = u - 0.5;
 				const uint32_t slot = c * nPad + pl;
 				if (fabs(q) <= 0.425) {
-					tile[slot] = as241Central(q) * sq[c];
+					tile[slot] = as241Central(q);
 				} else {
 					const uint32_t k = atomicAdd(qCountP, 1u);
 					qP[k] = u;
@@ -418,11 +419,11 @@ template <int NT> __global__ void __launch_bounds__(NT, NT == BM_THREADS ? 2 : 1
 			avail -= (int)(2 * need);
 			pl += stepP; c += stepC;
 			if (c >= TF) { c -= TF; pl++; }
-			// every BM_CHECK_EVERY-th batch: make sure the queue keeps room for the next ones (at most NT new tails per batch)
-			if ((++it & (BM_CHECK_EVERY - 1)) == 0) {
+			// every checkEvery-th batch: make sure the queue keeps room for the next ones (at most NT new tails per batch)
+			if ((++it & (checkEvery - 1u)) == 0) {
 				__syncthreads();
-				if (*qCountP > TAILQ - (BM_CHECK_EVERY + 1) * NT) {
-					bmDrainTails<NT>(qP, qSlot, *qCountP, tile, sq, nPad, tid);
+				if (*qCountP > drainAbove) {
+					bmDrainTails<NT>(qP, qSlot, *qCountP, tile, tid);
 					__syncthreads();
 					if (tid == 0) *qCountP = 0;
 					__syncthreads();
@@ -430,15 +431,16 @@ template <int NT> __global__ void __launch_bounds__(NT, NT == BM_THREADS ? 2 : 1
 			}
 		}
 		__syncthreads();
-		bmDrainTails<NT>(qP, qSlot, *qCountP, tile, sq, nPad, tid);
+		bmDrainTails<NT>(qP, qSlot, *qCountP, tile, tid);
 		__syncthreads();
 		if (tid == 0) *qCountP = 0;
 		if (n >= 32) {
 			double* dst = out + (size_t)warp * P + p0 + lane;
 			const double* srcRow = tile + warp * nPad + lane;
 			for (uint32_t cc = warp; cc < TF; cc += NT / 32) {
+				const double sdt = __ldg(sqrtDtPerColumn + cc);
 #pragma unroll 4
-				for (uint32_t i = 0; i + lane < n; i += 32) dst[i] = srcRow[i];
+				for (uint32_t i = 0; i + lane < n; i += 32) dst[i] = srcRow[i] * sdt;
 				dst += (size_t)(NT / 32) * P;
 				srcRow += (NT / 32) * nPad;
 			}
@@ -447,7 +449,7 @@ template <int NT> __global__ void __launch_bounds__(NT, NT == BM_THREADS ? 2 : 1
 			uint32_t cc = (uint32_t)tid / n, i = (uint32_t)tid - cc * n;
 			const uint32_t sC = NT / n, sI = NT - sC * n;
 			for (uint32_t idx = tid; idx < U; idx += NT) {
-				out[(size_t)cc * P + p0 + i] = tile[cc * nPad + i];
+				out[(size_t)cc * P + p0 + i] = tile[cc * nPad + i] * __ldg(sqrtDtPerColumn + cc);
 				cc += sC; i += sI;
 				if (i >= n) { i -= n; cc++; }
 			}
@@ -647,17 +649,21 @@ int fmb_bm_generate(int32_t seed, int T, int F, uint64_t paths, uint64_t path_of
 	const uint64_t TF = (uint64_t)T * F;
 	if (TF > 24000) { setError("bm_generate: T*F = %llu exceeds the shared-memory tile limit (24000)", (unsigned long long)TF); return FMB_EUNSUPPORTED; }
 
-	// shared-memory tile: [TF][nPad] doubles + ring + per-column sqrt(dt)
-	const size_t fixed = BM_HEADER + RING_ALLOC * sizeof(uint32_t) + TAILQ * (sizeof(double) + sizeof(uint32_t)) + ((TF + 1) & ~1ull) * sizeof(double);
-	// two blocks per SM when a >= 4-path tile fits in half of the 227 KB, else one block with the whole of it.  (Three blocks per SM with
-	// smaller tiles measured slower: one more level of jump-ahead heads costs more than the extra warps give, profiles/r01_notes.md.)
-	uint32_t tileN = 0;
-	const size_t budgets[2] = { 112 * 1024, 224 * 1024 };
-	for (int attempt = 0; attempt < 2; attempt++) {
+	// shared memory: header + ring + tail queue + tile [TF][nPad].  Two blocks per SM when a >= 4-path tile fits in half of the 227 KB -
+	// with the full tail queue if possible, else with a half-size one (wide T*F: two 320-thread blocks hide each other's barriers, one
+	// 640-thread block cannot) - else one block with the whole of it.  (Three blocks per SM with smaller tiles measured slower: one more
+	// level of jump-ahead heads costs more than the extra warps give, profiles/r01_notes.md.)
+	uint32_t tileN = 0, qCap = TAILQ;
+	size_t fixed = 0;
+	const size_t budgets[3] = { 112 * 1024, 112 * 1024, 224 * 1024 };
+	const uint32_t queues[3] = { (uint32_t)TAILQ, (uint32_t)TAILQ / 2, (uint32_t)TAILQ };
+	for (int attempt = 0; attempt < 3; attempt++) {
+		qCap = queues[attempt];
+		fixed = BM_HEADER + RING_ALLOC * sizeof(uint32_t) + (size_t)qCap * (sizeof(double) + sizeof(uint32_t));
 		const size_t avail = budgets[attempt] > fixed ? budgets[attempt] - fixed : 0;
 		const uint64_t maxPad = avail / (TF * sizeof(double));
 		if (maxPad >= 5) { tileN = (uint32_t)std::min<uint64_t>(((maxPad - 1) / 4) * 4, 256); break; }
-		if (attempt == 1) tileN = maxPad >= 2 ? (uint32_t)(maxPad - 1) : (uint32_t)maxPad;
+		if (attempt == 2) tileN = maxPad >= 2 ? (uint32_t)(maxPad - 1) : (uint32_t)maxPad;
 	}
 	if (tileN == 0) { setError("bm_generate: tile does not fit shared memory"); return FMB_EUNSUPPORTED; }
 	const uint32_t nPad = tileN >= 2 ? (tileN | 1u) : tileN;      // odd row stride: conflict-free 8-byte column writes
@@ -707,10 +713,10 @@ int fmb_bm_generate(int32_t seed, int T, int F, uint64_t paths, uint64_t path_of
 	if (rc == FMB_OK) {
 		if (wide)
 			bmGenerateKernel<BM_THREADS_WIDE><<<B, BM_THREADS_WIDE, smem, c.stream>>>((const uint32_t*)heads, (double*)slab->base, paths, (uint32_t)TF,
-			                                                                      (uint32_t)ppb, tileN, nPad, (const double*)dsq);
+			                                                                      (uint32_t)ppb, tileN, nPad, qCap, (const double*)dsq);
 		else
 			bmGenerateKernel<BM_THREADS><<<B, BM_THREADS, smem, c.stream>>>((const uint32_t*)heads, (double*)slab->base, paths, (uint32_t)TF,
-			                                                          (uint32_t)ppb, tileN, nPad, (const double*)dsq);
+			                                                          (uint32_t)ppb, tileN, nPad, qCap, (const double*)dsq);
 		countLaunch();
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess) { setError("bm_generate launch: %s", cudaGetErrorString(e)); rc = FMB_ECUDA; }
