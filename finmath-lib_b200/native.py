@@ -185,7 +185,10 @@ _lazy = os.environ.get("FMB_LAZY", "1") != "0"
 # Deferral pays where the device time dominates (it removes kernel launches and HBM round trips of intermediate results); on short
 # vectors a valuation is bound by the host, and eager launches overlap the device with the host better (measured on C5, profiles/
 # r01_notes.md).  Vectors shorter than this are evaluated eagerly.
-_lazy_min_n = int(os.environ.get("FMB_LAZY_MIN_N", "2000000"))
+try:
+    _lazy_min_n = int(os.environ.get("FMB_LAZY_MIN_N", "2000000"))
+except ValueError:
+    _lazy_min_n = 2000000
 
 
 def set_lazy(on, min_n=None):
