@@ -4,9 +4,17 @@ Paths are independent: rank g of G owns the contiguous path block [g*P/G, (g+1)*
 MT19937 sub-stream starts at word 2*T*F*path_offset (jump-ahead), so the union over ranks is bit-identical to the
 single-stream reference.  No path data ever moves between GPUs; the only exchange is the tiny reduction behind
 getAverage / getVariance / getMin / getMax and the regression's 27 moments: per rank a double-double pair per sum,
-all-gathered over torch.distributed (NCCL on GPUs, gloo in the CPU tests) and merged in rank order on every rank, so
-all ranks hold the same bits.
+all-gathered and merged in rank order on every rank, so all ranks hold the same bits.
+
+The partials are already on the host when they are exchanged (fmb_rv_reduce returns them).  Between processes of ONE node they
+travel through a shared-memory mailbox (a few microseconds); the torch.distributed all-gather (NCCL on GPUs: host -> device ->
+NVLink -> host, ~120 us for 16 bytes; gloo in the CPU tests) is the path across nodes and can be forced with
+FMB_TINY_COLLECTIVES=torch.  A Bermudan valuation issues ~70 of these exchanges (profiles/r01_scaling.md).
 """
+import atexit
+import os
+import time
+
 import numpy as np
 
 
@@ -22,11 +30,73 @@ def dd_merge(hi1, lo1, hi2, lo2):
     return _two_sum(s, e)
 
 
+class _Mailbox:
+    """All-gather of a few doubles between the processes of one node through POSIX shared memory.  Layout: per rank one cache line
+    with a sequence number, then two message buffers (alternating, so that a fast rank that is already in the next exchange never
+    overwrites what a slow rank still reads: a rank can only be two exchanges ahead after everybody has published the one in
+    between, i.e. has finished reading the previous one)."""
+    MAXN = 128                                             # doubles per message (the 27 + 27 regression moments fit)
+
+    def __init__(self, rank, world, name, create):
+        from multiprocessing import shared_memory
+        self.rank, self.world, self.seq = rank, world, 0
+        nbytes = world * 64 + 2 * world * self.MAXN * 8
+        self.shm = shared_memory.SharedMemory(name=name, create=create, size=nbytes)
+        if not create:
+            # only the creating rank owns (and unlinks) the segment; keep this process's resource tracker out of it
+            try:
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self.seqs = np.ndarray((world, 8), dtype=np.int64, buffer=self.shm.buf, offset=0)
+        self.data = np.ndarray((2, world, self.MAXN), dtype=np.float64, buffer=self.shm.buf, offset=world * 64)
+        if create:
+            self.seqs[:] = 0
+        self.owner = create
+
+    def all_gather(self, values, timeout=120.0):
+        n = len(values)
+        s = self.seq + 1
+        b = s & 1
+        self.data[b, self.rank, :n] = values
+        self.seqs[self.rank, 0] = s                        # publish after the payload (program order; x86 keeps stores ordered)
+        deadline = None
+        for r in range(self.world):
+            spins = 0
+            while self.seqs[r, 0] < s:
+                spins += 1
+                if spins > 2000:                           # a peer is far behind (e.g. still computing): stop burning the core
+                    if deadline is None:
+                        deadline = time.time() + timeout
+                    elif time.time() > deadline:
+                        raise RuntimeError("finmath_b200: rank %d did not join a reduction within %.0f s" % (r, timeout))
+                    time.sleep(0.00002)
+        out = self.data[b, :, :n].copy()
+        self.seq = s
+        return out
+
+    def close(self):
+        try:
+            self.seqs = self.data = None
+            self.shm.close()
+            if self.owner:
+                self.shm.unlink()
+        except Exception:
+            pass
+
+
 class ShardContext:
     def __init__(self, rank=0, world=1, group=None, device=None):
         self.rank, self.world, self.group, self.device = int(rank), int(world), group, device
         self.collectives = 0
         self._buffers = {}
+        self._mailbox = None
+
+    def use_mailbox(self, name, create):
+        """Switch the tiny all-gathers to the shared-memory mailbox (all ranks on one node)."""
+        self._mailbox = _Mailbox(self.rank, self.world, name, create)
+        atexit.register(self._mailbox.close)
 
     # ---- partition -----------------------------------------------------------------------------------------------
     def local_range(self, n_global):
@@ -48,10 +118,12 @@ class ShardContext:
     def _all_gather(self, values):
         """values: list of floats -> array [world][len(values)], identical on every rank.  One small NCCL all-gather over
         NVLink (gloo on CPU); buffers are cached per message length, the result comes back in a single device-to-host copy."""
-        import torch
-        import torch.distributed as dist
         self.collectives += 1
         n = len(values)
+        if self._mailbox is not None and n <= _Mailbox.MAXN:
+            return self._mailbox.all_gather(values)
+        import torch
+        import torch.distributed as dist
         bufs = self._buffers.get(n)
         if bufs is None:
             on_gpu = self.device is not None
@@ -144,4 +216,33 @@ def from_environment(backend=None):
         device = torch.device("cuda", local_rank)
     if not dist.is_initialized():
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
-    return ShardContext(rank, world, None, device)
+    shard = ShardContext(rank, world, None, device)
+    if os.environ.get("FMB_TINY_COLLECTIVES", "shm") != "torch":
+        # all ranks on one node (the launch contract of bench.py): host-resident partials go through shared memory
+        import socket
+        hosts = [None] * world
+        dist.all_gather_object(hosts, socket.gethostname())
+        if len(set(hosts)) == 1:
+            name = "fmb_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid() if "TORCHELASTIC_RUN_ID" in os.environ else 0)
+            names = [None] * world
+            dist.all_gather_object(names, name + "_%d" % os.getpid() if rank == 0 else None)
+            name = names[0]
+            ok = True
+            try:
+                if rank == 0:
+                    shard.use_mailbox(name, True)
+            except Exception:
+                ok = False
+            dist.barrier()
+            try:
+                if rank != 0:
+                    shard.use_mailbox(name, False)
+            except Exception:
+                ok = False
+            oks = [None] * world
+            dist.all_gather_object(oks, ok)
+            if not all(oks):                                   # somebody could not map the segment: everybody uses torch.distributed
+                if shard._mailbox is not None:
+                    shard._mailbox.close()
+                shard._mailbox = None
+    return shard

@@ -199,12 +199,14 @@ print("rank", shard.rank, "ok")
 '''
 
 
-def test_sharding_collectives_world_size_2_gloo(tmp_path):
-    """N > 1 host logic on CPU: two processes, gloo backend, 127.0.0.1 rendezvous."""
+@pytest.mark.parametrize("tiny", ["shm", "torch"])
+def test_sharding_collectives_world_size_2_gloo(tmp_path, tiny):
+    """N > 1 host logic on CPU: two processes, gloo backend, 127.0.0.1 rendezvous; the reductions' partials travel through the
+    shared-memory mailbox (co-located ranks) or through torch.distributed."""
     script = tmp_path / "worker.py"
-    script.write_text(_WORKER)
-    env = dict(os.environ, FMB_ROOT=ROOT)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)]
+    script.write_text(_WORKER.replace("assert shard.world == 2", "assert shard.world == 2 and (shard._mailbox is not None) == (os.environ['FMB_TINY_COLLECTIVES'] == 'shm')"))
+    env = dict(os.environ, FMB_ROOT=ROOT, FMB_TINY_COLLECTIVES=tiny)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29517" if tiny == "shm" else "29518", str(script)]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
     assert out.stdout.count("ok") == 2, out.stdout               # both ranks finished every assertion (their prints may interleave)
