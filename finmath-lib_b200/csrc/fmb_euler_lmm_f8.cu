@@ -1,0 +1,3 @@
+// eulerLmmKernel instantiations for F = 8 factors: see fmb_euler_lmm.cuh
+#include "fmb_euler_lmm.cuh"
+namespace fmb { FMB_LMM_DEFINE(8) }

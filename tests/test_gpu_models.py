@@ -111,6 +111,26 @@ def test_lmm_process_matches_oracle(gpu, orc, scheme, measure, state):
     assert p.getProcessValue(7, 3) is p.getProcessValue(3, 3) and p.getProcessValue(3, 3) is not p.getProcessValue(2, 3)
 
 
+@pytest.mark.parametrize("n_factors,schemes", [(1, [2, 1]), (4, [2, 3]), (5, [2, 0]), (6, [0, 1, 2, 3]), (7, [2]), (8, [2, 1]), (12, [2, 3])])
+def test_lmm_factor_counts_match_oracle(gpu, orc, n_factors, schemes):
+    """Every compile-time factor count of the fused kernel (F = 1..8: factor vectors in registers) and the run-time-F kernel above that
+    (factor vectors in shared memory).  T/montecarlo/interestrate/LIBORMarketModelValuationTest.java:75 uses 6 factors,
+    T/montecarlo/interestrate/HullWhiteModelTest.java:93 uses 1 for its LMM; all four schemes at F = 6, both measures."""
+    s = lmm_setup(gpu, n_libors=20, n_factors=n_factors)
+    for scheme in schemes:
+        for paths, measure in ((1500, "SPOT"), (333, "TERMINAL")):
+            dev = lmm_device(gpu, s, paths, scheme=scheme, measure=measure)
+            ref = lmm_oracle(orc, s, paths, scheme=scheme, measure=0 if measure == "SPOT" else 1)
+            got = device_process_array(dev, s["T"], s["N"])
+            assert dev.getProcess().usedFusedKernel == "lmm"
+            assert dev.getProcess().getNumberOfFactors() == n_factors
+            assert rel_err(got, ref.process(), scale=0.05) < PATH_TOL, (n_factors, scheme, measure)
+    if n_factors == 6:                                       # the op-by-op device path gives the same bits as the fused F = 6 kernel
+        a = lmm_device(gpu, s, 700, scheme=2)
+        b = lmm_device(gpu, s, 700, scheme=2, force_generic=True)
+        assert np.array_equal(device_process_array(a, s["T"], s["N"]), device_process_array(b, s["T"], s["N"]))
+
+
 def test_lmm_generic_path_equals_fused(gpu):
     s = lmm_setup(gpu, n_libors=10)
     a = lmm_device(gpu, s, 2000, scheme=1)
