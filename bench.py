@@ -142,6 +142,8 @@ def main():
     ap.add_argument("--cpu-paths", type=int, default=0, help="sample size of the CPU baseline (0 = auto)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-bermudan", action="store_true")
+    ap.add_argument("--skip-configs", action="store_true", help="skip the C1/C2/C3 side measurements")
+    ap.add_argument("--bermudan-strong-paths", type=int, default=8_000_000, help="total paths of the strong-scaling Bermudan valuation (C5: 8M)")
     args = ap.parse_args()
     if args.cpu_paths == 0:
         args.cpu_paths = 20000 * max(1, (os.cpu_count() or 1))
@@ -243,7 +245,13 @@ def main():
     achieved = euler_bytes / (eu * 1e-3) / 1e9
     import ctypes as C
     tf = C.c_double()
-    nv.check(nv.load().fmb_bench_dfma_tflops(C.byref(tf)))
+    dfma_sampler = ClockSampler(local_rank)
+    dfma_sampler.start()
+    dfma_sampler.wait_first_sample()
+    t_d0 = time.time()
+    for _ in range(3):
+        nv.check(nv.load().fmb_bench_dfma_tflops(C.byref(tf)))
+    dfma_clocks = dfma_sampler.finish([(t_d0, time.time())])
     # DRAM traffic per launch from the committed ncu --set full capture (profiles/r01_top_kernels_ncu.json), valid for the 4 M-path launch
     traffic = None
     try:
@@ -258,13 +266,19 @@ def main():
     # executed-instruction column of the ncu source page (profiles/r01_notes.md, profiles/tools/hot_path.py); DFMA-equivalent flops = 2 each
     fp64_instr = 56.0 * live * P_local
     fp64_achieved_tflops = 2.0 * fp64_instr / (eu * 1e-3) / 1e12
-    roofline = {"bound": "hbm", "kernel": "eulerLmmKernel<3,1,0,1,0>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": euler_bytes, "avg_launch_ms": eu,
-                "note": "this kernel is FP64-pipe bound (double log + exp + division per rate-step), not HBM bound: see 'fp64' and DESIGN.md 4.3"}
-    fp64 = {"bound": "fp64", "achieved": fp64_achieved_tflops, "peak": tf.value, "unit": "TFLOP/s (DFMA-equivalent)", "frac": fp64_achieved_tflops / tf.value,
-            "peak_source": "fmb_bench_dfma_tflops, measured in this run (8 independent DFMA chains per thread)",
-            "fp64_instructions_per_rate_step": 56, "euler_ms": eu, "brownian_ms": float(np.mean(bm_ms)),
-            "brownian_achieved_gbs": bm_bytes / (float(np.mean(bm_ms)) * 1e-3) / 1e9}
+    # The dominant kernel is FP64-pipe bound (double log + exp + division per rate-step; ncu: sm__pipe_fp64_cycles_active 68 %, DRAM 20 %), so
+    # the binding roofline is the FP64 pipe: DFMA-equivalent flops of the kernel's hot path / the DFMA peak measured in this run.  The
+    # HBM fraction (algorithmic bytes / measured copy bandwidth) is reported next to it in the same object.
+    roofline = {"bound": "fp64", "kernel": "eulerLmmKernel<3,1,0,1,0>", "achieved": fp64_achieved_tflops, "peak": tf.value,
+                "unit": "TFLOP/s", "frac": fp64_achieved_tflops / tf.value,
+                "peak_source": "fmb_bench_dfma_tflops measured in this run (8 independent DFMA chains per thread); MEASURED_PEAKS.json has no FP64 entry",
+                "fp64_instructions_per_rate_step": 56, "avg_launch_ms": eu,
+                "hbm": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": euler_bytes},
+                "traffic": traffic, "traffic_source": "static: profiles/r01_top_kernels_ncu.json (ncu --set full capture of this kernel at this size, not re-measured in this run)" if traffic else None,
+                "dfma_clocks": dfma_clocks}
+    fp64 = {"euler_ms": eu, "brownian_ms": float(np.mean(bm_ms)), "brownian_achieved_gbs": bm_bytes / (float(np.mean(bm_ms)) * 1e-3) / 1e9,
+            "brownian_hbm_frac": bm_bytes / (float(np.mean(bm_ms)) * 1e-3) / 1e9 / peak}
 
     # ---- optional FAST floating-point mode (not the headline: the headline is STRICT), same step, same sizes ---------------------------
     fast = None
@@ -282,29 +296,50 @@ def main():
         nv.set_fp_mode(0)
 
     # ---- C5: Bermudan swaption wall time (simulation + backward induction with regression, price on the host) ------------------
+    # weak: bermudan_paths per GPU (1 M: the north star's 8 M paths on 8 GPUs); strong: the SAME 8 M paths on however many GPUs run.
     bermudan = None
+    parity_inputs = None
     if not args.skip_bermudan:
         from common import bermudan_spec
         b = bermudan_spec(s)
         product = pkg.BermudanSwaption(b["is_exercise"], b["fixing"], b["lengths"], b["payment"], b["notionals"], b["swaprates"])
+
+        def bermudan_run(paths_total, fac, reps=3, with_swaption=False):
+            mdl = model if fac is factory else pkg.LIBORMarketModelFromCovarianceModel.of(s["tenor"], None, s["L0"], s["df"], fac, s["cov"], None,
+                                                                                      {"measure": "SPOT", "stateSpace": "LOGNORMAL"})
+            walls, price, sw, launches_b = [], None, None, 0
+            for rep in range(reps):
+                if fac is factory:
+                    barrier()
+                else:
+                    nv.synchronize()
+                l0 = nv.launch_count()
+                t0 = time.perf_counter()
+                bm = pkg.BrownianMotionCuda(s["sim"], F, paths_total, 3141, fac)
+                sim = pkg.LIBORMonteCarloSimulationFromLIBORModel(pkg.EulerSchemeFromProcessModel(mdl, bm, args.scheme))
+                price = product.getValue(sim)
+                nv.synchronize()
+                walls.append(time.perf_counter() - t0)
+                launches_b = nv.launch_count() - l0
+                if with_swaption and rep == reps - 1:
+                    sw = swaption.getValue(sim)
+                del sim, bm
+            wall = min(walls[1:]) if len(walls) > 1 else walls[0]
+            if dist is not None and fac is factory:
+                t = torch.tensor([wall], dtype=torch.float64, device=shard.device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                wall = float(t.item())
+            return {"wall_ms": 1e3 * wall, "paths": paths_total, "price": price, "launches": int(launches_b)}, sw
+
         Pb = args.bermudan_paths * world
-        walls = []
-        price_b = None
-        for rep in range(3):
-            barrier()
-            t0 = time.perf_counter()
-            bm = pkg.BrownianMotionCuda(s["sim"], F, Pb, 3141, factory)
-            sim = pkg.LIBORMonteCarloSimulationFromLIBORModel(pkg.EulerSchemeFromProcessModel(model, bm, args.scheme))
-            price_b = product.getValue(sim)
-            nv.synchronize()
-            walls.append(time.perf_counter() - t0)
-            del sim, bm
-        wall = min(walls[1:])
-        if dist is not None:
-            t = torch.tensor([wall], dtype=torch.float64, device=shard.device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            wall = float(t.item())
-        bermudan = {"wall_ms": 1e3 * wall, "paths": Pb, "price": price_b, "exercise_dates": 20, "basis_functions": 6}
+        weak, sw_sharded = bermudan_run(Pb, factory, with_swaption=True)
+        strong, _ = bermudan_run(args.bermudan_strong_paths, factory)
+        nv.load().fmb_pool_trim()
+        bermudan = dict(weak, exercise_dates=20, basis_functions=6, scaling="weak", paths_per_gpu=args.bermudan_paths,
+                        exchange=("native NCCL all-gather on the compute stream" if shard.native_comm else ("shared-memory mailbox" if shard._mailbox is not None else "torch.distributed"))
+                        if world > 1 else "none (1 GPU)",
+                        strong={"wall_ms": strong["wall_ms"], "paths": strong["paths"], "price": strong["price"], "scaling": "strong"})
+        parity_inputs = (Pb, weak["price"], sw_sharded, product, bermudan_run)
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only; bounded sample) ----------------------------------------------------
     cpu = None
@@ -323,6 +358,64 @@ def main():
                "reference_shaped": {"value": shaped_paths * T / sec_shaped, "cores": 1,
                                     "sample": "%d paths, one array pass + allocation per RandomVariable op, single sequential MT stream, %.1f s" % (shaped_paths, sec_shaped)}}
 
+    # ---- multi-rank parity (N > 1): the sharded prices against rank 0 recomputing the same logical simulation on ONE GPU, and a 20 000-path
+    #      sharded valuation against the CPU oracle, through the native exchange and through the host-side exchange -------------------
+    shard_parity = None
+    if world > 1 and parity_inputs is not None:
+        Pb, price_sharded, sw_sharded, product, bermudan_run = parity_inputs
+
+        def small_sharded(fac):
+            mdl = pkg.LIBORMarketModelFromCovarianceModel.of(s["tenor"], None, s["L0"], s["df"], fac, s["cov"], None, {"measure": "SPOT", "stateSpace": "LOGNORMAL"})
+            bm = pkg.BrownianMotionCuda(s["sim"], F, 20_000, 3141, fac)
+            sim = pkg.LIBORMonteCarloSimulationFromLIBORModel(pkg.EulerSchemeFromProcessModel(mdl, bm, args.scheme))
+            return product.getValue(sim), swaption.getValue(sim)
+
+        p20_native = small_sharded(factory)
+        exchanges = None
+        if shard.native_comm:
+            import ctypes as C
+            ex = C.c_uint64()
+            nv.check(nv.load().fmb_comm_info(None, None, C.byref(ex)))
+            exchanges = ex.value
+            barrier()
+            nv.check(nv.load().fmb_comm_shutdown())              # from here on the library reduces locally; shards are merged on the host
+            shard.native_comm = False
+        p20_host = small_sharded(pkg.RandomVariableCudaFactory(shard))           # torch.distributed (or mailbox) exchange of the same partials
+        barrier()
+        if rank == 0:
+            local = pkg.RandomVariableCudaFactory(pkg.LOCAL)
+            single, sw_single = bermudan_run(Pb, local, reps=2, with_swaption=True)
+            orc = graft.load_oracle()
+            from common import lmm_oracle
+            ref = lmm_oracle(orc, s, 20_000, scheme=args.scheme)
+            r = ref.bermudan(b["is_exercise"], b["fixing"], b["lengths"], b["payment"], b["notionals"], b["swaprates"])
+            ref_sw, _, _ = ref.swaption(5.0, fixing, payment, [0.05] * 10)
+            rel = lambda x, y: abs(x - y) / abs(y)
+            shard_parity = {
+                "paths": Pb, "bermudan_sharded": price_sharded, "bermudan_single_gpu": single["price"],
+                "bermudan_rel_vs_single_gpu": rel(price_sharded, single["price"]),
+                "swaption_rel_vs_single_gpu": rel(sw_sharded, sw_single),
+                "rel_vs_oracle_20k_paths": {"bermudan_native_exchange": rel(p20_native[0], r["price"]), "swaption_native_exchange": rel(p20_native[1], ref_sw),
+                                            "bermudan_host_exchange": rel(p20_host[0], r["price"]), "swaption_host_exchange": rel(p20_host[1], ref_sw)},
+                "single_gpu_same_paths_wall_ms": single["wall_ms"], "sharded_wall_ms": bermudan["wall_ms"],
+                "speedup_vs_single_gpu_same_paths": single["wall_ms"] / bermudan["wall_ms"],
+                "native_exchanges_total": exchanges, "tolerance": 1e-10,
+                "ok": bool(max(rel(price_sharded, single["price"]), rel(sw_sharded, sw_single), rel(p20_native[0], r["price"]), rel(p20_native[1], ref_sw),
+                               rel(p20_host[0], r["price"]), rel(p20_host[1], ref_sw)) <= 1e-10)}
+        barrier()
+
+    # ---- the other BASELINE.json configurations (N = 1 only; 1 warm-up + 2 timed repetitions each, device events) -----------------------
+    configs = None
+    if world == 1 and not args.skip_configs:
+        sys.path.insert(0, os.path.join(ROOT, "profiles"))
+        import bench_configs as bc
+        configs = bc.run_all(pkg)
+        if bermudan is not None:
+            configs.append({"config": "C5 LMM Bermudan swaption, %d paths (simulate + 20 exercise dates x 6 basis functions, price on the host)" % bermudan["paths"],
+                            "paths": bermudan["paths"], "steps": T, "ms": bermudan["wall_ms"], "path_steps_per_s": bermudan["paths"] * T / (bermudan["wall_ms"] * 1e-3)})
+            configs.append({"config": "C5 LMM Bermudan swaption, %d paths on this GPU count" % bermudan["strong"]["paths"], "paths": bermudan["strong"]["paths"], "steps": T,
+                            "ms": bermudan["strong"]["wall_ms"], "path_steps_per_s": bermudan["strong"]["paths"] * T / (bermudan["strong"]["wall_ms"] * 1e-3)})
+
     if rank == 0:
         line = {
             "metric": "LMM forward-rate path-steps/sec", "value": value, "unit": "path-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -335,7 +428,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "path-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "BrownianMotionCuda + EulerSchemeFromProcessModel + Swaption.getValue through the host API, price on the host each step",
                     "price": prices[-1]},
-            "roofline": roofline, "fp64": fp64, "fast_mode": fast, "bermudan": bermudan, "cpu_baseline": cpu,
+            "roofline": roofline, "kernels": fp64, "fast_mode": fast, "bermudan": bermudan, "shard_parity": shard_parity, "configs": configs,
+            "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     if dist is not None:

@@ -47,6 +47,20 @@ struct Vec {             // one RandomVariable's realizations on the device
 	size_t bytes;        // own allocation size (slab == nullptr)
 };
 
+// Multi-GPU exchange of reduction partials (one process per GPU): an NCCL communicator on the library's own compute stream, so that the
+// all-gather of a few doubles is stream-ordered between the local reduction kernel and the merge / solve kernel (no host round trip).
+// NCCL is bound at run time (dlopen of libnccl.so.2: the copy the host process already loaded, e.g. torch's, else the system's).
+struct Comm {
+	bool active = false;
+	int rank = 0, world = 1;
+	void* lib = nullptr;         // dlopen handle
+	void* comm = nullptr;        // ncclComm_t
+	double* sendBuf = nullptr;   // device, COMM_MAX_DOUBLES
+	double* gatherBuf = nullptr; // device, world * COMM_MAX_DOUBLES
+	uint64_t exchanges = 0;
+};
+static const int COMM_MAX_DOUBLES = 128;      // 2 * (8*9/2 + 8) = 88 doubles for the largest regression (K = 8)
+
 struct Context {
 	bool initialized = false;
 	int device = -1;
@@ -63,7 +77,12 @@ struct Context {
 	// small pinned + device scratch for reductions and parameter tables
 	void* pinned = nullptr; size_t pinnedBytes = 0;
 	void* scratch = nullptr; size_t scratchBytes = 0;
-	std::mutex scratchMu;       // serialises users of pinned/scratch (reductions, table uploads)
+	std::mutex scratchMu;       // serialises users of pinned/scratch (reductions, table uploads) and keeps their launch sequences contiguous on the stream
+	// results of reductions: written by the finalising kernel straight into mapped pinned host memory (no separate device-to-host copy)
+	double* hostResult = nullptr;      // host address, COMM_MAX_DOUBLES doubles
+	double* hostResultDev = nullptr;   // the same memory as the device sees it
+	unsigned int* ticket = nullptr;    // device counter of the last-block finalisation (zero between launches)
+	Comm comm;
 };
 
 Context& ctx();
@@ -78,7 +97,18 @@ size_t roundBytes(size_t bytes);
 int newVec(uint64_t n, fmb_handle* h, double** ptr);                    // own allocation
 int newSlab(size_t bytes, Slab** slab);
 fmb_handle newView(Slab* slab, double* ptr, uint64_t n);                 // refs = 1, slab->refs++
-int lookup(fmb_handle h, Vec** v);                                       // no ref change
+int lookup(fmb_handle h, Vec** v);                                       // pins the vector for the lifetime of the caller's PinScope
+int releaseRef(fmb_handle h);                                            // -1 reference; frees at zero (fmb_rv_free)
+// Every entry point that dereferences handles opens a PinScope first: lookup() then takes one reference per handle and the scope
+// gives them back when the entry point returns (after its kernels are enqueued), so a concurrent fmb_rv_free from a GC / cleaner
+// thread (the documented threading contract) can neither delete a Vec that is being read nor hand its block to another allocation
+// before the kernel that reads it is in the stream.
+struct PinScope {
+	std::vector<fmb_handle> held;
+	PinScope* prev;
+	PinScope();
+	~PinScope();
+};
 int lookupPtr(fmb_handle h, uint64_t expectN, const double** ptr);       // h == 0 -> nullptr; checks length if expectN != 0
 int ensureScratch(size_t pinnedBytes, size_t deviceBytes);
 

@@ -19,8 +19,18 @@ Context& ctx() {
 
 int requireInit() {
 	if (!ctx().initialized) {
-		// lazy init on device 0 / FMB_DEVICE so that a JNI caller does not need an explicit init
+		// lazy init so that a JNI caller does not need an explicit init: FMB_DEVICE, else LOCAL_RANK (one process per GPU under
+		// torchrun), else device 0.  A multi-process job without either must call fmb_init itself: silently putting every rank on
+		// device 0 would be wrong.
 		const char* d = getenv("FMB_DEVICE");
+		if (!d) d = getenv("LOCAL_RANK");
+		if (!d) {
+			const char* w = getenv("WORLD_SIZE");
+			if (w && atoi(w) > 1) {
+				setError("WORLD_SIZE=%s but neither FMB_DEVICE nor LOCAL_RANK is set: call fmb_init(device) explicitly", w);
+				return FMB_EINVAL;
+			}
+		}
 		return fmb_init(d ? atoi(d) : 0);
 	}
 	// the current device is per host thread; callers may be pool / GC threads
@@ -101,6 +111,14 @@ fmb_handle newView(Slab* slab, double* ptr, uint64_t n) {
 	return h;
 }
 
+static thread_local PinScope* g_scope = nullptr;
+
+PinScope::PinScope() : prev(g_scope) { g_scope = this; }
+PinScope::~PinScope() {
+	g_scope = prev;
+	for (fmb_handle h : held) releaseRef(h);
+}
+
 int lookup(fmb_handle h, Vec** v) {
 	Context& c = ctx();
 	std::lock_guard<std::mutex> lk(c.mu);
@@ -110,6 +128,26 @@ int lookup(fmb_handle h, Vec** v) {
 		return FMB_EHANDLE;
 	}
 	*v = it->second;
+	if (g_scope) { it->second->refs++; g_scope->held.push_back(h); }
+	return FMB_OK;
+}
+
+int releaseRef(fmb_handle h) {
+	Context& c = ctx();
+	Vec* v = nullptr;
+	Slab* dead = nullptr;
+	{
+		std::lock_guard<std::mutex> lk(c.mu);
+		auto it = c.table.find(h);
+		if (it == c.table.end()) { setError("unknown or freed handle 0x%llx", (unsigned long long)h); return FMB_EHANDLE; }
+		v = it->second;
+		if (--v->refs > 0) return FMB_OK;
+		c.table.erase(it);
+		if (v->slab && --v->slab->refs == 0) dead = v->slab;
+	}
+	if (!v->slab) poolFree(v->ptr, v->bytes);
+	if (dead) { poolFree(dead->base, dead->bytes); delete dead; }
+	delete v;
 	return FMB_OK;
 }
 
@@ -188,6 +226,10 @@ int fmb_init(int device) {
 	FMB_CUDA(cudaEventCreate(&c.ev1));
 	c.device = device;
 	c.smCount = prop.multiProcessorCount;
+	FMB_CUDA(cudaHostAlloc((void**)&c.hostResult, COMM_MAX_DOUBLES * sizeof(double), cudaHostAllocMapped));
+	FMB_CUDA(cudaHostGetDevicePointer((void**)&c.hostResultDev, c.hostResult, 0));
+	FMB_CUDA(cudaMalloc((void**)&c.ticket, 64));
+	FMB_CUDA(cudaMemsetAsync(c.ticket, 0, 64, c.stream));
 	c.initialized = true;
 	return ensureScratch(1 << 16, 1 << 20);
 }
@@ -211,8 +253,12 @@ int fmb_shutdown(void) {
 		c.freeLists.clear();
 		c.bytesCached = c.bytesInUse = 0;
 	}
+	fmb_comm_shutdown();
 	if (c.pinned) cudaFreeHost(c.pinned);
 	if (c.scratch) cudaFree(c.scratch);
+	if (c.hostResult) cudaFreeHost(c.hostResult);
+	if (c.ticket) cudaFree(c.ticket);
+	c.hostResult = c.hostResultDev = nullptr; c.ticket = nullptr;
 	c.pinned = c.scratch = nullptr; c.pinnedBytes = c.scratchBytes = 0;
 	cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1);
 	cudaStreamDestroy(c.stream);
@@ -275,6 +321,7 @@ int fmb_rv_upload(const double* host, uint64_t n, fmb_handle* out) {
 
 int fmb_rv_download(fmb_handle h, double* host, uint64_t n) {
 	FMB_TRY(requireInit());
+	PinScope pins;
 	Vec* v;
 	FMB_TRY(lookup(h, &v));
 	if (n != v->n) { setError("download of %llu elements from a vector of %llu", (unsigned long long)n, (unsigned long long)v->n); return FMB_EINVAL; }
@@ -287,6 +334,7 @@ int fmb_rv_download(fmb_handle h, double* host, uint64_t n) {
 
 int fmb_rv_get(fmb_handle h, uint64_t i, double* out) {
 	FMB_TRY(requireInit());
+	PinScope pins;
 	Vec* v;
 	FMB_TRY(lookup(h, &v));
 	if (i >= v->n) { setError("index %llu out of bounds (size %llu)", (unsigned long long)i, (unsigned long long)v->n); return FMB_EINVAL; }
@@ -296,6 +344,7 @@ int fmb_rv_get(fmb_handle h, uint64_t i, double* out) {
 }
 
 int fmb_rv_size(fmb_handle h, uint64_t* n) {
+	PinScope pins;
 	Vec* v;
 	FMB_TRY(lookup(h, &v));
 	*n = v->n;
@@ -303,6 +352,7 @@ int fmb_rv_size(fmb_handle h, uint64_t* n) {
 }
 
 int fmb_rv_device_ptr(fmb_handle h, void** dptr) {
+	PinScope pins;
 	Vec* v;
 	FMB_TRY(lookup(h, &v));
 	*dptr = v->ptr;
@@ -320,22 +370,7 @@ int fmb_rv_retain(fmb_handle h) {
 
 int fmb_rv_free(fmb_handle h) {
 	if (h == 0) return FMB_OK;
-	Context& c = ctx();
-	Vec* v = nullptr;
-	Slab* dead = nullptr;
-	{
-		std::lock_guard<std::mutex> lk(c.mu);
-		auto it = c.table.find(h);
-		if (it == c.table.end()) { setError("unknown or freed handle 0x%llx", (unsigned long long)h); return FMB_EHANDLE; }
-		v = it->second;
-		if (--v->refs > 0) return FMB_OK;
-		c.table.erase(it);
-		if (v->slab && --v->slab->refs == 0) dead = v->slab;
-	}
-	if (!v->slab) poolFree(v->ptr, v->bytes);
-	if (dead) { poolFree(dead->base, dead->bytes); delete dead; }
-	delete v;
-	return FMB_OK;
+	return releaseRef(h);
 }
 
 int fmb_pool_stats(uint64_t* bytes_in_use, uint64_t* bytes_cached, uint64_t* live_handles) {

@@ -270,6 +270,7 @@ extern "C" {
 
 int fmb_rv_fill(double value, uint64_t n, fmb_handle* out) {
 	FMB_TRY(requireInit());
+	PinScope pins;
 	if (!out) return FMB_EINVAL;
 	double* dst;
 	FMB_TRY(newVec(n, out, &dst));
@@ -280,6 +281,7 @@ int fmb_rv_fill(double value, uint64_t n, fmb_handle* out) {
 
 int fmb_rv_unary(int opcode, fmb_handle x, double a, fmb_handle* out) {
 	FMB_TRY(requireInit());
+	PinScope pins;
 	if (!out) return FMB_EINVAL;
 	if (opcode < 0 || opcode > FMB_U_POW) { setError("unknown unary op %d", opcode); return FMB_EINVAL; }
 	Context& c = ctx();
@@ -321,6 +323,7 @@ static int commonLength(const fmb_handle* hs, int cnt, uint64_t* n) {
 
 int fmb_rv_binary(int opcode, fmb_handle x, double sx, fmb_handle y, double sy, fmb_handle* out) {
 	FMB_TRY(requireInit());
+	PinScope pins;
 	if (!out) return FMB_EINVAL;
 	if (opcode < 0 || opcode > FMB_B_FLOOR) { setError("unknown binary op %d", opcode); return FMB_EINVAL; }
 	Context& c = ctx();
@@ -344,6 +347,7 @@ int fmb_rv_binary(int opcode, fmb_handle x, double sx, fmb_handle y, double sy, 
 
 int fmb_rv_ternary(int opcode, fmb_handle x, double sx, fmb_handle y, double sy, fmb_handle z, double sz, double a, fmb_handle* out) {
 	FMB_TRY(requireInit());
+	PinScope pins;
 	if (!out) return FMB_EINVAL;
 	if (opcode < 0 || opcode > FMB_T_CHOOSE) { setError("unknown ternary op %d", opcode); return FMB_EINVAL; }
 	Context& c = ctx();
@@ -369,6 +373,7 @@ int fmb_rv_ternary(int opcode, fmb_handle x, double sx, fmb_handle y, double sy,
 int fmb_rv_eval_chain(int n_instr, const unsigned char* code, int start_leaf, const fmb_handle* leaves, int n_leaves,
                       const double* scalars, int n_scalars, fmb_handle* out) {
 	FMB_TRY(requireInit());
+	PinScope pins;
 	if (!out || !code || !leaves || n_instr < 1 || n_instr > FMB_CHAIN_MAX_INSTR || n_leaves < 1 || n_leaves > FMB_CHAIN_MAX_LEAVES ||
 	    n_scalars < 0 || n_scalars > FMB_CHAIN_MAX_SCALARS || (n_scalars > 0 && !scalars) || start_leaf < 0 || start_leaf >= n_leaves) {
 		setError("eval_chain: bad argument");

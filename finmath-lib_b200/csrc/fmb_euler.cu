@@ -160,7 +160,8 @@ extern "C" {
 int fmb_euler_black_scholes(int scheme, int T, int F, uint64_t paths, const double* dt, const fmb_handle* dW,
                             double initial_value, double risk_free_rate, double volatility, fmb_handle* out) {
 	FMB_TRY(requireInit());
-	if (scheme < 0 || scheme > 3 || T <= 0 || F <= 0 || paths == 0 || !dt || !dW || !out) { setError("euler_black_scholes: bad argument"); return FMB_EINVAL; }
+	PinScope pins;
+	if (scheme < 0 || scheme > 3 || T <= 0 || F <= 0 || !dt || !dW || !out) { setError("euler_black_scholes: bad argument"); return FMB_EINVAL; }
 	Context& c = ctx();
 	std::vector<const double*> inc;
 	FMB_TRY(gatherIncrements(dW, T * F, paths, inc));
@@ -173,7 +174,7 @@ int fmb_euler_black_scholes(int scheme, int T, int F, uint64_t paths, const doub
 	const size_t oInc = blob.add(inc.data(), inc.size() * sizeof(double*));
 	const size_t oRows = blob.add(rows.data(), rows.size() * sizeof(double*));
 	int rc = blob.upload();
-	if (rc == FMB_OK) {
+	if (rc == FMB_OK && paths > 0) {                           // (a rank may own no paths: zero-length vectors, nothing to launch)
 		// BlackScholesModel.java:76-78: drift = r - sigma^2/2 (host scalars), initial state log(S0), X0 = exp(log S0)
 		const double drift = risk_free_rate - (volatility * volatility) / 2;
 		const double y0 = std::log(initial_value), x0 = std::exp(y0), ylog0 = std::log(x0);
@@ -199,7 +200,8 @@ int fmb_euler_heston(int scheme, int heston_scheme, int T, uint64_t paths, const
                      double initial_value, const double* risk_free_rate, double volatility, double theta, double kappa, double xi, double rho,
                      fmb_handle* out) {
 	FMB_TRY(requireInit());
-	if (scheme < 0 || scheme > 3 || heston_scheme < 0 || heston_scheme > 1 || T <= 0 || paths == 0 || !dt || !dW || !risk_free_rate || !out) {
+	PinScope pins;
+	if (scheme < 0 || scheme > 3 || heston_scheme < 0 || heston_scheme > 1 || T <= 0 || !dt || !dW || !risk_free_rate || !out) {
 		setError("euler_heston: bad argument"); return FMB_EINVAL;
 	}
 	Context& c = ctx();
@@ -215,7 +217,7 @@ int fmb_euler_heston(int scheme, int heston_scheme, int T, uint64_t paths, const
 	const size_t oInc = blob.add(inc.data(), inc.size() * sizeof(double*));
 	const size_t oRows = blob.add(rows.data(), rows.size() * sizeof(double*));
 	int rc = blob.upload();
-	if (rc == FMB_OK) {
+	if (rc == FMB_OK && paths > 0) {
 		HestonParams h;
 		const double y0 = std::log(initial_value);
 		h.x0 = std::exp(y0); h.ylog0 = std::log(h.x0); h.v0 = volatility * volatility;
@@ -239,7 +241,8 @@ int fmb_euler_heston(int scheme, int heston_scheme, int T, uint64_t paths, const
 int fmb_euler_hull_white(int T, uint64_t paths, const double* dt, const fmb_handle* dW, const double* drift0, const double* drift1,
                          const double* fl, fmb_handle* out) {
 	FMB_TRY(requireInit());
-	if (T <= 0 || paths == 0 || !dt || !dW || !drift0 || !drift1 || !fl || !out) { setError("euler_hull_white: bad argument"); return FMB_EINVAL; }
+	PinScope pins;
+	if (T <= 0 || !dt || !dW || !drift0 || !drift1 || !fl || !out) { setError("euler_hull_white: bad argument"); return FMB_EINVAL; }
 	Context& c = ctx();
 	std::vector<const double*> inc;
 	FMB_TRY(gatherIncrements(dW, T * 2, paths, inc));
@@ -255,7 +258,7 @@ int fmb_euler_hull_white(int T, uint64_t paths, const double* dt, const fmb_hand
 	const size_t oInc = blob.add(inc.data(), inc.size() * sizeof(double*));
 	const size_t oRows = blob.add(rows.data(), rows.size() * sizeof(double*));
 	int rc = blob.upload();
-	if (rc == FMB_OK) {
+	if (rc == FMB_OK && paths > 0) {
 		const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * 8, (paths + 255) / 256));
 		eulerHullWhiteKernel<<<grid, 256, 0, c.stream>>>(T, paths, blob.at<double>(oDt), blob.at<double>(oC0), blob.at<double>(oC1), blob.at<double>(oFl),
 		                                                blob.at<const double*>(oInc), (double* const*)blob.at<double*>(oRows));
@@ -273,8 +276,9 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
                   const double* dt, const fmb_handle* dW, const double* initial_state, const double* period_length,
                   const double* factor_loading, const double* variance, const int32_t* first_live, fmb_handle* out) {
 	FMB_TRY(requireInit());
+	PinScope pins;
 	if (scheme < 0 || scheme > 3 || measure < 0 || measure > 1 || state_space < 0 || state_space > 1 || T <= 0 || N <= 0 || F <= 0 || F > 64 ||
-	    paths == 0 || !dt || !dW || !initial_state || !period_length || !factor_loading || !variance || !first_live || !out) {
+	    !dt || !dW || !initial_state || !period_length || !factor_loading || !variance || !first_live || !out) {
 		setError("euler_lmm: bad argument"); return FMB_EINVAL;
 	}
 	Context& c = ctx();
@@ -323,7 +327,7 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
 	int rc = blob.upload();
 	void* scratch = nullptr;
 	size_t scratchBytes = 0;
-	if (rc == FMB_OK && liveRows) {
+	if (rc == FMB_OK && liveRows && paths > 0) {
 		LmmLaunch L;
 		LmmParams& q = L.q;
 		// FAST (fmb_set_fp_mode(1)): FMA contraction, and the functional schemes carry Y instead of re-deriving it as log(exp(Y)) every

@@ -644,9 +644,15 @@ int fmb_icdf(const double* host_p, uint64_t n, double* host_out) {
 
 int fmb_bm_generate(int32_t seed, int T, int F, uint64_t paths, uint64_t path_offset, const double* sqrt_dt, fmb_handle* out) {
 	FMB_TRY(requireInit());
-	if (T <= 0 || F <= 0 || paths == 0 || !sqrt_dt || !out) { setError("bm_generate: bad argument"); return FMB_EINVAL; }
+	if (T <= 0 || F <= 0 || !sqrt_dt || !out) { setError("bm_generate: bad argument"); return FMB_EINVAL; }
 	Context& c = ctx();
 	const uint64_t TF = (uint64_t)T * F;
+	if (paths == 0) {                                           // a rank that owns no paths of the logical simulation: zero-length increments
+		Slab* empty = nullptr;
+		FMB_TRY(newSlab(8, &empty));
+		for (uint64_t i = 0; i < TF; i++) out[i] = newView(empty, (double*)empty->base, 0);
+		return FMB_OK;
+	}
 	if (TF > 24000) { setError("bm_generate: T*F = %llu exceeds the shared-memory tile limit (24000)", (unsigned long long)TF); return FMB_EUNSUPPORTED; }
 
 	// shared memory: header + ring + tail queue + tile [TF][nPad].  Two blocks per SM when a >= 4-path tile fits in half of the 227 KB -

@@ -59,6 +59,22 @@ __device__ __forceinline__ double jmaxD(double a, double b) {
 
 static const int RED_THREADS = 256;
 
+// ---- last-block finalisation -------------------------------------------------------------------------------------------
+// Every CTA writes its partial, makes it visible (__threadfence) and takes a ticket; the CTA that draws the last ticket merges all
+// partials in a FIXED order (so the result is deterministic for a given grid) and writes the final value - to mapped pinned host
+// memory when the caller is waiting for a double, to the communicator's send buffer when shards are exchanged, or it goes straight on
+// to the regression solve.  atomicInc wraps the ticket back to zero, ready for the next launch (launches of these kernels are
+// serialised on the compute stream).
+__device__ __forceinline__ bool drawLastTicket(unsigned int* ticket) {
+	__shared__ bool isLast;
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) isLast = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+	__syncthreads();
+	if (isLast) __threadfence();
+	return isLast;
+}
+
 template <int OP> __device__ __forceinline__ double addend(double x, double w, double a) {
 	switch (OP) {
 	case FMB_R_SUM: return x;
@@ -69,8 +85,21 @@ template <int OP> __device__ __forceinline__ double addend(double x, double w, d
 	return x;
 }
 
+// block-level merge of one double-double per thread; result valid in thread 0
+__device__ __forceinline__ dd blockReduceDd(dd v) {
+	__shared__ dd sh[RED_THREADS / 32];
+	warpReduceDd(v);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	__syncthreads();                                   // (the buffer may still be read from a previous call)
+	if (lane == 0) sh[warp] = v;
+	__syncthreads();
+	if (threadIdx.x == 0) { for (int k = 1; k < RED_THREADS / 32; k++) ddMerge(v, sh[k]); }
+	return v;
+}
+
+// out2[0..1] = (hi, lo) of the sum over all n elements
 template <int OP> __global__ void __launch_bounds__(RED_THREADS) sumKernel(const double* __restrict__ x, const double* __restrict__ w,
-		double a, uint64_t n, double* __restrict__ partials /* [grid][2] */) {
+		double a, uint64_t n, double* __restrict__ partials /* [grid][2] */, unsigned int* ticket, double* __restrict__ out2) {
 	dd acc0 = {0.0, 0.0}, acc1 = {0.0, 0.0};
 	const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
 	uint64_t i = blockIdx.x * (uint64_t)RED_THREADS + threadIdx.x;
@@ -86,49 +115,182 @@ template <int OP> __global__ void __launch_bounds__(RED_THREADS) sumKernel(const
 		ddAdd(acc0, addend<OP>(x[i], w0, a));
 	}
 	ddMerge(acc0, acc1);
-	warpReduceDd(acc0);
-	__shared__ dd sh[RED_THREADS / 32];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	if (lane == 0) sh[warp] = acc0;
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		dd t = sh[0];
-		for (int k = 1; k < RED_THREADS / 32; k++) ddMerge(t, sh[k]);
-		partials[2 * blockIdx.x] = t.hi;
-		partials[2 * blockIdx.x + 1] = t.lo;
+	dd t = blockReduceDd(acc0);
+	if (gridDim.x == 1) {
+		if (threadIdx.x == 0) { out2[0] = t.hi; out2[1] = t.lo; }
+		return;
 	}
+	if (threadIdx.x == 0) { partials[2 * blockIdx.x] = t.hi; partials[2 * blockIdx.x + 1] = t.lo; }
+	if (!drawLastTicket(ticket)) return;
+	dd m = {0.0, 0.0};
+	for (unsigned int b = threadIdx.x; b < gridDim.x; b += RED_THREADS) { const dd o = { __ldcg(partials + 2 * b), __ldcg(partials + 2 * b + 1) }; ddMerge(m, o); }
+	m = blockReduceDd(m);
+	if (threadIdx.x == 0) { out2[0] = m.hi; out2[1] = m.lo; }
 }
 
-template <bool IS_MAX> __global__ void __launch_bounds__(RED_THREADS) minMaxKernel(const double* __restrict__ x, uint64_t n, double* __restrict__ partials) {
-	const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
-	uint64_t i = blockIdx.x * (uint64_t)RED_THREADS + threadIdx.x;
-	double m = x[i < n ? i : 0];
-	for (; i < n; i += stride) m = IS_MAX ? jmaxD(m, x[i]) : jminD(m, x[i]);
+// out2[0] = min / max with Math.min / Math.max semantics (NaN-propagating, -0.0 < +0.0), out2[1] = 1.0 (this shard holds data)
+template <bool IS_MAX> __device__ __forceinline__ double blockReduceMinMax(double m) {
+	__shared__ double sh[RED_THREADS / 32];
 #pragma unroll
 	for (int d = 16; d > 0; d >>= 1) {
 		const double o = __shfl_down_sync(0xffffffffu, m, d);
 		m = IS_MAX ? jmaxD(m, o) : jminD(m, o);
 	}
-	__shared__ double sh[RED_THREADS / 32];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	__syncthreads();
 	if (lane == 0) sh[warp] = m;
 	__syncthreads();
-	if (threadIdx.x == 0) {
-		double t = sh[0];
-		for (int k = 1; k < RED_THREADS / 32; k++) t = IS_MAX ? jmaxD(t, sh[k]) : jminD(t, sh[k]);
-		partials[blockIdx.x] = t;
+	if (threadIdx.x == 0) { for (int k = 1; k < RED_THREADS / 32; k++) m = IS_MAX ? jmaxD(m, sh[k]) : jminD(m, sh[k]); }
+	return m;
+}
+
+template <bool IS_MAX> __global__ void __launch_bounds__(RED_THREADS) minMaxKernel(const double* __restrict__ x, uint64_t n, double* __restrict__ partials,
+		unsigned int* ticket, double* __restrict__ out2) {
+	const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
+	uint64_t i = blockIdx.x * (uint64_t)RED_THREADS + threadIdx.x;
+	double m = x[i < n ? i : 0];
+	for (; i < n; i += stride) m = IS_MAX ? jmaxD(m, x[i]) : jminD(m, x[i]);
+	m = blockReduceMinMax<IS_MAX>(m);
+	if (gridDim.x == 1) {
+		if (threadIdx.x == 0) { out2[0] = m; out2[1] = 1.0; }
+		return;
+	}
+	if (threadIdx.x == 0) partials[blockIdx.x] = m;
+	if (!drawLastTicket(ticket)) return;
+	double t = __ldcg(partials + (threadIdx.x < gridDim.x ? threadIdx.x : 0));
+	for (unsigned int b = threadIdx.x; b < gridDim.x; b += RED_THREADS) { const double o = __ldcg(partials + b); t = IS_MAX ? jmaxD(t, o) : jminD(t, o); }
+	t = blockReduceMinMax<IS_MAX>(t);
+	if (threadIdx.x == 0) { out2[0] = t; out2[1] = 1.0; }
+}
+
+// merge of the gathered shard results in rank order (one launch, one warp): sums as double-double pairs, min / max with the
+// reference's semantics; shards without data (flag 0) are skipped, so an empty shard never turns a result into NaN.
+// gathered: [world][count] doubles; kind 0: count/2 (hi, lo) pairs -> out[2m], out[2m+1]; kind 1 / 2: (value, flag) -> out[0] = min / max
+__global__ void mergeShardsKernel(const double* __restrict__ gathered, int world, int count, int kind, double* __restrict__ out) {
+	const int m = threadIdx.x;
+	if (kind == 0) {
+		if (2 * m >= count) return;
+		dd t = { gathered[2 * m], gathered[2 * m + 1] };
+		for (int r = 1; r < world; r++) { const dd o = { gathered[(size_t)r * count + 2 * m], gathered[(size_t)r * count + 2 * m + 1] }; ddMerge(t, o); }
+		out[2 * m] = t.hi; out[2 * m + 1] = t.lo;
+	} else if (m == 0) {
+		bool any = false;
+		double t = 0.0;
+		for (int r = 0; r < world; r++) {
+			if (gathered[(size_t)r * count + 1] == 0.0) continue;
+			const double v = gathered[(size_t)r * count];
+			t = any ? (kind == 2 ? jmaxD(t, v) : jminD(t, v)) : v;
+			any = true;
+		}
+		out[0] = any ? t : NAN;
+		out[1] = any ? 1.0 : 0.0;
 	}
 }
 
-// ---- regression moments: all K(K+1)/2 + K sums in ONE pass over the paths (the reference makes 27 passes for K = 6,
-//      MonteCarloConditionalExpectationRegression.java:128-144).  Reads 8 B per stochastic basis function + 8 B for y per path.
+// ---- regression --------------------------------------------------------------------------------------------------------
+// x = pinv(A) b for the symmetric K x K moment matrix: one-sided Jacobi (Hestenes) SVD A = U S V^T, x = V S^+ U^T b with the
+// commons-math3 3.6.1 SingularValueDecomposition solver's cut-off  tol = max(K * s_max * 2^-52, sqrt(2^-1022))  (third-party jar,
+// SURVEY.md §8c).  ONE implementation for the host entry point (fmb_regression_solve_svd) and for the device-resident regression, so
+// both give the same coefficients.  U holds A on entry (row-major, K x K); V, s are work space.
+__host__ __device__ inline void jacobiPinvSolve(int K, double* U, double* V, double* s, const double* b, double* x, double* cond) {
+	for (int i = 0; i < K * K; i++) V[i] = 0.0;
+	for (int i = 0; i < K; i++) V[i * K + i] = 1.0;
+	for (int sweep = 0; sweep < 60; sweep++) {
+		bool rotated = false;
+		for (int p = 0; p < K - 1; p++) for (int q = p + 1; q < K; q++) {
+			double alpha = 0, beta = 0, gamma = 0;
+			for (int i = 0; i < K; i++) {
+				const double up = U[i * K + p], uq = U[i * K + q];
+				alpha += up * up; beta += uq * uq; gamma += up * uq;
+			}
+			if (gamma == 0.0 || fabs(gamma) <= 1e-300) continue;
+			if (fabs(gamma) <= 0x1.0p-53 * sqrt(alpha * beta)) continue;
+			rotated = true;
+			const double zeta = (beta - alpha) / (2.0 * gamma);
+			const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+			const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+			for (int i = 0; i < K; i++) {
+				const double up = U[i * K + p], uq = U[i * K + q];
+				U[i * K + p] = cs * up - sn * uq;
+				U[i * K + q] = sn * up + cs * uq;
+				const double vp = V[i * K + p], vq = V[i * K + q];
+				V[i * K + p] = cs * vp - sn * vq;
+				V[i * K + q] = sn * vp + cs * vq;
+			}
+		}
+		if (!rotated) break;
+	}
+	double smax = 0.0, smin = INFINITY;
+	for (int j = 0; j < K; j++) {
+		double nn = 0;
+		for (int i = 0; i < K; i++) nn += U[i * K + j] * U[i * K + j];
+		s[j] = sqrt(nn);
+		smax = s[j] > smax ? s[j] : smax; smin = s[j] < smin ? s[j] : smin;
+	}
+	if (cond) *cond = smax / smin;
+	const double tolA = (double)K * smax * 0x1.0p-52, tolB = 1.4916681462400413e-154 /* sqrt(2^-1022) */;
+	const double tol = tolA > tolB ? tolA : tolB;
+	for (int k = 0; k < K; k++) x[k] = 0.0;
+	for (int j = 0; j < K; j++) {
+		if (s[j] <= tol) continue;
+		double ub = 0;                              // (u_j . b) / s_j, with u_j = U[:,j] / s_j
+		for (int i = 0; i < K; i++) ub += U[i * K + j] * b[i];
+		const double wgt = ub / (s[j] * s[j]);
+		for (int k = 0; k < K; k++) x[k] += V[k * K + j] * wgt;
+	}
+}
+
 struct BasisArgs {
 	const double* ptr[8];
 	double scalar[8];
 };
 
-template <int K> __global__ void __launch_bounds__(RED_THREADS) momentsKernel(BasisArgs b, const double* __restrict__ y, uint64_t n,
-		double* __restrict__ partials /* [grid][M][2] */) {
+// device-resident result of a fit (one small vector behind a handle): XtX[K*K] (stride K) | Xty[8] | x[8] | cond
+static const int FIT_XTX = 0, FIT_XTY = 64, FIT_X = 72, FIT_COND = 80, FIT_DOUBLES = 96;
+
+struct FitArgs {
+	int world;                 // shards gathered in src ([world][M][2]); 1: the local moments
+	double n;                  // logical number of paths (all shards)
+	const double* cachedFit;   // non-null: XtX of an earlier fit of the same estimator (the reference caches its solver per instance, :125-138)
+	double* fit;               // FIT_DOUBLES doubles
+};
+
+// Called by one whole CTA.  src: moments as (hi, lo) pairs in the order (p <= q pairs row by row, then y*b_p).
+template <int K> __device__ void regressionFinish(const double* __restrict__ src, const BasisArgs& b, const FitArgs& f) {
+	constexpr int M = K * (K + 1) / 2 + K;
+	__shared__ double mean[M];
+	__shared__ double U[K * K], V[K * K], sv[K], rhs[K], xs[K];
+	if (threadIdx.x < M) {
+		const int m = threadIdx.x;
+		dd t = { __ldcg(src + 2 * m), __ldcg(src + 2 * m + 1) };
+		for (int r = 1; r < f.world; r++) { const dd o = { __ldcg(src + ((size_t)r * M + m) * 2), __ldcg(src + ((size_t)r * M + m) * 2 + 1) }; ddMerge(t, o); }
+		mean[m] = (t.hi + t.lo) / f.n;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		int m = 0;
+		for (int p = 0; p < K; p++) for (int q = p; q < K; q++) {
+			double v = mean[m++];
+			// deterministic x deterministic: the reference's mult() stays a scalar and its average is the product itself
+			if (b.ptr[p] == nullptr && b.ptr[q] == nullptr) v = b.scalar[p] * b.scalar[q];
+			if (f.cachedFit) v = f.cachedFit[FIT_XTX + p * K + q];
+			U[p * K + q] = U[q * K + p] = v;
+			f.fit[FIT_XTX + p * K + q] = f.fit[FIT_XTX + q * K + p] = v;
+		}
+		for (int p = 0; p < K; p++) { rhs[p] = mean[m++]; f.fit[FIT_XTY + p] = rhs[p]; }
+		double cond;
+		jacobiPinvSolve(K, U, V, sv, rhs, xs, &cond);
+		for (int p = 0; p < K; p++) f.fit[FIT_X + p] = xs[p];
+		f.fit[FIT_COND] = cond;
+	}
+}
+
+// All K(K+1)/2 + K sums in ONE pass over the paths (the reference makes 27 passes for K = 6, MonteCarloConditionalExpectationRegression
+// .java:128-144).  Reads 8 B per stochastic basis function + 8 B for y per path.  The last CTA merges the per-CTA partials and
+//   FINISH 0: writes the local moments ((hi, lo) pairs) to momOut (mapped host memory, or the communicator's send buffer),
+//   FINISH 1: (single GPU) goes straight on to the solve: no second launch, nothing returns to the host.
+template <int K, int FINISH> __global__ void __launch_bounds__(RED_THREADS) momentsKernel(BasisArgs b, const double* __restrict__ y, uint64_t n,
+		double* __restrict__ partials /* [grid][M][2] */, unsigned int* ticket, double* __restrict__ momOut, FitArgs f) {
 	constexpr int M = K * (K + 1) / 2 + K;
 	dd acc[M];
 #pragma unroll
@@ -162,16 +324,48 @@ template <int K> __global__ void __launch_bounds__(RED_THREADS) momentsKernel(Ba
 		partials[((size_t)blockIdx.x * M + threadIdx.x) * 2] = t.hi;
 		partials[((size_t)blockIdx.x * M + threadIdx.x) * 2 + 1] = t.lo;
 	}
+	if (!drawLastTicket(ticket)) return;
+	// merge over the CTAs: S lanes per moment take the CTAs s, s+S, ... in order, then a shuffle tree over the S lanes (fixed order)
+	constexpr int S = (M * 8 <= RED_THREADS) ? 8 : ((M * 4 <= RED_THREADS) ? 4 : 2);
+	const int m = threadIdx.x / S, sl = threadIdx.x % S;
+	dd t = {0.0, 0.0};
+	if (m < M) {
+		for (unsigned int blk = sl; blk < gridDim.x; blk += S) {
+			const dd o = { __ldcg(partials + ((size_t)blk * M + m) * 2), __ldcg(partials + ((size_t)blk * M + m) * 2 + 1) };
+			ddMerge(t, o);
+		}
+	}
+#pragma unroll
+	for (int d = S / 2; d > 0; d >>= 1) {
+		dd o;
+		o.hi = __shfl_down_sync(0xffffffffu, t.hi, d, S);
+		o.lo = __shfl_down_sync(0xffffffffu, t.lo, d, S);
+		ddMerge(t, o);
+	}
+	if (m < M && sl == 0) { momOut[2 * m] = t.hi; momOut[2 * m + 1] = t.lo; }
+	if (FINISH == 1) {
+		__threadfence_block();
+		__syncthreads();
+		regressionFinish<K>(momOut, b, f);
+	}
 }
 
-// conditional expectation: b_0*x_0, then + b_i*x_i in order (…Regression.java:103-107); 8 B per stochastic basis read, 8 B written
-struct PredictCoef { double x[8]; };
-template <int K> __global__ void __launch_bounds__(256) predictKernelV(BasisArgs b, PredictCoef c, double* __restrict__ out, uint64_t n) {
+// after the all-gather of the shards' moments: merge in rank order + solve (one CTA)
+template <int K> __global__ void __launch_bounds__(64) regressionSolveKernel(const double* __restrict__ gathered, BasisArgs b, FitArgs f) {
+	regressionFinish<K>(gathered, b, f);
+}
+
+// conditional expectation: b_0*x_0, then + b_i*x_i in order (…Regression.java:103-107); 8 B per stochastic basis read, 8 B written.
+// The coefficients come from the device-resident fit (uniform loads): the host never sees them on this path.
+template <int K> __global__ void __launch_bounds__(256) predictKernelV(BasisArgs b, const double* __restrict__ coef, double* __restrict__ out, uint64_t n) {
+	double c[K];
+#pragma unroll
+	for (int k = 0; k < K; k++) c[k] = __ldcg(coef + k);
 	const uint64_t stride = (uint64_t)gridDim.x * 256;
 	for (uint64_t i = blockIdx.x * (uint64_t)256 + threadIdx.x; i < n; i += stride) {
-		double ce = (b.ptr[0] ? b.ptr[0][i] : b.scalar[0]) * c.x[0];
+		double ce = (b.ptr[0] ? b.ptr[0][i] : b.scalar[0]) * c[0];
 #pragma unroll
-		for (int k = 1; k < K; k++) ce = ce + (b.ptr[k] ? b.ptr[k][i] : b.scalar[k]) * c.x[k];
+		for (int k = 1; k < K; k++) ce = ce + (b.ptr[k] ? b.ptr[k][i] : b.scalar[k]) * c[k];
 		out[i] = ce;
 	}
 }
@@ -190,11 +384,85 @@ __global__ void countLeKernel(const double* __restrict__ sorted, uint64_t n, con
 
 static int reduceGrid() { return ctx().smCount * 4; }
 
-template <int K> static void launchMoments(const BasisArgs& b, const double* y, uint64_t n, double* partials, int grid, cudaStream_t s) {
-	momentsKernel<K><<<grid, RED_THREADS, 0, s>>>(b, y, n, partials);
+int commAllGather(int count);                      // fmb_comm.cu
+
+template <int K> static void launchMoments(int finish, const BasisArgs& b, const double* y, uint64_t n, double* partials, unsigned int* ticket, double* momOut,
+		const FitArgs& f, int grid, cudaStream_t s) {
+	if (finish) momentsKernel<K, 1><<<grid, RED_THREADS, 0, s>>>(b, y, n, partials, ticket, momOut, f);
+	else momentsKernel<K, 0><<<grid, RED_THREADS, 0, s>>>(b, y, n, partials, ticket, momOut, f);
 }
-template <int K> static void launchPredict(const BasisArgs& b, const PredictCoef& c, double* out, uint64_t n, int grid, cudaStream_t s) {
-	predictKernelV<K><<<grid, 256, 0, s>>>(b, c, out, n);
+template <int K> static void launchSolve(const double* gathered, const BasisArgs& b, const FitArgs& f, cudaStream_t s) {
+	regressionSolveKernel<K><<<1, 64, 0, s>>>(gathered, b, f);
+}
+template <int K> static void launchPredict(const BasisArgs& b, const double* coef, double* out, uint64_t n, int grid, cudaStream_t s) {
+	predictKernelV<K><<<grid, 256, 0, s>>>(b, coef, out, n);
+}
+#define FMB_K_SWITCH(K, CALL) \
+	switch (K) { case 1: CALL(1); break; case 2: CALL(2); break; case 3: CALL(3); break; case 4: CALL(4); break; \
+	             case 5: CALL(5); break; case 6: CALL(6); break; case 7: CALL(7); break; default: CALL(8); break; }
+
+static int fillBasis(int K, const fmb_handle* basis, const double* basis_scalar, uint64_t* n, bool* any, BasisArgs* b) {
+	if (K < 1 || K > 8) { setError("regression kernels support 1..8 basis functions (got %d)", K); return FMB_EUNSUPPORTED; }
+	for (int k = 0; k < K; k++) {
+		b->ptr[k] = nullptr;
+		b->scalar[k] = basis_scalar ? basis_scalar[k] : 0.0;
+		if (basis[k] == 0) continue;
+		Vec* v;
+		FMB_TRY(lookup(basis[k], &v));
+		if (*any && v->n != *n) { setError("basis function sizes differ"); return FMB_EINVAL; }
+		*n = v->n; *any = true;
+		b->ptr[k] = v->ptr;
+	}
+	for (int k = K; k < 8; k++) { b->ptr[k] = nullptr; b->scalar[k] = 0.0; }
+	return FMB_OK;
+}
+
+// enqueue: local moments (+ all-gather + merge) + solve -> fit (device).  Caller holds scratchMu.
+static int enqueueFit(int K, const BasisArgs& b, const double* y, uint64_t nLocal, double nGlobal, const double* cachedFit, double* fit) {
+	Context& c = ctx();
+	const int M = K * (K + 1) / 2 + K;
+	const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * 2, (nLocal + RED_THREADS - 1) / RED_THREADS));
+	FMB_TRY(ensureScratch(0, (size_t)(grid * M * 2 + COMM_MAX_DOUBLES) * sizeof(double)));
+	double* dpart = (double*)c.scratch;
+	double* momLocal = c.comm.active ? c.comm.sendBuf : dpart + (size_t)grid * M * 2;
+	FitArgs f;
+	f.world = 1; f.n = nGlobal; f.cachedFit = cachedFit; f.fit = fit;
+	const int finish = c.comm.active ? 0 : 1;
+	if (nLocal == 0) {
+		// an empty shard contributes zero moments (it still takes part in the exchange)
+		FMB_CUDA(cudaMemsetAsync(momLocal, 0, (size_t)M * 2 * sizeof(double), c.stream));
+		if (finish) { setError("regression on an empty vector"); return FMB_EINVAL; }
+	} else {
+#define CALL(KV) launchMoments<KV>(finish, b, y, nLocal, dpart, c.ticket, momLocal, f, grid, c.stream)
+		FMB_K_SWITCH(K, CALL)
+#undef CALL
+		countLaunch();
+		FMB_CUDA(cudaGetLastError());
+	}
+	if (c.comm.active) {
+		FMB_TRY(commAllGather(2 * M));
+		f.world = c.comm.world;
+#define CALL(KV) launchSolve<KV>(c.comm.gatherBuf, b, f, c.stream)
+		FMB_K_SWITCH(K, CALL)
+#undef CALL
+		countLaunch();
+		FMB_CUDA(cudaGetLastError());
+	}
+	return FMB_OK;
+}
+
+static int enqueuePredict(int K, const BasisArgs& b, const double* coef, uint64_t n, fmb_handle* out) {
+	Context& c = ctx();
+	double* dst;
+	FMB_TRY(newVec(n, out, &dst));
+	if (n == 0) return FMB_OK;
+	const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * 8, (n + 255) / 256));
+#define CALL(KV) launchPredict<KV>(b, coef, dst, n, grid, c.stream)
+	FMB_K_SWITCH(K, CALL)
+#undef CALL
+	countLaunch();
+	FMB_CUDA(cudaGetLastError());
+	return FMB_OK;
 }
 
 } // namespace fmb
@@ -203,8 +471,11 @@ using namespace fmb;
 
 extern "C" {
 
+// With a communicator (fmb_comm_init) the result covers ALL shards: local kernel -> all-gather on the compute stream -> rank-ordered
+// merge kernel -> mapped host memory; without one it is the local result, written by the finalising CTA straight to mapped host memory.
 int fmb_rv_reduce(int op, fmb_handle x, fmb_handle w, double a, double* out2) {
 	FMB_TRY(requireInit());
+	PinScope pins;
 	if (!out2) return FMB_EINVAL;
 	if (op < 0 || op > FMB_R_MAX) { setError("unknown reduction %d", op); return FMB_EINVAL; }
 	Context& c = ctx();
@@ -216,192 +487,184 @@ int fmb_rv_reduce(int op, fmb_handle x, fmb_handle w, double a, double* out2) {
 		if (w == 0) { setError("reduction %d needs a weight vector", op); return FMB_EINVAL; }
 		FMB_TRY(lookupPtr(w, n, &wp));
 	}
+	const bool isMinMax = op >= FMB_R_MIN;
 	out2[0] = 0.0; out2[1] = 0.0;
-	if (n == 0) { out2[0] = (op >= FMB_R_MIN) ? NAN : 0.0; return FMB_OK; }
-	int grid = (int)std::min<uint64_t>((uint64_t)reduceGrid(), (n + RED_THREADS - 1) / RED_THREADS);
+	if (n == 0 && !c.comm.active) { out2[0] = isMinMax ? NAN : 0.0; return FMB_OK; }
+	const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)reduceGrid(), (n + RED_THREADS - 1) / RED_THREADS));
 	std::lock_guard<std::mutex> lk(c.scratchMu);
-	FMB_TRY(ensureScratch((size_t)grid * 2 * sizeof(double), (size_t)grid * 2 * sizeof(double)));
+	FMB_TRY(ensureScratch(0, (size_t)grid * 2 * sizeof(double)));
 	double* dpart = (double*)c.scratch;
-	double* hpart = (double*)c.pinned;
-	switch (op) {
-	case FMB_R_SUM: sumKernel<FMB_R_SUM><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, wp, a, n, dpart); break;
-	case FMB_R_SUM_PRODUCT: sumKernel<FMB_R_SUM_PRODUCT><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, wp, a, n, dpart); break;
-	case FMB_R_CENTERED_M2: sumKernel<FMB_R_CENTERED_M2><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, wp, a, n, dpart); break;
-	case FMB_R_CENTERED_M2_W: sumKernel<FMB_R_CENTERED_M2_W><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, wp, a, n, dpart); break;
-	case FMB_R_MIN: minMaxKernel<false><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, n, dpart); break;
-	case FMB_R_MAX: minMaxKernel<true><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, n, dpart); break;
-	}
-	countLaunch();
-	FMB_CUDA(cudaGetLastError());
-	const size_t cnt = (op >= FMB_R_MIN) ? grid : 2 * (size_t)grid;
-	FMB_CUDA(cudaMemcpyAsync(hpart, dpart, cnt * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-	FMB_CUDA(cudaStreamSynchronize(c.stream));
-	if (op >= FMB_R_MIN) {
-		double m = hpart[0];
-		for (int b = 1; b < grid; b++) {
-			const double v = hpart[b];
-			if (m != m) break;
-			if (v != v) { m = v; break; }
-			if (op == FMB_R_MIN) { if (v < m || (v == 0.0 && m == 0.0 && std::signbit(v))) m = v; }
-			else { if (v > m || (v == 0.0 && m == 0.0 && !std::signbit(v))) m = v; }
-		}
-		out2[0] = m;
+	double* dst = c.comm.active ? c.comm.sendBuf : c.hostResultDev;
+	if (n == 0) {
+		FMB_CUDA(cudaMemsetAsync(dst, 0, 2 * sizeof(double), c.stream));          // (0, 0): a zero sum / "no data" for min and max
 	} else {
-		dd t = { hpart[0], hpart[1] };
-		for (int b = 1; b < grid; b++) { dd o = { hpart[2 * b], hpart[2 * b + 1] }; ddMerge(t, o); }
-		out2[0] = t.hi; out2[1] = t.lo;
+		switch (op) {
+		case FMB_R_SUM: sumKernel<FMB_R_SUM><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, wp, a, n, dpart, c.ticket, dst); break;
+		case FMB_R_SUM_PRODUCT: sumKernel<FMB_R_SUM_PRODUCT><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, wp, a, n, dpart, c.ticket, dst); break;
+		case FMB_R_CENTERED_M2: sumKernel<FMB_R_CENTERED_M2><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, wp, a, n, dpart, c.ticket, dst); break;
+		case FMB_R_CENTERED_M2_W: sumKernel<FMB_R_CENTERED_M2_W><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, wp, a, n, dpart, c.ticket, dst); break;
+		case FMB_R_MIN: minMaxKernel<false><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, n, dpart, c.ticket, dst); break;
+		case FMB_R_MAX: minMaxKernel<true><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, n, dpart, c.ticket, dst); break;
+		}
+		countLaunch();
+		FMB_CUDA(cudaGetLastError());
 	}
+	if (c.comm.active) {
+		FMB_TRY(commAllGather(2));
+		mergeShardsKernel<<<1, 32, 0, c.stream>>>(c.comm.gatherBuf, c.comm.world, 2, isMinMax ? (op == FMB_R_MIN ? 1 : 2) : 0, c.hostResultDev);
+		countLaunch();
+		FMB_CUDA(cudaGetLastError());
+	}
+	FMB_CUDA(cudaStreamSynchronize(c.stream));
+	out2[0] = c.hostResult[0];
+	out2[1] = isMinMax ? 0.0 : c.hostResult[1];
 	return FMB_OK;
 }
 
-static int fillBasis(int K, const fmb_handle* basis, const double* basis_scalar, uint64_t* n, BasisArgs* b) {
-	if (K < 1 || K > 8) { setError("regression kernels support 1..8 basis functions (got %d)", K); return FMB_EUNSUPPORTED; }
-	bool any = false;
-	for (int k = 0; k < K; k++) {
-		b->ptr[k] = nullptr;
-		b->scalar[k] = basis_scalar ? basis_scalar[k] : 0.0;
-		if (basis[k] == 0) continue;
-		Vec* v;
-		FMB_TRY(lookup(basis[k], &v));
-		if (any && v->n != *n) { setError("basis function sizes differ"); return FMB_EINVAL; }
-		*n = v->n; any = true;
-		b->ptr[k] = v->ptr;
-	}
-	for (int k = K; k < 8; k++) { b->ptr[k] = nullptr; b->scalar[k] = 0.0; }
-	return FMB_OK;
-}
-
+// LOCAL moment sums as double-double pairs on the host (the caller exchanges them between shards itself and divides by n): the
+// host-resident variant of the regression, kept for hosts that exchange partials outside the library.
 int fmb_regression_moments(int K, const fmb_handle* basis, const double* basis_scalar, fmb_handle y,
                            double* XtX_hi, double* XtX_lo, double* Xty_hi, double* Xty_lo) {
 	FMB_TRY(requireInit());
+	PinScope pins;
 	if (!basis || !XtX_hi || !XtX_lo || !Xty_hi || !Xty_lo) return FMB_EINVAL;
 	Context& c = ctx();
 	BasisArgs b;
 	Vec* vy;
 	FMB_TRY(lookup(y, &vy));
 	uint64_t n = vy->n;
-	FMB_TRY(fillBasis(K, basis, basis_scalar, &n, &b));
+	bool any = false;
+	FMB_TRY(fillBasis(K, basis, basis_scalar, &n, &any, &b));
 	if (n != vy->n) { setError("basis functions and dependents differ in size"); return FMB_EINVAL; }
 	const int M = K * (K + 1) / 2 + K;
-	int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * 2, (n + RED_THREADS - 1) / RED_THREADS));
 	std::lock_guard<std::mutex> lk(c.scratchMu);
-	const size_t bytes = (size_t)grid * M * 2 * sizeof(double);
-	FMB_TRY(ensureScratch(bytes, bytes));
-	double* dpart = (double*)c.scratch;
-	double* hpart = (double*)c.pinned;
-	switch (K) {
-	case 1: launchMoments<1>(b, vy->ptr, n, dpart, grid, c.stream); break;
-	case 2: launchMoments<2>(b, vy->ptr, n, dpart, grid, c.stream); break;
-	case 3: launchMoments<3>(b, vy->ptr, n, dpart, grid, c.stream); break;
-	case 4: launchMoments<4>(b, vy->ptr, n, dpart, grid, c.stream); break;
-	case 5: launchMoments<5>(b, vy->ptr, n, dpart, grid, c.stream); break;
-	case 6: launchMoments<6>(b, vy->ptr, n, dpart, grid, c.stream); break;
-	case 7: launchMoments<7>(b, vy->ptr, n, dpart, grid, c.stream); break;
-	case 8: launchMoments<8>(b, vy->ptr, n, dpart, grid, c.stream); break;
+	if (n == 0) {
+		for (int i = 0; i < 2 * M; i++) c.hostResult[i] = 0.0;
+	} else {
+		const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * 2, (n + RED_THREADS - 1) / RED_THREADS));
+		FMB_TRY(ensureScratch(0, (size_t)grid * M * 2 * sizeof(double)));
+		FitArgs f = { 1, 0.0, nullptr, nullptr };
+#define CALL(KV) launchMoments<KV>(0, b, vy->ptr, n, (double*)c.scratch, c.ticket, c.hostResultDev, f, grid, c.stream)
+		FMB_K_SWITCH(K, CALL)
+#undef CALL
+		countLaunch();
+		FMB_CUDA(cudaGetLastError());
+		FMB_CUDA(cudaStreamSynchronize(c.stream));
 	}
-	countLaunch();
-	FMB_CUDA(cudaGetLastError());
-	FMB_CUDA(cudaMemcpyAsync(hpart, dpart, bytes, cudaMemcpyDeviceToHost, c.stream));
-	FMB_CUDA(cudaStreamSynchronize(c.stream));
-	std::vector<dd> tot(M);
-	for (int m = 0; m < M; m++) tot[m] = dd{ hpart[2 * m], hpart[2 * m + 1] };
-	for (int blk = 1; blk < grid; blk++)
-		for (int m = 0; m < M; m++) { dd o = { hpart[((size_t)blk * M + m) * 2], hpart[((size_t)blk * M + m) * 2 + 1] }; ddMerge(tot[m], o); }
+	const double* tot = c.hostResult;
 	int m = 0;
 	for (int p = 0; p < K; p++) for (int q = p; q < K; q++) {
-		XtX_hi[p * K + q] = XtX_hi[q * K + p] = tot[m].hi;
-		XtX_lo[p * K + q] = XtX_lo[q * K + p] = tot[m].lo;
+		XtX_hi[p * K + q] = XtX_hi[q * K + p] = tot[2 * m];
+		XtX_lo[p * K + q] = XtX_lo[q * K + p] = tot[2 * m + 1];
 		m++;
 	}
-	for (int p = 0; p < K; p++) { Xty_hi[p] = tot[m].hi; Xty_lo[p] = tot[m].lo; m++; }
+	for (int p = 0; p < K; p++) { Xty_hi[p] = tot[2 * m]; Xty_lo[p] = tot[2 * m + 1]; m++; }
 	return FMB_OK;
 }
 
-// One-sided Jacobi (Hestenes) SVD of the K x K matrix A = U S V^T; x = V S^+ U^T b with the commons-math3 3.6.1
-// SingularValueDecomposition solver's cut-off  tol = max(K * s_max * 2^-52, sqrt(2^-1022))  (third-party jar).
 int fmb_regression_solve_svd(int K, const double* A, const double* b, double* x, double* cond) {
 	if (K < 1 || !A || !b || !x) { setError("solve_svd: bad argument"); return FMB_EINVAL; }
-	std::vector<double> U(A, A + (size_t)K * K), V((size_t)K * K, 0.0);
-	for (int i = 0; i < K; i++) V[(size_t)i * K + i] = 1.0;
-	for (int sweep = 0; sweep < 60; sweep++) {
-		bool rotated = false;
-		for (int p = 0; p < K - 1; p++) for (int q = p + 1; q < K; q++) {
-			double alpha = 0, beta = 0, gamma = 0;
-			for (int i = 0; i < K; i++) {
-				const double up = U[(size_t)i * K + p], uq = U[(size_t)i * K + q];
-				alpha += up * up; beta += uq * uq; gamma += up * uq;
-			}
-			if (gamma == 0.0 || std::fabs(gamma) <= 1e-300) continue;
-			if (std::fabs(gamma) <= 0x1.0p-53 * std::sqrt(alpha * beta)) continue;
-			rotated = true;
-			const double zeta = (beta - alpha) / (2.0 * gamma);
-			const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
-			const double cs = 1.0 / std::sqrt(1.0 + t * t), sn = cs * t;
-			for (int i = 0; i < K; i++) {
-				const double up = U[(size_t)i * K + p], uq = U[(size_t)i * K + q];
-				U[(size_t)i * K + p] = cs * up - sn * uq;
-				U[(size_t)i * K + q] = sn * up + cs * uq;
-				const double vp = V[(size_t)i * K + p], vq = V[(size_t)i * K + q];
-				V[(size_t)i * K + p] = cs * vp - sn * vq;
-				V[(size_t)i * K + q] = sn * vp + cs * vq;
-			}
-		}
-		if (!rotated) break;
-	}
-	std::vector<double> s(K);
-	double smax = 0.0, smin = INFINITY;
-	for (int j = 0; j < K; j++) {
-		double nn = 0;
-		for (int i = 0; i < K; i++) nn += U[(size_t)i * K + j] * U[(size_t)i * K + j];
-		s[j] = std::sqrt(nn);
-		smax = std::max(smax, s[j]); smin = std::min(smin, s[j]);
-	}
-	if (cond) *cond = smax / smin;
-	const double tol = std::max((double)K * smax * 0x1.0p-52, std::sqrt(0x1.0p-1022));
-	for (int k = 0; k < K; k++) x[k] = 0.0;
-	for (int j = 0; j < K; j++) {
-		if (s[j] <= tol) continue;
-		double ub = 0;                              // (u_j . b) / s_j, with u_j = U[:,j] / s_j
-		for (int i = 0; i < K; i++) ub += U[(size_t)i * K + j] * b[i];
-		const double wgt = ub / (s[j] * s[j]);
-		for (int k = 0; k < K; k++) x[k] += V[(size_t)k * K + j] * wgt;
-	}
+	std::vector<double> U(A, A + (size_t)K * K), V((size_t)K * K, 0.0), s(K);
+	jacobiPinvSolve(K, U.data(), V.data(), s.data(), b, x, cond);
 	return FMB_OK;
 }
 
 int fmb_regression_predict(int K, const fmb_handle* basis, const double* basis_scalar, const double* x, fmb_handle* out) {
 	FMB_TRY(requireInit());
+	PinScope pins;
 	if (!basis || !x || !out) return FMB_EINVAL;
 	Context& c = ctx();
 	BasisArgs b;
 	uint64_t n = 0;
-	FMB_TRY(fillBasis(K, basis, basis_scalar, &n, &b));
 	bool any = false;
-	for (int k = 0; k < K; k++) any = any || b.ptr[k];
+	FMB_TRY(fillBasis(K, basis, basis_scalar, &n, &any, &b));
 	if (!any) { setError("predict: all basis functions deterministic; stays on the host"); return FMB_EINVAL; }
-	PredictCoef pc;
-	for (int k = 0; k < 8; k++) pc.x[k] = k < K ? x[k] : 0.0;
-	double* dst;
-	FMB_TRY(newVec(n, out, &dst));
-	if (n == 0) return FMB_OK;
-	const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * 8, (n + 255) / 256));
-	switch (K) {
-	case 1: launchPredict<1>(b, pc, dst, n, grid, c.stream); break;
-	case 2: launchPredict<2>(b, pc, dst, n, grid, c.stream); break;
-	case 3: launchPredict<3>(b, pc, dst, n, grid, c.stream); break;
-	case 4: launchPredict<4>(b, pc, dst, n, grid, c.stream); break;
-	case 5: launchPredict<5>(b, pc, dst, n, grid, c.stream); break;
-	case 6: launchPredict<6>(b, pc, dst, n, grid, c.stream); break;
-	case 7: launchPredict<7>(b, pc, dst, n, grid, c.stream); break;
-	case 8: launchPredict<8>(b, pc, dst, n, grid, c.stream); break;
+	// the coefficients travel through a small pool block (stream-ordered: the block is reused only after the kernel that reads it)
+	void* coef;
+	FMB_TRY(poolAlloc(8 * sizeof(double), &coef));
+	std::lock_guard<std::mutex> lk(c.scratchMu);
+	int rc = ensureScratch(8 * sizeof(double), 0);
+	if (rc == FMB_OK) {
+		double* h = (double*)c.pinned;
+		for (int k = 0; k < 8; k++) h[k] = k < K ? x[k] : 0.0;
+		cudaError_t e = cudaMemcpyAsync(coef, h, 8 * sizeof(double), cudaMemcpyHostToDevice, c.stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);          // the pinned staging buffer is shared
+		if (e != cudaSuccess) { setError("predict: %s", cudaGetErrorString(e)); rc = FMB_ECUDA; }
 	}
-	countLaunch();
-	FMB_CUDA(cudaGetLastError());
+	if (rc == FMB_OK) rc = enqueuePredict(K, b, (const double*)coef, n, out);
+	poolFree(coef, 8 * sizeof(double));
+	return rc;
+}
+
+// ---- device-resident regression (no host round trip): MonteCarloConditionalExpectationRegression.java:97-150 -----------------
+int fmb_regression_fit(int K, const fmb_handle* basis, const double* basis_scalar, fmb_handle y, uint64_t n_global, fmb_handle cached_fit,
+                       fmb_handle* fit) {
+	FMB_TRY(requireInit());
+	PinScope pins;
+	if (!basis || !fit) return FMB_EINVAL;
+	Context& c = ctx();
+	BasisArgs b;
+	Vec* vy;
+	FMB_TRY(lookup(y, &vy));
+	uint64_t n = vy->n;
+	bool any = false;
+	FMB_TRY(fillBasis(K, basis, basis_scalar, &n, &any, &b));
+	if (n != vy->n) { setError("basis functions and dependents differ in size"); return FMB_EINVAL; }
+	if (n_global == 0) n_global = n;
+	const double* cachedPtr = nullptr;
+	if (cached_fit) FMB_TRY(lookupPtr(cached_fit, FIT_DOUBLES, &cachedPtr));
+	double* fitPtr;
+	FMB_TRY(newVec(FIT_DOUBLES, fit, &fitPtr));
+	std::lock_guard<std::mutex> lk(c.scratchMu);
+	const int rc = enqueueFit(K, b, vy->ptr, n, (double)n_global, cachedPtr, fitPtr);
+	if (rc != FMB_OK) { releaseRef(*fit); *fit = 0; }
+	return rc;
+}
+
+int fmb_regression_fit_get(fmb_handle fit, int K, double* XtX, double* Xty, double* x, double* cond) {
+	FMB_TRY(requireInit());
+	PinScope pins;
+	if (K < 1 || K > 8) return FMB_EINVAL;
+	const double* p;
+	FMB_TRY(lookupPtr(fit, FIT_DOUBLES, &p));
+	double h[FIT_DOUBLES];
+	FMB_CUDA(cudaMemcpyAsync(h, p, sizeof(h), cudaMemcpyDeviceToHost, ctx().stream));
+	FMB_CUDA(cudaStreamSynchronize(ctx().stream));
+	if (XtX) for (int i = 0; i < K * K; i++) XtX[i] = h[FIT_XTX + i];
+	if (Xty) for (int i = 0; i < K; i++) Xty[i] = h[FIT_XTY + i];
+	if (x) for (int i = 0; i < K; i++) x[i] = h[FIT_X + i];
+	if (cond) *cond = h[FIT_COND];
 	return FMB_OK;
+}
+
+int fmb_regression_predict_fit(int K, const fmb_handle* basis, const double* basis_scalar, fmb_handle fit, fmb_handle* out) {
+	FMB_TRY(requireInit());
+	PinScope pins;
+	if (!basis || !out) return FMB_EINVAL;
+	BasisArgs b;
+	uint64_t n = 0;
+	bool any = false;
+	FMB_TRY(fillBasis(K, basis, basis_scalar, &n, &any, &b));
+	if (!any) { setError("predict: all basis functions deterministic; stays on the host"); return FMB_EINVAL; }
+	const double* p;
+	FMB_TRY(lookupPtr(fit, FIT_DOUBLES, &p));
+	return enqueuePredict(K, b, p + FIT_X, n, out);
+}
+
+int fmb_regression_conditional_expectation(int K, const fmb_handle* basis, const double* basis_scalar, fmb_handle y, uint64_t n_global,
+                                           fmb_handle cached_fit, int Kp, const fmb_handle* basis_pred, const double* basis_pred_scalar,
+                                           fmb_handle* fit, fmb_handle* out) {
+	if (!fit || !out) return FMB_EINVAL;
+	if (Kp != K) { setError("conditional_expectation: %d estimator and %d predictor basis functions", K, Kp); return FMB_EINVAL; }
+	FMB_TRY(fmb_regression_fit(K, basis, basis_scalar, y, n_global, cached_fit, fit));
+	const int rc = fmb_regression_predict_fit(Kp, basis_pred ? basis_pred : basis, basis_pred ? basis_pred_scalar : basis_scalar, *fit, out);
+	if (rc != FMB_OK) { releaseRef(*fit); *fit = 0; }
+	return rc;
 }
 
 int fmb_rv_sorted(fmb_handle x, fmb_handle* out) {
 	FMB_TRY(requireInit());
+	PinScope pins;
 	if (!out) return FMB_EINVAL;
 	Context& c = ctx();
 	Vec* vx;
@@ -424,6 +687,7 @@ int fmb_rv_sorted(fmb_handle x, fmb_handle* out) {
 
 int fmb_rv_count_le(fmb_handle sorted, const double* pts, int npts, uint64_t* counts) {
 	FMB_TRY(requireInit());
+	PinScope pins;
 	if (npts < 0 || (npts && (!pts || !counts))) return FMB_EINVAL;
 	if (npts == 0) return FMB_OK;
 	Context& c = ctx();

@@ -248,6 +248,14 @@ class LIBORMarketModelFromCovarianceModel:
             self._tables = self.covarianceModel.getFactorLoadingTable()
         return self._tables
 
+    def getDiscountFactorsFromForwardCurve(self):
+        """DiscountCurveFromForwardCurve(forwardRateCurve).getDiscountFactor(T_i) on the tenor grid (:130-142): running product of
+        1 / (1 + L_i(0) * (T_{i+1} - T_i)), starting from 1."""
+        df = [1.0]
+        for i in range(self.tenor.getNumberOfTimeSteps()):
+            df.append(df[-1] / (1.0 + float(self.L0[i]) * self.tenor.getTimeStep(i)))
+        return df
+
     def getInitialState(self, process):                      # :1080-1093
         c = self.getRandomVariableForConstant
         if self.stateSpace == self.LOGNORMAL:
@@ -261,7 +269,9 @@ class LIBORMarketModelFromCovarianceModel:
         return first
 
     def _sim_index(self, process, time):
-        ti = process.getTimeIndex(time)
+        # row of the covariance model's tables for a simulation time: ITS time discretization (AbstractLIBORCovarianceModel.java:70-76)
+        td = getattr(self.covarianceModel, "td", None)
+        ti = td.getTimeIndex(time) if td is not None else process.getTimeIndex(time)
         return ti if ti >= 0 else -ti - 2
 
     def getFactorLoading(self, process, timeIndex, componentIndex, realizationAtTimeIndex):
@@ -314,6 +324,25 @@ class LIBORMarketModelFromCovarianceModel:
         td = process.getTimeDiscretization()
         T, N = td.getNumberOfTimeSteps(), self.getNumberOfComponents()
         fl, var = self._tables_for(process)
+        fl, var = np.asarray(fl, dtype=np.float64), np.asarray(var, dtype=np.float64)
+        F = process.getNumberOfFactors()
+        if fl.ndim != 3 or fl.shape[1] != N or fl.shape[2] != F or var.shape != fl.shape[:2]:
+            return None                                      # driver / covariance model disagree on factors or components: generic loop (it raises or handles it per call like the reference)
+        # the covariance model has its own time discretization: row of process step t = its index of the step's start time
+        # (AbstractLIBORCovarianceModel.java:70-76: getTimeIndex(time), negative -> |index| - 2)
+        ctd = getattr(self.covarianceModel, "td", None)
+        if ctd is not None and not (ctd.getNumberOfTimeSteps() == T and all(ctd.getTime(t) == td.getTime(t) for t in range(T))):
+            rows = []
+            for t in range(T):
+                ci = ctd.getTimeIndex(td.getTime(t))
+                if ci < 0:
+                    ci = -ci - 2
+                if ci < 0 or ci >= fl.shape[0]:
+                    return None
+                rows.append(ci)
+            fl, var = fl[rows], var[rows]
+        elif fl.shape[0] != T:
+            return None
         y0 = [s.doubleValue() for s in self.getInitialState(process)]
         x0 = []
         for y in y0:

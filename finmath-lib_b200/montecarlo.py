@@ -341,6 +341,10 @@ class EulerSchemeFromProcessModel:
     def _precalculate(self):
         self._weights = self.stochasticDriver.getRandomVariableForConstant(1.0 / self.getNumberOfPaths())    # :184
         spec = None if self.forceGeneric else getattr(self.model, "getFusedSpecification", lambda p: None)(self)
+        if spec is not None and spec["kernel"] in ("heston", "hull_white") and self.stochasticDriver.getNumberOfFactors() != 2:
+            # the fused kernels of these two models read exactly two increments per step; any other driver runs the reference's
+            # generic recipe (addSumProduct over whatever factor loadings the model returns)
+            spec = None
         if spec is not None and isinstance(self.stochasticDriver, BrownianMotionCuda):
             self._precalculate_fused(spec)
             self.usedFusedKernel = spec["kernel"]
@@ -418,16 +422,23 @@ class EulerSchemeFromProcessModel:
 
 
 class MonteCarloConditionalExpectationRegression:
-    """Least-squares conditional expectation.  XtX and Xty are accumulated in ONE fused pass (fmb_regression_moments)
-    instead of K(K+1)/2 + K multiply-and-reduce passes; shards exchange the 27 double-double moments in one message."""
+    """Least-squares conditional expectation.  XtX and Xty are accumulated in ONE fused pass instead of K(K+1)/2 + K multiply-and-reduce
+    passes.  Default path (single GPU, or shards with the library's own communicator): everything stays on the device —
+    fmb_regression_conditional_expectation queues moments -> (all-gather of the shards' moments) -> K x K solve -> prediction on the
+    compute stream and returns at once, so a backward induction never waits for an exercise date.  The coefficients are downloaded
+    only when somebody asks for them (getLinearRegressionParameters / lastParameters).  With host-side exchange of the partials
+    (FMB_TINY_COLLECTIVES=shm|torch) the moments come back to the host, are merged across shards and solved there."""
 
     def __init__(self, basisFunctionsEstimator, basisFunctionsPredictor=None):
         est = [b for b in basisFunctionsEstimator if b is not None]            # :79-95 drops nulls
         pre = est if basisFunctionsPredictor is None else [b for b in basisFunctionsPredictor if b is not None]
         self.basisFunctionsEstimator, self.basisFunctionsPredictor = est, pre
         self._XTX = None
-        self.lastConditionNumber = None
-        self.lastParameters = None
+        self._cachedFit = None                               # device-resident first fit: its XtX is reused (the solver is cached per instance, :125-138)
+        self._lastFit = None
+        self._lastK = 0
+        self._lastParameters = None
+        self._lastConditionNumber = None
 
     @staticmethod
     def _as_cuda(rv, shard):
@@ -437,15 +448,57 @@ class MonteCarloConditionalExpectationRegression:
             return RandomVariableCuda(rv.getFiltrationTime(), rv.doubleValue(), shard)
         return RandomVariableCuda(rv.getFiltrationTime(), rv.getRealizations(), shard)
 
+    # ---- results of the last fit (downloaded on demand) ------------------------------------------------------------
+    def _fetch_fit(self):
+        if self._lastFit is not None and self._lastParameters is None:
+            K = self._lastK
+            x, cond = np.zeros(K), C.c_double()
+            nv.check(nv.load().fmb_regression_fit_get(self._lastFit.h, K, None, None, nv.dptr(x), C.byref(cond)))
+            self._lastParameters, self._lastConditionNumber = x, cond.value
+
+    @property
+    def lastParameters(self):
+        self._fetch_fit()
+        return self._lastParameters
+
+    @property
+    def lastConditionNumber(self):
+        self._fetch_fit()
+        return self._lastConditionNumber
+
+    @staticmethod
+    def _basis_args(basis):
+        hs = np.array([b.dv.h if b.dv is not None else 0 for b in basis], dtype=np.uint64)
+        sc = np.array([b.valueIfNonStochastic if b.dv is None else 0.0 for b in basis], dtype=np.float64)
+        return hs, sc
+
+    def _device_resident(self, y, basis):
+        shard = y.shard
+        return (y.dv is not None and len(basis) <= 8 and (shard.world == 1 or shard.native_comm)
+                and all(b.dv is None or b.dv.n == y.dv.n for b in basis))
+
+    def _fit_on_device(self, basis, y):
+        K = len(basis)
+        hs, sc = self._basis_args(basis)
+        fit = C.c_uint64()
+        cached = self._cachedFit.h if self._cachedFit is not None else 0
+        nv.check(nv.load().fmb_regression_fit(K, nv.hptr(hs), nv.dptr(sc), y.dv.h, y.size(), cached, C.byref(fit)))
+        self._set_fit(nv.DeviceVector(fit.value, 96), K)
+
+    def _set_fit(self, fit, K):
+        self._lastFit, self._lastK = fit, K
+        self._lastParameters = self._lastConditionNumber = None
+        if self._cachedFit is None:
+            self._cachedFit = fit
+
     def _moments(self, basis, y):
         K = len(basis)
         shard = y.shard
-        hs = np.array([b.dv.h if b.dv is not None else 0 for b in basis], dtype=np.uint64)
-        sc = np.array([b.valueIfNonStochastic if b.dv is None else 0.0 for b in basis], dtype=np.float64)
+        hs, sc = self._basis_args(basis)
         xh, xl = np.zeros(K * K), np.zeros(K * K)
         yh, yl = np.zeros(K), np.zeros(K)
         nv.check(nv.load().fmb_regression_moments(K, nv.hptr(hs), nv.dptr(sc), y.dv.h, nv.dptr(xh), nv.dptr(xl), nv.dptr(yh), nv.dptr(yl)))
-        H, L = shard.sum_dd_many(np.concatenate([xh, yh]), np.concatenate([xl, yl]))
+        H, L = shard.sum_dd_many(np.concatenate([xh, yh]), np.concatenate([xl, yl]), force=True)
         n = y.size()
         tot = (H + L) / n
         XTX, XTy = tot[:K * K].reshape(K, K).copy(), tot[K * K:].copy()
@@ -460,6 +513,9 @@ class MonteCarloConditionalExpectationRegression:
         y = self._as_cuda(dependents, shard)
         basis = [self._as_cuda(b, shard) for b in self.basisFunctionsEstimator]
         K = len(basis)
+        if self._device_resident(y, basis):
+            self._fit_on_device(basis, y)
+            return self.lastParameters
         if y.dv is None or K > 8:
             # deterministic dependents / more than 8 basis functions: the generic op path (one kernel per product + reduction)
             if self._XTX is None:
@@ -476,25 +532,44 @@ class MonteCarloConditionalExpectationRegression:
         A = nv.as_f64(XTX)
         b = nv.as_f64(XTy)
         nv.check(nv.load().fmb_regression_solve_svd(K, nv.dptr(A), nv.dptr(b), nv.dptr(x), C.byref(cond)))
-        self.lastConditionNumber = cond.value
-        self.lastParameters = x
+        self._lastFit = None
+        self._lastConditionNumber = cond.value
+        self._lastParameters = x
         return x
 
     def getConditionalExpectation(self, randomVariable):      # :97-110
-        x = self.getLinearRegressionParameters(randomVariable)
         shard = randomVariable.shard if isinstance(randomVariable, RandomVariableCuda) else LOCAL
-        basis = [self._as_cuda(b, shard) for b in self.basisFunctionsPredictor]
+        y = self._as_cuda(randomVariable, shard)
+        est = [self._as_cuda(b, shard) for b in self.basisFunctionsEstimator]
+        same = self.basisFunctionsPredictor is self.basisFunctionsEstimator
+        basis = est if same else [self._as_cuda(b, shard) for b in self.basisFunctionsPredictor]
         K = len(basis)
-        if K <= 8 and any(b.dv is not None for b in basis):
-            hs = np.array([b.dv.h if b.dv is not None else 0 for b in basis], dtype=np.uint64)
-            sc = np.array([b.valueIfNonStochastic if b.dv is None else 0.0 for b in basis], dtype=np.float64)
+        stochastic = next((b for b in basis if b.dv is not None), None)
+        plain = type(self).getLinearRegressionParameters is MonteCarloConditionalExpectationRegression.getLinearRegressionParameters
+        if (plain and stochastic is not None and K == len(est) and self._device_resident(y, est)
+                and all(b.dv is None or b.dv.n == y.dv.n for b in basis)):
+            # one call, nothing comes back: moments -> (exchange) -> solve -> prediction are queued on the compute stream
+            hs, sc = self._basis_args(est)
+            fit, out = C.c_uint64(), C.c_uint64()
+            cached = self._cachedFit.h if self._cachedFit is not None else 0
+            if same:
+                rc = nv.load().fmb_regression_conditional_expectation(K, nv.hptr(hs), nv.dptr(sc), y.dv.h, y.size(), cached, K, None, None, C.byref(fit), C.byref(out))
+            else:
+                hp, sp = self._basis_args(basis)
+                rc = nv.load().fmb_regression_conditional_expectation(K, nv.hptr(hs), nv.dptr(sc), y.dv.h, y.size(), cached, K, nv.hptr(hp), nv.dptr(sp),
+                                                                      C.byref(fit), C.byref(out))
+            nv.check(rc)
+            self._set_fit(nv.DeviceVector(fit.value, 96), K)
+            time = max(b.getFiltrationTime() for b in basis)
+            return RandomVariableCuda(time, None, shard, _dv=nv.DeviceVector(out.value, stochastic.dv.n), _n=stochastic.nGlobal)
+        x = self.getLinearRegressionParameters(randomVariable)
+        if K <= 8 and stochastic is not None:
+            hs, sc = self._basis_args(basis)
             out = C.c_uint64()
             xs = nv.as_f64(x)
             nv.check(nv.load().fmb_regression_predict(K, nv.hptr(hs), nv.dptr(sc), nv.dptr(xs), C.byref(out)))
-            n = next(b.dv.n for b in basis if b.dv is not None)
             time = max(b.getFiltrationTime() for b in basis)
-            n_logical = next(b.nGlobal for b in basis if b.dv is not None)      # the dependents may be deterministic (size 1)
-            return RandomVariableCuda(time, None, shard, _dv=nv.DeviceVector(out.value, n), _n=n_logical)
+            return RandomVariableCuda(time, None, shard, _dv=nv.DeviceVector(out.value, stochastic.dv.n), _n=stochastic.nGlobal)
         ce = basis[0].mult(float(x[0]))
         for i in range(1, K):
             ce = ce.addProduct(basis[i], float(x[i]))
@@ -515,11 +590,11 @@ class MonteCarloConditionalExpectationRegressionLocalizedOnDependents(MonteCarlo
         saved = self.basisFunctionsEstimator
         try:
             self.basisFunctionsEstimator = [b.mult(localizerWeights) for b in saved]
-            self._XTX = None
+            self._XTX = self._cachedFit = None
             return super().getLinearRegressionParameters(dependents.mult(localizerWeights))
         finally:
             self.basisFunctionsEstimator = saved
-            self._XTX = None
+            self._XTX = self._cachedFit = None
 
 
 class LinearRegression:

@@ -83,6 +83,14 @@ PROTOTYPES = {
     "fmb_regression_moments": [C.c_int, c_hp, c_dp, C.c_uint64, c_dp, c_dp, c_dp, c_dp],
     "fmb_regression_solve_svd": [C.c_int, c_dp, c_dp, c_dp, c_dp],
     "fmb_regression_predict": [C.c_int, c_hp, c_dp, c_dp, c_hp],
+    "fmb_regression_fit": [C.c_int, c_hp, c_dp, C.c_uint64, C.c_uint64, C.c_uint64, c_hp],
+    "fmb_regression_fit_get": [C.c_uint64, C.c_int, c_dp, c_dp, c_dp, c_dp],
+    "fmb_regression_predict_fit": [C.c_int, c_hp, c_dp, C.c_uint64, c_hp],
+    "fmb_regression_conditional_expectation": [C.c_int, c_hp, c_dp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, c_hp, c_dp, c_hp, c_hp],
+    "fmb_comm_unique_id": [C.c_char_p, C.c_int],
+    "fmb_comm_init": [C.c_char_p, C.c_int, C.c_int, C.c_int],
+    "fmb_comm_shutdown": [],
+    "fmb_comm_info": [C.POINTER(C.c_int), C.POINTER(C.c_int), c_hp],
     "fmb_bench_dfma_tflops": [c_dp],
     "fmb_bench_copy_gbs": [C.c_uint64, c_dp],
 }

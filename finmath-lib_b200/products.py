@@ -68,14 +68,29 @@ class Swaption(AbstractMonteCarloProduct):
             libor = model.getForwardRate(self.exerciseDate, fixingDate, paymentDate)
             payoff = libor.sub(swaprate).mult(periodLength).mult(self.notional)
             discountingDate = max(fixingDate, self.exerciseDate)
-            # discounting adjustment (:160-171): the model's discount curve is the curve implied by its forward curve in the
-            # configurations of this path, so forwardBondOnForwardCurve / forwardBondOnDiscountCurve == 1.0
-            discountingAdjustment = 1.0
+            discountingAdjustment = self._discounting_adjustment(model, discountingDate, paymentDate)
             value = value.add(payoff)
             value = value.discount(libor, paymentDate - discountingDate).mult(discountingAdjustment)
         values = value.floor(0.0)
         values = values.div(model.getNumeraire(float(self.exerciseDate))).mult(model.getMonteCarloWeights(float(self.exerciseDate)))
         return values.mult(model.getNumeraire(float(evaluationTime))).div(model.getMonteCarloWeights(float(evaluationTime)))
+
+
+    @staticmethod
+    def _discounting_adjustment(model, discountingDate, paymentDate):
+        """:160-171 — forwardBondOnForwardCurve / forwardBondOnDiscountCurve, 1.0 without a discount curve.  The curves are host-side
+        inputs given on the tenor grid (model.discountFactors; the forward-implied curve is DiscountCurveFromForwardCurve :130-142)."""
+        m = model.getModel() if hasattr(model, "getModel") else None
+        discountFactors = getattr(m, "discountFactors", None)
+        if m is None or discountFactors is None:
+            return 1.0
+        i0, i1 = m.getLiborPeriodIndex(discountingDate), m.getLiborPeriodIndex(paymentDate)
+        if i0 < 0 or i1 < 0:
+            raise NotImplementedError("discounting adjustment for dates off the tenor grid (curve interpolation) is outside the hot path")
+        implied = m.getDiscountFactorsFromForwardCurve()
+        forwardBondOnForwardCurve = implied[i0] / implied[i1]
+        forwardBondOnDiscountCurve = float(discountFactors[i0]) / float(discountFactors[i1])
+        return forwardBondOnForwardCurve / forwardBondOnDiscountCurve
 
 
 class BermudanSwaption(AbstractMonteCarloProduct):

@@ -6,10 +6,11 @@ single-stream reference.  No path data ever moves between GPUs; the only exchang
 getAverage / getVariance / getMin / getMax and the regression's 27 moments: per rank a double-double pair per sum,
 all-gathered and merged in rank order on every rank, so all ranks hold the same bits.
 
-The partials are already on the host when they are exchanged (fmb_rv_reduce returns them).  Between processes of ONE node they
-travel through a shared-memory mailbox (a few microseconds); the torch.distributed all-gather (NCCL on GPUs: host -> device ->
-NVLink -> host, ~120 us for 16 bytes; gloo in the CPU tests) is the path across nodes and can be forced with
-FMB_TINY_COLLECTIVES=torch.  A Bermudan valuation issues ~70 of these exchanges (profiles/r01_scaling.md).
+Default on GPUs (FMB_TINY_COLLECTIVES=nccl): the exchange happens INSIDE the native library — fmb_comm_init gives it an NCCL
+communicator on its own compute stream, fmb_rv_reduce / fmb_regression_fit all-gather the partials there and merge them in rank order
+on the device, so a regression needs no host round trip and a getAverage is one synchronisation.  The host-side variants remain as
+measured alternatives and for the CPU tests: FMB_TINY_COLLECTIVES=shm (a shared-memory mailbox between the processes of one x86 node)
+and =torch (torch.distributed all-gather: gloo on CPU, NCCL with host staging on GPUs).
 """
 import atexit
 import os
@@ -60,7 +61,10 @@ class _Mailbox:
         s = self.seq + 1
         b = s & 1
         self.data[b, self.rank, :n] = values
-        self.seqs[self.rank, 0] = s                        # publish after the payload (program order; x86 keeps stores ordered)
+        # publish after the payload.  Plain stores and loads through numpy views: correct only where the hardware keeps stores (and
+        # loads) in program order, i.e. x86-64 (TSO) - from_environment() enables the mailbox on such hosts only; everywhere else
+        # (aarch64: Grace) the exchange goes through the native communicator or torch.distributed.
+        self.seqs[self.rank, 0] = s
         deadline = None
         for r in range(self.world):
             spins = 0
@@ -92,6 +96,21 @@ class ShardContext:
         self.collectives = 0
         self._buffers = {}
         self._mailbox = None
+        self.native_comm = False                             # True: the native library exchanges the partials itself (fmb_comm_init)
+
+    def use_native_comm(self):
+        """Give the native library its own NCCL communicator (rank 0 creates the id, torch.distributed carries it to the others)."""
+        import ctypes as C
+        import torch.distributed as dist
+        from . import native as nv
+        lib = nv.load()
+        buf = C.create_string_buffer(128)
+        if self.rank == 0:
+            nv.check(lib.fmb_comm_unique_id(buf, 128))
+        box = [buf.raw if self.rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=self.group)
+        nv.check(lib.fmb_comm_init(box[0], 128, self.rank, self.world))
+        self.native_comm = True
 
     def use_mailbox(self, name, create):
         """Switch the tiny all-gathers to the shared-memory mailbox (all ranks on one node)."""
@@ -141,7 +160,7 @@ class ShardContext:
         return out_np.reshape(self.world, n).copy()
 
     def sum_dd(self, hi, lo):
-        if self.world == 1:
+        if self.world == 1 or self.native_comm:              # (native communicator: fmb_rv_reduce already returned the sum over all shards)
             return hi, lo
         g = self._all_gather([hi, lo])
         h, l = float(g[0, 0]), float(g[0, 1])
@@ -149,10 +168,11 @@ class ShardContext:
             h, l = dd_merge(h, l, float(g[r, 0]), float(g[r, 1]))
         return h, l
 
-    def sum_dd_many(self, his, los):
-        """Element-wise sum over ranks of arrays of double-double pairs (regression moments: one message)."""
+    def sum_dd_many(self, his, los, force=False):
+        """Element-wise sum over ranks of arrays of double-double pairs (regression moments: one message).  force: the values are
+        LOCAL partials even though a native communicator exists (fmb_regression_moments always returns local sums)."""
         his, los = np.asarray(his, dtype=np.float64), np.asarray(los, dtype=np.float64)
-        if self.world == 1:
+        if self.world == 1 or (self.native_comm and not force):
             return his, los
         g = self._all_gather(list(his.ravel()) + list(los.ravel()))
         n = his.size
@@ -162,17 +182,20 @@ class ShardContext:
                 H[i], L[i] = dd_merge(H[i], L[i], g[r, i], g[r, n + i])
         return H.reshape(his.shape), L.reshape(los.shape)
 
-    def min(self, v):
-        if self.world == 1:
+    def _extreme(self, v, has_data, pick):
+        if self.world == 1 or self.native_comm:
             return v
-        g = self._all_gather([v])[:, 0]
-        return float(np.nan) if np.isnan(g).any() else float(g.min())
+        g = self._all_gather([v if has_data else 0.0, 1.0 if has_data else 0.0])
+        vals = g[g[:, 1] != 0.0, 0]                          # shards that own no element do not take part (their NaN is "no data")
+        if vals.size == 0:
+            return float(np.nan)
+        return float(np.nan) if np.isnan(vals).any() else float(pick(vals))
 
-    def max(self, v):
-        if self.world == 1:
-            return v
-        g = self._all_gather([v])[:, 0]
-        return float(np.nan) if np.isnan(g).any() else float(g.max())
+    def min(self, v, has_data=True):
+        return self._extreme(v, has_data, np.min)
+
+    def max(self, v, has_data=True):
+        return self._extreme(v, has_data, np.max)
 
     def gather(self, local_array):
         """Concatenate the shards in rank order (getRealizations of the logical vector)."""
@@ -217,7 +240,15 @@ def from_environment(backend=None):
     if not dist.is_initialized():
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
     shard = ShardContext(rank, world, None, device)
-    if os.environ.get("FMB_TINY_COLLECTIVES", "shm") != "torch":
+    from . import native as nv
+    mode = os.environ.get("FMB_TINY_COLLECTIVES", "nccl" if backend == "nccl" else "shm")
+    if backend == "nccl":
+        nv.init(local_rank)                                  # one process per GPU: the native library on this rank's device
+    if mode == "nccl" and backend == "nccl":
+        shard.use_native_comm()
+        return shard
+    import platform
+    if mode != "torch" and platform.machine() in ("x86_64", "AMD64"):
         # all ranks on one node (the launch contract of bench.py): host-resident partials go through shared memory
         import socket
         hosts = [None] * world

@@ -642,14 +642,14 @@ class RandomVariableCuda(RandomVariable):
             return self.valueIfNonStochastic
         if self.dv.n == 0 and self.size() == 0:
             return float(np.finfo(np.float64).max)         # Double.MAX_VALUE :262-264
-        return self.shard.min(nv.reduce(nv.R_MIN, self.dv)[0])
+        return self.shard.min(nv.reduce(nv.R_MIN, self.dv)[0], self.dv.n > 0)
 
     def getMax(self):
         if self.dv is None:
             return self.valueIfNonStochastic
         if self.dv.n == 0 and self.size() == 0:
             return -float(np.finfo(np.float64).max)
-        return self.shard.max(nv.reduce(nv.R_MAX, self.dv)[0])
+        return self.shard.max(nv.reduce(nv.R_MAX, self.dv)[0], self.dv.n > 0)
 
     def _sorted_global(self):
         if self.shard.world == 1:

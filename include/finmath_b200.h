@@ -114,8 +114,9 @@ int fmb_rv_eval_chain(int n_instr, const unsigned char* code, int start_leaf, co
                       const double* scalars, int n_scalars, fmb_handle* out);
 
 /* ---- reductions (getAverage/getVariance/getMin/getMax ... :262-428).  Sums are accumulated in double-double
- *      (block + warp tree), returned as out2[0] = hi, out2[1] = lo so that shards can be combined exactly; the caller
- *      divides by n.  MIN/MAX return the value in out2[0]. -------------------------------------------------------------- */
+ *      (block + warp tree, the last CTA merges the per-CTA partials and writes the result straight into mapped host memory: one
+ *      launch, 16 bytes back), returned as out2[0] = hi, out2[1] = lo; the caller divides by n.  MIN/MAX return the value in
+ *      out2[0].  With a communicator (fmb_comm_init) the result covers all shards (empty shards are ignored by MIN/MAX). --------- */
 enum {
 	FMB_R_SUM = 0,            /* sum x_i */
 	FMB_R_SUM_PRODUCT = 1,    /* sum x_i * w_i */
@@ -180,6 +181,34 @@ int fmb_regression_moments(int K, const fmb_handle* basis, const double* basis_s
 int fmb_regression_solve_svd(int K, const double* A, const double* b, double* x, double* cond);
 /* b_0*x_0 then addProduct(b_i, x_i) in order (:103-107) */
 int fmb_regression_predict(int K, const fmb_handle* basis, const double* basis_scalar, const double* x, fmb_handle* out);
+
+/* Device-resident form of the same regression: nothing returns to the host, so a Bermudan backward induction queues one exercise
+ * date after the other without a round trip (MonteCarloConditionalExpectationRegression.java:97-150 is one getConditionalExpectation
+ * call per exercise date, BermudanSwaption.java:150-156).
+ *   fit: ONE pass accumulates the local moments (last CTA merges the per-CTA partials); with a communicator (fmb_comm_init) the
+ *   shards' moments are all-gathered on the compute stream and merged in rank order; mean = sum / n_global; the K x K system is solved
+ *   on the device with the same Jacobi SVD code as fmb_regression_solve_svd.  The result is a small device vector behind `fit`:
+ *   XtX, Xty, coefficients, condition number (fmb_regression_fit_get downloads it; only tests / getLinearRegressionParameters do).
+ *   cached_fit != 0: XtX is taken from that earlier fit (the reference caches its solver per estimator instance, :125-138).
+ *   n_global = logical number of paths over all shards (0: the local length).
+ *   conditional_expectation = fit + predict_fit; basis_pred == NULL: predict on the estimator's basis functions. */
+int fmb_regression_fit(int K, const fmb_handle* basis, const double* basis_scalar, fmb_handle y, uint64_t n_global, fmb_handle cached_fit,
+                       fmb_handle* fit);
+int fmb_regression_fit_get(fmb_handle fit, int K, double* XtX, double* Xty, double* x, double* cond);
+int fmb_regression_predict_fit(int K, const fmb_handle* basis, const double* basis_scalar, fmb_handle fit, fmb_handle* out);
+int fmb_regression_conditional_expectation(int K, const fmb_handle* basis, const double* basis_scalar, fmb_handle y, uint64_t n_global,
+                                           fmb_handle cached_fit, int Kp, const fmb_handle* basis_pred, const double* basis_pred_scalar,
+                                           fmb_handle* fit, fmb_handle* out);
+
+/* ---- multi-GPU: one process per GPU, paths sharded by MT19937 jump-ahead (fmb_bm_generate's path_offset).  The only exchange is the
+ *      reduction partials of fmb_rv_reduce and the regression moments of fmb_regression_fit: an NCCL all-gather of a few doubles on
+ *      the library's compute stream followed by a rank-ordered merge kernel, so every rank holds identical bits.  With a communicator,
+ *      fmb_rv_reduce returns the result over ALL shards.  NCCL is bound at run time (dlopen libnccl.so.2, or FMB_NCCL_LIB).
+ *      Rank 0 creates the 128-byte id, the host distributes it (any channel), every rank calls fmb_comm_init. ---------------------- */
+int fmb_comm_unique_id(unsigned char* id, int len);
+int fmb_comm_init(const unsigned char* id, int len, int rank, int world);
+int fmb_comm_shutdown(void);
+int fmb_comm_info(int* rank, int* world, uint64_t* exchanges);
 
 /* ---- micro-benchmarks used by bench.py to measure the roofline denominators on the box itself ---------------------- */
 int fmb_bench_dfma_tflops(double* tflops);          /* dependent-chain-free DFMA loop on all SMs: FP64 pipe peak */

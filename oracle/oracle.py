@@ -227,12 +227,18 @@ class LMM:
         lib().orc_lmm_forward_rate(self.h, C.c_double(time), C.c_double(start), C.c_double(end), out.ctypes.data_as(c_dp))
         return out
 
-    def swaption(self, exercise_date, fixing_dates, payment_dates, swaprates, notional=1.0):
+    def swaption(self, exercise_date, fixing_dates, payment_dates, swaprates, notional=1.0, discounting_adjustments=None):
         f, fp = _d(fixing_dates)
         p, pp = _d(payment_dates)
         s, sp = _d(swaprates)
         vals = np.empty(self.paths)
         se = C.c_double()
+        if discounting_adjustments is not None:
+            a, ap = _d(discounting_adjustments)
+            lib().orc_lmm_swaption_adj.restype = C.c_double
+            price = lib().orc_lmm_swaption_adj(self.h, C.c_double(exercise_date), fp, pp, sp, C.c_int(f.size), C.c_double(notional), ap,
+                                               vals.ctypes.data_as(c_dp), C.byref(se))
+            return price, vals, se.value
         price = lib().orc_lmm_swaption(self.h, C.c_double(exercise_date), fp, pp, sp, C.c_int(f.size), C.c_double(notional),
                                        vals.ctypes.data_as(c_dp), C.byref(se))
         return price, vals, se.value

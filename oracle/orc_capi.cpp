@@ -211,6 +211,15 @@ double orc_lmm_swaption(void* hv, double exerciseDate, const double* fixingDates
 	if (stdErrOut) *stdErrOut = getStandardError(v);
 	return getAverage(v);
 }
+// the same with per-period discounting adjustments forwardBondOnForwardCurve / forwardBondOnDiscountCurve (Swaption.java:160-171)
+double orc_lmm_swaption_adj(void* hv, double exerciseDate, const double* fixingDates, const double* paymentDates, const double* swaprates,
+		int n, double notional, const double* adjustments, double* valuesOut, double* stdErrOut) {
+	auto* h = (LmmHandle*)hv;
+	P v = swaptionValue(h->sim, 0.0, exerciseDate, vecOf(fixingDates, n), vecOf(paymentDates, n), vecOf(swaprates, n), notional, vecOf(adjustments, n));
+	if (valuesOut) store(v, valuesOut, h->bm->paths);
+	if (stdErrOut) *stdErrOut = getStandardError(v);
+	return getAverage(v);
+}
 double orc_lmm_caplet(void* hv, double maturity, double periodLength, double strike, double daycountFraction, int isFloorlet, double* valuesOut) {
 	auto* h = (LmmHandle*)hv;
 	P v = capletValue(h->sim, 0.0, maturity, periodLength, strike, daycountFraction, isFloorlet != 0);

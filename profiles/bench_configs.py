@@ -14,9 +14,13 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import __graft_entry__ as graft  # noqa: E402
 
-pkg = graft.load_package()
-nv = pkg.native
-nv.init(0)
+pkg = None
+nv = None
+
+
+def bind(package):
+    global pkg, nv
+    pkg, nv = package, package.native
 
 
 def timed(fn, reps=3):
@@ -30,11 +34,24 @@ def timed(fn, reps=3):
     return float(np.mean(ms))
 
 
-def report(name, paths, steps, bytes_per_path_step, ms, extra=None):
+def report(name, paths, steps, bytes_per_path_step, ms, extra=None, emit=True):
     d = {"config": name, "paths": paths, "steps": steps, "ms": ms, "path_steps_per_s": paths * steps / (ms * 1e-3),
          "algorithmic_GBps": paths * steps * bytes_per_path_step / (ms * 1e-3) / 1e9}
     d.update(extra or {})
-    print(json.dumps(d), flush=True)
+    if emit:
+        print(json.dumps(d), flush=True)
+    return d
+
+
+def run_all(package, c3_paths=4_000_000):
+    """C1, C2, C3 for bench.py's `configs` key (C5 is measured by bench.py itself): 1 warm-up + 2 timed repetitions each."""
+    bind(package)
+    out = [report("C1 Black-Scholes 100k x 100, EULER_FUNCTIONAL, incl. call price", 100_000, 100, 16, timed(c1, reps=2), emit=False),
+           report("C2 Hull-White 1M x 200 (dt 0.1y), piecewise-constant sigma(t), EULER", 1_000_000, 200, 32, timed(c2, reps=2), emit=False)]
+    nv.load().fmb_pool_trim()
+    out.append(report("C3 Heston full truncation %dM x 1000, 8-strike smile" % (c3_paths // 1_000_000), c3_paths, 1000, 32, timed(c3(c3_paths), reps=2), emit=False))
+    nv.load().fmb_pool_trim()
+    return out
 
 
 def c1(seed):
@@ -74,6 +91,8 @@ def c5(paths):
 
 
 if __name__ == "__main__":
+    bind(graft.load_package())
+    nv.init(0)
     which = sys.argv[1:] or ["c1", "c2", "c3", "c5"]
     if "c1" in which:
         report("C1 Black-Scholes 100k x 100, EULER_FUNCTIONAL, incl. call price", 100_000, 100, 16, timed(c1))

@@ -186,6 +186,9 @@ assert shard.global_count(hi - lo) == n
 Hm, Lm = shard.sum_dd_many(np.array([1.0 + shard.rank, 2.0]), np.array([0.0, 1e-20]))
 assert Hm.tolist() == [3.0, 4.0]
 assert shard.min(float(shard.rank)) == 0.0 and shard.max(float(shard.rank)) == 1.0
+# a shard that owns no element does not take part (its local NaN means "no data", not NaN)
+assert shard.min(5.0 if shard.rank == 0 else float('nan'), shard.rank == 0) == 5.0 and shard.max(float('nan'), False) != shard.max(float('nan'), False)
+assert np.isnan(shard.max(float('nan') if shard.rank == 1 else 1.0))
 g = shard.gather(x[lo:hi])
 assert np.array_equal(g, x)
 # every rank holds identical bits

@@ -209,6 +209,61 @@ def test_lmm_numeraire_forward_rate_swaption_caplet(gpu, orc):
     assert abs(caplet.getValue(dev) - ref_c) <= PRICE_TOL * abs(ref_c)
 
 
+def test_swaption_discounting_adjustment_with_a_separate_discount_curve(gpu, orc):
+    """Swaption.java:160-171: with a discount curve that is NOT the one implied by the forward curve every period's value is scaled by
+    forwardBondOnForwardCurve / forwardBondOnDiscountCurve.  The oracle gets the adjustments as an explicit array (computed here from
+    the two curves), the device-side product derives them from the model's curves."""
+    paths = 20_000
+    s = lmm_setup(gpu)
+    tenor = s["tenor"]
+    s["df"] = np.array([np.exp(-0.03 * tenor.getTime(i) - 0.0005 * tenor.getTime(i) ** 2) for i in range(s["N"] + 1)])     # OIS-like curve below the 5 % forwards
+    dev = lmm_device(gpu, s, paths, scheme=2)
+    ref = lmm_oracle(orc, s, paths, scheme=2)
+    fixing = [5.0 + 0.5 * i for i in range(10)]
+    payment = [5.5 + 0.5 * i for i in range(10)]
+    implied = [1.0]
+    for i in range(s["N"]):
+        implied.append(implied[-1] / (1.0 + s["L0"][i] * tenor.getTimeStep(i)))
+    adj = []
+    for f, p in zip(fixing, payment):
+        i0, i1 = tenor.getTimeIndex(max(f, 5.0)), tenor.getTimeIndex(p)
+        adj.append((implied[i0] / implied[i1]) / (s["df"][i0] / s["df"][i1]))
+    assert max(abs(a - 1.0) for a in adj) > 1e-3                      # the adjustment matters in this set-up
+    price = gpu.Swaption(5.0, fixing, payment, [0.05] * 10).getValue(dev)
+    ref_price, _, _ = ref.swaption(5.0, fixing, payment, [0.05] * 10, discounting_adjustments=adj)
+    assert abs(price - ref_price) <= PRICE_TOL * abs(ref_price)
+    plain, _, _ = ref.swaption(5.0, fixing, payment, [0.05] * 10)
+    assert abs(price - plain) > 1e-6 * abs(plain)
+
+
+def test_fused_kernels_are_not_used_with_a_mismatching_driver(gpu):
+    """The fused Heston / Hull-White kernels read exactly two increments per step and the fused LMM kernel takes the factor count from
+    the driver: a driver that does not match the model's tables must run the generic loop (the reference's addSumProduct over whatever
+    loadings the model returns), never a fused kernel with wrong strides."""
+    td = gpu.TimeDiscretizationFromArray(0.0, 30, 0.1)
+    bm3 = gpu.BrownianMotionCuda(td, 3, 3000, 31415)
+    model = gpu.HestonModel(1.0, 0.05, 0.3, 0.05, 0.09, 0.1, 0.5, 0.1, 1, bm3.randomVariableFactory)
+    a = gpu.EulerSchemeFromProcessModel(model, bm3)
+    b = gpu.EulerSchemeFromProcessModel(model, gpu.BrownianMotionView(bm3, [0, 1]))
+    for c in (0, 1):
+        assert np.array_equal(a.getProcessValue(30, c).getRealizations(), b.getProcessValue(30, c).getRealizations())
+    assert a.usedFusedKernel is None and b.usedFusedKernel is None
+    # LMM tables built for 3 factors, driver with 2: no fused kernel
+    s = lmm_setup(gpu, n_libors=8, n_factors=3)
+    factory = gpu.RandomVariableCudaFactory()
+    lmm = gpu.LIBORMarketModelFromCovarianceModel.of(s["tenor"], None, s["L0"], s["df"], factory, s["cov"], None, {})
+    proc = gpu.EulerSchemeFromProcessModel(lmm, gpu.BrownianMotionCuda(s["sim"], 2, 500, 3141, factory))
+    assert lmm.getFusedSpecification(proc) is None
+    # covariance model on a finer grid than the process: rows are mapped by time (AbstractLIBORCovarianceModel.java:70-76), fused == generic
+    s2 = lmm_setup(gpu, n_libors=8, n_factors=2, dt=0.25)
+    coarse = gpu.TimeDiscretizationFromArray(0.0, 8, 0.5)
+    lmm2 = gpu.LIBORMarketModelFromCovarianceModel.of(s2["tenor"], None, s2["L0"], s2["df"], factory, s2["cov"], None, {})
+    bm = gpu.BrownianMotionCuda(coarse, 2, 700, 3141, factory)
+    f, g = gpu.EulerSchemeFromProcessModel(lmm2, bm), gpu.EulerSchemeFromProcessModel(lmm2, bm, forceGeneric=True)
+    assert np.array_equal(f.getProcessValue(5, 7).getRealizations(), g.getProcessValue(5, 7).getRealizations())
+    assert f.usedFusedKernel == "lmm" and g.usedFusedKernel is None
+
+
 @pytest.mark.parametrize("scheme", [2, 1])
 def test_lmm_bermudan_swaption_matches_oracle(gpu, orc, scheme):
     paths = 20_000
@@ -256,6 +311,41 @@ def test_regression_moments_and_solver(gpu, orc):
     est2 = gpu.MonteCarloConditionalExpectationRegression([RV(0.0, b1), RV(0.0, b1)])
     x2 = est2.getLinearRegressionParameters(RV(0.0, 4.0 * b1))
     assert np.allclose(x2, [2.0, 2.0], atol=1e-9)
+
+
+def test_device_resident_regression_equals_the_host_resident_one(gpu):
+    """fmb_regression_conditional_expectation (moments, solve and prediction queued on the device, nothing returns to the host) against the
+    host-resident sequence fmb_regression_moments -> fmb_regression_solve_svd -> fmb_regression_predict: same moments, same Jacobi code on
+    both sides, so the coefficients and fitted values agree to the last bit; the solver (XtX) is cached per estimator (:125-138)."""
+    import ctypes as C
+    nv = gpu.native
+    RV = gpu.RandomVariableCuda
+    rng = np.random.default_rng(11)
+    for n, K in ((1, 2), (257, 3), (300_001, 6), (50_000, 8)):
+        cols = [rng.random(n) + 0.25 * k for k in range(K - 1)]
+        basis = [gpu.RandomVariableFromDoubleArray(1.0)] + [RV(0.0, c) for c in cols]
+        y = RV(1.0, sum((k + 1.0) * c for k, c in enumerate(cols)) + 0.1 * rng.standard_normal(n))
+        est = gpu.MonteCarloConditionalExpectationRegression(basis)
+        ce = est.getConditionalExpectation(y)
+        assert est._lastFit is not None                       # took the device-resident path
+        x_dev, cond_dev = est.lastParameters.copy(), est.lastConditionNumber
+        b = [est._as_cuda(v, y.shard) for v in basis]
+        XTX, XTy = est._moments(b, y)
+        x = np.zeros(K)
+        cond = C.c_double()
+        nv.check(nv.load().fmb_regression_solve_svd(K, nv.dptr(nv.as_f64(XTX)), nv.dptr(nv.as_f64(XTy)), nv.dptr(x), C.byref(cond)))
+        assert np.array_equal(x, x_dev) and cond.value == cond_dev, (n, K, x, x_dev)
+        hs, sc = est._basis_args(b)
+        out = C.c_uint64()
+        nv.check(nv.load().fmb_regression_predict(K, nv.hptr(hs), nv.dptr(sc), nv.dptr(x), C.byref(out)))
+        assert np.array_equal(nv.DeviceVector(out.value, n).download(), ce.getRealizations())
+        # second dependent on the same estimator: XtX comes from the first fit
+        y2 = RV(1.0, rng.standard_normal(n))
+        est.getConditionalExpectation(y2)
+        XtX1, XtX2 = np.zeros(K * K), np.zeros(K * K)
+        nv.check(nv.load().fmb_regression_fit_get(est._cachedFit.h, K, nv.dptr(XtX1), None, None, None))
+        nv.check(nv.load().fmb_regression_fit_get(est._lastFit.h, K, nv.dptr(XtX2), None, None, None))
+        assert np.array_equal(XtX1, XtX2) and est._lastFit is not est._cachedFit
 
 
 # ---- Hull-White (C2 shape, small) -------------------------------------------------------------------------------------------

@@ -151,6 +151,52 @@ def test_pool_reuse_and_handle_errors(gpu):
         nv.binary(0, nv.DeviceVector.upload(np.zeros(3)), 0.0, nv.DeviceVector.upload(np.zeros(4)), 0.0)
 
 
+def test_free_from_another_thread_while_a_vector_is_in_use(gpu):
+    """The documented threading contract: GC / cleaner threads free handles while pool threads compute.  An entry point pins the handles
+    it dereferences until its kernels are queued, so a concurrent fmb_rv_free can neither delete the vector under it nor recycle its block
+    early: every call either succeeds with the right numbers or fails cleanly with FMB_EHANDLE."""
+    import ctypes as C
+    import threading
+    nv = gpu.native
+    lib = nv.load()
+    n = 200_000
+    src = np.arange(n, dtype=np.float64)
+    errors = []
+
+    def worker(h, results):
+        out = C.c_uint64()
+        for _ in range(400):
+            rc = lib.fmb_rv_unary(nv.U_MULT, h, 2.0, C.byref(out))
+            if rc == nv.FMB_EHANDLE:
+                results.append("freed")
+                return
+            if rc != 0:
+                errors.append(rc)
+                return
+            got = np.empty(n)
+            if lib.fmb_rv_download(out.value, nv.dptr(got), n) != 0 or got[n - 1] != 2.0 * (n - 1) or got[1] != 2.0:
+                errors.append("wrong values")
+            lib.fmb_rv_free(out.value)
+        results.append("done")
+
+    for rep in range(6):
+        h = C.c_uint64()
+        nv.check(lib.fmb_rv_upload(nv.dptr(src), n, C.byref(h)))
+        results = []
+        ts = [threading.Thread(target=worker, args=(h.value, results)) for _ in range(3)]
+        for t in ts:
+            t.start()
+        import time
+        time.sleep(0.002 * rep)
+        lib.fmb_rv_free(h.value)                            # "the cleaner" frees while the workers are busy
+        for t in ts:
+            t.join()
+        assert not errors, errors
+        assert len(results) == 3
+    live = C.c_uint64()
+    nv.check(lib.fmb_pool_stats(None, None, C.byref(live)))
+
+
 def test_concurrent_callers_like_the_reference_thread_pool(gpu):
     """EulerSchemeFromProcessModel.java:199,:232-269 submits one task per component to a thread pool, and the JVM frees from GC
     threads: the C ABI must be re-entrant.  8 host threads hammer ops, reductions and frees concurrently (ctypes drops the GIL)."""
