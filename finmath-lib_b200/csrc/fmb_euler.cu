@@ -107,6 +107,187 @@ __global__ void __launch_bounds__(256) eulerHullWhiteKernel(int T, uint64_t P, c
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Two-component, two-factor models (Heston, Hull-White) with the increments streamed through shared memory by the bulk asynchronous
+// copy engine (TMA, cp.async.bulk + mbarrier).  The plain kernels above issue two dependent 8-byte loads per lane and step; with a
+// thousand sequential steps per path ncu shows long_scoreboard as the dominant stall (52 %) and 256-byte row segments that scatter over
+// thousands of DRAM pages (0.55 of the HBM peak, profiles/r01_notes.md).  Here a CTA owns a tile of 2*NT consecutive paths (two paths
+// per thread: ILP 2 on the exp / log / sqrt chains); one elected thread keeps S stages of KS time steps in flight - per stage 2*KS bulk
+// copies of the tile's row segments (8*2*NT contiguous bytes each, 4 KB at NT = 256) that complete on the stage's "full" mbarrier; the
+// warps release a stage through its "empty" mbarrier.  No block-wide barrier in the time loop.  Results are written with 16-byte
+// stores (the thread's two adjacent paths), 16*NT contiguous bytes per row and CTA.  Same arithmetic, same order: bit-identical to the
+// plain kernels.  Needs an even number of paths (16-byte aligned rows); the plain kernels remain for odd path counts.
+// Algorithmic HBM bytes per path-step: 16 read + 16 written.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smemAddr(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarArrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smemAddr(bar)) : "memory"); }
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
+	uint32_t done;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smemAddr(bar)), "r"(parity) : "memory");
+	} while (!done);
+}
+__device__ __forceinline__ void bulkLoad(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(smemAddr(sdst)), "l"(gsrc), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+}
+
+struct HestonStep {
+	HestonParams h;
+	const double* dt; const double* rate;
+	bool functional, pc;
+	__device__ __forceinline__ void init(double* a, double* b, double* ya, double* yb) const {
+#pragma unroll
+		for (int u = 0; u < 2; u++) { a[u] = h.x0; b[u] = h.v0; ya[u] = h.ylog0; yb[u] = h.v0; }
+	}
+	// two paths at once; per path exactly the operations of eulerHestonKernel
+	__device__ __forceinline__ void step(int t, const double* w0, const double* w1, double* s, double* v, double* y0, double* y1) const {
+		const double d = __ldg(dt + t), r = __ldg(rate + t);
+		double var[2], mu0[2], mu1[2], vol[2];
+#pragma unroll
+		for (int u = 0; u < 2; u++) { hestonDrift(h, v[u], r, var[u], mu0[u], mu1[u]); vol[u] = sqrt(var[u]); }
+		if (functional) {
+			if (t == 0) { y0[0] = h.ylog0; y0[1] = h.ylog0; } else flogN<2>(s, y0);
+			y1[0] = v[0]; y1[1] = v[1];
+		}
+#pragma unroll
+		for (int u = 0; u < 2; u++) {
+			y0[u] = y0[u] + mu0[u] * d;
+			y0[u] = y0[u] + vol[u] * w0[u];
+			y0[u] = y0[u] + w1[u] * 0.0;
+			const double volv = vol[u] * h.xi;
+			y1[u] = y1[u] + mu1[u] * d;
+			y1[u] = y1[u] + (volv * h.rho) * w0[u];
+			y1[u] = y1[u] + (volv * h.rhoBar) * w1[u];
+		}
+		fexpN<2>(y0, s);
+		v[0] = y1[0]; v[1] = y1[1];
+		if (pc) {
+#pragma unroll
+			for (int u = 0; u < 2; u++) {
+				double varP, mu0P, mu1P;
+				hestonDrift(h, v[u], r, varP, mu0P, mu1P);
+				y0[u] = y0[u] + ((mu0P - mu0[u]) / 2.0) * d;
+				y1[u] = y1[u] + ((mu1P - mu1[u]) / 2.0) * d;
+			}
+			fexpN<2>(y0, s);
+			v[0] = y1[0]; v[1] = y1[1];
+		}
+	}
+};
+
+struct HullWhiteStep {
+	const double* dt; const double* c0; const double* c1; const double* fl;
+	__device__ __forceinline__ void init(double* a, double* b, double* ya, double* yb) const {
+#pragma unroll
+		for (int u = 0; u < 2; u++) { a[u] = 0.0; b[u] = 0.0; ya[u] = 0.0; yb[u] = 0.0; }
+	}
+	__device__ __forceinline__ void step(int t, const double* w0, const double* w1, double* x0, double* x1, double*, double*) const {
+		const double d = __ldg(dt + t), k0 = __ldg(c0 + t), k1 = __ldg(c1 + t);
+		const double2 fa = __ldg(reinterpret_cast<const double2*>(fl) + 2 * t), fb = __ldg(reinterpret_cast<const double2*>(fl) + 2 * t + 1);
+#pragma unroll
+		for (int u = 0; u < 2; u++) {
+			const double mu0 = x0[u] * k0, mu1 = x0[u] * k1;
+			double y0 = x0[u] + mu0 * d;
+			y0 = y0 + w0[u] * fa.x;
+			y0 = y0 + w1[u] * fa.y;
+			double y1 = x1[u] + mu1 * d;
+			y1 = y1 + w0[u] * fb.x;
+			y1 = y1 + w1[u] * fb.y;
+			x0[u] = y0; x1[u] = y1;
+		}
+	}
+};
+
+template <class Model, int NT, int KS, int S> __global__ void __launch_bounds__(NT) eulerTwoFactorTmaKernel(Model m, int T, uint64_t P,
+		const double* const* __restrict__ dW, double* const* __restrict__ X) {
+	constexpr int TP = 2 * NT;                                   // paths per tile
+	extern __shared__ __align__(128) unsigned char smemRaw[];
+	double* stage = reinterpret_cast<double*>(smemRaw);          // [S][KS * 2 rows][TP]
+	uint64_t* full = reinterpret_cast<uint64_t*>(smemRaw + (size_t)S * KS * 2 * TP * sizeof(double));
+	uint64_t* empty = full + S;
+	const int tid = threadIdx.x, lane = tid & 31;
+	if (tid == 0) {
+		for (int s = 0; s < S; s++) { mbarInit(full + s, 1); mbarInit(empty + s, NT / 32); }
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	const uint64_t tiles = (P + TP - 1) / TP;
+	const int chunksPerTile = (T + KS - 1) / KS;
+	// chunk sequence of this CTA: (tile, chunk in tile), tiles blockIdx.x, + gridDim.x, ...; g counts them, stage = g % S, phase = (g / S) & 1
+	uint64_t myTiles = blockIdx.x < tiles ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+	const uint64_t totalChunks = myTiles * chunksPerTile;
+	uint64_t gIssue = 0;                                          // (thread 0) next chunk to request
+	auto issue = [&](uint64_t g) {
+		const uint64_t tileIdx = blockIdx.x + (g / chunksPerTile) * gridDim.x;
+		const int ck = (int)(g % chunksPerTile);
+		const uint64_t p0 = tileIdx * TP;
+		const uint32_t n = (uint32_t)min((uint64_t)TP, P - p0);
+		const int t0 = ck * KS, steps = min(KS, T - t0);
+		const int s = (int)(g % S);
+		if (g >= (uint64_t)S) mbarWait(empty + s, (uint32_t)(((g / S) - 1) & 1));     // every warp has finished reading the stage's previous chunk
+		mbarExpectTx(full + s, (uint32_t)(steps * 2) * n * 8u);
+		double* dst = stage + (size_t)s * KS * 2 * TP;
+		for (int r = 0; r < steps * 2; r++) bulkLoad(dst + (size_t)r * TP, dW[(size_t)t0 * 2 + r] + p0, n * 8u, full + s);
+	};
+	if (tid == 0) { for (; gIssue < (uint64_t)(S - 1) && gIssue < totalChunks; gIssue++) issue(gIssue); }
+	uint64_t g = 0;
+	for (uint64_t tileIdx = blockIdx.x; tileIdx < tiles; tileIdx += gridDim.x) {
+		const uint64_t p0 = tileIdx * TP;
+		const uint64_t p = p0 + 2 * (uint64_t)tid;
+		const bool active = p < P;                                // P is even: both paths of an active thread exist
+		double a[2], b[2], ya[2], yb[2];
+		m.init(a, b, ya, yb);
+		for (int ck = 0; ck < chunksPerTile; ck++, g++) {
+			if (tid == 0 && gIssue < totalChunks) { issue(gIssue); gIssue++; }
+			const int s = (int)(g % S);
+			mbarWait(full + s, (uint32_t)((g / S) & 1));
+			const double* src = stage + (size_t)s * KS * 2 * TP + 2 * tid;
+			const int t0 = ck * KS, steps = min(KS, T - t0);
+			if (active) {
+#pragma unroll
+				for (int k = 0; k < KS; k++) {
+					if (k < steps) {
+						const double2 w0 = *reinterpret_cast<const double2*>(src + (size_t)(2 * k) * TP);
+						const double2 w1 = *reinterpret_cast<const double2*>(src + (size_t)(2 * k + 1) * TP);
+						const double w0v[2] = { w0.x, w0.y }, w1v[2] = { w1.x, w1.y };
+						m.step(t0 + k, w0v, w1v, a, b, ya, yb);
+						*reinterpret_cast<double2*>(X[2 * (size_t)(t0 + k + 1)] + p) = make_double2(a[0], a[1]);
+						*reinterpret_cast<double2*>(X[2 * (size_t)(t0 + k + 1) + 1] + p) = make_double2(b[0], b[1]);
+					}
+				}
+			}
+			__syncwarp();
+			if (lane == 0) mbarArrive(empty + s);
+		}
+	}
+}
+
+static const int TMA2F_NT = 256, TMA2F_KS = 2, TMA2F_S = 4;
+template <class Model> static int launchTwoFactorTma(const Model& m, int T, uint64_t paths, const double* const* dW, double* const* X) {
+	Context& c = ctx();
+	auto kernel = eulerTwoFactorTmaKernel<Model, TMA2F_NT, TMA2F_KS, TMA2F_S>;
+	const size_t smem = (size_t)TMA2F_S * TMA2F_KS * 2 * (2 * TMA2F_NT) * sizeof(double) + 2 * TMA2F_S * sizeof(uint64_t);
+	static bool attr = false;
+	if (!attr) { FMB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+	int perSm = 0;
+	FMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, TMA2F_NT, smem));
+	const uint64_t tiles = (paths + 2 * TMA2F_NT - 1) / (2 * TMA2F_NT);
+	const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * std::max(perSm, 1), tiles));
+	kernel<<<grid, TMA2F_NT, smem, c.stream>>>(m, T, paths, dW, X);
+	return FMB_OK;
+}
+// the bulk-copy kernels need 16-byte aligned row segments: an even number of paths (FMB_EULER_TMA=0 forces the plain kernels: A/B runs)
+static bool useTwoFactorTma(uint64_t paths) {
+	if (paths % 2 != 0 || paths < 2) return false;
+	const char* e = getenv("FMB_EULER_TMA");
+	return !(e && atoi(e) == 0);
+}
+
 // ---- host helpers -------------------------------------------------------------------------------------------------
 struct DeviceBlob {                // one pool allocation holding all parameter tables of a launch
 	void* base = nullptr;
@@ -225,10 +406,18 @@ int fmb_euler_heston(int scheme, int heston_scheme, int T, uint64_t paths, const
 		h.rhoBar = std::sqrt(((rho * rho) - 1) * -1);      // HestonModel.java:182
 		h.hestonScheme = heston_scheme; h.scheme = scheme;
 		if (scheme == SCHEME_EULER || scheme == SCHEME_PC) h.ylog0 = y0;
-		const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * 8, (paths + 255) / 256));
-		eulerHestonKernel<<<grid, 256, 0, c.stream>>>(h, T, paths, blob.at<double>(oDt), blob.at<double>(oRate), blob.at<const double*>(oInc),
-		                                             (double* const*)blob.at<double*>(oRows));
-		rc = launchCheck("euler_heston");
+		if (useTwoFactorTma(paths)) {
+			HestonStep m;
+			m.h = h; m.dt = blob.at<double>(oDt); m.rate = blob.at<double>(oRate);
+			m.functional = (scheme == SCHEME_EULER_FUNCTIONAL || scheme == SCHEME_PC_FUNCTIONAL);
+			m.pc = (scheme == SCHEME_PC || scheme == SCHEME_PC_FUNCTIONAL);
+			rc = launchTwoFactorTma(m, T, paths, blob.at<const double*>(oInc), (double* const*)blob.at<double*>(oRows));
+		} else {
+			const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * 8, (paths + 255) / 256));
+			eulerHestonKernel<<<grid, 256, 0, c.stream>>>(h, T, paths, blob.at<double>(oDt), blob.at<double>(oRate), blob.at<const double*>(oInc),
+			                                             (double* const*)blob.at<double*>(oRows));
+		}
+		if (rc == FMB_OK) rc = launchCheck("euler_heston");
 	}
 	if (rc == FMB_OK) {
 		out[0] = out[1] = 0;
@@ -259,10 +448,16 @@ int fmb_euler_hull_white(int T, uint64_t paths, const double* dt, const fmb_hand
 	const size_t oRows = blob.add(rows.data(), rows.size() * sizeof(double*));
 	int rc = blob.upload();
 	if (rc == FMB_OK && paths > 0) {
-		const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * 8, (paths + 255) / 256));
-		eulerHullWhiteKernel<<<grid, 256, 0, c.stream>>>(T, paths, blob.at<double>(oDt), blob.at<double>(oC0), blob.at<double>(oC1), blob.at<double>(oFl),
-		                                                blob.at<const double*>(oInc), (double* const*)blob.at<double*>(oRows));
-		rc = launchCheck("euler_hull_white");
+		if (useTwoFactorTma(paths)) {
+			HullWhiteStep m;
+			m.dt = blob.at<double>(oDt); m.c0 = blob.at<double>(oC0); m.c1 = blob.at<double>(oC1); m.fl = blob.at<double>(oFl);
+			rc = launchTwoFactorTma(m, T, paths, blob.at<const double*>(oInc), (double* const*)blob.at<double*>(oRows));
+		} else {
+			const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * 8, (paths + 255) / 256));
+			eulerHullWhiteKernel<<<grid, 256, 0, c.stream>>>(T, paths, blob.at<double>(oDt), blob.at<double>(oC0), blob.at<double>(oC1), blob.at<double>(oFl),
+			                                                blob.at<const double*>(oInc), (double* const*)blob.at<double*>(oRows));
+		}
+		if (rc == FMB_OK) rc = launchCheck("euler_hull_white");
 	}
 	if (rc == FMB_OK) {
 		out[0] = out[1] = 0;

@@ -325,12 +325,32 @@ static const int BM_HEADER = 16;                 // bytes in front of the ring (
 
 // Tail draws (|u - 0.5| > 0.425, 15 % of all) cost ~3x a central draw (log, sqrt, a second rational) and would make
 // almost every warp execute both branches.  They are parked in a shared-memory queue and evaluated by full warps.
-template <int NT> __device__ __forceinline__ void bmDrainTails(const double* __restrict__ qP, const uint32_t* __restrict__ qSlot, uint32_t count,
-		double* __restrict__ tile, int tid) {
+template <int NT, bool SCALED> __device__ __forceinline__ void bmDrainTails(const double* __restrict__ qP, const uint32_t* __restrict__ qSlot, uint32_t count,
+		double* __restrict__ tile, int tid, float invPad, const double* __restrict__ sqrtDtPerColumn) {
 	for (uint32_t i = tid; i < count; i += NT) {
 		const double p = qP[i];
-		tile[qSlot[i]] = as241Tail(p, p - 0.5);
+		const uint32_t slot = qSlot[i];
+		double v = as241Tail(p, p - 0.5);
+		if (SCALED) {
+			// column of the slot = slot / nPad; slot < 2^22, so (slot + 0.5) / nPad truncated in single precision is exact
+			const uint32_t c = __float2uint_rz(((float)slot + 0.5f) * invPad);
+			v = v * __ldg(sqrtDtPerColumn + c);
+		}
+		tile[slot] = v;
 	}
+}
+
+// ---- TMA (bulk asynchronous copy engine) helpers: a finished tile row leaves shared memory as ONE bulk store instead of n 8-byte
+//      stores with per-element address arithmetic.  The generic-proxy writes of the tile are made visible to the async proxy with
+//      fence.proxy.async before the barrier that precedes the stores.
+__device__ __forceinline__ void fenceProxyAsyncShared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulkStoreRow(double* gdst, const double* ssrc, uint32_t bytes) {
+	const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(ssrc);
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkCommitAndWaitRead() {
+	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+	asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // next 624 raw words: block nb from block nb-1 (mod RING_BLOCKS).  x[k+624] = x[k+397] ^ twist(x[k], x[k+1]).
@@ -358,8 +378,14 @@ __device__ __forceinline__ void bmRefreshBlock(uint32_t* __restrict__ ring, uint
 	__syncthreads();
 }
 
-template <int NT> __global__ void __launch_bounds__(NT, NT == BM_THREADS ? 2 : 1) bmGenerateKernel(const uint32_t* __restrict__ states, double* __restrict__ out,
-		uint64_t P, uint32_t TF, uint32_t ppb, uint32_t tileN, uint32_t nPad, uint32_t qCap, const double* __restrict__ sqrtDtPerColumn) {
+// TMA: the tile holds the increments already scaled by sqrt(dt) (row stride nPad even: 16-byte aligned rows) and every row is written with
+// one bulk store; needs P, tileN even.  !TMA: standard normals in the tile (odd row stride), scaled and stored element by element.
+template <int NT, bool TMA> __global__ void __launch_bounds__(NT, NT == BM_THREADS ? 2 : 1) bmGenerateKernel(const uint32_t* __restrict__ states, double* __restrict__ out,
+		uint64_t P, uint64_t Pr, uint32_t TF, uint32_t colChunks, uint32_t ppb, uint32_t tileN, uint32_t nPad, uint32_t qCap,
+		const double* __restrict__ sqrtDtPerColumn) {
+	// P paths of TF columns each, row stride of the output Pr (= P).  colChunks > 1 (T*F too large for one path to fit the tile): the
+	// "paths" are column chunks of the real paths - virtual path v = (real path v / colChunks, chunk v % colChunks), TF columns each, in
+	// the same stream order - and Pr is the real number of paths; tiles then hold a single virtual path.
 	extern __shared__ __align__(16) unsigned char smemRaw[];
 	uint32_t* qCountP = reinterpret_cast<uint32_t*>(smemRaw);
 	uint32_t* ring = reinterpret_cast<uint32_t*>(smemRaw + BM_HEADER);
@@ -387,6 +413,7 @@ template <int NT> __global__ void __launch_bounds__(NT, NT == BM_THREADS ? 2 : 1
 	const uint64_t pEnd = min(P, pBeg + (uint64_t)ppb);
 	// (path in tile, column) of this thread's draw, advanced by NT draws per iteration without divisions
 	const uint32_t stepP = NT / TF, stepC = NT % TF;
+	const float invPad = 1.0f / (float)nPad;
 
 	for (uint64_t p0 = pBeg; p0 < pEnd; p0 += tileN) {
 		const uint32_t n = (uint32_t)min((uint64_t)tileN, pEnd - p0);
@@ -407,7 +434,7 @@ template <int NT> __global__ void __launch_bounds__(NT, NT == BM_THREADS ? 2 : 1
 				const double q = u - 0.5;
 				const uint32_t slot = c * nPad + pl;
 				if (fabs(q) <= 0.425) {
-					tile[slot] = as241Central(q);
+					tile[slot] = TMA ? as241Central(q) * __ldg(sqrtDtPerColumn + c) : as241Central(q);
 				} else {
 					const uint32_t k = atomicAdd(qCountP, 1u);
 					qP[k] = u;
@@ -423,7 +450,7 @@ template <int NT> __global__ void __launch_bounds__(NT, NT == BM_THREADS ? 2 : 1
 			if ((++it & (checkEvery - 1u)) == 0) {
 				__syncthreads();
 				if (*qCountP > drainAbove) {
-					bmDrainTails<NT>(qP, qSlot, *qCountP, tile, tid);
+					bmDrainTails<NT, TMA>(qP, qSlot, *qCountP, tile, tid, invPad, sqrtDtPerColumn);
 					__syncthreads();
 					if (tid == 0) *qCountP = 0;
 					__syncthreads();
@@ -431,10 +458,16 @@ template <int NT> __global__ void __launch_bounds__(NT, NT == BM_THREADS ? 2 : 1
 			}
 		}
 		__syncthreads();
-		bmDrainTails<NT>(qP, qSlot, *qCountP, tile, tid);
+		bmDrainTails<NT, TMA>(qP, qSlot, *qCountP, tile, tid, invPad, sqrtDtPerColumn);
+		if (TMA) fenceProxyAsyncShared();
 		__syncthreads();
 		if (tid == 0) *qCountP = 0;
-		if (n >= 32) {
+		if (TMA) {
+			// one bulk store per column: n consecutive paths of column cc, 8n bytes (n even), source row and destination both 16-byte aligned
+			bool issued = false;
+			for (uint32_t cc = tid; cc < TF; cc += NT) { bulkStoreRow(out + (size_t)cc * P + p0, tile + (size_t)cc * nPad, n * 8u); issued = true; }
+			if (issued) bulkCommitAndWaitRead();                  // the tile may be overwritten once the engine has READ it
+		} else if (n >= 32) {
 			double* dst = out + (size_t)warp * P + p0 + lane;
 			const double* srcRow = tile + warp * nPad + lane;
 			for (uint32_t cc = warp; cc < TF; cc += NT / 32) {
@@ -448,8 +481,16 @@ template <int NT> __global__ void __launch_bounds__(NT, NT == BM_THREADS ? 2 : 1
 			// narrow tile (wide T*F): n consecutive paths per column, (column, path) advanced without a division per element
 			uint32_t cc = (uint32_t)tid / n, i = (uint32_t)tid - cc * n;
 			const uint32_t sC = NT / n, sI = NT - sC * n;
+			double* obase = out + p0;
+			const double* sdt = sqrtDtPerColumn;
+			if (colChunks > 1) {                               // (n == 1) columns [kc*TF, (kc+1)*TF) of real path pr
+				const uint64_t pr = p0 / colChunks;
+				const uint32_t kc = (uint32_t)(p0 - pr * colChunks);
+				obase = out + (size_t)kc * TF * Pr + pr;
+				sdt += (size_t)kc * TF;
+			}
 			for (uint32_t idx = tid; idx < U; idx += NT) {
-				out[(size_t)cc * P + p0 + i] = tile[cc * nPad + i] * __ldg(sqrtDtPerColumn + cc);
+				obase[(size_t)cc * Pr + i] = tile[cc * nPad + i] * __ldg(sdt + cc);
 				cc += sC; i += sI;
 				if (i >= n) { i -= n; cc++; }
 			}
@@ -653,12 +694,15 @@ int fmb_bm_generate(int32_t seed, int T, int F, uint64_t paths, uint64_t path_of
 		for (uint64_t i = 0; i < TF; i++) out[i] = newView(empty, (double*)empty->base, 0);
 		return FMB_OK;
 	}
-	if (TF > 24000) { setError("bm_generate: T*F = %llu exceeds the shared-memory tile limit (24000)", (unsigned long long)TF); return FMB_EUNSUPPORTED; }
 
 	// shared memory: header + ring + tail queue + tile [TF][nPad].  Two blocks per SM when a >= 4-path tile fits in half of the 227 KB -
 	// with the full tail queue if possible, else with a half-size one (wide T*F: two 320-thread blocks hide each other's barriers, one
 	// 640-thread block cannot) - else one block with the whole of it.  (Three blocks per SM with smaller tiles measured slower: one more
 	// level of jump-ahead heads costs more than the extra warps give, profiles/r01_notes.md.)
+	// TMA flush (one bulk store per tile row) needs 16-byte aligned rows on both sides: an even number of paths and an even tile
+	// width / row stride.  FMB_BM_TMA=0 forces the element-wise flush (A/B measurements, profiles/r02_notes.md).
+	bool tma = (paths % 2 == 0);
+	if (const char* e = getenv("FMB_BM_TMA")) tma = tma && atoi(e) != 0;
 	uint32_t tileN = 0, qCap = TAILQ;
 	size_t fixed = 0;
 	const size_t budgets[3] = { 112 * 1024, 112 * 1024, 224 * 1024 };
@@ -666,25 +710,41 @@ int fmb_bm_generate(int32_t seed, int T, int F, uint64_t paths, uint64_t path_of
 	for (int attempt = 0; attempt < 3; attempt++) {
 		qCap = queues[attempt];
 		fixed = BM_HEADER + RING_ALLOC * sizeof(uint32_t) + (size_t)qCap * (sizeof(double) + sizeof(uint32_t));
+		fixed = (fixed + 15) & ~(size_t)15;                           // the tile starts 16-byte aligned
 		const size_t avail = budgets[attempt] > fixed ? budgets[attempt] - fixed : 0;
 		const uint64_t maxPad = avail / (TF * sizeof(double));
-		if (maxPad >= 5) { tileN = (uint32_t)std::min<uint64_t>(((maxPad - 1) / 4) * 4, 256); break; }
-		if (attempt == 2) tileN = maxPad >= 2 ? (uint32_t)(maxPad - 1) : (uint32_t)maxPad;
+		if (maxPad >= 6) { tileN = (uint32_t)std::min<uint64_t>(((maxPad - 2) / 4) * 4, 256); break; }
+		if (attempt == 2) tileN = maxPad >= 4 ? (uint32_t)((maxPad - 2) & ~1ull) : (maxPad >= 2 ? (uint32_t)(maxPad - 1) : (uint32_t)maxPad);
 	}
-	if (tileN == 0) { setError("bm_generate: tile does not fit shared memory"); return FMB_EUNSUPPORTED; }
-	const uint32_t nPad = tileN >= 2 ? (tileN | 1u) : tileN;      // odd row stride: conflict-free 8-byte column writes
-	const size_t smem = fixed + (size_t)TF * nPad * sizeof(double);
+	// T*F so large that not even one path fits the tile: cut every path into colChunks chunks of TFk columns (a divisor of T*F that fits) and
+	// run the kernel on these "virtual paths" - the stream order is unchanged, only the flush addresses differ
+	uint64_t TFk = TF, colChunks = 1;
+	if (tileN == 0) {
+		const uint64_t cap = (224 * 1024 - fixed) / sizeof(double);
+		for (uint64_t d = 2; d <= TF / 512 && colChunks == 1; d++) if (TF % d == 0 && TF / d <= cap) colChunks = d;
+		if (colChunks == 1) { setError("bm_generate: T*F = %llu has no divisor between 512 and %llu to cut the paths into tile-sized column chunks", (unsigned long long)TF, (unsigned long long)cap); return FMB_EUNSUPPORTED; }
+		TFk = TF / colChunks;
+		tileN = 1;
+		tma = false;
+	}
+	if (tileN % 2) tma = false;
+	// row stride: TMA: even, and = 2 (mod 8) doubles so that consecutive columns start 4 banks apart (a warp writes 32 consecutive
+	// columns of one path: 4-way instead of 16-way conflicts); element-wise flush: odd (conflict-free column writes)
+	uint32_t nPad = tileN >= 2 ? (tileN | 1u) : tileN;
+	if (tma) nPad = tileN + 2;
+	const size_t smem = fixed + (size_t)TFk * nPad * sizeof(double);
+	const uint64_t vpaths = paths * colChunks;                    // (virtual) paths the kernel iterates over
 
 	// sub-streams: enough blocks to fill the machine, but at least ~32k uniforms each so that jump-ahead stays a small fraction
 	const int blocksPerSm = smem <= 113 * 1024 ? 2 : 1;
 	uint64_t Bmax = (uint64_t)c.smCount * blocksPerSm;            // one wave of equal sub-streams
 	const uint64_t totalUniforms = paths * TF;
 	Bmax = std::max<uint64_t>(1, std::min<uint64_t>(Bmax, totalUniforms / 32768 + 1));
-	uint64_t ppb = (paths + Bmax - 1) / Bmax;
+	uint64_t ppb = (vpaths + Bmax - 1) / Bmax;
 	ppb = ((ppb + tileN - 1) / tileN) * tileN;
-	const int B = (int)((paths + ppb - 1) / ppb);
+	const int B = (int)((vpaths + ppb - 1) / ppb);
 	if (ppb > 0xffffffffull) { setError("bm_generate: too many paths per block"); return FMB_EUNSUPPORTED; }
-	const uint64_t chunk = ppb * 2ull * TF;
+	const uint64_t chunk = ppb * 2ull * TFk;
 
 	void* heads = nullptr;
 	FMB_TRY(poolAlloc((size_t)B * MT_N * sizeof(uint32_t), &heads));
@@ -708,24 +768,20 @@ int fmb_bm_generate(int32_t seed, int T, int F, uint64_t paths, uint64_t path_of
 	// one CTA per SM only (wide tile): 640 threads, so that the SM still has 20 resident warps
 	const bool wide = blocksPerSm == 1;
 	if (rc == FMB_OK) {
-		static size_t attrSmem[2] = {0, 0};
-		if (smem > attrSmem[wide ? 1 : 0]) {
-			cudaError_t e = wide ? cudaFuncSetAttribute(bmGenerateKernel<BM_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-			                     : cudaFuncSetAttribute(bmGenerateKernel<BM_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			if (e != cudaSuccess) { setError("bm_generate: %s", cudaGetErrorString(e)); rc = FMB_ECUDA; }
-			attrSmem[wide ? 1 : 0] = smem;
-		}
-	}
-	if (rc == FMB_OK) {
-		if (wide)
-			bmGenerateKernel<BM_THREADS_WIDE><<<B, BM_THREADS_WIDE, smem, c.stream>>>((const uint32_t*)heads, (double*)slab->base, paths, (uint32_t)TF,
-			                                                                      (uint32_t)ppb, tileN, nPad, qCap, (const double*)dsq);
-		else
-			bmGenerateKernel<BM_THREADS><<<B, BM_THREADS, smem, c.stream>>>((const uint32_t*)heads, (double*)slab->base, paths, (uint32_t)TF,
-			                                                          (uint32_t)ppb, tileN, nPad, qCap, (const double*)dsq);
-		countLaunch();
-		cudaError_t e = cudaGetLastError();
-		if (e != cudaSuccess) { setError("bm_generate launch: %s", cudaGetErrorString(e)); rc = FMB_ECUDA; }
+		auto launch = [&](auto kernel, int NT, int slot) -> int {
+			static size_t attrSmem[4] = {0, 0, 0, 0};
+			if (smem > attrSmem[slot]) {
+				FMB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+				attrSmem[slot] = smem;
+			}
+			kernel<<<B, NT, smem, c.stream>>>((const uint32_t*)heads, (double*)slab->base, vpaths, paths, (uint32_t)TFk, (uint32_t)colChunks, (uint32_t)ppb, tileN, nPad, qCap,
+			                                  (const double*)dsq);
+			countLaunch();
+			FMB_CUDA(cudaGetLastError());
+			return FMB_OK;
+		};
+		if (wide) rc = tma ? launch(bmGenerateKernel<BM_THREADS_WIDE, true>, BM_THREADS_WIDE, 0) : launch(bmGenerateKernel<BM_THREADS_WIDE, false>, BM_THREADS_WIDE, 1);
+		else rc = tma ? launch(bmGenerateKernel<BM_THREADS, true>, BM_THREADS, 2) : launch(bmGenerateKernel<BM_THREADS, false>, BM_THREADS, 3);
 	}
 	if (rc == FMB_OK) {
 		for (uint64_t i = 0; i < TF; i++) out[i] = newView(slab, (double*)slab->base + i * paths, paths);

@@ -1,0 +1,95 @@
+"""A/B timings of round-2 kernel variants on one B200 (device events on the library's stream, best of 3):
+Brownian generation with the element-wise flush vs the bulk-store (TMA) flush, Heston / Hull-White Euler with plain loads vs the
+bulk-copy + mbarrier pipeline.  Environment switches FMB_BM_TMA / FMB_EULER_TMA are read per call.
+
+    python profiles/tools/ab_kernels.py [c4] [c3] [c2]
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+
+pkg = graft.load_package()
+nv = pkg.native
+nv.init(0)
+
+
+def best(fn, reps=3):
+    fn()
+    nv.synchronize()
+    ms = []
+    for _ in range(reps):
+        nv.timer_start()
+        fn()
+        ms.append(nv.timer_stop_ms())
+    return min(ms)
+
+
+def bm_only(T, dt, F, P):
+    td = pkg.TimeDiscretizationFromArray(0.0, T, dt)
+
+    def run():
+        bm = pkg.BrownianMotionCuda(td, F, P, 3141)
+        bm.getBrownianIncrement(0, 0)
+    return run
+
+
+def main():
+    which = sys.argv[1:] or ["c4", "c3", "c2"]
+    out = []
+    if "c4" in which:
+        for tma in ("0", "1"):
+            os.environ["FMB_BM_TMA"] = tma
+            ms = best(bm_only(40, 0.5, 3, 4_000_000))
+            out.append({"what": "Brownian generation C4 (4M paths x 40 x 3)", "FMB_BM_TMA": tma, "ms": ms, "GBps": 4e6 * 120 * 8 / ms / 1e6})
+    if "c3" in which:
+        P = 2_000_000
+        for tma in ("0", "1"):
+            os.environ["FMB_BM_TMA"] = tma
+            ms = best(bm_only(1000, 0.005, 2, P), reps=2)
+            out.append({"what": "Brownian generation C3 shape (2M paths x 1000 x 2)", "FMB_BM_TMA": tma, "ms": ms, "GBps": P * 2000 * 8 / ms / 1e6})
+        os.environ["FMB_BM_TMA"] = "1"
+        td = pkg.TimeDiscretizationFromArray(0.0, 1000, 0.005)
+        bm = pkg.BrownianMotionCuda(td, 2, P, 31415)
+        bm.getBrownianIncrement(0, 0)
+        model = pkg.HestonModel(1.0, 0.05, 0.3, 0.05, 0.09, 0.1, 0.5, 0.1, 1, bm.randomVariableFactory)
+        for tma in ("0", "1"):
+            os.environ["FMB_EULER_TMA"] = tma
+
+            def run():
+                pkg.EulerSchemeFromProcessModel(model, bm).getProcessValue(1000, 0)
+            ms = best(run, reps=2)
+            out.append({"what": "Heston Euler kernel (2M paths x 1000)", "FMB_EULER_TMA": tma, "ms": ms, "GBps": P * 1000 * 32 / ms / 1e6})
+        del bm
+        nv.load().fmb_pool_trim()
+    if "c2" in which:
+        P = 4_000_000
+        td = pkg.TimeDiscretizationFromArray(0.0, 200, 0.1)
+        vt = np.arange(0, 21.0)
+        vm = pkg.ShortRateVolatilityModelAsGiven(pkg.TimeDiscretizationFromArray(vt), 0.005 + 0.0005 * np.floor(vt) / 20, np.full(vt.size, 0.1))
+        bm = pkg.BrownianMotionCuda(td, 2, P, 3141)
+        bm.getBrownianIncrement(0, 0)
+        hw = pkg.HullWhiteModel(bm.randomVariableFactory, pkg.TimeDiscretizationFromArray(0.0, 40, 0.5), vm)
+        pkg.EulerSchemeFromProcessModel(hw, bm, 0).getProcessValue(200, 1)          # host-side coefficient tables built once
+        for tma in ("0", "1"):
+            os.environ["FMB_EULER_TMA"] = tma
+            best_ms = 1e9
+            for _ in range(3):
+                proc = pkg.EulerSchemeFromProcessModel(hw, bm, 0)
+                spec = hw.getFusedSpecification(proc)                                   # (host work outside the timed region)
+                nv.synchronize()
+                nv.timer_start()
+                proc._precalculate_fused(spec)
+                best_ms = min(best_ms, nv.timer_stop_ms())
+            out.append({"what": "Hull-White Euler kernel (4M paths x 200)", "FMB_EULER_TMA": tma, "ms": best_ms, "GBps": P * 200 * 32 / best_ms / 1e6})
+    for o in out:
+        print(json.dumps(o), flush=True)
+
+
+if __name__ == "__main__":
+    main()

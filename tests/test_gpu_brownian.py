@@ -49,10 +49,14 @@ def test_icdf_device_matches_oracle(gpu, orc):
 
 
 @pytest.mark.parametrize("T,F,P,off", [(7, 3, 1000, 0), (100, 1, 5000, 0), (40, 3, 4097, 0), (5, 2, 1, 0), (5, 2, 3, 0), (3, 1, 131, 0),
-                                       (1000, 2, 37, 0), (40, 3, 2500, 1234), (13, 4, 777, 10_000_000)])
+                                       (1000, 2, 37, 0), (40, 3, 2500, 1234), (13, 4, 777, 10_000_000),
+                                       # bulk-store (TMA) flush: even path counts, full and ragged last tiles, narrow tiles (T*F = 2000: 4-path rows)
+                                       (40, 3, 20_000, 0), (40, 3, 1002, 6), (1000, 2, 1000, 0), (1000, 2, 38, 2), (3, 2, 2, 0),
+                                       # T*F beyond one path per tile (13 000 columns: 1-path tiles; 30 000: column chunks of the paths, no cap)
+                                       (6500, 2, 6, 0), (15000, 2, 5, 1), (10000, 3, 4, 0)])
 def test_brownian_increments_match_oracle(gpu, orc, T, F, P, off):
     nv = gpu.native
-    td = gpu.TimeDiscretizationFromArray(0.0, T, 0.1 if T != 1000 else 0.005)
+    td = gpu.TimeDiscretizationFromArray(0.0, T, 0.1 if T < 1000 else 0.005)
     sq = np.sqrt(np.diff(td.times))
     out = np.zeros(T * F, dtype=np.uint64)
     nv.check(nv.load().fmb_bm_generate(3141, T, F, P, off, nv.dptr(sq), nv.hptr(out)))
