@@ -225,6 +225,8 @@ class LIBORMarketModelFromCovarianceModel:
         self.measure = {"SPOT": 0, "TERMINAL": 1}[properties.get("measure", "SPOT")]                 # defaults :186-194
         self.stateSpace = {"NORMAL": 0, "LOGNORMAL": 1}[properties.get("stateSpace", "LOGNORMAL")]
         self.liborCap = float(properties.get("liborCap", 1e5))
+        self.interpolationMethod = properties.get("interpolationMethod", "LOG_LINEAR_UNCORRECTED")    # :186-194
+        self.forwardCurve = properties.get("forwardCurve")   # optional callable time -> forward (host-side curve input); default: L0 by tenor period
         self._tables = factorLoadingTable
         self._numeraires, self._numeraireDiscountFactors, self._numerairesProcess = {}, {}, None
         self._numerairesAdjusted = {}
@@ -356,7 +358,42 @@ class LIBORMarketModelFromCovarianceModel:
     def getLIBOR(self, process, timeIndex, liborIndex):
         return process.getProcessValue(timeIndex, liborIndex)
 
-    def getForwardRate(self, process, time, periodStart, periodEnd):                 # :1237-1305 (tenor-grid periods)
+    def getForwardRateCurveForward(self, time):
+        """getForwardRateCurve().getForward(model, time, paymentOffset) (:1374-1375).  The forward curve is a host-side input given on the
+        tenor grid (the curve classes are outside the path): between grid points the forward of the tenor period containing `time` is
+        used — for a flat curve, every configuration here, exactly what the reference's ForwardCurveInterpolation returns."""
+        if self.forwardCurve is not None:
+            return float(self.forwardCurve(time))
+        i = self.tenor.getTimeIndex(time)
+        if i < 0:
+            i = -i - 2
+        return float(self.L0[max(0, min(i, self.getNumberOfComponents() - 1))])
+
+    def _onePlusInterpolatedLIBORDt(self, process, timeIndex, periodStartTime, liborPeriodIndex):      # :1324-1395
+        tenorPeriodStartTime, tenorPeriodEndTime = self.getLiborPeriod(liborPeriodIndex), self.getLiborPeriod(liborPeriodIndex + 1)
+        tenorDt = tenorPeriodEndTime - tenorPeriodStartTime
+        if tenorPeriodStartTime < process.getTime(timeIndex):
+            timeIndex = min(timeIndex, process.getTimeIndex(tenorPeriodStartTime))       # fixed at the long period's start
+            if timeIndex < 0:
+                raise ValueError("Tenor discretization not part of time discretization.")
+        onePlusLongLIBORDt = self.getLIBOR(process, timeIndex, liborPeriodIndex).mult(tenorDt).add(1.0)
+        smallDt = tenorPeriodEndTime - periodStartTime
+        alpha = smallDt / tenorDt
+        if self.interpolationMethod == "LINEAR":
+            onePlusInterpolatedLIBORDt = onePlusLongLIBORDt.mult(alpha).add(1 - alpha)
+        elif self.interpolationMethod == "LOG_LINEAR_UNCORRECTED":
+            onePlusInterpolatedLIBORDt = onePlusLongLIBORDt.log().mult(alpha).exp()
+        else:
+            raise NotImplementedError("interpolation method %s (drift-adjusted log-linear interpolation) is outside the hot path" % self.interpolationMethod)
+        analyticOnePlusLongLIBORDt = 1 + self.getForwardRateCurveForward(tenorPeriodStartTime) * tenorDt
+        analyticOnePlusShortLIBORDt = 1 + self.getForwardRateCurveForward(periodStartTime) * smallDt
+        if self.interpolationMethod == "LINEAR":
+            analyticOnePlusInterpolatedLIBORDt = analyticOnePlusLongLIBORDt * alpha + (1 - alpha)
+        else:
+            analyticOnePlusInterpolatedLIBORDt = math.exp(math.log(analyticOnePlusLongLIBORDt) * alpha)
+        return onePlusInterpolatedLIBORDt.mult(analyticOnePlusShortLIBORDt / analyticOnePlusInterpolatedLIBORDt)
+
+    def getForwardRate(self, process, time, periodStart, periodEnd):                 # :1237-1305
         ps, pe = self.getLiborPeriodIndex(periodStart), self.getLiborPeriodIndex(periodEnd)
         time = min(time, periodStart)
         ti = process.getTimeIndex(time)
@@ -364,8 +401,22 @@ class LIBORMarketModelFromCovarianceModel:
             ti = -ti - 2
             if time - process.getTime(ti) > process.getTime(ti + 1) - time:           # ROUND_NEAREST
                 ti += 1
-        if ps < 0 or pe < 0:
-            raise NotImplementedError("forward rates off the tenor grid (tenor interpolation) are outside the hot path")
+        if pe < 0:                                           # period end between tenor points (:1257-1264)
+            previousEndIndex = (-pe - 1) - 1
+            nextEndTime = self.getLiborPeriod(previousEndIndex + 1)
+            onePlusLongLIBORdt = self.getForwardRate(process, time, periodStart, nextEndTime).mult(nextEndTime - periodStart).add(1.0)
+            onePlusInterpolatedLIBORDt = self._onePlusInterpolatedLIBORDt(process, ti, periodEnd, previousEndIndex)
+            return onePlusLongLIBORdt.div(onePlusInterpolatedLIBORDt).sub(1.0).div(periodEnd - periodStart)
+        if ps < 0:                                           # period start between tenor points (:1267-1279)
+            previousStartIndex = (-ps - 1) - 1
+            nextStartTime = self.getLiborPeriod(previousStartIndex + 1)
+            if nextStartTime > periodEnd:
+                raise AssertionError("Interpolation not possible.")
+            if nextStartTime == periodEnd:
+                return self._onePlusInterpolatedLIBORDt(process, ti, periodStart, previousStartIndex).sub(1.0).div(periodEnd - periodStart)
+            onePlusLongLIBORdt = self.getForwardRate(process, time, nextStartTime, periodEnd).mult(periodEnd - nextStartTime).add(1.0)
+            onePlusInterpolatedLIBORDt = self._onePlusInterpolatedLIBORDt(process, ti, periodStart, previousStartIndex)
+            return onePlusLongLIBORdt.mult(onePlusInterpolatedLIBORDt).sub(1.0).div(periodEnd - periodStart)
         if ps + 1 == pe:
             return self.getLIBOR(process, ti, ps)
         acc = None
@@ -405,11 +456,33 @@ class LIBORMarketModelFromCovarianceModel:
             self._numeraires[li] = n
         return n
 
-    def _numeraire_unadjusted(self, process, time):
+    def _numeraire_unadjusted(self, process, time):          # :962-1015
         li = self.getLiborPeriodIndex(time)
-        if li < 0:
-            raise NotImplementedError("numeraire off the tenor grid is outside the hot path")
+        if li < 0:                                           # between tenor points (:969-1006)
+            upperIndex = -li - 1
+            lowerIndex = upperIndex - 1
+            if lowerIndex < 0:
+                raise ValueError("Numeraire requested for time %r. Unsupported" % time)
+            if self.measure == self.TERMINAL:
+                n = self.getRandomVariableForConstant(1.0)
+                for k in range(upperIndex, self.tenor.getNumberOfTimeSteps()):
+                    libor = self.getLIBOR(process, process.getTimeIndex(min(time, self.tenor.getTime(k))), k)
+                    n = n.discount(libor, self.tenor.getTimeStep(k))
+            else:
+                n = self._numeraire_unadjusted(process, self.getLiborPeriod(upperIndex))
+            # multiply with the short period bond
+            return n.discount(self.getForwardRate(process, time, time, self.getLiborPeriod(upperIndex)), self.getLiborPeriod(upperIndex) - time)
         return self._numeraire_unadjusted_at(process, li)
+
+    def _defaultable_zero_bond_at(self, process, time):      # :886-905: log-linear interpolation of the adjustment between tenor points
+        ti = self.tenor.getTimeIndex(time)
+        if ti >= 0:
+            return self._defaultable_zero_bond(process, ti)
+        timeIndexPrev = min(-ti - 2, self.tenor.getNumberOfTimes() - 2)
+        timeIndexNext = timeIndexPrev + 1
+        timePrev, timeNext = self.tenor.getTime(timeIndexPrev), self.tenor.getTime(timeIndexNext)
+        prev, nxt = self._defaultable_zero_bond(process, timeIndexPrev), self._defaultable_zero_bond(process, timeIndexNext)
+        return prev.mult(nxt.div(prev).pow((time - timePrev) / (timeNext - timePrev)))
 
     def _defaultable_zero_bond(self, process, timeIndex):                              # :915-944
         self._ensure_cache(process)
@@ -434,10 +507,7 @@ class LIBORMarketModelFromCovarianceModel:
             cached = self._numerairesAdjusted.get(time)
             if cached is not None:
                 return cached
-            ti = self.tenor.getTimeIndex(time)
-            if ti < 0:
-                raise NotImplementedError("numeraire adjustment off the tenor grid is outside the hot path")
-            dz = self._defaultable_zero_bond(process, ti)
+            dz = self._defaultable_zero_bond_at(process, time)
             nonDefaultableZeroBond = n.invert().mult(self._numeraire_unadjusted(process, 0.0)).getAverage()
             n = n.mult(nonDefaultableZeroBond).div(dz)
             self._numerairesAdjusted[time] = n
@@ -714,8 +784,11 @@ class HullWhiteModel:
         if time == process.getTime(0):
             return self.getRandomVariableForConstant(1.0)
         ti = process.getTimeIndex(time)
-        if ti < 0:
-            raise NotImplementedError("Hull-White numeraire off the simulation grid (log-linear interpolation) is outside the hot path")
+        if ti < 0:                                           # between simulation times: log-linear interpolation (:317-333)
+            previousTimeIndex = (-ti - 1) - 1
+            previousTime, nextTime = process.getTime(previousTimeIndex), process.getTime(previousTimeIndex + 1)
+            return self.getNumeraire(process, previousTime).log().mult(nextTime - time) \
+                .add(self.getNumeraire(process, nextTime).log().mult(time - previousTime)).div(nextTime - previousTime).exp()
         numeraireNormalized = process.getProcessValue(ti, 1).add(self.getV(0, time).mult(0.5)).exp()
         numeraireNormalized = numeraireNormalized.mult(numeraireNormalized.invert().getAverage())   # control variate on the zero bond
         fromForward = self._df_from_forward_curve(time)

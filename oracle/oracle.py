@@ -217,6 +217,10 @@ class LMM:
         lib().orc_lmm_brownian(self.h, out.ctypes.data_as(c_dp))
         return out
 
+    def set_interpolation(self, method):
+        """0 LINEAR, 1 LOG_LINEAR_UNCORRECTED (default) — interpolation of forward rates on fractional tenor points."""
+        lib().orc_lmm_set_interpolation(self.h, C.c_int(method))
+
     def numeraire(self, time):
         out = np.empty(self.paths)
         lib().orc_lmm_numeraire(self.h, C.c_double(time), out.ctypes.data_as(c_dp))

@@ -195,6 +195,7 @@ void orc_lmm_brownian(void* hv, double* out /* [T][F][P] */) {
 	for (int t = 0; t < T; t++) for (int f = 0; f < h->bm->F; f++)
 		std::memcpy(out + ((size_t)t * h->bm->F + f) * h->bm->paths, h->bm->inc[t][f]->r.data(), sizeof(double) * h->bm->paths);
 }
+void orc_lmm_set_interpolation(void* hv, int method) { ((LmmHandle*)hv)->model.interpolationMethod = method; }
 void orc_lmm_numeraire(void* hv, double time, double* out) {
 	auto* h = (LmmHandle*)hv;
 	store(h->sim.getNumeraire(time), out, h->bm->paths);

@@ -252,7 +252,39 @@ struct LIBORMarketModel : ProcessModel {
 
 	P getLIBOR(Process& p, int timeIndex, int liborIndex) { return p.getProcessValue(timeIndex, liborIndex); }
 
-	// :1237-1305, tenor-grid periods only (the configs never leave the grid)
+	// Interpolation of forward rates on fractional tenor points (:1244-1281, :1324-1395).  interpolationMethod: 0 LINEAR,
+	// 1 LOG_LINEAR_UNCORRECTED (the default, :186-194); LOG_LINEAR_CORRECTED is not restated.
+	int interpolationMethod = 1;
+	// getForwardRateCurve().getForward(model, time, paymentOffset): the curve is a host-side input given on the tenor grid (the curve
+	// classes are outside the path); between grid points the forward of the tenor period containing `time` is used -
+	// for a flat curve (every configuration here) that is what the reference's ForwardCurveInterpolation returns as well.
+	double analyticForward(double time) const {
+		int i = tenor.getTimeIndex(time);
+		if (i < 0) i = -i - 2;
+		i = std::max(0, std::min(i, getNumberOfComponents() - 1));
+		return L0[i];
+	}
+	P getOnePlusInterpolatedLIBORDt(Process& p, int timeIndex, double periodStartTime, int liborPeriodIndex) {     // :1324-1395
+		const double tenorPeriodStartTime = getLiborPeriod(liborPeriodIndex), tenorPeriodEndTime = getLiborPeriod(liborPeriodIndex + 1);
+		const double tenorDt = tenorPeriodEndTime - tenorPeriodStartTime;
+		if (tenorPeriodStartTime < p.getTime(timeIndex)) {
+			timeIndex = std::min(timeIndex, p.getTimeIndex(tenorPeriodStartTime));
+			if (timeIndex < 0) throw std::invalid_argument("Tenor discretization not part of time discretization.");
+		}
+		P onePlusLongLIBORDt = add(mult(getLIBOR(p, timeIndex, liborPeriodIndex), tenorDt), 1.0);
+		const double smallDt = tenorPeriodEndTime - periodStartTime;
+		const double alpha = smallDt / tenorDt;
+		P onePlusInterpolatedLIBORDt;
+		if (interpolationMethod == 0) onePlusInterpolatedLIBORDt = add(mult(onePlusLongLIBORDt, alpha), 1 - alpha);
+		else if (interpolationMethod == 1) onePlusInterpolatedLIBORDt = exp(mult(log(onePlusLongLIBORDt), alpha));
+		else throw std::runtime_error("oracle: LOG_LINEAR_CORRECTED interpolation not restated");
+		const double analyticOnePlusLongLIBORDt = 1 + analyticForward(tenorPeriodStartTime) * tenorDt;
+		const double analyticOnePlusShortLIBORDt = 1 + analyticForward(periodStartTime) * smallDt;
+		const double analyticOnePlusInterpolatedLIBORDt = interpolationMethod == 0 ? analyticOnePlusLongLIBORDt * alpha + (1 - alpha)
+		                                                                           : std::exp(std::log(analyticOnePlusLongLIBORDt) * alpha);
+		return mult(onePlusInterpolatedLIBORDt, analyticOnePlusShortLIBORDt / analyticOnePlusInterpolatedLIBORDt);
+	}
+	// :1237-1305
 	P getForwardRate(Process& p, double time, double periodStart, double periodEnd) {
 		const int ps = getLiborPeriodIndex(periodStart), pe = getLiborPeriodIndex(periodEnd);
 		time = std::min(time, periodStart);
@@ -261,7 +293,22 @@ struct LIBORMarketModel : ProcessModel {
 			ti = -ti - 2;
 			if (time - p.getTime(ti) > p.getTime(ti + 1) - time) ti++;                        // ROUND_NEAREST
 		}
-		if (ps < 0 || pe < 0) throw std::runtime_error("oracle: tenor interpolation not restated");
+		if (pe < 0) {                                                                         // :1257-1264
+			const int previousEndIndex = (-pe - 1) - 1;
+			const double nextEndTime = getLiborPeriod(previousEndIndex + 1);
+			P onePlusLongLIBORdt = add(mult(getForwardRate(p, time, periodStart, nextEndTime), nextEndTime - periodStart), 1.0);
+			P onePlusInterpolatedLIBORDt = getOnePlusInterpolatedLIBORDt(p, ti, periodEnd, previousEndIndex);
+			return div(orc::sub(div(onePlusLongLIBORdt, onePlusInterpolatedLIBORDt), 1.0), periodEnd - periodStart);
+		}
+		if (ps < 0) {                                                                         // :1267-1279
+			const int previousStartIndex = (-ps - 1) - 1;
+			const double nextStartTime = getLiborPeriod(previousStartIndex + 1);
+			if (nextStartTime > periodEnd) throw std::runtime_error("Interpolation not possible.");
+			if (nextStartTime == periodEnd) return div(orc::sub(getOnePlusInterpolatedLIBORDt(p, ti, periodStart, previousStartIndex), 1.0), periodEnd - periodStart);
+			P onePlusLongLIBORdt = add(mult(getForwardRate(p, time, nextStartTime, periodEnd), periodEnd - nextStartTime), 1.0);
+			P onePlusInterpolatedLIBORDt = getOnePlusInterpolatedLIBORDt(p, ti, periodStart, previousStartIndex);
+			return div(orc::sub(mult(onePlusLongLIBORdt, onePlusInterpolatedLIBORDt), 1.0), periodEnd - periodStart);
+		}
 		if (ps + 1 == pe) return getLIBOR(p, ti, ps);
 		P acc;
 		for (int k = ps; k < pe; k++) {
@@ -293,8 +340,26 @@ struct LIBORMarketModel : ProcessModel {
 	}
 	P numeraireUnadjusted(Process& p, double time) {                                        // :962-1015
 		const int li = getLiborPeriodIndex(time);
-		if (li < 0) throw std::runtime_error("oracle: numeraire off the tenor grid not restated");
+		if (li < 0) {                                                                       // :969-1006
+			const int upperIndex = -li - 1, lowerIndex = upperIndex - 1;
+			if (lowerIndex < 0) throw std::invalid_argument("Numeraire requested for a time before the tenor grid. Unsupported");
+			P n;
+			if (measure == TERMINAL) {
+				n = scalar(1.0);
+				for (int k = upperIndex; k <= tenor.getNumberOfTimeSteps() - 1; k++)
+					n = discount(n, getLIBOR(p, p.getTimeIndex(std::min(time, tenor.getTime(k))), k), tenor.getTimeStep(k));
+			} else n = numeraireUnadjusted(p, getLiborPeriod(upperIndex));
+			return discount(n, getForwardRate(p, time, time, getLiborPeriod(upperIndex)), getLiborPeriod(upperIndex) - time);
+		}
 		return numeraireUnadjustedAtIndex(p, li);
+	}
+	P defaultableZeroBondAsOfTimeZeroAt(double time) {                                      // :886-905 (interpolation on the tenor grid)
+		const int timeIndex = tenor.getTimeIndex(time);
+		if (timeIndex >= 0) return defaultableZeroBondAsOfTimeZero(timeIndex);
+		const int timeIndexPrev = std::min(-timeIndex - 2, tenor.getNumberOfTimes() - 2), timeIndexNext = timeIndexPrev + 1;
+		const double timePrev = tenor.getTime(timeIndexPrev), timeNext = tenor.getTime(timeIndexNext);
+		P prev = defaultableZeroBondAsOfTimeZero(timeIndexPrev), next = defaultableZeroBondAsOfTimeZero(timeIndexNext);
+		return mult(prev, pow(div(next, prev), (time - timePrev) / (timeNext - timePrev)));
 	}
 	P defaultableZeroBondAsOfTimeZero(int timeIndex) {                                      // :915-944
 		if (numeraireDiscountFactors.empty()) {
@@ -313,9 +378,7 @@ struct LIBORMarketModel : ProcessModel {
 		if (time < 0) throw std::runtime_error("oracle: numeraire for negative time not restated");
 		P n = numeraireUnadjusted(p, time);
 		if (!discountFactors.empty()) {
-			const int ti = tenor.getTimeIndex(time);
-			if (ti < 0) throw std::runtime_error("oracle: numeraire adjustment off the tenor grid not restated");
-			P dz = defaultableZeroBondAsOfTimeZero(ti);
+			P dz = defaultableZeroBondAsOfTimeZeroAt(time);
 			const double nonDefaultableZeroBond = getAverage(mult(invert(n), numeraireUnadjusted(p, 0.0)));
 			n = div(mult(n, nonDefaultableZeroBond), dz);
 		}
@@ -519,7 +582,12 @@ struct HullWhiteModel : ProcessModel {
 	P getNumeraire(Process& p, double time) {                                                  // :305-357
 		if (time == p.getTime(0)) return scalar(1.0);
 		const int ti = p.getTimeIndex(time);
-		if (ti < 0) throw std::runtime_error("oracle: Hull-White numeraire off the simulation grid not restated");
+		if (ti < 0) {                                                                          // :317-333 log-linear interpolation
+			const int previousTimeIndex = (-ti - 1) - 1;
+			const double previousTime = p.getTime(previousTimeIndex), nextTime = p.getTime(previousTimeIndex + 1);
+			return exp(div(add(mult(log(getNumeraire(p, previousTime)), nextTime - time), mult(log(getNumeraire(p, nextTime)), time - previousTime)),
+			               nextTime - previousTime));
+		}
 		P logNum = add(p.getProcessValue(ti, 1), mult(getV(0, time), 0.5));
 		P n = exp(logNum);
 		n = mult(n, getAverage(invert(n)));

@@ -209,6 +209,57 @@ def test_lmm_numeraire_forward_rate_swaption_caplet(gpu, orc):
     assert abs(caplet.getValue(dev) - ref_c) <= PRICE_TOL * abs(ref_c)
 
 
+@pytest.mark.parametrize("measure,method", [("SPOT", "LOG_LINEAR_UNCORRECTED"), ("SPOT", "LINEAR"), ("TERMINAL", "LOG_LINEAR_UNCORRECTED")])
+def test_lmm_forward_rate_and_numeraire_between_tenor_points(gpu, orc, measure, method):
+    """Interpolation on fractional tenor points: LIBORMarketModelFromCovarianceModel.getForwardRate :1244-1281 with
+    getOnePlusInterpolatedLIBORDt :1324-1395 (LINEAR and the default LOG_LINEAR_UNCORRECTED), the unadjusted numeraire between tenor
+    points :969-1006 and the log-linear interpolation of the discount-curve adjustment :886-905; simulation times off the grid are rounded
+    to the nearest point (:1248-1253)."""
+    paths = 5000
+    s = lmm_setup(gpu)
+    tenor = s["tenor"]
+    s["df"] = np.array([np.exp(-0.035 * tenor.getTime(i)) for i in range(s["N"] + 1)])
+    factory = gpu.RandomVariableCudaFactory()
+    props = {"measure": measure, "stateSpace": "LOGNORMAL", "interpolationMethod": method}
+    model = gpu.LIBORMarketModelFromCovarianceModel.of(s["tenor"], None, s["L0"], s["df"], factory, s["cov"], None, props)
+    dev = gpu.LIBORMonteCarloSimulationFromLIBORModel(gpu.EulerSchemeFromProcessModel(model, gpu.BrownianMotionCuda(s["sim"], s["F"], paths, 3141, factory)))
+    ref = lmm_oracle(orc, s, paths, measure=0 if measure == "SPOT" else 1)
+    ref.set_interpolation(0 if method == "LINEAR" else 1)
+    cases = [(2.0, 2.0, 2.3),            # period end between tenor points
+             (2.0, 2.2, 2.5),            # period start between tenor points, end = the next tenor point
+             (1.5, 2.2, 4.0),            # start between tenor points, several whole periods behind it
+             (3.0, 3.1, 5.3),            # both ends off the grid
+             (2.7, 3.25, 3.75),          # simulation time off the grid too (rounded to the nearest point), half-period shifted LIBOR
+             (4.26, 6.0, 6.4)]
+    for t, a, b in cases:
+        got = dev.getForwardRate(t, a, b).getRealizations()
+        want = ref.forward_rate(t, a, b)
+        assert rel_err(got, want, scale=0.05) < PATH_TOL, (t, a, b)
+    for t in (2.3, 0.7, 7.25, 2.0):
+        assert rel_err(dev.getNumeraire(t).getRealizations(), ref.numeraire(t)) < PATH_TOL, t
+
+
+def test_hull_white_numeraire_between_simulation_times(gpu, orc):
+    """HullWhiteModel.getNumeraire :317-333: log-linear interpolation between the neighbouring simulation times (a caplet paying between
+    two simulation dates needs it)."""
+    paths = 20_000
+    td = gpu.TimeDiscretizationFromArray(0.0, 20, 0.5)
+    tenor = gpu.TimeDiscretizationFromArray(0.0, 40, 0.25)
+    vt = np.arange(0, 11.0)
+    vol, mr = 0.005 + 0.0005 * np.floor(vt) / 20, np.full(vt.size, 0.1)
+    ct = tenor.times
+    df = np.exp(-(0.03 + 0.01 * ct / 40.0) * ct)
+    vm = gpu.ShortRateVolatilityModelAsGiven(gpu.TimeDiscretizationFromArray(vt), vol, mr)
+    bm = gpu.BrownianMotionCuda(td, 2, paths, 3141)
+    model = gpu.HullWhiteModel(bm.randomVariableFactory, tenor, vm, None, df, df)
+    sim = gpu.LIBORMonteCarloSimulationFromLIBORModel(model, gpu.EulerSchemeFromProcessModel(model, bm, 0))
+    price = gpu.Caplet(5.0, 0.25, 0.03).getValue(sim)                       # pays at 5.25, between the simulation times 5.0 and 5.5
+    ref_price, _, ref_num, ref_fr = orc.hull_white_caplet(3141, td.times, paths, vt, vol, mr, ct, df, df, 0, 5.0, 0.25, 0.03)
+    assert rel_err(sim.getNumeraire(5.25).getRealizations(), ref_num) < PATH_TOL
+    assert rel_err(sim.getForwardRate(5.0, 5.0, 5.25).getRealizations(), ref_fr, scale=0.03) < 1e-11
+    assert abs(price - ref_price) <= PRICE_TOL * abs(ref_price)
+
+
 def test_swaption_discounting_adjustment_with_a_separate_discount_curve(gpu, orc):
     """Swaption.java:160-171: with a discount curve that is NOT the one implied by the forward curve every period's value is scaled by
     forwardBondOnForwardCurve / forwardBondOnDiscountCurve.  The oracle gets the adjustments as an explicit array (computed here from
