@@ -373,6 +373,12 @@ int fmb_rv_free(fmb_handle h) {
 	return releaseRef(h);
 }
 
+int fmb_rv_free_many(const fmb_handle* handles, uint64_t count) {
+	if (count && !handles) return FMB_EINVAL;
+	for (uint64_t i = 0; i < count; i++) if (handles[i]) releaseRef(handles[i]);      // unknown handles are skipped, like free() from a cleaner
+	return FMB_OK;
+}
+
 int fmb_pool_stats(uint64_t* bytes_in_use, uint64_t* bytes_cached, uint64_t* live_handles) {
 	Context& c = ctx();
 	std::lock_guard<std::mutex> lk(c.mu);

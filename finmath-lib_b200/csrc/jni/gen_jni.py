@@ -39,6 +39,7 @@ TABLE = [
     ("size", "fmb_rv_size", "long", [("h", "handle")], "(fmb_handle)handle, OUT"),
     ("retain", "fmb_rv_retain", "void", [("h", "handle")], "(fmb_handle)handle"),
     ("free", "fmb_rv_free", "nothrow", [("h", "handle")], "(fmb_handle)handle"),
+    ("freeMany", "fmb_rv_free_many", "void", [("H", "handles")], "(const fmb_handle*)handles_p, (uint64_t)handles_n"),
     ("devicePointer", "fmb_rv_device_ptr", "custom", [("h", "handle")], ""),
     ("poolStats", "fmb_pool_stats", "custom", [], ""),
     ("poolTrim", "fmb_pool_trim", "void", [], ""),

@@ -263,11 +263,10 @@ class _LazyProcessValues:
 
     def __del__(self):
         try:
-            lib = nv.load()
-            for i, h in enumerate(self.handles):
-                h = int(h)
-                if h != 0 and i not in self.owned:
-                    lib.fmb_rv_free(h)                       # one native reference per returned entry (aliases included)
+            hs = self.handles.copy()                         # one native reference per returned entry (aliases included) ...
+            if self.owned:
+                hs[list(self.owned)] = 0                     # ... except those handed to a DeviceVector, which releases its own
+            nv.load().fmb_rv_free_many(nv.hptr(hs), hs.size)
         except Exception:
             pass
 

@@ -11,6 +11,11 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfinmath_b200.so")
 
+try:
+    from . import _fmbfast as _F          # C accelerator of this binding (csrc/host/fmbfast.c): storage types + fast paths of the hot operations
+except ImportError as e:                  # pragma: no cover
+    raise ImportError("finmath_b200: the host accelerator _fmbfast is not built: run `python -c 'import __graft_entry__ as g; g.build()'` (%s)" % e)
+
 FMB_OK, FMB_EINVAL, FMB_ENODEVICE, FMB_ENOMEM, FMB_ECUDA, FMB_EHANDLE, FMB_EUNSUPPORTED = range(7)
 
 # op codes (include/finmath_b200.h)
@@ -60,6 +65,7 @@ PROTOTYPES = {
     "fmb_rv_size": [C.c_uint64, c_hp],
     "fmb_rv_retain": [C.c_uint64],
     "fmb_rv_free": [C.c_uint64],
+    "fmb_rv_free_many": [c_hp, C.c_uint64],
     "fmb_rv_device_ptr": [C.c_uint64, C.POINTER(C.c_void_p)],
     "fmb_pool_stats": [c_hp, c_hp, c_hp],
     "fmb_pool_trim": [],
@@ -109,7 +115,21 @@ def load():
             fn.argtypes = argtypes
             fn.restype = C.c_char_p if name == "fmb_last_error" else C.c_int
         _lib = lib
+        _bind_fast()
     return _lib
+
+
+def _bind_fast():
+    """Hand the accelerator the addresses of the four entry points it calls (the very library ctypes loaded) and the classes it creates."""
+    if _lib is None:
+        return
+    try:
+        from .stochastic import RandomVariableCuda
+    except ImportError:                   # stochastic.py is still being imported: it calls _bind_fast() again when it is done
+        return
+    addr = lambda name: C.cast(getattr(_lib, name), C.c_void_p).value
+    _F.bind(addr("fmb_rv_unary"), addr("fmb_rv_binary"), addr("fmb_rv_ternary"), addr("fmb_rv_free"), check, RandomVariableCuda, DeviceVector)
+    _F.set_lazy_min_n(_lazy_min_n if _lazy else 2 ** 64 - 1)
 
 
 def check(rc):
@@ -148,21 +168,9 @@ def hptr(a):
     return a.ctypes.data_as(c_hp)
 
 
-class DeviceVector:
-    """Owner of one native handle; freed on garbage collection (the Java side uses a Cleaner)."""
-    __slots__ = ("h", "n", "__weakref__")
-
-    def __init__(self, h, n):
-        self.h = int(h)
-        self.n = int(n)
-
-    def __del__(self):
-        h, self.h = self.h, 0
-        if h and _lib is not None:
-            try:
-                _lib.fmb_rv_free(h)
-            except Exception:
-                pass
+class DeviceVector(_F.DV):
+    """Owner of one native handle (h, n live in the C base type); released when the object is collected (the Java side uses a Cleaner)."""
+    __slots__ = ()
 
     @staticmethod
     def upload(values):
@@ -205,6 +213,7 @@ def set_lazy(on, min_n=None):
     _lazy = bool(on)
     if min_n is not None:
         _lazy_min_n = int(min_n)
+    _F.set_lazy_min_n(_lazy_min_n if _lazy else 2 ** 64 - 1)
 
 
 def lazy_enabled():

@@ -303,8 +303,12 @@ class RandomVariableFromDoubleArray(RandomVariable):
         return getattr(gpu, name)
 
 
-class RandomVariableCuda(RandomVariable):
-    """Device-resident RandomVariable, type priority 2."""
+class RandomVariableCuda(nv._F.RV, RandomVariable):
+    """Device-resident RandomVariable, type priority 2.
+
+    The five attributes (time, valueIfNonStochastic, shard, nGlobal, dv) live in the C base type, which also implements the common
+    cases of the hot operations (_fast_unary / _fast_binary / _fast_ternary: stochastic op number, stochastic op stochastic, with the
+    same filtration-time rules as the methods below); they return NotImplemented for everything else and the method carries on."""
 
     def __init__(self, time, value, shard=None, _dv=None, _n=None):
         self.time = float(time)
@@ -415,17 +419,21 @@ class RandomVariableCuda(RandomVariable):
         return t
 
     # ---- unary and rv∘double: :742-1020 -------------------------------------------------------------------------
-    def squared(self): return self._map1(nv.U_SQUARED)
-    def sqrt(self): return self._map1(nv.U_SQRT)
-    def exp(self): return self._map1(nv.U_EXP)
-    def expm1(self): return self._map1(nv.U_EXPM1)
-    def log(self): return self._map1(nv.U_LOG)
-    def sin(self): return self._map1(nv.U_SIN)
-    def cos(self): return self._map1(nv.U_COS)
-    def invert(self): return self._map1(nv.U_INVERT)
-    def abs(self): return self._map1(nv.U_ABS)
-    def isNaN(self): return self._map1(nv.U_ISNAN)
-    def pow(self, exponent): return self._map1(nv.U_POW, exponent)
+    def _map1f(self, op, a=0.0):
+        r = self._fast_unary(op, a)
+        return r if r is not NotImplemented else self._map1(op, a)
+
+    def squared(self): return self._map1f(nv.U_SQUARED)
+    def sqrt(self): return self._map1f(nv.U_SQRT)
+    def exp(self): return self._map1f(nv.U_EXP)
+    def expm1(self): return self._map1f(nv.U_EXPM1)
+    def log(self): return self._map1f(nv.U_LOG)
+    def sin(self): return self._map1f(nv.U_SIN)
+    def cos(self): return self._map1f(nv.U_COS)
+    def invert(self): return self._map1f(nv.U_INVERT)
+    def abs(self): return self._map1f(nv.U_ABS)
+    def isNaN(self): return self._map1f(nv.U_ISNAN)
+    def pow(self, exponent): return self._map1f(nv.U_POW, exponent)
 
     def average(self):                                     # :877-880
         return RandomVariableCuda(NEG_INF, self.getAverage(), self.shard)
@@ -441,6 +449,9 @@ class RandomVariableCuda(RandomVariable):
         return self._new(t, nv.binary(op, self.dv, self.valueIfNonStochastic, ydv, yv))
 
     def add(self, x):
+        r = self._fast_binary(nv.B_ADD, nv.U_ADD, x, True)
+        if r is not NotImplemented:
+            return r
         if _is_number(x):
             return self._map1(nv.U_ADD, x)
         if x.getTypePriority() > 2:
@@ -448,6 +459,9 @@ class RandomVariableCuda(RandomVariable):
         return self._bin(nv.B_ADD, x, lambda a, b: a + b, nv.U_ADD)
 
     def sub(self, x):
+        r = self._fast_binary(nv.B_SUB, nv.U_SUB, x, True)
+        if r is not NotImplemented:
+            return r
         if _is_number(x):
             return self._map1(nv.U_SUB, x)
         if x.getTypePriority() > 2:
@@ -466,6 +480,9 @@ class RandomVariableCuda(RandomVariable):
         return self._new(t, nv.binary(nv.B_SUB, ydv, yv, self.dv, self.valueIfNonStochastic))
 
     def mult(self, x):
+        r = self._fast_binary(nv.B_MULT, nv.U_MULT, x, True)
+        if r is not NotImplemented:
+            return r
         if _is_number(x):
             return self._map1(nv.U_MULT, x)
         if x.getTypePriority() > 2:
@@ -473,6 +490,9 @@ class RandomVariableCuda(RandomVariable):
         return self._bin(nv.B_MULT, x, lambda a, b: a * b, nv.U_MULT)
 
     def div(self, x):
+        r = self._fast_binary(nv.B_DIV, nv.U_DIV, x, False)
+        if r is not NotImplemented:
+            return r
         if _is_number(x):
             return self._map1(nv.U_DIV, x)
         if x.getTypePriority() > 2:
@@ -491,6 +511,9 @@ class RandomVariableCuda(RandomVariable):
         return self._new(t, nv.binary(nv.B_DIV, ydv, yv, self.dv, self.valueIfNonStochastic))
 
     def cap(self, x):
+        r = self._fast_binary(nv.B_CAP, nv.U_CAP, x, False)
+        if r is not NotImplemented:
+            return r
         if _is_number(x):
             return self._map1(nv.U_CAP, x)
         if x.getTypePriority() > 2:
@@ -498,6 +521,9 @@ class RandomVariableCuda(RandomVariable):
         return self._bin(nv.B_CAP, x, _jmin, None)
 
     def floor(self, x):
+        r = self._fast_binary(nv.B_FLOOR, nv.U_FLOOR, x, True)
+        if r is not NotImplemented:
+            return r
         if _is_number(x):
             return self._map1(nv.U_FLOOR, x)
         if x.getTypePriority() > 2:
@@ -506,6 +532,9 @@ class RandomVariableCuda(RandomVariable):
 
     # ---- ternary: :1278-1479 -----------------------------------------------------------------------------------
     def accrue(self, rate, periodLength):
+        r = self._fast_ternary(nv.T_ACCRUE, rate, None, periodLength)
+        if r is not NotImplemented:
+            return r
         if rate.getTypePriority() > 2:
             return rate.mult(periodLength).add(1.0).mult(self)
         rdv, rval = self._operand(rate)
@@ -514,6 +543,9 @@ class RandomVariableCuda(RandomVariable):
         return self._new(self._tmax(rate), nv.ternary(nv.T_ACCRUE, self.dv, self.valueIfNonStochastic, rdv, rval, None, 0.0, periodLength))
 
     def discount(self, rate, periodLength):
+        r = self._fast_ternary(nv.T_DISCOUNT, rate, None, periodLength)
+        if r is not NotImplemented:
+            return r
         if rate.getTypePriority() > 2:
             return rate.mult(periodLength).add(1.0).invert().mult(self)
         rdv, rval = self._operand(rate)
@@ -522,6 +554,9 @@ class RandomVariableCuda(RandomVariable):
         return self._new(self._tmax(rate), nv.ternary(nv.T_DISCOUNT, self.dv, self.valueIfNonStochastic, rdv, rval, None, 0.0, periodLength))
 
     def choose(self, valueIfTriggerNonNegative, valueIfTriggerNegative):
+        r = self._fast_ternary(nv.T_CHOOSE, valueIfTriggerNonNegative, valueIfTriggerNegative, 0.0)
+        if r is not NotImplemented:
+            return r
         if self.dv is None:
             return valueIfTriggerNonNegative if self.valueIfNonStochastic >= 0 else valueIfTriggerNegative
         t = self._tmax(valueIfTriggerNonNegative, valueIfTriggerNegative)
@@ -530,6 +565,9 @@ class RandomVariableCuda(RandomVariable):
         return self._new(t, nv.ternary(nv.T_CHOOSE, self.dv, 0.0, adv, av, bdv, bv))
 
     def addProduct(self, factor1, factor2):
+        r = self._fast_ternary(nv.T_ADD_PRODUCT_D, factor1, None, factor2) if type(factor2) is float else self._fast_ternary(nv.T_ADD_PRODUCT, factor1, factor2, 0.0)
+        if r is not NotImplemented:
+            return r
         if _is_number(factor2):                            # addProduct(RandomVariable, double) :1365-1391
             if factor1.getTypePriority() > 2:
                 return factor1.mult(factor2).add(self)
@@ -757,3 +795,6 @@ class RandomVariableCudaFactory:
 
     def fromDevice(self, time, dv, n=None):
         return RandomVariableCuda(time, None, self.shard, _dv=dv, _n=n)
+
+
+nv._bind_fast()       # (native.load() may have run before this module existed: give the accelerator the class it instantiates)

@@ -63,6 +63,7 @@ int fmb_rv_get(fmb_handle h, uint64_t i, double* out);                    /* get
 int fmb_rv_size(fmb_handle h, uint64_t* n);
 int fmb_rv_retain(fmb_handle h);                                          /* +1 reference (aliased process values) */
 int fmb_rv_free(fmb_handle h);                                            /* -1 reference; memory returns to the pool */
+int fmb_rv_free_many(const fmb_handle* handles, uint64_t count);            /* fmb_rv_free for each (0 entries skipped): one call when a process with thousands of values is collected */
 int fmb_rv_device_ptr(fmb_handle h, void** dptr);                         /* raw device pointer (interop / tests) */
 int fmb_pool_stats(uint64_t* bytes_in_use, uint64_t* bytes_cached, uint64_t* live_handles);
 int fmb_pool_trim(void);                                                  /* release cached blocks to the driver */

@@ -36,6 +36,7 @@ int fmb_rv_get(fmb_handle h, uint64_t i, double* o) { *o = 0; return 0; }
 int fmb_rv_size(fmb_handle h, uint64_t* n) { *n = sz(h); return 0; }
 int fmb_rv_retain(fmb_handle h) { return 0; }
 int fmb_rv_free(fmb_handle h) { return 0; }
+int fmb_rv_free_many(const fmb_handle* h, uint64_t n) { return 0; }
 int fmb_rv_device_ptr(fmb_handle h, void** p) { *p = 0; return 0; }
 int fmb_pool_stats(uint64_t* a, uint64_t* b, uint64_t* c) { if (a) *a = 0; if (b) *b = 0; if (c) *c = 0; return 0; }
 int fmb_pool_trim(void) { return 0; }

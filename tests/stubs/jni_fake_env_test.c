@@ -63,7 +63,7 @@ jint J(deviceCount)(JNIEnv*, jclass); jstring J(deviceName)(JNIEnv*, jclass); vo
 jint J(getFpMode)(JNIEnv*, jclass); void J(timerStart)(JNIEnv*, jclass); jdouble J(timerStopMs)(JNIEnv*, jclass); jlong J(kernelLaunchCount)(JNIEnv*, jclass);
 jlong J(create)(JNIEnv*, jclass, jlong); jlong J(upload)(JNIEnv*, jclass, jdoubleArray); jlong J(fill)(JNIEnv*, jclass, jdouble, jlong);
 jdoubleArray J(download)(JNIEnv*, jclass, jlong); jdouble J(get)(JNIEnv*, jclass, jlong, jlong); jlong J(size)(JNIEnv*, jclass, jlong);
-void J(retain)(JNIEnv*, jclass, jlong); void J(free)(JNIEnv*, jclass, jlong); jlong J(devicePointer)(JNIEnv*, jclass, jlong); jlongArray J(poolStats)(JNIEnv*, jclass);
+void J(retain)(JNIEnv*, jclass, jlong); void J(free)(JNIEnv*, jclass, jlong); void J(freeMany)(JNIEnv*, jclass, jlongArray); jlong J(devicePointer)(JNIEnv*, jclass, jlong); jlongArray J(poolStats)(JNIEnv*, jclass);
 void J(poolTrim)(JNIEnv*, jclass); jlong J(unary)(JNIEnv*, jclass, jint, jlong, jdouble); jlong J(binary)(JNIEnv*, jclass, jint, jlong, jdouble, jlong, jdouble);
 jlong J(ternary)(JNIEnv*, jclass, jint, jlong, jdouble, jlong, jdouble, jlong, jdouble, jdouble); jlong J(evalChain)(JNIEnv*, jclass, jbyteArray, jint, jlongArray, jdoubleArray);
 jdoubleArray J(reduce)(JNIEnv*, jclass, jint, jlong, jlong, jdouble); jlong J(sorted)(JNIEnv*, jclass, jlong); jlongArray J(countLessOrEqual)(JNIEnv*, jclass, jlong, jdoubleArray);
@@ -106,6 +106,7 @@ static void hostOnly(void) {
 	jlongArray st; OK(st = J(poolStats)(env, NULL)); EXPECT(st && st->len == 3, "poolStats");
 	OK(J(free)(env, NULL, 0));                                       /* free(0) and free(unknown) never throw (cleaner threads) */
 	OK(J(free)(env, NULL, 12345));
+	{ const jlong hs[3] = { 0, 12345, 777 }; OK(J(freeMany)(env, NULL, longs(3, hs))); }
 	THROWS(RTE, J(size)(env, NULL, 12345));                          /* unknown handle: FMB_EHANDLE -> RuntimeException */
 	THROWS(RTE, J(retain)(env, NULL, 12345));
 }
