@@ -9,6 +9,7 @@ from . import native
 from .sharding import ShardContext, LOCAL, from_environment
 from .stochastic import (RandomVariable, Scalar, RandomVariableFromDoubleArray, RandomVariableCuda, RandomVariableCudaFactory)
 from .montecarlo import (TimeDiscretizationFromArray, BrownianMotionCuda, BrownianMotionView, CorrelatedBrownianMotion, EulerSchemeFromProcessModel, Scheme,
+                         MersenneTwister, RandomNumberGeneratorFrom1D, IndependentIncrementsFromICDF, BrownianMotionFromRandomNumberGenerator,
                          MonteCarloConditionalExpectationRegression, MonteCarloConditionalExpectationRegressionLocalizedOnDependents,
                          LinearRegression)
 from .models import (BlackScholesModel, HestonModel, MonteCarloAssetModel, MonteCarloBlackScholesModel,

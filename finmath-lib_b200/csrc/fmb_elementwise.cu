@@ -5,6 +5,7 @@
 // multiply followed by a rounded add, as on the JVM.
 #include "fmb_common.cuh"
 #include "fmb_math.cuh"
+#include "fmb_icdf.cuh"
 
 namespace fmb {
 
@@ -41,6 +42,7 @@ template <int OP> __device__ __forceinline__ double unaryOp(double x, double a) 
 	case FMB_U_CAP: return jmin(x, a);
 	case FMB_U_FLOOR: return jmax(x, a);
 	case FMB_U_POW: return pow(x, a);
+	case FMB_U_ICDF_NORMAL: return inverseCumulativeNormal(x);
 	}
 	return x;
 }
@@ -160,6 +162,7 @@ __device__ __forceinline__ double unaryDyn(int op, double x, double a) {
 	case FMB_U_VID: return unaryOp<FMB_U_VID>(x, a);
 	case FMB_U_CAP: return unaryOp<FMB_U_CAP>(x, a);
 	case FMB_U_FLOOR: return unaryOp<FMB_U_FLOOR>(x, a);
+	case FMB_U_ICDF_NORMAL: return unaryOp<FMB_U_ICDF_NORMAL>(x, a);
 	default: return unaryOp<FMB_U_POW>(x, a);
 	}
 }
@@ -283,7 +286,7 @@ int fmb_rv_unary(int opcode, fmb_handle x, double a, fmb_handle* out) {
 	FMB_TRY(requireInit());
 	PinScope pins;
 	if (!out) return FMB_EINVAL;
-	if (opcode < 0 || opcode > FMB_U_POW) { setError("unknown unary op %d", opcode); return FMB_EINVAL; }
+	if (opcode < 0 || opcode > FMB_U_ICDF_NORMAL) { setError("unknown unary op %d", opcode); return FMB_EINVAL; }
 	Context& c = ctx();
 	Vec* vx;
 	FMB_TRY(lookup(x, &vx));
@@ -301,7 +304,7 @@ int fmb_rv_unary(int opcode, fmb_handle x, double a, fmb_handle* out) {
 		LAUNCH_UNARY(FMB_U_SQUARED) LAUNCH_UNARY(FMB_U_SQRT) LAUNCH_UNARY(FMB_U_EXP) LAUNCH_UNARY(FMB_U_LOG) LAUNCH_UNARY(FMB_U_SIN)
 		LAUNCH_UNARY(FMB_U_COS) LAUNCH_UNARY(FMB_U_INVERT) LAUNCH_UNARY(FMB_U_ABS) LAUNCH_UNARY(FMB_U_ISNAN) LAUNCH_UNARY(FMB_U_EXPM1)
 		LAUNCH_UNARY(FMB_U_ADD) LAUNCH_UNARY(FMB_U_SUB) LAUNCH_UNARY(FMB_U_BUS) LAUNCH_UNARY(FMB_U_MULT) LAUNCH_UNARY(FMB_U_DIV)
-		LAUNCH_UNARY(FMB_U_VID) LAUNCH_UNARY(FMB_U_CAP) LAUNCH_UNARY(FMB_U_FLOOR) LAUNCH_UNARY(FMB_U_POW)
+		LAUNCH_UNARY(FMB_U_VID) LAUNCH_UNARY(FMB_U_CAP) LAUNCH_UNARY(FMB_U_FLOOR) LAUNCH_UNARY(FMB_U_POW) LAUNCH_UNARY(FMB_U_ICDF_NORMAL)
 	}
 	return finishLaunch(out);
 }
@@ -395,7 +398,7 @@ int fmb_rv_eval_chain(int n_instr, const unsigned char* code, int start_leaf, co
 		memcpy(&c, code + 8 * k, sizeof(c));
 		bool ok = c.kind <= 2;
 		if (ok && c.kind == 0) {
-			ok = c.op <= FMB_U_POW && (c.refA & 128) && refOk(c.refA);
+			ok = c.op <= FMB_U_ICDF_NORMAL && (c.refA & 128) && refOk(c.refA);
 			// Math.pow(x, 0.5) / Math.pow(x, 2.0) must equal sqrt / x*x bit-for-bit, as in fmb_rv_unary
 			if (ok && c.op == FMB_U_POW && p.scalar[c.refA & 127] == 0.5) c.op = FMB_U_SQRT;
 			else if (ok && c.op == FMB_U_POW && p.scalar[c.refA & 127] == 2.0) c.op = FMB_U_SQUARED;

@@ -380,7 +380,9 @@ __device__ __forceinline__ void bmRefreshBlock(uint32_t* __restrict__ ring, uint
 
 // TMA: the tile holds the increments already scaled by sqrt(dt) (row stride nPad even: 16-byte aligned rows) and every row is written with
 // one bulk store; needs P, tileN even.  !TMA: standard normals in the tile (odd row stride), scaled and stored element by element.
-template <int NT, bool TMA> __global__ void __launch_bounds__(NT, NT == BM_THREADS ? 2 : 1) bmGenerateKernel(const uint32_t* __restrict__ states, double* __restrict__ out,
+// UNIFORM: the tile receives the uniforms themselves (IndependentIncrementsFromICDF: the caller applies its own inverse distribution
+// functions); the host then passes a scale table of ones.
+template <int NT, bool TMA, bool UNIFORM> __global__ void __launch_bounds__(NT, NT == BM_THREADS ? 2 : 1) bmGenerateKernel(const uint32_t* __restrict__ states, double* __restrict__ out,
 		uint64_t P, uint64_t Pr, uint32_t TF, uint32_t colChunks, uint32_t ppb, uint32_t tileN, uint32_t nPad, uint32_t qCap,
 		const double* __restrict__ sqrtDtPerColumn) {
 	// P paths of TF columns each, row stride of the output Pr (= P).  colChunks > 1 (T*F too large for one path to fit the tile): the
@@ -433,7 +435,9 @@ template <int NT, bool TMA> __global__ void __launch_bounds__(NT, NT == BM_THREA
 				const double u = mtUniform(mtTemper(ww.x), mtTemper(ww.y));
 				const double q = u - 0.5;
 				const uint32_t slot = c * nPad + pl;
-				if (fabs(q) <= 0.425) {
+				if (UNIFORM) {
+					tile[slot] = u;
+				} else if (fabs(q) <= 0.425) {
 					tile[slot] = TMA ? as241Central(q) * __ldg(sqrtDtPerColumn + c) : as241Central(q);
 				} else {
 					const uint32_t k = atomicAdd(qCountP, 1u);
@@ -683,9 +687,10 @@ int fmb_icdf(const double* host_p, uint64_t n, double* host_out) {
 	return FMB_OK;
 }
 
-int fmb_bm_generate(int32_t seed, int T, int F, uint64_t paths, uint64_t path_offset, const double* sqrt_dt, fmb_handle* out) {
+// uniform == false: Brownian increments ICDF(u) * sqrt_dt[t];  uniform == true: the uniforms u themselves (sqrt_dt ignored)
+static int generateIncrements(int64_t seed, int T, int F, uint64_t paths, uint64_t path_offset, const double* sqrt_dt, bool uniform, fmb_handle* out) {
 	FMB_TRY(requireInit());
-	if (T <= 0 || F <= 0 || !sqrt_dt || !out) { setError("bm_generate: bad argument"); return FMB_EINVAL; }
+	if (T <= 0 || F <= 0 || (!sqrt_dt && !uniform) || !out) { setError("bm_generate: bad argument"); return FMB_EINVAL; }
 	Context& c = ctx();
 	const uint64_t TF = (uint64_t)T * F;
 	if (paths == 0) {                                           // a rank that owns no paths of the logical simulation: zero-length increments
@@ -748,7 +753,7 @@ int fmb_bm_generate(int32_t seed, int T, int F, uint64_t paths, uint64_t path_of
 
 	void* heads = nullptr;
 	FMB_TRY(poolAlloc((size_t)B * MT_N * sizeof(uint32_t), &heads));
-	int rc = buildStreamHeads((int64_t)seed, path_offset * 2ull * TF, chunk, B, (uint32_t*)heads);
+	int rc = buildStreamHeads(seed, path_offset * 2ull * TF, chunk, B, (uint32_t*)heads);
 
 	Slab* slab = nullptr;
 	void* dsq = nullptr;
@@ -758,7 +763,7 @@ int fmb_bm_generate(int32_t seed, int T, int F, uint64_t paths, uint64_t path_of
 		rc = ensureScratch(TF * sizeof(double), 0);
 		if (rc == FMB_OK) {
 			double* h = (double*)c.pinned;
-			for (int t = 0; t < T; t++) for (int f = 0; f < F; f++) h[(size_t)t * F + f] = sqrt_dt[t];
+			for (int t = 0; t < T; t++) for (int f = 0; f < F; f++) h[(size_t)t * F + f] = uniform ? 1.0 : sqrt_dt[t];
 			cudaError_t e = cudaMemcpyAsync(dsq, h, TF * sizeof(double), cudaMemcpyHostToDevice, c.stream);
 			if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
 			if (e != cudaSuccess) { setError("bm_generate: %s", cudaGetErrorString(e)); rc = FMB_ECUDA; }
@@ -769,7 +774,7 @@ int fmb_bm_generate(int32_t seed, int T, int F, uint64_t paths, uint64_t path_of
 	const bool wide = blocksPerSm == 1;
 	if (rc == FMB_OK) {
 		auto launch = [&](auto kernel, int NT, int slot) -> int {
-			static size_t attrSmem[4] = {0, 0, 0, 0};
+			static size_t attrSmem[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 			if (smem > attrSmem[slot]) {
 				FMB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 				attrSmem[slot] = smem;
@@ -780,8 +785,13 @@ int fmb_bm_generate(int32_t seed, int T, int F, uint64_t paths, uint64_t path_of
 			FMB_CUDA(cudaGetLastError());
 			return FMB_OK;
 		};
-		if (wide) rc = tma ? launch(bmGenerateKernel<BM_THREADS_WIDE, true>, BM_THREADS_WIDE, 0) : launch(bmGenerateKernel<BM_THREADS_WIDE, false>, BM_THREADS_WIDE, 1);
-		else rc = tma ? launch(bmGenerateKernel<BM_THREADS, true>, BM_THREADS, 2) : launch(bmGenerateKernel<BM_THREADS, false>, BM_THREADS, 3);
+		if (uniform) {
+			if (wide) rc = tma ? launch(bmGenerateKernel<BM_THREADS_WIDE, true, true>, BM_THREADS_WIDE, 4) : launch(bmGenerateKernel<BM_THREADS_WIDE, false, true>, BM_THREADS_WIDE, 5);
+			else rc = tma ? launch(bmGenerateKernel<BM_THREADS, true, true>, BM_THREADS, 6) : launch(bmGenerateKernel<BM_THREADS, false, true>, BM_THREADS, 7);
+		} else {
+			if (wide) rc = tma ? launch(bmGenerateKernel<BM_THREADS_WIDE, true, false>, BM_THREADS_WIDE, 0) : launch(bmGenerateKernel<BM_THREADS_WIDE, false, false>, BM_THREADS_WIDE, 1);
+			else rc = tma ? launch(bmGenerateKernel<BM_THREADS, true, false>, BM_THREADS, 2) : launch(bmGenerateKernel<BM_THREADS, false, false>, BM_THREADS, 3);
+		}
 	}
 	if (rc == FMB_OK) {
 		for (uint64_t i = 0; i < TF; i++) out[i] = newView(slab, (double*)slab->base + i * paths, paths);
@@ -792,6 +802,14 @@ int fmb_bm_generate(int32_t seed, int T, int F, uint64_t paths, uint64_t path_of
 	if (dsq) poolFree(dsq, TF * sizeof(double));
 	poolFree(heads, (size_t)B * MT_N * sizeof(uint32_t));
 	return rc;
+}
+
+int fmb_bm_generate(int32_t seed, int T, int F, uint64_t paths, uint64_t path_offset, const double* sqrt_dt, fmb_handle* out) {
+	return generateIncrements((int64_t)seed, T, F, paths, path_offset, sqrt_dt, false, out);
+}
+
+int fmb_uniforms_generate(int64_t seed, int T, int F, uint64_t paths, uint64_t path_offset, fmb_handle* out) {
+	return generateIncrements(seed, T, F, paths, path_offset, nullptr, true, out);
 }
 
 } // extern "C"

@@ -57,6 +57,8 @@ TABLE = [
     ("icdf", "fmb_icdf", "doubles:p_n", [("D", "p")], "p_p, (uint64_t)p_n, OUT"),
     ("brownianGenerate", "fmb_bm_generate", "handles:T * F", [("i", "seed"), ("i", "T"), ("i", "F"), ("l", "paths"), ("l", "pathOffset"), ("D", "sqrtDt")],
      "seed, T, F, (uint64_t)paths, (uint64_t)pathOffset, sqrtDt_p, OUT"),
+    ("uniformsGenerate", "fmb_uniforms_generate", "handles:T * F", [("l", "seed"), ("i", "T"), ("i", "F"), ("l", "paths"), ("l", "pathOffset")],
+     "(int64_t)seed, T, F, (uint64_t)paths, (uint64_t)pathOffset, OUT"),
     ("eulerBlackScholes", "fmb_euler_black_scholes", "handles:T + 1",
      [("i", "scheme"), ("i", "T"), ("i", "F"), ("l", "paths"), ("D", "dt"), ("H", "dW"), ("d", "initialValue"), ("d", "riskFreeRate"), ("d", "volatility")],
      "scheme, T, F, (uint64_t)paths, dt_p, (const fmb_handle*)dW_p, initialValue, riskFreeRate, volatility, OUT"),

@@ -165,6 +165,177 @@ class BrownianMotionCuda:
 
 
 
+class MersenneTwister:
+    """J/randomnumbers/MersenneTwister.java:19-58 — the 1-D generator `new MersenneTwister(long seed)`.  On this backend it is a
+    description of a stream (seed + position); the numbers themselves are produced on the device by jump-ahead."""
+
+    def __init__(self, seed):
+        self.seed = int(seed)
+        self._position = 0                                   # uniforms handed out so far through nextDouble()
+
+    def getDimension(self):
+        return 1
+
+    def nextDouble(self):                                    # sequential host access (tests, small uses): one device round trip per call
+        u = np.empty(1)
+        nv.check(nv.load().fmb_mt_uniforms(self.seed, self._position, 1, nv.dptr(u)))
+        self._position += 1
+        return float(u[0])
+
+    def getNext(self):
+        return [self.nextDouble()]
+
+
+class RandomNumberGeneratorFrom1D:
+    """J/randomnumbers/RandomNumberGeneratorFrom1D.java — `dimension` consecutive draws of a 1-D generator form one vector."""
+
+    def __init__(self, randomNumberGenerator1D, dimension):
+        self.generator, self.dimension = randomNumberGenerator1D, int(dimension)
+
+    def getDimension(self):
+        return self.dimension
+
+    def getNext(self):
+        return [self.generator.nextDouble() for _ in range(self.dimension)]
+
+
+class _IncrementsFromUniforms:
+    """Common part of the two classes below: uniforms U[t][f][path] in the reference's draw order (path -> time -> factor), generated on
+    the device when the source is a MersenneTwister stream (bit-exact with the sequential generator at any path offset, so shards work),
+    taken from the host generator path by path otherwise."""
+
+    def _device_uniforms(self, seed):
+        T, F = self.timeDiscretization.getNumberOfTimeSteps(), self.numberOfFactors
+        lo, hi = self.shard.local_range(self.numberOfPaths)
+        out = np.zeros(T * F, dtype=np.uint64)
+        nv.check(nv.load().fmb_uniforms_generate(int(seed), T, F, hi - lo, lo, nv.hptr(out)))
+        return [[nv.DeviceVector(out[t * F + f], hi - lo) for f in range(F)] for t in range(T)]
+
+    def _host_uniforms(self, generator):
+        T, F, P = self.timeDiscretization.getNumberOfTimeSteps(), self.numberOfFactors, self.numberOfPaths
+        if generator.getDimension() < T * F:
+            raise ValueError("The dimension of the random number generator is smaller than timeSteps * factors.")
+        u = np.empty((P, T * F))
+        for path in range(P):                                # the generator is a host object: sequential by contract (:160-161)
+            u[path] = generator.getNext()[:T * F]
+        lo, hi = self.shard.local_range(P)
+        return [[nv.DeviceVector.upload(u[lo:hi, t * F + f]) for f in range(F)] for t in range(T)]
+
+    def _wrap(self, timeIndex, dv):
+        return self.randomVariableFactory.fromDevice(self.timeDiscretization.getTime(timeIndex + 1), dv, self.numberOfPaths)
+
+    def getTimeDiscretization(self): return self.timeDiscretization
+    def getNumberOfFactors(self): return self.numberOfFactors
+    def getNumberOfPaths(self): return self.numberOfPaths
+    def getRandomVariableForConstant(self, value): return self.randomVariableFactory.createRandomVariable(value)
+
+
+class IndependentIncrementsFromICDF(_IncrementsFromUniforms):
+    """J/montecarlo/IndependentIncrementsFromICDF.java:41-240 — Z_j(t_i) = ICDF_{i,j}(U_{i,j}), uniforms from MersenneTwister(seed) in
+    the order path -> time -> factor (:173-206).  The uniforms are generated on the device.  An inverse distribution function is applied
+    on the device when it accepts a RandomVariable (it is then written with RandomVariable operations, e.g.
+    ``lambda u: u.mult(-1.0).add(1.0).log().mult(-1.0 / lam)``; NORMAL_ICDF is the built-in AS241 transform); a plain double -> double
+    callable is applied on the host (download, map, upload), like `apply(DoubleUnaryOperator)` of the reference type would."""
+
+    @staticmethod
+    def NORMAL_ICDF(u):
+        """NormalDistribution.inverseCumulativeDistribution as a device operation on a RandomVariableCuda."""
+        return u._new(u.time, nv.unary(nv.U_ICDF_NORMAL, u.dv))
+
+    def __init__(self, timeDiscretization, numberOfFactors, numberOfPaths, seed, inverseCumulativeDistributionFunctions, randomVariableFactory=None,
+                 shard=None):
+        self.timeDiscretization, self.numberOfFactors, self.numberOfPaths = timeDiscretization, int(numberOfFactors), int(numberOfPaths)
+        self.seed = int(np.int32(seed))
+        self.inverseCumulativeDistributionFunctions = inverseCumulativeDistributionFunctions
+        self.shard = shard if shard is not None else (randomVariableFactory.shard if randomVariableFactory is not None else LOCAL)
+        self.randomVariableFactory = randomVariableFactory if randomVariableFactory is not None else RandomVariableCudaFactory(self.shard)
+        self._lock = threading.Lock()
+        self._increments = None
+
+    def _generate(self):
+        uniforms = self._device_uniforms(self.seed)
+        T, F = self.timeDiscretization.getNumberOfTimeSteps(), self.numberOfFactors
+        incs = []
+        for t in range(T):
+            row = []
+            for f in range(F):
+                icdf = self.inverseCumulativeDistributionFunctions(t)(f)
+                u = self._wrap(t, uniforms[t][f])
+                try:
+                    z = icdf(u)
+                    if not isinstance(z, RandomVariableCuda):
+                        raise TypeError
+                    z = z if z.time == u.time else z._new(u.time, z.dv)
+                except (TypeError, AttributeError):
+                    values = u.getLocalRealizations()
+                    z = self._wrap(t, nv.DeviceVector.upload(np.array([icdf(float(v)) for v in values], dtype=np.float64)))
+                row.append(z)
+            incs.append(row)
+        self._increments = incs
+
+    def getIncrement(self, timeIndex, factor):
+        with self._lock:
+            if self._increments is None:
+                self._generate()
+        return self._increments[timeIndex][factor]
+
+    def getSeed(self): return self.seed
+
+    def getCloneWithModifiedSeed(self, seed):
+        return IndependentIncrementsFromICDF(self.timeDiscretization, self.numberOfFactors, self.numberOfPaths, seed, self.inverseCumulativeDistributionFunctions,
+                                             self.randomVariableFactory, self.shard)
+
+    def getCloneWithModifiedTimeDiscretization(self, newTimeDiscretization):
+        return IndependentIncrementsFromICDF(newTimeDiscretization, self.numberOfFactors, self.numberOfPaths, self.seed, self.inverseCumulativeDistributionFunctions,
+                                             self.randomVariableFactory, self.shard)
+
+
+class BrownianMotionFromRandomNumberGenerator(_IncrementsFromUniforms):
+    """J/montecarlo/BrownianMotionFromRandomNumberGenerator.java:41-220 — increments ICDF(u_{t*F+f}) * sqrt(dt_t) from the vectors
+    `randomNumberGenerator.getNext()`, one per path (:160-170).  A MersenneTwister-based generator (RandomNumberGeneratorFrom1D over
+    MersenneTwister) never leaves the device: the same jump-ahead stream as BrownianMotionFromMersenneRandomNumbers; any other generator
+    object is asked path by path on the host and its numbers are uploaded; ICDF and scaling always run on the device."""
+
+    def __init__(self, timeDiscretization, numberOfFactors, numberOfPaths, randomNumberGenerator, randomVariableFactory=None, shard=None):
+        self.timeDiscretization, self.numberOfFactors, self.numberOfPaths = timeDiscretization, int(numberOfFactors), int(numberOfPaths)
+        self.randomNumberGenerator = randomNumberGenerator
+        self.shard = shard if shard is not None else (randomVariableFactory.shard if randomVariableFactory is not None else LOCAL)
+        self.randomVariableFactory = randomVariableFactory if randomVariableFactory is not None else RandomVariableCudaFactory(self.shard)
+        self._lock = threading.Lock()
+        self._increments = None
+
+    def _generate(self):
+        g = self.randomNumberGenerator
+        T, F = self.timeDiscretization.getNumberOfTimeSteps(), self.numberOfFactors
+        if isinstance(g, RandomNumberGeneratorFrom1D) and isinstance(g.generator, MersenneTwister) and g.generator._position == 0 and g.getDimension() == T * F:
+            uniforms = self._device_uniforms(g.generator.seed)
+        else:
+            uniforms = self._host_uniforms(g)
+        incs = []
+        for t in range(T):
+            sqrtDeltaT = math.sqrt(self.timeDiscretization.getTimeStep(t))                  # :146-149
+            incs.append([self._wrap(t, nv.unary(nv.U_MULT, nv.unary(nv.U_ICDF_NORMAL, uniforms[t][f]), sqrtDeltaT)) for f in range(F)])
+        self._increments = incs
+
+    def getBrownianIncrement(self, timeIndex, factor):
+        with self._lock:
+            if self._increments is None:
+                self._generate()
+        return self._increments[timeIndex][factor]
+
+    def getIncrement(self, timeIndex, factor=None):
+        if factor is None:
+            return [self.getBrownianIncrement(timeIndex, f) for f in range(self.numberOfFactors)]
+        return self.getBrownianIncrement(timeIndex, factor)
+
+    def getCloneWithModifiedSeed(self, seed):
+        raise NotImplementedError("a clone with a modified seed is not defined for a generic random number generator")    # :206-209 returns null
+
+    def getCloneWithModifiedTimeDiscretization(self, newTimeDiscretization):
+        return BrownianMotionFromRandomNumberGenerator(newTimeDiscretization, self.numberOfFactors, self.numberOfPaths, self.randomNumberGenerator,
+                                                       self.randomVariableFactory, self.shard)
+
+
 class _BrownianMotionDecorator:
     """Shared plumbing of the two wrappers below: they are not BrownianMotionCuda instances, so an Euler scheme on top of them
     runs the generic device loop (one kernel per RandomVariable operation) — the fused kernels need the raw increment slab."""

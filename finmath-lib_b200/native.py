@@ -20,7 +20,7 @@ FMB_OK, FMB_EINVAL, FMB_ENODEVICE, FMB_ENOMEM, FMB_ECUDA, FMB_EHANDLE, FMB_EUNSU
 
 # op codes (include/finmath_b200.h)
 U_SQUARED, U_SQRT, U_EXP, U_LOG, U_SIN, U_COS, U_INVERT, U_ABS, U_ISNAN, U_EXPM1 = range(10)
-U_ADD, U_SUB, U_BUS, U_MULT, U_DIV, U_VID, U_CAP, U_FLOOR, U_POW = range(10, 19)
+U_ADD, U_SUB, U_BUS, U_MULT, U_DIV, U_VID, U_CAP, U_FLOOR, U_POW, U_ICDF_NORMAL = range(10, 20)
 B_ADD, B_SUB, B_MULT, B_DIV, B_CAP, B_FLOOR = range(6)
 T_ADD_PRODUCT, T_ADD_PRODUCT_D, T_ADD_RATIO, T_SUB_RATIO, T_ACCRUE, T_DISCOUNT, T_CHOOSE = range(7)
 R_SUM, R_SUM_PRODUCT, R_CENTERED_M2, R_CENTERED_M2_W, R_MIN, R_MAX = range(6)
@@ -80,6 +80,7 @@ PROTOTYPES = {
     "fmb_mt_uniforms": [C.c_int64, C.c_uint64, C.c_uint64, c_dp],
     "fmb_icdf": [c_dp, C.c_uint64, c_dp],
     "fmb_bm_generate": [C.c_int32, C.c_int, C.c_int, C.c_uint64, C.c_uint64, c_dp, c_hp],
+    "fmb_uniforms_generate": [C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_uint64, c_hp],
     "fmb_euler_black_scholes": [C.c_int, C.c_int, C.c_int, C.c_uint64, c_dp, c_hp, C.c_double, C.c_double, C.c_double, c_hp],
     "fmb_euler_heston": [C.c_int, C.c_int, C.c_int, C.c_uint64, c_dp, c_hp, C.c_double, c_dp, C.c_double, C.c_double, C.c_double,
                          C.c_double, C.c_double, c_hp],

@@ -82,7 +82,9 @@ enum {  /* fmb_rv_unary: out = f(x, a) */
 	FMB_U_VID = 15,   /* a / x   :850 */
 	FMB_U_CAP = 16,   /* Math.min(x, a) — NaN-propagating, -0.0 < +0.0  :745 */
 	FMB_U_FLOOR = 17, /* Math.max(x, a)  :760 */
-	FMB_U_POW = 18    /* Math.pow(x, a); a == 0.5 is sqrt, a == 2.0 is x*x bit-for-bit (T/montecarlo/RandomVariableTest.java:101-127) */
+	FMB_U_POW = 18,   /* Math.pow(x, a); a == 0.5 is sqrt, a == 2.0 is x*x bit-for-bit (T/montecarlo/RandomVariableTest.java:101-127) */
+	FMB_U_ICDF_NORMAL = 19   /* NormalDistribution.inverseCumulativeDistribution(x), AS241 (J/functions/NormalDistribution.java:47-162): the
+	                            transform BrownianMotionFromRandomNumberGenerator / IndependentIncrementsFromICDF apply to uniforms */
 };
 enum {  /* fmb_rv_binary: out = f(x, y) */
 	FMB_B_ADD = 0, FMB_B_SUB = 1, FMB_B_MULT = 2, FMB_B_DIV = 3, FMB_B_CAP = 4, FMB_B_FLOOR = 5
@@ -145,6 +147,11 @@ int fmb_icdf(const double* host_p, uint64_t n, double* host_out);
  * out[t*F+f] = handle of length `paths`, value ICDF(u_{((path_offset+p)*T+t)*F+f}) * sqrt_dt[t].
  * All T*F vectors live in one slab in [t][f][path] order. */
 int fmb_bm_generate(int32_t seed, int T, int F, uint64_t paths, uint64_t path_offset, const double* sqrt_dt, fmb_handle* out);
+
+/* The uniforms themselves in the same [t][f][path] layout and draw order (out[t*F+f][p] = u_{((path_offset+p)*T+t)*F+f}, bit-exact):
+ * IndependentIncrementsFromICDF (J/montecarlo/IndependentIncrementsFromICDF.java:173-206) applies its own inverse distribution functions
+ * to them; seed is the long the reference hands to MersenneTwister(seed). */
+int fmb_uniforms_generate(int64_t seed, int T, int F, uint64_t paths, uint64_t path_offset, fmb_handle* out);
 
 /* ---- fused Euler schemes: EulerSchemeFromProcessModel J/montecarlo/process/EulerSchemeFromProcessModel.java:170-326.
  *      scheme: 0 EULER, 1 PREDICTOR_CORRECTOR, 2 EULER_FUNCTIONAL, 3 PREDICTOR_CORRECTOR_FUNCTIONAL (:68-73).

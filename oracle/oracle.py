@@ -44,6 +44,11 @@ def lib():
     return _LIB
 
 
+def set_math(mode):
+    """0: libm exp / log (default).  1 (diagnostic): the device kernels' exp / log compiled for the host, to attribute deviations."""
+    lib().orc_set_math(C.c_int(mode))
+
+
 def _d(a):
     a = np.ascontiguousarray(a, dtype=np.float64)
     return a, a.ctypes.data_as(c_dp)
@@ -253,6 +258,28 @@ class LMM:
         price = lib().orc_lmm_caplet(self.h, C.c_double(maturity), C.c_double(period_length), C.c_double(strike), C.c_double(dcf),
                                      C.c_int(1 if is_floorlet else 0), vals.ctypes.data_as(c_dp))
         return price, vals
+
+    def bermudan_given(self, is_exercise, fixing_dates, period_lengths, payment_dates, notionals, swaprates, coefficients, weight, is_callable=True):
+        """Replay of the backward induction on this (window of) paths with GIVEN regression coefficients [nExercise][6] and Monte-Carlo
+        weight: per-path values and exercise times."""
+        ex = np.ascontiguousarray(is_exercise, dtype=np.int32)
+        f, fp = _d(fixing_dates)
+        pl, plp = _d(period_lengths)
+        p, pp = _d(payment_dates)
+        nt, ntp = _d(notionals)
+        s, sp = _d(swaprates)
+        co, cop = _d(np.asarray(coefficients, dtype=np.float64).reshape(-1))
+        vals, ext = np.empty(self.paths), np.empty(self.paths)
+        lib().orc_lmm_bermudan_given(self.h, ex.ctypes.data_as(C.POINTER(C.c_int)), fp, plp, pp, ntp, sp, C.c_int(f.size), C.c_int(1 if is_callable else 0),
+                                     cop, C.c_int(co.size // 6), C.c_double(weight), vals.ctypes.data_as(c_dp), ext.ctypes.data_as(c_dp))
+        return vals, ext
+
+    def bermudan_basis(self, fixing_date, fixing_dates, payment_dates):
+        f, fp = _d(fixing_dates)
+        p, pp = _d(payment_dates)
+        out = np.empty((6, self.paths))
+        lib().orc_lmm_bermudan_basis(self.h, C.c_double(fixing_date), fp, pp, C.c_int(f.size), out.ctypes.data_as(c_dp))
+        return out
 
     def bermudan(self, is_exercise, fixing_dates, period_lengths, payment_dates, notionals, swaprates, is_callable=True):
         ex = np.ascontiguousarray(is_exercise, dtype=np.int32)

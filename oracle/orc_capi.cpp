@@ -7,6 +7,14 @@
 
 using namespace orc;
 
+// Diagnostic only: the device kernels' exp / log (finmath-lib_b200/csrc/fmb_math.cuh, host-compilable) for orc_set_math(1).
+#pragma GCC diagnostic push
+#pragma GCC diagnostic ignored "-Wunknown-pragmas"
+#include "../finmath-lib_b200/csrc/fmb_math.cuh"
+#pragma GCC diagnostic pop
+static double deviceExp(double x) { return fmb::fexp(x); }
+static double deviceLog(double x) { return fmb::flog(x); }
+
 namespace {
 std::vector<double> vecOf(const double* p, int n) { return std::vector<double>(p, p + n); }
 P wrap(const double* x, uint64_t n) { return rvvec(0.0, std::vector<double>(x, x + n)); }
@@ -195,6 +203,12 @@ void orc_lmm_brownian(void* hv, double* out /* [T][F][P] */) {
 	for (int t = 0; t < T; t++) for (int f = 0; f < h->bm->F; f++)
 		std::memcpy(out + ((size_t)t * h->bm->F + f) * h->bm->paths, h->bm->inc[t][f]->r.data(), sizeof(double) * h->bm->paths);
 }
+// 0: libm exp / log (the default, what "the oracle" means everywhere).  1: the device's exp / log restated on the host - used by the
+// tests to show that what separates the device paths from the oracle's is ONLY the last-bit difference of two exp / log libraries.
+void orc_set_math(int mode) {
+	mathExp() = mode == 1 ? deviceExp : stdExp;
+	mathLog() = mode == 1 ? deviceLog : stdLog;
+}
 void orc_lmm_set_interpolation(void* hv, int method) { ((LmmHandle*)hv)->model.interpolationMethod = method; }
 void orc_lmm_numeraire(void* hv, double time, double* out) {
 	auto* h = (LmmHandle*)hv;
@@ -241,6 +255,25 @@ double orc_lmm_bermudan(void* hv, const int* isExercise, const double* fixingDat
 	if (condOut) for (size_t e = 0; e < r.regressionCond.size(); e++) condOut[e] = r.regressionCond[e];
 	if (stdErrOut) *stdErrOut = getStandardError(r.value);
 	return getAverage(r.value);
+}
+
+// replay with given regression coefficients ([nExercise][6], loop order) and Monte-Carlo weight: per-path values / exercise times of a window
+void orc_lmm_bermudan_given(void* hv, const int* isExercise, const double* fixingDates, const double* periodLengths, const double* paymentDates,
+		const double* notionals, const double* swaprates, int n, int isCallable, const double* coefficients, int nExercise, double weight,
+		double* valuesOut, double* exerciseTimeOut) {
+	auto* h = (LmmHandle*)hv;
+	std::vector<std::vector<double>> coef(nExercise);
+	for (int e = 0; e < nExercise; e++) coef[e] = vecOf(coefficients + 6 * e, 6);
+	BermudanResult r = bermudanSwaptionValues(h->sim, 0.0, std::vector<int>(isExercise, isExercise + n), vecOf(fixingDates, n),
+		vecOf(periodLengths, n), vecOf(paymentDates, n), vecOf(notionals, n), vecOf(swaprates, n), isCallable != 0, &coef, weight);
+	if (valuesOut) store(r.value, valuesOut, h->bm->paths);
+	if (exerciseTimeOut) store(r.exerciseTime, exerciseTimeOut, h->bm->paths);
+}
+// the six regression basis functions of BermudanSwaption.getBasisFunctions (:215-252) at one exercise date: out[6][P]
+void orc_lmm_bermudan_basis(void* hv, double fixingDate, const double* fixingDates, const double* paymentDates, int n, double* out) {
+	auto* h = (LmmHandle*)hv;
+	std::vector<P> b = bermudanBasisFunctions(h->sim, fixingDate, vecOf(fixingDates, n), vecOf(paymentDates, n));
+	for (size_t k = 0; k < b.size(); k++) store(b[k], out + k * (size_t)h->bm->paths, h->bm->paths);
 }
 
 // ---- Hull-White (process values only; [T+1][2][P]) -----------------------------------------------------------------

@@ -28,6 +28,16 @@
 
 namespace orc {
 
+// Math.exp / Math.log of the reference are libm calls (std::exp / std::log here, like the JVM's: < 1 ulp, not bit-specified).  Every
+// exp / log of the restatement goes through these two pointers so that a DIAGNOSTIC mode can swap in another implementation
+// (orc_set_math in orc_capi.cpp: the exp / log the device kernels use, compiled for the host).  With it the tests can attribute a
+// deviation either to the arithmetic (none: the device then agrees to the last bit) or to the two libraries' last-bit differences.
+typedef double (*MathFn)(double);
+inline double stdExp(double x) { return std::exp(x); }
+inline double stdLog(double x) { return std::log(x); }
+inline MathFn& mathExp() { static MathFn f = stdExp; return f; }
+inline MathFn& mathLog() { static MathFn f = stdLog; return f; }
+
 // ---------------------------------------------------------------------------------------------------------------
 // MT19937 as in org.apache.commons.math3.random.MersenneTwister 3.6.1 (bytecode-verified in SURVEY.md §8c) behind
 // the wrapper J/randomnumbers/MersenneTwister.java:26-29 (seed ctor) and :48-51 (nextDoubleFast).
@@ -137,7 +147,7 @@ inline double inverseCumulativeNormal(double p) {
 	}
 	r = (q < 0.0) ? p : 1.0 - p;
 	if (r <= 0.0) return 0.0;
-	r = std::sqrt(-std::log(r));
+	r = std::sqrt(-mathLog()(r));
 	double x;
 	if (r <= 5.0) {
 		r -= 1.6;
@@ -250,12 +260,19 @@ inline P div(const P& a, double x) { return map1(a, [x](double y) { return y / x
 inline P vid(const P& a, double x) { return map1(a, [x](double y) { return x / y; }); }
 inline P cap(const P& a, double x) { return map1(a, [x](double y) { return jmin(y, x); }); }
 inline P floor(const P& a, double x) { return map1(a, [x](double y) { return jmax(y, x); }); }
-inline P pow(const P& a, double x) { return map1(a, [x](double y) { return std::pow(y, x); }); }
+// Math.pow: the reference's own tests require pow(x, 2.0) == x * x and pow(x, 0.5) == sqrt(x) bit for bit
+// (T/montecarlo/RandomVariableTest.java:101-127; HotSpot's pow intrinsic special-cases both exponents), which a libm pow does not
+// guarantee in the last bit - restated explicitly.
+inline P pow(const P& a, double x) {
+	if (x == 2.0) return map1(a, [](double y) { return y * y; });
+	if (x == 0.5) return map1(a, [](double y) { return std::sqrt(y); });
+	return map1(a, [x](double y) { return std::pow(y, x); });
+}
 inline P squared(const P& a) { return map1(a, [](double y) { return y * y; }); }
 inline P sqrt(const P& a) { return map1(a, [](double y) { return std::sqrt(y); }); }
-inline P exp(const P& a) { return map1(a, [](double y) { return std::exp(y); }); }
+inline P exp(const P& a) { return map1(a, [](double y) { return mathExp()(y); }); }
 inline P expm1(const P& a) { return map1(a, [](double y) { return std::expm1(y); }); }
-inline P log(const P& a) { return map1(a, [](double y) { return std::log(y); }); }
+inline P log(const P& a) { return map1(a, [](double y) { return mathLog()(y); }); }
 inline P sin(const P& a) { return map1(a, [](double y) { return std::sin(y); }); }
 inline P cos(const P& a) { return map1(a, [](double y) { return std::cos(y); }); }
 inline P invert(const P& a) { return map1(a, [](double y) { return 1.0 / y; }); }

@@ -156,10 +156,15 @@ inline std::vector<P> bermudanBasisFunctions(LIBORSimulation& m, double fixingDa
 	b.push_back(invert(m.getNumeraire(fixingDate)));
 	return b;
 }
+// givenCoefficients (test aid): replay the induction with these regression coefficients (one vector per exercise date, in loop order)
+// instead of estimating them, and weightOverride > 0 as the Monte-Carlo weight - a WINDOW of paths of a large simulation then reproduces
+// the per-path values and exercise decisions of the full run (the coefficients are the only quantity that depends on all paths).
 inline BermudanResult bermudanSwaptionValues(LIBORSimulation& m, double evaluationTime, const std::vector<int>& isExercise,
 		const std::vector<double>& fixingDates, const std::vector<double>& periodLengths, const std::vector<double>& paymentDates,
-		const std::vector<double>& notionals, const std::vector<double>& swaprates, bool isCallable) {
+		const std::vector<double>& notionals, const std::vector<double>& swaprates, bool isCallable,
+		const std::vector<std::vector<double>>* givenCoefficients = nullptr, double weightOverride = 0.0) {
 	BermudanResult res;
+	size_t exerciseCount = 0;
 	P values = m.getRandomVariableForConstant(0.0);
 	P valuesUnderlying = m.getRandomVariableForConstant(0.0);
 	P exerciseTime = m.getRandomVariableForConstant(std::numeric_limits<double>::infinity());
@@ -169,20 +174,26 @@ inline BermudanResult bermudanSwaptionValues(LIBORSimulation& m, double evaluati
 		P libor = m.getForwardRate(fixingDate, fixingDate, fixingDate + periodLength);
 		P payoff = mult(mult(sub(libor, swaprate), periodLength), notional);
 		P numeraire = m.getNumeraire(paymentDate);
-		P w = m.getMonteCarloWeights(paymentDate);
+		P w = weightOverride > 0.0 ? scalar(weightOverride) : m.getMonteCarloWeights(paymentDate);
 		payoff = mult(div(payoff, numeraire), w);
 		if (isCallable) valuesUnderlying = add(valuesUnderlying, payoff); else values = add(values, payoff);
 		if (isExercise[period]) {
 			P trig = sub(values, valuesUnderlying);
 			Regression reg(bermudanBasisFunctions(m, fixingDate, fixingDates, paymentDates));
-			P triggerValues = reg.getConditionalExpectation(trig);
+			P triggerValues;
+			if (givenCoefficients) {                                                             // :103-107 with the supplied parameters
+				const std::vector<double>& x = (*givenCoefficients)[exerciseCount++];
+				triggerValues = mult(reg.basis[0], x[0]);
+				for (size_t i = 1; i < reg.basis.size(); i++) triggerValues = addProduct(triggerValues, reg.basis[i], x[i]);
+				reg.lastParameters = x; reg.lastCond = 0.0;
+			} else triggerValues = reg.getConditionalExpectation(trig);
 			res.regressionParameters.push_back(reg.lastParameters);
 			res.regressionCond.push_back(reg.lastCond);
 			values = choose(triggerValues, values, valuesUnderlying);
 			exerciseTime = choose(triggerValues, exerciseTime, scalar(exerciseDate));
 		}
 	}
-	values = div(mult(values, m.getNumeraire(evaluationTime)), m.getMonteCarloWeights(evaluationTime));
+	values = div(mult(values, m.getNumeraire(evaluationTime)), weightOverride > 0.0 ? scalar(weightOverride) : m.getMonteCarloWeights(evaluationTime));
 	res.value = values;
 	res.exerciseTime = exerciseTime;
 	return res;

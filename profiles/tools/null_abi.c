@@ -53,6 +53,7 @@ int fmb_mt_uniforms(int64_t s, uint64_t o, uint64_t n, double* out) { memset(out
 int fmb_icdf(const double* p, uint64_t n, double* o) { memset(o, 0, 8 * n); return 0; }
 int fmb_bm_generate(int32_t seed, int T, int F, uint64_t paths, uint64_t off, const double* sq, fmb_handle* out) {
 	for (int i = 0; i < T * F; i++) out[i] = mk(paths); launches += 10; return 0; }
+int fmb_uniforms_generate(int64_t seed, int T, int F, uint64_t paths, uint64_t off, fmb_handle* out) { for (int i = 0; i < T * F; i++) out[i] = mk(paths); launches += 10; return 0; }
 static void proc(int T, int N, uint64_t paths, fmb_handle* out) { for (int j = 0; j < N; j++) out[j] = 0; for (int i = N; i < (T + 1) * N; i++) out[i] = mk(paths); launches++; }
 int fmb_euler_black_scholes(int s, int T, int F, uint64_t paths, const double* dt, const fmb_handle* dW, double a, double b, double c, fmb_handle* out) { proc(T, 1, paths, out); return 0; }
 int fmb_euler_heston(int s, int hs, int T, uint64_t paths, const double* dt, const fmb_handle* dW, double iv, const double* r, double v, double th, double k, double xi, double rho, fmb_handle* out) { proc(T, 2, paths, out); return 0; }

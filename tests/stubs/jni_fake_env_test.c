@@ -69,6 +69,7 @@ jlong J(ternary)(JNIEnv*, jclass, jint, jlong, jdouble, jlong, jdouble, jlong, j
 jdoubleArray J(reduce)(JNIEnv*, jclass, jint, jlong, jlong, jdouble); jlong J(sorted)(JNIEnv*, jclass, jlong); jlongArray J(countLessOrEqual)(JNIEnv*, jclass, jlong, jdoubleArray);
 jintArray J(mtWords)(JNIEnv*, jclass, jlong, jlong, jint); jdoubleArray J(mtUniforms)(JNIEnv*, jclass, jlong, jlong, jint); jdoubleArray J(icdf)(JNIEnv*, jclass, jdoubleArray);
 jlongArray J(brownianGenerate)(JNIEnv*, jclass, jint, jint, jint, jlong, jlong, jdoubleArray);
+jlongArray J(uniformsGenerate)(JNIEnv*, jclass, jlong, jint, jint, jlong, jlong);
 jlongArray J(eulerBlackScholes)(JNIEnv*, jclass, jint, jint, jint, jlong, jdoubleArray, jlongArray, jdouble, jdouble, jdouble);
 jlongArray J(eulerHeston)(JNIEnv*, jclass, jint, jint, jint, jlong, jdoubleArray, jlongArray, jdouble, jdoubleArray, jdouble, jdouble, jdouble, jdouble, jdouble);
 jlongArray J(eulerLmm)(JNIEnv*, jclass, jint, jint, jint, jdouble, jint, jint, jint, jlong, jdoubleArray, jlongArray, jdoubleArray, jdoubleArray, jdoubleArray, jdoubleArray, jintArray);
@@ -125,6 +126,7 @@ static void noDevice(void) {
 	THROWS(RTE, J(evalChain)(env, NULL, bc, 0, longs(2, hs), doubles(2, sq))); THROWS(RTE, J(reduce)(env, NULL, 0, 1, 0, 0.0)); THROWS(RTE, J(sorted)(env, NULL, 1));
 	THROWS(RTE, J(countLessOrEqual)(env, NULL, 1, doubles(2, sq))); THROWS(RTE, J(mtWords)(env, NULL, 3141, 0, 4)); THROWS(RTE, J(mtUniforms)(env, NULL, 3141, 0, 4));
 	THROWS(RTE, J(icdf)(env, NULL, doubles(3, v))); THROWS(RTE, J(brownianGenerate)(env, NULL, 3141, 2, 1, 10, 0, doubles(2, sq)));
+	THROWS(RTE, J(uniformsGenerate)(env, NULL, 3141, 2, 1, 10, 0));
 	THROWS(RTE, J(eulerBlackScholes)(env, NULL, 2, 2, 1, 10, doubles(2, sq), longs(2, hs), 1.0, 0.05, 0.3));
 	THROWS(RTE, J(eulerHeston)(env, NULL, 2, 1, 1, 10, doubles(2, sq), longs(2, hs), 1.0, doubles(2, sq), 0.3, 0.09, 0.1, 0.5, 0.1));
 	THROWS(RTE, J(eulerLmm)(env, NULL, 2, 0, 1, 1e5, 2, 1, 1, 10, doubles(2, sq), longs(2, hs), doubles(2, sq), doubles(2, sq), doubles(2, sq), doubles(2, sq), ints(2, fl)));
@@ -174,6 +176,9 @@ static void onGpu(void) {
 	jlongArray dW; OK(dW = J(brownianGenerate)(env, NULL, 3141, T, 1, P, 0, doubles(T, sq))); EXPECT(dW && dW->len == T, "T*F increments");
 	jlongArray X; OK(X = J(eulerBlackScholes)(env, NULL, 2, T, 1, P, doubles(T, dt), dW, 1.0, 0.05, 0.2)); EXPECT(X && X->len == T + 1 && L(X)[0] == 0 && L(X)[T] != 0, "process handles");
 	OK(r = J(reduce)(env, NULL, 0, L(X)[T], 0, 0)); EXPECT(fabs((D(r)[0] + D(r)[1]) / P - exp(0.05)) < 0.01, "E[S(1)] = exp(r)");
+	{ jlongArray U; OK(U = J(uniformsGenerate)(env, NULL, 3141, 1, 2, 4, 0)); jdoubleArray u0; OK(u0 = J(download)(env, NULL, L(U)[0]));
+	  EXPECT(u0 && D(u0)[0] == 0.48112854170930563 && D(u0)[1] == 0.7730656542235694, "uniforms in draw order (path-major)");
+	  jlong z2 = 0; OK(z2 = J(unary)(env, NULL, 19 /* U_ICDF_NORMAL */, L(U)[0], 0.0)); OK(u0 = J(download)(env, NULL, z2)); EXPECT(fabs(D(u0)[0] + 0.047321386241461816) < 1e-15, "ICDF op"); }
 	/* Heston / Hull-White / LMM through the shim: shapes only (numerics are covered by the Python-driven parity tests) */
 	jlongArray dW2; OK(dW2 = J(brownianGenerate)(env, NULL, 31415, T, 2, P, 0, doubles(T, sq)));
 	double rate[4] = { 0.05, 0.05, 0.05, 0.05 };

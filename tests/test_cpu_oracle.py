@@ -154,3 +154,49 @@ def test_regression_solver_against_numpy(orc):
     A2 = np.array([[1.0, 1.0], [1.0, 1.0]])
     x2, _ = orc.solve_pinv(A2, np.array([2.0, 2.0]))
     assert np.allclose(x2, [1.0, 1.0])                                      # minimum-norm solution of a singular system
+
+
+def test_bermudan_replay_with_given_coefficients_reproduces_the_valuation(orc, pkg):
+    """The window check of the 8 M-path Bermudan (tests/test_gpu_fullsize.py) hands the device's regression coefficients to the oracle:
+    replaying the oracle's own coefficients (and weight) must give back its own per-path values and exercise times exactly, also on a
+    window started at a path offset with the coefficients of the full run."""
+    from common import lmm_setup, lmm_oracle, bermudan_spec
+    s = lmm_setup(pkg)
+    b = bermudan_spec(s)
+    args = (b["is_exercise"], b["fixing"], b["lengths"], b["payment"], b["notionals"], b["swaprates"])
+    paths = 3000
+    full = lmm_oracle(orc, s, paths, with_discount_curve=False)
+    r = full.bermudan(*args)
+    vals, ext = full.bermudan_given(*args, r["regression"], 1.0 / paths)
+    assert np.array_equal(vals, r["values"]) and np.array_equal(ext, r["exercise_time"])
+    window = lmm_oracle(orc, s, 500, with_discount_curve=False, path_offset=1700)
+    vals_w, ext_w = window.bermudan_given(*args, r["regression"], 1.0 / paths)
+    assert np.array_equal(vals_w, r["values"][1700:2200]) and np.array_equal(ext_w, r["exercise_time"][1700:2200])
+    basis = window.bermudan_basis(b["fixing"][3], b["fixing"], b["payment"])
+    assert basis.shape == (6, 500) and np.all(basis[0] == 1.0) and np.all(basis[2] == basis[1] * basis[1])
+
+
+def test_two_math_libraries_separate_heston_paths_at_the_variance_kink(orc, pkg):
+    """The same restatement with libm's exp / log and with the device kernels' exp / log (both on the CPU, both < 1 ulp): under full
+    truncation with the Feller condition violated (xi = 0.5) a small fraction of paths touches V ~ 0, where sqrt amplifies a last-bit
+    difference - beyond 1e-12 for ~1e-4 of the paths, while the price agrees to 1e-13.  This is why the GPU parity test checks the 1e-12
+    path gate against the oracle in the device-math mode and bounds the deviation from the libm oracle by this libm-vs-libm figure.  With
+    xi = 0 (no kink) the two agree within 1e-12 on every path."""
+    td = pkg.TimeDiscretizationFromArray(0.0, 100, 0.05)
+    paths = 20_000
+    for xi in (0.5, 0.0):
+        args = (31415, td.times, paths, 1.0, 0.05, 0.3, 0.05, 0.09, 0.1, xi, 0.1, 1, 2, 5.0, 1.10)
+        p_libm, proc_libm, _ = orc.heston_european(*args)
+        orc.set_math(1)
+        try:
+            p_dev, proc_dev, _ = orc.heston_european(*args)
+        finally:
+            orc.set_math(0)
+        e0 = np.abs(proc_libm[:, 0] - proc_dev[:, 0]) / np.maximum(np.abs(proc_libm[:, 0]), 1.0)
+        e1 = np.abs(proc_libm[:, 1] - proc_dev[:, 1]) / np.maximum(np.abs(proc_libm[:, 1]), 0.09)
+        bad = np.mean(((e0 > 1e-12) | (e1 > 1e-12)).any(axis=0))
+        assert abs(p_libm - p_dev) <= 1e-12 * abs(p_libm)
+        if xi > 0:
+            assert 0 < bad < 2e-3 and max(e0.max(), e1.max()) < 1e-9
+        else:
+            assert bad == 0.0

@@ -109,3 +109,77 @@ def test_brownian_view_and_correlated(gpu, orc):
     a = gpu.EulerSchemeFromProcessModel(model, gpu.BrownianMotionView(bm, [0])).getProcessValue(20, 0).getRealizations()
     b = gpu.EulerSchemeFromProcessModel(model, bm).getProcessValue(20, 0).getRealizations()
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("T,F,P,off", [(5, 2, 1000, 0), (40, 3, 2001, 0), (7, 1, 64, 12345), (1000, 2, 10, 3)])
+def test_uniform_increments_are_bit_exact_in_draw_order(gpu, orc, T, F, P, off):
+    """fmb_uniforms_generate: out[t*F+f][p] = u_{((off+p)*T+t)*F+f} of `new MersenneTwister(seed)` (IndependentIncrementsFromICDF.java:186-194)."""
+    nv = gpu.native
+    out = np.zeros(T * F, dtype=np.uint64)
+    nv.check(nv.load().fmb_uniforms_generate(53252, T, F, P, off, nv.hptr(out)))
+    got = np.stack([nv.DeviceVector(int(h), P).download() for h in out]).reshape(T, F, P)
+    seq = orc.mt_uniforms(53252, off * T * F, P * T * F).reshape(P, T, F)
+    assert np.array_equal(got, np.transpose(seq, (1, 2, 0)))
+
+
+def test_independent_increments_from_icdf(gpu, orc):
+    """IndependentIncrementsFromICDF (J/montecarlo/IndependentIncrementsFromICDF.java:173-206): per (time, factor) inverse distribution
+    functions on device-generated uniforms - the built-in normal transform, a function written with RandomVariable operations
+    (exponential distribution) and a plain double -> double callable (applied on the host)."""
+    import math
+    T, F, P = 6, 3, 4000
+    td = gpu.TimeDiscretizationFromArray(0.0, T, 0.25)
+    lam = 2.5
+    exponential = lambda u: u.mult(-1.0).add(1.0).log().mult(-1.0 / lam)
+    plain = lambda x: x * x                                  # double -> double
+    icdfs = lambda t: (lambda f: [gpu.IndependentIncrementsFromICDF.NORMAL_ICDF, exponential, plain][f])
+    inc = gpu.IndependentIncrementsFromICDF(td, F, P, 3141, icdfs)
+    u = np.transpose(orc.mt_uniforms(3141, 0, P * T * F).reshape(P, T, F), (1, 2, 0))
+    for t in (0, 3, 5):
+        z = inc.getIncrement(t, 0)
+        assert z.getFiltrationTime() == td.getTime(t + 1)
+        assert rel_err(z.getRealizations(), orc.icdf(u[t, 0])) < 2e-15
+        assert rel_err(inc.getIncrement(t, 1).getRealizations(), -np.log(1.0 - u[t, 1]) / lam) < 1e-14
+        assert np.array_equal(inc.getIncrement(t, 2).getRealizations(), u[t, 2] * u[t, 2])
+    clone = inc.getCloneWithModifiedSeed(31415)
+    assert not np.array_equal(clone.getIncrement(0, 0).getRealizations(), inc.getIncrement(0, 0).getRealizations())
+
+
+def test_brownian_motion_from_random_number_generator(gpu, orc):
+    """BrownianMotionFromRandomNumberGenerator (J/montecarlo/BrownianMotionFromRandomNumberGenerator.java:137-186): with the Mersenne
+    Twister as generator it is the same stream as BrownianMotionFromMersenneRandomNumbers (device-generated); any other generator is a
+    host object asked path by path."""
+    T, F, P = 8, 2, 3000
+    td = gpu.TimeDiscretizationFromArray(0.0, T, 0.5)
+    mt = gpu.RandomNumberGeneratorFrom1D(gpu.MersenneTwister(3141), T * F)
+    bm = gpu.BrownianMotionFromRandomNumberGenerator(td, F, P, mt)
+    ref = gpu.BrownianMotionCuda(td, F, P, 3141)
+    for t, f in ((0, 0), (3, 1), (7, 0)):
+        assert np.array_equal(bm.getBrownianIncrement(t, f).getRealizations(), ref.getBrownianIncrement(t, f).getRealizations())
+        assert bm.getBrownianIncrement(t, f).getFiltrationTime() == td.getTime(t + 1)
+    # an Euler scheme on top of it (generic device loop) gives the paths of the fused kernel on the Mersenne driver
+    model = gpu.BlackScholesModel(1.0, 0.05, 0.3, ref.randomVariableFactory)
+    a = gpu.EulerSchemeFromProcessModel(model, gpu.BrownianMotionView(bm, [0])).getProcessValue(T, 0).getRealizations()
+    b = gpu.EulerSchemeFromProcessModel(model, gpu.BrownianMotionCuda(td, F, P, 3141)).getProcessValue(T, 0).getRealizations()
+    assert np.array_equal(a, b)
+
+    class Halton2:                                           # any host-side generator: here a van der Corput / Halton pair per step
+        def __init__(self, dim): self.dim, self.i = dim, 0
+        def getDimension(self): return self.dim
+        def getNext(self):
+            self.i += 1
+            out = []
+            for d in range(self.dim):
+                base, f, r, i = [2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53][d], 1.0, 0.0, self.i
+                while i > 0:
+                    f /= base
+                    r += f * (i % base)
+                    i //= base
+                out.append(r)
+            return out
+    q = gpu.BrownianMotionFromRandomNumberGenerator(td, F, 500, Halton2(T * F))
+    h = Halton2(T * F)
+    u = np.array([h.getNext() for _ in range(500)])
+    for t, f in ((0, 0), (5, 1)):
+        want = orc.icdf(u[:, t * F + f]) * np.sqrt(td.getTimeStep(t))
+        assert rel_err(q.getBrownianIncrement(t, f).getRealizations(), want) < 2e-15

@@ -81,3 +81,46 @@ def test_c5_bermudan_8m_paths_price_is_consistent_with_1m(gpu):
     (v1, e1), (v8, e8) = res[1_000_000], res[8_000_000]
     assert abs(v1 - v8) < 4 * np.hypot(e1, e8)
     assert e8 < e1 / 2.5                                       # standard error shrinks like 1/sqrt(8)
+
+
+def test_c5_bermudan_8m_paths_windows_match_oracle(gpu, orc):
+    """The north-star configuration at full size on one GPU: 8 M paths, 20 exercise dates, 6 basis functions.  The regression coefficients
+    are the only quantities that depend on all paths; everything else is path-local.  So windows of paths are checked against the oracle
+    started at the same path offset: (1) the regression INPUTS (the six basis functions at several exercise dates), (2) with the device's
+    coefficients handed to the oracle's backward induction, the per-path Bermudan values and the exercise times.  (No discount-curve
+    adjustment here: its getAverage over all paths would be a second all-path quantity.)"""
+    from common import bermudan_spec
+    P = 8_000_000
+    s = lmm_setup(gpu)
+    b = bermudan_spec(s)
+    product = gpu.BermudanSwaption(b["is_exercise"], b["fixing"], b["lengths"], b["payment"], b["notionals"], b["swaprates"])
+    sim = lmm_device(gpu, s, P, scheme=2, with_discount_curve=False)
+    res = product.getValues(0.0, sim)
+    values, exercise = res["value"].getRealizations(), res["exerciseTime"].getRealizations()
+    coefficients = np.array([est.lastParameters for est in product.lastRegressions])
+    conds = np.array([est.lastConditionNumber for est in product.lastRegressions])
+    assert coefficients.shape == (20, 6) and np.all(np.isfinite(coefficients)) and np.all(conds > 1)
+    n = 1500
+    offsets = (0, 3_999_777, P - n)
+    dates = (b["fixing"][0], b["fixing"][7], b["fixing"][19])
+    device_basis = {}
+    for date in dates:                                         # keep only the windows of the 8 M-element vectors on the host
+        got = product.getBasisFunctions(date, sim)
+        for k in range(1, 6):
+            full = got[k].getRealizations()
+            for off in offsets:
+                device_basis[(date, k, off)] = full[off:off + n].copy()
+        del got, full
+    for off in offsets:
+        ref = lmm_oracle(orc, s, n, scheme=2, with_discount_curve=False, path_offset=off)
+        for date in dates:
+            want = ref.bermudan_basis(date, b["fixing"], b["payment"])
+            for k in range(1, 6):
+                assert rel_err(device_basis[(date, k, off)], want[k]) < 1e-12, (off, date, k)
+        vals, ext = ref.bermudan_given(b["is_exercise"], b["fixing"], b["lengths"], b["payment"], b["notionals"], b["swaprates"], coefficients, 1.0 / P)
+        same = ext == exercise[off:off + n]
+        # an exercise decision may flip where the fitted trigger is zero to rounding (|trigger| ~ 1e-13 of its scale): count, do not hide
+        assert np.sum(~same) <= 2, (off, int(np.sum(~same)))
+        assert rel_err(values[off:off + n][same], vals[same], scale=1e-3) < 1e-11, off
+    # and the price is the mean of exactly these per-path values
+    assert abs(res["value"].getAverage() - float(np.mean(values))) < 1e-13

@@ -60,15 +60,32 @@ def test_heston_paths_and_price(gpu, orc, xi, hscheme, scheme):
     ref_price, ref_proc, _ = orc.heston_european(31415, td.times, paths, 1.0, 0.05, sigma, 0.05, sigma * sigma, 0.1, xi, 0.1, hscheme, scheme, 5.0, 1.10)
     assert mc.getProcess().usedFusedKernel == "heston"
     got = device_process_array(mc, T, 2)
-    # per-component scale (S0 = 1, theta = 0.09): the variance crosses zero under full truncation, SURVEY.md §8d parity gates
-    # sqrt(V+) amplifies a 1e-17 absolute difference in V by 1/(2 sqrt(V)) when a path sits at V ~ 0 (Feller violated for xi = 0.5):
-    # 1e-12 must hold for all but a vanishing fraction of the stored values.
-    e0 = np.abs(got[:, 0] - ref_proc[:, 0]) / np.maximum(np.abs(ref_proc[:, 0]), 1.0)
-    e1 = np.abs(got[:, 1] - ref_proc[:, 1]) / np.maximum(np.abs(ref_proc[:, 1]), 0.09)
-    # (the kink of sqrt at 0 makes isolated paths ill-conditioned for ANY two exp/log implementations, JVM vs libm included)
-    assert e0.max() < 1e-6 and e1.max() < 1e-6
+
+    def errors(ref):
+        # per-component scale (S0 = 1, theta = 0.09): the variance crosses zero under full truncation, SURVEY.md 8d parity gates
+        return (np.abs(got[:, 0] - ref[:, 0]) / np.maximum(np.abs(ref[:, 0]), 1.0), np.abs(got[:, 1] - ref[:, 1]) / np.maximum(np.abs(ref[:, 1]), 0.09))
+
+    # (1) The arithmetic: against the oracle evaluated with the SAME exp / log as the kernels (diagnostic mode of the oracle: the device's
+    #     functions compiled for the host) every stored value of every path is within 1e-12 - in fact bit-identical almost everywhere.
+    orc.set_math(1)
+    try:
+        same_price, same_proc, _ = orc.heston_european(31415, td.times, paths, 1.0, 0.05, sigma, 0.05, sigma * sigma, 0.1, xi, 0.1, hscheme, scheme, 5.0, 1.10)
+    finally:
+        orc.set_math(0)
+    e0, e1 = errors(same_proc)
+    assert e0.max() < PATH_TOL and e1.max() < PATH_TOL, (e0.max(), e1.max())
+    assert abs(price - same_price) <= PRICE_TOL * abs(same_price)
+    # (2) Against the oracle with libm's exp / log.  sqrt(V+) has infinite slope at 0 (Feller violated for xi = 0.5), so a path that touches
+    #     V ~ 0 amplifies a 1-ulp difference between two exp / log implementations.  The oracle shows exactly this between ITS two modes
+    #     (libm vs the device functions, both on the CPU): ~1.5e-4 of the paths beyond 1e-12, worst ~1e-11.  The device deviates from the
+    #     libm oracle by no more than the libm oracle deviates from its own second math library.
+    e0, e1 = errors(ref_proc)
+    l0 = np.abs(same_proc[:, 0] - ref_proc[:, 0]) / np.maximum(np.abs(ref_proc[:, 0]), 1.0)
+    l1 = np.abs(same_proc[:, 1] - ref_proc[:, 1]) / np.maximum(np.abs(ref_proc[:, 1]), 0.09)
     bad_paths = np.mean(((e0 > PATH_TOL) | (e1 > PATH_TOL)).any(axis=0))
-    assert bad_paths < (0.01 if xi > 0 else 1e-9), bad_paths             # xi = 0: the variance is deterministic, no kink, every path within 1e-12
+    bad_libm = np.mean(((l0 > PATH_TOL) | (l1 > PATH_TOL)).any(axis=0))
+    assert max(e0.max(), e1.max()) <= max(2.0 * max(l0.max(), l1.max()), PATH_TOL) and max(e0.max(), e1.max()) < 1e-9
+    assert bad_paths <= (max(2.0 * bad_libm, 1e-3) if xi > 0 else 1e-9), (bad_paths, bad_libm)   # xi = 0: deterministic variance, no kink, every path within 1e-12
     assert abs(price - ref_price) <= PRICE_TOL * abs(ref_price)
 
 
