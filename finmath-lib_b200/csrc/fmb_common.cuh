@@ -59,7 +59,7 @@ struct Comm {
 	double* gatherBuf = nullptr; // device, world * COMM_MAX_DOUBLES
 	uint64_t exchanges = 0;
 };
-static const int COMM_MAX_DOUBLES = 128;      // 2 * (8*9/2 + 8) = 88 doubles for the largest regression (K = 8)
+static const int COMM_MAX_DOUBLES = 512;      // 2 * (8*9/2 + 8) = 88 doubles for the largest regression (K = 8); 256 for a radix-select histogram
 
 struct Context {
 	bool initialized = false;

@@ -393,7 +393,9 @@ template <int NT, bool TMA, bool UNIFORM> __global__ void __launch_bounds__(NT, 
 	uint32_t* ring = reinterpret_cast<uint32_t*>(smemRaw + BM_HEADER);
 	double* qP = reinterpret_cast<double*>(smemRaw + BM_HEADER + RING_ALLOC * sizeof(uint32_t));
 	uint32_t* qSlot = reinterpret_cast<uint32_t*>(qP + qCap);          // qCap entries (even): tail draws parked until a dense drain
-	double* tile = reinterpret_cast<double*>(qSlot + qCap);      // standard normals; sqrt(dt) of the column is applied when the tile is written out
+	// the tile starts 16-byte aligned (bulk stores read whole 16-byte units); !TMA: standard normals, sqrt(dt) of the column is applied when the
+	// tile is written out; TMA: already scaled
+	double* tile = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(qSlot + qCap) + 15) & ~(uintptr_t)15);
 	const int tid = threadIdx.x;
 	const int lane = tid & 31, warp = tid >> 5;
 	static_assert(NT >= MT_N - MT_M && 2 * NT - 2 + 2 * MT_N <= RING, "block size against the refresh width / ring depth");

@@ -8,7 +8,6 @@
 //
 // Streaming kernels: HBM-bound, 8 B read per element and operand; grid = 4 CTAs per SM.
 #include "fmb_common.cuh"
-#include <cub/cub.cuh>
 #include <cmath>
 #include <algorithm>
 
@@ -370,18 +369,6 @@ template <int K> __global__ void __launch_bounds__(256) predictKernelV(BasisArgs
 	}
 }
 
-__global__ void countLeKernel(const double* __restrict__ sorted, uint64_t n, const double* __restrict__ pts, int npts, unsigned long long* __restrict__ counts) {
-	const int k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k >= npts) return;
-	const double p = pts[k];
-	uint64_t lo = 0, hi = n;                       // first index with sorted[idx] > p
-	while (lo < hi) {
-		const uint64_t mid = (lo + hi) >> 1;
-		if (sorted[mid] <= p) lo = mid + 1; else hi = mid;
-	}
-	counts[k] = lo;
-}
-
 static int reduceGrid() { return ctx().smCount * 4; }
 
 int commAllGather(int count);                      // fmb_comm.cu
@@ -660,51 +647,6 @@ int fmb_regression_conditional_expectation(int K, const fmb_handle* basis, const
 	const int rc = fmb_regression_predict_fit(Kp, basis_pred ? basis_pred : basis, basis_pred ? basis_pred_scalar : basis_scalar, *fit, out);
 	if (rc != FMB_OK) { releaseRef(*fit); *fit = 0; }
 	return rc;
-}
-
-int fmb_rv_sorted(fmb_handle x, fmb_handle* out) {
-	FMB_TRY(requireInit());
-	PinScope pins;
-	if (!out) return FMB_EINVAL;
-	Context& c = ctx();
-	Vec* vx;
-	FMB_TRY(lookup(x, &vx));
-	const uint64_t n = vx->n;
-	if (n > 0x7fffffffull) { setError("sort: more than 2^31-1 elements"); return FMB_EUNSUPPORTED; }
-	double* dst;
-	FMB_TRY(newVec(n, out, &dst));
-	if (n == 0) return FMB_OK;
-	size_t tmpBytes = 0;
-	FMB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmpBytes, vx->ptr, dst, (int)n, 0, 64, c.stream));
-	void* tmp;
-	FMB_TRY(poolAlloc(tmpBytes, &tmp));
-	cudaError_t e = cub::DeviceRadixSort::SortKeys(tmp, tmpBytes, vx->ptr, dst, (int)n, 0, 64, c.stream);
-	countLaunch(4);
-	poolFree(tmp, tmpBytes);
-	if (e != cudaSuccess) { setError("sort: %s", cudaGetErrorString(e)); return FMB_ECUDA; }
-	return FMB_OK;
-}
-
-int fmb_rv_count_le(fmb_handle sorted, const double* pts, int npts, uint64_t* counts) {
-	FMB_TRY(requireInit());
-	PinScope pins;
-	if (npts < 0 || (npts && (!pts || !counts))) return FMB_EINVAL;
-	if (npts == 0) return FMB_OK;
-	Context& c = ctx();
-	Vec* vs;
-	FMB_TRY(lookup(sorted, &vs));
-	void* dp; void* dc;
-	FMB_TRY(poolAlloc(npts * sizeof(double), &dp));
-	FMB_TRY(poolAlloc(npts * sizeof(uint64_t), &dc));
-	cudaError_t e = cudaMemcpyAsync(dp, pts, npts * sizeof(double), cudaMemcpyHostToDevice, c.stream);
-	countLeKernel<<<(npts + 127) / 128, 128, 0, c.stream>>>(vs->ptr, vs->n, (const double*)dp, npts, (unsigned long long*)dc);
-	countLaunch();
-	if (e == cudaSuccess) e = cudaMemcpyAsync(counts, dc, npts * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
-	poolFree(dp, npts * sizeof(double));
-	poolFree(dc, npts * sizeof(uint64_t));
-	if (e != cudaSuccess) { setError("count_le: %s", cudaGetErrorString(e)); return FMB_ECUDA; }
-	return FMB_OK;
 }
 
 } // extern "C"

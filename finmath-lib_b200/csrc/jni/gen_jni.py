@@ -50,8 +50,9 @@ TABLE = [
     ("evalChain", "fmb_rv_eval_chain", "handle", [("B", "code"), ("i", "startLeaf"), ("H", "leaves"), ("D", "scalars")],
      "code_n / 8, (const unsigned char*)code_p, startLeaf, (const fmb_handle*)leaves_p, leaves_n, scalars_p, scalars_n, OUT"),
     ("reduce", "fmb_rv_reduce", "doubles:2", [("i", "op"), ("h", "x"), ("h", "w"), ("d", "a")], "op, (fmb_handle)x, (fmb_handle)w, a, OUT"),
-    ("sorted", "fmb_rv_sorted", "handle", [("h", "x")], "(fmb_handle)x, OUT"),
-    ("countLessOrEqual", "fmb_rv_count_le", "custom", [("h", "sorted"), ("D", "points")], ""),
+    ("select", "fmb_rv_select", "double", [("h", "x"), ("l", "rank")], "(fmb_handle)x, (uint64_t)rank, OUT"),
+    ("countLessOrEqual", "fmb_rv_count_le", "custom", [("h", "x"), ("D", "points")], ""),
+    ("rangeSum", "fmb_rv_range_sum", "doubles:4", [("h", "x"), ("d", "lo"), ("d", "hi")], "(fmb_handle)x, lo, hi, OUT"),
     ("mtWords", "fmb_mt_words", "custom", [("l", "seed"), ("l", "wordOffset"), ("i", "n")], ""),
     ("mtUniforms", "fmb_mt_uniforms", "doubles:n", [("l", "seed"), ("l", "uniformOffset"), ("i", "n")], "(int64_t)seed, (uint64_t)uniformOffset, (uint64_t)n, OUT"),
     ("icdf", "fmb_icdf", "doubles:p_n", [("D", "p")], "p_p, (uint64_t)p_n, OUT"),
@@ -113,7 +114,7 @@ CUSTOM_C = {
                   "\tjlong w[3] = { (jlong)v[0], (jlong)v[1], (jlong)v[2] };\n\t(*env)->SetLongArrayRegion(env, out, 0, 3, w);\n\treturn out;\n"),
     "countLessOrEqual": ("jlongArray", None,
                          "\tjlongArray out = (*env)->NewLongArray(env, points_n);\n\tjlong* o = out ? (*env)->GetLongArrayElements(env, out, NULL) : NULL;\n"
-                         "\tconst int rc = o ? fmb_rv_count_le((fmb_handle)sorted, points_p, points_n, (uint64_t*)o) : FMB_ENOMEM;\n"
+                         "\tconst int rc = o ? fmb_rv_count_le((fmb_handle)x, points_p, points_n, (uint64_t*)o) : FMB_ENOMEM;\n"
                          "\tif (o) (*env)->ReleaseLongArrayElements(env, out, o, 0);\n@RELEASE@\tif (rc != FMB_OK) { throwFor(env, rc); return NULL; }\n\treturn out;\n"),
     "mtWords": ("jintArray", "",
                 "\tjintArray out = (*env)->NewIntArray(env, n);\n\tif (!out) return NULL;\n\tjint* o = (*env)->GetIntArrayElements(env, out, NULL);\n"

@@ -74,8 +74,9 @@ PROTOTYPES = {
     "fmb_rv_ternary": [C.c_int, C.c_uint64, C.c_double, C.c_uint64, C.c_double, C.c_uint64, C.c_double, C.c_double, c_hp],
     "fmb_rv_eval_chain": [C.c_int, C.c_char_p, C.c_int, c_hp, C.c_int, c_dp, C.c_int, c_hp],
     "fmb_rv_reduce": [C.c_int, C.c_uint64, C.c_uint64, C.c_double, c_dp],
-    "fmb_rv_sorted": [C.c_uint64, c_hp],
+    "fmb_rv_select": [C.c_uint64, C.c_uint64, c_dp],
     "fmb_rv_count_le": [C.c_uint64, c_dp, C.c_int, c_hp],
+    "fmb_rv_range_sum": [C.c_uint64, C.c_double, C.c_double, c_dp],
     "fmb_mt_words": [C.c_int64, C.c_uint64, C.c_uint64, c_u32p],
     "fmb_mt_uniforms": [C.c_int64, C.c_uint64, C.c_uint64, c_dp],
     "fmb_icdf": [c_dp, C.c_uint64, c_dp],

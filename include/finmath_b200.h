@@ -129,10 +129,15 @@ enum {
 	FMB_R_MAX = 5
 };
 int fmb_rv_reduce(int op, fmb_handle x, fmb_handle w, double a, double* out2);
-/* sorted copy (getQuantile/getHistogram, :445-575) */
-int fmb_rv_sorted(fmb_handle x, fmb_handle* out);
-/* number of elements <= each of the npts thresholds in a SORTED vector (histogram buckets, :528-550) */
-int fmb_rv_count_le(fmb_handle sorted, const double* pts, int npts, uint64_t* counts);
+/* Order statistics (getQuantile / getQuantileExpectation / getHistogram, :445-575) without a sort and without moving path data between
+ * GPUs; with a communicator all three cover the logical vector over all shards (only a 256-bin histogram, a few counts or partial sums
+ * are exchanged).  Order = Arrays.sort(double[]): -0.0 < +0.0, NaN above everything. */
+/* element of rank `rank` (0-based) of the sorted order: MSB-first radix select, 8 passes of 8 bits over order-preserving keys */
+int fmb_rv_select(fmb_handle x, uint64_t rank, double* out);
+/* counts[j] = number of elements <= pts[j] (any order of pts, at most 511 per call; NaN elements are never counted) */
+int fmb_rv_count_le(fmb_handle x, const double* pts, int npts, uint64_t* counts);
+/* out4[0] + out4[1] = double-double sum of the elements strictly between lo and hi, out4[2] = #{x <= lo}, out4[3] = #{x < hi} */
+int fmb_rv_range_sum(fmb_handle x, double lo, double hi, double* out4);
 
 /* ---- MT19937 + AS241 Brownian driver: BrownianMotionFromMersenneRandomNumbers
  *      J/montecarlo/BrownianMotionFromMersenneRandomNumbers.java:141-191, MersenneTwister J/randomnumbers/MersenneTwister.java:26-51,

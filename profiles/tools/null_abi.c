@@ -46,7 +46,8 @@ int fmb_rv_ternary(int op, fmb_handle x, double sx, fmb_handle y, double sy, fmb
 	*o = mk(sz(x ? x : (y ? y : z))); launches++; return 0; }
 int fmb_rv_eval_chain(int n, const unsigned char* code, int s, const fmb_handle* l, int nl, const double* sc, int ns, fmb_handle* o) { *o = mk(sz(l[0])); launches++; return 0; }
 int fmb_rv_reduce(int op, fmb_handle x, fmb_handle w, double a, double* o) { o[0] = 0.5 * (double)sz(x); o[1] = 0; launches++; return 0; }
-int fmb_rv_sorted(fmb_handle x, fmb_handle* o) { *o = mk(sz(x)); return 0; }
+int fmb_rv_select(fmb_handle x, uint64_t r, double* o) { *o = 0; return 0; }
+int fmb_rv_range_sum(fmb_handle x, double lo, double hi, double* o) { o[0] = o[1] = o[2] = o[3] = 0; return 0; }
 int fmb_rv_count_le(fmb_handle s, const double* p, int n, uint64_t* c) { for (int i = 0; i < n; i++) c[i] = 0; return 0; }
 int fmb_mt_words(int64_t s, uint64_t o, uint64_t n, uint32_t* out) { memset(out, 0, 4 * n); return 0; }
 int fmb_mt_uniforms(int64_t s, uint64_t o, uint64_t n, double* out) { memset(out, 0, 8 * n); return 0; }

@@ -66,7 +66,7 @@ jdoubleArray J(download)(JNIEnv*, jclass, jlong); jdouble J(get)(JNIEnv*, jclass
 void J(retain)(JNIEnv*, jclass, jlong); void J(free)(JNIEnv*, jclass, jlong); void J(freeMany)(JNIEnv*, jclass, jlongArray); jlong J(devicePointer)(JNIEnv*, jclass, jlong); jlongArray J(poolStats)(JNIEnv*, jclass);
 void J(poolTrim)(JNIEnv*, jclass); jlong J(unary)(JNIEnv*, jclass, jint, jlong, jdouble); jlong J(binary)(JNIEnv*, jclass, jint, jlong, jdouble, jlong, jdouble);
 jlong J(ternary)(JNIEnv*, jclass, jint, jlong, jdouble, jlong, jdouble, jlong, jdouble, jdouble); jlong J(evalChain)(JNIEnv*, jclass, jbyteArray, jint, jlongArray, jdoubleArray);
-jdoubleArray J(reduce)(JNIEnv*, jclass, jint, jlong, jlong, jdouble); jlong J(sorted)(JNIEnv*, jclass, jlong); jlongArray J(countLessOrEqual)(JNIEnv*, jclass, jlong, jdoubleArray);
+jdoubleArray J(reduce)(JNIEnv*, jclass, jint, jlong, jlong, jdouble); jdouble J(select)(JNIEnv*, jclass, jlong, jlong); jdoubleArray J(rangeSum)(JNIEnv*, jclass, jlong, jdouble, jdouble); jlongArray J(countLessOrEqual)(JNIEnv*, jclass, jlong, jdoubleArray);
 jintArray J(mtWords)(JNIEnv*, jclass, jlong, jlong, jint); jdoubleArray J(mtUniforms)(JNIEnv*, jclass, jlong, jlong, jint); jdoubleArray J(icdf)(JNIEnv*, jclass, jdoubleArray);
 jlongArray J(brownianGenerate)(JNIEnv*, jclass, jint, jint, jint, jlong, jlong, jdoubleArray);
 jlongArray J(uniformsGenerate)(JNIEnv*, jclass, jlong, jint, jint, jlong, jlong);
@@ -85,7 +85,7 @@ static int failures = 0, calls = 0;
 #define EXPECT(cond, what) do { if (!(cond)) { printf("FAIL %s (line %d), pending exception '%s' %s\n", what, __LINE__, pending, pendingMessage); failures++; } } while (0)
 /* the call must have thrown exactly this exception class */
 #define THROWS(cls, call) do { pending[0] = 0; call; calls++; EXPECT(strcmp(pending, cls) == 0, #call " should throw " cls); pending[0] = 0; } while (0)
-#define OK(call) do { pending[0] = 0; call; calls++; EXPECT(pending[0] == 0, #call " should not throw"); pending[0] = 0; } while (0)
+#define OK(call) do { pending[0] = 0; call; calls++; if (pending[0]) { printf("FAIL %s threw %s: %s (line %d)\n", #call, pending, pendingMessage, __LINE__); fflush(stdout); exit(2); } } while (0)
 #define RTE "java/lang/RuntimeException"
 #define IAE "java/lang/IllegalArgumentException"
 #define UOE "java/lang/UnsupportedOperationException"
@@ -123,7 +123,7 @@ static void noDevice(void) {
 	THROWS(RTE, J(create)(env, NULL, 10)); THROWS(RTE, J(upload)(env, NULL, doubles(3, v))); THROWS(RTE, J(fill)(env, NULL, 1.0, 10));
 	THROWS(RTE, J(download)(env, NULL, 1)); THROWS(RTE, J(get)(env, NULL, 1, 0)); THROWS(RTE, J(devicePointer)(env, NULL, 1));
 	THROWS(RTE, J(unary)(env, NULL, 0, 1, 0.0)); THROWS(RTE, J(binary)(env, NULL, 0, 1, 0.0, 2, 0.0)); THROWS(RTE, J(ternary)(env, NULL, 0, 1, 0, 2, 0, 3, 0, 0));
-	THROWS(RTE, J(evalChain)(env, NULL, bc, 0, longs(2, hs), doubles(2, sq))); THROWS(RTE, J(reduce)(env, NULL, 0, 1, 0, 0.0)); THROWS(RTE, J(sorted)(env, NULL, 1));
+	THROWS(RTE, J(evalChain)(env, NULL, bc, 0, longs(2, hs), doubles(2, sq))); THROWS(RTE, J(reduce)(env, NULL, 0, 1, 0, 0.0)); THROWS(RTE, J(select)(env, NULL, 1, 0)); THROWS(RTE, J(rangeSum)(env, NULL, 1, 0.0, 1.0));
 	THROWS(RTE, J(countLessOrEqual)(env, NULL, 1, doubles(2, sq))); THROWS(RTE, J(mtWords)(env, NULL, 3141, 0, 4)); THROWS(RTE, J(mtUniforms)(env, NULL, 3141, 0, 4));
 	THROWS(RTE, J(icdf)(env, NULL, doubles(3, v))); THROWS(RTE, J(brownianGenerate)(env, NULL, 3141, 2, 1, 10, 0, doubles(2, sq)));
 	THROWS(RTE, J(uniformsGenerate)(env, NULL, 3141, 2, 1, 10, 0));
@@ -158,8 +158,9 @@ static void onGpu(void) {
 	jdouble g = 0; OK(g = J(get)(env, NULL, x, 2)); EXPECT(g == 3, "get");
 	jdoubleArray r; OK(r = J(reduce)(env, NULL, 0 /* R_SUM */, x, 0, 0)); EXPECT(D(r)[0] + D(r)[1] == 10, "sum");
 	OK(r = J(reduce)(env, NULL, 5 /* R_MAX */, y, 0, 0)); EXPECT(D(r)[0] == 2, "max");
-	jlong s = 0; OK(s = J(sorted)(env, NULL, y)); const double pts[2] = { 0.5, 1.0 };
-	jlongArray cnt; OK(cnt = J(countLessOrEqual)(env, NULL, s, doubles(2, pts))); EXPECT(L(cnt)[0] == 2 && L(cnt)[1] == 2, "count <=");
+	jdouble sel = 0; OK(sel = J(select)(env, NULL, y, 2)); EXPECT(sel == 2.0, "third smallest of {0.5, 0.5, 2, 2}"); const double pts[2] = { 0.5, 1.0 };
+	jlongArray cnt; OK(cnt = J(countLessOrEqual)(env, NULL, y, doubles(2, pts))); EXPECT(L(cnt)[0] == 2 && L(cnt)[1] == 2, "count <=");
+	jdoubleArray rs; OK(rs = J(rangeSum)(env, NULL, x, 1.0, 4.0)); EXPECT(D(rs)[0] + D(rs)[1] == 5.0 && D(rs)[2] == 1 && D(rs)[3] == 3, "sum of {2, 3}, one <= 1, three < 4");
 	jlong f = 0; OK(f = J(fill)(env, NULL, 7.0, 4)); OK(d = J(download)(env, NULL, f)); EXPECT(D(d)[1] == 7, "fill");
 	jlong c0 = 0; OK(c0 = J(create)(env, NULL, 16)); jlong ptr = 0; OK(ptr = J(devicePointer)(env, NULL, c0)); EXPECT(ptr != 0, "device pointer");
 	OK(J(retain)(env, NULL, c0)); OK(J(free)(env, NULL, c0)); OK(n = J(size)(env, NULL, c0)); EXPECT(n == 16, "retained handle survives one free"); OK(J(free)(env, NULL, c0));
@@ -217,6 +218,7 @@ static void onGpu(void) {
 }
 
 int main(int argc, char** argv) {
+	setvbuf(stdout, NULL, _IONBF, 0);
 	const char* mode = argc > 1 ? argv[1] : "nodevice";
 	hostOnly();
 	if (strcmp(mode, "gpu") == 0) onGpu(); else noDevice();

@@ -126,6 +126,47 @@ def test_reductions_match_kahan_oracle(gpu, orc, n):
     assert np.array_equal(g.getHistogram(pts), orc.rv_histogram(x, pts))
 
 
+def test_order_statistics_by_radix_select_match_the_sorted_reference(gpu, orc):
+    """getQuantile / getQuantileExpectation / getHistogram (RandomVariableFromDoubleArray.java:445-575 clone and sort): here a radix select,
+    one counting pass and one range-sum pass - same numbers as the sort, including ties, signed zeros and NaN (Arrays.sort order)."""
+    RV = gpu.RandomVariableCuda
+    rng = np.random.default_rng(5)
+    cases = [rng.standard_normal(100_003), np.round(rng.standard_normal(50_000), 1),                 # many ties
+             np.array([0.0, -0.0, 1.0, -1.0, 0.0, -0.0, 5e-324, -5e-324]), np.array([3.0, np.nan, -np.inf, 2.0, np.inf, np.nan, -7.5]),
+             np.full(1000, 2.5), rng.standard_normal(1_000_003) * 1e-300, np.array([42.0])]
+    for x in cases:
+        g = RV(0.0, x)
+        s = np.sort(x)                                       # numpy sorts like Arrays.sort: NaN last (signed zeros compare equal: checked by value)
+        n = x.size
+        for q in (0.0, 0.001, 0.3, 0.5, 0.77, 0.999, 1.0):
+            got, want = g.getQuantile(q), s[min(max(int(np.floor((n + 1) * q - 1 + 0.5)), 0), n - 1)]
+            assert (got == want) or (np.isnan(got) and np.isnan(want)), (n, q, got, want)
+            assert got == orc.rv_reduce(9, x, a=q) or np.isnan(got)
+        if not np.isnan(x).any():
+            for q0, q1 in ((0.1, 0.9), (0.0, 1.0), (0.45, 0.55), (0.3, 0.3)):
+                i0 = min(max(int(np.floor((n + 1) * q0 - 1 + 0.5)), 0), n - 1)
+                i1 = min(max(int(np.floor((n + 1) * q1 - 1 + 0.5)), 0), n - 1)
+                want = float(np.sum(s[i0:i1 + 1].astype(np.longdouble)) / (i1 - i0 + 1))
+                got = g.getQuantileExpectation(q0, q1)
+                assert abs(got - want) <= 1e-13 * max(abs(want), np.max(np.abs(s[i0:i1 + 1]))), (n, q0, q1, got, want)
+            pts = np.array([-1.0, 0.0, 0.5, 2.5, 1.0])           # not ascending on purpose: each threshold is counted on its own
+            assert np.array_equal(g.getHistogram(np.sort(pts)), orc.rv_histogram(x, np.sort(pts)))
+    # signed zeros: -0.0 sorts below +0.0
+    z = RV(0.0, np.array([0.0, -0.0, 0.0, -0.0]))
+    assert np.signbit(z.getQuantile(0.0)) and not np.signbit(z.getQuantile(1.0))
+    # many thresholds (chunked calls) and counts straight from the C ABI
+    import ctypes as C
+    nv = gpu.native
+    x = rng.standard_normal(200_000)
+    pts = np.linspace(-4, 4, 1201)
+    h = RV(0.0, x).getHistogram(pts)
+    assert np.array_equal(h, orc.rv_histogram(x, pts)) and abs(h.sum() - 1.0) < 1e-12
+    cnt = np.zeros(3, dtype=np.uint64)
+    probe = np.array([0.5, np.nan, -0.5])
+    nv.check(nv.load().fmb_rv_count_le(RV(0.0, x).dv.h, nv.dptr(probe), 3, cnt.ctypes.data_as(nv.c_hp)))
+    assert cnt.tolist() == [int(np.sum(x <= 0.5)), 0, int(np.sum(x <= -0.5))]
+
+
 def test_empty_and_nan_reductions(gpu):
     RV = gpu.RandomVariableCuda
     assert np.isnan(RV(0.0, np.array([])).getAverage())
