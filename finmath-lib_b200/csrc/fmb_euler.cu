@@ -267,25 +267,37 @@ template <class Model, int NT, int KS, int S> __global__ void __launch_bounds__(
 	}
 }
 
-static const int TMA2F_NT = 256, TMA2F_KS = 2, TMA2F_S = 4;
-template <class Model> static int launchTwoFactorTma(const Model& m, int T, uint64_t paths, const double* const* dW, double* const* X) {
+template <class Model, int NT, int KS, int S> static int launchTwoFactorTmaCfg(const Model& m, int T, uint64_t paths, const double* const* dW, double* const* X) {
 	Context& c = ctx();
-	auto kernel = eulerTwoFactorTmaKernel<Model, TMA2F_NT, TMA2F_KS, TMA2F_S>;
-	const size_t smem = (size_t)TMA2F_S * TMA2F_KS * 2 * (2 * TMA2F_NT) * sizeof(double) + 2 * TMA2F_S * sizeof(uint64_t);
-	static bool attr = false;
-	if (!attr) { FMB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+	auto kernel = eulerTwoFactorTmaKernel<Model, NT, KS, S>;
+	const size_t smem = (size_t)S * KS * 2 * (2 * NT) * sizeof(double) + 2 * S * sizeof(uint64_t);
+	FMB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int perSm = 0;
-	FMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, TMA2F_NT, smem));
-	const uint64_t tiles = (paths + 2 * TMA2F_NT - 1) / (2 * TMA2F_NT);
+	FMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, NT, smem));
+	const uint64_t tiles = (paths + 2 * NT - 1) / (2 * NT);
 	const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * std::max(perSm, 1), tiles));
-	kernel<<<grid, TMA2F_NT, smem, c.stream>>>(m, T, paths, dW, X);
+	kernel<<<grid, NT, smem, c.stream>>>(m, T, paths, dW, X);
 	return FMB_OK;
 }
+// (threads per CTA, time steps per stage, stages): FMB_TMA_CFG selects one for A/B runs; the defaults are the measured best per model
+// (profiles/r02_notes.md)
+template <class Model> static int launchTwoFactorTma(const Model& m, int T, uint64_t paths, const double* const* dW, double* const* X, int defaultCfg) {
+	int cfg = defaultCfg;
+	if (const char* e = getenv("FMB_TMA_CFG")) cfg = atoi(e);
+	switch (cfg) {
+	case 1: return launchTwoFactorTmaCfg<Model, 256, 4, 3>(m, T, paths, dW, X);
+	case 2: return launchTwoFactorTmaCfg<Model, 256, 8, 2>(m, T, paths, dW, X);
+	case 3: return launchTwoFactorTmaCfg<Model, 128, 4, 4>(m, T, paths, dW, X);
+	case 4: return launchTwoFactorTmaCfg<Model, 128, 8, 3>(m, T, paths, dW, X);
+	case 5: return launchTwoFactorTmaCfg<Model, 128, 2, 6>(m, T, paths, dW, X);
+	default: return launchTwoFactorTmaCfg<Model, 256, 2, 4>(m, T, paths, dW, X);
+	}
+}
 // the bulk-copy kernels need 16-byte aligned row segments: an even number of paths (FMB_EULER_TMA=0 forces the plain kernels: A/B runs)
-static bool useTwoFactorTma(uint64_t paths) {
+static bool useTwoFactorTma(uint64_t paths, bool byDefault) {
 	if (paths % 2 != 0 || paths < 2) return false;
 	const char* e = getenv("FMB_EULER_TMA");
-	return !(e && atoi(e) == 0);
+	return e ? atoi(e) != 0 : byDefault;
 }
 
 // ---- host helpers -------------------------------------------------------------------------------------------------
@@ -406,12 +418,13 @@ int fmb_euler_heston(int scheme, int heston_scheme, int T, uint64_t paths, const
 		h.rhoBar = std::sqrt(((rho * rho) - 1) * -1);      // HestonModel.java:182
 		h.hestonScheme = heston_scheme; h.scheme = scheme;
 		if (scheme == SCHEME_EULER || scheme == SCHEME_PC) h.ylog0 = y0;
-		if (useTwoFactorTma(paths)) {
+		// (Heston is bound by its exp / log / sqrt chains, not by the increment loads: the plain kernel measured faster, profiles/r02_notes.md)
+		if (useTwoFactorTma(paths, false)) {
 			HestonStep m;
 			m.h = h; m.dt = blob.at<double>(oDt); m.rate = blob.at<double>(oRate);
 			m.functional = (scheme == SCHEME_EULER_FUNCTIONAL || scheme == SCHEME_PC_FUNCTIONAL);
 			m.pc = (scheme == SCHEME_PC || scheme == SCHEME_PC_FUNCTIONAL);
-			rc = launchTwoFactorTma(m, T, paths, blob.at<const double*>(oInc), (double* const*)blob.at<double*>(oRows));
+			rc = launchTwoFactorTma(m, T, paths, blob.at<const double*>(oInc), (double* const*)blob.at<double*>(oRows), 0);
 		} else {
 			const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * 8, (paths + 255) / 256));
 			eulerHestonKernel<<<grid, 256, 0, c.stream>>>(h, T, paths, blob.at<double>(oDt), blob.at<double>(oRate), blob.at<const double*>(oInc),
@@ -448,10 +461,11 @@ int fmb_euler_hull_white(int T, uint64_t paths, const double* dt, const fmb_hand
 	const size_t oRows = blob.add(rows.data(), rows.size() * sizeof(double*));
 	int rc = blob.upload();
 	if (rc == FMB_OK && paths > 0) {
-		if (useTwoFactorTma(paths)) {
+		// (Hull-White has no transcendental in the step: HBM-bound, 0.92 of the measured copy bandwidth with the bulk-copy pipeline vs 0.68 without)
+		if (useTwoFactorTma(paths, true)) {
 			HullWhiteStep m;
 			m.dt = blob.at<double>(oDt); m.c0 = blob.at<double>(oC0); m.c1 = blob.at<double>(oC1); m.fl = blob.at<double>(oFl);
-			rc = launchTwoFactorTma(m, T, paths, blob.at<const double*>(oInc), (double* const*)blob.at<double*>(oRows));
+			rc = launchTwoFactorTma(m, T, paths, blob.at<const double*>(oInc), (double* const*)blob.at<double*>(oRows), 0);
 		} else {
 			const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * 8, (paths + 255) / 256));
 			eulerHullWhiteKernel<<<grid, 256, 0, c.stream>>>(T, paths, blob.at<double>(oDt), blob.at<double>(oC0), blob.at<double>(oC1), blob.at<double>(oFl),

@@ -720,8 +720,11 @@ static int generateIncrements(int64_t seed, int T, int F, uint64_t paths, uint64
 		fixed = (fixed + 15) & ~(size_t)15;                           // the tile starts 16-byte aligned
 		const size_t avail = budgets[attempt] > fixed ? budgets[attempt] - fixed : 0;
 		const uint64_t maxPad = avail / (TF * sizeof(double));
-		if (maxPad >= 6) { tileN = (uint32_t)std::min<uint64_t>(((maxPad - 2) / 4) * 4, 256); break; }
-		if (attempt == 2) tileN = maxPad >= 4 ? (uint32_t)((maxPad - 2) & ~1ull) : (maxPad >= 2 ? (uint32_t)(maxPad - 1) : (uint32_t)maxPad);
+		// rows of at least 16 paths: bulk-store flush (row stride tileN + 2); narrower tiles (T*F in the thousands): element-wise flush
+		// with the odd row stride tileN + 1 - bulk copies of 32-64 bytes do not pay (measured, profiles/r02_notes.md)
+		if (tma && maxPad >= 18) { tileN = (uint32_t)std::min<uint64_t>(((maxPad - 2) / 4) * 4, 256); break; }
+		if (maxPad >= 5) { tileN = (uint32_t)std::min<uint64_t>(((maxPad - 1) / 4) * 4, 256); tma = false; break; }
+		if (attempt == 2) { tileN = maxPad >= 2 ? (uint32_t)(maxPad - 1) : (uint32_t)maxPad; tma = false; }
 	}
 	// T*F so large that not even one path fits the tile: cut every path into colChunks chunks of TFk columns (a divisor of T*F that fits) and
 	// run the kernel on these "virtual paths" - the stream order is unchanged, only the flush addresses differ
@@ -734,7 +737,7 @@ static int generateIncrements(int64_t seed, int T, int F, uint64_t paths, uint64
 		tileN = 1;
 		tma = false;
 	}
-	if (tileN % 2) tma = false;
+	if (tileN % 2 || tileN < 16) tma = false;
 	// row stride: TMA: even, and = 2 (mod 8) doubles so that consecutive columns start 4 banks apart (a warp writes 32 consecutive
 	// columns of one path: 4-way instead of 16-way conflicts); element-wise flush: odd (conflict-free column writes)
 	uint32_t nPad = tileN >= 2 ? (tileN | 1u) : tileN;

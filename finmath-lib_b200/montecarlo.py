@@ -485,6 +485,8 @@ class EulerSchemeFromProcessModel:
     def getNumberOfComponents(self): return self.model.getNumberOfComponents()
 
     def getProcessValue(self, timeIndex, componentIndex=None):
+        if timeIndex < 0 or timeIndex >= self.timeDiscretization.getNumberOfTimes():
+            raise IndexError("time index %d out of bounds" % timeIndex)      # ArrayIndexOutOfBoundsException in the reference (no wrap-around)
         with self._lock:
             if self._discreteProcess is None:
                 self._precalculate()

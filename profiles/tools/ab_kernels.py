@@ -58,13 +58,18 @@ def main():
         bm = pkg.BrownianMotionCuda(td, 2, P, 31415)
         bm.getBrownianIncrement(0, 0)
         model = pkg.HestonModel(1.0, 0.05, 0.3, 0.05, 0.09, 0.1, 0.5, 0.1, 1, bm.randomVariableFactory)
-        for tma in ("0", "1"):
+        for tma, cfg in (("0", "-"), ("1", "0"), ("1", "1"), ("1", "2"), ("1", "3"), ("1", "4"), ("1", "5")):
             os.environ["FMB_EULER_TMA"] = tma
+            if cfg != "-":
+                os.environ["FMB_TMA_CFG"] = cfg
 
             def run():
                 pkg.EulerSchemeFromProcessModel(model, bm).getProcessValue(1000, 0)
             ms = best(run, reps=2)
-            out.append({"what": "Heston Euler kernel (2M paths x 1000)", "FMB_EULER_TMA": tma, "ms": ms, "GBps": P * 1000 * 32 / ms / 1e6})
+            out.append({"what": "Heston Euler kernel (2M paths x 1000)", "FMB_EULER_TMA": tma, "FMB_TMA_CFG (NT,KS,S: 0=256,2,4 1=256,4,3 2=256,8,2 3=128,4,4 4=128,8,3 5=128,2,6)": cfg,
+                        "ms": ms, "GBps": P * 1000 * 32 / ms / 1e6})
+        os.environ.pop("FMB_TMA_CFG", None)
+        os.environ.pop("FMB_EULER_TMA", None)
         del bm
         nv.load().fmb_pool_trim()
     if "c2" in which:
@@ -76,8 +81,10 @@ def main():
         bm.getBrownianIncrement(0, 0)
         hw = pkg.HullWhiteModel(bm.randomVariableFactory, pkg.TimeDiscretizationFromArray(0.0, 40, 0.5), vm)
         pkg.EulerSchemeFromProcessModel(hw, bm, 0).getProcessValue(200, 1)          # host-side coefficient tables built once
-        for tma in ("0", "1"):
+        for tma, cfg in (("0", "-"), ("1", "0"), ("1", "1"), ("1", "2"), ("1", "3"), ("1", "4"), ("1", "5")):
             os.environ["FMB_EULER_TMA"] = tma
+            if cfg != "-":
+                os.environ["FMB_TMA_CFG"] = cfg
             best_ms = 1e9
             for _ in range(3):
                 proc = pkg.EulerSchemeFromProcessModel(hw, bm, 0)
@@ -86,7 +93,9 @@ def main():
                 nv.timer_start()
                 proc._precalculate_fused(spec)
                 best_ms = min(best_ms, nv.timer_stop_ms())
-            out.append({"what": "Hull-White Euler kernel (4M paths x 200)", "FMB_EULER_TMA": tma, "ms": best_ms, "GBps": P * 200 * 32 / best_ms / 1e6})
+            out.append({"what": "Hull-White Euler kernel (4M paths x 200)", "FMB_EULER_TMA": tma, "FMB_TMA_CFG": cfg, "ms": best_ms, "GBps": P * 200 * 32 / best_ms / 1e6})
+        os.environ.pop("FMB_TMA_CFG", None)
+        os.environ.pop("FMB_EULER_TMA", None)
     for o in out:
         print(json.dumps(o), flush=True)
 

@@ -233,7 +233,9 @@ def test_lmm_forward_rate_and_numeraire_between_tenor_points(gpu, orc, measure, 
     points :969-1006 and the log-linear interpolation of the discount-curve adjustment :886-905; simulation times off the grid are rounded
     to the nearest point (:1248-1253)."""
     paths = 5000
-    s = lmm_setup(gpu)
+    # (under the terminal measure the reference reads the LIBORs at the requested time itself, :986, so that time must be a simulation time:
+    #  a quarter-year simulation grid under the half-year tenor)
+    s = lmm_setup(gpu, dt=0.5 if measure == "SPOT" else 0.25)
     tenor = s["tenor"]
     s["df"] = np.array([np.exp(-0.035 * tenor.getTime(i)) for i in range(s["N"] + 1)])
     factory = gpu.RandomVariableCudaFactory()
@@ -252,8 +254,11 @@ def test_lmm_forward_rate_and_numeraire_between_tenor_points(gpu, orc, measure, 
         got = dev.getForwardRate(t, a, b).getRealizations()
         want = ref.forward_rate(t, a, b)
         assert rel_err(got, want, scale=0.05) < PATH_TOL, (t, a, b)
-    for t in (2.3, 0.7, 7.25, 2.0):
+    for t in ((2.3, 0.7, 7.25, 2.0) if measure == "SPOT" else (2.25, 0.75, 7.25, 2.0)):
         assert rel_err(dev.getNumeraire(t).getRealizations(), ref.numeraire(t)) < PATH_TOL, t
+    if measure == "TERMINAL":                                # a time that is not a simulation time: the reference indexes out of bounds there
+        with pytest.raises(IndexError):
+            dev.getNumeraire(2.3)
 
 
 def test_hull_white_numeraire_between_simulation_times(gpu, orc):
