@@ -265,6 +265,28 @@ static int finishLaunch(fmb_handle* out) {
 	return FMB_OK;
 }
 
+
+// ---- multi-period forward rate: ((1 + L_a d_a)(1 + L_{a+1} d_{a+1}) ... - 1) / (T_b - T_a) in ONE pass.
+// LIBORMarketModelFromCovarianceModel.getForwardRate (:1288-1302) builds it with one accrue() pass per period - up to 20 passes for the
+// long rate of a Bermudan's basis functions, 210 over a valuation.  Same operations in the same order (l.mult(d).add(1.0), then
+// accrue = x * (1 + y * a) per period, then sub(1.0).div(length)), so the result is bit-identical to the op-by-op evaluation.
+struct AccrueChainArgs {
+	const double* rate[32];
+	double delta[32];
+};
+__global__ void __launch_bounds__(256) accrueChainKernel(AccrueChainArgs a, int n, const double* __restrict__ accIn, int finalize, double divisor,
+		double* __restrict__ out, uint64_t len) {
+	const uint64_t stride = (uint64_t)gridDim.x * 256;
+	for (uint64_t i = blockIdx.x * (uint64_t)256 + threadIdx.x; i < len; i += stride) {
+		double acc;
+		int k = 0;
+		if (accIn) acc = accIn[i];
+		else { acc = a.rate[0][i] * a.delta[0] + 1.0; k = 1; }
+		for (; k < n; k++) acc = acc * (1 + a.rate[k][i] * a.delta[k]);
+		out[i] = finalize ? (acc - 1.0) / divisor : acc;
+	}
+}
+
 } // namespace fmb
 
 using namespace fmb;
@@ -417,6 +439,37 @@ int fmb_rv_eval_chain(int n_instr, const unsigned char* code, int start_leaf, co
 	for (int i = 0; i < n_leaves; i++) vec = vec && aligned16(p.leaf[i]);
 	chainKernel<<<ewGrid(n), 256, 0, ctx().stream>>>(p, dst, n, n_leaves, vec);
 	return finishLaunch(out);
+}
+
+int fmb_rv_accrue_chain(int n, const fmb_handle* rates, const double* period_lengths, double divisor, fmb_handle* out) {
+	FMB_TRY(requireInit());
+	PinScope pins;
+	if (n < 1 || !rates || !period_lengths || !out) { setError("accrue_chain: bad argument"); return FMB_EINVAL; }
+	uint64_t len = 0;
+	std::vector<const double*> ptr(n);
+	for (int k = 0; k < n; k++) {
+		Vec* v;
+		if (rates[k] == 0) { setError("accrue_chain: rate %d is not a device vector", k); return FMB_EINVAL; }
+		FMB_TRY(lookup(rates[k], &v));
+		if (k > 0 && v->n != len) { setError("operand sizes differ (%llu vs %llu)", (unsigned long long)v->n, (unsigned long long)len); return FMB_EINVAL; }
+		len = v->n;
+		ptr[k] = v->ptr;
+	}
+	double* dst;
+	FMB_TRY(newVec(len, out, &dst));
+	if (len == 0) return FMB_OK;
+	const int grid = ewGrid(len);
+	const double* accIn = nullptr;
+	for (int k0 = 0; k0 < n; k0 += 32) {                       // (more than 32 periods: the partial product is carried in the result vector)
+		AccrueChainArgs a;
+		const int m = std::min(32, n - k0);
+		for (int k = 0; k < 32; k++) { a.rate[k] = k < m ? ptr[k0 + k] : nullptr; a.delta[k] = k < m ? period_lengths[k0 + k] : 0.0; }
+		accrueChainKernel<<<grid, 256, 0, ctx().stream>>>(a, m, accIn, k0 + m >= n ? 1 : 0, divisor, dst, len);
+		countLaunch();
+		accIn = dst;
+	}
+	FMB_CUDA(cudaGetLastError());
+	return FMB_OK;
 }
 
 } // extern "C"

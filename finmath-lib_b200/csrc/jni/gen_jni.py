@@ -47,6 +47,8 @@ TABLE = [
     ("binary", "fmb_rv_binary", "handle", [("i", "op"), ("h", "x"), ("d", "sx"), ("h", "y"), ("d", "sy")], "op, (fmb_handle)x, sx, (fmb_handle)y, sy, OUT"),
     ("ternary", "fmb_rv_ternary", "handle", [("i", "op"), ("h", "x"), ("d", "sx"), ("h", "y"), ("d", "sy"), ("h", "z"), ("d", "sz"), ("d", "a")],
      "op, (fmb_handle)x, sx, (fmb_handle)y, sy, (fmb_handle)z, sz, a, OUT"),
+    ("accrueChain", "fmb_rv_accrue_chain", "handle", [("H", "rates"), ("D", "periodLengths"), ("d", "divisor")],
+     "rates_n, (const fmb_handle*)rates_p, periodLengths_p, divisor, OUT"),
     ("evalChain", "fmb_rv_eval_chain", "handle", [("B", "code"), ("i", "startLeaf"), ("H", "leaves"), ("D", "scalars")],
      "code_n / 8, (const unsigned char*)code_p, startLeaf, (const fmb_handle*)leaves_p, leaves_n, scalars_p, scalars_n, OUT"),
     ("reduce", "fmb_rv_reduce", "doubles:2", [("i", "op"), ("h", "x"), ("h", "w"), ("d", "a")], "op, (fmb_handle)x, (fmb_handle)w, a, OUT"),

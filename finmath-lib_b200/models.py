@@ -16,7 +16,8 @@ import weakref
 import numpy as np
 
 from .montecarlo import BrownianMotionCuda, EulerSchemeFromProcessModel, Scheme
-from .stochastic import RandomVariableCudaFactory, Scalar
+from .stochastic import RandomVariableCuda, RandomVariableCudaFactory, Scalar
+from . import native as nv
 
 
 class BlackScholesModel:
@@ -207,6 +208,20 @@ class LIBORCovarianceModelFromVolatilityAndCorrelation:
                     fl[t, j, k] = vol * self.correlationModel.getFactorLoading(t, k, j)
                 var[t, j] = (vol * vol) * self.correlationModel.getCorrelation(t, j, j)
         return fl, var
+
+
+def _accrue_chain(libors, subs, divisor):
+    """((1 + L_a d_a) ... (1 + L_{b-1} d_{b-1}) - 1) / divisor in one kernel (fmb_rv_accrue_chain) when every rate is a device vector of
+    the same shard; the same operations in the same order as the loop of accrue() calls it replaces (bit-identical).  None otherwise."""
+    import ctypes as C
+    first = libors[0]
+    if len(libors) < 3 or not all(type(l) is RandomVariableCuda and l.dv is not None and l.dv.n == first.dv.n and l.shard is first.shard for l in libors):
+        return None
+    hs = np.array([l.dv.h for l in libors], dtype=np.uint64)
+    ds = np.array(subs, dtype=np.float64)
+    out = C.c_uint64()
+    nv.check(nv.load().fmb_rv_accrue_chain(len(libors), nv.hptr(hs), nv.dptr(ds), float(divisor), C.byref(out)))
+    return RandomVariableCuda(max(l.time for l in libors), None, first.shard, _dv=nv.DeviceVector(out.value, first.dv.n), _n=first.nGlobal)
 
 
 class LIBORMarketModelFromCovarianceModel:
@@ -419,10 +434,13 @@ class LIBORMarketModelFromCovarianceModel:
             return onePlusLongLIBORdt.mult(onePlusInterpolatedLIBORDt).sub(1.0).div(periodEnd - periodStart)
         if ps + 1 == pe:
             return self.getLIBOR(process, ti, ps)
+        libors = [self.getLIBOR(process, ti, k) for k in range(ps, pe)]
+        subs = [self.getLiborPeriod(k + 1) - self.getLiborPeriod(k) for k in range(ps, pe)]
+        fused = _accrue_chain(libors, subs, periodEnd - periodStart)
+        if fused is not None:
+            return fused
         acc = None
-        for k in range(ps, pe):
-            sub = self.getLiborPeriod(k + 1) - self.getLiborPeriod(k)
-            l = self.getLIBOR(process, ti, k)
+        for l, sub in zip(libors, subs):                     # :1288-1302, one pass per period
             acc = l.mult(sub).add(1.0) if acc is None else acc.accrue(l, sub)
         return acc.sub(1.0).div(periodEnd - periodStart)
 

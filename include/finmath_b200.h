@@ -102,6 +102,12 @@ int fmb_rv_unary(int op, fmb_handle x, double a, fmb_handle* out);
 int fmb_rv_binary(int op, fmb_handle x, double sx, fmb_handle y, double sy, fmb_handle* out);
 int fmb_rv_ternary(int op, fmb_handle x, double sx, fmb_handle y, double sy, fmb_handle z, double sz, double a, fmb_handle* out);
 
+/* ((1 + r_0 d_0)(1 + r_1 d_1) ... (1 + r_{n-1} d_{n-1}) - 1) / divisor in ONE pass: the multi-period forward rate of
+ * LIBORMarketModelFromCovarianceModel.getForwardRate (J/montecarlo/interestrate/models/LIBORMarketModelFromCovarianceModel.java:1288-1302),
+ * which the reference builds with one accrue() pass per period.  Same operations and order (r_0.mult(d_0).add(1.0), accrue per further
+ * period, sub(1.0).div(divisor)): bit-identical to the op-by-op evaluation. */
+int fmb_rv_accrue_chain(int n, const fmb_handle* rates, const double* period_lengths, double divisor, fmb_handle* out);
+
 /* A chain of element-wise operations evaluated in ONE pass over the vectors (deferred evaluation in the host binding: a result that
  * is only consumed by the next operation never becomes a vector in HBM).  acc = leaves[start_leaf][i]; instruction k replaces acc by
  * its operation with acc at operand position `pos`; the other operands are leaf vectors or broadcast scalars.  Same device functions,

@@ -44,6 +44,7 @@ int fmb_rv_unary(int op, fmb_handle x, double a, fmb_handle* o) { *o = mk(sz(x))
 int fmb_rv_binary(int op, fmb_handle x, double sx, fmb_handle y, double sy, fmb_handle* o) { *o = mk(sz(x ? x : y)); launches++; return 0; }
 int fmb_rv_ternary(int op, fmb_handle x, double sx, fmb_handle y, double sy, fmb_handle z, double sz_, double a, fmb_handle* o) {
 	*o = mk(sz(x ? x : (y ? y : z))); launches++; return 0; }
+int fmb_rv_accrue_chain(int n, const fmb_handle* r, const double* d, double div, fmb_handle* o) { *o = mk(sz(r[0])); launches++; return 0; }
 int fmb_rv_eval_chain(int n, const unsigned char* code, int s, const fmb_handle* l, int nl, const double* sc, int ns, fmb_handle* o) { *o = mk(sz(l[0])); launches++; return 0; }
 int fmb_rv_reduce(int op, fmb_handle x, fmb_handle w, double a, double* o) { o[0] = 0.5 * (double)sz(x); o[1] = 0; launches++; return 0; }
 int fmb_rv_select(fmb_handle x, uint64_t r, double* o) { *o = 0; return 0; }

@@ -65,7 +65,7 @@ jlong J(create)(JNIEnv*, jclass, jlong); jlong J(upload)(JNIEnv*, jclass, jdoubl
 jdoubleArray J(download)(JNIEnv*, jclass, jlong); jdouble J(get)(JNIEnv*, jclass, jlong, jlong); jlong J(size)(JNIEnv*, jclass, jlong);
 void J(retain)(JNIEnv*, jclass, jlong); void J(free)(JNIEnv*, jclass, jlong); void J(freeMany)(JNIEnv*, jclass, jlongArray); jlong J(devicePointer)(JNIEnv*, jclass, jlong); jlongArray J(poolStats)(JNIEnv*, jclass);
 void J(poolTrim)(JNIEnv*, jclass); jlong J(unary)(JNIEnv*, jclass, jint, jlong, jdouble); jlong J(binary)(JNIEnv*, jclass, jint, jlong, jdouble, jlong, jdouble);
-jlong J(ternary)(JNIEnv*, jclass, jint, jlong, jdouble, jlong, jdouble, jlong, jdouble, jdouble); jlong J(evalChain)(JNIEnv*, jclass, jbyteArray, jint, jlongArray, jdoubleArray);
+jlong J(ternary)(JNIEnv*, jclass, jint, jlong, jdouble, jlong, jdouble, jlong, jdouble, jdouble); jlong J(evalChain)(JNIEnv*, jclass, jbyteArray, jint, jlongArray, jdoubleArray); jlong J(accrueChain)(JNIEnv*, jclass, jlongArray, jdoubleArray, jdouble);
 jdoubleArray J(reduce)(JNIEnv*, jclass, jint, jlong, jlong, jdouble); jdouble J(select)(JNIEnv*, jclass, jlong, jlong); jdoubleArray J(rangeSum)(JNIEnv*, jclass, jlong, jdouble, jdouble); jlongArray J(countLessOrEqual)(JNIEnv*, jclass, jlong, jdoubleArray);
 jintArray J(mtWords)(JNIEnv*, jclass, jlong, jlong, jint); jdoubleArray J(mtUniforms)(JNIEnv*, jclass, jlong, jlong, jint); jdoubleArray J(icdf)(JNIEnv*, jclass, jdoubleArray);
 jlongArray J(brownianGenerate)(JNIEnv*, jclass, jint, jint, jint, jlong, jlong, jdoubleArray);
@@ -123,7 +123,7 @@ static void noDevice(void) {
 	THROWS(RTE, J(create)(env, NULL, 10)); THROWS(RTE, J(upload)(env, NULL, doubles(3, v))); THROWS(RTE, J(fill)(env, NULL, 1.0, 10));
 	THROWS(RTE, J(download)(env, NULL, 1)); THROWS(RTE, J(get)(env, NULL, 1, 0)); THROWS(RTE, J(devicePointer)(env, NULL, 1));
 	THROWS(RTE, J(unary)(env, NULL, 0, 1, 0.0)); THROWS(RTE, J(binary)(env, NULL, 0, 1, 0.0, 2, 0.0)); THROWS(RTE, J(ternary)(env, NULL, 0, 1, 0, 2, 0, 3, 0, 0));
-	THROWS(RTE, J(evalChain)(env, NULL, bc, 0, longs(2, hs), doubles(2, sq))); THROWS(RTE, J(reduce)(env, NULL, 0, 1, 0, 0.0)); THROWS(RTE, J(select)(env, NULL, 1, 0)); THROWS(RTE, J(rangeSum)(env, NULL, 1, 0.0, 1.0));
+	THROWS(RTE, J(evalChain)(env, NULL, bc, 0, longs(2, hs), doubles(2, sq))); THROWS(RTE, J(accrueChain)(env, NULL, longs(2, hs), doubles(2, sq), 1.0)); THROWS(RTE, J(reduce)(env, NULL, 0, 1, 0, 0.0)); THROWS(RTE, J(select)(env, NULL, 1, 0)); THROWS(RTE, J(rangeSum)(env, NULL, 1, 0.0, 1.0));
 	THROWS(RTE, J(countLessOrEqual)(env, NULL, 1, doubles(2, sq))); THROWS(RTE, J(mtWords)(env, NULL, 3141, 0, 4)); THROWS(RTE, J(mtUniforms)(env, NULL, 3141, 0, 4));
 	THROWS(RTE, J(icdf)(env, NULL, doubles(3, v))); THROWS(RTE, J(brownianGenerate)(env, NULL, 3141, 2, 1, 10, 0, doubles(2, sq)));
 	THROWS(RTE, J(uniformsGenerate)(env, NULL, 3141, 2, 1, 10, 0));
@@ -211,6 +211,8 @@ static void onGpu(void) {
 	jbyteArray bc = fNewByteArray(env, 16); memcpy(bc->data, code, 16);
 	jlong leaves[2]; leaves[0] = x; leaves[1] = y; double sc[1] = { 2.0 };
 	jlong ch = 0; OK(ch = J(evalChain)(env, NULL, bc, 0, longs(2, leaves), doubles(1, sc))); OK(d = J(download)(env, NULL, ch)); EXPECT(D(d)[2] == 3 * 2 + 2.0, "chain");
+	{ jlong two[2]; two[0] = x; two[1] = y; const double dl[2] = { 0.5, 0.5 }; jlong ac = 0; OK(ac = J(accrueChain)(env, NULL, longs(2, two), doubles(2, dl), 1.0));
+	  OK(d = J(download)(env, NULL, ac)); EXPECT(D(d)[0] == ((1 * 0.5 + 1.0) * (1 + 0.5 * 0.5) - 1.0) / 1.0, "accrue chain"); }
 	OK(J(timerStart)(env, NULL)); jdouble ms = -1; OK(ms = J(timerStopMs)(env, NULL)); EXPECT(ms >= 0, "timer");
 	jdouble tf = 0; OK(tf = J(benchDfmaTflops)(env, NULL)); EXPECT(tf > 1, "DFMA peak"); jdouble gb = 0; OK(gb = J(benchCopyGbs)(env, NULL, 1 << 26)); EXPECT(gb > 100, "copy bandwidth");
 	OK(J(synchronize)(env, NULL));

@@ -282,6 +282,24 @@ def test_hull_white_numeraire_between_simulation_times(gpu, orc):
     assert abs(price - ref_price) <= PRICE_TOL * abs(ref_price)
 
 
+def test_multi_period_forward_rate_in_one_kernel_equals_the_accrue_loop(gpu):
+    """getForwardRate over several tenor periods (:1288-1302) runs as ONE kernel (fmb_rv_accrue_chain) instead of one accrue() pass per
+    period: same operations, same order, so the bits equal the op-by-op loop - also beyond 32 periods (chunked)."""
+    for n_libors, period, t_index, start, end in ((40, 0.5, 10, 5.0, 15.0), (80, 0.25, 1, 0.25, 20.0)):
+        s = lmm_setup(gpu, n_libors=n_libors, period=period, dt=period)
+        dev = lmm_device(gpu, s, 3001)
+        model, process = dev.getModel(), dev.getProcess()
+        fused = dev.getForwardRate(start, start, end)
+        k0, k1 = model.getLiborPeriodIndex(start), model.getLiborPeriodIndex(end)
+        acc = None
+        for k in range(k0, k1):
+            libor, sub = model.getLIBOR(process, t_index, k), model.getLiborPeriod(k + 1) - model.getLiborPeriod(k)
+            acc = libor.mult(sub).add(1.0) if acc is None else acc.accrue(libor, sub)
+        loop = acc.sub(1.0).div(end - start)
+        assert np.array_equal(fused.getRealizations(), loop.getRealizations())
+        assert fused.getFiltrationTime() == loop.getFiltrationTime()
+
+
 def test_swaption_discounting_adjustment_with_a_separate_discount_curve(gpu, orc):
     """Swaption.java:160-171: with a discount curve that is NOT the one implied by the forward curve every period's value is scaled by
     forwardBondOnForwardCurve / forwardBondOnDiscountCurve.  The oracle gets the adjustments as an explicit array (computed here from
