@@ -573,7 +573,11 @@ int fmb_euler_lmm(int scheme, int measure, int state_space, double libor_cap, in
 		}
 		if (rc == FMB_OK) {
 			L.scratch = (double*)scratch;
-			rc = launcher(L, c.smCount, true);
+			// FMB_LMM_VARIANT=shuffle: the experimental lane-per-rate kernel (warp-shuffle prefix sums, fmb_euler_lmm_shuffle.cu) for A/B runs
+			const char* variant = getenv("FMB_LMM_VARIANT");
+			int vr = FMB_EUNSUPPORTED;
+			if (variant && strcmp(variant, "shuffle") == 0) vr = lmmLaunchLanePerRate(L, c.smCount);
+			rc = vr == FMB_EUNSUPPORTED ? launcher(L, c.smCount, true) : vr;
 			if (rc == FMB_OK) rc = launchCheck("euler_lmm");
 		}
 	}

@@ -337,6 +337,7 @@ template <int FT> static int lmmLaunchF(LmmLaunch& a, int smCount, bool launchNo
 #define FMB_LMM_DECLARE(FT) int lmmLaunchF##FT(LmmLaunch& a, int smCount, bool launchNow);
 FMB_LMM_DECLARE(0) FMB_LMM_DECLARE(1) FMB_LMM_DECLARE(2) FMB_LMM_DECLARE(3) FMB_LMM_DECLARE(4)
 FMB_LMM_DECLARE(5) FMB_LMM_DECLARE(6) FMB_LMM_DECLARE(7) FMB_LMM_DECLARE(8)
+int lmmLaunchLanePerRate(LmmLaunch& a, int smCount);   // experiment, fmb_euler_lmm_shuffle.cu
 #define FMB_LMM_DEFINE(FT) int lmmLaunchF##FT(LmmLaunch& a, int smCount, bool launchNow) { return lmmLaunchF<FT>(a, smCount, launchNow); }
 
 } // namespace fmb

@@ -40,8 +40,34 @@ def bm_only(T, dt, F, P):
 
 
 def main():
-    which = sys.argv[1:] or ["c4", "c3", "c2"]
+    which = sys.argv[1:] or ["c4", "c3", "c2", "lmm"]
     out = []
+    if "lmm" in which:
+        # production LMM Euler kernel (lane per path, serial prefix sum in registers) vs the experimental lane-per-rate kernel (warp-shuffle scans)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from common import lmm_setup
+        s_ = lmm_setup(pkg)
+        P = 4_000_000
+        factory = pkg.RandomVariableCudaFactory()
+        model = pkg.LIBORMarketModelFromCovarianceModel.of(s_["tenor"], None, s_["L0"], s_["df"], factory, s_["cov"], None, {"measure": "SPOT", "stateSpace": "LOGNORMAL"})
+        bm = pkg.BrownianMotionCuda(s_["sim"], 3, P, 3141, factory)
+        bm.getBrownianIncrement(0, 0)
+        vals = {}
+        for variant in ("production", "shuffle"):
+            os.environ["FMB_LMM_VARIANT"] = variant
+
+            def run():
+                pkg.EulerSchemeFromProcessModel(model, bm, 2).getProcessValue(40, 39)
+            ms = best(run)
+            proc = pkg.EulerSchemeFromProcessModel(model, bm, 2)
+            vals[variant] = [proc.getProcessValue(t, j).getRealizations()[:200_000] for t, j in ((1, 39), (20, 21), (40, 39))]
+            out.append({"what": "LMM Euler kernel C4 (4M paths, 780 live rate-steps per path)", "FMB_LMM_VARIANT": variant, "ms": ms})
+            del proc
+        os.environ.pop("FMB_LMM_VARIANT", None)
+        dev = max(float(np.max(np.abs(a - b) / np.maximum(np.abs(a), 0.05))) for a, b in zip(vals["production"], vals["shuffle"]))
+        out.append({"what": "max relative deviation lane-per-rate vs production (scale 0.05)", "value": dev})
+        del bm, vals
+        nv.load().fmb_pool_trim()
     if "c4" in which:
         for tma in ("0", "1"):
             os.environ["FMB_BM_TMA"] = tma
