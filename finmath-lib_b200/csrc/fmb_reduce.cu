@@ -239,6 +239,56 @@ __host__ __device__ inline void jacobiPinvSolve(int K, double* U, double* V, dou
 	}
 }
 
+// The same algorithm with K known at compile time and every loop unrolled: on the device U and V then live in registers (the rotation chain is
+// latency-bound, 65 us -> see profiles/r02_notes.md).  Same operations in the same order: bit-identical to the run-time-K version.
+template <int K> __host__ __device__ inline void jacobiPinvSolveT(double* U, double* V, double* s, const double* b, double* x, double* cond) {
+	_Pragma("unroll") for (int i = 0; i < K * K; i++) V[i] = 0.0;
+	_Pragma("unroll") for (int i = 0; i < K; i++) V[i * K + i] = 1.0;
+	for (int sweep = 0; sweep < 60; sweep++) {
+		bool rotated = false;
+		_Pragma("unroll") for (int p = 0; p < K - 1; p++) _Pragma("unroll") for (int q = p + 1; q < K; q++) {
+			double alpha = 0, beta = 0, gamma = 0;
+			_Pragma("unroll") for (int i = 0; i < K; i++) {
+				const double up = U[i * K + p], uq = U[i * K + q];
+				alpha += up * up; beta += uq * uq; gamma += up * uq;
+			}
+			if (gamma == 0.0 || fabs(gamma) <= 1e-300) continue;
+			if (fabs(gamma) <= 0x1.0p-53 * sqrt(alpha * beta)) continue;
+			rotated = true;
+			const double zeta = (beta - alpha) / (2.0 * gamma);
+			const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+			const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+			_Pragma("unroll") for (int i = 0; i < K; i++) {
+				const double up = U[i * K + p], uq = U[i * K + q];
+				U[i * K + p] = cs * up - sn * uq;
+				U[i * K + q] = sn * up + cs * uq;
+				const double vp = V[i * K + p], vq = V[i * K + q];
+				V[i * K + p] = cs * vp - sn * vq;
+				V[i * K + q] = sn * vp + cs * vq;
+			}
+		}
+		if (!rotated) break;
+	}
+	double smax = 0.0, smin = INFINITY;
+	_Pragma("unroll") for (int j = 0; j < K; j++) {
+		double nn = 0;
+		_Pragma("unroll") for (int i = 0; i < K; i++) nn += U[i * K + j] * U[i * K + j];
+		s[j] = sqrt(nn);
+		smax = s[j] > smax ? s[j] : smax; smin = s[j] < smin ? s[j] : smin;
+	}
+	if (cond) *cond = smax / smin;
+	const double tolA = (double)K * smax * 0x1.0p-52, tolB = 1.4916681462400413e-154 /* sqrt(2^-1022) */;
+	const double tol = tolA > tolB ? tolA : tolB;
+	_Pragma("unroll") for (int k = 0; k < K; k++) x[k] = 0.0;
+	_Pragma("unroll") for (int j = 0; j < K; j++) {
+		if (s[j] <= tol) continue;
+		double ub = 0;                              // (u_j . b) / s_j, with u_j = U[:,j] / s_j
+		_Pragma("unroll") for (int i = 0; i < K; i++) ub += U[i * K + j] * b[i];
+		const double wgt = ub / (s[j] * s[j]);
+		_Pragma("unroll") for (int k = 0; k < K; k++) x[k] += V[k * K + j] * wgt;
+	}
+}
+
 struct BasisArgs {
 	const double* ptr[8];
 	double scalar[8];
@@ -258,7 +308,6 @@ struct FitArgs {
 template <int K> __device__ void regressionFinish(const double* __restrict__ src, const BasisArgs& b, const FitArgs& f) {
 	constexpr int M = K * (K + 1) / 2 + K;
 	__shared__ double mean[M];
-	__shared__ double U[K * K], V[K * K], sv[K], rhs[K], xs[K];
 	if (threadIdx.x < M) {
 		const int m = threadIdx.x;
 		dd t = { __ldcg(src + 2 * m), __ldcg(src + 2 * m + 1) };
@@ -267,8 +316,12 @@ template <int K> __device__ void regressionFinish(const double* __restrict__ src
 	}
 	__syncthreads();
 	if (threadIdx.x == 0) {
+		double U[K * K], V[K * K], sv[K], rhs[K], xs[K];
 		int m = 0;
-		for (int p = 0; p < K; p++) for (int q = p; q < K; q++) {
+#pragma unroll
+		for (int p = 0; p < K; p++)
+#pragma unroll
+		for (int q = p; q < K; q++) {
 			double v = mean[m++];
 			// deterministic x deterministic: the reference's mult() stays a scalar and its average is the product itself
 			if (b.ptr[p] == nullptr && b.ptr[q] == nullptr) v = b.scalar[p] * b.scalar[q];
@@ -276,9 +329,11 @@ template <int K> __device__ void regressionFinish(const double* __restrict__ src
 			U[p * K + q] = U[q * K + p] = v;
 			f.fit[FIT_XTX + p * K + q] = f.fit[FIT_XTX + q * K + p] = v;
 		}
+#pragma unroll
 		for (int p = 0; p < K; p++) { rhs[p] = mean[m++]; f.fit[FIT_XTY + p] = rhs[p]; }
 		double cond;
-		jacobiPinvSolve(K, U, V, sv, rhs, xs, &cond);
+		jacobiPinvSolveT<K>(U, V, sv, rhs, xs, &cond);
+#pragma unroll
 		for (int p = 0; p < K; p++) f.fit[FIT_X + p] = xs[p];
 		f.fit[FIT_COND] = cond;
 	}
@@ -552,7 +607,19 @@ int fmb_regression_moments(int K, const fmb_handle* basis, const double* basis_s
 int fmb_regression_solve_svd(int K, const double* A, const double* b, double* x, double* cond) {
 	if (K < 1 || !A || !b || !x) { setError("solve_svd: bad argument"); return FMB_EINVAL; }
 	std::vector<double> U(A, A + (size_t)K * K), V((size_t)K * K, 0.0), s(K);
-	jacobiPinvSolve(K, U.data(), V.data(), s.data(), b, x, cond);
+	double condLocal = 0.0;
+	double* cp = cond ? cond : &condLocal;
+	switch (K) {                                    // (the same code as the device-resident regression runs: identical coefficients)
+	case 1: jacobiPinvSolveT<1>(U.data(), V.data(), s.data(), b, x, cp); break;
+	case 2: jacobiPinvSolveT<2>(U.data(), V.data(), s.data(), b, x, cp); break;
+	case 3: jacobiPinvSolveT<3>(U.data(), V.data(), s.data(), b, x, cp); break;
+	case 4: jacobiPinvSolveT<4>(U.data(), V.data(), s.data(), b, x, cp); break;
+	case 5: jacobiPinvSolveT<5>(U.data(), V.data(), s.data(), b, x, cp); break;
+	case 6: jacobiPinvSolveT<6>(U.data(), V.data(), s.data(), b, x, cp); break;
+	case 7: jacobiPinvSolveT<7>(U.data(), V.data(), s.data(), b, x, cp); break;
+	case 8: jacobiPinvSolveT<8>(U.data(), V.data(), s.data(), b, x, cp); break;
+	default: jacobiPinvSolve(K, U.data(), V.data(), s.data(), b, x, cp); break;
+	}
 	return FMB_OK;
 }
 
