@@ -141,7 +141,8 @@ def test_order_statistics_by_radix_select_match_the_sorted_reference(gpu, orc):
         for q in (0.0, 0.001, 0.3, 0.5, 0.77, 0.999, 1.0):
             got, want = g.getQuantile(q), s[min(max(int(np.floor((n + 1) * q - 1 + 0.5)), 0), n - 1)]
             assert (got == want) or (np.isnan(got) and np.isnan(want)), (n, q, got, want)
-            assert got == orc.rv_reduce(9, x, a=q) or np.isnan(got)
+            if not np.isnan(x).any():                        # (the oracle's std::sort is undefined with NaN in the data; numpy sorts like Arrays.sort)
+                assert got == orc.rv_reduce(9, x, a=q)
         if not np.isnan(x).any():
             for q0, q1 in ((0.1, 0.9), (0.0, 1.0), (0.45, 0.55), (0.3, 0.3)):
                 i0 = min(max(int(np.floor((n + 1) * q0 - 1 + 0.5)), 0), n - 1)
