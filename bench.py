@@ -94,24 +94,57 @@ def market(pkg):
     return lmm_setup(pkg, n_libors=N_LIBORS, n_factors=N_FACTORS, period=PERIOD, dt=PERIOD)
 
 
+def reference_inputs(orc):
+    """The C4 market data for the reference arm, built WITHOUT the product package (numpy + the oracle's time grid only): four-parameter
+    volatility sigma_j(t_i) = (a + b tau) exp(-c tau) + d (0 once fixed), correlation exp(-0.1 |T_i - T_j|) reduced to 3 factors like
+    LinearAlgebra.factorReduction (eigen-decomposition, largest eigenvalues, first entry positive, row renormalisation, second pass).
+    tests/test_cpu_host.py checks that it agrees with the product's own tables."""
+    import math
+    sim = orc.time_discretization(0.0, int(round(N_LIBORS * PERIOD / PERIOD)), PERIOD)
+    tenor = orc.time_discretization(0.0, N_LIBORS, PERIOD)
+    T, N = sim.size - 1, tenor.size - 1
+    a, b, c, d = 0.2, 0.0, 0.25, 0.3
+    sigma = np.zeros((T, N))
+    for t in range(T):
+        for j in range(N):
+            ttm = tenor[j] - sim[t]
+            sigma[t, j] = 0.0 if ttm <= 0 else (b * ttm + a) * math.exp(c * (-ttm)) + d
+
+    def factor_matrix(corr, F):
+        ev, V = np.linalg.eigh(corr)
+        order = np.argsort(-ev, kind="stable")
+        fm = np.zeros((corr.shape[0], F))
+        for f in range(F):
+            v = V[:, order[f]]
+            sign = 1.0 if v[0] > 0.0 else -1.0
+            fm[:, f] = sign * math.sqrt(max(float(ev[order[f]]), 0.0) / float(np.sum(v * v))) * v
+        return fm
+    corr = np.array([[math.exp(-0.1 * abs(tenor[r] - tenor[c_])) for c_ in range(N)] for r in range(N)])
+    fm = factor_matrix(corr, N_FACTORS)
+    for row in range(N):
+        fm[row] = fm[row] / math.sqrt(float(np.sum(fm[row] * fm[row])))
+    fm = factor_matrix(fm @ fm.T, N_FACTORS)
+    return {"sim": sim, "tenor": tenor, "sigma": sigma, "factor_matrix": fm, "L0": np.full(N, 0.05), "T": T}
+
+
 def run_reference(args):
-    """Reference arm: the reference's CPU path (oracle port, all host threads) on a bounded sample of the same workload."""
+    """Reference arm: the reference's CPU path (oracle port, all host threads) on a bounded sample of the same workload.  Nothing of the
+    product package is on this path: inputs from reference_inputs(), arithmetic in oracle/."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    pkg = graft.load_package()
     orc = graft.load_oracle()
-    s = market(pkg)
+    s = reference_inputs(orc)
     cores = os.cpu_count() or 1
     T = s["T"]
     sample = args.cpu_paths
-    sec, _ = orc.time_lmm_fused(3141, s["sim"].times, s["tenor"].times, N_FACTORS, min(sample, 20000), s["L0"], s["sigma"], s["factor_matrix"], args.scheme, cores)
+    sec, _ = orc.time_lmm_fused(3141, s["sim"], s["tenor"], N_FACTORS, min(sample, 20000), s["L0"], s["sigma"], s["factor_matrix"], args.scheme, cores)
     inner = max(1, int(4.0 / max(sec * sample / min(sample, 20000), 1e-3)))       # each timed step ~4 s of CPU work
     times = []
     for _ in range(args.warmup + args.steps):
         sec = 0.0
         for r in range(inner):
-            dt_, _ = orc.time_lmm_fused(3141 + r, s["sim"].times, s["tenor"].times, N_FACTORS, sample, s["L0"], s["sigma"], s["factor_matrix"], args.scheme, cores)
+            dt_, _ = orc.time_lmm_fused(3141 + r, s["sim"], s["tenor"], N_FACTORS, sample, s["L0"], s["sigma"], s["factor_matrix"], args.scheme, cores)
             sec += dt_
         times.append(sec)
     times = times[args.warmup:]
@@ -256,8 +289,8 @@ def main():
     traffic = None
     try:
         if P_local == 4_000_000 and args.scheme == 2:
-            for k in json.load(open(os.path.join(ROOT, "profiles", "r01_top_kernels_ncu.json"))):
-                if "eulerLmmKernel" in k["Kernel Name"]:
+            for k in json.load(open(os.path.join(ROOT, "profiles", "r02_top_kernels_ncu.json"))):
+                if "eulerLmmKernel" in k["Kernel Name"] and float(k["gpu__time_duration.sum"].split()[0]) > 10.0:      # the 4 M-path launch
                     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
                     traffic = sum(float(k[m].split()[0]) * scale[k[m].split()[1]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
     except Exception:
@@ -275,7 +308,7 @@ def main():
                 "fp64_instructions_per_rate_step": 56, "avg_launch_ms": eu,
                 "hbm": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": euler_bytes},
-                "traffic": traffic, "traffic_source": "static: profiles/r01_top_kernels_ncu.json (ncu --set full capture of this kernel at this size, not re-measured in this run)" if traffic else None,
+                "traffic": traffic, "traffic_source": "static: profiles/r02_top_kernels_ncu.json (ncu --set full capture of this kernel at this size, not re-measured in this run)" if traffic else None,
                 "dfma_clocks": dfma_clocks}
     fp64 = {"euler_ms": eu, "brownian_ms": float(np.mean(bm_ms)), "brownian_achieved_gbs": bm_bytes / (float(np.mean(bm_ms)) * 1e-3) / 1e9,
             "brownian_hbm_frac": bm_bytes / (float(np.mean(bm_ms)) * 1e-3) / 1e9 / peak}

@@ -1,7 +1,7 @@
 """Derives the polynomial coefficients used by finmath-lib_b200/csrc/fmb_math.cuh (device exp / log).
 
 Near-minimax fits by interpolation at Chebyshev nodes in 60-digit arithmetic (mpmath), coefficients rounded to binary64,
-then the rounded polynomial's maximum error is measured in high precision.  Run: python oracle/tools/fit_math_coefficients.py
+then the rounded polynomial's maximum error is measured in high precision.  Run: python finmath-lib_b200/tools/fit_math_coefficients.py
 """
 import mpmath as mp
 

@@ -315,3 +315,21 @@ def test_deferred_arithmetic_builds_the_documented_chain_encoding(pkg, monkeypat
     finally:
         for v in (x, y, z):
             v.h = 0                                            # fake handles: nothing to free
+
+
+def test_reference_arm_inputs_are_independent_of_and_equal_to_the_products_tables(pkg, orc):
+    """bench.py --impl reference builds its market data with numpy + the oracle only (reference_inputs); the product's host classes build
+    the same tables for the device arm.  Two independent constructions of the volatility table and of the 3-factor reduction: they must
+    agree (factor matrix to 1e-12: both call LAPACK's symmetric eigen-solver, the sign / scaling / second-pass conventions are restated
+    twice)."""
+    import importlib
+    import sys
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    from common import lmm_setup
+    r = bench.reference_inputs(orc)
+    s = lmm_setup(pkg)
+    assert np.array_equal(r["sim"], s["sim"].times) and np.array_equal(r["tenor"], s["tenor"].times)
+    assert np.array_equal(r["sigma"], s["sigma"])
+    assert np.max(np.abs(r["factor_matrix"] - s["factor_matrix"])) < 1e-12
+    assert np.array_equal(r["L0"], s["L0"])
