@@ -43,6 +43,37 @@ def report(name, paths, steps, bytes_per_path_step, ms, extra=None, emit=True):
     return d
 
 
+def kernel_only(process, model):
+    """Device time of the fused Euler kernel alone (host-side table set-up outside the timed region), best of 3."""
+    best_ms = 1e9
+    for _ in range(3):
+        proc = process()
+        spec = model.getFusedSpecification(proc)
+        proc.stochasticDriver.getBrownianIncrement(0, 0)
+        nv.synchronize()
+        nv.timer_start()
+        proc._precalculate_fused(spec)
+        best_ms = min(best_ms, nv.timer_stop_ms())
+        del proc
+    return best_ms
+
+
+def c2_kernel():
+    td = pkg.TimeDiscretizationFromArray(0.0, 200, 0.1)
+    vt = np.arange(0, 21.0)
+    vm = pkg.ShortRateVolatilityModelAsGiven(pkg.TimeDiscretizationFromArray(vt), 0.005 + 0.0005 * np.floor(vt) / 20, np.full(vt.size, 0.1))
+    bm = pkg.BrownianMotionCuda(td, 2, 1_000_000, 3141)
+    hw = pkg.HullWhiteModel(bm.randomVariableFactory, pkg.TimeDiscretizationFromArray(0.0, 40, 0.5), vm)
+    return kernel_only(lambda: pkg.EulerSchemeFromProcessModel(hw, bm, 0), hw)
+
+
+def c3_kernel(paths):
+    td = pkg.TimeDiscretizationFromArray(0.0, 1000, 0.005)
+    bm = pkg.BrownianMotionCuda(td, 2, paths, 31415)
+    model = pkg.HestonModel(1.0, 0.05, 0.3, 0.05, 0.09, 0.1, 0.5, 0.1, 1, bm.randomVariableFactory)
+    return kernel_only(lambda: pkg.EulerSchemeFromProcessModel(model, bm), model)
+
+
 def run_all(package, c3_paths=4_000_000):
     """C1, C2, C3 for bench.py's `configs` key (C5 is measured by bench.py itself): 1 warm-up + 2 timed repetitions each."""
     bind(package)
@@ -50,6 +81,23 @@ def run_all(package, c3_paths=4_000_000):
            report("C2 Hull-White 1M x 200 (dt 0.1y), piecewise-constant sigma(t), EULER", 1_000_000, 200, 32, timed(c2, reps=2), emit=False)]
     nv.load().fmb_pool_trim()
     out.append(report("C3 Heston full truncation %dM x 1000, 8-strike smile" % (c3_paths // 1_000_000), c3_paths, 1000, 32, timed(c3(c3_paths), reps=2), emit=False))
+    nv.load().fmb_pool_trim()
+    # kernel-level numbers of the two-component Euler kernels (algorithmic 32 B per path-step: 16 read + 16 written)
+    hbm = None
+    try:
+        hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    ms = c2_kernel()
+    gbs = 1_000_000 * 200 * 32 / ms / 1e6
+    out[1]["euler_kernel"] = {"kernel": "eulerTwoFactorTmaKernel<HullWhiteStep,256,2,4> (bulk-copy + mbarrier pipeline)", "ms": ms, "achieved_GBps": gbs,
+                              "hbm_frac": gbs / hbm if hbm else None, "bound": "hbm"}
+    nv.load().fmb_pool_trim()
+    kp = min(c3_paths, 2_000_000)
+    ms = c3_kernel(kp)
+    gbs = kp * 1000 * 32 / ms / 1e6
+    out[2]["euler_kernel"] = {"kernel": "eulerHestonKernel", "paths": kp, "ms": ms, "achieved_GBps": gbs, "hbm_frac": gbs / hbm if hbm else None,
+                              "bound": "issue / FP64 latency (exp + log + sqrt per step): ncu issue slots 59 %, FP64 pipe 43 %, DRAM 43 %"}
     nv.load().fmb_pool_trim()
     return out
 
