@@ -239,32 +239,55 @@ __host__ __device__ inline void jacobiPinvSolve(int K, double* U, double* V, dou
 	}
 }
 
-// The same algorithm with K known at compile time and every loop unrolled: on the device U and V then live in registers (the rotation chain is
-// latency-bound, 65 us -> see profiles/r02_notes.md).  Same operations in the same order: bit-identical to the run-time-K version.
+// K known at compile time (the regression kernels support K <= 8): one-sided Jacobi with the ROUND-ROBIN (tournament) ordering - a sweep is
+// KP - 1 rounds of KP / 2 rotations on disjoint column pairs (KP = K rounded up to even).  The rotations of a round are independent, so
+// their dot products, divisions and square roots - a strictly sequential latency chain in the cyclic ordering above, ~70 us for K = 6 on one
+// GPU thread - overlap (instruction-level parallelism of KP / 2 in ONE thread, no synchronisation), and U, V live in registers because
+// every index is a compile-time constant.  The convergence test compares squares (no square root).  Same cut-off for the pseudo-inverse.
+// Host (fmb_regression_solve_svd, K <= 8) and device run this very code: identical coefficients on both sides.
 template <int K> __host__ __device__ inline void jacobiPinvSolveT(double* U, double* V, double* s, const double* b, double* x, double* cond) {
+	constexpr int KP = (K + 1) & ~1, H = KP / 2, R = KP > 1 ? KP - 1 : 1;
 	_Pragma("unroll") for (int i = 0; i < K * K; i++) V[i] = 0.0;
 	_Pragma("unroll") for (int i = 0; i < K; i++) V[i * K + i] = 1.0;
-	for (int sweep = 0; sweep < 60; sweep++) {
+	for (int sweep = 0; sweep < 60 && K > 1; sweep++) {
 		bool rotated = false;
-		_Pragma("unroll") for (int p = 0; p < K - 1; p++) _Pragma("unroll") for (int q = p + 1; q < K; q++) {
-			double alpha = 0, beta = 0, gamma = 0;
-			_Pragma("unroll") for (int i = 0; i < K; i++) {
-				const double up = U[i * K + p], uq = U[i * K + q];
-				alpha += up * up; beta += uq * uq; gamma += up * uq;
+		_Pragma("unroll") for (int r = 0; r < R; r++) {
+			double cs[H], sn[H];
+			bool on[H];
+			// circle method: the last index stays, the others rotate; pair m of round r is (r + m, r - m) mod (KP - 1), pair 0 is (KP - 1, r)
+			_Pragma("unroll") for (int m = 0; m < H; m++) {
+				const int pa = m == 0 ? KP - 1 : (r + m) % R, pb = m == 0 ? r : (r - m + R) % R;
+				const int p = pa < pb ? pa : pb, q = pa < pb ? pb : pa;
+				on[m] = false; cs[m] = 1.0; sn[m] = 0.0;
+				if (q < K) {                                     // (K odd: the pair with the padding index is idle)
+					double alpha = 0, beta = 0, gamma = 0;
+					_Pragma("unroll") for (int i = 0; i < K; i++) {
+						const double up = U[i * K + p], uq = U[i * K + q];
+						alpha += up * up; beta += uq * uq; gamma += up * uq;
+					}
+					if (!(gamma == 0.0 || fabs(gamma) <= 1e-300 || gamma * gamma <= 0x1.0p-106 * (alpha * beta))) {
+						on[m] = true;
+						const double zeta = (beta - alpha) / (2.0 * gamma);
+						const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+						cs[m] = 1.0 / sqrt(1.0 + t * t);
+						sn[m] = cs[m] * t;
+					}
+				}
 			}
-			if (gamma == 0.0 || fabs(gamma) <= 1e-300) continue;
-			if (fabs(gamma) <= 0x1.0p-53 * sqrt(alpha * beta)) continue;
-			rotated = true;
-			const double zeta = (beta - alpha) / (2.0 * gamma);
-			const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-			const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
-			_Pragma("unroll") for (int i = 0; i < K; i++) {
-				const double up = U[i * K + p], uq = U[i * K + q];
-				U[i * K + p] = cs * up - sn * uq;
-				U[i * K + q] = sn * up + cs * uq;
-				const double vp = V[i * K + p], vq = V[i * K + q];
-				V[i * K + p] = cs * vp - sn * vq;
-				V[i * K + q] = sn * vp + cs * vq;
+			_Pragma("unroll") for (int m = 0; m < H; m++) {
+				const int pa = m == 0 ? KP - 1 : (r + m) % R, pb = m == 0 ? r : (r - m + R) % R;
+				const int p = pa < pb ? pa : pb, q = pa < pb ? pb : pa;
+				if (q < K && on[m]) {
+					rotated = true;
+					_Pragma("unroll") for (int i = 0; i < K; i++) {
+						const double up = U[i * K + p], uq = U[i * K + q];
+						U[i * K + p] = cs[m] * up - sn[m] * uq;
+						U[i * K + q] = sn[m] * up + cs[m] * uq;
+						const double vp = V[i * K + p], vq = V[i * K + q];
+						V[i * K + p] = cs[m] * vp - sn[m] * vq;
+						V[i * K + q] = sn[m] * vp + cs[m] * vq;
+					}
+				}
 			}
 		}
 		if (!rotated) break;
@@ -350,11 +373,25 @@ template <int K, int FINISH> __global__ void __launch_bounds__(RED_THREADS) mome
 #pragma unroll
 	for (int m = 0; m < M; m++) { acc[m].hi = 0.0; acc[m].lo = 0.0; }
 	const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
-	for (uint64_t i = blockIdx.x * (uint64_t)RED_THREADS + threadIdx.x; i < n; i += stride) {
+	uint64_t i = blockIdx.x * (uint64_t)RED_THREADS + threadIdx.x;
+	// the loads of the next element are issued before the ~190 dependent double-double operations of the current one (the kernel runs at one
+	// CTA per SM - 27 double-double accumulators per thread - so memory latency is not hidden by other warps)
+	double nv[K], ny = 0.0;
+	if (i < n) {
+#pragma unroll
+		for (int k = 0; k < K; k++) nv[k] = b.ptr[k] ? b.ptr[k][i] : b.scalar[k];
+		ny = y[i];
+	}
+	for (; i < n; i += stride) {
 		double v[K];
 #pragma unroll
-		for (int k = 0; k < K; k++) v[k] = b.ptr[k] ? b.ptr[k][i] : b.scalar[k];
-		const double yy = y[i];
+		for (int k = 0; k < K; k++) v[k] = nv[k];
+		const double yy = ny;
+		if (i + stride < n) {
+#pragma unroll
+			for (int k = 0; k < K; k++) nv[k] = b.ptr[k] ? b.ptr[k][i + stride] : b.scalar[k];
+			ny = y[i + stride];
+		}
 		int m = 0;
 #pragma unroll
 		for (int p = 0; p < K; p++) {
