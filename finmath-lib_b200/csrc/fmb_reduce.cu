@@ -239,78 +239,128 @@ __host__ __device__ inline void jacobiPinvSolve(int K, double* U, double* V, dou
 	}
 }
 
-// K known at compile time (the regression kernels support K <= 8): one-sided Jacobi with the ROUND-ROBIN (tournament) ordering - a sweep is
-// KP - 1 rounds of KP / 2 rotations on disjoint column pairs (KP = K rounded up to even).  The rotations of a round are independent, so
-// their dot products, divisions and square roots - a strictly sequential latency chain in the cyclic ordering above, ~70 us for K = 6 on one
-// GPU thread - overlap (instruction-level parallelism of KP / 2 in ONE thread, no synchronisation), and U, V live in registers because
-// every index is a compile-time constant.  The convergence test compares squares (no square root).  Same cut-off for the pseudo-inverse.
-// Host (fmb_regression_solve_svd, K <= 8) and device run this very code: identical coefficients on both sides.
-template <int K> __host__ __device__ inline void jacobiPinvSolveT(double* U, double* V, double* s, const double* b, double* x, double* cond) {
-	constexpr int KP = (K + 1) & ~1, H = KP / 2, R = KP > 1 ? KP - 1 : 1;
-	_Pragma("unroll") for (int i = 0; i < K * K; i++) V[i] = 0.0;
-	_Pragma("unroll") for (int i = 0; i < K; i++) V[i * K + i] = 1.0;
-	for (int sweep = 0; sweep < 60 && K > 1; sweep++) {
-		bool rotated = false;
-		_Pragma("unroll") for (int r = 0; r < R; r++) {
-			double cs[H], sn[H];
-			bool on[H];
-			// circle method: the last index stays, the others rotate; pair m of round r is (r + m, r - m) mod (KP - 1), pair 0 is (KP - 1, r)
-			_Pragma("unroll") for (int m = 0; m < H; m++) {
-				const int pa = m == 0 ? KP - 1 : (r + m) % R, pb = m == 0 ? r : (r - m + R) % R;
-				const int p = pa < pb ? pa : pb, q = pa < pb ? pb : pa;
-				on[m] = false; cs[m] = 1.0; sn[m] = 0.0;
-				if (q < K) {                                     // (K odd: the pair with the padding index is idle)
-					double alpha = 0, beta = 0, gamma = 0;
-					_Pragma("unroll") for (int i = 0; i < K; i++) {
-						const double up = U[i * K + p], uq = U[i * K + q];
-						alpha += up * up; beta += uq * uq; gamma += up * uq;
-					}
-					if (!(gamma == 0.0 || fabs(gamma) <= 1e-300 || gamma * gamma <= 0x1.0p-106 * (alpha * beta))) {
-						on[m] = true;
-						const double zeta = (beta - alpha) / (2.0 * gamma);
-						const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-						cs[m] = 1.0 / sqrt(1.0 + t * t);
-						sn[m] = cs[m] * t;
-					}
-				}
-			}
-			_Pragma("unroll") for (int m = 0; m < H; m++) {
-				const int pa = m == 0 ? KP - 1 : (r + m) % R, pb = m == 0 ? r : (r - m + R) % R;
-				const int p = pa < pb ? pa : pb, q = pa < pb ? pb : pa;
-				if (q < K && on[m]) {
-					rotated = true;
-					_Pragma("unroll") for (int i = 0; i < K; i++) {
-						const double up = U[i * K + p], uq = U[i * K + q];
-						U[i * K + p] = cs[m] * up - sn[m] * uq;
-						U[i * K + q] = sn[m] * up + cs[m] * uq;
-						const double vp = V[i * K + p], vq = V[i * K + q];
-						V[i * K + p] = cs[m] * vp - sn[m] * vq;
-						V[i * K + q] = sn[m] * vp + cs[m] * vq;
-					}
-				}
-			}
-		}
-		if (!rotated) break;
-	}
+// K <= 8: one-sided Jacobi with the ROUND-ROBIN (tournament) ordering - a sweep is KP - 1 rounds of KP / 2 rotations on disjoint column
+// pairs (KP = K rounded up to even), and the rotations of a round are independent.  The device version runs them on ONE WARP: lane = (pair,
+// row), 8 lanes per pair; the three column dot products of a pair are 8-lane butterfly reductions, every lane of the pair evaluates the
+// rotation, each lane updates its own row of U and V in shared memory.  Compact code (one small loop body - a fully unrolled single-thread
+// version spent more time on cold instruction-cache lines than on arithmetic) and ~40 rounds instead of ~120 sequential rotations.
+// The host version below (fmb_regression_solve_svd, K <= 8) performs the same operations in the same order - including the butterfly's
+// summation tree ((t0+t4)+(t2+t6))+((t1+t5)+(t3+t7)) - so both sides produce identical coefficients.
+__host__ __device__ inline void roundRobinPair(int KP, int r, int m, int& p, int& q) {
+	const int R = KP - 1;
+	const int pa = m == 0 ? KP - 1 : (r + m) % R, pb = m == 0 ? r : (r - m + R) % R;
+	p = pa < pb ? pa : pb; q = pa < pb ? pb : pa;
+}
+// rotation of the column pair from its three dot products; false: the pair is already orthogonal to working precision
+__host__ __device__ inline bool jacobiRotation(double alpha, double beta, double gamma, double& cs, double& sn) {
+	cs = 1.0; sn = 0.0;
+	if (gamma == 0.0 || fabs(gamma) <= 1e-300 || gamma * gamma <= 0x1.0p-106 * (alpha * beta)) return false;
+	const double zeta = (beta - alpha) / (2.0 * gamma);
+	const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+	cs = 1.0 / sqrt(1.0 + t * t);
+	sn = cs * t;
+	return true;
+}
+// singular values, condition number and x = V S^+ U^T b from the rotated U (columns u_j s_j) and V; sequential, K x K
+__host__ __device__ inline void jacobiFinish(int K, const double* U, const double* V, double* s, const double* b, double* x, double* cond) {
 	double smax = 0.0, smin = INFINITY;
-	_Pragma("unroll") for (int j = 0; j < K; j++) {
+	for (int j = 0; j < K; j++) {
 		double nn = 0;
-		_Pragma("unroll") for (int i = 0; i < K; i++) nn += U[i * K + j] * U[i * K + j];
+		for (int i = 0; i < K; i++) nn += U[i * K + j] * U[i * K + j];
 		s[j] = sqrt(nn);
 		smax = s[j] > smax ? s[j] : smax; smin = s[j] < smin ? s[j] : smin;
 	}
 	if (cond) *cond = smax / smin;
 	const double tolA = (double)K * smax * 0x1.0p-52, tolB = 1.4916681462400413e-154 /* sqrt(2^-1022) */;
 	const double tol = tolA > tolB ? tolA : tolB;
-	_Pragma("unroll") for (int k = 0; k < K; k++) x[k] = 0.0;
-	_Pragma("unroll") for (int j = 0; j < K; j++) {
+	for (int k = 0; k < K; k++) x[k] = 0.0;
+	for (int j = 0; j < K; j++) {
 		if (s[j] <= tol) continue;
 		double ub = 0;                              // (u_j . b) / s_j, with u_j = U[:,j] / s_j
-		_Pragma("unroll") for (int i = 0; i < K; i++) ub += U[i * K + j] * b[i];
+		for (int i = 0; i < K; i++) ub += U[i * K + j] * b[i];
 		const double wgt = ub / (s[j] * s[j]);
-		_Pragma("unroll") for (int k = 0; k < K; k++) x[k] += V[k * K + j] * wgt;
+		for (int k = 0; k < K; k++) x[k] += V[k * K + j] * wgt;
 	}
 }
+inline double tree8(const double* t) { return ((t[0] + t[4]) + (t[2] + t[6])) + ((t[1] + t[5]) + (t[3] + t[7])); }
+// host twin of the warp solver (K <= 8)
+inline void jacobiPinvSolveRoundRobinHost(int K, double* U, double* V, double* s, const double* b, double* x, double* cond) {
+	const int KP = (K + 1) & ~1, H = KP / 2;
+	for (int i = 0; i < K * K; i++) V[i] = 0.0;
+	for (int i = 0; i < K; i++) V[i * K + i] = 1.0;
+	for (int sweep = 0; sweep < 60 && K > 1; sweep++) {
+		bool rotated = false;
+		for (int r = 0; r < KP - 1; r++) {
+			double cs[4], sn[4];
+			bool on[4];
+			for (int m = 0; m < H; m++) {                      // all rotations of the round from the SAME U
+				int p, q;
+				roundRobinPair(KP, r, m, p, q);
+				on[m] = false; cs[m] = 1.0; sn[m] = 0.0;
+				if (q >= K) continue;
+				double ta[8] = {0}, tb[8] = {0}, tg[8] = {0};
+				for (int i = 0; i < K; i++) { const double up = U[i * K + p], uq = U[i * K + q]; ta[i] = up * up; tb[i] = uq * uq; tg[i] = up * uq; }
+				on[m] = jacobiRotation(tree8(ta), tree8(tb), tree8(tg), cs[m], sn[m]);
+			}
+			for (int m = 0; m < H; m++) {
+				if (!on[m]) continue;
+				int p, q;
+				roundRobinPair(KP, r, m, p, q);
+				rotated = true;
+				for (int i = 0; i < K; i++) {
+					const double up = U[i * K + p], uq = U[i * K + q];
+					U[i * K + p] = cs[m] * up - sn[m] * uq;
+					U[i * K + q] = sn[m] * up + cs[m] * uq;
+					const double vp = V[i * K + p], vq = V[i * K + q];
+					V[i * K + p] = cs[m] * vp - sn[m] * vq;
+					V[i * K + q] = sn[m] * vp + cs[m] * vq;
+				}
+			}
+		}
+		if (!rotated) break;
+	}
+	jacobiFinish(K, U, V, s, b, x, cond);
+}
+#ifdef __CUDACC__
+// one warp; U (= A on entry), V: K x K in shared memory; s, b, x: K doubles in shared memory.  All 32 lanes must call.
+__device__ inline void jacobiPinvSolveWarp(int K, double* U, double* V, double* s, const double* b, double* x, double* cond) {
+	const int lane = threadIdx.x & 31, g = lane >> 3, i = lane & 7;
+	const int KP = (K + 1) & ~1, H = KP / 2;
+	for (int idx = lane; idx < K * K; idx += 32) V[idx] = (idx / K == idx % K) ? 1.0 : 0.0;
+	__syncwarp();
+	for (int sweep = 0; sweep < 60 && K > 1; sweep++) {
+		bool rotated = false;
+		for (int r = 0; r < KP - 1; r++) {
+			int p = 0, q = 0;
+			roundRobinPair(KP, r, g < H ? g : 0, p, q);
+			const bool pairOk = g < H && q < K, rowOk = pairOk && i < K;
+			const double up = rowOk ? U[i * K + p] : 0.0, uq = rowOk ? U[i * K + q] : 0.0;
+			double alpha = up * up, beta = uq * uq, gamma = up * uq;
+#pragma unroll
+			for (int o = 4; o > 0; o >>= 1) {
+				alpha = alpha + __shfl_xor_sync(0xffffffffu, alpha, o);
+				beta = beta + __shfl_xor_sync(0xffffffffu, beta, o);
+				gamma = gamma + __shfl_xor_sync(0xffffffffu, gamma, o);
+			}
+			double cs, sn;
+			const bool on = jacobiRotation(alpha, beta, gamma, cs, sn) && pairOk;
+			__syncwarp();                                      // every lane has read the round's U before anybody writes
+			if (on && rowOk) {
+				U[i * K + p] = cs * up - sn * uq;
+				U[i * K + q] = sn * up + cs * uq;
+				const double vp = V[i * K + p], vq = V[i * K + q];
+				V[i * K + p] = cs * vp - sn * vq;
+				V[i * K + q] = sn * vp + cs * vq;
+			}
+			rotated = __any_sync(0xffffffffu, on) || rotated;
+			__syncwarp();
+		}
+		if (!rotated) break;
+	}
+	if (lane == 0) jacobiFinish(K, U, V, s, b, x, cond);
+	__syncwarp();
+}
+#endif
 
 struct BasisArgs {
 	const double* ptr[8];
@@ -337,14 +387,11 @@ template <int K> __device__ void regressionFinish(const double* __restrict__ src
 		for (int r = 1; r < f.world; r++) { const dd o = { __ldcg(src + ((size_t)r * M + m) * 2), __ldcg(src + ((size_t)r * M + m) * 2 + 1) }; ddMerge(t, o); }
 		mean[m] = (t.hi + t.lo) / f.n;
 	}
+	__shared__ double U[K * K], V[K * K], sv[K], rhs[K], xs[K], condS;
 	__syncthreads();
 	if (threadIdx.x == 0) {
-		double U[K * K], V[K * K], sv[K], rhs[K], xs[K];
 		int m = 0;
-#pragma unroll
-		for (int p = 0; p < K; p++)
-#pragma unroll
-		for (int q = p; q < K; q++) {
+		for (int p = 0; p < K; p++) for (int q = p; q < K; q++) {
 			double v = mean[m++];
 			// deterministic x deterministic: the reference's mult() stays a scalar and its average is the product itself
 			if (b.ptr[p] == nullptr && b.ptr[q] == nullptr) v = b.scalar[p] * b.scalar[q];
@@ -352,13 +399,13 @@ template <int K> __device__ void regressionFinish(const double* __restrict__ src
 			U[p * K + q] = U[q * K + p] = v;
 			f.fit[FIT_XTX + p * K + q] = f.fit[FIT_XTX + q * K + p] = v;
 		}
-#pragma unroll
 		for (int p = 0; p < K; p++) { rhs[p] = mean[m++]; f.fit[FIT_XTY + p] = rhs[p]; }
-		double cond;
-		jacobiPinvSolveT<K>(U, V, sv, rhs, xs, &cond);
-#pragma unroll
-		for (int p = 0; p < K; p++) f.fit[FIT_X + p] = xs[p];
-		f.fit[FIT_COND] = cond;
+	}
+	__syncthreads();
+	if (threadIdx.x < 32) {                            // one warp solves (round-robin Jacobi, lanes = (pair, row))
+		jacobiPinvSolveWarp(K, U, V, sv, rhs, xs, &condS);
+		if (threadIdx.x < K) f.fit[FIT_X + threadIdx.x] = xs[threadIdx.x];
+		if (threadIdx.x == 0) f.fit[FIT_COND] = condS;
 	}
 }
 
@@ -646,17 +693,8 @@ int fmb_regression_solve_svd(int K, const double* A, const double* b, double* x,
 	std::vector<double> U(A, A + (size_t)K * K), V((size_t)K * K, 0.0), s(K);
 	double condLocal = 0.0;
 	double* cp = cond ? cond : &condLocal;
-	switch (K) {                                    // (the same code as the device-resident regression runs: identical coefficients)
-	case 1: jacobiPinvSolveT<1>(U.data(), V.data(), s.data(), b, x, cp); break;
-	case 2: jacobiPinvSolveT<2>(U.data(), V.data(), s.data(), b, x, cp); break;
-	case 3: jacobiPinvSolveT<3>(U.data(), V.data(), s.data(), b, x, cp); break;
-	case 4: jacobiPinvSolveT<4>(U.data(), V.data(), s.data(), b, x, cp); break;
-	case 5: jacobiPinvSolveT<5>(U.data(), V.data(), s.data(), b, x, cp); break;
-	case 6: jacobiPinvSolveT<6>(U.data(), V.data(), s.data(), b, x, cp); break;
-	case 7: jacobiPinvSolveT<7>(U.data(), V.data(), s.data(), b, x, cp); break;
-	case 8: jacobiPinvSolveT<8>(U.data(), V.data(), s.data(), b, x, cp); break;
-	default: jacobiPinvSolve(K, U.data(), V.data(), s.data(), b, x, cp); break;
-	}
+	if (K <= 8) jacobiPinvSolveRoundRobinHost(K, U.data(), V.data(), s.data(), b, x, cp);    // the device-resident regression's algorithm: identical coefficients
+	else jacobiPinvSolve(K, U.data(), V.data(), s.data(), b, x, cp);
 	return FMB_OK;
 }
 
