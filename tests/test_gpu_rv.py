@@ -164,7 +164,8 @@ def test_order_statistics_by_radix_select_match_the_sorted_reference(gpu, orc):
     assert np.array_equal(h, orc.rv_histogram(x, pts)) and abs(h.sum() - 1.0) < 1e-12
     cnt = np.zeros(3, dtype=np.uint64)
     probe = np.array([0.5, np.nan, -0.5])
-    nv.check(nv.load().fmb_rv_count_le(RV(0.0, x).dv.h, nv.dptr(probe), 3, cnt.ctypes.data_as(nv.c_hp)))
+    keep = RV(0.0, x)                                       # (the handle lives as long as its owner)
+    nv.check(nv.load().fmb_rv_count_le(keep.dv.h, nv.dptr(probe), 3, cnt.ctypes.data_as(nv.c_hp)))
     assert cnt.tolist() == [int(np.sum(x <= 0.5)), 0, int(np.sum(x <= -0.5))]
 
 
