@@ -468,9 +468,18 @@ template <int K, int FINISH> __global__ void __launch_bounds__(RED_THREADS) mome
 	const int m = threadIdx.x / S, sl = threadIdx.x % S;
 	dd t = {0.0, 0.0};
 	if (m < M) {
-		for (unsigned int blk = sl; blk < gridDim.x; blk += S) {
-			const dd o = { __ldcg(partials + ((size_t)blk * M + m) * 2), __ldcg(partials + ((size_t)blk * M + m) * 2 + 1) };
-			ddMerge(t, o);
+		// four partials are fetched (L2 latency each) before they are merged in order
+		for (unsigned int blk = sl; blk < gridDim.x; blk += 4 * S) {
+			dd o[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const unsigned int bb = blk + u * S;
+				const bool ok = bb < gridDim.x;
+				o[u].hi = ok ? __ldcg(partials + ((size_t)bb * M + m) * 2) : 0.0;
+				o[u].lo = ok ? __ldcg(partials + ((size_t)bb * M + m) * 2 + 1) : 0.0;
+			}
+#pragma unroll
+			for (int u = 0; u < 4; u++) if (blk + u * S < gridDim.x) ddMerge(t, o[u]);
 		}
 	}
 #pragma unroll
