@@ -74,42 +74,82 @@ public class RandomVariableCuda implements RandomVariable {
 	@Override public RandomVariable apply(final DoubleTernaryOperator o, final RandomVariable a, final RandomVariable b) { throw new UnsupportedOperationException("lambdas cannot run on the device"); }
 
 	// ---- reductions (double-double sums on the device, RandomVariableFromDoubleArray.java:262-428)
-	@Override public double getMin() { return handle == 0 ? valueIfNonStochastic : reduce(R_MIN, handle, 0, 0); }
-	@Override public double getMax() { return handle == 0 ? valueIfNonStochastic : reduce(R_MAX, handle, 0, 0); }
+	/** hi + lo of the double-double sum (all shards when the library holds a communicator); min / max in [0]. */
+	private static double reduced(final int op, final long x, final long w, final double a) { final double[] r = reduce(op, x, w, a); return r[0] + r[1]; }
+	@Override public double getMin() { return handle == 0 ? valueIfNonStochastic : reduce(R_MIN, handle, 0, 0)[0]; }
+	@Override public double getMax() { return handle == 0 ? valueIfNonStochastic : reduce(R_MAX, handle, 0, 0)[0]; }
 	@Override public double getAverage() {
 		if (handle == 0) return valueIfNonStochastic;
 		if (size == 0) return Double.NaN;
-		return reduce(R_SUM, handle, 0, 0) / size;
+		return reduced(R_SUM, handle, 0, 0) / size;
 	}
 	@Override public double getAverage(final RandomVariable p) {
 		if (handle == 0) return valueIfNonStochastic * p.getAverage();
 		if (size == 0) return Double.NaN;
 		if (p.isDeterministic()) return mult(p.doubleValue()).getAverage();
-		return reduce(R_SUM_PRODUCT, handle, handleOf(p), 0) / size;
+		return reduced(R_SUM_PRODUCT, handle, handleOf(p), 0) / size;
 	}
 	@Override public double getVariance() {
 		if (handle == 0 || size == 1) return 0.0;
 		if (size == 0) return Double.NaN;
-		return reduce(R_CENTERED_M2, handle, 0, getAverage()) / size;
+		return reduced(R_CENTERED_M2, handle, 0, getAverage()) / size;
 	}
 	@Override public double getVariance(final RandomVariable p) {          // not divided by n (:379)
 		if (handle == 0) return 0.0;
 		if (size == 0) return Double.NaN;
 		final double average = getAverage(p);
 		if (p.isDeterministic()) return ((RandomVariableCuda) sub(average).squared().mult(p.doubleValue())).sum();
-		return reduce(R_CENTERED_M2_W, handle, handleOf(p), average);
+		return reduced(R_CENTERED_M2_W, handle, handleOf(p), average);
 	}
-	private double sum() { return reduce(R_SUM, handle, 0, 0); }
+	private double sum() { return reduced(R_SUM, handle, 0, 0); }
 	@Override public double getSampleVariance() { return (handle == 0 || size == 1) ? 0.0 : getVariance() * size / (size - 1); }
 	@Override public double getStandardDeviation() { return handle == 0 ? 0.0 : Math.sqrt(getVariance()); }
 	@Override public double getStandardDeviation(final RandomVariable p) { return handle == 0 ? 0.0 : Math.sqrt(getVariance(p)); }
 	@Override public double getStandardError() { return handle == 0 ? 0.0 : getStandardDeviation() / Math.sqrt(size); }
 	@Override public double getStandardError(final RandomVariable p) { return handle == 0 ? 0.0 : getStandardDeviation(p) / Math.sqrt(size); }
-	@Override public double getQuantile(final double q) { throw new UnsupportedOperationException("bind fmb_rv_sorted as in stochastic.py"); }
-	@Override public double getQuantile(final double q, final RandomVariable p) { throw new RuntimeException("Method not implemented."); }
-	@Override public double getQuantileExpectation(final double a, final double b) { throw new UnsupportedOperationException("bind fmb_rv_sorted as in stochastic.py"); }
-	@Override public double[] getHistogram(final double[] pts) { throw new UnsupportedOperationException("bind fmb_rv_count_le as in stochastic.py"); }
-	@Override public double[][] getHistogram(final int n, final double sd) { throw new UnsupportedOperationException("bind fmb_rv_count_le as in stochastic.py"); }
+	// ---- order statistics without a sort (radix select / counting pass / range sum on the device; :445-575)
+	private long quantileIndex(final double q) { return Math.min(Math.max(Math.round((size + 1) * q - 1), 0), size - 1); }      // :454-459
+	@Override public double getQuantile(final double q) {
+		if (handle == 0) return valueIfNonStochastic;
+		if (size == 0) return Double.NaN;
+		return select(handle, quantileIndex(q));
+	}
+	@Override public double getQuantile(final double q, final RandomVariable p) { throw new RuntimeException("Method not implemented."); }   // :471
+	@Override public double getQuantileExpectation(final double a, final double b) {
+		if (handle == 0) return valueIfNonStochastic;
+		if (size == 0) return Double.NaN;
+		if (a > b) return getQuantileExpectation(b, a);
+		final long i0 = quantileIndex(a), i1 = quantileIndex(b);
+		final double v0 = select(handle, i0), v1 = select(handle, i1);
+		if (v0 == v1) return v0;
+		final double[] r = rangeSum(handle, v0, v1);        // {sum hi, sum lo, #(x <= v0), #(x < v1)}
+		return (r[0] + r[1] + ((long) r[2] - i0) * v0 + (i1 - (long) r[3] + 1) * v1) / (i1 - i0 + 1);
+	}
+	@Override public double[] getHistogram(final double[] pts) {
+		final double[] h = new double[pts.length + 1];
+		if (handle == 0) {                                      // :505-517
+			for (int k = 0; k < pts.length; k++) if (valueIfNonStochastic > pts[k]) { h[k] = 1.0; break; }
+			h[pts.length] = 1.0;
+			return h;
+		}
+		final long[] counts = countLessOrEqual(handle, pts);    // (at most 511 thresholds per call: chunk longer arrays)
+		long prev = 0;
+		for (int k = 0; k < pts.length; k++) { final long c = Math.max(counts[k], prev); h[k] = c - prev; prev = c; }   // :528-550
+		h[pts.length] = size - prev;
+		if (size > 0) for (int k = 0; k < h.length; k++) h[k] /= size;
+		return h;
+	}
+	@Override public double[][] getHistogram(final int n, final double sd) {                                                     // :553-575
+		final double[] pts = new double[n], anchors = new double[n + 1];
+		final double center = getAverage(), radius = sd * getStandardDeviation(), stepSize = (n - 1) / 2.0;
+		for (int i = 0; i < n; i++) {
+			final double alpha = (-(double) (n - 1) / 2.0 + i) / stepSize;
+			pts[i] = center + alpha * radius;
+			anchors[i] = center + alpha * radius - radius / (2 * stepSize);
+		}
+		anchors[n] = center + 1 * radius + radius / (2 * stepSize);
+		return new double[][] { anchors, getHistogram(pts) };
+	}
 
 	// ---- unary and rv op double (:742-1020)
 	@Override public RandomVariable cap(final double c) { return map(U_CAP, c, x -> Math.min(x, c)); }
