@@ -16,4 +16,6 @@ from .models import (BlackScholesModel, HestonModel, MonteCarloAssetModel, Monte
                      LIBORVolatilityModelFourParameterExponentialForm, LIBORCorrelationModelExponentialDecay,
                      LIBORCovarianceModelFromVolatilityAndCorrelation, LIBORMarketModelFromCovarianceModel,
                      LIBORMonteCarloSimulationFromLIBORModel, factorReduction, HullWhiteModel, ShortRateVolatilityModelAsGiven)
-from .products import EuropeanOption, Caplet, Swaption, BermudanSwaption, BermudanOption
+from .products import EuropeanOption, DigitalOption, Caplet, Swaption, BermudanSwaption, BermudanOption
+from .autodiff import (RandomVariableDifferentiable, RandomVariableDifferentiableAAD, RandomVariableDifferentiableAADFactory,
+                       DiracDeltaApproximationMethod)

@@ -16,7 +16,7 @@ import weakref
 import numpy as np
 
 from .montecarlo import BrownianMotionCuda, EulerSchemeFromProcessModel, Scheme
-from .stochastic import RandomVariableCuda, RandomVariableCudaFactory, Scalar
+from .stochastic import RandomVariable, RandomVariableCuda, RandomVariableCudaFactory, Scalar
 from . import native as nv
 
 
@@ -24,15 +24,18 @@ class BlackScholesModel:
     def __init__(self, initialValue, riskFreeRate, volatility, randomVariableFactory=None):
         f = randomVariableFactory if randomVariableFactory is not None else RandomVariableCudaFactory()
         self.randomVariableFactory = f
-        self.initialValue = f.createRandomVariable(initialValue)
-        self.riskFreeRate = f.createRandomVariable(riskFreeRate)
-        self.volatility = f.createRandomVariable(volatility)
+        # numbers or RandomVariables (BlackScholesModel.java:59-81): with a differentiable factory the three parameters are independents
+        asRV = lambda v: v if isinstance(v, RandomVariable) else f.createRandomVariable(v)
+        self.initialValue, self.riskFreeRate, self.volatility = asRV(initialValue), asRV(riskFreeRate), asRV(volatility)
         self.initialState = [self.initialValue.log()]                                          # :76
         self.drift = [self.riskFreeRate.sub(self.volatility.squared().div(2))]                 # :77
         self.factorLoadings = [self.volatility]
 
     def getNumberOfComponents(self): return 1
     def getNumberOfFactors(self): return 1
+    def getInitialValue(self): return [self.initialValue]
+    def getRiskFreeRate(self): return self.riskFreeRate
+    def getVolatility(self): return self.volatility
     def getInitialState(self, process): return self.initialState
     def getDrift(self, process, timeIndex, realizationAtTimeIndex, realizationPredictor): return self.drift
     def getFactorLoading(self, process, timeIndex, component, realizationAtTimeIndex): return self.factorLoadings
@@ -245,6 +248,7 @@ class LIBORMarketModelFromCovarianceModel:
         self._tables = factorLoadingTable
         self._numeraires, self._numeraireDiscountFactors, self._numerairesProcess = {}, {}, None
         self._numerairesAdjusted = {}
+        self._initialState = None
 
     @classmethod
     def of(cls, liborPeriodDiscretization, analyticModel, forwardRates, discountFactors, randomVariableFactory, covarianceModel, calibrationItems=None,
@@ -274,10 +278,14 @@ class LIBORMarketModelFromCovarianceModel:
         return df
 
     def getInitialState(self, process):                      # :1080-1093
-        c = self.getRandomVariableForConstant
-        if self.stateSpace == self.LOGNORMAL:
-            return [c(math.log(max(r, 0.0)) if max(r, 0.0) > 0 else float("-inf")) for r in self.L0]
-        return [c(float(r)) for r in self.L0]
+        # created once per model: with a differentiable factory these are the independents of the forward-rate sensitivities
+        if self._initialState is None:
+            c = self.getRandomVariableForConstant
+            if self.stateSpace == self.LOGNORMAL:
+                self._initialState = [c(math.log(max(r, 0.0)) if max(r, 0.0) > 0 else float("-inf")) for r in self.L0]
+            else:
+                self._initialState = [c(float(r)) for r in self.L0]
+        return list(self._initialState)
 
     def _first(self, time):
         first = self.getLiborPeriodIndex(time) + 1          # :1127-1130

@@ -17,7 +17,7 @@ import numpy as np
 
 from . import native as nv
 from .sharding import LOCAL
-from .stochastic import RandomVariableCuda, RandomVariableCudaFactory, Scalar
+from .stochastic import RandomVariableCuda, RandomVariableCudaFactory, Scalar, _unwrap
 
 TIME_TICK_SIZE = 1.0 / (365.0 * 24.0)                       # TimeDiscretizationFromArray.java:39
 
@@ -512,7 +512,11 @@ class EulerSchemeFromProcessModel:
     # ---- evolution -------------------------------------------------------------------------------------------------
     def _precalculate(self):
         self._weights = self.stochasticDriver.getRandomVariableForConstant(1.0 / self.getNumberOfPaths())    # :184
-        spec = None if self.forceGeneric else getattr(self.model, "getFusedSpecification", lambda p: None)(self)
+        differentiable = any(hasattr(getattr(o, "randomVariableFactory", None), "createRandomVariableNonDifferentiable")
+                             for o in (self.model, self.stochasticDriver))
+        # parameters or increments from a differentiable factory: every operation has to be recorded, so the reference's generic
+        # recipe runs on (wrapped) device RandomVariables instead of the fused kernel (autodiff.py)
+        spec = None if (self.forceGeneric or differentiable) else getattr(self.model, "getFusedSpecification", lambda p: None)(self)
         if spec is not None and spec["kernel"] in ("heston", "hull_white") and self.stochasticDriver.getNumberOfFactors() != 2:
             # the fused kernels of these two models read exactly two increments per step; any other driver runs the reference's
             # generic recipe (addSumProduct over whatever factor loadings the model returns)
@@ -614,6 +618,7 @@ class MonteCarloConditionalExpectationRegression:
 
     @staticmethod
     def _as_cuda(rv, shard):
+        rv = _unwrap(rv)                                      # basis functions / dependents may be AAD wrappers: regress on their device values
         if isinstance(rv, RandomVariableCuda):
             return rv
         if rv.isDeterministic():

@@ -2,6 +2,7 @@
 type the way the unchanged Java classes would (none of them ever touches realizations on the host).
 
 * EuropeanOption      J/montecarlo/assetderivativevaluation/products/EuropeanOption.java:172-193
+* DigitalOption       J/montecarlo/assetderivativevaluation/products/DigitalOption.java:73-93
 * Caplet              J/montecarlo/interestrate/products/Caplet.java:114-160
 * Swaption            J/montecarlo/interestrate/products/Swaption.java:137-200
 * BermudanSwaption    J/montecarlo/interestrate/products/BermudanSwaption.java:90-252
@@ -32,6 +33,20 @@ class EuropeanOption(AbstractMonteCarloProduct):
         numeraireAtEvalTime = model.getNumeraire(float(evaluationTime))
         monteCarloWeightsAtEvalTime = model.getMonteCarloWeights(float(evaluationTime))
         return values.mult(numeraireAtEvalTime).div(monteCarloWeightsAtEvalTime)
+
+
+class DigitalOption(AbstractMonteCarloProduct):
+    """J/montecarlo/assetderivativevaluation/products/DigitalOption.java:73-93 — the indicator payoff 1(S(T) - K >= 0) (a choose: the
+    operation whose derivative autodiff.py approximates)."""
+
+    def __init__(self, maturity, strike, underlyingIndex=0):
+        self.maturity, self.strike, self.underlyingIndex = maturity, strike, underlyingIndex
+
+    def getValueRV(self, evaluationTime, model):
+        underlyingAtMaturity = model.getAssetValue(float(self.maturity), self.underlyingIndex)
+        values = underlyingAtMaturity.sub(self.strike).choose(Scalar(1.0), Scalar(0.0))
+        values = values.div(model.getNumeraire(float(self.maturity))).mult(model.getMonteCarloWeights(float(self.maturity)))
+        return values.mult(model.getNumeraire(float(evaluationTime))).div(model.getMonteCarloWeights(float(evaluationTime)))
 
 
 class Caplet(AbstractMonteCarloProduct):

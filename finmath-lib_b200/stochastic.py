@@ -100,6 +100,12 @@ class RandomVariable:
     def getConditionalExpectation(self, estimator):
         return estimator.getConditionalExpectation(self)
 
+    def getValues(self):                                     # RandomVariable.java:62-64: "this" unless the type wraps inner values (AAD)
+        return self
+
+    def expectation(self):                                   # RandomVariable.java:466-468
+        return self.average()
+
     def variance(self):
         return self.squared().average().sub(self.average().squared())
 
@@ -303,6 +309,14 @@ class RandomVariableFromDoubleArray(RandomVariable):
         return getattr(gpu, name)
 
 
+def _unwrap(rv):
+    """The innermost values of a wrapping RandomVariable (getValues() chain; the identity for plain types)."""
+    inner = rv.getValues()
+    while inner is not rv:
+        rv, inner = inner, inner.getValues()
+    return rv
+
+
 class RandomVariableCuda(nv._F.RV, RandomVariable):
     """Device-resident RandomVariable, type priority 2.
 
@@ -397,6 +411,8 @@ class RandomVariableCuda(nv._F.RV, RandomVariable):
 
     def _operand(self, rv):
         """(device vector or None, scalar value) of any RandomVariable."""
+        if rv.getTypePriority() > 2:                        # a wrapper (AAD) met where no delegation applies (choose): its inner values, no copy
+            rv = _unwrap(rv)
         if isinstance(rv, RandomVariableCuda):
             if rv.dv is not None:
                 self._pending_n = rv.nGlobal
