@@ -286,10 +286,19 @@ def test_black_scholes_greeks_through_the_recorded_simulation(env):
     assert abs(option.getValue(mcPlain) - value.getAverage()) < 1e-12
     assert mcPlain.getProcess().usedFusedKernel == ("black_scholes" if env.device else None)
     eps = 1e-5
+
+    def smooth(mc):                                          # a pay-off without a kink: the bumped runs differentiate it to O(eps^2)
+        v = mc.getAssetValue(T, 0)
+        return v.log().squared().add(v.sqrt()).div(mc.getNumeraire(T))
+    gs = smooth(mc).getGradient()
     for k, bump in enumerate(((eps, 0, 0), (0, eps, 0), (0, 0, eps))):
-        up = option.getValue(_black_scholes(env, env.Factory(), s0 + bump[0], r + bump[1], sigma + bump[2], td, paths)[1])
-        dn = option.getValue(_black_scholes(env, env.Factory(), s0 - bump[0], r - bump[1], sigma - bump[2], td, paths)[1])
-        assert abs((up - dn) / (2 * eps) - aad[k]) < 2e-6 * max(1.0, abs(aad[k])), (k, (up - dn) / (2 * eps), aad[k])
+        up = _black_scholes(env, env.Factory(), s0 + bump[0], r + bump[1], sigma + bump[2], td, paths)[1]
+        dn = _black_scholes(env, env.Factory(), s0 - bump[0], r - bump[1], sigma - bump[2], td, paths)[1]
+        fd = (smooth(up).getAverage() - smooth(dn).getAverage()) / (2 * eps)
+        assert abs(fd - gs[ids[k]].getAverage()) < 1e-8 * max(1.0, abs(fd)), (k, fd, gs[ids[k]].getAverage())
+        # the call: the ~N p(K) |dS/dθ| 2 eps paths whose kink lies inside the bump make the difference quotient noisy (not the adjoint)
+        fd = (option.getValue(up) - option.getValue(dn)) / (2 * eps)
+        assert abs(fd - aad[k]) < 2e-4 * max(1.0, abs(aad[k])), (k, fd, aad[k])
     d1 = (np.log(s0 / K) + (r + 0.5 * sigma * sigma) * T) / (sigma * np.sqrt(T))
     d2 = d1 - sigma * np.sqrt(T)
     analytic = [norm.cdf(d1), K * T * np.exp(-r * T) * norm.cdf(d2), s0 * np.sqrt(T) * norm.pdf(d1)]
@@ -344,7 +353,7 @@ def test_conditional_expectation_operator(env):
     td = pkg.TimeDiscretizationFromArray(0.0, 2, 1.0)
     s0, r, sigma, K = 1.0, 0.05, 0.30, 1.0
 
-    def bermudan(factory, s0):
+    def bermudan(factory, s0, frozenTrigger=None):
         model, mc = _black_scholes(env, factory, s0, r, sigma, td, paths)
         s1, s2 = mc.getAssetValue(1, 0), mc.getAssetValue(2, 0)
         continuation = s2.bus(K).floor(0.0).div(mc.getNumeraire(2.0))           # put pay-off at t = 2
@@ -352,17 +361,26 @@ def test_conditional_expectation_operator(env):
         s1v = s1.getValues()
         estimator = pkg.MonteCarloConditionalExpectationRegression([s1v.mult(0.0).add(1.0), s1v, s1v.squared()])
         expected = continuation.getConditionalExpectation(estimator)
-        trigger = expected.sub(exercise)
-        return model, trigger.choose(continuation, exercise)
+        trigger = expected.sub(exercise) if frozenTrigger is None else frozenTrigger
+        return model, trigger.choose(continuation, exercise), trigger
 
+    # Dirac method ZERO = the pathwise derivative at FIXED exercise decisions.  (Bumped runs that re-decide move paths across the
+    # boundary; with a quadratic regression of a kinked pay-off the rule is not optimal there, so that term does not vanish: measured
+    # -0.327 / -0.360 for bumps of 1e-4 / 2e-2 against -0.345.)  The comparison therefore freezes the decisions of the base run.
     fZero = pkg.RandomVariableDifferentiableAADFactory(env.Factory(), {"diracDeltaApproximationMethod": "ZERO"})
-    model, value = bermudan(fZero, s0)
+    model, value, trigger = bermudan(fZero, s0)
+    assert type(trigger) is pkg.RandomVariableDifferentiableAAD and trigger.getOperatorTreeNode().arguments[0].operatorType == "CONDITIONAL_EXPECTATION"
     delta = value.getGradient()[model.getInitialValue()[0].getID()].getAverage()
-    eps = 1e-4
-    up = bermudan(env.Factory(), s0 + eps)[1].getAverage()
-    dn = bermudan(env.Factory(), s0 - eps)[1].getAverage()
+    eps = 1e-5
+    frozen = trigger.getValues()
+    up = bermudan(env.Factory(), s0 + eps, frozen)[1].getAverage()
+    dn = bermudan(env.Factory(), s0 - eps, frozen)[1].getAverage()
     fd = (up - dn) / (2 * eps)
-    assert delta < 0 and abs(fd - delta) < 5e-3, (fd, delta)   # (the exercise boundary moves in the bumped runs: agreement to MC noise)
+    assert delta < 0 and abs(fd - delta) < 2e-4, (fd, delta)  # (put kinks inside the bump: see the Black-Scholes test)
+    # with the default discrete delta the boundary term is part of the adjoint: the estimate moves, by less than its noise band
+    model, value, _ = bermudan(env.f, s0)
+    withBoundary = value.getGradient()[model.getInitialValue()[0].getID()].getAverage()
+    assert withBoundary != delta and abs(withBoundary - delta) < 0.1
     # the operator itself: d/dx E[ E(x·W² | W) ] = E[W²]
     w = pkg.BrownianMotionCuda(td, 1, paths, 77).getBrownianIncrement(0, 0)
     x = env.f.createRandomVariable(2.0)
