@@ -19,3 +19,5 @@ from .models import (BlackScholesModel, HestonModel, MonteCarloAssetModel, Monte
 from .products import EuropeanOption, DigitalOption, Caplet, Swaption, BermudanSwaption, BermudanOption
 from .autodiff import (RandomVariableDifferentiable, RandomVariableDifferentiableAAD, RandomVariableDifferentiableAADFactory,
                        DiracDeltaApproximationMethod)
+from .calibration import (LevenbergMarquardt, OptimizerFactoryLevenbergMarquardt, RegularizationMethod, CalibrationProduct, SolverException,
+                          solveLinearEquationSVD)

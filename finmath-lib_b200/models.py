@@ -16,7 +16,7 @@ import weakref
 import numpy as np
 
 from .montecarlo import BrownianMotionCuda, EulerSchemeFromProcessModel, Scheme
-from .stochastic import RandomVariable, RandomVariableCuda, RandomVariableCudaFactory, Scalar
+from .stochastic import RandomVariable, RandomVariableCuda, RandomVariableCudaFactory, Scalar, _jexp
 from . import native as nv
 
 
@@ -146,12 +146,39 @@ class MonteCarloBlackScholesModel(MonteCarloAssetModel):
 class LIBORVolatilityModelFourParameterExponentialForm:
     def __init__(self, timeDiscretization, liborPeriodDiscretization, a, b, c, d, isCalibrateable=False):
         self.td, self.tenor, self.a, self.b, self.c, self.d = timeDiscretization, liborPeriodDiscretization, a, b, c, d
+        self.isCalibrateable = isCalibrateable
+
+    def getTimeDiscretization(self): return self.td
+    def getLiborPeriodDiscretization(self): return self.tenor
 
     def getVolatility(self, timeIndex, liborIndex):          # :168-190
         ttm = self.tenor.getTime(liborIndex) - self.td.getTime(timeIndex)
         if ttm <= 0:
             return 0.0
-        return (self.b * ttm + self.a) * math.exp(self.c * (-ttm)) + self.d
+        return (self.b * ttm + self.a) * _jexp(self.c * (-ttm)) + self.d
+
+    def getVolatilityTable(self):
+        """[T][N] of getVolatility (the same expression, evaluated for the whole grid at once: a calibration builds it per evaluation)."""
+        t = np.asarray(self.td.getAsDoubleArray(), dtype=np.float64)[:self.td.getNumberOfTimeSteps()]
+        ttm = np.asarray(self.tenor.getAsDoubleArray(), dtype=np.float64)[None, :self.tenor.getNumberOfTimeSteps()] - t[:, None]
+        with np.errstate(over="ignore", invalid="ignore"):
+            vol = (self.b * ttm + self.a) * _exp_like_libm(self.c * (-ttm)) + self.d
+        return np.where(ttm <= 0, 0.0, vol)
+
+    # parametric interface (:134-166): null unless calibrateable
+    def getParameterAsDouble(self):
+        return [self.a, self.b, self.c, self.d] if self.isCalibrateable else None
+
+    def getCloneWithModifiedParameter(self, parameter):
+        if not self.isCalibrateable:
+            return self
+        a, b, c, d = (float(v.doubleValue()) if hasattr(v, "doubleValue") else float(v) for v in parameter[:4])
+        return LIBORVolatilityModelFourParameterExponentialForm(self.td, self.tenor, a, b, c, d, True)
+
+
+def _exp_like_libm(x):
+    # element by element through math.exp, so that the table equals getVolatility() bit for bit (numpy's vectorised exp may differ by an ulp)
+    return np.vectorize(_jexp, otypes=[np.float64])(x)
 
 
 def _factor_matrix(correlation, numberOfFactors):
@@ -180,7 +207,8 @@ def factorReduction(correlation, numberOfFactors):           # LinearAlgebra.fac
 
 class LIBORCorrelationModelExponentialDecay:
     def __init__(self, timeDiscretization, liborPeriodDiscretization, numberOfFactors, a, isCalibrateable=False):
-        a = max(a, 0)
+        self.td, self.tenor, self.numberOfFactors, self.a, self.isCalibrateable = timeDiscretization, liborPeriodDiscretization, numberOfFactors, a, isCalibrateable
+        a = max(a, 0)                                                                               # :99 (the stored parameter stays as given)
         n = liborPeriodDiscretization.getNumberOfTimeSteps()
         T = liborPeriodDiscretization.getAsDoubleArray()
         corr = np.array([[math.exp(-a * abs(T[r] - T[c])) for c in range(n)] for r in range(n)])     # :102-112
@@ -191,6 +219,20 @@ class LIBORCorrelationModelExponentialDecay:
     def getNumberOfFactors(self): return self.factorMatrix.shape[1]
     def getFactorLoading(self, timeIndex, factor, component): return float(self.factorMatrix[component, factor])
     def getCorrelation(self, timeIndex, c1, c2): return float(self.correlationMatrix[c1, c2])
+    def getTimeDiscretization(self): return self.td
+    def getLiborPeriodDiscretization(self): return self.tenor
+
+    # parametric interface (:74-80, :137-147)
+    def getParameterAsDouble(self):
+        return [self.a] if self.isCalibrateable else None
+
+    def getCloneWithModifiedParameter(self, parameter):
+        a = float(parameter[0].doubleValue()) if hasattr(parameter[0], "doubleValue") else float(parameter[0])
+        if not self.isCalibrateable or self.a == a:
+            return self
+        # (the reference's clone drops the flag, :79 — a one-shot quirk that does not matter there because calibration always clones
+        # from the ORIGINAL model; kept calibrateable here so that a calibrated model can be calibrated again)
+        return LIBORCorrelationModelExponentialDecay(self.td, self.tenor, self.numberOfFactors, a, True)
 
 
 class LIBORCovarianceModelFromVolatilityAndCorrelation:
@@ -198,10 +240,19 @@ class LIBORCovarianceModelFromVolatilityAndCorrelation:
         self.td, self.tenor, self.volatilityModel, self.correlationModel = timeDiscretization, liborPeriodDiscretization, volatilityModel, correlationModel
 
     def getNumberOfFactors(self): return self.correlationModel.getNumberOfFactors()
+    def getTimeDiscretization(self): return self.td
+    def getLiborPeriodDiscretization(self): return self.tenor
+    def getVolatilityModel(self): return self.volatilityModel
+    def getCorrelationModel(self): return self.correlationModel
 
     def getFactorLoadingTable(self):
         """[T][N][F] deterministic factor loadings sigma_j(t_i) * F[j][k] (:47-57) and [T][N] variances sigma*sigma*corr_jj (:82-93)."""
         T, N, F = self.td.getNumberOfTimeSteps(), self.tenor.getNumberOfTimeSteps(), self.getNumberOfFactors()
+        table = getattr(self.volatilityModel, "getVolatilityTable", None)
+        fm, cm = getattr(self.correlationModel, "factorMatrix", None), getattr(self.correlationModel, "correlationMatrix", None)
+        if table is not None and fm is not None and cm is not None:
+            vol = table()                                    # the same products, whole grid at once (bit-identical to the loop below)
+            return vol[:, :, None] * fm[None, :N, :F], (vol * vol) * np.diagonal(cm)[None, :N]
         fl = np.zeros((T, N, F))
         var = np.zeros((T, N))
         for t in range(T):
@@ -211,6 +262,26 @@ class LIBORCovarianceModelFromVolatilityAndCorrelation:
                     fl[t, j, k] = vol * self.correlationModel.getFactorLoading(t, k, j)
                 var[t, j] = (vol * vol) * self.correlationModel.getCorrelation(t, j, j)
         return fl, var
+
+    # ---- parametric interface (LIBORCovarianceModelFromVolatilityAndCorrelation.java:100-160): volatility parameters, then correlation's
+    def getParameterAsDouble(self):
+        v, c = self.volatilityModel.getParameterAsDouble(), self.correlationModel.getParameterAsDouble()
+        return list(v or []) + list(c or [])
+
+    def getCloneWithModifiedParameters(self, parameters):
+        v, c = self.volatilityModel.getParameterAsDouble(), self.correlationModel.getParameterAsDouble()
+        nv_ = len(v) if v is not None else 0
+        vol, corr = self.volatilityModel, self.correlationModel
+        if v is not None:
+            vol = vol.getCloneWithModifiedParameter(list(parameters[:nv_]))
+        if c is not None:
+            corr = corr.getCloneWithModifiedParameter(list(parameters[nv_:nv_ + len(c)]))
+        return LIBORCovarianceModelFromVolatilityAndCorrelation(self.td, self.tenor, vol, corr)
+
+    def getCloneCalibrated(self, calibrationModel, calibrationProducts, calibrationParameters=None):
+        """AbstractLIBORCovarianceModelParametric.java:134-157 -> calibration.getCloneCalibrated."""
+        from .calibration import getCloneCalibrated
+        return getCloneCalibrated(self, calibrationModel, calibrationProducts, calibrationParameters)
 
 
 def _accrue_chain(libors, subs, divisor):
@@ -235,6 +306,7 @@ class LIBORMarketModelFromCovarianceModel:
                  factorLoadingTable=None):
         """forwardRates[j] = L_j(0) on the tenor grid (the forward curve evaluated there); discountFactors[i] = P^d(T_i) or None."""
         properties = dict(properties or {})
+        self._properties = properties
         self.tenor = liborPeriodDiscretization
         self.L0 = np.asarray(forwardRates, dtype=np.float64)
         self.discountFactors = None if discountFactors is None else np.asarray(discountFactors, dtype=np.float64)
@@ -253,7 +325,19 @@ class LIBORMarketModelFromCovarianceModel:
     @classmethod
     def of(cls, liborPeriodDiscretization, analyticModel, forwardRates, discountFactors, randomVariableFactory, covarianceModel, calibrationItems=None,
            properties=None):
-        return cls(liborPeriodDiscretization, forwardRates, discountFactors, randomVariableFactory, covarianceModel, properties)
+        model = cls(liborPeriodDiscretization, forwardRates, discountFactors, randomVariableFactory, covarianceModel, properties)
+        if calibrationItems:                                 # LIBORMarketModelFromCovarianceModel.java:296-318: calibrate, if data is given
+            if not hasattr(covarianceModel, "getCloneCalibrated"):
+                raise TypeError("Calibration restricted to covariance models implementing LIBORCovarianceModelCalibrateable.")   # ClassCastException
+            calibrated = covarianceModel.getCloneCalibrated(model, calibrationItems, (properties or {}).get("calibrationParameters"))
+            return model.getCloneWithModifiedCovarianceModel(calibrated)
+        return model
+
+    def getCovarianceModel(self): return self.covarianceModel
+
+    def getCloneWithModifiedCovarianceModel(self, covarianceModel):                     # :1420-1426: same curves, factory and properties
+        return LIBORMarketModelFromCovarianceModel(self.tenor, self.L0, self.discountFactors, self.randomVariableFactory, covarianceModel,
+                                                   self._properties)
 
     # ---- ProcessModel callbacks -----------------------------------------------------------------------------------------
     def getNumberOfComponents(self): return self.tenor.getNumberOfTimeSteps()
