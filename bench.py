@@ -449,6 +449,11 @@ def main():
             configs.append({"config": "C5 LMM Bermudan swaption, %d paths on this GPU count" % bermudan["strong"]["paths"], "paths": bermudan["strong"]["paths"], "steps": T,
                             "ms": bermudan["strong"]["wall_ms"], "path_steps_per_s": bermudan["strong"]["paths"] * T / (bermudan["strong"]["wall_ms"] * 1e-3)})
 
+    # ---- SURVEY §8f rank 4 on the device: a calibration loop over the fused simulation and an AAD sweep (N = 1 only) --------------------
+    f4 = None
+    if world == 1 and not args.skip_configs:
+        f4 = bc.next_rows(pkg)
+
     if rank == 0:
         line = {
             "metric": "LMM forward-rate path-steps/sec", "value": value, "unit": "path-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -461,7 +466,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "path-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "BrownianMotionCuda + EulerSchemeFromProcessModel + Swaption.getValue through the host API, price on the host each step",
                     "price": prices[-1]},
-            "roofline": roofline, "kernels": fp64, "fast_mode": fast, "bermudan": bermudan, "shard_parity": shard_parity, "configs": configs,
+            "roofline": roofline, "kernels": fp64, "fast_mode": fast, "bermudan": bermudan, "shard_parity": shard_parity, "configs": configs, "f4": f4,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

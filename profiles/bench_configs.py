@@ -102,6 +102,75 @@ def run_all(package, c3_paths=4_000_000):
     return out
 
 
+def next_rows(package, calibration_paths=100_000, aad_paths=1_000_000):
+    """SURVEY §8f rank 4 on the device, for bench.py's `f4` key (wall clock around whole host-API calls; N = 1 only):
+    * calibration: the C4 model shape (40 rates x 3 factors x 40 steps), five covariance parameters against 16 swaption prices of a
+      known model, Levenberg-Marquardt; every evaluation = table set-up + fused LMM kernel on resident increments + 16 valuations;
+    * aad: Black-Scholes European call, 10 steps, forward recording + backward sweep for delta / rho / vega on device vectors."""
+    bind(package)
+    from common import lmm_setup
+    s = lmm_setup(pkg)
+
+    def cov(a, b, c, d, decay):
+        vol = pkg.LIBORVolatilityModelFourParameterExponentialForm(s["sim"], s["tenor"], a, b, c, d, True)
+        corr = pkg.LIBORCorrelationModelExponentialDecay(s["sim"], s["tenor"], s["F"], decay, True)
+        return pkg.LIBORCovarianceModelFromVolatilityAndCorrelation(s["sim"], s["tenor"], vol, corr)
+    factory = pkg.RandomVariableCudaFactory()
+    bm = pkg.BrownianMotionCuda(s["sim"], s["F"], calibration_paths, 31415, factory)
+    products = []
+    for e in (1.0, 2.0, 5.0, 10.0):
+        for n in (2, 4, 10, 20):
+            fix = [e + 0.5 * i for i in range(n)]
+            if fix[-1] + 0.5 <= 20.0:
+                products.append(pkg.Swaption(e, fix, [t + 0.5 for t in fix], [0.05] * n))
+
+    def simulate(c):
+        m = pkg.LIBORMarketModelFromCovarianceModel.of(s["tenor"], None, s["L0"], s["df"], factory, c, None, {"measure": "SPOT"})
+        return m, pkg.LIBORMonteCarloSimulationFromLIBORModel(pkg.EulerSchemeFromProcessModel(m, bm))
+    _, truth = simulate(cov(0.25, 0.02, 0.30, 0.20, 0.15))
+    targets = [p.getValue(truth) for p in products]
+    items = [pkg.CalibrationProduct(p, t, 1.0) for p, t in zip(products, targets)]
+    start = cov(0.15, 0.0, 0.20, 0.30, 0.05)
+    model0, sim0 = simulate(start)
+    rms0 = float(np.sqrt(np.mean([(p.getValue(sim0) - t) ** 2 for p, t in zip(products, targets)])))
+    nv.synchronize()
+    t0 = time.perf_counter()
+    done = start.getCloneCalibrated(model0, items, {"brownianMotion": bm, "maxIterations": 100, "accuracy": 1e-12, "parameterStep": 1e-5})
+    wall = time.perf_counter() - t0
+    info = done.lastCalibration
+    calibration = {"model": "LMM 40 rates x 3 factors x 40 steps, %d paths, increments resident" % calibration_paths, "parameters": 5,
+                   "products": len(products), "iterations": info["iterations"], "evaluations": info["evaluations"], "wall_ms": wall * 1e3,
+                   "ms_per_evaluation": wall * 1e3 / info["evaluations"], "rms_start": rms0, "rms_end": info["rootMeanSquaredError"]}
+    del truth, sim0, done
+    nv.load().fmb_pool_trim()
+
+    td = pkg.TimeDiscretizationFromArray(0.0, 10, 0.5)
+    f = pkg.RandomVariableDifferentiableAADFactory(factory)
+    bmA = pkg.BrownianMotionCuda(td, 1, aad_paths, 3141, factory)
+    bmA.getBrownianIncrement(0, 0)
+
+    def greeks():
+        model = pkg.BlackScholesModel(1.0, 0.05, 0.30, f)
+        mc = pkg.MonteCarloAssetModel(model, pkg.EulerSchemeFromProcessModel(model, bmA))
+        nv.synchronize()
+        t0 = time.perf_counter()
+        launches0 = nv.launch_count()
+        value = pkg.EuropeanOption(5.0, 1.05).getValueRV(0.0, mc)
+        price = value.getAverage()
+        t1 = time.perf_counter()
+        launches1 = nv.launch_count()
+        g = value.getGradient()
+        out = [g[i].getAverage() for i in (model.getInitialValue()[0].getID(), model.getRiskFreeRate().getID(), model.getVolatility().getID())]
+        t2 = time.perf_counter()
+        return price, out, (t1 - t0) * 1e3, (t2 - t1) * 1e3, launches1 - launches0, nv.launch_count() - launches1
+    greeks()
+    price, g, fwd, bwd, lf, lb = greeks()
+    aad = {"model": "Black-Scholes 10 steps, %d paths, European call: recorded generic Euler recipe on device vectors" % aad_paths,
+           "price": price, "delta": g[0], "rho": g[1], "vega": g[2], "forward_ms": fwd, "backward_ms": bwd, "forward_launches": lf, "backward_launches": lb}
+    nv.load().fmb_pool_trim()
+    return {"calibration": calibration, "aad": aad}
+
+
 def c1(seed):
     td = pkg.TimeDiscretizationFromArray(0.0, 100, 0.05)
     m = pkg.MonteCarloBlackScholesModel(1.0, 0.05, 0.30, pkg.BrownianMotionCuda(td, 1, 100_000, 3141 + seed))
