@@ -305,29 +305,29 @@ __global__ void uniformsFromWordsKernel(const uint32_t* __restrict__ w, double* 
 
 // ---------------------------------------------------------------------------------------------------------------
 // Brownian increments.  Block b owns paths [b*ppb, min(P,(b+1)*ppb)) and the MT sub-stream that starts at its first word.
-// The raw MT19937 words live in a shared-memory ring of five 624-word blocks.  (1) Whenever fewer than 2*need raw words are
-// left, the block generates the next 624 (227 threads, three words each, one barrier; every index a compile-time offset from the
-// block base).  Then (2) each thread turns two tempered words into a uniform, applies AS241, scales by sqrt(dt) and drops the
-// value into a shared-memory tile laid out [c = t*F+f][path in tile], (3) full tiles are written to HBM as rows of consecutive
-// paths (coalesced, whole 32-byte sectors).
-// Ring depth: at most 2*NT - 2 + 624 raw words are unconsumed when a block is regenerated (1262 for 320 threads, 1902 for 640), so
-// with five blocks the 624 words being overwritten are never ones a slower warp of the previous batch may still be reading (no
-// barrier between consumption and the next refresh).
+// The raw MT19937 words live in a shared-memory ring of eight 624-word blocks.  (1) One block is always being generated ahead of the
+// consumers (227 threads, three words each, every index a compile-time offset from the block base; completion is signalled through an
+// mbarrier that is waited for one batch later).  (2) Each thread turns two tempered words into a uniform, applies AS241 (central
+// rational for every lane, straight-line; tail draws are parked in a per-warp queue and evaluated by full warps), scales by sqrt(dt)
+// and drops the value into a shared-memory tile laid out [c = t*F+f][path in tile], (3) full tiles are written to HBM as rows of
+// consecutive paths (one bulk store per row, or coalesced element-wise stores for narrow tiles).
 // Algorithmic HBM bytes: 8 per increment (write only).
 // ---------------------------------------------------------------------------------------------------------------
 static const int BM_THREADS = 320;               // 10 warps: 312 uniforms per 624-word block keep 97.5 % of the lanes busy; two CTAs per SM
 static const int BM_THREADS_WIDE = 640;          // used when the tile is so wide (large T*F) that only one CTA per SM fits
-static const int RING_BLOCKS = 5;                // enough for both block sizes (see above: 2*NT - 2 + 624 unconsumed words at most)
+static const int RING_BLOCKS = 8;                // see the static_assert in bmGenerateKernel
 static const int RING = RING_BLOCKS * MT_N;      // raw words
 static const int RING_ALLOC = RING + 2;          // (+ padding: thread 169 reads one word past the last block before replacing the value)
-static const int TAILQ = 2048;                   // deferred tail draws per block (p and tile slot), drained densely
 static const int BM_HEADER = 16;                 // bytes in front of the ring (tail-queue counter)
 
 // Tail draws (|u - 0.5| > 0.425, 15 % of all) cost ~3x a central draw (log, sqrt, a second rational) and would make
-// almost every warp execute both branches.  They are parked in a shared-memory queue and evaluated by full warps.
-template <int NT, bool SCALED> __device__ __forceinline__ void bmDrainTails(const double* __restrict__ qP, const uint32_t* __restrict__ qSlot, uint32_t count,
-		double* __restrict__ tile, int tid, float invPad, const double* __restrict__ sqrtDtPerColumn) {
-	for (uint32_t i = tid; i < count; i += NT) {
+// almost every warp execute both branches.  They are parked in a shared-memory queue and evaluated by full warps.  Every WARP owns a
+// slice of the queue and keeps its fill count in a register (ballot + popc give each lane its position): no atomics, no shuffles, no
+// block-wide barrier around a drain.  A drain evaluates the dense multiple-of-32 prefix and moves the remainder (< 32) to the front.
+template <bool SCALED> __device__ __forceinline__ uint32_t bmDrainWarp(double* __restrict__ qP, uint32_t* __restrict__ qSlot, uint32_t count, bool all,
+		double* __restrict__ tile, int lane, float invPad, const double* __restrict__ sqrtDtPerColumn) {
+	const uint32_t full = all ? count : (count & ~31u);
+	for (uint32_t i = lane; i < full; i += 32) {
 		const double p = qP[i];
 		const uint32_t slot = qSlot[i];
 		double v = as241Tail(p, p - 0.5);
@@ -338,6 +338,12 @@ template <int NT, bool SCALED> __device__ __forceinline__ void bmDrainTails(cons
 		}
 		tile[slot] = v;
 	}
+	const uint32_t rem = count - full;
+	if (rem) {                                                     // (full >= 32 > rem: source and destination do not overlap)
+		if ((uint32_t)lane < rem) { qP[lane] = qP[full + lane]; qSlot[lane] = qSlot[full + lane]; }
+	}
+	__syncwarp();
+	return rem;
 }
 
 // ---- TMA (bulk asynchronous copy engine) helpers: a finished tile row leaves shared memory as ONE bulk store instead of n 8-byte
@@ -357,11 +363,13 @@ __device__ __forceinline__ void bulkCommitAndWaitRead() {
 // Thread i < 227 produces words i, i+227 and i+454 one after the other: word i+227 needs word i and word i+454 needs word i+227
 // (its own results, kept in registers), everything else comes from the previous block - so the whole block needs ONE barrier.
 // The only cross-thread input, x[624] = new word 0 for the very last word, is recomputed by that thread.
-__device__ __forceinline__ void bmRefreshBlock(uint32_t* __restrict__ ring, uint32_t nb, int tid) {
+__device__ __forceinline__ void bmRefreshBlock(uint32_t* __restrict__ ring, uint32_t prevOff, uint32_t newOff, int tid) {
+	// prevOff / newOff: word offsets of the previous and of the new block in the ring (loop-carried by the caller: every address below is
+	// one register plus a compile-time offset)
 	constexpr int W = MT_N - MT_M;                                 // 227
 	if (tid < W) {
-		uint32_t* nw = ring + nb * MT_N + tid;
-		const uint32_t* od = ring + (nb == 0 ? RING_BLOCKS - 1 : nb - 1) * MT_N + tid;
+		uint32_t* nw = ring + newOff + tid;
+		const uint32_t* od = ring + prevOff + tid;
 		const uint32_t v0 = od[MT_M] ^ mtTwist(od[0], od[1]);
 		nw[0] = v0;
 		const uint32_t v1 = v0 ^ mtTwist(od[W], od[W + 1]);
@@ -369,13 +377,32 @@ __device__ __forceinline__ void bmRefreshBlock(uint32_t* __restrict__ ring, uint
 		if (tid < MT_N - 2 * W) {                                  // 170 words
 			uint32_t next = od[2 * W + 1];
 			if (tid == MT_N - 2 * W - 1) {                             // word 623 reads x[624]: the new word 0
-				const uint32_t* o0 = od - tid;
+				const uint32_t* o0 = ring + prevOff;
 				next = o0[MT_M] ^ mtTwist(o0[0], o0[1]);
 			}
 			nw[2 * W] = v1 ^ mtTwist(od[2 * W], next);
 		}
 	}
-	__syncthreads();
+}
+
+// The refresh is decoupled from its consumers with an mbarrier instead of __syncthreads(): a warp ARRIVES when its part of block k+1 is
+// written and only WAITS for block k+1 one batch later, after it has consumed a batch from the blocks before it - by then every warp
+// has long arrived, so nobody stalls at the barrier (with __syncthreads() the single hottest instruction of the kernel was the
+// branch behind the barrier: 11 % of all stall samples, profiles/r02_notes.md).  One refresh is always in flight.
+__device__ __forceinline__ uint32_t bmSmemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bmBarInit(uint64_t* bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bmSmemAddr(bar)), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bmBarArriveWarp(uint64_t* bar, int lane) {
+	__syncwarp();                                                  // the warp's writes are ordered before lane 0's (releasing) arrive
+	if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bmSmemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void bmBarWait(uint64_t* bar, uint32_t parity) {
+	uint32_t done;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bmSmemAddr(bar)), "r"(parity) : "memory");
+	} while (!done);
 }
 
 // TMA: the tile holds the increments already scaled by sqrt(dt) (row stride nPad even: 16-byte aligned rows) and every row is written with
@@ -389,30 +416,39 @@ template <int NT, bool TMA, bool UNIFORM> __global__ void __launch_bounds__(NT, 
 	// "paths" are column chunks of the real paths - virtual path v = (real path v / colChunks, chunk v % colChunks), TF columns each, in
 	// the same stream order - and Pr is the real number of paths; tiles then hold a single virtual path.
 	extern __shared__ __align__(16) unsigned char smemRaw[];
-	uint32_t* qCountP = reinterpret_cast<uint32_t*>(smemRaw);
 	uint32_t* ring = reinterpret_cast<uint32_t*>(smemRaw + BM_HEADER);
 	double* qP = reinterpret_cast<double*>(smemRaw + BM_HEADER + RING_ALLOC * sizeof(uint32_t));
 	uint32_t* qSlot = reinterpret_cast<uint32_t*>(qP + qCap);          // qCap entries (even): tail draws parked until a dense drain
-	// the tile starts 16-byte aligned (bulk stores read whole 16-byte units); !TMA: standard normals, sqrt(dt) of the column is applied when the
-	// tile is written out; TMA: already scaled
-	double* tile = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(qSlot + qCap) + 15) & ~(uintptr_t)15);
+	// the tile starts 16-byte aligned (bulk stores read whole 16-byte units); an OFFSET from the shared-memory base, so that the compiler
+	// keeps the shared address space (32-bit addresses, STS) - rounding the pointer itself made every tile access a generic 64-bit one.
+	// !TMA: standard normals, sqrt(dt) of the column is applied when the tile is written out; TMA: already scaled
+	const uint32_t tileOff = (uint32_t)(BM_HEADER + RING_ALLOC * sizeof(uint32_t) + (size_t)qCap * (sizeof(double) + sizeof(uint32_t)) + 15) & ~15u;
+	double* tile = reinterpret_cast<double*>(smemRaw + tileOff);
 	const int tid = threadIdx.x;
 	const int lane = tid & 31, warp = tid >> 5;
-	static_assert(NT >= MT_N - MT_M && 2 * NT - 2 + 2 * MT_N <= RING, "block size against the refresh width / ring depth");
-	static_assert(TAILQ / 2 >= 2 * BM_THREADS + 64 && TAILQ >= 2 * BM_THREADS_WIDE + 64, "tail queue against the batch size");
-	// batches between two looks at the tail queue: two when that still leaves a full pass of work for a drain (queue >= 4 batches of
-	// worst-case tails), else one
-	const uint32_t checkEvery = (qCap >= 4u * NT) ? 2u : 1u;
-	const uint32_t drainAbove = qCap - (checkEvery + 1u) * NT;
+	// ring depth: when a thread starts writing a new block, at most 2*NT - 2 + 624 complete words are unconsumed and one more block
+	// has just been completed; the slowest warp may still be reading the batch before (2*NT words further back: a warp passes the
+	// wait for refresh k only after every warp has arrived for it, i.e. has finished the batch before the one in which k was issued)
+	static_assert(NT >= MT_N - MT_M && 4 * NT + 3 * MT_N <= RING, "block size against the refresh width / ring depth");
 	static_assert((BM_HEADER + RING_ALLOC * sizeof(uint32_t)) % 8 == 0, "queue alignment");
+	// this warp's slice of the tail queue (a multiple of 32 entries, >= 64) and its fill count
+	const uint32_t wCap = (qCap / (NT / 32)) & ~31u;
+	double* wqP = qP + (uint32_t)warp * wCap;
+	uint32_t* wqSlot = qSlot + (uint32_t)warp * wCap;
+	uint32_t wcount = 0;
+	const uint32_t ltMask = (1u << lane) - 1u;
 
+	uint64_t* refreshBar = reinterpret_cast<uint64_t*>(smemRaw);      // (the 16-byte header)
 	for (int i = tid; i < MT_N; i += NT) ring[i] = states[(size_t)blockIdx.x * MT_N + i];
-	if (tid == 0) *qCountP = 0;
+	if (tid == 0) bmBarInit(refreshBar, NT / 32);
 	__syncthreads();
 
-	// ring position of the next unconsumed raw word (always even), number of generated but unconsumed words, next block to generate
-	uint32_t cpos = MT_N, nb = 1;
+	// ring position of the next unconsumed raw word (always even), number of complete but unconsumed words, word offsets of the newest
+	// complete block and of the block in flight, parity of the refresh in flight
+	uint32_t cpos = MT_N, prevOff = 0, newOff = MT_N, refreshParity = 0;
 	int avail = 0;
+	bmRefreshBlock(ring, prevOff, newOff, tid);
+	bmBarArriveWarp(refreshBar, lane);
 	const uint64_t pBeg = (uint64_t)blockIdx.x * ppb;
 	const uint64_t pEnd = min(P, pBeg + (uint64_t)ppb);
 	// (path in tile, column) of this thread's draw, advanced by NT draws per iteration without divisions
@@ -422,52 +458,63 @@ template <int NT, bool TMA, bool UNIFORM> __global__ void __launch_bounds__(NT, 
 	for (uint64_t p0 = pBeg; p0 < pEnd; p0 += tileN) {
 		const uint32_t n = (uint32_t)min((uint64_t)tileN, pEnd - p0);
 		const uint32_t U = n * TF;
-		uint32_t pl = (uint32_t)tid / TF, c = (uint32_t)tid % TF, it = 0;
+		uint32_t pl = (uint32_t)tid / TF, c = (uint32_t)tid % TF;
 		for (uint32_t u0 = 0; u0 < U; u0 += NT) {
 			const uint32_t need = min((uint32_t)NT, U - u0);
 			while (avail < (int)(2 * need)) {
-				bmRefreshBlock(ring, nb, tid);
-				nb = (nb == RING_BLOCKS - 1) ? 0 : nb + 1;
+				bmBarWait(refreshBar, refreshParity);                  // the block in flight is complete ...
+				refreshParity ^= 1u;
 				avail += MT_N;
+				prevOff = newOff;
+				newOff = (newOff == RING - MT_N) ? 0 : newOff + MT_N;
+				bmRefreshBlock(ring, prevOff, newOff, tid);            // ... and the next one starts from it
+				bmBarArriveWarp(refreshBar, lane);
 			}
-			if ((uint32_t)tid < need) {
-				uint32_t j = cpos + 2 * tid;                           // even, pair never wraps (RING is even)
-				if (j >= RING) j -= RING;
-				const uint2 ww = *reinterpret_cast<const uint2*>(ring + j);
-				const double u = mtUniform(mtTemper(ww.x), mtTemper(ww.y));
+			const bool act = (uint32_t)tid < need;
+			const uint32_t slot = c * nPad + pl;
+			const double sdt = (TMA && !UNIFORM) ? __ldg(sqrtDtPerColumn + c) : 1.0;
+			uint32_t j = cpos + 2 * tid;                               // even, pair never wraps (RING is even)
+			if (j >= RING) j -= RING;
+			// (a thread without a draw reads words that are not generated yet: harmless, always inside the ring)
+			const uint2 ww = *reinterpret_cast<const uint2*>(ring + j);
+			const double u = mtUniform(mtTemper(ww.x), mtTemper(ww.y));
+			if (UNIFORM) {
+				if (act) tile[slot] = u;
+			} else {
+				// the central rational is evaluated for every lane (practically every warp holds central draws, so a branch around it
+				// saves nothing) with a division that has no out-of-line slow path: straight-line code
 				const double q = u - 0.5;
-				const uint32_t slot = c * nPad + pl;
-				if (UNIFORM) {
-					tile[slot] = u;
-				} else if (fabs(q) <= 0.425) {
-					tile[slot] = TMA ? as241Central(q) * __ldg(sqrtDtPerColumn + c) : as241Central(q);
-				} else {
-					const uint32_t k = atomicAdd(qCountP, 1u);
-					qP[k] = u;
-					qSlot[k] = slot;
+				const bool isTail = act && !(fabs(q) <= 0.425);
+				double v = as241Central(q);
+				if (TMA) v = v * sdt;
+				if (act && !isTail) tile[slot] = v;
+				// (the whole warp is here: the batch loop is uniform across the block)
+				const uint32_t tails = __ballot_sync(0xffffffffu, isTail);
+				if (isTail) {
+					const uint32_t pos = wcount + __popc(tails & ltMask);
+					wqP[pos] = u;
+					wqSlot[pos] = slot;
+				}
+				wcount += __popc(tails);
+				// as soon as a full warp's worth of tails is parked, evaluate it: small, frequent drains keep the warps of the block in step
+				// (a warp that drains six groups at once falls five batches behind and the others wait for it at the refresh barrier)
+				if (wcount >= 32u) {
+					__syncwarp();
+					wcount = bmDrainWarp<TMA>(wqP, wqSlot, wcount, false, tile, lane, invPad, sqrtDtPerColumn);
 				}
 			}
+			pl += stepP; c += stepC;
+			if (c >= TF) { c -= TF; pl++; }
 			cpos += 2 * need;
 			if (cpos >= RING) cpos -= RING;
 			avail -= (int)(2 * need);
-			pl += stepP; c += stepC;
-			if (c >= TF) { c -= TF; pl++; }
-			// every checkEvery-th batch: make sure the queue keeps room for the next ones (at most NT new tails per batch)
-			if ((++it & (checkEvery - 1u)) == 0) {
-				__syncthreads();
-				if (*qCountP > drainAbove) {
-					bmDrainTails<NT, TMA>(qP, qSlot, *qCountP, tile, tid, invPad, sqrtDtPerColumn);
-					__syncthreads();
-					if (tid == 0) *qCountP = 0;
-					__syncthreads();
-				}
-			}
 		}
-		__syncthreads();
-		bmDrainTails<NT, TMA>(qP, qSlot, *qCountP, tile, tid, invPad, sqrtDtPerColumn);
+		if (!UNIFORM) {
+			__syncwarp();
+			wcount = bmDrainWarp<TMA>(wqP, wqSlot, wcount, true, tile, lane, invPad, sqrtDtPerColumn);
+		}
 		if (TMA) fenceProxyAsyncShared();
 		__syncthreads();
-		if (tid == 0) *qCountP = 0;
 		if (TMA) {
 			// one bulk store per column: n consecutive paths of column cc, 8n bytes (n even), source row and destination both 16-byte aligned
 			bool issued = false;
@@ -710,21 +757,27 @@ static int generateIncrements(int64_t seed, int T, int F, uint64_t paths, uint64
 	// width / row stride.  FMB_BM_TMA=0 forces the element-wise flush (A/B measurements, profiles/r02_notes.md).
 	bool tma = (paths % 2 == 0);
 	if (const char* e = getenv("FMB_BM_TMA")) tma = tma && atoi(e) != 0;
-	uint32_t tileN = 0, qCap = TAILQ;
+	// the tail queue: 64 entries per warp (31 parked + 32 new at most)
+	uint32_t tileN = 0, qCap = (BM_THREADS / 32) * 64;
 	size_t fixed = 0;
-	const size_t budgets[3] = { 112 * 1024, 112 * 1024, 224 * 1024 };
-	const uint32_t queues[3] = { (uint32_t)TAILQ, (uint32_t)TAILQ / 2, (uint32_t)TAILQ };
-	for (int attempt = 0; attempt < 3; attempt++) {
-		qCap = queues[attempt];
+	int blocksPerSm = 1;
+	// blocks per SM to try, most first: FMB_BM_CTAS=3 adds three 320-thread blocks per SM (A/B switch: more resident warps, but half
+	// again as many sub-stream heads for the jump-ahead)
+	int maxCtas = 2;
+	if (const char* e = getenv("FMB_BM_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= 3) maxCtas = v; }
+	for (int ctas = maxCtas; ctas >= 1; ctas--) {
+		const size_t budget = ctas == 3 ? 74 * 1024 : (ctas == 2 ? 112 * 1024 : 224 * 1024);
+		qCap = ((ctas == 1 ? BM_THREADS_WIDE : BM_THREADS) / 32) * 64;
 		fixed = BM_HEADER + RING_ALLOC * sizeof(uint32_t) + (size_t)qCap * (sizeof(double) + sizeof(uint32_t));
 		fixed = (fixed + 15) & ~(size_t)15;                           // the tile starts 16-byte aligned
-		const size_t avail = budgets[attempt] > fixed ? budgets[attempt] - fixed : 0;
+		const size_t avail = budget > fixed ? budget - fixed : 0;
 		const uint64_t maxPad = avail / (TF * sizeof(double));
+		blocksPerSm = ctas;
 		// rows of at least 16 paths: bulk-store flush (row stride tileN + 2); narrower tiles (T*F in the thousands): element-wise flush
 		// with the odd row stride tileN + 1 - bulk copies of 32-64 bytes do not pay (measured, profiles/r02_notes.md)
 		if (tma && maxPad >= 18) { tileN = (uint32_t)std::min<uint64_t>(((maxPad - 2) / 4) * 4, 256); break; }
 		if (maxPad >= 5) { tileN = (uint32_t)std::min<uint64_t>(((maxPad - 1) / 4) * 4, 256); tma = false; break; }
-		if (attempt == 2) { tileN = maxPad >= 2 ? (uint32_t)(maxPad - 1) : (uint32_t)maxPad; tma = false; }
+		if (ctas == 1) { tileN = maxPad >= 2 ? (uint32_t)(maxPad - 1) : (uint32_t)maxPad; tma = false; }
 	}
 	// T*F so large that not even one path fits the tile: cut every path into colChunks chunks of TFk columns (a divisor of T*F that fits) and
 	// run the kernel on these "virtual paths" - the stream order is unchanged, only the flush addresses differ
@@ -746,7 +799,6 @@ static int generateIncrements(int64_t seed, int T, int F, uint64_t paths, uint64
 	const uint64_t vpaths = paths * colChunks;                    // (virtual) paths the kernel iterates over
 
 	// sub-streams: enough blocks to fill the machine, but at least ~32k uniforms each so that jump-ahead stays a small fraction
-	const int blocksPerSm = smem <= 113 * 1024 ? 2 : 1;
 	uint64_t Bmax = (uint64_t)c.smCount * blocksPerSm;            // one wave of equal sub-streams
 	const uint64_t totalUniforms = paths * TF;
 	Bmax = std::max<uint64_t>(1, std::min<uint64_t>(Bmax, totalUniforms / 32768 + 1));
@@ -779,7 +831,7 @@ static int generateIncrements(int64_t seed, int T, int F, uint64_t paths, uint64
 	const bool wide = blocksPerSm == 1;
 	if (rc == FMB_OK) {
 		auto launch = [&](auto kernel, int NT, int slot) -> int {
-			static size_t attrSmem[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+			static size_t attrSmem[8] = {0};
 			if (smem > attrSmem[slot]) {
 				FMB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 				attrSmem[slot] = smem;
