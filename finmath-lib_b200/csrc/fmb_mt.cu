@@ -196,6 +196,22 @@ static void polyMulX(Poly& p) {
 	if ((p[DEG >> 6] >> (DEG & 63)) & 1ull) for (int w = 0; w < PW; w++) p[w] ^= g_phi.bits[w];
 }
 
+// a * b mod phi (shift-and-add over the set bits of b)
+static Poly polyMul(const Poly& a, const Poly& b) {
+	std::vector<uint64_t> v(2 * PW + 1, 0);
+	for (int w = 0; w < PW; w++) {
+		uint64_t bits = b[w];
+		while (bits) {
+			const int s = __builtin_ctzll(bits);
+			bits &= bits - 1;
+			if (s == 0) { for (int i = 0; i < PW; i++) v[w + i] ^= a[i]; }
+			else { for (int i = 0; i < PW; i++) { v[w + i] ^= a[i] << s; v[w + i + 1] ^= a[i] >> (64 - s); } }
+		}
+	}
+	reduceModPhi(v);
+	return Poly(v.begin(), v.begin() + PW);
+}
+
 // x^J mod phi
 static Poly polyPowX(uint64_t J) {
 	Poly r(PW, 0);
@@ -235,15 +251,21 @@ static const int JUMP_THREADS = 640;
 static const int JUMP_PAD = SEQ_LEN;              // list padding entry: seq[n + JUMP_PAD] is a zero word for every n < 624
 static const int JUMP_SMEM_WORDS = SEQ_LEN + MT_N;
 
-// grid (numOutputs, segments).  Block (o, s): expands source state src[o] to the raw words its share of the coefficient list needs
-// (shared memory), then thread n XORs seq[n + i] over the set coefficients i in list[s*perSeg, (s+1)*perSeg).  The list (ascending
-// exponents, one per set coefficient, built once per polynomial on the host) replaces a bit-scan loop: eight independent
-// shared-memory loads per iteration, addresses known up front.
-__global__ void __launch_bounds__(JUMP_THREADS) mtJumpApplyKernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
-		const uint16_t* __restrict__ list, int listLen, int perSeg, int atomicCombine) {
+// One level of the radix-8 jump tree.  grid (numOutputs, segments).  Output o = (j - 1) * have + i is source state i (< have) jumped with
+// polynomial j (1..7) of the level: dst[o] = g_j applied to src[i].  Block (o, s) expands its source state to the raw words its share of
+// the coefficient list needs (shared memory), then thread n XORs seq[n + e] over the set coefficients e in list_j[s*perSeg, (s+1)*perSeg).
+// The list (ascending exponents, one per set coefficient, built once per polynomial on the host) replaces a bit-scan loop: eight
+// independent shared-memory loads per iteration, addresses known up front.
+static const int JUMP_RADIX = 8;
+struct JumpLevel { int listLen[JUMP_RADIX - 1]; };
+__global__ void __launch_bounds__(JUMP_THREADS) mtJumpApplyKernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int have,
+		const uint16_t* __restrict__ lists, JumpLevel level, int perSeg, int atomicCombine) {
 	extern __shared__ uint32_t seq[];
 	const int tid = threadIdx.x;
-	const uint32_t* s = src + (size_t)blockIdx.x * MT_N;
+	const int jm1 = blockIdx.x / have, i0 = blockIdx.x - jm1 * have;
+	const uint32_t* s = src + (size_t)i0 * MT_N;
+	const uint16_t* list = lists + (size_t)jm1 * JUMP_LIST_MAX;
+	const int listLen = level.listLen[jm1];
 	const int kBeg = blockIdx.y * perSeg;
 	const int kEnd = min(listLen, kBeg + perSeg);
 	if (kBeg >= kEnd) return;
@@ -555,58 +577,77 @@ template <int NT, bool TMA, bool UNIFORM> __global__ void __launch_bounds__(NT, 
 // ================================================================================================================
 // Host orchestration
 // ================================================================================================================
-struct DevicePolys {                               // g_{chunk * 2^k}, k = 0..levels-1, as coefficient lists (JUMP_LIST_MAX uint16 each) on the device
-	uint16_t* dev = nullptr;
-	int levels = 0;
-	int listLen[24] = {0};                         // padded list length per level
-	Poly last;                                     // host copy of the highest level (to extend by squaring)
+// Jump polynomials of one sub-stream length ("chunk", in words), radix 8: level k, j = 1..7: g = x^(j * 8^k * chunk) mod phi, as
+// coefficient lists (JUMP_LIST_MAX uint16 each) on the device.  Built on demand (a level's j-th polynomial is the (j-1)-th times the
+// first; the next level's first is the previous level's first raised to the 8th power: three squarings) and cached per chunk.
+// Nine dependent launches of ~60 us (binary tree, B = 296) become three.
+struct JumpLevelPolys {
+	uint16_t* dev = nullptr;                       // (JUMP_RADIX - 1) lists
+	int count = 0;                                 // polynomials built so far (j = 1..count)
+	int listLen[JUMP_RADIX - 1] = {0};
+	Poly first, last;                              // host copies of g_1 and of g_count
 };
+struct DevicePolys { std::vector<JumpLevelPolys> levels; };
 static std::map<uint64_t, DevicePolys> g_polyCache;     // key: chunk (words)
 static std::mutex g_polyMu;
-static const int MAX_LEVELS = 24;
+static const int MAX_LEVELS = 20;                       // 8^20 sub-streams
 
-struct LevelLists { const uint16_t* dev; const int* listLen; };
-
-static int getLevelPolys(uint64_t chunk, int levels, LevelLists* out) {
+// level `level` of chunk with at least `need` polynomials (1..7)
+static int getLevelPolys(uint64_t chunk, int level, int need, const JumpLevelPolys** out) {
 	FMB_TRY(ensureCharPoly());
 	std::lock_guard<std::mutex> lk(g_polyMu);
-	if (levels > MAX_LEVELS) { setError("too many jump levels"); return FMB_EINVAL; }
+	if (level >= MAX_LEVELS || need < 1 || need > JUMP_RADIX - 1) { setError("too many jump levels"); return FMB_EINVAL; }
 	DevicePolys& dp = g_polyCache[chunk];
-	if (!dp.dev) {
-		FMB_CUDA(cudaMalloc(&dp.dev, (size_t)MAX_LEVELS * JUMP_LIST_MAX * sizeof(uint16_t)));
+	dp.levels.reserve(MAX_LEVELS);                              // (callers keep a pointer to a level: no reallocation later)
+	if ((int)dp.levels.size() <= level) dp.levels.resize(level + 1);
+	for (int k = 0; k <= level; k++) {
+		JumpLevelPolys& L = dp.levels[k];
+		const int want = (k == level) ? need : 1;                   // lower levels: only their first polynomial is needed to climb
+		if (!L.dev && (k == level)) FMB_CUDA(cudaMalloc(&L.dev, (size_t)(JUMP_RADIX - 1) * JUMP_LIST_MAX * sizeof(uint16_t)));
+		while (L.count < want) {
+			if (L.count == 0) {
+				if (k == 0) L.first = polyPowX(chunk);
+				else { L.first = dp.levels[k - 1].first; for (int q = 0; q < 3; q++) polySquare(L.first); }
+				L.last = L.first;
+			} else {
+				L.last = polyMul(L.last, L.first);
+			}
+			if (!L.dev) FMB_CUDA(cudaMalloc(&L.dev, (size_t)(JUMP_RADIX - 1) * JUMP_LIST_MAX * sizeof(uint16_t)));
+			std::vector<uint16_t> list(JUMP_LIST_MAX);
+			L.listLen[L.count] = polyToBitList(L.last, list.data(), (uint16_t)JUMP_PAD);
+			FMB_CUDA(cudaMemcpyAsync(L.dev + (size_t)L.count * JUMP_LIST_MAX, list.data(), JUMP_LIST_MAX * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx().stream));
+			FMB_CUDA(cudaStreamSynchronize(ctx().stream));
+			L.count++;
+		}
 	}
-	while (dp.levels < levels) {
-		if (dp.levels == 0) dp.last = polyPowX(chunk); else polySquare(dp.last);
-		std::vector<uint16_t> list(JUMP_LIST_MAX);
-		dp.listLen[dp.levels] = polyToBitList(dp.last, list.data(), (uint16_t)JUMP_PAD);
-		FMB_CUDA(cudaMemcpyAsync(dp.dev + (size_t)dp.levels * JUMP_LIST_MAX, list.data(), JUMP_LIST_MAX * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx().stream));
-		FMB_CUDA(cudaStreamSynchronize(ctx().stream));
-		dp.levels++;
-	}
-	out->dev = dp.dev;
-	out->listLen = dp.listLen;
+	*out = &dp.levels[level];
 	return FMB_OK;
 }
 
-static int launchJump(const uint32_t* src, uint32_t* dst, const uint16_t* list, int listLen, int count) {
+// dst[(j - 1) * have + i] = g_j applied to src[i], for the first `count` outputs
+static int launchJump(const uint32_t* src, uint32_t* dst, int have, const JumpLevelPolys& L, int count) {
 	static bool attrSet = false;
 	const size_t smem = (size_t)JUMP_SMEM_WORDS * sizeof(uint32_t);
 	if (!attrSet) {
 		FMB_CUDA(cudaFuncSetAttribute(mtJumpApplyKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attrSet = true;
 	}
-	if (listLen == 0) {                                        // zero polynomial cannot occur (x^J mod phi != 0); keep the output defined
+	const int polys = (count + have - 1) / have;
+	JumpLevel lv;
+	int maxLen = 0;
+	for (int j = 0; j < JUMP_RADIX - 1; j++) { lv.listLen[j] = j < polys ? L.listLen[j] : 0; maxLen = std::max(maxLen, lv.listLen[j]); }
+	if (maxLen == 0) {                                         // zero polynomial cannot occur (x^J mod phi != 0); keep the output defined
 		FMB_CUDA(cudaMemsetAsync(dst, 0, (size_t)count * MT_N * sizeof(uint32_t), ctx().stream));
 		return FMB_OK;
 	}
-	// split the coefficient list over several blocks while the level has fewer outputs than the machine has SM slots
+	// split the coefficient lists over several blocks while the level has fewer outputs than the machine has SM slots
 	const int slots = 2 * ctx().smCount;
 	// (about two waves of blocks: a level whose output count is not a multiple of the SM count would otherwise wait for a ragged last wave)
 	int segs = std::max(1, std::min(32, (2 * slots + count - 1) / count));
-	int perSeg = (((listLen + segs - 1) / segs) + 7) & ~7;
-	segs = (listLen + perSeg - 1) / perSeg;
+	int perSeg = (((maxLen + segs - 1) / segs) + 7) & ~7;
+	segs = (maxLen + perSeg - 1) / perSeg;
 	if (segs > 1) FMB_CUDA(cudaMemsetAsync(dst, 0, (size_t)count * MT_N * sizeof(uint32_t), ctx().stream));
-	mtJumpApplyKernel<<<dim3(count, segs), JUMP_THREADS, smem, ctx().stream>>>(src, dst, list, listLen, perSeg, segs > 1 ? 1 : 0);
+	mtJumpApplyKernel<<<dim3(count, segs), JUMP_THREADS, smem, ctx().stream>>>(src, dst, have, L.dev, lv, perSeg, segs > 1 ? 1 : 0);
 	countLaunch();
 	FMB_CUDA(cudaGetLastError());
 	return FMB_OK;
@@ -621,26 +662,23 @@ static int buildStreamHeads(int64_t seed, uint64_t firstWord, uint64_t chunk, in
 		FMB_CUDA(cudaMemcpyAsync(heads, st, sizeof(st), cudaMemcpyHostToDevice, c.stream));
 		FMB_CUDA(cudaStreamSynchronize(c.stream));
 	} else {
-		LevelLists ll;
-		FMB_TRY(getLevelPolys(firstWord, 1, &ll));
+		const JumpLevelPolys* L;
+		FMB_TRY(getLevelPolys(firstWord, 0, 1, &L));
 		void* tmp;
 		FMB_TRY(poolAlloc(sizeof(st), &tmp));
 		FMB_CUDA(cudaMemcpyAsync(tmp, st, sizeof(st), cudaMemcpyHostToDevice, c.stream));
 		FMB_CUDA(cudaStreamSynchronize(c.stream));
-		int rc = launchJump((const uint32_t*)tmp, heads, ll.dev, ll.listLen[0], 1);
+		int rc = launchJump((const uint32_t*)tmp, heads, 1, *L, 1);
 		poolFree(tmp, sizeof(st));
 		FMB_TRY(rc);
 	}
-	if (B > 1) {
-		int levels = 0;
-		while ((1 << levels) < B) levels++;
-		LevelLists ll;
-		FMB_TRY(getLevelPolys(chunk, levels, &ll));
-		for (int k = 0; k < levels; k++) {
-			const int have = 1 << k;
-			const int cnt = std::min(have, B - have);
-			FMB_TRY(launchJump(heads, heads + (size_t)have * MT_N, ll.dev + (size_t)k * JUMP_LIST_MAX, ll.listLen[k], cnt));
-		}
+	// radix-8 tree: level k turns heads [0, 8^k) into heads [8^k, 8^(k+1)): head[j * 8^k + i] = head[i] jumped by j * 8^k * chunk
+	int level = 0;
+	for (int64_t have = 1; have < B; have *= JUMP_RADIX, level++) {
+		const int cnt = (int)std::min<int64_t>((JUMP_RADIX - 1) * have, B - have);
+		const JumpLevelPolys* L;
+		FMB_TRY(getLevelPolys(chunk, level, (int)((cnt + have - 1) / have), &L));
+		FMB_TRY(launchJump(heads, heads + (size_t)have * MT_N, (int)have, *L, cnt));
 	}
 	return FMB_OK;
 }
@@ -662,6 +700,15 @@ int fmb_test_host_jump(int64_t seed, uint64_t J, uint32_t* state_out /* 624 */, 
 	std::vector<uint32_t> raw;
 	mtRawSequence(st, SEQ_LEN, raw);
 	Poly g = polyPowX(J);
+	if (J >= 3) {
+		// self-check of the general product the radix-8 jump tree is built from: x^a * x^(J-a) = x^J (mod phi), and a cube by squaring
+		// and multiplying
+		const uint64_t a = J / 3;
+		const Poly pa = polyPowX(a);
+		Poly sq = pa;
+		polySquare(sq);
+		if (polyMul(pa, polyPowX(J - a)) != g || polyMul(sq, pa) != polyPowX(3 * a)) { setError("test_host_jump: polynomial product mismatch"); return FMB_ECUDA; }
+	}
 	uint32_t w32[MT_N];
 	polyToWords32(g, w32);
 	for (int n = 0; n < MT_N; n++) {
