@@ -131,7 +131,8 @@ def _bind_fast():
     except ImportError:                   # stochastic.py is still being imported: it calls _bind_fast() again when it is done
         return
     addr = lambda name: C.cast(getattr(_lib, name), C.c_void_p).value
-    _F.bind(addr("fmb_rv_unary"), addr("fmb_rv_binary"), addr("fmb_rv_ternary"), addr("fmb_rv_free"), check, RandomVariableCuda, DeviceVector)
+    _F.bind(addr("fmb_rv_unary"), addr("fmb_rv_binary"), addr("fmb_rv_ternary"), addr("fmb_rv_free"), addr("fmb_rv_eval_chain"), check,
+            RandomVariableCuda, DeviceVector, LazyVector)
     _F.set_lazy_min_n(_lazy_min_n if _lazy else 2 ** 64 - 1)
 
 
@@ -198,16 +199,15 @@ class DeviceVector(_F.DV):
 # element-wise operation the chain grows; when anything else needs it (a reduction, a kernel argument, a download: every access to
 # `.h`), the whole chain is evaluated in ONE pass by fmb_rv_eval_chain.  Same device functions, order and roundings as the one-op
 # kernels: results are bit-identical to eager evaluation (tests/test_gpu_rv.py compares both modes).  FMB_LAZY=0 or
-# set_lazy(False) switches the deferral off.
+# set_lazy(False) switches the deferral off.  The recording itself is C code (csrc/host/fmbfast.c: ~0.3 us per operation), so it pays at
+# every vector length: measured with deferral for all sizes against deferral from 2 M elements (round 1, when the recording was Python):
+# Bermudan 1 M paths 11.86 -> 11.57 ms (567 -> 313 launches), calibration evaluation (100 k paths, 16 swaptions) 7.4 -> 4.7 ms.
 CHAIN_MAX_INSTR, CHAIN_MAX_LEAVES, CHAIN_MAX_SCALARS = 16, 8, 24
 _lazy = os.environ.get("FMB_LAZY", "1") != "0"
-# Deferral pays where the device time dominates (it removes kernel launches and HBM round trips of intermediate results); on short
-# vectors a valuation is bound by the host, and eager launches overlap the device with the host better (measured on C5, profiles/
-# r01_notes.md).  Vectors shorter than this are evaluated eagerly.
 try:
-    _lazy_min_n = int(os.environ.get("FMB_LAZY_MIN_N", "2000000"))
+    _lazy_min_n = int(os.environ.get("FMB_LAZY_MIN_N", "0"))
 except ValueError:
-    _lazy_min_n = 2000000
+    _lazy_min_n = 0
 
 
 def set_lazy(on, min_n=None):
@@ -227,38 +227,10 @@ def lazy_min_n():
     return _lazy_min_n
 
 
-class LazyVector:
-    """Result of element-wise operations that has not been evaluated yet.  Duck-types DeviceVector (h, n, download, get).
-    start: the leaf the accumulator starts from; prog: tuple of (kind, op, pos, others, a) with others = vectors or floats;
-    nvec / nsca: upper bounds of the distinct leaf vectors / scalars the chain needs."""
-    __slots__ = ("_h", "n", "start", "prog", "uses", "nvec", "nsca", "__weakref__")
-
-    def __init__(self, n, start, prog, nvec, nsca):
-        self._h = 0
-        self.n = n
-        self.start = start
-        self.prog = prog
-        self.uses = 0
-        self.nvec = nvec
-        self.nsca = nsca
-
-    @property
-    def h(self):
-        if self._h == 0:
-            self._materialize()
-        return self._h
-
-    def pending(self):
-        return self._h == 0
-
-    def __del__(self):
-        h = self._h
-        if h and _lib is not None:
-            self._h = 0
-            try:
-                _lib.fmb_rv_free(h)
-            except Exception:
-                pass
+class LazyVector(_F.LV):
+    """Result of element-wise operations that has not been evaluated yet (the recorded chain and its evaluation live in the C base type,
+    csrc/host/fmbfast.c).  Duck-types DeviceVector: h (evaluates on first access), n, download, get."""
+    __slots__ = ()
 
     def download(self):
         out = np.empty(self.n, dtype=np.float64)
@@ -270,101 +242,10 @@ class LazyVector:
         check(load().fmb_rv_get(self.h, int(i), C.byref(v)))
         return v.value
 
-    def _materialize(self):
-        out = C.c_uint64()
-        prog, lib = self.prog, _lib
-        if len(prog) == 1:                                   # one operation: the specialised kernel
-            kind, op, pos, others, a = prog[0]
-            if kind == 0:
-                rc = lib.fmb_rv_unary(op, self.start.h, a, _byref(out))
-            else:
-                ops = list(others)
-                ops.insert(pos, self.start)
-                hs = [0 if type(o) is float else o.h for o in ops]
-                sc = [o if type(o) is float else 0.0 for o in ops]
-                if kind == 1:
-                    rc = lib.fmb_rv_binary(op, hs[0], sc[0], hs[1], sc[1], _byref(out))
-                else:
-                    rc = lib.fmb_rv_ternary(op, hs[0], sc[0], hs[1], sc[1], hs[2], sc[2], a, _byref(out))
-        else:
-            leaves, leaf_index, scalars, scalar_index = [self.start], {id(self.start): 0}, [], {}
-            code = bytearray()
-            for kind, op, pos, others, a in prog:
-                refs = [0, 0, 0]
-                k = 0
-                for o in others:
-                    if type(o) is float:
-                        mergeable = o == o and o != 0.0                   # NaN and signed zeros are never merged (0.0 == -0.0)
-                        i = scalar_index.get(o) if mergeable else None
-                        if i is None:
-                            i = len(scalars)
-                            scalars.append(o)
-                            if mergeable:
-                                scalar_index[o] = i
-                        refs[k] = 128 | i
-                    else:
-                        i = leaf_index.get(id(o))
-                        if i is None:
-                            i = leaf_index[id(o)] = len(leaves)
-                            leaves.append(o)
-                        refs[k] = i
-                    k += 1
-                if kind != 1:                                # the operation's own double argument
-                    mergeable = a == a and a != 0.0
-                    i = scalar_index.get(a) if mergeable else None
-                    if i is None:
-                        i = len(scalars)
-                        scalars.append(a)
-                        if mergeable:
-                            scalar_index[a] = i
-                    refs[2 if kind == 2 else 0] = 128 | i
-                code += bytes((kind, op, pos, refs[0], refs[1], refs[2], 0, 0))
-            hs = (C.c_uint64 * len(leaves))(*[o.h for o in leaves])
-            sc = (C.c_double * max(1, len(scalars)))(*scalars)
-            rc = lib.fmb_rv_eval_chain(len(prog), bytes(code), 0, hs, len(leaves), sc, len(scalars), _byref(out))
-        if rc != FMB_OK:
-            check(rc)
-        self._h = out.value
-        self.start = None
-        self.prog = None
-
-
-_byref = C.byref
-
 
 def _lazy_op(kind, op, operands, a):
-    """operands: positional list of DeviceVector / LazyVector / float (scalar broadcast).  Returns a LazyVector."""
-    n = -1
-    host = -1
-    nvec = nsca = 0
-    for i, o in enumerate(operands):
-        if type(o) is float:
-            nsca += 1
-            continue
-        if n < 0:
-            n = o.n
-        elif o.n != n:
-            raise ValueError("finmath_b200: operand sizes differ (%d vs %d)" % (o.n, n))      # IllegalArgumentException, as the eager call
-        nvec += 1
-        # the operand whose pending chain this operation extends: the first unevaluated, not yet consumed LazyVector with room left
-        if type(o) is LazyVector and o._h == 0:
-            if host < 0 and o.uses == 0 and len(o.prog) < CHAIN_MAX_INSTR and o.nvec + 2 <= CHAIN_MAX_LEAVES and o.nsca + 3 <= CHAIN_MAX_SCALARS:
-                host = i
-            else:
-                o._materialize()                             # second consumer, or the chain is full: evaluate it, use it as a leaf
-    if kind != 1:
-        nsca += 1
-    if host >= 0:
-        base = operands[host]
-        if base._h == 0:                                     # (not the case when the same object sits in two operand positions)
-            base.uses = 1
-            others = tuple(x for j, x in enumerate(operands) if j != host)
-            return LazyVector(n, base.start, base.prog + ((kind, op, host, others, a),), base.nvec + nvec - 1, base.nsca + nsca)
-    start = 0
-    while type(operands[start]) is float:
-        start += 1
-    others = tuple(x for j, x in enumerate(operands) if j != start)
-    return LazyVector(n, operands[start], ((kind, op, start, others, a),), nvec, nsca)
+    """operands: positional tuple of DeviceVector / LazyVector / float (scalar broadcast).  Returns a LazyVector."""
+    return _F.lazy_op(kind, op, operands, a)
 
 
 def unary(op, x, a=0.0):

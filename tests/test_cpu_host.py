@@ -234,15 +234,29 @@ def test_hull_white_coefficient_tables_equal_oracle(pkg, orc):
         assert np.array_equal(mine, coef)
 
 
+_KEEP_ALIVE = []
+
+
 class _FakeLib:
-    """Stands in for libfinmath_b200.so under native.LazyVector: records the C-ABI calls a chain turns into (no device needed)."""
+    """Stands in for libfinmath_b200.so under native.LazyVector: records the C-ABI calls a chain turns into (no device needed).  The chain
+    logic lives in the C accelerator, which calls the entry points by ADDRESS: the fakes are handed over as ctypes callbacks."""
 
     def __init__(self):
         self.calls, self.next_handle = [], 100
+        H, D, I = C.c_uint64, C.c_double, C.c_int
+        self.callbacks = [
+            C.CFUNCTYPE(I, I, H, D, C.POINTER(H))(self.fmb_rv_unary),
+            C.CFUNCTYPE(I, I, H, D, H, D, C.POINTER(H))(self.fmb_rv_binary),
+            C.CFUNCTYPE(I, I, H, D, H, D, H, D, D, C.POINTER(H))(self.fmb_rv_ternary),
+            C.CFUNCTYPE(I, H)(self.fmb_rv_free),
+            C.CFUNCTYPE(I, I, C.POINTER(C.c_ubyte), I, C.POINTER(H), I, C.POINTER(D), I, C.POINTER(H))(self.fmb_rv_eval_chain)]
+
+    def addresses(self):
+        return [C.cast(cb, C.c_void_p).value for cb in self.callbacks]
 
     def _out(self, ref):
         self.next_handle += 1
-        ref._obj.value = self.next_handle
+        ref[0] = self.next_handle
         return 0
 
     def fmb_rv_unary(self, op, x, a, out):
@@ -258,7 +272,7 @@ class _FakeLib:
         return self._out(out)
 
     def fmb_rv_eval_chain(self, n, code, start, leaves, nl, scalars, ns, out):
-        self.calls.append(("chain", n, bytes(code), start, [int(leaves[i]) for i in range(nl)], [float(scalars[i]) for i in range(ns)]))
+        self.calls.append(("chain", n, bytes(code[i] for i in range(8 * n)), start, [int(leaves[i]) for i in range(nl)], [float(scalars[i]) for i in range(ns)]))
         return self._out(out)
 
     def fmb_rv_free(self, h):
@@ -270,9 +284,12 @@ def test_deferred_arithmetic_builds_the_documented_chain_encoding(pkg, monkeypat
     element-wise consumer evaluates them, one-operation chains use the specialised kernel, scalars that must not be merged are not."""
     nv = pkg.native
     fake = _FakeLib()
+    _KEEP_ALIVE.append(fake)                                 # (objects of this test release their fake handles through these callbacks later)
     monkeypatch.setattr(nv, "_lib", fake)
     monkeypatch.setattr(nv, "_lazy", True)
     monkeypatch.setattr(nv, "_lazy_min_n", 0)
+    nv._F.bind(*fake.addresses(), nv.check, pkg.RandomVariableCuda, nv.DeviceVector, nv.LazyVector)
+    nv._F.set_lazy_min_n(0)
     x, y, z = nv.DeviceVector(11, 8), nv.DeviceVector(12, 8), nv.DeviceVector(13, 8)
     try:
         # (x - 0.03) * 0.5 / y, then  z + that * y  (the pending chain sits in the second operand position of the ternary)
@@ -312,9 +329,28 @@ def test_deferred_arithmetic_builds_the_documented_chain_encoding(pkg, monkeypat
             c = nv.unary(nv.U_ADD, c, 1.0)
         c.h
         assert [cc[1] for cc in fake.calls if cc[0] == "chain"] == [nv.CHAIN_MAX_INSTR, 3]
+        # the same through the RandomVariable fast paths: (X * 2 + Y).exp() is one chain, evaluated when a handle is asked for
+        fake.calls.clear()
+        RV = pkg.RandomVariableCuda
+        X, Y = RV(0.5, None, _dv=x, _n=8), RV(1.5, None, _dv=y, _n=8)
+        r = X.mult(2.0).add(Y).exp()
+        assert fake.calls == [] and type(r.dv) is nv.LazyVector and r.dv.chain_length() == 3 and r.getFiltrationTime() == 1.5
+        r.dv.h
+        assert [c[0] for c in fake.calls] == ["chain"] and fake.calls[0][4] == [11, 12]
+        # short vectors are launched at once
+        nv._F.set_lazy_min_n(9)
+        fake.calls.clear()
+        e = X.mult(2.0)
+        assert type(e.dv) is nv.DeviceVector and [c[0] for c in fake.calls] == ["unary"]
+        e.dv.h = 0
     finally:
         for v in (x, y, z):
             v.h = 0                                            # fake handles: nothing to free
+        monkeypatch.undo()
+        nv._F.set_lazy_min_n(2 ** 64 - 1)
+        nv._lib = None if not hasattr(nv._lib, "fmb_init") else nv._lib
+        if nv._lib is not None:
+            nv._bind_fast()                                    # the real library again for the tests that follow
 
 
 def test_reference_arm_inputs_are_independent_of_and_equal_to_the_products_tables(pkg, orc):
