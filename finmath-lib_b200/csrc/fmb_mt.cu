@@ -397,10 +397,12 @@ __device__ __forceinline__ void bmRefreshBlock(uint32_t* __restrict__ ring, uint
 		const uint32_t v1 = v0 ^ mtTwist(od[W], od[W + 1]);
 		nw[W] = v1;
 		if (tid < MT_N - 2 * W) {                                  // 170 words
-			uint32_t next = od[2 * W + 1];
-			if (tid == MT_N - 2 * W - 1) {                             // word 623 reads x[624]: the new word 0
+			uint32_t next;
+			if (tid == MT_N - 2 * W - 1) {                             // word 623 needs x[624], the new word 0 (thread 0 is writing it): recomputed
 				const uint32_t* o0 = ring + prevOff;
 				next = o0[MT_M] ^ mtTwist(o0[0], o0[1]);
+			} else {
+				next = od[2 * W + 1];
 			}
 			nw[2 * W] = v1 ^ mtTwist(od[2 * W], next);
 		}
