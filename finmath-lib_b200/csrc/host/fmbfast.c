@@ -8,7 +8,7 @@
  * general path and as the specification):
  *     stochastic (device vector) op number,  stochastic op deterministic RandomVariableCuda (add / sub / mult),
  *     stochastic op stochastic,  accrue / discount / addProduct / choose with stochastic operands.
- * Anything else (deterministic receivers, other RandomVariable types, deferred chains, size mismatches) returns NotImplemented and
+ * Anything else (deterministic receivers, other RandomVariable types, size mismatches) returns NotImplemented and
  * the Python method carries on.  No numerics here: the functions called are fmb_rv_unary / fmb_rv_binary / fmb_rv_ternary /
  * fmb_rv_free of libfinmath_b200.so, bound by address from the ctypes handle (no second copy of the library is loaded).
  *

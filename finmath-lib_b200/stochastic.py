@@ -322,7 +322,8 @@ class RandomVariableCuda(nv._F.RV, RandomVariable):
 
     The five attributes (time, valueIfNonStochastic, shard, nGlobal, dv) live in the C base type, which also implements the common
     cases of the hot operations (_fast_unary / _fast_binary / _fast_ternary: stochastic op number, stochastic op stochastic, with the
-    same filtration-time rules as the methods below); they return NotImplemented for everything else and the method carries on."""
+    same filtration-time rules as the methods below); they return NotImplemented for everything else and the method carries on.
+    ``dv`` is a DeviceVector or a LazyVector (element-wise operations recorded for one fused evaluation: native.py); both offer h and n."""
 
     def __init__(self, time, value, shard=None, _dv=None, _n=None):
         self.time = float(time)
