@@ -369,7 +369,8 @@ def main():
         strong, _ = bermudan_run(args.bermudan_strong_paths, factory)
         nv.load().fmb_pool_trim()
         bermudan = dict(weak, exercise_dates=20, basis_functions=6, scaling="weak", paths_per_gpu=args.bermudan_paths,
-                        exchange=("native NCCL all-gather on the compute stream" if shard.native_comm else ("shared-memory mailbox" if shard._mailbox is not None else "torch.distributed"))
+                        exchange=(("native: peer-memory stores over NVLink + flags, one kernel per exchange on the compute stream" if getattr(shard, "peer_exchange", False)
+                                   else "native NCCL all-gather on the compute stream") if shard.native_comm else ("shared-memory mailbox" if shard._mailbox is not None else "torch.distributed"))
                         if world > 1 else "none (1 GPU)",
                         strong={"wall_ms": strong["wall_ms"], "paths": strong["paths"], "price": strong["price"], "scaling": "strong"})
         parity_inputs = (Pb, weak["price"], sw_sharded, product, bermudan_run)

@@ -57,12 +57,40 @@ static int bindNccl() {
 	return FMB_OK;
 }
 
+// ---- peer-memory exchange ----------------------------------------------------------------------------------------------------
+// The payloads are a few hundred bytes: what an exchange costs is latency, and an NCCL all-gather of 16 bytes per rank takes ~13 us on
+// 8 GPUs (launch + protocol).  With the gather buffers of all ranks mapped into every process (CUDA IPC: one process per GPU), ONE
+// small kernel per rank stores its partials into everybody's buffer over NVLink, releases a flag per destination and waits for the flags of
+// the others.  The reductions and the regression go one step further and do this from the finalising CTA of the very kernel that
+// produced the partials, which then also merges the shards (and solves): no second and third launch per exchange (fmb_reduce.cu); the
+// stand-alone kernel below serves the remaining callers (order statistics, empty shards).  Two buffer halves are used alternately: a rank can only be one exchange ahead of the slowest one (it needs
+// everybody's flag to finish an exchange), so the half it overwrites has been consumed everywhere.
+__global__ void __launch_bounds__(128) peerGatherKernel(const double* __restrict__ send, int count, PeerArgs px) { peerExchangeBlock(px, send, count); }
+
+// arguments of the next peer exchange (advances the exchange counter; comm.gatherBuf = where the gathered partials will be)
+void peerArgsNext(PeerArgs& px) {
+	Comm& m = ctx().comm;
+	px.rank = m.rank; px.world = m.world; px.half = (int)(m.exchanges & 1); px.seq = m.exchanges + 1; px.err = m.peerErrDev;
+	for (int r = 0; r < 8; r++) px.base[r] = m.peerGather[r];
+	m.gatherBuf = m.peerBase + px.half * PEER_HALF_DOUBLES;
+	m.exchanges++;
+}
+
 // all-gather `count` doubles per rank from comm.sendBuf into comm.gatherBuf ([world][count]) on the compute stream
 int commAllGather(int count) {
 	Context& c = ctx();
 	Comm& m = c.comm;
 	if (!m.active) return FMB_OK;
 	if (count > COMM_MAX_DOUBLES) { setError("exchange of %d doubles exceeds the buffer (%d)", count, COMM_MAX_DOUBLES); return FMB_EINVAL; }
+	if (m.peer) {
+		if (*m.peerErrHost) { setError("peer exchange: a rank did not arrive (timed out)"); return FMB_ECUDA; }
+		PeerArgs px;
+		peerArgsNext(px);
+		peerGatherKernel<<<1, 128, 0, c.stream>>>(m.sendBuf, count, px);
+		FMB_CUDA(cudaGetLastError());
+		countLaunch();
+		return FMB_OK;
+	}
 	const int rc = g_nccl.allGather(m.sendBuf, m.gatherBuf, (size_t)count, kNcclFloat64, m.comm, c.stream);
 	if (rc != 0) { setError("ncclAllGather failed: %s", g_nccl.errorString(rc)); return FMB_ECUDA; }
 	m.exchanges++;
@@ -112,13 +140,78 @@ int fmb_comm_shutdown(void) {
 	if (!m.active) return FMB_OK;
 	cudaStreamSynchronize(c.stream);
 	g_nccl.commDestroy(m.comm);
+	if (m.peer) {
+		for (int r = 0; r < m.world; r++) if (r != m.rank && m.peerGather[r]) cudaIpcCloseMemHandle(m.peerGather[r]);
+		for (int r = 0; r < 8; r++) m.peerGather[r] = nullptr;
+		m.gatherBuf = m.ncclGatherBuf;
+		m.peer = false;
+	}
+	if (m.peerBase) { cudaFree(m.peerBase); m.peerBase = nullptr; }
+	if (m.peerErrHost) { cudaFreeHost((void*)m.peerErrHost); m.peerErrHost = nullptr; m.peerErrDev = nullptr; }
 	cudaFree(m.sendBuf); cudaFree(m.gatherBuf);
-	m.sendBuf = m.gatherBuf = nullptr; m.comm = nullptr; m.active = false; m.rank = 0; m.world = 1;
+	m.sendBuf = m.gatherBuf = m.ncclGatherBuf = nullptr; m.comm = nullptr; m.active = false; m.rank = 0; m.world = 1;
+	return FMB_OK;
+}
+
+// Peer-memory exchange, step 1: this rank's buffer (allocated on the first call) as a 64-byte CUDA IPC handle.  The host gathers the
+// handles of all ranks (any channel) and hands them to fmb_comm_peer_open.
+int fmb_comm_peer_handle(unsigned char* handle, int len) {
+	FMB_TRY(requireInit());
+	if (!handle || len < (int)sizeof(cudaIpcMemHandle_t)) { setError("comm_peer_handle: the buffer must hold %d bytes", (int)sizeof(cudaIpcMemHandle_t)); return FMB_EINVAL; }
+	Context& c = ctx();
+	Comm& m = c.comm;
+	std::lock_guard<std::mutex> lk(c.scratchMu);
+	if (!m.active || m.world < 2 || m.world > 8) { setError("comm_peer_handle: needs a communicator of 2..8 ranks (fmb_comm_init first)"); return FMB_EUNSUPPORTED; }
+	if (!m.peerBase) {
+		FMB_CUDA(cudaMalloc((void**)&m.peerBase, PEER_ALLOC_BYTES));
+		FMB_CUDA(cudaMemset(m.peerBase, 0, PEER_ALLOC_BYTES));
+		unsigned int* eh = nullptr;
+		FMB_CUDA(cudaHostAlloc((void**)&eh, sizeof(unsigned int), cudaHostAllocMapped));
+		*eh = 0;
+		m.peerErrHost = eh;
+		FMB_CUDA(cudaHostGetDevicePointer((void**)&m.peerErrDev, eh, 0));
+	}
+	cudaIpcMemHandle_t h;
+	FMB_CUDA(cudaIpcGetMemHandle(&h, m.peerBase));
+	memcpy(handle, &h, sizeof(h));
+	return FMB_OK;
+}
+
+// step 2: handles = world x 64 bytes in rank order (this rank's own entry is ignored).  From then on the exchanges of the reductions and
+// regressions go through peer memory instead of NCCL.  Every rank must have called fmb_comm_peer_handle before any rank calls this, and
+// all ranks must switch at the same point of their (identical) call sequences.
+int fmb_comm_peer_open(const unsigned char* handles, int len) {
+	FMB_TRY(requireInit());
+	Context& c = ctx();
+	Comm& m = c.comm;
+	std::lock_guard<std::mutex> lk(c.scratchMu);
+	if (!m.active || !m.peerBase) { setError("comm_peer_open: call fmb_comm_peer_handle first"); return FMB_EINVAL; }
+	if (!handles || len < m.world * (int)sizeof(cudaIpcMemHandle_t)) { setError("comm_peer_open: %d handles of %d bytes expected", m.world, (int)sizeof(cudaIpcMemHandle_t)); return FMB_EINVAL; }
+	if (m.peer) return FMB_OK;
+	FMB_CUDA(cudaStreamSynchronize(c.stream));
+	for (int r = 0; r < m.world; r++) {
+		if (r == m.rank) { m.peerGather[r] = m.peerBase; continue; }
+		cudaIpcMemHandle_t h;
+		memcpy(&h, handles + (size_t)r * sizeof(h), sizeof(h));
+		void* p = nullptr;
+		const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess) {
+			for (int q = 0; q < r; q++) if (q != m.rank && m.peerGather[q]) { cudaIpcCloseMemHandle(m.peerGather[q]); m.peerGather[q] = nullptr; }
+			setError("comm_peer_open: cannot map the buffer of rank %d (%s)", r, cudaGetErrorString(e));
+			cudaGetLastError();
+			return FMB_EUNSUPPORTED;
+		}
+		m.peerGather[r] = (double*)p;
+	}
+	m.ncclGatherBuf = m.gatherBuf;
+	m.exchanges &= ~1ull;                                  // (all ranks share the call sequence: the same count everywhere; start on half 0)
+	m.peer = true;
 	return FMB_OK;
 }
 
 int fmb_comm_info(int* rank, int* world, uint64_t* exchanges) {
 	const Comm& m = ctx().comm;
+	if (m.peer && m.peerErrHost && *m.peerErrHost) { setError("peer exchange: a rank did not arrive (timed out)"); return FMB_ECUDA; }
 	if (rank) *rank = m.rank;
 	if (world) *world = m.active ? m.world : 1;
 	if (exchanges) *exchanges = m.exchanges;

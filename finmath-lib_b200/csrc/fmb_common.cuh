@@ -56,10 +56,57 @@ struct Comm {
 	void* lib = nullptr;         // dlopen handle
 	void* comm = nullptr;        // ncclComm_t
 	double* sendBuf = nullptr;   // device, COMM_MAX_DOUBLES
-	double* gatherBuf = nullptr; // device, world * COMM_MAX_DOUBLES
+	double* gatherBuf = nullptr; // device, world * COMM_MAX_DOUBLES (peer mode: the half of peerBase the last exchange filled)
 	uint64_t exchanges = 0;
+	// peer-memory exchange (fmb_comm_peer_open): every rank stores its partials straight into the gather buffers of all ranks over
+	// NVLink; one allocation per rank: gather[2][world][COMM_MAX_DOUBLES] doubles, then flags[2][world] (two halves used alternately)
+	bool peer = false;
+	double* ncclGatherBuf = nullptr;             // the NCCL path's gather buffer while the peer path is active
+	double* peerBase = nullptr;                  // this rank's allocation (exported with cudaIpcGetMemHandle)
+	double* peerGather[8] = {nullptr};           // base of every rank's allocation as mapped into this process (own included)
+	unsigned int* peerErrDev = nullptr;          // set by a kernel that gave up waiting for a peer
+	volatile unsigned int* peerErrHost = nullptr;
 };
 static const int COMM_MAX_DOUBLES = 512;      // 2 * (8*9/2 + 8) = 88 doubles for the largest regression (K = 8); 256 for a radix-select histogram
+
+// ---- peer-memory exchange (fmb_comm.cu sets it up; the reduction kernels call peerExchangeBlock from their finalising CTA) -------------
+static const size_t PEER_HALF_DOUBLES = 8 * (size_t)COMM_MAX_DOUBLES;          // gather[world <= 8][COMM_MAX_DOUBLES]
+static const size_t PEER_FLAGS_OFFSET = 2 * PEER_HALF_DOUBLES;                 // in 8-byte words: flags[2][8] behind the two halves
+static const size_t PEER_ALLOC_BYTES = (PEER_FLAGS_OFFSET + 16) * sizeof(double);
+struct PeerArgs {
+	int rank = 0, world = 1, half = 0;       // world == 1: no exchange
+	unsigned long long seq = 0;              // value of the flags of this exchange (unique, non-zero, the same on all ranks)
+	double* base[8] = {nullptr};             // every rank's buffer as mapped into this process
+	unsigned int* err = nullptr;
+};
+#ifdef __CUDACC__
+// Called by ALL threads of one CTA (blockDim >= world).  Stores `count` doubles of payload into slot `rank` of every rank's gather
+// buffer (NVLink stores), releases this rank's flag at every destination and waits until every rank's flag has arrived here.  On return
+// the payloads of all ranks are at peerGathered(px, count) as [world][count].
+__device__ __forceinline__ const double* peerGathered(const PeerArgs& px) { return px.base[px.rank] + px.half * PEER_HALF_DOUBLES; }
+__device__ inline void peerExchangeBlock(const PeerArgs& px, const double* payload, int count) {
+	const int tid = threadIdx.x;
+	for (int d = 0; d < px.world; d++) {
+		double* dst = px.base[d] + px.half * PEER_HALF_DOUBLES + (size_t)px.rank * count;
+		for (int i = tid; i < count; i += blockDim.x) dst[i] = payload[i];
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (tid < px.world) {
+		unsigned long long* f = reinterpret_cast<unsigned long long*>(px.base[tid] + PEER_FLAGS_OFFSET) + px.half * 8 + px.rank;
+		asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(f), "l"(px.seq) : "memory");
+		const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(px.base[px.rank] + PEER_FLAGS_OFFSET) + px.half * 8 + tid;
+		unsigned long long v;
+		const long long t0 = clock64();
+		for (;;) {
+			asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+			if (v == px.seq) break;
+			if (clock64() - t0 > 60000000000ll) { atomicExch(px.err, 1u); break; }     // ~30 s: a peer never arrived (reported by the next reduction)
+		}
+	}
+	__syncthreads();
+}
+#endif
 
 struct Context {
 	bool initialized = false;

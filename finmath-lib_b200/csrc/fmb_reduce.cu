@@ -97,8 +97,23 @@ __device__ __forceinline__ dd blockReduceDd(dd v) {
 }
 
 // out2[0..1] = (hi, lo) of the sum over all n elements
+// shard merge in the finalising CTA (peer exchange): payload (hi, lo) of this rank -> all ranks -> rank-ordered double-double merge
+__device__ inline void finishSumShards(const PeerArgs& px, dd t, double* __restrict__ out2) {
+	__shared__ double payload[2];
+	if (threadIdx.x == 0) { payload[0] = t.hi; payload[1] = t.lo; }
+	__syncthreads();
+	peerExchangeBlock(px, payload, 2);
+	if (threadIdx.x == 0) {
+		const double* g = peerGathered(px);
+		dd m = { __ldcg(g), __ldcg(g + 1) };
+		for (int r = 1; r < px.world; r++) { const dd o = { __ldcg(g + 2 * r), __ldcg(g + 2 * r + 1) }; ddMerge(m, o); }
+		out2[0] = m.hi; out2[1] = m.lo;
+	}
+}
+
+// px.world > 1: the finalising CTA also exchanges the result with the other ranks (peer memory) and writes the merged value to out2
 template <int OP> __global__ void __launch_bounds__(RED_THREADS) sumKernel(const double* __restrict__ x, const double* __restrict__ w,
-		double a, uint64_t n, double* __restrict__ partials /* [grid][2] */, unsigned int* ticket, double* __restrict__ out2) {
+		double a, uint64_t n, double* __restrict__ partials /* [grid][2] */, unsigned int* ticket, double* __restrict__ out2, const PeerArgs px) {
 	dd acc0 = {0.0, 0.0}, acc1 = {0.0, 0.0};
 	const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
 	uint64_t i = blockIdx.x * (uint64_t)RED_THREADS + threadIdx.x;
@@ -116,6 +131,7 @@ template <int OP> __global__ void __launch_bounds__(RED_THREADS) sumKernel(const
 	ddMerge(acc0, acc1);
 	dd t = blockReduceDd(acc0);
 	if (gridDim.x == 1) {
+		if (px.world > 1) { finishSumShards(px, t, out2); return; }
 		if (threadIdx.x == 0) { out2[0] = t.hi; out2[1] = t.lo; }
 		return;
 	}
@@ -124,6 +140,7 @@ template <int OP> __global__ void __launch_bounds__(RED_THREADS) sumKernel(const
 	dd m = {0.0, 0.0};
 	for (unsigned int b = threadIdx.x; b < gridDim.x; b += RED_THREADS) { const dd o = { __ldcg(partials + 2 * b), __ldcg(partials + 2 * b + 1) }; ddMerge(m, o); }
 	m = blockReduceDd(m);
+	if (px.world > 1) { finishSumShards(px, m, out2); return; }
 	if (threadIdx.x == 0) { out2[0] = m.hi; out2[1] = m.lo; }
 }
 
@@ -143,14 +160,36 @@ template <bool IS_MAX> __device__ __forceinline__ double blockReduceMinMax(doubl
 	return m;
 }
 
+// (value, "this shard holds data") of this rank -> all ranks -> min / max over the shards that hold data, in rank order
+template <bool IS_MAX> __device__ inline void finishMinMaxShards(const PeerArgs& px, double v, double* __restrict__ out2) {
+	__shared__ double payload[2];
+	if (threadIdx.x == 0) { payload[0] = v; payload[1] = 1.0; }
+	__syncthreads();
+	peerExchangeBlock(px, payload, 2);
+	if (threadIdx.x == 0) {
+		const double* g = peerGathered(px);
+		bool any = false;
+		double t = 0.0;
+		for (int r = 0; r < px.world; r++) {
+			if (__ldcg(g + 2 * r + 1) == 0.0) continue;
+			const double o = __ldcg(g + 2 * r);
+			t = any ? (IS_MAX ? jmaxD(t, o) : jminD(t, o)) : o;
+			any = true;
+		}
+		out2[0] = any ? t : NAN;
+		out2[1] = any ? 1.0 : 0.0;
+	}
+}
+
 template <bool IS_MAX> __global__ void __launch_bounds__(RED_THREADS) minMaxKernel(const double* __restrict__ x, uint64_t n, double* __restrict__ partials,
-		unsigned int* ticket, double* __restrict__ out2) {
+		unsigned int* ticket, double* __restrict__ out2, const PeerArgs px) {
 	const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
 	uint64_t i = blockIdx.x * (uint64_t)RED_THREADS + threadIdx.x;
 	double m = x[i < n ? i : 0];
 	for (; i < n; i += stride) m = IS_MAX ? jmaxD(m, x[i]) : jminD(m, x[i]);
 	m = blockReduceMinMax<IS_MAX>(m);
 	if (gridDim.x == 1) {
+		if (px.world > 1) { finishMinMaxShards<IS_MAX>(px, m, out2); return; }
 		if (threadIdx.x == 0) { out2[0] = m; out2[1] = 1.0; }
 		return;
 	}
@@ -159,6 +198,7 @@ template <bool IS_MAX> __global__ void __launch_bounds__(RED_THREADS) minMaxKern
 	double t = __ldcg(partials + (threadIdx.x < gridDim.x ? threadIdx.x : 0));
 	for (unsigned int b = threadIdx.x; b < gridDim.x; b += RED_THREADS) { const double o = __ldcg(partials + b); t = IS_MAX ? jmaxD(t, o) : jminD(t, o); }
 	t = blockReduceMinMax<IS_MAX>(t);
+	if (px.world > 1) { finishMinMaxShards<IS_MAX>(px, t, out2); return; }
 	if (threadIdx.x == 0) { out2[0] = t; out2[1] = 1.0; }
 }
 
@@ -414,7 +454,7 @@ template <int K> __device__ void regressionFinish(const double* __restrict__ src
 //   FINISH 0: writes the local moments ((hi, lo) pairs) to momOut (mapped host memory, or the communicator's send buffer),
 //   FINISH 1: (single GPU) goes straight on to the solve: no second launch, nothing returns to the host.
 template <int K, int FINISH> __global__ void __launch_bounds__(RED_THREADS) momentsKernel(BasisArgs b, const double* __restrict__ y, uint64_t n,
-		double* __restrict__ partials /* [grid][M][2] */, unsigned int* ticket, double* __restrict__ momOut, FitArgs f) {
+		double* __restrict__ partials /* [grid][M][2] */, unsigned int* ticket, double* __restrict__ momOut, FitArgs f, const PeerArgs px) {
 	constexpr int M = K * (K + 1) / 2 + K;
 	dd acc[M];
 #pragma unroll
@@ -495,6 +535,13 @@ template <int K, int FINISH> __global__ void __launch_bounds__(RED_THREADS) mome
 		__syncthreads();
 		regressionFinish<K>(momOut, b, f);
 	}
+	if (FINISH == 2) {
+		// sharded: the local moments go to all ranks through peer memory, then every rank merges the shards in rank order and solves
+		__threadfence_block();
+		__syncthreads();
+		peerExchangeBlock(px, momOut, 2 * M);
+		regressionFinish<K>(peerGathered(px), b, f);
+	}
 }
 
 // after the all-gather of the shards' moments: merge in rank order + solve (one CTA)
@@ -520,11 +567,13 @@ template <int K> __global__ void __launch_bounds__(256) predictKernelV(BasisArgs
 static int reduceGrid() { return ctx().smCount * 4; }
 
 int commAllGather(int count);                      // fmb_comm.cu
+void peerArgsNext(PeerArgs& px);                   // fmb_comm.cu
 
 template <int K> static void launchMoments(int finish, const BasisArgs& b, const double* y, uint64_t n, double* partials, unsigned int* ticket, double* momOut,
-		const FitArgs& f, int grid, cudaStream_t s) {
-	if (finish) momentsKernel<K, 1><<<grid, RED_THREADS, 0, s>>>(b, y, n, partials, ticket, momOut, f);
-	else momentsKernel<K, 0><<<grid, RED_THREADS, 0, s>>>(b, y, n, partials, ticket, momOut, f);
+		const FitArgs& f, int grid, cudaStream_t s, const PeerArgs& px = PeerArgs()) {
+	if (finish == 2) momentsKernel<K, 2><<<grid, RED_THREADS, 0, s>>>(b, y, n, partials, ticket, momOut, f, px);
+	else if (finish) momentsKernel<K, 1><<<grid, RED_THREADS, 0, s>>>(b, y, n, partials, ticket, momOut, f, px);
+	else momentsKernel<K, 0><<<grid, RED_THREADS, 0, s>>>(b, y, n, partials, ticket, momOut, f, px);
 }
 template <int K> static void launchSolve(const double* gathered, const BasisArgs& b, const FitArgs& f, cudaStream_t s) {
 	regressionSolveKernel<K><<<1, 64, 0, s>>>(gathered, b, f);
@@ -562,19 +611,29 @@ static int enqueueFit(int K, const BasisArgs& b, const double* y, uint64_t nLoca
 	double* momLocal = c.comm.active ? c.comm.sendBuf : dpart + (size_t)grid * M * 2;
 	FitArgs f;
 	f.world = 1; f.n = nGlobal; f.cachedFit = cachedFit; f.fit = fit;
-	const int finish = c.comm.active ? 0 : 1;
+	// sharded with peer exchange: ONE kernel accumulates, exchanges over NVLink, merges the shards and solves (an empty shard has no
+	// accumulation kernel: it takes part through the stand-alone exchange kernel below - same protocol)
+	const bool fused = c.comm.active && c.comm.peer && nLocal > 0;
+	const int finish = fused ? 2 : (c.comm.active ? 0 : 1);
+	PeerArgs px;
+	if (fused) {
+		if (*c.comm.peerErrHost) { setError("peer exchange: a rank did not arrive (timed out)"); return FMB_ECUDA; }
+		peerArgsNext(px);
+		f.world = c.comm.world;
+		momLocal = dpart + (size_t)grid * M * 2;
+	}
 	if (nLocal == 0) {
 		// an empty shard contributes zero moments (it still takes part in the exchange)
 		FMB_CUDA(cudaMemsetAsync(momLocal, 0, (size_t)M * 2 * sizeof(double), c.stream));
 		if (finish) { setError("regression on an empty vector"); return FMB_EINVAL; }
 	} else {
-#define CALL(KV) launchMoments<KV>(finish, b, y, nLocal, dpart, c.ticket, momLocal, f, grid, c.stream)
+#define CALL(KV) launchMoments<KV>(finish, b, y, nLocal, dpart, c.ticket, momLocal, f, grid, c.stream, px)
 		FMB_K_SWITCH(K, CALL)
 #undef CALL
 		countLaunch();
 		FMB_CUDA(cudaGetLastError());
 	}
-	if (c.comm.active) {
+	if (c.comm.active && !fused) {
 		FMB_TRY(commAllGather(2 * M));
 		f.world = c.comm.world;
 #define CALL(KV) launchSolve<KV>(c.comm.gatherBuf, b, f, c.stream)
@@ -629,22 +688,30 @@ int fmb_rv_reduce(int op, fmb_handle x, fmb_handle w, double a, double* out2) {
 	std::lock_guard<std::mutex> lk(c.scratchMu);
 	FMB_TRY(ensureScratch(0, (size_t)grid * 2 * sizeof(double)));
 	double* dpart = (double*)c.scratch;
-	double* dst = c.comm.active ? c.comm.sendBuf : c.hostResultDev;
+	// sharded with peer exchange: the finalising CTA exchanges over NVLink, merges the shards and writes the result (one launch); an
+	// empty shard has no reduction kernel and takes part through the stand-alone exchange kernel (same protocol)
+	const bool fused = c.comm.active && c.comm.peer && n > 0;
+	PeerArgs px;
+	if (fused) {
+		if (*c.comm.peerErrHost) { setError("peer exchange: a rank did not arrive (timed out)"); return FMB_ECUDA; }
+		peerArgsNext(px);
+	}
+	double* dst = (c.comm.active && !fused) ? c.comm.sendBuf : c.hostResultDev;
 	if (n == 0) {
 		FMB_CUDA(cudaMemsetAsync(dst, 0, 2 * sizeof(double), c.stream));          // (0, 0): a zero sum / "no data" for min and max
 	} else {
 		switch (op) {
-		case FMB_R_SUM: sumKernel<FMB_R_SUM><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, wp, a, n, dpart, c.ticket, dst); break;
-		case FMB_R_SUM_PRODUCT: sumKernel<FMB_R_SUM_PRODUCT><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, wp, a, n, dpart, c.ticket, dst); break;
-		case FMB_R_CENTERED_M2: sumKernel<FMB_R_CENTERED_M2><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, wp, a, n, dpart, c.ticket, dst); break;
-		case FMB_R_CENTERED_M2_W: sumKernel<FMB_R_CENTERED_M2_W><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, wp, a, n, dpart, c.ticket, dst); break;
-		case FMB_R_MIN: minMaxKernel<false><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, n, dpart, c.ticket, dst); break;
-		case FMB_R_MAX: minMaxKernel<true><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, n, dpart, c.ticket, dst); break;
+		case FMB_R_SUM: sumKernel<FMB_R_SUM><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, wp, a, n, dpart, c.ticket, dst, px); break;
+		case FMB_R_SUM_PRODUCT: sumKernel<FMB_R_SUM_PRODUCT><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, wp, a, n, dpart, c.ticket, dst, px); break;
+		case FMB_R_CENTERED_M2: sumKernel<FMB_R_CENTERED_M2><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, wp, a, n, dpart, c.ticket, dst, px); break;
+		case FMB_R_CENTERED_M2_W: sumKernel<FMB_R_CENTERED_M2_W><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, wp, a, n, dpart, c.ticket, dst, px); break;
+		case FMB_R_MIN: minMaxKernel<false><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, n, dpart, c.ticket, dst, px); break;
+		case FMB_R_MAX: minMaxKernel<true><<<grid, RED_THREADS, 0, c.stream>>>(vx->ptr, n, dpart, c.ticket, dst, px); break;
 		}
 		countLaunch();
 		FMB_CUDA(cudaGetLastError());
 	}
-	if (c.comm.active) {
+	if (c.comm.active && !fused) {
 		FMB_TRY(commAllGather(2));
 		mergeShardsKernel<<<1, 32, 0, c.stream>>>(c.comm.gatherBuf, c.comm.world, 2, isMinMax ? (op == FMB_R_MIN ? 1 : 2) : 0, c.hostResultDev);
 		countLaunch();

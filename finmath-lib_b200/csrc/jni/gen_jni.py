@@ -92,6 +92,8 @@ TABLE = [
     ("commInit", "fmb_comm_init", "void", [("B", "id"), ("i", "rank"), ("i", "world")], "(const unsigned char*)id_p, id_n, rank, world"),
     ("commShutdown", "fmb_comm_shutdown", "void", [], ""),
     ("commInfo", "fmb_comm_info", "custom", [], ""),
+    ("commPeerHandle", "fmb_comm_peer_handle", "custom", [], ""),
+    ("commPeerOpen", "fmb_comm_peer_open", "void", [("B", "handles")], "(const unsigned char*)handles_p, handles_n"),
     ("benchDfmaTflops", "fmb_bench_dfma_tflops", "double", [], "OUT"),
     ("benchCopyGbs", "fmb_bench_copy_gbs", "double", [("l", "bytes")], "(uint64_t)bytes, OUT"),
 ]
@@ -150,6 +152,9 @@ CUSTOM_C = {
     "commUniqueId": ("jbyteArray", "",
                      "\tunsigned char id[128];\n\tCHECK(fmb_comm_unique_id(id, 128));\n\tjbyteArray out = (*env)->NewByteArray(env, 128);\n\tif (!out) return NULL;\n"
                      "\t(*env)->SetByteArrayRegion(env, out, 0, 128, (const jbyte*)id);\n\treturn out;\n"),
+    "commPeerHandle": ("jbyteArray", "",
+                       "\tunsigned char h[64];\n\tCHECK(fmb_comm_peer_handle(h, 64));\n\tjbyteArray out = (*env)->NewByteArray(env, 64);\n\tif (!out) return NULL;\n"
+                       "\t(*env)->SetByteArrayRegion(env, out, 0, 64, (const jbyte*)h);\n\treturn out;\n"),
     # { rank, world, exchanges }
     "commInfo": ("jlongArray", "",
                  "\tint rank = 0, world = 1;\n\tuint64_t ex = 0;\n\tCHECK(fmb_comm_info(&rank, &world, &ex));\n\tjlongArray out = (*env)->NewLongArray(env, 3);\n\tif (!out) return NULL;\n"
@@ -157,7 +162,7 @@ CUSTOM_C = {
 }
 CUSTOM_JAVA = {"lastError": "String", "deviceName": "String", "timerStopMs": "double", "upload": "long", "download": "double[]", "devicePointer": "long",
                "poolStats": "long[]", "countLessOrEqual": "long[]", "mtWords": "int[]", "regressionMoments": "double[]", "solveSvd": "double[]",
-               "regressionFitGet": "double[]", "regressionConditionalExpectation": "long[]", "commUniqueId": "byte[]", "commInfo": "long[]"}
+               "regressionFitGet": "double[]", "regressionConditionalExpectation": "long[]", "commUniqueId": "byte[]", "commInfo": "long[]", "commPeerHandle": "byte[]"}
 
 
 def acquire(args):

@@ -100,6 +100,8 @@ PROTOTYPES = {
     "fmb_comm_init": [C.c_char_p, C.c_int, C.c_int, C.c_int],
     "fmb_comm_shutdown": [],
     "fmb_comm_info": [C.POINTER(C.c_int), C.POINTER(C.c_int), c_hp],
+    "fmb_comm_peer_handle": [C.c_char_p, C.c_int],
+    "fmb_comm_peer_open": [C.c_char_p, C.c_int],
     "fmb_bench_dfma_tflops": [c_dp],
     "fmb_bench_copy_gbs": [C.c_uint64, c_dp],
 }

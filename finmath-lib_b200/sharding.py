@@ -6,11 +6,12 @@ single-stream reference.  No path data ever moves between GPUs; the only exchang
 getAverage / getVariance / getMin / getMax and the regression's 27 moments: per rank a double-double pair per sum,
 all-gathered and merged in rank order on every rank, so all ranks hold the same bits.
 
-Default on GPUs (FMB_TINY_COLLECTIVES=nccl): the exchange happens INSIDE the native library — fmb_comm_init gives it an NCCL
-communicator on its own compute stream, fmb_rv_reduce / fmb_regression_fit all-gather the partials there and merge them in rank order
-on the device, so a regression needs no host round trip and a getAverage is one synchronisation.  The host-side variants remain as
-measured alternatives and for the CPU tests: FMB_TINY_COLLECTIVES=shm (a shared-memory mailbox between the processes of one x86 node)
-and =torch (torch.distributed all-gather: gloo on CPU, NCCL with host staging on GPUs).
+Default on GPUs (FMB_TINY_COLLECTIVES=peer): the exchange happens INSIDE the native library, on its compute stream — every rank stores
+its partials straight into the gather buffers of all ranks over NVLink (CUDA IPC mappings of one small buffer per rank) from one small
+kernel, the partials are merged in rank order on the device, so a regression needs no host round trip and a getAverage is one
+synchronisation.  =nccl does the same with an NCCL all-gather per exchange (the fallback when the devices have no peer access, and
+across nodes).  The host-side variants remain as measured alternatives and for the CPU tests: FMB_TINY_COLLECTIVES=shm (a shared-memory
+mailbox between the processes of one x86 node) and =torch (torch.distributed all-gather: gloo on CPU, NCCL with host staging on GPUs).
 """
 import atexit
 import os
@@ -97,6 +98,7 @@ class ShardContext:
         self._buffers = {}
         self._mailbox = None
         self.native_comm = False                             # True: the native library exchanges the partials itself (fmb_comm_init)
+        self.peer_exchange = False                           # True: through peer memory over NVLink instead of NCCL all-gathers
 
     def use_native_comm(self):
         """Give the native library its own NCCL communicator (rank 0 creates the id, torch.distributed carries it to the others)."""
@@ -111,6 +113,35 @@ class ShardContext:
         dist.broadcast_object_list(box, src=0, group=self.group)
         nv.check(lib.fmb_comm_init(box[0], 128, self.rank, self.world))
         self.native_comm = True
+        self.peer_exchange = False
+
+    def use_peer_exchange(self):
+        """Map the gather buffers of all ranks into every process (CUDA IPC) so that the native exchanges go through peer memory instead of
+        NCCL.  All ranks of one node, 2..8 of them; returns False (and changes nothing, on any rank) if some rank cannot map a peer."""
+        import ctypes as C
+        import socket
+        import torch.distributed as dist
+        from . import native as nv
+        lib = nv.load()
+        if not self.native_comm or not 2 <= self.world <= 8:
+            return False
+        buf = C.create_string_buffer(64)
+        ok = lib.fmb_comm_peer_handle(buf, 64) == nv.FMB_OK
+        mine = (socket.gethostname(), buf.raw if ok else None)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        if len(set(h for h, _ in everyone)) != 1 or any(b is None for _, b in everyone):
+            return False
+        # two phases, so that either every rank switches or none does: map (can fail), agree, then switch
+        rc = lib.fmb_comm_peer_open(b"".join(b for _, b in everyone), 64 * self.world)
+        oks = [None] * self.world
+        dist.all_gather_object(oks, rc == nv.FMB_OK, group=self.group)
+        if not all(oks):
+            if rc == nv.FMB_OK:
+                raise RuntimeError("finmath_b200: peer exchange could be set up on some ranks only")
+            return False
+        self.peer_exchange = True
+        return True
 
     def use_mailbox(self, name, create):
         """Switch the tiny all-gathers to the shared-memory mailbox (all ranks on one node)."""
@@ -241,11 +272,13 @@ def from_environment(backend=None):
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
     shard = ShardContext(rank, world, None, device)
     from . import native as nv
-    mode = os.environ.get("FMB_TINY_COLLECTIVES", "nccl" if backend == "nccl" else "shm")
+    mode = os.environ.get("FMB_TINY_COLLECTIVES", "peer" if backend == "nccl" else "shm")
     if backend == "nccl":
         nv.init(local_rank)                                  # one process per GPU: the native library on this rank's device
-    if mode == "nccl" and backend == "nccl":
+    if mode in ("peer", "nccl") and backend == "nccl":
         shard.use_native_comm()
+        if mode == "peer":
+            shard.use_peer_exchange()                        # (stays on NCCL if the devices cannot map each other)
         return shard
     import platform
     if mode != "torch" and platform.machine() in ("x86_64", "AMD64"):

@@ -228,6 +228,13 @@ int fmb_comm_unique_id(unsigned char* id, int len);
 int fmb_comm_init(const unsigned char* id, int len, int rank, int world);
 int fmb_comm_shutdown(void);
 int fmb_comm_info(int* rank, int* world, uint64_t* exchanges);
+/* Peer-memory exchange (one node, 2..8 ranks, one process per GPU): instead of an NCCL all-gather per reduction, every rank stores its
+ * partials straight into the gather buffers of all ranks over NVLink (CUDA IPC mappings) from one small kernel and waits for the others'
+ * flags - the payloads are tens of bytes, so the latency of the exchange is what counts.  Every rank calls fmb_comm_peer_handle (64
+ * bytes out), the host gathers the handles in rank order (any channel) and every rank calls fmb_comm_peer_open at the same point of the
+ * call sequence.  FMB_EUNSUPPORTED (no peer access between the devices): the NCCL path simply stays in use. */
+int fmb_comm_peer_handle(unsigned char* handle, int len);
+int fmb_comm_peer_open(const unsigned char* handles, int len);
 
 /* ---- micro-benchmarks used by bench.py to measure the roofline denominators on the box itself ---------------------- */
 int fmb_bench_dfma_tflops(double* tflops);          /* dependent-chain-free DFMA loop on all SMs: FP64 pipe peak */

@@ -79,7 +79,8 @@ jlong J(regressionPredict)(JNIEnv*, jclass, jlongArray, jdoubleArray, jdoubleArr
 jdoubleArray J(regressionFitGet)(JNIEnv*, jclass, jlong, jint); jlong J(regressionPredictFit)(JNIEnv*, jclass, jlongArray, jdoubleArray, jlong);
 jlongArray J(regressionConditionalExpectation)(JNIEnv*, jclass, jlongArray, jdoubleArray, jlong, jlong, jlong, jlongArray, jdoubleArray);
 jbyteArray J(commUniqueId)(JNIEnv*, jclass); void J(commInit)(JNIEnv*, jclass, jbyteArray, jint, jint); void J(commShutdown)(JNIEnv*, jclass);
-jlongArray J(commInfo)(JNIEnv*, jclass); jdouble J(benchDfmaTflops)(JNIEnv*, jclass); jdouble J(benchCopyGbs)(JNIEnv*, jclass, jlong);
+jlongArray J(commInfo)(JNIEnv*, jclass); jbyteArray J(commPeerHandle)(JNIEnv*, jclass); void J(commPeerOpen)(JNIEnv*, jclass, jbyteArray);
+jdouble J(benchDfmaTflops)(JNIEnv*, jclass); jdouble J(benchCopyGbs)(JNIEnv*, jclass, jlong);
 
 static int failures = 0, calls = 0;
 #define EXPECT(cond, what) do { if (!(cond)) { printf("FAIL %s (line %d), pending exception '%s' %s\n", what, __LINE__, pending, pendingMessage); failures++; } } while (0)
@@ -136,6 +137,7 @@ static void noDevice(void) {
 	THROWS(RTE, J(regressionPredictFit)(env, NULL, longs(2, hs), doubles(2, sq), 3));
 	THROWS(RTE, J(regressionConditionalExpectation)(env, NULL, longs(2, hs), doubles(2, sq), 3, 0, 0, NULL, NULL));
 	THROWS(RTE, J(commUniqueId)(env, NULL)); THROWS(RTE, J(commInit)(env, NULL, fNewByteArray(env, 128), 0, 2));
+	THROWS(RTE, J(commPeerHandle)(env, NULL)); THROWS(RTE, J(commPeerOpen)(env, NULL, fNewByteArray(env, 128)));
 	THROWS(RTE, J(benchDfmaTflops)(env, NULL)); THROWS(RTE, J(benchCopyGbs)(env, NULL, 1 << 20));
 	jint init = 1; OK(init = J(isInitialized)(env, NULL)); EXPECT(init == 0, "not initialised without a device");
 	OK(J(shutdown)(env, NULL));
@@ -147,6 +149,8 @@ static jlong* L(jlongArray a) { return (jlong*)a->data; }
 static void onGpu(void) {
 	OK(J(init)(env, NULL, 0));
 	jint init = 0; OK(init = J(isInitialized)(env, NULL)); EXPECT(init == 1, "initialised");
+	THROWS(UOE, J(commPeerHandle)(env, NULL));                      /* peer exchange needs a communicator of 2..8 ranks */
+	THROWS(IAE, J(commPeerOpen)(env, NULL, fNewByteArray(env, 128)));
 	jstring name; OK(name = J(deviceName)(env, NULL)); printf("device: %s\n", name ? name->text : "?");
 	const double v[4] = { 1, 2, 3, 4 }, w[4] = { 0.5, 0.5, 2, 2 };
 	jlong x = 0, y = 0, z = 0; OK(x = J(upload)(env, NULL, doubles(4, v))); OK(y = J(upload)(env, NULL, doubles(4, w)));
