@@ -146,7 +146,8 @@ int fmb_comm_shutdown(void) {
 		m.gatherBuf = m.ncclGatherBuf;
 		m.peer = false;
 	}
-	if (m.peerBase) { cudaFree(m.peerBase); m.peerBase = nullptr; }
+	// (the exported buffer itself is NOT freed here: another rank may still hold its mapping - freeing before every importer has closed is
+	// undefined; 64 KB, reused by a later fmb_comm_peer_handle, released with the process)
 	if (m.peerErrHost) { cudaFreeHost((void*)m.peerErrHost); m.peerErrHost = nullptr; m.peerErrDev = nullptr; }
 	cudaFree(m.sendBuf); cudaFree(m.gatherBuf);
 	m.sendBuf = m.gatherBuf = m.ncclGatherBuf = nullptr; m.comm = nullptr; m.active = false; m.rank = 0; m.world = 1;
