@@ -163,9 +163,14 @@ int fmb_comm_peer_handle(unsigned char* handle, int len) {
 	Comm& m = c.comm;
 	std::lock_guard<std::mutex> lk(c.scratchMu);
 	if (!m.active || m.world < 2 || m.world > 8) { setError("comm_peer_handle: needs a communicator of 2..8 ranks (fmb_comm_init first)"); return FMB_EUNSUPPORTED; }
-	if (!m.peerBase) {
+	if (m.peer) { setError("comm_peer_handle: the peer exchange is already open"); return FMB_EINVAL; }
+	if (m.peerBase) {
+		FMB_CUDA(cudaMemset(m.peerBase, 0, PEER_ALLOC_BYTES));      // a buffer kept from an earlier communicator: its flags are stale
+	} else {
 		FMB_CUDA(cudaMalloc((void**)&m.peerBase, PEER_ALLOC_BYTES));
 		FMB_CUDA(cudaMemset(m.peerBase, 0, PEER_ALLOC_BYTES));
+	}
+	if (!m.peerErrHost) {
 		unsigned int* eh = nullptr;
 		FMB_CUDA(cudaHostAlloc((void**)&eh, sizeof(unsigned int), cudaHostAllocMapped));
 		*eh = 0;
