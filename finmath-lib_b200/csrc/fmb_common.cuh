@@ -129,6 +129,7 @@ struct Context {
 	double* hostResult = nullptr;      // host address, COMM_MAX_DOUBLES doubles
 	double* hostResultDev = nullptr;   // the same memory as the device sees it
 	unsigned int* ticket = nullptr;    // device counter of the last-block finalisation (zero between launches)
+	unsigned int* ticketMany = nullptr; // 65 counters of fmb_rv_reduce_many (one per vector + vectors done)
 	Comm comm;
 };
 

@@ -228,8 +228,9 @@ int fmb_init(int device) {
 	c.smCount = prop.multiProcessorCount;
 	FMB_CUDA(cudaHostAlloc((void**)&c.hostResult, COMM_MAX_DOUBLES * sizeof(double), cudaHostAllocMapped));
 	FMB_CUDA(cudaHostGetDevicePointer((void**)&c.hostResultDev, c.hostResult, 0));
-	FMB_CUDA(cudaMalloc((void**)&c.ticket, 64));
-	FMB_CUDA(cudaMemsetAsync(c.ticket, 0, 64, c.stream));
+	FMB_CUDA(cudaMalloc((void**)&c.ticket, 64 + 66 * sizeof(unsigned int)));
+	FMB_CUDA(cudaMemsetAsync(c.ticket, 0, 64 + 66 * sizeof(unsigned int), c.stream));
+	c.ticketMany = c.ticket + 16;
 	c.initialized = true;
 	return ensureScratch(1 << 16, 1 << 20);
 }
@@ -258,7 +259,7 @@ int fmb_shutdown(void) {
 	if (c.scratch) cudaFree(c.scratch);
 	if (c.hostResult) cudaFreeHost(c.hostResult);
 	if (c.ticket) cudaFree(c.ticket);
-	c.hostResult = c.hostResultDev = nullptr; c.ticket = nullptr;
+	c.hostResult = c.hostResultDev = nullptr; c.ticket = nullptr; c.ticketMany = nullptr;
 	c.pinned = c.scratch = nullptr; c.pinnedBytes = c.scratchBytes = 0;
 	cudaEventDestroy(c.ev0); cudaEventDestroy(c.ev1);
 	cudaStreamDestroy(c.stream);

@@ -64,15 +64,16 @@ static const int RED_THREADS = 256;
 // memory when the caller is waiting for a double, to the communicator's send buffer when shards are exchanged, or it goes straight on
 // to the regression solve.  atomicInc wraps the ticket back to zero, ready for the next launch (launches of these kernels are
 // serialised on the compute stream).
-__device__ __forceinline__ bool drawLastTicket(unsigned int* ticket) {
+__device__ __forceinline__ bool drawLastTicketOf(unsigned int* ticket, unsigned int total) {
 	__shared__ bool isLast;
 	__threadfence();
 	__syncthreads();
-	if (threadIdx.x == 0) isLast = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+	if (threadIdx.x == 0) isLast = (atomicInc(ticket, total - 1) == total - 1);
 	__syncthreads();
 	if (isLast) __threadfence();
 	return isLast;
 }
+__device__ __forceinline__ bool drawLastTicket(unsigned int* ticket) { return drawLastTicketOf(ticket, gridDim.x); }
 
 template <int OP> __device__ __forceinline__ double addend(double x, double w, double a) {
 	switch (OP) {
@@ -223,6 +224,55 @@ __global__ void mergeShardsKernel(const double* __restrict__ gathered, int world
 		}
 		out[0] = any ? t : NAN;
 		out[1] = any ? 1.0 : 0.0;
+	}
+}
+
+// ---- the same sum over MANY vectors in one launch ------------------------------------------------------------------------------
+// The LMM's numeraire adjustment needs E[N(0) / N(T_i)] for every tenor date (LIBORMarketModelFromCovarianceModel.java:859-876 evaluates
+// them one getAverage at a time: one kernel, one host synchronisation and - sharded - one rendezvous of all ranks per date).  Here the
+// sums of up to 64 vectors are ONE launch: blockIdx.y = vector, per-vector last-block merge exactly as sumKernel, and the CTA that
+// completes the LAST vector exchanges all results with the other ranks at once (peer memory), merges the shards and writes them out.
+static const int REDUCE_MANY_MAX = 64;
+struct ManyArgs { const double* x[REDUCE_MANY_MAX]; };
+template <int OP> __device__ __forceinline__ double addendMany(double x, double a) { return OP == FMB_RM_SUM ? x : (1.0 / x) * a; }
+
+template <int OP> __global__ void __launch_bounds__(RED_THREADS) sumManyKernel(const __grid_constant__ ManyArgs v, int count, double a, uint64_t n,
+		double* __restrict__ partials /* [count][gridDim.x][2] */, unsigned int* tickets /* [count] per vector, [count] = vectors done */,
+		double* __restrict__ results /* [count][2], device */, double* __restrict__ out /* [count][2] */, const PeerArgs px) {
+	const int vi = blockIdx.y;
+	const double* __restrict__ x = v.x[vi];
+	dd acc0 = {0.0, 0.0}, acc1 = {0.0, 0.0};
+	const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
+	uint64_t i = blockIdx.x * (uint64_t)RED_THREADS + threadIdx.x;
+	for (; i + stride < n; i += 2 * stride) {
+		const double x0 = x[i], x1 = x[i + stride];
+		ddAdd(acc0, addendMany<OP>(x0, a));
+		ddAdd(acc1, addendMany<OP>(x1, a));
+	}
+	if (i < n) ddAdd(acc0, addendMany<OP>(x[i], a));
+	ddMerge(acc0, acc1);
+	dd t = blockReduceDd(acc0);
+	if (gridDim.x > 1) {
+		if (threadIdx.x == 0) { partials[((size_t)vi * gridDim.x + blockIdx.x) * 2] = t.hi; partials[((size_t)vi * gridDim.x + blockIdx.x) * 2 + 1] = t.lo; }
+		if (!drawLastTicketOf(tickets + vi, gridDim.x)) return;
+		dd m = {0.0, 0.0};
+		const double* row = partials + (size_t)vi * gridDim.x * 2;
+		for (unsigned int b = threadIdx.x; b < gridDim.x; b += RED_THREADS) { const dd o = { __ldcg(row + 2 * b), __ldcg(row + 2 * b + 1) }; ddMerge(m, o); }
+		t = blockReduceDd(m);
+	}
+	if (threadIdx.x == 0) { results[2 * vi] = t.hi; results[2 * vi + 1] = t.lo; }
+	if (!drawLastTicketOf(tickets + count, gridDim.y)) return;
+	// every vector's local sum is in results: exchange (sharded), merge in rank order, write
+	if (px.world > 1) {
+		peerExchangeBlock(px, results, 2 * count);
+		const double* g = peerGathered(px);
+		for (int m = threadIdx.x; m < count; m += RED_THREADS) {
+			dd s = { __ldcg(g + 2 * m), __ldcg(g + 2 * m + 1) };
+			for (int r = 1; r < px.world; r++) { const dd o = { __ldcg(g + (size_t)r * 2 * count + 2 * m), __ldcg(g + (size_t)r * 2 * count + 2 * m + 1) }; ddMerge(s, o); }
+			out[2 * m] = s.hi; out[2 * m + 1] = s.lo;
+		}
+	} else {
+		for (int m = threadIdx.x; m < 2 * count; m += RED_THREADS) out[m] = __ldcg(results + m);
 	}
 }
 
@@ -720,6 +770,61 @@ int fmb_rv_reduce(int op, fmb_handle x, fmb_handle w, double a, double* out2) {
 	FMB_CUDA(cudaStreamSynchronize(c.stream));
 	out2[0] = c.hostResult[0];
 	out2[1] = isMinMax ? 0.0 : c.hostResult[1];
+	return FMB_OK;
+}
+
+// sums of `count` (<= 64) vectors of one length in one launch: out2[2i], out2[2i+1] = (hi, lo) of sum_p f(x_i[p]); with a communicator over
+// all shards.  FMB_RM_SUM: f(x) = x; FMB_RM_SUM_INVERT_MULT: f(x) = (1 / x) * a  (RandomVariable.invert().mult(a), summed).
+int fmb_rv_reduce_many(int op, int count, const fmb_handle* x, double a, double* out2) {
+	FMB_TRY(requireInit());
+	PinScope pins;
+	if (!x || !out2 || count < 1 || count > REDUCE_MANY_MAX || (op != FMB_RM_SUM && op != FMB_RM_SUM_INVERT_MULT)) { setError("reduce_many: bad argument"); return FMB_EINVAL; }
+	Context& c = ctx();
+	ManyArgs v;
+	uint64_t n = 0;
+	for (int i = 0; i < REDUCE_MANY_MAX; i++) v.x[i] = nullptr;
+	for (int i = 0; i < count; i++) {
+		Vec* vx;
+		if (x[i] == 0) { setError("reduce_many: vector %d is not a device vector", i); return FMB_EINVAL; }
+		FMB_TRY(lookup(x[i], &vx));
+		if (i > 0 && vx->n != n) { setError("operand sizes differ (%llu vs %llu)", (unsigned long long)vx->n, (unsigned long long)n); return FMB_EINVAL; }
+		n = vx->n;
+		v.x[i] = vx->ptr;
+	}
+	for (int i = 0; i < 2 * count; i++) out2[i] = 0.0;
+	if (n == 0 && !c.comm.active) return FMB_OK;
+	// CTAs per vector: about eight elements per thread at least, and about eight CTAs per SM over all vectors (a few long vectors get
+	// many CTAs each, many vectors few)
+	const uint64_t gxCap = std::max<uint64_t>(32, ((uint64_t)c.smCount * 8 + count - 1) / count);
+	const int gx = (int)std::max<uint64_t>(1, std::min<uint64_t>(gxCap, (n + (uint64_t)RED_THREADS * 8 - 1) / ((uint64_t)RED_THREADS * 8)));
+	std::lock_guard<std::mutex> lk(c.scratchMu);
+	FMB_TRY(ensureScratch(0, ((size_t)count * gx * 2 + 2 * (size_t)count) * sizeof(double)));
+	double* dpart = (double*)c.scratch;
+	double* results = dpart + (size_t)count * gx * 2;
+	const bool fused = c.comm.active && c.comm.peer && n > 0;
+	PeerArgs px;
+	if (fused) {
+		if (*c.comm.peerErrHost) { setError("peer exchange: a rank did not arrive (timed out)"); return FMB_ECUDA; }
+		peerArgsNext(px);
+	}
+	double* dst = (c.comm.active && !fused) ? c.comm.sendBuf : c.hostResultDev;
+	if (n == 0) {
+		FMB_CUDA(cudaMemsetAsync(dst, 0, 2 * (size_t)count * sizeof(double), c.stream));
+	} else {
+		const dim3 grid(gx, count);
+		if (op == FMB_RM_SUM) sumManyKernel<FMB_RM_SUM><<<grid, RED_THREADS, 0, c.stream>>>(v, count, a, n, dpart, c.ticketMany, results, dst, px);
+		else sumManyKernel<FMB_RM_SUM_INVERT_MULT><<<grid, RED_THREADS, 0, c.stream>>>(v, count, a, n, dpart, c.ticketMany, results, dst, px);
+		countLaunch();
+		FMB_CUDA(cudaGetLastError());
+	}
+	if (c.comm.active && !fused) {
+		FMB_TRY(commAllGather(2 * count));
+		mergeShardsKernel<<<1, REDUCE_MANY_MAX, 0, c.stream>>>(c.comm.gatherBuf, c.comm.world, 2 * count, 0, c.hostResultDev);
+		countLaunch();
+		FMB_CUDA(cudaGetLastError());
+	}
+	FMB_CUDA(cudaStreamSynchronize(c.stream));
+	for (int i = 0; i < 2 * count; i++) out2[i] = c.hostResult[i];
 	return FMB_OK;
 }
 

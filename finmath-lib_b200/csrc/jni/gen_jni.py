@@ -52,6 +52,7 @@ TABLE = [
     ("evalChain", "fmb_rv_eval_chain", "handle", [("B", "code"), ("i", "startLeaf"), ("H", "leaves"), ("D", "scalars")],
      "code_n / 8, (const unsigned char*)code_p, startLeaf, (const fmb_handle*)leaves_p, leaves_n, scalars_p, scalars_n, OUT"),
     ("reduce", "fmb_rv_reduce", "doubles:2", [("i", "op"), ("h", "x"), ("h", "w"), ("d", "a")], "op, (fmb_handle)x, (fmb_handle)w, a, OUT"),
+    ("reduceMany", "fmb_rv_reduce_many", "doubles:2 * x_n", [("i", "op"), ("H", "x"), ("d", "a")], "op, x_n, (const fmb_handle*)x_p, a, OUT"),
     ("select", "fmb_rv_select", "double", [("h", "x"), ("l", "rank")], "(fmb_handle)x, (uint64_t)rank, OUT"),
     ("countLessOrEqual", "fmb_rv_count_le", "custom", [("h", "x"), ("D", "points")], ""),
     ("rangeSum", "fmb_rv_range_sum", "doubles:4", [("h", "x"), ("d", "lo"), ("d", "hi")], "(fmb_handle)x, lo, hi, OUT"),

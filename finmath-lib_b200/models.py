@@ -320,6 +320,7 @@ class LIBORMarketModelFromCovarianceModel:
         self._tables = factorLoadingTable
         self._numeraires, self._numeraireDiscountFactors, self._numerairesProcess = {}, {}, None
         self._numerairesAdjusted = {}
+        self._zeroBondAverages, self._zeroBondRequests = None, set()
         self._initialState = None
 
     @classmethod
@@ -542,6 +543,7 @@ class LIBORMarketModelFromCovarianceModel:
             self._numeraires.clear()
             self._numeraireDiscountFactors.clear()
             self._numerairesAdjusted.clear()
+            self._zeroBondAverages = None
             self._numerairesProcess = weakref.ref(process)
 
     def _numeraire_unadjusted_at(self, process, li):                                   # :1017-1074
@@ -618,10 +620,60 @@ class LIBORMarketModelFromCovarianceModel:
             if cached is not None:
                 return cached
             dz = self._defaultable_zero_bond_at(process, time)
-            nonDefaultableZeroBond = n.invert().mult(self._numeraire_unadjusted(process, 0.0)).getAverage()
+            nonDefaultableZeroBond = self._zero_bond_averages(process, time)
+            if nonDefaultableZeroBond is None:
+                nonDefaultableZeroBond = n.invert().mult(self._numeraire_unadjusted(process, 0.0)).getAverage()
             n = n.mult(nonDefaultableZeroBond).div(dz)
             self._numerairesAdjusted[time] = n
         return n
+
+    def _zero_bond_averages(self, process, time):
+        """E[N(0) / N(T_k)] for ALL tenor dates up to `time` that have not been averaged yet, in one go.  The reference evaluates them one
+        getAverage at a time (one kernel, one host synchronisation and - sharded - one rendezvous of all ranks per date: 20 of the 43 in a
+        Bermudan valuation); under the spot measure N(T_k) is a by-product of N(T_i) for every k < i (the accrual chain), so
+        fmb_rv_reduce_many sums them all in one launch the first time the latest date is asked for (a backward induction asks for it
+        first).  Same operations per path (invert, mult by the deterministic N(0), double-double sum, division by the number of paths).
+        Only from the third distinct date on: a product that needs one or two numeraires (a swaption: the exercise date) keeps the
+        reference's route, where the accrual chain up to that date is a single fused evaluation and nothing else is averaged.
+        Returns the average for `time`, or None where this route does not apply (terminal measure, dates between tenor points, other
+        RandomVariable types): the caller then takes the reference's."""
+        self._ensure_cache(process)
+        if self._zeroBondAverages is None:
+            self._zeroBondAverages, self._zeroBondRequests = {}, set()
+        known = self._zeroBondAverages.get(time)
+        li = self.getLiborPeriodIndex(time)
+        if known is not None or li < 0 or self.measure != self.SPOT:
+            return known
+        self._zeroBondRequests.add(time)
+        if len(self._zeroBondRequests) < 3:
+            return None
+        li = max(li, max(self.getLiborPeriodIndex(t) for t in self._zeroBondRequests))
+        n0 = self._numeraire_unadjusted(process, 0.0)
+        if not n0.isDeterministic():
+            return None
+        dates, vectors = [], []
+        for k in range(li + 1):
+            date = self.tenor.getTime(k)
+            if date in self._zeroBondAverages or date in self._numerairesAdjusted:
+                continue
+            n = self._numeraire_unadjusted_at(process, k)
+            if type(n) is not RandomVariableCuda:
+                return None
+            if n.dv is None:                                  # deterministic (T_0): host scalars, as the type does it
+                self._zeroBondAverages[date] = n.invert().mult(n0).getAverage()
+                continue
+            dates.append(date)
+            vectors.append(n)
+        if vectors:
+            if not all(v.shard is vectors[0].shard and v.dv.n == vectors[0].dv.n for v in vectors):
+                return None
+            shard, size = vectors[0].shard, vectors[0].size()
+            for k in range(0, len(vectors), 64):
+                hi, lo = nv.reduce_many(nv.RM_SUM_INVERT_MULT, [v.dv for v in vectors[k:k + 64]], n0.doubleValue())
+                hi, lo = shard.sum_dd_many(hi, lo)
+                for date, h, l in zip(dates[k:k + 64], hi, lo):
+                    self._zeroBondAverages[date] = float("nan") if size == 0 else float(h + l) / size
+        return self._zeroBondAverages.get(time)
 
 
 class LIBORMonteCarloSimulationFromLIBORModel:

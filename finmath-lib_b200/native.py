@@ -75,6 +75,7 @@ PROTOTYPES = {
     "fmb_rv_accrue_chain": [C.c_int, c_hp, c_dp, C.c_double, c_hp],
     "fmb_rv_eval_chain": [C.c_int, C.c_char_p, C.c_int, c_hp, C.c_int, c_dp, C.c_int, c_hp],
     "fmb_rv_reduce": [C.c_int, C.c_uint64, C.c_uint64, C.c_double, c_dp],
+    "fmb_rv_reduce_many": [C.c_int, C.c_int, c_hp, C.c_double, c_dp],
     "fmb_rv_select": [C.c_uint64, C.c_uint64, c_dp],
     "fmb_rv_count_le": [C.c_uint64, c_dp, C.c_int, c_hp],
     "fmb_rv_range_sum": [C.c_uint64, C.c_double, C.c_double, c_dp],
@@ -281,6 +282,17 @@ def reduce(op, x, w=None, a=0.0):
     out = (C.c_double * 2)()
     check(load().fmb_rv_reduce(op, x.h, w.h if w is not None else 0, float(a), out))
     return out[0], out[1]
+
+
+RM_SUM, RM_SUM_INVERT_MULT = 0, 1
+
+
+def reduce_many(op, vectors, a=0.0):
+    """(hi, lo) arrays of sum_p f(x_i[p]) for a list of DeviceVector / LazyVector of one length: one launch, one synchronisation."""
+    hs = np.array([v.h for v in vectors], dtype=np.uint64)
+    out = np.zeros(2 * len(vectors))
+    check(load().fmb_rv_reduce_many(op, len(vectors), hptr(hs), float(a), dptr(out)))
+    return out[0::2].copy(), out[1::2].copy()
 
 
 def launch_count():

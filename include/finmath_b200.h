@@ -135,6 +135,14 @@ enum {
 	FMB_R_MAX = 5
 };
 int fmb_rv_reduce(int op, fmb_handle x, fmb_handle w, double a, double* out2);
+/* The same sums for up to 64 vectors of one length in ONE launch, one synchronisation and (sharded) one exchange: out2[2i], out2[2i+1] =
+ * (hi, lo) of sum_p f(x_i[p]).  Replaces the sequence of getAverage calls behind the LIBOR market model's numeraire adjustment
+ * (LIBORMarketModelFromCovarianceModel.java:859-876: E[N(0) / N(T_i)] for every tenor date). */
+enum {
+	FMB_RM_SUM = 0,               /* f(x) = x */
+	FMB_RM_SUM_INVERT_MULT = 1    /* f(x) = (1 / x) * a: RandomVariable.invert().mult(a) */
+};
+int fmb_rv_reduce_many(int op, int count, const fmb_handle* x, double a, double* out2);
 /* Order statistics (getQuantile / getQuantileExpectation / getHistogram, :445-575) without a sort and without moving path data between
  * GPUs; with a communicator all three cover the logical vector over all shards (only a 256-bin histogram, a few counts or partial sums
  * are exchanged).  Order = Arrays.sort(double[]): -0.0 < +0.0, NaN above everything. */

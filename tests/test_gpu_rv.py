@@ -342,3 +342,32 @@ def test_deferred_operations_report_size_mismatch_at_once(gpu):
                 a.add(1.0).mult(b)
         finally:
             gpu.native.set_lazy(True, min_n=keep)
+
+
+def test_sums_of_many_vectors_in_one_launch(gpu):
+    """fmb_rv_reduce_many (the batched numeraire adjustment of the LIBOR market model): the double-double sums of up to 64 vectors from one
+    launch equal the one-at-a-time reductions (the grids differ, so the merge order differs: a last-bit tolerance), for plain sums and for
+    sum((1 / x) * a) = invert().mult(a) summed, also on deferred chains, and one launch is what it takes."""
+    nv = gpu.native
+    RV = gpu.RandomVariableCuda
+    rng = np.random.default_rng(99)
+    for n in (1, 255, 4097, 300_001):
+        xs = [rng.uniform(0.5, 2.0, n) for _ in range(41)]
+        vs = [RV(0.0, x) for x in xs]
+        vs[3] = vs[3].mult(2.0).add(1.0)                     # a recorded chain among the operands
+        xs[3] = xs[3] * 2.0 + 1.0
+        before = nv.launch_count()
+        hi, lo = nv.reduce_many(nv.RM_SUM, [v.dv for v in vs])
+        assert nv.launch_count() - before <= 2               # (the chain, then ONE launch for all 41 sums)
+        for v, h, l, x in zip(vs, hi, lo, xs):
+            single = v.getAverage() * n
+            assert abs((h + l) - single) <= 2e-16 * abs(single)
+            assert abs((h + l) - float(np.sum(x.astype(np.longdouble)))) <= 1e-15 * abs(single)
+        hi, lo = nv.reduce_many(nv.RM_SUM_INVERT_MULT, [v.dv for v in vs], 1.25)
+        for v, h, l in zip(vs, hi, lo):
+            single = v.invert().mult(1.25).getAverage() * n
+            assert abs((h + l) - single) <= 2e-16 * abs(single)
+    with pytest.raises(ValueError):
+        nv.reduce_many(nv.RM_SUM, [RV(0.0, np.ones(3)).dv, RV(0.0, np.ones(4)).dv])
+    with pytest.raises(ValueError):
+        nv.reduce_many(nv.RM_SUM, [RV(0.0, np.ones(3)).dv] * 65)
