@@ -287,6 +287,24 @@ __global__ void __launch_bounds__(256) accrueChainKernel(AccrueChainArgs a, int 
 	}
 }
 
+// every prefix of the accrual chain in one pass: out_k = start * (1 + r_0 d_0) * ... * (1 + r_k d_k), k < n (the spot-measure numeraire at every
+// tenor date, LIBORMarketModelFromCovarianceModel.java:1050-1069: each accrue() there is one more array pass)
+struct AccruePrefixArgs {
+	const double* rate[64];
+	double delta[64];
+};
+__global__ void __launch_bounds__(256) accruePrefixKernel(const __grid_constant__ AccruePrefixArgs a, int n, double start, const double* __restrict__ accIn,
+		double* __restrict__ out /* [n][len] */, uint64_t len) {
+	const uint64_t stride = (uint64_t)gridDim.x * 256;
+	for (uint64_t i = blockIdx.x * (uint64_t)256 + threadIdx.x; i < len; i += stride) {
+		double acc = accIn ? accIn[i] : start;
+		for (int k = 0; k < n; k++) {
+			acc = acc * (1 + a.rate[k][i] * a.delta[k]);
+			out[(size_t)k * len + i] = acc;
+		}
+	}
+}
+
 } // namespace fmb
 
 using namespace fmb;
@@ -469,6 +487,41 @@ int fmb_rv_accrue_chain(int n, const fmb_handle* rates, const double* period_len
 		accIn = dst;
 	}
 	FMB_CUDA(cudaGetLastError());
+	return FMB_OK;
+}
+
+int fmb_rv_accrue_prefix(int n, double start, const fmb_handle* rates, const double* period_lengths, fmb_handle* out) {
+	FMB_TRY(requireInit());
+	PinScope pins;
+	if (n < 1 || !rates || !period_lengths || !out) { setError("accrue_prefix: bad argument"); return FMB_EINVAL; }
+	uint64_t len = 0;
+	std::vector<const double*> ptr(n);
+	for (int k = 0; k < n; k++) {
+		Vec* v;
+		if (rates[k] == 0) { setError("accrue_prefix: rate %d is not a device vector", k); return FMB_EINVAL; }
+		FMB_TRY(lookup(rates[k], &v));
+		if (k > 0 && v->n != len) { setError("operand sizes differ (%llu vs %llu)", (unsigned long long)v->n, (unsigned long long)len); return FMB_EINVAL; }
+		len = v->n;
+		ptr[k] = v->ptr;
+	}
+	Slab* slab = nullptr;
+	FMB_TRY(newSlab(std::max<size_t>(8, (size_t)n * len * sizeof(double)), &slab));
+	double* base = (double*)slab->base;
+	if (len > 0) {
+		const int grid = ewGrid(len);
+		const double* accIn = nullptr;
+		for (int k0 = 0; k0 < n; k0 += 64) {                       // (more than 64 periods: the running product is carried by the last output)
+			AccruePrefixArgs a;
+			const int m = std::min(64, n - k0);
+			for (int k = 0; k < 64; k++) { a.rate[k] = k < m ? ptr[k0 + k] : nullptr; a.delta[k] = k < m ? period_lengths[k0 + k] : 0.0; }
+			accruePrefixKernel<<<grid, 256, 0, ctx().stream>>>(a, m, start, accIn, base + (size_t)k0 * len, len);
+			countLaunch();
+			accIn = base + (size_t)(k0 + m - 1) * len;
+		}
+		const cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) { poolFree(slab->base, slab->bytes); delete slab; setError("accrue_prefix: %s", cudaGetErrorString(e)); return FMB_ECUDA; }
+	}
+	for (int k = 0; k < n; k++) out[k] = newView(slab, base + (size_t)k * len, len);
 	return FMB_OK;
 }
 

@@ -49,6 +49,8 @@ TABLE = [
      "op, (fmb_handle)x, sx, (fmb_handle)y, sy, (fmb_handle)z, sz, a, OUT"),
     ("accrueChain", "fmb_rv_accrue_chain", "handle", [("H", "rates"), ("D", "periodLengths"), ("d", "divisor")],
      "rates_n, (const fmb_handle*)rates_p, periodLengths_p, divisor, OUT"),
+    ("accruePrefix", "fmb_rv_accrue_prefix", "handles:rates_n", [("d", "start"), ("H", "rates"), ("D", "periodLengths")],
+     "rates_n, start, (const fmb_handle*)rates_p, periodLengths_p, OUT"),
     ("evalChain", "fmb_rv_eval_chain", "handle", [("B", "code"), ("i", "startLeaf"), ("H", "leaves"), ("D", "scalars")],
      "code_n / 8, (const unsigned char*)code_p, startLeaf, (const fmb_handle*)leaves_p, leaves_n, scalars_p, scalars_n, OUT"),
     ("reduce", "fmb_rv_reduce", "doubles:2", [("i", "op"), ("h", "x"), ("h", "w"), ("d", "a")], "op, (fmb_handle)x, (fmb_handle)w, a, OUT"),

@@ -549,6 +549,9 @@ class LIBORMarketModelFromCovarianceModel:
     def _numeraire_unadjusted_at(self, process, li):                                   # :1017-1074
         self._ensure_cache(process)
         n = self._numeraires.get(li)
+        if n is None and self.measure == self.SPOT and li >= 3:
+            self._numeraires_by_prefix_accrual(process, li)  # N(T_1) .. N(T_li) from one kernel where possible
+            n = self._numeraires.get(li)
         if n is None:
             if self.measure == self.TERMINAL:
                 ti = process.getTimeIndex(self.tenor.getTime(li))
@@ -626,6 +629,49 @@ class LIBORMarketModelFromCovarianceModel:
             n = n.mult(nonDefaultableZeroBond).div(dz)
             self._numerairesAdjusted[time] = n
         return n
+
+    def _numeraires_by_prefix_accrual(self, process, li):
+        """The unadjusted spot-measure numeraires N(T_1) .. N(T_li) that are not cached yet, all from ONE kernel (fmb_rv_accrue_prefix) instead
+        of one accrue() pass per date; the same operations in the same order as _numeraire_unadjusted_at (bit-identical).  Does nothing
+        where that is not possible (other RandomVariable types, deterministic rates): the per-date route then fills the cache."""
+        import ctypes as C
+        self._ensure_cache(process)
+        first = 1
+        while first <= li and first in self._numeraires:
+            first += 1
+        if first > li:
+            return
+        start = self._numeraires.get(first - 1) if first > 1 else self._numeraire_unadjusted_at(process, 0)
+        if start is None or not start.isDeterministic():
+            return                                           # (continuing from a stochastic N would need its vector as the carry: the per-date route)
+        while first <= li:                                   # the head of the chain is deterministic (rates fixed at time 0): host scalars
+            ti = process.getTimeIndex(self.tenor.getTime(first - 1))
+            L = self.getLIBOR(process, ti if ti >= 0 else -ti - 1, first - 1)
+            if not L.isDeterministic():
+                break
+            start = start.accrue(L, self.tenor.getTimeStep(first - 1))
+            self._numeraires[first] = start
+            first += 1
+        if li - first < 2:
+            return
+        rates, dts, times = [], [], []
+        t = start.getFiltrationTime()
+        for k in range(first, li + 1):
+            ti = process.getTimeIndex(self.tenor.getTime(k - 1))
+            if ti < 0:
+                ti = -ti - 1
+            L = self.getLIBOR(process, ti, k - 1)
+            if type(L) is not RandomVariableCuda or L.dv is None or (rates and (L.dv.n != rates[0].dv.n or L.shard is not rates[0].shard)):
+                return
+            rates.append(L)
+            dts.append(self.tenor.getTimeStep(k - 1))
+            t = max(t, L.time)
+            times.append(t)
+        hs = np.array([L.dv.h for L in rates], dtype=np.uint64)
+        out = np.zeros(len(rates), dtype=np.uint64)
+        nv.check(nv.load().fmb_rv_accrue_prefix(len(rates), start.doubleValue(), nv.hptr(hs), nv.dptr(np.array(dts, dtype=np.float64)), nv.hptr(out)))
+        for j, k in enumerate(range(first, li + 1)):
+            self._numeraires[k] = RandomVariableCuda(times[j], None, rates[0].shard, _dv=nv.DeviceVector(out[j], rates[0].dv.n), _n=rates[0].nGlobal)
 
     def _zero_bond_averages(self, process, time):
         """E[N(0) / N(T_k)] for ALL tenor dates up to `time` that have not been averaged yet, in one go.  The reference evaluates them one

@@ -73,6 +73,7 @@ PROTOTYPES = {
     "fmb_rv_binary": [C.c_int, C.c_uint64, C.c_double, C.c_uint64, C.c_double, c_hp],
     "fmb_rv_ternary": [C.c_int, C.c_uint64, C.c_double, C.c_uint64, C.c_double, C.c_uint64, C.c_double, C.c_double, c_hp],
     "fmb_rv_accrue_chain": [C.c_int, c_hp, c_dp, C.c_double, c_hp],
+    "fmb_rv_accrue_prefix": [C.c_int, C.c_double, c_hp, c_dp, c_hp],
     "fmb_rv_eval_chain": [C.c_int, C.c_char_p, C.c_int, c_hp, C.c_int, c_dp, C.c_int, c_hp],
     "fmb_rv_reduce": [C.c_int, C.c_uint64, C.c_uint64, C.c_double, c_dp],
     "fmb_rv_reduce_many": [C.c_int, C.c_int, c_hp, C.c_double, c_dp],

@@ -107,6 +107,10 @@ int fmb_rv_ternary(int op, fmb_handle x, double sx, fmb_handle y, double sy, fmb
  * which the reference builds with one accrue() pass per period.  Same operations and order (r_0.mult(d_0).add(1.0), accrue per further
  * period, sub(1.0).div(divisor)): bit-identical to the op-by-op evaluation. */
 int fmb_rv_accrue_chain(int n, const fmb_handle* rates, const double* period_lengths, double divisor, fmb_handle* out);
+/* Every prefix of an accrual chain in ONE pass: out[k] = start * (1 + r_0 d_0) * ... * (1 + r_k d_k), k < n - the spot-measure numeraire at
+ * every tenor date (LIBORMarketModelFromCovarianceModel.java:1050-1069 builds it with one accrue() pass per date).  Same operations and
+ * order as the chain of accrue() calls: bit-identical. */
+int fmb_rv_accrue_prefix(int n, double start, const fmb_handle* rates, const double* period_lengths, fmb_handle* out);
 
 /* A chain of element-wise operations evaluated in ONE pass over the vectors (deferred evaluation in the host binding: a result that
  * is only consumed by the next operation never becomes a vector in HBM).  acc = leaves[start_leaf][i]; instruction k replaces acc by
