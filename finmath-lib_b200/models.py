@@ -320,7 +320,7 @@ class LIBORMarketModelFromCovarianceModel:
         self._tables = factorLoadingTable
         self._numeraires, self._numeraireDiscountFactors, self._numerairesProcess = {}, {}, None
         self._numerairesAdjusted = {}
-        self._zeroBondAverages, self._zeroBondRequests = None, set()
+        self._zeroBondAverages, self._zeroBondRequests, self._zeroBondLastIndex = None, set(), None
         self._initialState = None
 
     @classmethod
@@ -679,19 +679,24 @@ class LIBORMarketModelFromCovarianceModel:
         Bermudan valuation); under the spot measure N(T_k) is a by-product of N(T_i) for every k < i (the accrual chain), so
         fmb_rv_reduce_many sums them all in one launch the first time the latest date is asked for (a backward induction asks for it
         first).  Same operations per path (invert, mult by the deterministic N(0), double-double sum, division by the number of paths).
-        Only from the third distinct date on: a product that needs one or two numeraires (a swaption: the exercise date) keeps the
-        reference's route, where the accrual chain up to that date is a single fused evaluation and nothing else is averaged.
+        Only from the third distinct date on and only for consecutive tenor dates: a product that needs one or two numeraires (a swaption:
+        the exercise date) keeps the reference's route, where the accrual chain up to that date is a single fused evaluation and nothing else
+        is averaged.
         Returns the average for `time`, or None where this route does not apply (terminal measure, dates between tenor points, other
         RandomVariable types): the caller then takes the reference's."""
         self._ensure_cache(process)
         if self._zeroBondAverages is None:
-            self._zeroBondAverages, self._zeroBondRequests = {}, set()
+            self._zeroBondAverages, self._zeroBondRequests, self._zeroBondLastIndex = {}, set(), None
         known = self._zeroBondAverages.get(time)
         li = self.getLiborPeriodIndex(time)
         if known is not None or li < 0 or self.measure != self.SPOT:
             return known
+        # a sweep over consecutive tenor dates (a backward induction) is what the batch is for; scattered dates (a portfolio of swaptions
+        # with a handful of exercise dates) keep the reference's route
+        adjacent = self._zeroBondLastIndex is not None and abs(li - self._zeroBondLastIndex) == 1
         self._zeroBondRequests.add(time)
-        if len(self._zeroBondRequests) < 3:
+        self._zeroBondLastIndex = li
+        if len(self._zeroBondRequests) < 3 or not adjacent:
             return None
         li = max(li, max(self.getLiborPeriodIndex(t) for t in self._zeroBondRequests))
         n0 = self._numeraire_unadjusted(process, 0.0)
