@@ -17,6 +17,7 @@ import math
 
 import numpy as np
 
+from . import native as nv
 from .stochastic import Scalar
 
 
@@ -299,8 +300,10 @@ def getCloneCalibrated(covarianceModel, calibrationModel, calibrationProducts, c
         for item in calibrationProducts:
             try:
                 residuals.append(item.getProduct().getValueRV(0.0, simulation).sub(item.getTargetValue()).mult(item.getWeight()))
+            except (nv.NoDeviceError, nv.FmbError, MemoryError):
+                raise                                        # a failing device is not a "non-working product"
             except Exception:
-                residuals.append(None)                       # "automatically exclude non-working calibration products"
+                residuals.append(None)                       # "automatically exclude non-working calibration products" (:395-398)
         for k, r in enumerate(residuals):                    # the averages are read after all products are queued
             values[k] = r.getAverage() if r is not None else 0.0
 

@@ -46,6 +46,8 @@ int fmb_rv_ternary(int op, fmb_handle x, double sx, fmb_handle y, double sy, fmb
 	*o = mk(sz(x ? x : (y ? y : z))); launches++; return 0; }
 int fmb_rv_accrue_chain(int n, const fmb_handle* r, const double* d, double div, fmb_handle* o) { *o = mk(sz(r[0])); launches++; return 0; }
 int fmb_rv_eval_chain(int n, const unsigned char* code, int s, const fmb_handle* l, int nl, const double* sc, int ns, fmb_handle* o) { *o = mk(sz(l[0])); launches++; return 0; }
+int fmb_rv_accrue_prefix(int n, double s0, const fmb_handle* r, const double* d, fmb_handle* o) { for (int k = 0; k < n; k++) o[k] = mk(sz(r[0])); launches++; return 0; }
+int fmb_rv_reduce_many(int op, int n, const fmb_handle* x, double a, double* o) { for (int k = 0; k < n; k++) { o[2 * k] = 0.5 * (double)sz(x[k]); o[2 * k + 1] = 0; } launches++; return 0; }
 int fmb_rv_reduce(int op, fmb_handle x, fmb_handle w, double a, double* o) { o[0] = 0.5 * (double)sz(x); o[1] = 0; launches++; return 0; }
 int fmb_rv_select(fmb_handle x, uint64_t r, double* o) { *o = 0; return 0; }
 int fmb_rv_range_sum(fmb_handle x, double lo, double hi, double* o) { o[0] = o[1] = o[2] = o[3] = 0; return 0; }
@@ -77,6 +79,8 @@ int fmb_regression_conditional_expectation(int K, const fmb_handle* b, const dou
 int fmb_comm_unique_id(unsigned char* id, int len) { memset(id, 0, 128); return 0; }
 int fmb_comm_init(const unsigned char* id, int len, int r, int w) { return 0; }
 int fmb_comm_shutdown(void) { return 0; }
+int fmb_comm_peer_handle(unsigned char* h, int len) { return 6; }
+int fmb_comm_peer_open(const unsigned char* h, int len) { return 6; }
 int fmb_comm_info(int* r, int* w, uint64_t* e) { if (r) *r = 0; if (w) *w = 1; if (e) *e = 0; return 0; }
 int fmb_bench_dfma_tflops(double* t) { *t = 1; return 0; }
 int fmb_bench_copy_gbs(uint64_t b, double* g) { *g = 1; return 0; }
