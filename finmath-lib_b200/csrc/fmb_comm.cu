@@ -192,7 +192,17 @@ int fmb_comm_peer_open(const unsigned char* handles, int len) {
 	Comm& m = c.comm;
 	std::lock_guard<std::mutex> lk(c.scratchMu);
 	if (!m.active || !m.peerBase) { setError("comm_peer_open: call fmb_comm_peer_handle first"); return FMB_EINVAL; }
-	if (!handles || len < m.world * (int)sizeof(cudaIpcMemHandle_t)) { setError("comm_peer_open: %d handles of %d bytes expected", m.world, (int)sizeof(cudaIpcMemHandle_t)); return FMB_EINVAL; }
+	if (!handles) {                                        // NULL: back to the NCCL path (a rank could not map its peers: nobody may use them)
+		if (m.peer) {
+			FMB_CUDA(cudaStreamSynchronize(c.stream));
+			for (int r = 0; r < m.world; r++) if (r != m.rank && m.peerGather[r]) cudaIpcCloseMemHandle(m.peerGather[r]);
+			for (int r = 0; r < 8; r++) m.peerGather[r] = nullptr;
+			m.gatherBuf = m.ncclGatherBuf;
+			m.peer = false;
+		}
+		return FMB_OK;
+	}
+	if (len < m.world * (int)sizeof(cudaIpcMemHandle_t)) { setError("comm_peer_open: %d handles of %d bytes expected", m.world, (int)sizeof(cudaIpcMemHandle_t)); return FMB_EINVAL; }
 	if (m.peer) return FMB_OK;
 	FMB_CUDA(cudaStreamSynchronize(c.stream));
 	for (int r = 0; r < m.world; r++) {

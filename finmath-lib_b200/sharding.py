@@ -138,7 +138,7 @@ class ShardContext:
         dist.all_gather_object(oks, rc == nv.FMB_OK, group=self.group)
         if not all(oks):
             if rc == nv.FMB_OK:
-                raise RuntimeError("finmath_b200: peer exchange could be set up on some ranks only")
+                nv.check(lib.fmb_comm_peer_open(None, 0))    # some other rank could not map its peers: everybody stays on NCCL
             return False
         self.peer_exchange = True
         return True

@@ -244,7 +244,8 @@ int fmb_comm_info(int* rank, int* world, uint64_t* exchanges);
  * partials straight into the gather buffers of all ranks over NVLink (CUDA IPC mappings) from one small kernel and waits for the others'
  * flags - the payloads are tens of bytes, so the latency of the exchange is what counts.  Every rank calls fmb_comm_peer_handle (64
  * bytes out), the host gathers the handles in rank order (any channel) and every rank calls fmb_comm_peer_open at the same point of the
- * call sequence.  FMB_EUNSUPPORTED (no peer access between the devices): the NCCL path simply stays in use. */
+ * call sequence.  FMB_EUNSUPPORTED (no peer access between the devices): the NCCL path simply stays in use; handles == NULL switches
+ * back to it (for the ranks that could map their peers when another rank could not). */
 int fmb_comm_peer_handle(unsigned char* handle, int len);
 int fmb_comm_peer_open(const unsigned char* handles, int len);
 
