@@ -786,6 +786,7 @@ class HullWhiteModel:
         self.dfForward = None if discountFactorsFromForwardCurve is None else np.asarray(discountFactorsFromForwardCurve, dtype=np.float64)
         self._numeraireDiscountFactors, self._dfFromForwardCache, self._forwardRateCache = [], [], []
         self._mrTimeCache = {}
+        self._fusedSpecCache = {}                            # time discretization -> per-step coefficient tables
 
     def getNumberOfComponents(self): return 2
     def getNumberOfFactors(self): return 1                                                        # :287-290 (sic; the driver's count is used)
@@ -894,15 +895,21 @@ class HullWhiteModel:
     def getFusedSpecification(self, process):
         if process.getScheme() in (Scheme.PREDICTOR_CORRECTOR, Scheme.PREDICTOR_CORRECTOR_FUNCTIONAL):
             return None                                       # the corrector is not fused for this model: generic device loop
-        T = process.getTimeDiscretization().getNumberOfTimeSteps()
-        d0, d1, fl = [], [], []
-        for t in range(T):
-            c0, c1 = self._drift_coefficients(process, t)
-            f0, f1 = self.getFactorLoading(process, t, 0, None), self.getFactorLoading(process, t, 1, None)
-            d0.append(c0.doubleValue())
-            d1.append(c1.doubleValue())
-            fl.append([f0[0].doubleValue(), f0[1].doubleValue(), f1[0].doubleValue(), f1[1].doubleValue()])
-        return dict(kernel="hull_white", drift0=d0, drift1=d1, factorLoadings=np.array(fl), initialValues=[0.0, 0.0])
+        td = process.getTimeDiscretization()
+        T = td.getNumberOfTimeSteps()
+        # the per-step coefficients depend on the (immutable) model and the time grid only: a model that is simulated again - another
+        # seed, another path count - does not evaluate its closed forms again (they are ~100 Scalar operations per step on the host)
+        spec = self._fusedSpecCache.get(td)
+        if spec is None:
+            d0, d1, fl = [], [], []
+            for t in range(T):
+                c0, c1 = self._drift_coefficients(process, t)
+                f0, f1 = self.getFactorLoading(process, t, 0, None), self.getFactorLoading(process, t, 1, None)
+                d0.append(c0.doubleValue())
+                d1.append(c1.doubleValue())
+                fl.append([f0[0].doubleValue(), f0[1].doubleValue(), f1[0].doubleValue(), f1[1].doubleValue()])
+            spec = self._fusedSpecCache[td] = dict(kernel="hull_white", drift0=d0, drift1=d1, factorLoadings=np.array(fl), initialValues=[0.0, 0.0])
+        return spec
 
     # ---- term structure functions of the Hull-White model (:305-357, :431-582, :797-950); deterministic parts are Scalars -------------
     def getLiborPeriod(self, i): return self.liborPeriodDiscretization.getTime(i)
