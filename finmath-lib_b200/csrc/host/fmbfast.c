@@ -163,6 +163,7 @@ static fmb_handle vec_handle(PyObject* o) {
 static int lv_materialize(LV* v) {
 	fmb_handle out = 0;
 	int rc;
+	if (!v->start || v->nprog < 1 || !v->prog) { PyErr_SetString(PyExc_ValueError, "finmath_b200: an empty LazyVector (they are created by operations, not directly)"); return -1; }
 	if (v->nprog == 1) {                                   /* one operation: the specialised kernel */
 		const Instr* in = &v->prog[0];
 		fmb_handle hs[3] = {0, 0, 0};
