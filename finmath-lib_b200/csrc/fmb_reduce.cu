@@ -615,6 +615,12 @@ template <int K> __global__ void __launch_bounds__(256) predictKernelV(BasisArgs
 }
 
 static int reduceGrid() { return ctx().smCount * 4; }
+// CTAs of the moments kernel: one per SM - its accumulators leave room for one resident CTA per SM only, so a second wave would just
+// double the partials the last CTA has to merge (FMB_MOMENTS_WAVES=2: the earlier geometry, for A/B runs: 80 vs 70 us per regression at 1 M)
+static int momentsGrid(uint64_t n) {
+	static const int waves = (getenv("FMB_MOMENTS_WAVES") && atoi(getenv("FMB_MOMENTS_WAVES")) == 2) ? 2 : 1;
+	return (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx().smCount * waves, (n + RED_THREADS - 1) / RED_THREADS));
+}
 
 int commAllGather(int count);                      // fmb_comm.cu
 void peerArgsNext(PeerArgs& px);                   // fmb_comm.cu
@@ -655,7 +661,7 @@ static int fillBasis(int K, const fmb_handle* basis, const double* basis_scalar,
 static int enqueueFit(int K, const BasisArgs& b, const double* y, uint64_t nLocal, double nGlobal, const double* cachedFit, double* fit) {
 	Context& c = ctx();
 	const int M = K * (K + 1) / 2 + K;
-	const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * 2, (nLocal + RED_THREADS - 1) / RED_THREADS));
+	const int grid = momentsGrid(nLocal);
 	FMB_TRY(ensureScratch(0, (size_t)(grid * M * 2 + COMM_MAX_DOUBLES) * sizeof(double)));
 	double* dpart = (double*)c.scratch;
 	double* momLocal = c.comm.active ? c.comm.sendBuf : dpart + (size_t)grid * M * 2;
@@ -848,7 +854,7 @@ int fmb_regression_moments(int K, const fmb_handle* basis, const double* basis_s
 	if (n == 0) {
 		for (int i = 0; i < 2 * M; i++) c.hostResult[i] = 0.0;
 	} else {
-		const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)c.smCount * 2, (n + RED_THREADS - 1) / RED_THREADS));
+		const int grid = momentsGrid(n);                        // (the same geometry as the device-resident fit: identical moments, bit for bit)
 		FMB_TRY(ensureScratch(0, (size_t)grid * M * 2 * sizeof(double)));
 		FitArgs f = { 1, 0.0, nullptr, nullptr };
 #define CALL(KV) launchMoments<KV>(0, b, vy->ptr, n, (double*)c.scratch, c.ticket, c.hostResultDev, f, grid, c.stream)
