@@ -43,6 +43,44 @@ __device__ __forceinline__ void warpReduceDd(dd& v) {
 	for (int d = 16; d > 0; d >>= 1) { dd o = ddShflDown(v, d); ddMerge(v, o); }
 }
 
+// Warp reduction of CNT double-doubles per lane with 1/5 of the shuffles of CNT separate trees: in every round a lane hands one half of
+// its values to the partner (lane ^ D) and merges the partner's other half into its own, so the number of values per lane halves while
+// the lanes covered by each double: after five rounds a lane holds the complete sums of at most two values.  ddMerge is commutative and
+// the partners are those of the shuffle tree (16, 8, 4, 2, 1), so every sum is the one warpReduceDd produces, bit for bit.
+template <int CNT, int D> struct DdButterfly {
+	static constexpr int HALF = (CNT + 1) / 2;
+	static __device__ __forceinline__ void run(dd* acc, int lane) {
+		const bool upper = (lane & D) != 0;
+#pragma unroll
+		for (int j = 0; j < HALF; j++) {
+			const dd a = acc[j];
+			dd b = {0.0, 0.0};
+			if (j + HALF < CNT) b = acc[j + HALF];
+			dd keep, send, recv;
+			keep.hi = upper ? b.hi : a.hi; keep.lo = upper ? b.lo : a.lo;
+			send.hi = upper ? a.hi : b.hi; send.lo = upper ? a.lo : b.lo;
+			recv.hi = __shfl_xor_sync(0xffffffffu, send.hi, D);
+			recv.lo = __shfl_xor_sync(0xffffffffu, send.lo, D);
+			ddMerge(keep, recv);
+			acc[j] = keep;
+		}
+		DdButterfly<HALF, D / 2>::run(acc, lane);
+	}
+	// index (among the CNT values the round started with) of the value this lane ends up holding in slot j; ok: it is a real one
+	static __device__ __forceinline__ int origin(int j, int lane, bool& ok) {
+		int pos = DdButterfly<HALF, D / 2>::origin(j, lane, ok);
+		if (lane & D) pos += HALF;
+		ok = ok && pos < CNT;
+		return pos;
+	}
+};
+template <int CNT> struct DdButterfly<CNT, 0> {
+	static constexpr int LEFT = CNT;
+	static __device__ __forceinline__ void run(dd*, int) {}
+	static __device__ __forceinline__ int origin(int j, int, bool& ok) { ok = j < CNT; return j; }
+};
+template <int M> struct DdButterflyLeft { static constexpr int value = (((((M + 1) / 2 + 1) / 2 + 1) / 2 + 1) / 2 + 1) / 2; };
+
 __device__ __forceinline__ double jminD(double a, double b) {
 	if (a != a) return a;
 	if (b != b) return b;
@@ -452,6 +490,25 @@ __device__ inline void jacobiPinvSolveWarp(int K, double* U, double* V, double* 
 }
 #endif
 
+// asynchronous 8-byte global -> shared copies (LDGSTS) of a thread into its own slots
+// (shared-window addresses are computed once by the caller: __cvta_generic_to_shared inside a loop costs an S2UR per copy)
+__device__ __forceinline__ void cpAsync8(unsigned smemDst, const double* gsrc) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smemDst), "l"(gsrc) : "memory");
+}
+// the same, ordered after the value read from that slot has arrived
+__device__ __forceinline__ void cpAsync8After(unsigned smemDst, const double* gsrc, double readBefore) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smemDst), "l"(gsrc), "d"(readBefore) : "memory");
+}
+__device__ __forceinline__ double ldShared(unsigned smemSrc) {
+	double v;
+	asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(smemSrc) : "memory");
+	return v;
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+// stages of the moments kernel's copy ring: as many (2..6) as fit 42 KB of the 48 KB of static shared memory next to the reduction scratch
+#define MOMENTS_STAGES(K) (21 / ((K) + 1) < 2 ? 2 : (21 / ((K) + 1) > 6 ? 6 : 21 / ((K) + 1)))
+
 struct BasisArgs {
 	const double* ptr[8];
 	double scalar[8];
@@ -511,24 +568,47 @@ template <int K, int FINISH> __global__ void __launch_bounds__(RED_THREADS) mome
 	for (int m = 0; m < M; m++) { acc[m].hi = 0.0; acc[m].lo = 0.0; }
 	const uint64_t stride = (uint64_t)gridDim.x * RED_THREADS;
 	uint64_t i = blockIdx.x * (uint64_t)RED_THREADS + threadIdx.x;
-	// the loads of the next element are issued before the ~190 dependent double-double operations of the current one (the kernel runs at one
-	// CTA per SM - 27 double-double accumulators per thread - so memory latency is not hidden by other warps)
-	double nv[K], ny = 0.0;
-	if (i < n) {
+	// The kernel runs at one CTA per SM (27 double-double accumulators per thread for K = 6), so other warps do not hide memory latency, and
+	// a prefetch held in registers cannot go deeper than one element: every thread keeps its next D elements on the way as asynchronous
+	// 8-byte copies into its OWN shared-memory slots (no other thread reads them: the only synchronisation is cp.async.wait_group),
+	// D x (K+1) x 2 KB per CTA.  Against the one-element register prefetch (K = 6): 238 -> 174 registers, 66 -> 64.5 us per regression at
+	// 1 M paths (L2-resident inputs), 304 -> 228 us at 8 M (inputs from HBM).
+	constexpr int D = MOMENTS_STAGES(K);
+	__shared__ double stage[D][K + 1][RED_THREADS];
+	const int tid = threadIdx.x;
+	const unsigned slot0 = (unsigned)__cvta_generic_to_shared(&stage[0][0][tid]);
+	constexpr unsigned ROW = RED_THREADS * sizeof(double), STAGE = (K + 1) * ROW;
 #pragma unroll
-		for (int k = 0; k < K; k++) nv[k] = b.ptr[k] ? b.ptr[k][i] : b.scalar[k];
-		ny = y[i];
+	for (int d = 0; d < D; d++) {
+		const uint64_t idx = i + d * stride;
+#pragma unroll
+		for (int k = 0; k < K; k++) if (!b.ptr[k]) stage[d][k][tid] = b.scalar[k];      // a deterministic basis function: its slots hold the constant
+		if (idx < n) {
+#pragma unroll
+			for (int k = 0; k < K; k++) if (b.ptr[k]) cpAsync8(slot0 + d * STAGE + k * ROW, b.ptr[k] + idx);
+			cpAsync8(slot0 + d * STAGE + K * ROW, y + idx);
+		}
+		cpAsyncCommit();
 	}
+	int s = 0;
 	for (; i < n; i += stride) {
+		cpAsyncWait<D - 1>();                              // the oldest of the D groups in flight: this element
+		const unsigned cur = slot0 + s * STAGE;
 		double v[K];
 #pragma unroll
-		for (int k = 0; k < K; k++) v[k] = nv[k];
-		const double yy = ny;
-		if (i + stride < n) {
+		for (int k = 0; k < K; k++) v[k] = ldShared(cur + k * ROW);
+		const double yy = ldShared(cur + K * ROW);
+		{
+			// refill the slot just read (the values are operands of the asm, so the reads have completed before the copies are issued)
+			const uint64_t idx = i + D * stride;
+			if (idx < n) {
 #pragma unroll
-			for (int k = 0; k < K; k++) nv[k] = b.ptr[k] ? b.ptr[k][i + stride] : b.scalar[k];
-			ny = y[i + stride];
+				for (int k = 0; k < K; k++) if (b.ptr[k]) cpAsync8After(cur + k * ROW, b.ptr[k] + idx, v[k]);
+				cpAsync8After(cur + K * ROW, y + idx, yy);
+			}
+			cpAsyncCommit();
 		}
+		s = (s + 1 == D) ? 0 : s + 1;
 		int m = 0;
 #pragma unroll
 		for (int p = 0; p < K; p++) {
@@ -538,12 +618,15 @@ template <int K, int FINISH> __global__ void __launch_bounds__(RED_THREADS) mome
 #pragma unroll
 		for (int p = 0; p < K; p++) { ddAdd(acc[m], yy * v[p]); m++; }
 	}
+	cpAsyncWait<0>();
 	__shared__ dd sh[RED_THREADS / 32][M];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	DdButterfly<M, 16>::run(acc, lane);
 #pragma unroll
-	for (int m = 0; m < M; m++) {
-		warpReduceDd(acc[m]);
-		if (lane == 0) sh[warp][m] = acc[m];
+	for (int j = 0; j < DdButterflyLeft<M>::value; j++) {
+		bool ok;
+		const int m = DdButterfly<M, 16>::origin(j, lane, ok);
+		if (ok) sh[warp][m] = acc[j];
 	}
 	__syncthreads();
 	if (threadIdx.x < M) {

@@ -2,10 +2,13 @@ import os, sys, time
 import numpy as np
 sys.path.insert(0, "/root/repo")
 import __graft_entry__ as g
-pkg = g.load_package(); nv = pkg.native; nv.init(0)
+pkg = g.load_package(); nv = pkg.native
+if os.environ.get("FMB_AB_LIB"):
+    nv.LIB_PATH = os.environ["FMB_AB_LIB"]          # A/B builds of the library (timing tool only)
+nv.init(0)
 RV = pkg.RandomVariableCuda
 rng = np.random.default_rng(1)
-for n in (2000, 1_000_000):
+for n in ([int(a) for a in sys.argv[1:]] or [2000, 1_000_000]):
     z1, z2, z3 = rng.standard_normal((3, n))
     d = 1 / (1 + 0.05 * np.exp(0.2 * z1 - 0.02) * 0.5)
     D = 1 / (1 + 0.05 * np.exp(0.15 * (0.7 * z1 + 0.7 * z2) - 0.01) * 10)
