@@ -322,6 +322,7 @@ class LIBORMarketModelFromCovarianceModel:
         self._numerairesAdjusted = {}
         self._zeroBondAverages, self._zeroBondRequests, self._zeroBondLastIndex = None, set(), None
         self._initialState = None
+        self._periodLengthSlices = {}
 
     @classmethod
     def of(cls, liborPeriodDiscretization, analyticModel, forwardRates, discountFactors, randomVariableFactory, covarianceModel, calibrationItems=None,
@@ -527,6 +528,9 @@ class LIBORMarketModelFromCovarianceModel:
             return onePlusLongLIBORdt.mult(onePlusInterpolatedLIBORDt).sub(1.0).div(periodEnd - periodStart)
         if ps + 1 == pe:
             return self.getLIBOR(process, ti, ps)
+        fused = self._forward_rate_from_handles(process, ti, ps, pe, periodEnd - periodStart)
+        if fused is not None:
+            return fused
         libors = [self.getLIBOR(process, ti, k) for k in range(ps, pe)]
         subs = [self.getLiborPeriod(k + 1) - self.getLiborPeriod(k) for k in range(ps, pe)]
         fused = _accrue_chain(libors, subs, periodEnd - periodStart)
@@ -536,6 +540,32 @@ class LIBORMarketModelFromCovarianceModel:
         for l, sub in zip(libors, subs):                     # :1288-1302, one pass per period
             acc = l.mult(sub).add(1.0) if acc is None else acc.accrue(l, sub)
         return acc.sub(1.0).div(periodEnd - periodStart)
+
+    def _forward_rate_from_handles(self, process, ti, ps, pe, divisor):
+        """The multi-period forward rate of a fused simulation straight from the native handles of L_ps..L_{pe-1} at time index ti (a
+        contiguous slice of the handle table): the same kernel on the same vectors as _accrue_chain, without wrapping every rate into a
+        RandomVariable first (the Bermudan's basis functions ask for up to 19 rates per call).  None: the caller takes the general way."""
+        import ctypes as C
+        if pe - ps < 3 or ti == 0:
+            return None
+        if getattr(process, "_discreteProcess", None) is None:
+            process.getProcessValue(ti, ps)                  # (runs the simulation)
+        lp = getattr(process, "_discreteProcess", None)
+        handles = getattr(lp, "handles", None)
+        if handles is None:
+            return None
+        N = lp.N
+        hs = handles[ti * N + ps:ti * N + pe]
+        # a deterministic rate (no handle), or every rate frozen before this time index (the result's filtration time is then an earlier one)
+        if not hs.all() or not (hs != handles[(ti - 1) * N + ps:(ti - 1) * N + pe]).any():
+            return None
+        key = (ps, pe)
+        ds = self._periodLengthSlices.get(key)
+        if ds is None:
+            ds = self._periodLengthSlices[key] = np.array([self.getLiborPeriod(k + 1) - self.getLiborPeriod(k) for k in range(ps, pe)], dtype=np.float64)
+        out = C.c_uint64()
+        nv.check(nv.load().fmb_rv_accrue_chain(pe - ps, nv.hptr(hs), nv.dptr(ds), float(divisor), C.byref(out)))
+        return lp.factory.fromDevice(lp.td.getTime(ti), nv.DeviceVector(out.value, lp.P), lp.nPaths)
 
     def _ensure_cache(self, process):
         # :951-961; a weak reference: the process owns device memory and already references this model (no cycle for the GC to find)
@@ -614,14 +644,16 @@ class LIBORMarketModelFromCovarianceModel:
     def getNumeraire(self, process, time):                                             # :859-876
         if time < 0:
             raise NotImplementedError("numeraire for negative times is outside the hot path")
-        n = self._numeraire_unadjusted(process, time)
         if self.discountFactors is not None:
             # The reference re-evaluates the adjustment (three array passes and a getAverage) on every call; the value is a pure function
             # of (process, time), so the immutable result is kept per time: identical numbers, one reduction (and, sharded, one collective)
             # per distinct date instead of one per call.
+            self._ensure_cache(process)
             cached = self._numerairesAdjusted.get(time)
             if cached is not None:
                 return cached
+        n = self._numeraire_unadjusted(process, time)
+        if self.discountFactors is not None:
             dz = self._defaultable_zero_bond_at(process, time)
             nonDefaultableZeroBond = self._zero_bond_averages(process, time)
             if nonDefaultableZeroBond is None:

@@ -34,6 +34,7 @@ class TimeDiscretizationFromArray:
         self.times = np.array(rounded, dtype=np.float64)
         self._list = rounded                                # the same values as Python floats (scalar lookups without numpy overhead)
         self._index = {t: i for i, t in enumerate(rounded)}
+        self._asked = {}
 
     def _round(self, t):
         try:
@@ -54,11 +55,15 @@ class TimeDiscretizationFromArray:
         return self._list[i + 1] - self._list[i]
 
     def getTimeIndex(self, time):                           # Arrays.binarySearch :272-274
-        key = self._round(time)
-        i = self._index.get(key)
-        if i is not None:
-            return i
-        return -(bisect.bisect_left(self._list, key) + 1)
+        i = self._asked.get(time)                           # (products ask for the same few dates over and over)
+        if i is None:
+            key = self._round(time)
+            i = self._index.get(key)
+            if i is None:
+                i = -(bisect.bisect_left(self._list, key) + 1)
+            if len(self._asked) < 4096:
+                self._asked[time] = i
+        return i
 
     def getTimeIndexNearestLessOrEqual(self, time):
         i = self.getTimeIndex(time)

@@ -46,7 +46,8 @@ def main():
 
     valuation()
     l0 = nv.launch_count()
-    best = min(valuation()[:2] for _ in range(args.reps))
+    runs = [valuation()[:2] for _ in range(args.reps)]
+    best = (min(r[0] for r in runs), min(r[1] for r in runs))
     calls = (nv.launch_count() - l0) / args.reps
     print("host only (null ABI): simulate set-up %.2f ms, Bermudan induction %.2f ms, %.0f native launches per valuation" % (1e3 * best[0], 1e3 * best[1], calls))
     if args.profile:
@@ -55,7 +56,7 @@ def main():
         for _ in range(5):
             valuation()
         pr.disable()
-        pstats.Stats(pr).sort_stats("tottime").print_stats(28)
+        pstats.Stats(pr).sort_stats(os.environ.get("FMB_PROFILE_SORT", "tottime")).print_stats(int(os.environ.get("FMB_PROFILE_ROWS", "28")))
 
 
 if __name__ == "__main__":
