@@ -369,3 +369,19 @@ def test_reference_arm_inputs_are_independent_of_and_equal_to_the_products_table
     assert np.array_equal(r["sigma"], s["sigma"])
     assert np.max(np.abs(r["factor_matrix"] - s["factor_matrix"])) < 1e-12
     assert np.array_equal(r["L0"], s["L0"])
+
+
+def test_bermudan_host_logic_over_a_handle_only_stub(tmp_path):
+    """The host mirror of a whole C5 valuation (fused LMM simulation, 20 exercise dates, numeraire batch, regression calls) driven against
+    profiles/tools/null_abi.c - a stand-in for the C ABI that only hands out handles - in a separate process: every call the mirror makes
+    exists in the header with the argument types the binding declares, and the number of native launches per valuation stays at the
+    figure the design documents (255 on the GPU; the stub does not alias frozen rates, a few more here)."""
+    lib = tmp_path / "libnull_abi.so"
+    subprocess.check_call(["gcc", "-O1", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "profiles", "tools", "null_abi.c"),
+                           "-o", str(lib)])
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "tools", "host_profile.py"), "--lib", str(lib), "--reps", "2", "--paths", "5000"],
+                         capture_output=True, text=True, timeout=300, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert out.returncode == 0, out.stderr[-2000:]
+    m = re.search(r"(\d+) native launches per valuation", out.stdout)
+    assert m, out.stdout
+    assert 200 <= int(m.group(1)) <= 270, out.stdout
