@@ -177,8 +177,12 @@ class LIBORVolatilityModelFourParameterExponentialForm:
 
 
 def _exp_like_libm(x):
-    # element by element through math.exp, so that the table equals getVolatility() bit for bit (numpy's vectorised exp may differ by an ulp)
-    return np.vectorize(_jexp, otypes=[np.float64])(x)
+    # through math.exp, so that the table equals getVolatility() bit for bit (numpy's vectorised exp may differ by an ulp); once per
+    # DISTINCT argument: on a regular grid a [T][N] table of times to maturity holds T + N distinct values, not T * N
+    x = np.asarray(x, dtype=np.float64)
+    u, inverse = np.unique(x.ravel(), return_inverse=True)
+    e = np.array([_jexp(v) for v in u.tolist()], dtype=np.float64)
+    return e[inverse].reshape(x.shape)
 
 
 def _factor_matrix(correlation, numberOfFactors):
@@ -323,6 +327,7 @@ class LIBORMarketModelFromCovarianceModel:
         self._zeroBondAverages, self._zeroBondRequests, self._zeroBondLastIndex = None, set(), None
         self._initialState = None
         self._periodLengthSlices = {}
+        self._forwardCurveDiscountFactors = None
 
     @classmethod
     def of(cls, liborPeriodDiscretization, analyticModel, forwardRates, discountFactors, randomVariableFactory, covarianceModel, calibrationItems=None,
@@ -358,9 +363,12 @@ class LIBORMarketModelFromCovarianceModel:
     def getDiscountFactorsFromForwardCurve(self):
         """DiscountCurveFromForwardCurve(forwardRateCurve).getDiscountFactor(T_i) on the tenor grid (:130-142): running product of
         1 / (1 + L_i(0) * (T_{i+1} - T_i)), starting from 1."""
-        df = [1.0]
-        for i in range(self.tenor.getNumberOfTimeSteps()):
-            df.append(df[-1] / (1.0 + float(self.L0[i]) * self.tenor.getTimeStep(i)))
+        df = self._forwardCurveDiscountFactors               # (the curve and the tenor grid are fixed at construction; a swaption asks per period)
+        if df is None:
+            df = [1.0]
+            for i in range(self.tenor.getNumberOfTimeSteps()):
+                df.append(df[-1] / (1.0 + float(self.L0[i]) * self.tenor.getTimeStep(i)))
+            self._forwardCurveDiscountFactors = df
         return df
 
     def getInitialState(self, process):                      # :1080-1093
