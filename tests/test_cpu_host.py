@@ -385,3 +385,31 @@ def test_bermudan_host_logic_over_a_handle_only_stub(tmp_path):
     m = re.search(r"(\d+) native launches per valuation", out.stdout)
     assert m, out.stdout
     assert 200 <= int(m.group(1)) <= 270, out.stdout
+
+
+def test_volatility_table_equals_the_elementwise_definition_bit_for_bit(pkg):
+    """getVolatilityTable evaluates exp once per distinct time to maturity; the table must equal getVolatility(t, j) entry by entry (the
+    fused kernel is fed from the table, the generic loop from the method), and the forward-implied discount factors kept per model must
+    be the running product the discounting adjustment of a swaption expects."""
+    import math
+    td = pkg.TimeDiscretizationFromArray(0.0, 12, 0.25)
+    tenor = pkg.TimeDiscretizationFromArray(0.0, 7, 0.5)
+    vol = pkg.LIBORVolatilityModelFourParameterExponentialForm(td, tenor, 0.21, 0.013, 0.37, 0.11, True)
+    table = vol.getVolatilityTable()
+    assert table.shape == (12, 7)
+    for t in range(12):
+        for j in range(7):
+            v = vol.getVolatility(t, j)
+            v = v.doubleValue() if hasattr(v, "doubleValue") else float(v)
+            assert table[t, j] == v, (t, j, table[t, j], v)
+    corr = pkg.LIBORCorrelationModelExponentialDecay(td, tenor, 2, 0.1, True)
+    cov = pkg.LIBORCovarianceModelFromVolatilityAndCorrelation(td, tenor, vol, corr)
+    L0 = [0.02 + 0.003 * i for i in range(7)]
+    model = pkg.LIBORMarketModelFromCovarianceModel.of(tenor, None, L0, None, None, cov, None, {"measure": "SPOT"})
+    df = model.getDiscountFactorsFromForwardCurve()
+    assert df is model.getDiscountFactorsFromForwardCurve() and len(df) == 8 and df[0] == 1.0
+    expect = 1.0
+    for i in range(7):
+        expect = expect / (1.0 + L0[i] * 0.5)
+        assert df[i + 1] == expect
+    assert math.isclose(df[-1], math.prod(1.0 / (1.0 + l * 0.5) for l in L0), rel_tol=1e-14)
