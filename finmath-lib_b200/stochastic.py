@@ -100,6 +100,12 @@ class RandomVariable:
     def getConditionalExpectation(self, estimator):
         return estimator.getConditionalExpectation(self)
 
+    def appy(self, operator):                                # RandomVariable.java:316-318 (sic): a RandomVariable -> RandomVariable function
+        return operator(self)
+
+    def expm1(self):                                         # RandomVariable.java:502-504
+        return self.exp().sub(1.0)
+
     def getValues(self):                                     # RandomVariable.java:62-64: "this" unless the type wraps inner values (AAD)
         return self
 
@@ -142,6 +148,18 @@ class Scalar(RandomVariable):
 
     def doubleValue(self):
         return self.value
+
+    def getOperator(self):                                   # Scalar.java:88-95: both null
+        return None
+
+    def getRealizationsStream(self):
+        return None
+
+    def getHistogram(self, *args):                           # Scalar.java:168-175: UnsupportedOperationException
+        raise NotImplementedError("getHistogram of a Scalar")
+
+    def apply(self, operator, *arguments):                   # Scalar.java:183-197: the unary form only; the others return null
+        return Scalar(operator(self.value)) if not arguments else None
 
     def getRealizations(self):
         return None                                       # Scalar.java:83-85

@@ -413,3 +413,20 @@ def test_volatility_table_equals_the_elementwise_definition_bit_for_bit(pkg):
         expect = expect / (1.0 + L0[i] * 0.5)
         assert df[i + 1] == expect
     assert math.isclose(df[-1], math.prod(1.0 / (1.0 + l * 0.5) for l in L0), rel_tol=1e-14)
+
+
+def test_randomvariable_mirror_offers_every_method_of_the_reference_interface(pkg):
+    """Every method name of net.finmath.stochastic.RandomVariable (fixture tests/golden/randomvariable_interface.json, written by
+    tests/golden/make_interface_list.py from the reference checkout) exists on the device type, on Scalar and on the AAD type, so code
+    written against the interface does not meet an AttributeError half way through a valuation."""
+    import json
+    names = json.load(open(os.path.join(ROOT, "tests", "golden", "randomvariable_interface.json")))["methods"]
+    assert len(names) >= 50
+    for cls in (pkg.RandomVariableCuda, pkg.Scalar, pkg.RandomVariableDifferentiableAAD):
+        assert [n for n in names if not hasattr(cls, n)] == [], cls
+    s = pkg.Scalar(2.0)
+    assert s.apply(lambda x: x * x).doubleValue() == 4.0 and s.apply(lambda x, y: x + y, pkg.Scalar(1.0)) is None     # Scalar.java:183-197
+    assert s.getOperator() is None and s.getRealizationsStream() is None                                          # Scalar.java:88-95
+    with pytest.raises(NotImplementedError):
+        s.getHistogram([0.0, 1.0])
+    assert s.appy(lambda r: r.add(1.0)).doubleValue() == 3.0                                                      # RandomVariable.java:316
