@@ -44,6 +44,14 @@ class BlackScholesModel:
     def getNumeraire(self, process, time): return self.riskFreeRate.mult(time).exp()
     def getRandomVariableForConstant(self, value): return self.randomVariableFactory.createRandomVariable(value)
 
+    def getReferenceDate(self): return None
+
+    def getCloneWithModifiedData(self, dataModified):        # BlackScholesModel.java:157-166: numbers, defaults = the averages of the current parameters
+        d = dict(dataModified or {})
+        pick = lambda key, current: float(d[key]) if d.get(key) is not None else current.getAverage()
+        return BlackScholesModel(pick("initialValue", self.initialValue), pick("riskFreeRate", self.riskFreeRate), pick("volatility", self.volatility),
+                                 self.randomVariableFactory)
+
     def getFusedSpecification(self, process):
         s0 = self.initialValue.doubleValue()
         return dict(kernel="black_scholes", initialValue=s0, riskFreeRate=self.riskFreeRate.doubleValue(),
@@ -85,6 +93,21 @@ class HestonModel:
     def applyStateSpaceTransformInverse(self, process, timeIndex, componentIndex, rv): return rv.log() if componentIndex == 0 else rv
     def getNumeraire(self, process, time): return self.discountRate.mult(time).exp()
     def getRandomVariableForConstant(self, value): return self.randomVariableFactory.createRandomVariable(value)
+
+    def getReferenceDate(self): return None
+
+    def getCloneWithModifiedData(self, dataModified):        # HestonModel.java:448-465 (parameters are deterministic here: numbers or Scalars)
+        d = dict(dataModified or {})
+        factory = d.get("randomVariableFactory", self.randomVariableFactory)
+
+        def pick(key, current):
+            v = d.get(key)
+            if v is None:
+                return current.doubleValue()
+            return v.doubleValue() if isinstance(v, RandomVariable) else float(v)
+        return HestonModel(pick("initialValue", self.initialValue), pick("riskFreeRate", self.riskFreeRate), pick("volatility", self.volatility),
+                           pick("discountRate", self.discountRate), pick("theta", self.theta), pick("kappa", self.kappa), pick("xi", self.xi),
+                           pick("rho", self.rho), self.scheme, factory)
 
     def getFusedSpecification(self, process):
         T = process.getTimeDiscretization().getNumberOfTimeSteps()
@@ -129,6 +152,18 @@ class MonteCarloAssetModel:
         timeIndex = self.getTimeIndex(time) if isinstance(time, float) else time
         return self.process.getMonteCarloWeights(timeIndex)
 
+    def getReferenceDate(self): return self.model.getReferenceDate()
+
+    def getCloneWithModifiedData(self, dataModified):        # MonteCarloAssetModel.java:116-138
+        d = dict(dataModified or {})
+        newModel = self.model.getCloneWithModifiedData(d)
+        forProcess = dict(d)
+        forProcess.setdefault("model", newModel)
+        return MonteCarloAssetModel(newModel, self.process.getCloneWithModifiedData(forProcess))
+
+    def getCloneWithModifiedSeed(self, seed):                # :146-150
+        raise NotImplementedError("Method not implemented")
+
 
 class MonteCarloBlackScholesModel(MonteCarloAssetModel):
     seed = 3141                                                                                 # MonteCarloBlackScholesModel.java:50
@@ -140,6 +175,23 @@ class MonteCarloBlackScholesModel(MonteCarloAssetModel):
         else:                                                # (initialValue, riskFreeRate, volatility, brownianMotion)
             s0, r, sigma, driver = args
         super().__init__(BlackScholesModel(s0, r, sigma, driver.randomVariableFactory), driver)
+
+    def _fresh_driver(self, seed):
+        old = self.process.getStochasticDriver()
+        return BrownianMotionCuda(self.getTimeDiscretization(), 1, self.getNumberOfPaths(), seed, getattr(old, "randomVariableFactory", None))
+
+    def _with(self, model, driver):
+        clone = MonteCarloBlackScholesModel.__new__(MonteCarloBlackScholesModel)
+        MonteCarloAssetModel.__init__(clone, model, driver)
+        return clone
+
+    def getCloneWithModifiedData(self, dataModified):
+        """MonteCarloBlackScholesModel.java:112-148: a new model from the map, on a NEW Brownian motion with this class's seed (the
+        reference builds a seeded / time-shifted driver first and then does not use it, :146: mirrored as it behaves)."""
+        return self._with(self.model.getCloneWithModifiedData(dataModified), self._fresh_driver(self.seed))
+
+    def getCloneWithModifiedSeed(self, seed):                # :151-155
+        return self._with(self.model, self._fresh_driver(int(seed)))
 
 
 # ---- LIBOR market model ------------------------------------------------------------------------------------------------
@@ -267,6 +319,38 @@ class LIBORCovarianceModelFromVolatilityAndCorrelation:
                 var[t, j] = (vol * vol) * self.correlationModel.getCorrelation(t, j, j)
         return fl, var
 
+    # ---- point-wise accessors of the LIBORCovarianceModel interface (deterministic here: Scalars) -------------------------------------
+    @staticmethod
+    def _is_index(x):
+        return isinstance(x, (int, np.integer)) and not isinstance(x, bool)
+
+    def _time_index(self, time):                             # AbstractLIBORCovarianceModel.java:54-60, :69-76
+        ti = self.td.getTimeIndex(time)
+        return ti if ti >= 0 else -ti - 2
+
+    def getFactorLoading(self, time, component, realizationAtTimeIndex=None):
+        """:47-57 for (timeIndex, componentIndex); AbstractLIBORCovarianceModel.java:45-60 for the overloads taking a time and / or a
+        fixing date (Java picks them by int / double; so does this, by the Python type of the argument)."""
+        if not self._is_index(component):
+            ci = self.tenor.getTimeIndex(component)
+            component = ci if ci >= 0 else -ci - 2
+        timeIndex = time if self._is_index(time) else self._time_index(time)
+        volatility = Scalar(self.volatilityModel.getVolatility(timeIndex, component))
+        return [volatility.mult(self.correlationModel.getFactorLoading(timeIndex, f, component)) for f in range(self.getNumberOfFactors())]
+
+    def getFactorLoadingPseudoInverse(self, timeIndex, component, factor, realizationAtTimeIndex=None):       # :60-77
+        inverse = Scalar(self.volatilityModel.getVolatility(timeIndex, component)).invert().mult(self.correlationModel.getFactorLoading(timeIndex, factor, component))
+        factorWeight = 0.0
+        for c in range(self.tenor.getNumberOfTimeSteps()):
+            e = self.correlationModel.getFactorLoading(timeIndex, factor, c)
+            factorWeight += e * e
+        return inverse.mult(1 / factorWeight)
+
+    def getCovariance(self, time, component1, component2, realizationAtTimeIndex=None):                        # :82-93
+        timeIndex = time if self._is_index(time) else self._time_index(time)
+        v1, v2 = Scalar(self.volatilityModel.getVolatility(timeIndex, component1)), Scalar(self.volatilityModel.getVolatility(timeIndex, component2))
+        return v1.mult(v2).mult(self.correlationModel.getCorrelation(timeIndex, component1, component2))
+
     # ---- parametric interface (LIBORCovarianceModelFromVolatilityAndCorrelation.java:100-160): volatility parameters, then correlation's
     def getParameterAsDouble(self):
         v, c = self.volatilityModel.getParameterAsDouble(), self.correlationModel.getParameterAsDouble()
@@ -328,6 +412,7 @@ class LIBORMarketModelFromCovarianceModel:
         self._initialState = None
         self._periodLengthSlices = {}
         self._forwardCurveDiscountFactors = None
+        self._integratedLIBORCovariance = None
 
     @classmethod
     def of(cls, liborPeriodDiscretization, analyticModel, forwardRates, discountFactors, randomVariableFactory, covarianceModel, calibrationItems=None,
@@ -345,6 +430,57 @@ class LIBORMarketModelFromCovarianceModel:
     def getCloneWithModifiedCovarianceModel(self, covarianceModel):                     # :1420-1426: same curves, factory and properties
         return LIBORMarketModelFromCovarianceModel(self.tenor, self.L0, self.discountFactors, self.randomVariableFactory, covarianceModel,
                                                    self._properties)
+
+    def getCloneWithModifiedData(self, dataModified):
+        """:1653-1696.  Keys: randomVariableFactory, liborPeriodDiscretization, covarianceModel, forwardRateCurve / discountCurve (here the
+        host-side inputs they stand for: forward rates L_j(0) / discount factors on the tenor grid), forwardRateShift (added to the
+        forward rates); swaptionMarketData is refused as in the reference.  The clone keeps measure, state space, interpolation, cap."""
+        d = dict(dataModified or {})
+        if "swaptionMarketData" in d:
+            raise RuntimeError("Swaption market data as input for getCloneWithModifiedData not supported.")
+        forwardRates = np.asarray(d.get("forwardRateCurve", self.L0), dtype=np.float64)
+        if "forwardRateShift" in d:
+            forwardRates = forwardRates + np.asarray(d["forwardRateShift"], dtype=np.float64)
+        properties = dict(self._properties)
+        properties.pop("calibrationParameters", None)
+        return LIBORMarketModelFromCovarianceModel.of(d.get("liborPeriodDiscretization", self.tenor), d.get("analyticModel"), forwardRates,
+                                                      d.get("discountCurve", self.discountFactors), d.get("randomVariableFactory", self.randomVariableFactory),
+                                                      d.get("covarianceModel", self.covarianceModel), None, properties)
+
+    def getReferenceDate(self):                              # :1412-1414: the forward curve's reference date; curves are arrays here
+        return None
+
+    def getForwardDiscountBond(self, process, time, maturity):                          # :947-952
+        if self.discountFactors is None:
+            raise ValueError("getForwardDiscountBond needs a discount curve (the reference dereferences it)")
+        inverseForwardBondAsOfTime = self.getForwardRate(process, time, time, maturity).mult(maturity - time).add(1.0)
+        inverseForwardBondAsOfZero = self.getForwardRate(process, 0.0, time, maturity).mult(maturity - time).add(1.0)
+        forwardDiscountBondAsOfZero = self._defaultable_zero_bond_at(process, maturity).div(self._defaultable_zero_bond_at(process, time))
+        return forwardDiscountBondAsOfZero.mult(inverseForwardBondAsOfZero).div(inverseForwardBondAsOfTime)
+
+    def getIntegratedLIBORCovariance(self, simulationTimeDiscretization):
+        """:1552-1596: [t][i][j] = sum over s <= t of sum_f FL_i,f(s) FL_j,f(s) dt_s for rates not yet fixed at s (zero otherwise), the
+        same products in the same order; computed once per model like the reference's lazy field.  (As there, the lower triangle of the
+        first time index is left at zero: the symmetrisation runs inside the time integration, which starts at index 1.)"""
+        if self._integratedLIBORCovariance is None:
+            td, N = simulationTimeDiscretization, self.tenor.getNumberOfTimeSteps()
+            T = td.getNumberOfTimeSteps()
+            out = np.zeros((T, N, N))
+            upper = np.triu(np.ones((N, N), dtype=bool))
+            for t in range(T):
+                dt = td.getTime(t + 1) - td.getTime(t)
+                fl = np.array([[f.doubleValue() for f in self.covarianceModel.getFactorLoading(td.getTime(t), self.tenor.getTime(c), None)] for c in range(N)])
+                acc = np.zeros((N, N))
+                for f in range(fl.shape[1]):
+                    acc = acc + fl[:, f][:, None] * fl[:, f][None, :] * dt
+                live = np.array([self.getLiborPeriod(c) > td.getTime(t) for c in range(N)])
+                out[t] = np.where(upper & live[:, None], acc, 0.0)
+            for t in range(1, T):
+                summed = out[t - 1] + out[t]
+                out[t] = np.where(upper, summed, 0.0)
+                out[t] = out[t] + np.triu(out[t], 1).T
+            self._integratedLIBORCovariance = out
+        return self._integratedLIBORCovariance
 
     # ---- ProcessModel callbacks -----------------------------------------------------------------------------------------
     def getNumberOfComponents(self): return self.tenor.getNumberOfTimeSteps()
@@ -797,6 +933,20 @@ class LIBORMonteCarloSimulationFromLIBORModel:
     def getCloneWithModifiedSeed(self, seed):
         return LIBORMonteCarloSimulationFromLIBORModel(self.model, self.process.getCloneWithModifiedSeed(seed))
 
+    def getNumberOfFactors(self): return self.process.getNumberOfFactors()              # LIBORMonteCarloSimulationFromLIBORModel.java:67-69
+    def getNumberOfComponents(self): return self.model.getNumberOfComponents()
+    def getReferenceDate(self): return self.model.getReferenceDate()                    # :77-79
+
+    def getLIBORs(self, timeIndex):                                                     # :112-120
+        return [self.getLIBOR(timeIndex, c) for c in range(self.getNumberOfComponents())]
+
+    def getCloneWithModifiedData(self, dataModified, value=None):                       # :174-200 (map, or key and value)
+        d = dict(dataModified) if value is None and not isinstance(dataModified, str) else {dataModified: value}
+        modelClone = self.model.getCloneWithModifiedData(d)
+        if "discountCurve" in d and len(d) == 1:
+            return LIBORMonteCarloSimulationFromLIBORModel(modelClone, self.process)       # the paths do not depend on the discount curve: re-used
+        return LIBORMonteCarloSimulationFromLIBORModel(self.process.getCloneWithModifiedModel(modelClone))
+
 
 # ---- Hull-White ------------------------------------------------------------------------------------------------------------
 class ShortRateVolatilityModelAsGiven:
@@ -822,11 +972,19 @@ class HullWhiteModel:
         self.randomVariableFactory = randomVariableFactory if randomVariableFactory is not None else RandomVariableCudaFactory()
         self.liborPeriodDiscretization = liborPeriodDiscretization
         self.volatilityModel = volatilityModel
+        self._properties = properties
         self.dfDiscount = None if discountFactors is None else np.asarray(discountFactors, dtype=np.float64)
         self.dfForward = None if discountFactorsFromForwardCurve is None else np.asarray(discountFactorsFromForwardCurve, dtype=np.float64)
         self._numeraireDiscountFactors, self._dfFromForwardCache, self._forwardRateCache = [], [], []
         self._mrTimeCache = {}
         self._fusedSpecCache = {}                            # time discretization -> per-step coefficient tables
+
+    def getReferenceDate(self): return None
+
+    def getCloneWithModifiedData(self, dataModified):        # :478-487: randomVariableFactory, volatilityModel
+        d = dict(dataModified or {})
+        return HullWhiteModel(d.get("randomVariableFactory", self.randomVariableFactory), self.liborPeriodDiscretization,
+                              d.get("volatilityModel", self.volatilityModel), self._properties, self.dfDiscount, self.dfForward)
 
     def getNumberOfComponents(self): return 2
     def getNumberOfFactors(self): return 1                                                        # :287-290 (sic; the driver's count is used)

@@ -23,11 +23,20 @@ TIME_TICK_SIZE = 1.0 / (365.0 * 24.0)                       # TimeDiscretization
 
 
 class TimeDiscretizationFromArray:
+    SHORT_PERIOD_AT_START, SHORT_PERIOD_AT_END = 0, 1       # ShortPeriodLocation :44-47
+
     def __init__(self, *args, tickSize=TIME_TICK_SIZE):
         self.tick = tickSize
         if len(args) == 3:                                  # (initial, numberOfTimeSteps, deltaT) :210-217
             initial, n, dt = args
             times = [initial + i * dt for i in range(int(n) + 1)]
+        elif len(args) == 4:                                # (initial, last, deltaT, shortPeriodLocation) :227-249
+            initial, last, dt, where = args
+            count = int(math.ceil((last - initial) / dt)) + 1
+            if where == self.SHORT_PERIOD_AT_END:
+                times = [min(last, initial + i * dt) for i in range(count)]
+            else:
+                times = [max(initial, last - i * dt) for i in range(count)]
         else:
             times = list(args[0])
         rounded = sorted(set(self._round(t) for t in times))      # :57-64 round, distinct, sorted
@@ -69,8 +78,46 @@ class TimeDiscretizationFromArray:
         i = self.getTimeIndex(time)
         return i if i >= 0 else -i - 2
 
+    def getTimeIndexNearestGreaterOrEqual(self, time):     # :286-292 (binary search on the unrounded time, as in the reference)
+        i = bisect.bisect_left(self._list, time)
+        return i                                            # found: its index; not found: the insertion point (-index-1 of a negative result)
+
     def getAsDoubleArray(self):
         return self.times.copy()
+
+    def getAsArrayList(self):                               # :301-307
+        return list(self._list)
+
+    def getFirstTime(self):                                 # TimeDiscretization.java:84-95
+        return self._list[0]
+
+    def getLastTime(self):
+        return self._list[-1]
+
+    def getTickSize(self):                                  # :345-347
+        return self.tick
+
+    def doubleStream(self):                                 # TimeDiscretization.java:118-120 (an iterator stands in for the DoubleStream)
+        return iter(self._list)
+
+    def __iter__(self):                                     # :350-352
+        return iter(self._list)
+
+    def getTimeShiftedTimeDiscretization(self, timeShift):  # :310-318: shifted times rounded with THIS tick size, new grid with the default one
+        return TimeDiscretizationFromArray([self._round(t + timeShift) for t in self._list])
+
+    def filter(self, timesToKeep):                          # :321-323
+        return TimeDiscretizationFromArray([t for t in self._list if timesToKeep(t)], tickSize=self.tick)
+
+    def union(self, that):                                  # :330-334: the finer tick size
+        return TimeDiscretizationFromArray(self._list + list(that.getAsDoubleArray()), tickSize=min(self.tick, that.getTickSize()))
+
+    def intersect(self, that):                              # :337-342: exact matches only, the coarser tick size
+        other = set(float(t) for t in that.getAsDoubleArray())
+        return TimeDiscretizationFromArray([t for t in self._list if t in other], tickSize=max(self.tick, that.getTickSize()))
+
+    def __repr__(self):
+        return "TimeDiscretizationFromArray [timeDiscretizationFromArray=%s, timeTickSize=%r]" % (self._list, self.tick)
 
     def __eq__(self, other):
         return isinstance(other, TimeDiscretizationFromArray) and np.array_equal(self.times, other.times) and self.tick == other.tick
@@ -513,6 +560,17 @@ class EulerSchemeFromProcessModel:
 
     def getCloneWithModifiedSeed(self, seed):
         return EulerSchemeFromProcessModel(self.model, self.stochasticDriver.getCloneWithModifiedSeed(seed), self.scheme, self.forceGeneric)
+
+    def getCloneWithModifiedData(self, dataModified):         # EulerSchemeFromProcessModel.java:370-391: model, seed | stochasticDriver, scheme
+        d = dict(dataModified or {})
+        if "seed" in d and "stochasticDriver" in d:
+            raise ValueError("Simultaneous specification of stochasticDriver and seed.")
+        driver = self.stochasticDriver
+        if "seed" in d:
+            driver = driver.getCloneWithModifiedSeed(int(d["seed"]))
+        elif "stochasticDriver" in d:
+            driver = d["stochasticDriver"]
+        return EulerSchemeFromProcessModel(d.get("model", self.model), driver, d.get("scheme", self.scheme), self.forceGeneric)
 
     # ---- evolution -------------------------------------------------------------------------------------------------
     def _precalculate(self):

@@ -843,5 +843,17 @@ class RandomVariableCudaFactory:
     def fromDevice(self, time, dv, n=None):
         return RandomVariableCuda(time, None, self.shard, _dv=dv, _n=n)
 
+    @staticmethod
+    def getRandomVariableOrDefault(randomVariableFactory, value, defaultValue):    # RandomVariableFactory.java:32-48
+        if value is None:
+            return defaultValue
+        if isinstance(value, RandomVariable):
+            return value
+        if _is_number(value):
+            if randomVariableFactory is None:
+                raise TypeError("Object value of type Number but nor randomVariableFactory given.")          # NullPointerException there
+            return randomVariableFactory.createRandomVariable(float(value))
+        raise ValueError("Object value must be of type Number or RandomVariable.")
+
 
 nv._bind_fast()       # (native.load() may have run before this module existed: give the accelerator the class it instantiates)

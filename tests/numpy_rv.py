@@ -131,6 +131,9 @@ def make(pkg):
                                                                                 z[t, f] * np.sqrt(timeDiscretization.getTimeStep(t)))
                                 for f in range(numberOfFactors)] for t in range(T)]
 
+        def getCloneWithModifiedSeed(self, seed):
+            return NumpyBrownianMotion(self.timeDiscretization, self.numberOfFactors, self.numberOfPaths, seed, self.randomVariableFactory)
+
         def getTimeDiscretization(self): return self.timeDiscretization
         def getNumberOfFactors(self): return self.numberOfFactors
         def getNumberOfPaths(self): return self.numberOfPaths
