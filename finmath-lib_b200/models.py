@@ -227,6 +227,13 @@ class LIBORVolatilityModelFourParameterExponentialForm:
         a, b, c, d = (float(v.doubleValue()) if hasattr(v, "doubleValue") else float(v) for v in parameter[:4])
         return LIBORVolatilityModelFourParameterExponentialForm(self.td, self.tenor, a, b, c, d, True)
 
+    def getCloneWithModifiedData(self, dataModified):        # :212-253: timeDiscretization, liborPeriodDiscretization, isCalibrateable, a, b, c, d
+        m = dict(dataModified or {})
+        num = lambda v: float(v.doubleValue()) if hasattr(v, "doubleValue") else float(v)
+        return LIBORVolatilityModelFourParameterExponentialForm(m.get("timeDiscretization", self.td), m.get("liborPeriodDiscretization", self.tenor),
+                                                                num(m.get("a", self.a)), num(m.get("b", self.b)), num(m.get("c", self.c)), num(m.get("d", self.d)),
+                                                                bool(m.get("isCalibrateable", self.isCalibrateable)))
+
 
 def _exp_like_libm(x):
     # through math.exp, so that the table equals getVolatility() bit for bit (numpy's vectorised exp may differ by an ulp); once per
@@ -289,6 +296,12 @@ class LIBORCorrelationModelExponentialDecay:
         # (the reference's clone drops the flag, :79 — a one-shot quirk that does not matter there because calibration always clones
         # from the ORIGINAL model; kept calibrateable here so that a calibrated model can be calibrated again)
         return LIBORCorrelationModelExponentialDecay(self.td, self.tenor, self.numberOfFactors, a, True)
+
+    def getCloneWithModifiedData(self, dataModified):        # :150-167: timeDiscretization, liborPeriodDiscretization, numberOfFactors, a, isCalibrateable
+        m = dict(dataModified or {})
+        return LIBORCorrelationModelExponentialDecay(m.get("timeDiscretization", self.td), m.get("liborPeriodDiscretization", self.tenor),
+                                                     int(m.get("numberOfFactors", self.numberOfFactors)), float(m.get("a", self.a)),
+                                                     bool(m.get("isCalibrateable", self.isCalibrateable)))
 
 
 class LIBORCovarianceModelFromVolatilityAndCorrelation:
@@ -365,6 +378,17 @@ class LIBORCovarianceModelFromVolatilityAndCorrelation:
         if c is not None:
             corr = corr.getCloneWithModifiedParameter(list(parameters[nv_:nv_ + len(c)]))
         return LIBORCovarianceModelFromVolatilityAndCorrelation(self.td, self.tenor, vol, corr)
+
+    def getCloneWithModifiedData(self, dataModified):        # :180-208
+        m = dict(dataModified or {})
+        vol, corr = self.volatilityModel, self.correlationModel
+        if "timeDiscretization" in m or "liborPeriodDiscretization" in m or "randomVariableFactory" in m:
+            if "volatilityModel" not in m:
+                vol = vol.getCloneWithModifiedData(m)
+            if "correlationModel" not in m:
+                corr = corr.getCloneWithModifiedData(m)
+        return LIBORCovarianceModelFromVolatilityAndCorrelation(m.get("timeDiscretization", self.td), m.get("liborPeriodDiscretization", self.tenor),
+                                                                m.get("volatilityModel", vol), m.get("correlationModel", corr))
 
     def getCloneCalibrated(self, calibrationModel, calibrationProducts, calibrationParameters=None):
         """AbstractLIBORCovarianceModelParametric.java:134-157 -> calibration.getCloneCalibrated."""

@@ -149,3 +149,22 @@ def test_factory_value_or_default(pkg):
         F.getRandomVariableOrDefault(None, 3.0, None)
     with pytest.raises(ValueError):
         F.getRandomVariableOrDefault(F(), "3", None)
+
+
+def test_covariance_model_clone_with_modified_data(pkg):
+    """LIBORCovarianceModelFromVolatilityAndCorrelation.java:180-208, LIBORVolatilityModelFourParameterExponentialForm.java:212-253,
+    LIBORCorrelationModelExponentialDecay.java:150-167: a changed grid is handed down to the parts unless a part is given explicitly."""
+    s = lmm_setup(pkg, n_libors=8, n_factors=2)
+    cov = s["cov"]
+    finer = pkg.TimeDiscretizationFromArray(0.0, 16, 0.25)
+    c = cov.getCloneWithModifiedData({"timeDiscretization": finer})
+    assert c.getTimeDiscretization() is finer and c.getVolatilityModel().getTimeDiscretization() is finer and c.getCorrelationModel().getTimeDiscretization() is finer
+    assert c.getLiborPeriodDiscretization() is cov.getLiborPeriodDiscretization()
+    assert c.getFactorLoadingTable()[0].shape == (16, 8, 2)
+    assert np.array_equal(c.getFactorLoadingTable()[0][::2], cov.getFactorLoadingTable()[0])        # the same function of (t, T_j) on the common times
+    v = cov.getVolatilityModel().getCloneWithModifiedData({"a": 0.5, "d": pkg.Scalar(0.1), "isCalibrateable": True})
+    assert (v.a, v.b, v.c, v.d, v.isCalibrateable) == (0.5, cov.getVolatilityModel().b, cov.getVolatilityModel().c, 0.1, True)
+    k = cov.getCorrelationModel().getCloneWithModifiedData({"numberOfFactors": 3, "a": 0.2})
+    assert k.getNumberOfFactors() == 3 and k.a == 0.2
+    given = cov.getCloneWithModifiedData({"volatilityModel": v})
+    assert given.getVolatilityModel() is v and given.getCorrelationModel() is cov.getCorrelationModel()
