@@ -95,6 +95,14 @@ class HestonModel:
     def getRandomVariableForConstant(self, value): return self.randomVariableFactory.createRandomVariable(value)
 
     def getReferenceDate(self): return None
+    def getInitialValue(self): return self.initialValue      # HestonModel.java:474-530
+    def getRiskFreeRate(self): return self.riskFreeRate
+    def getVolatility(self): return self.volatility
+    def getTheta(self): return self.theta
+    def getKappa(self): return self.kappa
+    def getXi(self): return self.xi
+    def getRho(self): return self.rho
+    def getScheme(self): return self.scheme
 
     def getCloneWithModifiedData(self, dataModified):        # HestonModel.java:448-465 (parameters are deterministic here: numbers or Scalars)
         d = dict(dataModified or {})
@@ -227,6 +235,13 @@ class LIBORVolatilityModelFourParameterExponentialForm:
         a, b, c, d = (float(v.doubleValue()) if hasattr(v, "doubleValue") else float(v) for v in parameter[:4])
         return LIBORVolatilityModelFourParameterExponentialForm(self.td, self.tenor, a, b, c, d, True)
 
+    def getParameter(self):                                  # :134-150: the parameters as (deterministic) RandomVariables, null unless calibrateable
+        p = self.getParameterAsDouble()
+        return None if p is None else [Scalar(v) for v in p]
+
+    def clone(self):
+        return self.getCloneWithModifiedData(None)
+
     def getCloneWithModifiedData(self, dataModified):        # :212-253: timeDiscretization, liborPeriodDiscretization, isCalibrateable, a, b, c, d
         m = dict(dataModified or {})
         num = lambda v: float(v.doubleValue()) if hasattr(v, "doubleValue") else float(v)
@@ -296,6 +311,13 @@ class LIBORCorrelationModelExponentialDecay:
         # (the reference's clone drops the flag, :79 — a one-shot quirk that does not matter there because calibration always clones
         # from the ORIGINAL model; kept calibrateable here so that a calibrated model can be calibrated again)
         return LIBORCorrelationModelExponentialDecay(self.td, self.tenor, self.numberOfFactors, a, True)
+
+    def getParameter(self):                                  # :137-147
+        p = self.getParameterAsDouble()
+        return None if p is None else [Scalar(v) for v in p]
+
+    def clone(self):
+        return self.getCloneWithModifiedData(None)
 
     def getCloneWithModifiedData(self, dataModified):        # :150-167: timeDiscretization, liborPeriodDiscretization, numberOfFactors, a, isCalibrateable
         m = dict(dataModified or {})
@@ -378,6 +400,12 @@ class LIBORCovarianceModelFromVolatilityAndCorrelation:
         if c is not None:
             corr = corr.getCloneWithModifiedParameter(list(parameters[nv_:nv_ + len(c)]))
         return LIBORCovarianceModelFromVolatilityAndCorrelation(self.td, self.tenor, vol, corr)
+
+    def getParameter(self):                                  # :95-115: the volatility model's parameters, then the correlation model's
+        return [Scalar(v) for v in self.getParameterAsDouble()]
+
+    def clone(self):
+        return self.getCloneWithModifiedData(None)
 
     def getCloneWithModifiedData(self, dataModified):        # :180-208
         m = dict(dataModified or {})
@@ -473,6 +501,20 @@ class LIBORMarketModelFromCovarianceModel:
 
     def getReferenceDate(self):                              # :1412-1414: the forward curve's reference date; curves are arrays here
         return None
+
+    def getMeasure(self): return self.measure                # :1530-1550
+    def getInterpolationMethod(self): return self.interpolationMethod
+    def getSwaptionMarketData(self): return None
+    def clone(self): return self.getCloneWithModifiedData(None)
+
+    def getNumeraireAdjustments(self):
+        """:1504-1506: tenor time -> forward rate of the discount curve over the period starting there (the numeraire adjustment's
+        building blocks); empty until a numeraire has been asked for, like the reference's lazily filled map."""
+        if self.discountFactors is None or not self._numeraireDiscountFactors:
+            return {}
+        c = self.randomVariableFactory.createRandomVariable
+        return {self.tenor.getTime(i): c((float(self.discountFactors[i]) / float(self.discountFactors[i + 1]) - 1.0) / self.tenor.getTimeStep(i))
+                for i in range(self.tenor.getNumberOfTimeSteps())}
 
     def getForwardDiscountBond(self, process, time, maturity):                          # :947-952
         if self.discountFactors is None:
@@ -1009,6 +1051,22 @@ class HullWhiteModel:
         d = dict(dataModified or {})
         return HullWhiteModel(d.get("randomVariableFactory", self.randomVariableFactory), self.liborPeriodDiscretization,
                               d.get("volatilityModel", self.volatilityModel), self._properties, self.dfDiscount, self.dfForward)
+
+    def getVolatilityModel(self): return self.volatilityModel                                      # :805-812
+
+    def getCloneWithModifiedVolatilityModel(self, volatilityModel):                                # :801-804
+        return self.getCloneWithModifiedData({"volatilityModel": volatilityModel})
+
+    def getForwardDiscountBond(self, process, time, maturity):                                     # :360-365
+        if self.dfDiscount is None:
+            raise ValueError("getForwardDiscountBond needs a discount curve (the reference dereferences it)")
+        inverseForwardBondAsOfTime = self.getForwardRate(process, time, time, maturity).mult(maturity - time).add(1.0)
+        inverseForwardBondAsOfZero = self.getForwardRate(process, 0.0, time, maturity).mult(maturity - time).add(1.0)
+        forwardDiscountBondAsOfZero = self._curve_interpolated(maturity, self._discount_factor_at).div(self._curve_interpolated(time, self._discount_factor_at))
+        return forwardDiscountBondAsOfZero.mult(inverseForwardBondAsOfZero).div(inverseForwardBondAsOfTime)
+
+    def getIntegratedBondSquaredVolatility(self, time, maturity):                                  # :797-799
+        return self.getShortRateConditionalVariance(0, time).mult(self.getB(time, maturity).squared())
 
     def getNumberOfComponents(self): return 2
     def getNumberOfFactors(self): return 1                                                        # :287-290 (sic; the driver's count is used)

@@ -660,6 +660,16 @@ class EulerSchemeFromProcessModel:
         self._discreteProcess = proc
 
 
+class RegressionBasisFunctionsGiven:
+    """MonteCarloConditionalExpectationRegression.java:45-60 (RegressionBasisFunctions: a supplier of basis functions)."""
+
+    def __init__(self, basisFunctions):
+        self.basisFunctions = list(basisFunctions)
+
+    def getBasisFunctions(self):
+        return self.basisFunctions
+
+
 class MonteCarloConditionalExpectationRegression:
     """Least-squares conditional expectation.  XtX and Xty are accumulated in ONE fused pass instead of K(K+1)/2 + K multiply-and-reduce
     passes.  Default path (single GPU, or shards with the library's own communicator): everything stays on the device —
@@ -776,6 +786,12 @@ class MonteCarloConditionalExpectationRegression:
         self._lastConditionNumber = cond.value
         self._lastParameters = x
         return x
+
+    def getBasisFunctionsEstimator(self):                     # MonteCarloConditionalExpectationRegression.java:152-158
+        return RegressionBasisFunctionsGiven(self.basisFunctionsEstimator)
+
+    def getBasisFunctionsPredictor(self):
+        return RegressionBasisFunctionsGiven(self.basisFunctionsPredictor)
 
     def getConditionalExpectation(self, randomVariable):      # :97-110
         shard = randomVariable.shard if isinstance(randomVariable, RandomVariableCuda) else LOCAL

@@ -19,10 +19,35 @@ class AbstractMonteCarloProduct:
             return self.getValueRV(0.0, args[0]).getAverage()
         return self.getValueRV(*args)
 
+    def getValues(self, *args):                              # :87-104, :132-135: {"value": average, "error": standard error}
+        evaluationTime, model = (0.0, args[0]) if len(args) == 1 else args
+        values = self.getValueRV(evaluationTime, model)
+        if values is None:
+            return None
+        return {"value": values.getAverage(), "error": values.getStandardError()}
+
+    def getValuesForModifiedData(self, *args):
+        """:110-156: (evaluationTime, model, map) | (evaluationTime, model, key, value) | (model, map) | (model, key, value): the values on
+        model.getCloneWithModifiedData(...) — a bump-and-revalue on the same random numbers."""
+        if not isinstance(args[0], (int, float)):
+            args = (0.0,) + args
+        evaluationTime, model = args[0], args[1]
+        dataModified = args[2] if len(args) == 3 else {args[2]: args[3]}
+        return self.getValues(evaluationTime, model.getCloneWithModifiedData(dataModified))
+
+    def getCurrency(self):                                   # :159-161 (no currency given)
+        return None
+
 
 class EuropeanOption(AbstractMonteCarloProduct):
     def __init__(self, maturity, strike, callOrPutSign=1.0, underlyingIndex=0):
         self.maturity, self.strike, self.sign, self.underlyingIndex = maturity, strike, float(callOrPutSign), underlyingIndex
+
+    def getMaturity(self): return self.maturity              # EuropeanOption.java:195-240
+    def getStrike(self): return self.strike
+    def getCallOrPut(self): return self.sign
+    def getUnderlyingIndex(self): return self.underlyingIndex
+    def getNameOfUnderliyng(self): return None               # (sic; assets are addressed by index here)
 
     def getValueRV(self, evaluationTime, model):
         underlyingAtMaturity = model.getAssetValue(float(self.maturity), self.underlyingIndex)
@@ -73,6 +98,16 @@ class Swaption(AbstractMonteCarloProduct):
         self.exerciseDate, self.fixingDates, self.paymentDates, self.swaprates = exerciseDate, list(fixingDates), list(paymentDates), list(swaprates)
         self.notional, self.periodLengths = notional, periodLengths
 
+    def getExerciseDate(self): return self.exerciseDate      # Swaption.java:241-275
+    def getFixingDates(self): return self.fixingDates
+    def getPaymentDates(self): return self.paymentDates
+    def getPeriodLengths(self): return self.periodLengths
+    def getSwaprates(self): return self.swaprates
+    def getNotional(self): return self.notional
+
+    def getExerciseIndicator(self, model):                   # :241-243: 1 where the swaption is exercised (value at the exercise date > 0)
+        return self.getValueRV(self.exerciseDate, model).mult(-1.0).choose(Scalar(0.0), Scalar(1.0))
+
     def getValueRV(self, evaluationTime, model):
         value = model.getRandomVariableForConstant(0.0)
         for period in range(len(self.fixingDates) - 1, -1, -1):
@@ -115,6 +150,15 @@ class BermudanSwaption(AbstractMonteCarloProduct):
         self.paymentDates, self.periodNotionals, self.swaprates = list(paymentDates), list(periodNotionals), list(swaprates)
         self.isCallable, self.regressionBasisFunctionsProvider = isCallable, regressionBasisFunctionsProvider
         self.lastRegressions = []
+
+    def getFixingDates(self): return self.fixingDates        # BermudanSwaption.java:254-311
+    def getPeriodLengths(self): return self.periodLengths
+    def getPaymentDates(self): return self.paymentDates
+    def getPeriodNotionals(self): return self.periodNotionals
+    def getSwapRates(self): return self.swaprates
+    def getIsCallable(self): return self.isCallable
+    def getFinalMaturity(self): return self.paymentDates[-1]
+    def getExerciseTimes(self): return [t for t, e in zip(self.fixingDates, self.isExercise) if e]
 
     def getValues(self, evaluationTime, model):
         self.lastRegressions = []
@@ -193,6 +237,11 @@ class BermudanOption(AbstractMonteCarloProduct):
         self.numberOfBasisFunctions, self.intrinsicValueAsBasisFunction, self.useBinning = numberOfBasisFunctions, intrinsicValueAsBasisFunction, useBinning
         self.lastValuationExerciseTime = None
         self.lastRegressions = []
+
+    def getExerciseDates(self): return self.exerciseDates    # BermudanOption.java:332-360
+    def getNotionals(self): return self.notionals
+    def getStrikes(self): return self.strikes
+    def getLastValuationExerciseTime(self): return self.lastValuationExerciseTime
 
     def getValueRV(self, evaluationTime, model):
         self.lastRegressions = []

@@ -168,3 +168,66 @@ def test_covariance_model_clone_with_modified_data(pkg):
     assert k.getNumberOfFactors() == 3 and k.a == 0.2
     given = cov.getCloneWithModifiedData({"volatilityModel": v})
     assert given.getVolatilityModel() is v and given.getCorrelationModel() is cov.getCorrelationModel()
+
+
+def test_product_accessors_and_bump_and_revalue(pkg):
+    """AbstractMonteCarloProduct.java:87-161 (getValues / getValuesForModifiedData) and the getters of the products on the path."""
+    _, Factory, BM = numpy_rv.make(pkg)
+    td = pkg.TimeDiscretizationFromArray(0.0, 10, 0.1)
+    sim = pkg.MonteCarloAssetModel(pkg.BlackScholesModel(1.0, 0.05, 0.2, Factory()), BM(td, 1, 20000, 3141))
+    option = pkg.EuropeanOption(1.0, 1.05)
+    assert (option.getMaturity(), option.getStrike(), option.getCallOrPut(), option.getUnderlyingIndex(), option.getCurrency()) == (1.0, 1.05, 1.0, 0, None)
+    v = option.getValues(sim)
+    assert v["value"] == option.getValue(sim) and v["error"] == option.getValue(0.0, sim).getStandardError() and 0 < v["error"] < 0.01
+    up = option.getValuesForModifiedData(sim, "initialValue", 1.01)
+    same = option.getValuesForModifiedData(0.0, sim, {"initialValue": 1.01})
+    assert up == same
+    delta = (up["value"] - v["value"]) / 0.01
+    assert 0.4 < delta < 0.8                                  # Black-Scholes delta of this slightly out-of-the-money call is about 0.58
+    s = lmm_setup(pkg, n_libors=8, n_factors=2)
+    lmm = _numpy_lmm(pkg, s, paths=2000)
+    swaption = pkg.Swaption(1.0, [1.0, 1.5, 2.0], [1.5, 2.0, 2.5], [0.05] * 3)
+    assert (swaption.getExerciseDate(), swaption.getFixingDates(), swaption.getPaymentDates(), swaption.getSwaprates(), swaption.getNotional()) == \
+        (1.0, [1.0, 1.5, 2.0], [1.5, 2.0, 2.5], [0.05] * 3, 1.0)
+    indicator = np.asarray(swaption.getExerciseIndicator(lmm).getRealizations())
+    value = np.asarray(swaption.getValue(1.0, lmm).getRealizations())
+    assert set(np.unique(indicator)) <= {0.0, 1.0} and np.array_equal(indicator == 1.0, value > 0)
+    bermudan = pkg.BermudanSwaption([True, False, True], [1.0, 1.5, 2.0], [0.5] * 3, [1.5, 2.0, 2.5], [1.0] * 3, [0.05] * 3)
+    assert bermudan.getExerciseTimes() == [1.0, 2.0] and bermudan.getFinalMaturity() == 2.5 and bermudan.getIsCallable() is True
+    assert bermudan.getSwapRates() == [0.05] * 3 and bermudan.getPeriodNotionals() == [1.0] * 3
+    assert _numpy_lmm(pkg, s).getModel().getNumeraireAdjustments() == {}        # nothing evaluated yet
+    model = lmm.getModel()
+    lmm.getNumeraire(1.0)
+    adjustments = model.getNumeraireAdjustments()
+    assert sorted(adjustments) == [0.5 * i for i in range(8)]
+    assert adjustments[0.5].doubleValue() == (s["df"][1] / s["df"][2] - 1.0) / 0.5
+    assert model.clone().covarianceModel is model.covarianceModel and model.getMeasure() == model.SPOT
+    heston = pkg.HestonModel(1.0, 0.05, 0.2, 0.05, 0.04, 1.0, 0.3, -0.5, pkg.HestonModel.REFLECTION, Factory())
+    assert [g().doubleValue() for g in (heston.getInitialValue, heston.getRiskFreeRate, heston.getVolatility, heston.getTheta, heston.getKappa, heston.getXi, heston.getRho)] == \
+        [1.0, 0.05, 0.2, 0.04, 1.0, 0.3, -0.5] and heston.getScheme() == pkg.HestonModel.REFLECTION
+
+
+def test_hull_white_and_parametric_accessors(pkg):
+    """HullWhiteModel.java:360-365, :797-812; getParameter / clone of the parametric covariance parts; the regression's basis-function suppliers."""
+    tenor = pkg.TimeDiscretizationFromArray(0.0, 10, 0.5)
+    voltd = pkg.TimeDiscretizationFromArray([0.0, 2.0])
+    vm = pkg.ShortRateVolatilityModelAsGiven(voltd, [0.01, 0.012], [0.1, 0.1])
+    df = [np.exp(-0.03 * 0.5 * i) for i in range(11)]
+    dff = [np.exp(-0.04 * 0.5 * i) for i in range(11)]
+    hw = pkg.HullWhiteModel(None, tenor, vm, None, df, dff)
+    assert hw.getVolatilityModel() is vm
+    vm2 = pkg.ShortRateVolatilityModelAsGiven(voltd, [0.02, 0.02], [0.1, 0.1])
+    clone = hw.getCloneWithModifiedVolatilityModel(vm2)
+    assert clone.getVolatilityModel() is vm2 and clone.getLiborPeriodDiscretization() is tenor and np.array_equal(clone.dfDiscount, hw.dfDiscount)
+    v = hw.getIntegratedBondSquaredVolatility(1.0, 3.0).doubleValue()
+    assert v == hw.getShortRateConditionalVariance(0, 1.0).mult(hw.getB(1.0, 3.0).squared()).doubleValue() and v > 0
+    s = lmm_setup(pkg, n_libors=8, n_factors=2)
+    cov = s["cov"]
+    vol, corr = cov.getVolatilityModel(), cov.getCorrelationModel()
+    assert [x.doubleValue() for x in cov.getParameter()] == cov.getParameterAsDouble()
+    assert (vol.getParameter() is None) == (vol.getParameterAsDouble() is None) and (corr.getParameter() is None) == (corr.getParameterAsDouble() is None)
+    c = cov.clone()
+    assert c is not cov and np.array_equal(c.getFactorLoadingTable()[0], cov.getFactorLoadingTable()[0])
+    one, x = pkg.Scalar(1.0), pkg.Scalar(2.0)
+    est = pkg.MonteCarloConditionalExpectationRegression([one, x])
+    assert est.getBasisFunctionsEstimator().getBasisFunctions() == [one, x] and est.getBasisFunctionsPredictor().getBasisFunctions() == [one, x]
