@@ -507,6 +507,23 @@ class LIBORMarketModelFromCovarianceModel:
     def getSwaptionMarketData(self): return None
     def clone(self): return self.getCloneWithModifiedData(None)
 
+    def getModelParameters(self):
+        """:1699-1733: name -> RandomVariable for the initial forward rates (as the process cached by the numeraire sees them at time 0),
+        the covariance model's parameters and the numeraire adjustments: with a differentiable factory the keys under which a gradient
+        is read.  (Times are formatted by Python's repr, which agrees with Java's Double.toString for the usual grid values.)"""
+        process = self._numerairesProcess() if self._numerairesProcess is not None else None
+        parameters = {}
+        for i in range(self.tenor.getNumberOfTimeSteps()):
+            forward = self.getLIBOR(process, 0, i) if process is not None else None
+            parameters["FORWARD(%r,%r)" % (self.getLiborPeriod(i), self.getLiborPeriod(i + 1))] = forward
+        getParameter = getattr(self.covarianceModel, "getParameter", None)
+        if getParameter is not None:
+            for i, p in enumerate(getParameter() or []):
+                parameters["COVARIANCEMODELPARAMETER(%d)" % i] = p
+        for t, adjustment in self.getNumeraireAdjustments().items():
+            parameters["NUMERAIREADJUSTMENT(%r)" % t] = adjustment
+        return dict(sorted(parameters.items()))             # a TreeMap there
+
     def getNumeraireAdjustments(self):
         """:1504-1506: tenor time -> forward rate of the discount curve over the period starting there (the numeraire adjustment's
         building blocks); empty until a numeraire has been asked for, like the reference's lazily filled map."""
@@ -1002,6 +1019,8 @@ class LIBORMonteCarloSimulationFromLIBORModel:
     def getNumberOfFactors(self): return self.process.getNumberOfFactors()              # LIBORMonteCarloSimulationFromLIBORModel.java:67-69
     def getNumberOfComponents(self): return self.model.getNumberOfComponents()
     def getReferenceDate(self): return self.model.getReferenceDate()                    # :77-79
+
+    def getModelParameters(self): return self.model.getModelParameters()                # :202-205
 
     def getLIBORs(self, timeIndex):                                                     # :112-120
         return [self.getLIBOR(timeIndex, c) for c in range(self.getNumberOfComponents())]

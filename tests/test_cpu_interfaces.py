@@ -231,3 +231,18 @@ def test_hull_white_and_parametric_accessors(pkg):
     one, x = pkg.Scalar(1.0), pkg.Scalar(2.0)
     est = pkg.MonteCarloConditionalExpectationRegression([one, x])
     assert est.getBasisFunctionsEstimator().getBasisFunctions() == [one, x] and est.getBasisFunctionsPredictor().getBasisFunctions() == [one, x]
+
+
+def test_lmm_model_parameters(pkg):
+    """LIBORMarketModelFromCovarianceModel.java:1699-1733."""
+    s = lmm_setup(pkg, n_libors=4, n_factors=2)
+    lmm = _numpy_lmm(pkg, s)
+    before = lmm.getModelParameters()
+    assert before["FORWARD(0.0,0.5)"] is None and not any(k.startswith("NUMERAIREADJUSTMENT") for k in before)      # no process seen yet
+    lmm.getNumeraire(1.0)
+    p = lmm.getModelParameters()
+    assert list(p) == sorted(p)
+    assert [k for k in p if k.startswith("FORWARD")] == ["FORWARD(0.0,0.5)", "FORWARD(0.5,1.0)", "FORWARD(1.0,1.5)", "FORWARD(1.5,2.0)"]
+    assert p["FORWARD(1.0,1.5)"].doubleValue() == pytest.approx(s["L0"][2], rel=1e-15)
+    assert p["NUMERAIREADJUSTMENT(0.5)"].doubleValue() == (s["df"][1] / s["df"][2] - 1.0) / 0.5
+    assert ("COVARIANCEMODELPARAMETER(0)" in p) == bool(s["cov"].getParameterAsDouble())
