@@ -430,3 +430,20 @@ def test_randomvariable_mirror_offers_every_method_of_the_reference_interface(pk
     with pytest.raises(NotImplementedError):
         s.getHistogram([0.0, 1.0])
     assert s.appy(lambda r: r.add(1.0)).doubleValue() == 3.0                                                      # RandomVariable.java:316
+
+
+def test_reference_arm_of_the_bench_prints_the_contract_line():
+    """`bench.py --impl reference` needs no GPU (it times the CPU restatement on the host cores): one JSON line with the keys the driver
+    reads, the same metric / unit as the product arm, zero copy bytes, and only the oracle's library loaded."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "LMM forward-rate path-steps/sec" and line["unit"] == "path-steps/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1 and line["value"] > 0 and line["dtype"] == "f64"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]
